@@ -1,0 +1,141 @@
+"""Deterministic synthetic inputs for the HTD RoI-head path.
+
+Everything is generated on the CPU with explicitly seeded ``torch.Generator`` objects so the
+authoring container (which produces ``tests/golden``) and the GPU box (same image, same torch
+build) see bit-identical tensors.  Used by ``bench.py``, the tests and ``oracle/gen_golden.py``.
+
+Pyramid shapes for an 800x1333 image padded to 800x1344 are the reference's own test shapes
+(``tests/test_models/test_roi_extractor.py:31-36``) plus P6 = stride-2 max-pool of P5
+(``mmdet/models/necks/fpn.py:199``).
+"""
+import math
+import zlib
+
+import torch
+
+STRIDES = (4, 8, 16, 32, 64)
+
+
+def pyramid_shapes(img_h=800, img_w=1333, pad=32):
+    """Feature-map (H, W) of P2..P6 for an image padded to a multiple of ``pad``."""
+    ph = int(math.ceil(img_h / pad) * pad)
+    pw = int(math.ceil(img_w / pad) * pad)
+    shapes = [(ph // s, pw // s) for s in STRIDES[:4]]
+    h5, w5 = shapes[-1]
+    shapes.append(((h5 + 1) // 2, (w5 + 1) // 2))  # max_pool2d(1, stride=2)
+    return shapes
+
+
+def make_pyramid(num_imgs, img_h=800, img_w=1333, channels=256, seed=1000, dtype=torch.float32):
+    """List of 5 NCHW tensors; image ``i`` is drawn from seed ``seed + i`` (N(0,1))."""
+    shapes = pyramid_shapes(img_h, img_w)
+    levels = []
+    for li, (h, w) in enumerate(shapes):
+        per_img = []
+        for i in range(num_imgs):
+            g = torch.Generator().manual_seed(seed + i + 7919 * li)
+            per_img.append(torch.randn(1, channels, h, w, generator=g, dtype=torch.float32))
+        levels.append(torch.cat(per_img, 0).to(dtype))
+    return levels
+
+
+def make_proposals(num_imgs, num_rois=512, img_h=800, img_w=1333, seed=1234,
+                   min_scale=16.0, max_scale=800.0):
+    """Per-image [num_rois, 4] boxes: scale ~ logU(min,max), aspect ~ logU(.5, 2), centre
+    uniform over the image, corners clipped to the image."""
+    out = []
+    for i in range(num_imgs):
+        g = torch.Generator().manual_seed(seed + i)
+        u = torch.rand(num_rois, 4, generator=g, dtype=torch.float64)
+        s = torch.exp(math.log(min_scale) + u[:, 0] * (math.log(max_scale) - math.log(min_scale)))
+        r = torch.exp(math.log(0.5) + u[:, 1] * (math.log(2.0) - math.log(0.5)))
+        w = s * torch.sqrt(r)
+        h = s / torch.sqrt(r)
+        cx = u[:, 2] * img_w
+        cy = u[:, 3] * img_h
+        x1 = (cx - w / 2).clamp(0, img_w)
+        x2 = (cx + w / 2).clamp(0, img_w)
+        y1 = (cy - h / 2).clamp(0, img_h)
+        y2 = (cy + h / 2).clamp(0, img_h)
+        out.append(torch.stack([x1, y1, x2, y2], 1).float())
+    return out
+
+
+def make_gt(num_imgs, proposals, num_pos=128, num_classes=80, seed=4321):
+    """Synthetic sampling outcome: the first ``num_pos`` proposals of every image are the
+    positives (``SamplingResult.bboxes`` puts positives first,
+    ``mmdet/core/bbox/samplers/sampling_result.py:52-54``).  Returns per-image dicts with
+    ``pos_gt_labels`` (U{0..79}), ``pos_gt_bboxes`` (the positive box jittered so regression
+    targets are O(1)) and ``gt_labels_unique`` (5 classes per image for the SFA loss)."""
+    out = []
+    for i in range(num_imgs):
+        g = torch.Generator().manual_seed(seed + i)
+        p = proposals[i][:num_pos]
+        labels = torch.randint(0, num_classes, (p.shape[0],), generator=g)
+        jit = 1.0 + 0.1 * torch.randn(p.shape[0], 4, generator=g)
+        w = (p[:, 2] - p[:, 0]).clamp(min=1.0)
+        h = (p[:, 3] - p[:, 1]).clamp(min=1.0)
+        cx = (p[:, 0] + p[:, 2]) * 0.5 + 0.05 * w * torch.randn(p.shape[0], generator=g)
+        cy = (p[:, 1] + p[:, 3]) * 0.5 + 0.05 * h * torch.randn(p.shape[0], generator=g)
+        gw = w * jit[:, 0].abs()
+        gh = h * jit[:, 1].abs()
+        gtb = torch.stack([cx - gw / 2, cy - gh / 2, cx + gw / 2, cy + gh / 2], 1)
+        uniq = torch.randperm(num_classes, generator=g)[:5].sort().values
+        out.append(dict(pos_gt_labels=labels, pos_gt_bboxes=gtb, gt_labels_unique=uniq))
+    return out
+
+
+def _gen_for(name, seed):
+    return torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+
+
+def fill_params_(module, scheme='n005', seed=0):
+    """Deterministically (re)initialise every parameter of ``module`` from its state-dict
+    name, so the reference head (oracle side) and this package's head (product side) get
+    identical weights without shipping a 189 MB checkpoint.
+
+    scheme 'n005': every tensor ~ N(0, 0.05) (GroupNorm weight 1 + N(0, 0.05)); makes the
+    PGraph softmax non-trivial.  scheme 'init': magnitudes of the reference's
+    own initialisers (normal 0.01 / 0.001 for fc_cls / fc_reg, xavier-uniform Linear,
+    kaiming-normal conv, zero biases) - ``htd_bbox_head.py:136-145``.
+    """
+    seen = set()
+    with torch.no_grad():
+        for name, p in module.named_parameters(remove_duplicate=False):
+            if id(p) in seen:      # AdptRoIExtractor registers conv1/conv2 twice (att.1/att.3)
+                continue
+            seen.add(id(p))
+            g = _gen_for(name, seed)
+            z = torch.randn(p.shape, generator=g, dtype=torch.float32)
+            if scheme == 'n005':
+                v = 0.05 * z
+                if name.endswith('gn.weight'):
+                    v = 1.0 + v
+                if '.fc_reg.' in name:      # keep refined boxes non-degenerate
+                    v = 0.001 * z
+            elif scheme == 'init':
+                if name.endswith('bias'):
+                    v = torch.zeros_like(z)
+                elif name.endswith('gn.weight'):
+                    v = torch.ones_like(z)
+                elif name.endswith('fc_cls.weight') or name.endswith('glbctx_head.fc.weight'):
+                    v = 0.01 * z
+                elif name.endswith('fc_reg.weight'):
+                    v = 0.001 * z
+                elif p.dim() == 2:
+                    bound = math.sqrt(6.0 / (p.shape[0] + p.shape[1]))
+                    u = torch.rand(p.shape, generator=g, dtype=torch.float32)
+                    v = (2 * u - 1) * bound
+                else:
+                    fan_out = p.shape[0] * p[0][0].numel()
+                    v = math.sqrt(2.0 / fan_out) * z
+            else:
+                raise ValueError(scheme)
+            p.copy_(v.to(p.dtype))
+    return module
+
+
+def level_histogram(rois, finest_scale=56.0, num_levels=4):
+    scale = torch.sqrt((rois[:, 2] - rois[:, 0]) * (rois[:, 3] - rois[:, 1]))
+    lv = torch.floor(torch.log2(scale / finest_scale + 1e-6)).clamp(0, num_levels - 1).long()
+    return torch.bincount(lv, minlength=num_levels).tolist()

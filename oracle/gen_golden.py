@@ -1,0 +1,83 @@
+"""ORACLE (test infrastructure).  Generates tests/golden/*.npz by running the REFERENCE's own
+unmodified modules (oracle/refshim.py, reading /root/reference in place) on the seeded cases
+of oracle/cases.py.  Run here (the authoring container); the fixtures travel, the reference
+does not.
+
+    python -m oracle.gen_golden            # all cases, fp64 + fp32
+
+Fixtures hold, per tensor, a strided sample of <=1024 elements plus sum / abs-sum / max-abs
+(float tensors) or the full tensor (integer tensors: level indices, mask bitsets, degrees).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from htd_b200 import synth
+from . import cases, ref_driver, refshim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def boundary_rois():
+    """RoIs whose sqrt(w*h)/56 + 1e-6 sits on / one ulp around the level boundaries
+    (scale 112, 224, 448), plus degenerate (zero-area) and huge boxes."""
+    rows = []
+    for s in (112.0, 224.0, 448.0, 56.0, 896.0):
+        base = np.float32(s)
+        for k in range(-3, 4):
+            w = base
+            for _ in range(abs(k)):
+                w = np.nextafter(w, np.float32(np.inf if k > 0 else -np.inf), dtype=np.float32)
+            rows.append([0.0, 10.0, 20.0, 10.0 + float(w), 20.0 + float(base)])
+            rows.append([0.0, 0.0, 0.0, float(w), float(w)])
+    rows += [[0, 5, 5, 5, 5], [0, 5, 5, 5, 50], [0, 0, 0, 1333, 800], [0, 3, 4, 3.5, 4.25],
+             [0, 100, 100, 100 + 111.99999, 100 + 112.00001]]
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = refshim.load()
+    torch.set_num_threads(os.cpu_count())
+    # --- level assignment (bit-exact integer fixture) --------------------------------------
+    ext = ns.SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=0), 256,
+                                [4, 8, 16, 32])
+    props = synth.make_proposals(8, 512, seed=99)
+    rois = torch.cat([torch.cat([p.new_full((p.size(0), 1), i), p], 1)
+                      for i, p in enumerate(props)], 0)
+    rois = torch.cat([rois, boundary_rois()], 0)
+    lv = ext.map_roi_levels(rois, 4)
+    np.savez_compressed(os.path.join(OUT, 'levels.npz'), rois=rois.numpy(),
+                        levels=lv.numpy().astype(np.int8))
+    print('levels:', torch.bincount(lv).tolist())
+    # --- graph masks (bit-exact) --------------------------------------------------------------
+    for name in cases.CASES:
+        c, x, pr, gts, shapes = cases.case_inputs(name)
+        r = cases._rois(pr)
+        masks = cases.graph_masks(ns.bbox_overlaps, ext.map_roi_levels(r, 4), r)
+        flat = {}
+        for (b, i), (idx, M, deg) in masks.items():
+            flat[f'{b}_{i}|idx'] = idx.numpy()
+            flat[f'{b}_{i}|bits'] = np.packbits(M.numpy().astype(np.uint8), axis=1)
+            flat[f'{b}_{i}|deg'] = deg.numpy().astype(np.int32)
+        np.savez_compressed(os.path.join(OUT, f'masks_{name}.npz'), **flat)
+    # --- module / head / training fixtures ----------------------------------------------------
+    for name, c in cases.CASES.items():
+        for dt, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
+            head = refshim.build_head(double=(dt == torch.float64))
+            synth.fill_params_(head, c['scheme'], c['seed'])
+            outs = {}
+            outs.update(cases.run_extractors(head, name, dt))
+            outs.update(cases.run_head(head, name, dt))
+            outs.update(cases.run_train(head, ref_driver.ref_forward_train_sampled,
+                                        ref_driver.ref_simple_test_scores, name, dt))
+            path = os.path.join(OUT, f'{name}_{tag}.npz')
+            cases.save_fixture(path, outs)
+            print(name, tag, len(outs), 'tensors ->', path, os.path.getsize(path) // 1024, 'KiB',
+                  {k: float(v) for k, v in outs.items() if k.startswith('train.') and v.numel() == 1})
+
+
+if __name__ == '__main__':
+    sys.exit(main())

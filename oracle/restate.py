@@ -1,0 +1,570 @@
+"""ORACLE (test infrastructure, not product code).
+
+CPU restatement, in plain PyTorch + the C RoIAlign of ``oracle/roi_align_ref.c``, of the
+reference's HTD RoI-head hot path.  Every function cites the reference file:line it follows
+(paths relative to /root/reference).  It exists because the reference tree does not travel to
+the GPU box; it is PINNED to the reference in two ways:
+
+  * ``tests/test_oracle_cpu.py::test_restatement_equals_reference*`` run the reference's own
+    unmodified modules (``oracle/refshim.py``) next to this file on identical inputs (only
+    where /root/reference exists), and
+  * ``tests/golden/*.npz`` hold outputs produced by the reference itself
+    (``oracle/gen_golden.py``); ``tests/test_oracle_cpu.py::test_restatement_matches_golden*``
+    re-check this file against them anywhere.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl
+reference`` legs may import this module.  State-dict key names equal the reference's so that
+``htd_b200.synth.fill_params_`` gives both sides identical weights.
+"""
+import ctypes
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, '_build', 'liboracle.so')
+        if not os.path.isfile(path):
+            import subprocess
+            subprocess.check_call(['make', '-C', _HERE, '-s'])
+        _LIB = ctypes.CDLL(path)
+    return _LIB
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+# --------------------------------------------------------------------------------------
+# RoIAlign  (mmcv.ops.RoIAlign, aligned=True, sampling_ratio=0, avg) - SURVEY §8 a4/a5
+# --------------------------------------------------------------------------------------
+class _RoIAlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rois, out_h, out_w, spatial_scale, sampling_ratio, aligned):
+        assert x.device.type == 'cpu' and x.dtype in (torch.float32, torch.float64)
+        x = x.contiguous()
+        rois = rois.to(x.dtype).contiguous()
+        B, C, H, W = x.shape
+        K = rois.shape[0]
+        out = x.new_zeros(K, C, out_h, out_w)
+        sfx, ct = ('f32', ctypes.c_float) if x.dtype == torch.float32 else ('f64', ctypes.c_double)
+        if K > 0:
+            getattr(lib(), 'roi_align_fwd_' + sfx)(
+                _ptr(x), _ptr(rois), _ptr(out), B, C, H, W, K, out_h, out_w,
+                ct(spatial_scale), int(sampling_ratio), int(bool(aligned)))
+        ctx.save_for_backward(rois)
+        ctx.cfg = (x.shape, out_h, out_w, spatial_scale, sampling_ratio, aligned, sfx, ct)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        (rois,) = ctx.saved_tensors
+        shape, out_h, out_w, spatial_scale, sampling_ratio, aligned, sfx, ct = ctx.cfg
+        B, C, H, W = shape
+        go = go.contiguous()
+        gi = go.new_zeros(shape)
+        K = rois.shape[0]
+        if K > 0:
+            getattr(lib(), 'roi_align_bwd_' + sfx)(
+                _ptr(go), _ptr(rois), _ptr(gi), B, C, H, W, K, out_h, out_w,
+                ct(spatial_scale), int(sampling_ratio), int(bool(aligned)))
+        return gi, None, None, None, None, None, None
+
+
+class RoIAlign(nn.Module):
+    """Signature of mmcv.ops.RoIAlign as used at base_roi_extractor.py:49-55."""
+
+    def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg',
+                 aligned=True, use_torchvision=False):
+        super().__init__()
+        self.output_size = (output_size, output_size) if isinstance(output_size, int) \
+            else tuple(output_size)
+        self.spatial_scale = float(spatial_scale)
+        self.sampling_ratio = int(sampling_ratio)
+        assert pool_mode == 'avg'
+        self.aligned = aligned
+
+    def forward(self, x, rois):
+        return _RoIAlignFn.apply(x, rois, self.output_size[0], self.output_size[1],
+                                 self.spatial_scale, self.sampling_ratio, self.aligned)
+
+
+def map_roi_levels(rois, num_levels, finest_scale=56):
+    """single_level_roi_extractor.py:32-51 (duplicate: htd_bbox_head.py:129-135)."""
+    scale = torch.sqrt((rois[:, 3] - rois[:, 1]) * (rois[:, 4] - rois[:, 2]))
+    target_lvls = torch.floor(torch.log2(scale / finest_scale + 1e-6))
+    return target_lvls.clamp(min=0, max=num_levels - 1).long()
+
+
+def bbox2roi(bbox_list):
+    """core/bbox/transforms.py:58-77."""
+    rois_list = []
+    for img_id, bboxes in enumerate(bbox_list):
+        if bboxes.size(0) > 0:
+            img_inds = bboxes.new_full((bboxes.size(0), 1), img_id)
+            rois = torch.cat([img_inds, bboxes[:, :4]], dim=-1)
+        else:
+            rois = bboxes.new_zeros((0, 5))
+        rois_list.append(rois)
+    return torch.cat(rois_list, 0)
+
+
+def bbox_overlaps(b1, b2, eps=1e-6):
+    """iou2d_calculator.py:43-158, mode='iou', is_aligned=False branch (:129-150)."""
+    rows, cols = b1.size(0), b2.size(0)
+    if rows * cols == 0:
+        return b1.new_zeros((rows, cols))
+    area1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    area2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    lt = torch.max(b1[:, None, :2], b2[None, :, :2])
+    rb = torch.min(b1[:, None, 2:], b2[None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    overlap = wh[..., 0] * wh[..., 1]
+    union = area1[:, None] + area2[None, :] - overlap
+    union = torch.max(union, union.new_tensor([eps]))
+    return overlap / union
+
+
+def bbox2delta(proposals, gt, means, stds):
+    """delta_xywh_bbox_coder.py:78-120."""
+    proposals = proposals.float()      # the reference computes targets in fp32 (:98-99)
+    gt = gt.float()
+    px = (proposals[..., 0] + proposals[..., 2]) * 0.5
+    py = (proposals[..., 1] + proposals[..., 3]) * 0.5
+    pw = proposals[..., 2] - proposals[..., 0]
+    ph = proposals[..., 3] - proposals[..., 1]
+    gx = (gt[..., 0] + gt[..., 2]) * 0.5
+    gy = (gt[..., 1] + gt[..., 3]) * 0.5
+    gw = gt[..., 2] - gt[..., 0]
+    gh = gt[..., 3] - gt[..., 1]
+    deltas = torch.stack([(gx - px) / pw, (gy - py) / ph, torch.log(gw / pw),
+                          torch.log(gh / ph)], dim=-1)
+    means = deltas.new_tensor(means).unsqueeze(0)
+    stds = deltas.new_tensor(stds).unsqueeze(0)
+    return deltas.sub_(means).div_(stds)
+
+
+def delta2bbox(rois, deltas, means, stds, max_shape=None, wh_ratio_clip=16 / 1000):
+    """delta_xywh_bbox_coder.py:123-204 (class-agnostic: deltas [N,4])."""
+    means = deltas.new_tensor(means).view(1, -1)
+    stds = deltas.new_tensor(stds).view(1, -1)
+    d = deltas * stds + means
+    dx, dy, dw, dh = d[:, 0::4], d[:, 1::4], d[:, 2::4], d[:, 3::4]
+    max_ratio = np.abs(np.log(wh_ratio_clip))
+    dw = dw.clamp(min=-max_ratio, max=max_ratio)
+    dh = dh.clamp(min=-max_ratio, max=max_ratio)
+    px = ((rois[:, 0] + rois[:, 2]) * 0.5).unsqueeze(1).expand_as(dx)
+    py = ((rois[:, 1] + rois[:, 3]) * 0.5).unsqueeze(1).expand_as(dy)
+    pw = (rois[:, 2] - rois[:, 0]).unsqueeze(1).expand_as(dw)
+    ph = (rois[:, 3] - rois[:, 1]).unsqueeze(1).expand_as(dh)
+    gw = pw * dw.exp()
+    gh = ph * dh.exp()
+    gx = px + pw * dx
+    gy = py + ph * dy
+    x1, y1, x2, y2 = gx - gw * 0.5, gy - gh * 0.5, gx + gw * 0.5, gy + gh * 0.5
+    if max_shape is not None:
+        x1 = x1.clamp(min=0, max=max_shape[1])
+        y1 = y1.clamp(min=0, max=max_shape[0])
+        x2 = x2.clamp(min=0, max=max_shape[1])
+        y2 = y2.clamp(min=0, max=max_shape[0])
+    return torch.stack([x1, y1, x2, y2], dim=-1).view(deltas.size())
+
+
+# --------------------------------------------------------------------------------------
+# extractors
+# --------------------------------------------------------------------------------------
+class SingleRoIExtractor(nn.Module):
+    """single_level_roi_extractor.py:53-99."""
+
+    def __init__(self, out_channels=256, featmap_strides=(4, 8, 16, 32), finest_scale=56,
+                 output_size=7, sampling_ratio=0):
+        super().__init__()
+        self.roi_layers = nn.ModuleList(
+            [RoIAlign(output_size, 1 / s, sampling_ratio) for s in featmap_strides])
+        self.out_channels = out_channels
+        self.featmap_strides = featmap_strides
+        self.finest_scale = finest_scale
+
+    @property
+    def num_inputs(self):
+        return len(self.featmap_strides)
+
+    def map_roi_levels(self, rois, num_levels):
+        return map_roi_levels(rois, num_levels, self.finest_scale)
+
+    def forward(self, feats, rois):
+        out_size = self.roi_layers[0].output_size
+        num_levels = len(feats)
+        roi_feats = feats[0].new_zeros(rois.size(0), self.out_channels, *out_size)
+        target_lvls = map_roi_levels(rois, num_levels, self.finest_scale)
+        for i in range(num_levels):
+            inds = (target_lvls == i).nonzero(as_tuple=False).squeeze(1)
+            if inds.numel() > 0:
+                roi_feats[inds] = self.roi_layers[i](feats[i], rois[inds])
+            else:
+                roi_feats = roi_feats + feats[i].sum() * 0.
+        return roi_feats
+
+
+class AdptRoIExtractor(nn.Module):
+    """BA extractor, adaptative_roi_extractor.py:24-91 (aggregation='sum', edge from cfg)."""
+
+    def __init__(self, out_channels=256, featmap_strides=(4, 8, 16, 32), edge=1, output_size=7,
+                 sampling_ratio=0):
+        super().__init__()
+        self.roi_layers = nn.ModuleList(
+            [RoIAlign(output_size, 1 / s, sampling_ratio) for s in featmap_strides])
+        self.out_channels = out_channels
+        self.featmap_strides = featmap_strides
+        self.edge = edge
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.conv1 = nn.Conv2d(256, 128, 1)
+        self.conv2 = nn.Conv2d(128, 1, 1)
+        self.att = nn.Sequential(self.pool, self.conv1, nn.Tanh(), self.conv2)
+
+    @property
+    def num_inputs(self):
+        return len(self.featmap_strides)
+
+    def forward(self, feats, rois):
+        out_size = self.roi_layers[0].output_size
+        num_levels = len(feats)
+        if rois.size(0) == 0:
+            return feats[0].new_zeros(0, self.out_channels, *out_size)
+        roi_feat, atts = [], []
+        for i in range(num_levels):
+            t = self.roi_layers[i](feats[i], rois)
+            # reference: self.att(t).squeeze().unsqueeze(0) (:73) - for n == 1 the reference
+            # crashes; the restatement keeps the RoI dim (documented).
+            atts.append(self.att(t).reshape(1, -1))
+            roi_feat.append(t.unsqueeze(0))
+        roi_feat = torch.cat(roi_feat, dim=0)
+        lvl, n, c, x, y = roi_feat.size()
+        atts = torch.cat(atts, dim=0).softmax(0)
+        atts = atts.unsqueeze(-1).repeat(1, 1, c * x * y).view(lvl, n, c, x, y)
+        fused = (atts * roi_feat).sum(0)
+        enh = self.roi_layers[0](feats[0], rois)
+        e = self.edge
+        mask = torch.ones_like(enh)
+        mask[:, :, e:-e, e:-e] = 0     # in-place zeroing at :88, expressed as a mask
+        return fused + enh * mask
+
+
+# --------------------------------------------------------------------------------------
+# heads
+# --------------------------------------------------------------------------------------
+class ConvModule(nn.Module):
+    """mmcv ConvModule defaults used by the reference: conv -> GN -> ReLU, bias='auto'."""
+
+    def __init__(self, i, o, k, padding=0, norm_groups=None, bias='auto'):
+        super().__init__()
+        with_norm = norm_groups is not None
+        if bias == 'auto':
+            bias = not with_norm
+        self.conv = nn.Conv2d(i, o, k, 1, padding, bias=bias)
+        self.gn = nn.GroupNorm(norm_groups, o) if with_norm else None
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.gn is not None:
+            x = self.gn(x)
+        return F.relu(x)
+
+
+class GlobalContextHead(nn.Module):
+    """SFA, global_context_head.py:323-401."""
+
+    def __init__(self, num_convs=4, in_channels=256, conv_out_channels=256, num_classes=81,
+                 loss_weight=3.0):
+        super().__init__()
+        self.convs = nn.ModuleList(
+            [ConvModule(in_channels if i == 0 else conv_out_channels, conv_out_channels, 3, 1)
+             for i in range(num_convs)])
+        self.fc = nn.Linear(conv_out_channels, num_classes)
+        self.loss_weight = loss_weight
+
+    def forward(self, feats):
+        x = feats[-1]
+        for conv in self.convs:
+            x = conv(x)
+        x = F.adaptive_avg_pool2d(x, 1)
+        return self.fc(x.reshape(x.size(0), -1)), x
+
+    def loss(self, pred, labels):
+        labels = [lbl.unique() for lbl in labels]
+        targets = pred.new_zeros(pred.size())
+        for i, label in enumerate(labels):
+            targets[i, label] = 1.0
+        return self.loss_weight * F.binary_cross_entropy_with_logits(pred, targets)
+
+
+def fuse_global(roi_feats, global_feat, rois):
+    """htd_roi_head.py:133-141 / htd_bbox_head.py:147-155."""
+    img_inds = torch.unique(rois[:, 0], sorted=True).long()
+    fused = torch.zeros_like(roi_feats)
+    for img_id in img_inds:
+        inds = rois[:, 0] == img_id.item()
+        fused[inds] = roi_feats[inds] + global_feat[img_id]
+    return fused
+
+
+def cross_entropy_loss(cls_score, labels, label_weights, avg_factor):
+    """losses/cross_entropy_loss.py:9-39 + utils.py:26-52."""
+    loss = F.cross_entropy(cls_score, labels, reduction='none')
+    return (loss * label_weights.to(loss.dtype)).sum() / avg_factor
+
+
+def smooth_l1(pred, target, weight, avg_factor, beta=1.0):
+    """losses/smooth_l1_loss.py:9-27."""
+    diff = torch.abs(pred - target)
+    loss = torch.where(diff < beta, 0.5 * diff * diff / beta, diff - 0.5 * beta)
+    return (loss * weight).sum() / avg_factor
+
+
+def accuracy(pred, target):
+    """losses/accuracy.py:4-48, topk=1."""
+    if pred.size(0) == 0:
+        return pred.new_tensor(0.)
+    lab = pred.topk(1, dim=1)[1].t()
+    correct = lab.eq(target.view(1, -1))
+    return correct[:1].reshape(-1).float().sum(0, keepdim=True).mul_(100.0 / pred.size(0))
+
+
+class BBoxHeadBase(nn.Module):
+    """bbox_head.py:85-335 (targets, loss, refine, regress) for class-agnostic regression."""
+    num_classes = 80
+    target_means = (0., 0., 0., 0.)
+    target_stds = (0.1, 0.1, 0.2, 0.2)
+
+    def get_targets(self, samp, pos_weight=-1):
+        labels, lw, bt, bw = [], [], [], []
+        for res in samp:
+            num_pos, num_neg = res.pos_bboxes.size(0), res.neg_bboxes.size(0)
+            n = num_pos + num_neg
+            lab = res.pos_bboxes.new_full((n,), self.num_classes, dtype=torch.long)
+            w = res.pos_bboxes.new_zeros(n)
+            t = res.pos_bboxes.new_zeros(n, 4)
+            tw = res.pos_bboxes.new_zeros(n, 4)
+            if num_pos > 0:
+                lab[:num_pos] = res.pos_gt_labels
+                w[:num_pos] = 1.0 if pos_weight <= 0 else pos_weight
+                t[:num_pos] = bbox2delta(res.pos_bboxes, res.pos_gt_bboxes, self.target_means,
+                                         self.target_stds)
+                tw[:num_pos] = 1
+            if num_neg > 0:
+                w[-num_neg:] = 1.0
+            labels.append(lab), lw.append(w), bt.append(t), bw.append(tw)
+        return torch.cat(labels), torch.cat(lw), torch.cat(bt), torch.cat(bw)
+
+    def loss(self, cls_score, bbox_pred, rois, labels, label_weights, bbox_targets,
+             bbox_weights):
+        losses = {}
+        avg_factor = max(torch.sum(label_weights > 0).float().item(), 1.)
+        losses['loss_cls'] = cross_entropy_loss(cls_score, labels, label_weights, avg_factor)
+        losses['acc'] = accuracy(cls_score, labels)
+        pos = (labels >= 0) & (labels < self.num_classes)
+        if pos.any():
+            losses['loss_bbox'] = smooth_l1(bbox_pred.view(bbox_pred.size(0), 4)[pos],
+                                            bbox_targets[pos], bbox_weights[pos],
+                                            avg_factor=bbox_targets.size(0))
+        else:
+            losses['loss_bbox'] = bbox_pred[pos].sum()
+        return losses
+
+    def regress_by_class(self, rois, label, bbox_pred, img_shape):
+        bboxes = delta2bbox(rois[:, 1:], bbox_pred, self.target_means, self.target_stds,
+                            max_shape=img_shape)
+        return torch.cat((rois[:, [0]], bboxes), dim=1)
+
+    def refine_bboxes(self, rois, labels, bbox_preds, pos_is_gts, img_shapes):
+        out = []
+        for i in range(len(img_shapes)):
+            inds = torch.nonzero(rois[:, 0] == i, as_tuple=False).squeeze(1)
+            b = self.regress_by_class(rois[inds], labels[inds], bbox_preds[inds],
+                                      img_shapes[i])[:, 1:]
+            keep = pos_is_gts[i].new_ones(inds.numel())
+            keep[:len(pos_is_gts[i])] = 1 - pos_is_gts[i]
+            out.append(b[keep.type(torch.bool)])
+        return out
+
+
+class Shared2FCBBoxHead(BBoxHeadBase):
+    """convfc_bbox_head.py:135-189 with the htd_resnet50_1x.py:57-74 arguments."""
+
+    def __init__(self):
+        super().__init__()
+        self.shared_fcs = nn.ModuleList([nn.Linear(256 * 49, 1024), nn.Linear(1024, 1024)])
+        self.fc_cls = nn.Linear(1024, 81)
+        self.fc_reg = nn.Linear(1024, 4)
+
+    def forward(self, x):
+        x = x.flatten(1)
+        for fc in self.shared_fcs:
+            x = F.relu(fc(x))
+        return self.fc_cls(x), self.fc_reg(x)
+
+
+class HTDBBoxHead(BBoxHeadBase):
+    """htd_bbox_head.py:34-230 with relpace=False, average=False, alpha=1 (all HTD configs)."""
+    target_stds = (0.05, 0.05, 0.1, 0.1)
+
+    def __init__(self):
+        super().__init__()
+        mid = 16 * 36
+        self.fc_cls = nn.Linear(1024, 81)
+        self.fc_reg = nn.Linear(1024, 4)
+        self.convs = nn.Sequential(
+            ConvModule(256, mid, 3, 1, norm_groups=36, bias=False),
+            ConvModule(mid, mid, 3, 1, norm_groups=36, bias=False),
+            ConvModule(mid, mid, 3, 1, norm_groups=36, bias=False),
+            ConvModule(mid, 1024, 3, 1, norm_groups=None, bias=False))
+        self.fcs = nn.Sequential(nn.Linear(256 * 49, 1024), nn.ReLU(), nn.Linear(1024, 1024),
+                                 nn.ReLU())
+        for i in range(4):
+            setattr(self, f'graph_lvl{i}_cls', nn.Linear(1024, 1024))
+
+    def graph_group(self, rois_, x_, sam_, lvl):
+        """One (image, level) group, htd_bbox_head.py:204-217.  Returns new_cls and the mask."""
+        M = bbox_overlaps(rois_, rois_).fill_diagonal_(1.)
+        M[M > 0] = 1.
+        D = torch.diag(torch.sum(M, dim=-1).pow(-0.5))
+        A_local = torch.mm(torch.mm(D, M), D)
+        G = 1. - M
+        mixed = torch.mm(A_local, x_)
+        sim = torch.mm(sam_, sam_.t())
+        A_global = (G * sim).softmax(-1)
+        lin = getattr(self, f'graph_lvl{lvl}_cls')
+        return F.relu(lin(torch.matmul(A_global, mixed))), M
+
+    def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
+                global_feat=None, return_masks=False):
+        prototype = torch.cat((fc_cls_0.weight, fc_cls_0.bias.unsqueeze(1)), 1).detach()
+        bs = int(torch.max(rois[..., 0])) + 1
+        if global_feat is not None:
+            x_cls_glb = fuse_global(x_cls, global_feat, rois)
+            x_reg = fuse_global(x_reg, global_feat, pos_rois)
+            x_cls_glb = self.fcs(x_cls_glb.flatten(1))
+        x_reg = x_reg + enhanced_feat
+        x_reg = self.convs(x_reg)
+        x_reg = F.avg_pool2d(x_reg, 7).view(x_reg.size(0), -1)
+        x_cls = self.fcs(x_cls.flatten(1))
+        sam = torch.mm(fc_cls_0(x_cls).softmax(-1), prototype)
+        target_lvls = map_roi_levels(rois, len(feat))
+        refined = x_cls.new_zeros(x_cls.size(0), 1024)
+        masks = {}
+        for b in range(bs):
+            bs_indx = rois[..., 0] == b
+            for i in range(len(feat)):
+                sel = torch.logical_and(target_lvls == i, bs_indx)
+                if sel.any():
+                    new_cls, M = self.graph_group(rois[sel, 1:5], x_cls[sel, :], sam[sel, :], i)
+                    refined = refined.index_put((sel.nonzero(as_tuple=True)[0],), new_cls)
+                    masks[(b, i)] = (sel.nonzero(as_tuple=True)[0], M)
+        feat_cls_new = (x_cls_glb if global_feat is not None else x_cls) + refined
+        out = self.fc_cls(feat_cls_new), self.fc_reg(x_reg)
+        return out + (masks,) if return_masks else out
+
+
+def make_sampling(bboxes, num_pos, gt):
+    """Synthetic SamplingResult (positives first, sampling_result.py:52-54): the first
+    ``num_pos`` rows of ``bboxes`` are positives with the targets in ``gt``."""
+    n = min(num_pos, bboxes.size(0))
+    return SimpleNamespace(pos_bboxes=bboxes[:n], neg_bboxes=bboxes[n:],
+                           pos_gt_bboxes=gt['pos_gt_bboxes'][:n].to(bboxes.dtype),
+                           pos_gt_labels=gt['pos_gt_labels'][:n],
+                           pos_is_gt=torch.zeros(n, dtype=torch.uint8),
+                           bboxes=bboxes)
+
+
+class HTDRoIHead(nn.Module):
+    """htd_roi_head.py:13-386 restricted to the box path of configs/htd/*.py."""
+
+    def __init__(self):
+        super().__init__()
+        self.bbox_roi_extractor = nn.ModuleList([SingleRoIExtractor(), AdptRoIExtractor()])
+        self.bbox_head = nn.ModuleList([Shared2FCBBoxHead(), HTDBBoxHead()])
+        self.glbctx_head = GlobalContextHead()
+        self.stage_loss_weights = [1, 0.5]
+
+    def _bbox_forward(self, stage, x, rois, global_feat, samp=None):
+        """htd_roi_head.py:143-201."""
+        ext, enh = self.bbox_roi_extractor
+        x4 = x[:ext.num_inputs]
+        if stage == 0:
+            feats = fuse_global(ext(x4, rois), global_feat, rois)
+            cls_score, bbox_pred = self.bbox_head[0](feats)
+            return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=feats)
+        head = self.bbox_head[1]
+        if samp is not None:
+            pos_rois = bbox2roi([r.pos_bboxes for r in samp])
+            feats = ext(x4, rois)
+            sef = enh(x4, pos_rois)
+            # generalisation of the reference's hard-coded <=2 images (:157-170):
+            # positives are the prefix of every image's block
+            pos_idx, off = [], 0
+            for r in samp:
+                pos_idx.append(torch.arange(off, off + r.pos_bboxes.size(0)))
+                off += r.bboxes.size(0)
+            pos_idx = torch.cat(pos_idx)
+            cls_score, bbox_pred = head(feats, feats[pos_idx], x4, rois,
+                                        self.bbox_head[0].fc_cls, sef, pos_rois, global_feat)
+            full = cls_score.new_zeros(cls_score.size(0), 4)
+            full = full.index_put((pos_idx,), bbox_pred)
+            return dict(cls_score=cls_score, bbox_pred=full)
+        feats = ext(x4, rois)
+        sef = enh(x4, rois)
+        cls_score, bbox_pred = head(feats, feats, x4, rois, self.bbox_head[0].fc_cls, sef, rois,
+                                    global_feat)
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred)
+
+    def forward_train_sampled(self, x, proposals, gts, img_shapes, num_pos=128):
+        """htd_roi_head.py:217-317 with the assign+sample steps (:254-264, :300-310) replaced
+        by the synthetic positives-first sampling of SURVEY §8d."""
+        losses = {}
+        mc_pred, g = self.glbctx_head(x)
+        losses['loss_global'] = self.glbctx_head.loss(mc_pred,
+                                                      [gt['gt_labels_unique'] for gt in gts])
+        samp = [make_sampling(p, num_pos, gt) for p, gt in zip(proposals, gts)]
+        rois = bbox2roi([r.bboxes for r in samp])
+        res = self._bbox_forward(0, x, rois, g)
+        targets = self.bbox_head[0].get_targets(samp)
+        l0 = self.bbox_head[0].loss(res['cls_score'], res['bbox_pred'], rois, *targets)
+        for k, v in l0.items():
+            losses[f's0.{k}'] = v * self.stage_loss_weights[0] if 'loss' in k else v
+        with torch.no_grad():
+            roi_labels = torch.where(targets[0] == 80, res['cls_score'][:, :-1].argmax(1),
+                                     targets[0])
+            refined = self.bbox_head[0].refine_bboxes(rois, roi_labels, res['bbox_pred'],
+                                                      [r.pos_is_gt for r in samp], img_shapes)
+        samp = [make_sampling(p, num_pos, gt) for p, gt in zip(refined, gts)]
+        rois = bbox2roi([r.bboxes for r in samp])
+        res = self._bbox_forward(1, x, rois, g, samp)
+        targets = self.bbox_head[1].get_targets(samp)
+        l1 = self.bbox_head[1].loss(res['cls_score'], res['bbox_pred'], rois, *targets)
+        for k, v in l1.items():
+            losses[f's1.{k}'] = v * self.stage_loss_weights[1] if 'loss' in k else v
+        return losses
+
+    def simple_test_scores(self, x, proposals, img_shapes):
+        """htd_roi_head.py:319-366 up to (and excluding) get_bboxes/NMS: returns the refined
+        rois, the stage-averaged cls_score and the stage-1 bbox_pred."""
+        rois = bbox2roi(proposals)
+        _, g = self.glbctx_head(x)
+        r0 = self._bbox_forward(0, x, rois, g)
+        n = [len(p) for p in proposals]
+        label = r0['cls_score'][:, :-1].argmax(1)
+        new_rois = torch.cat([
+            self.bbox_head[0].regress_by_class(r, l, p, s)
+            for r, l, p, s in zip(rois.split(n), label.split(n), r0['bbox_pred'].split(n),
+                                  img_shapes)])
+        r1 = self._bbox_forward(1, x, new_rois, g)
+        return new_rois, (r0['cls_score'] + r1['cls_score']) / 2.0, r1['bbox_pred']

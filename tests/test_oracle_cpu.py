@@ -1,0 +1,140 @@
+"""CPU tests that PIN the oracle: the C RoIAlign against torchvision-CPU, the restatement
+against the reference's own modules (when /root/reference is present) and against the golden
+fixtures generated from the reference (anywhere), plus the reference's own known-answer vectors
+for the adjacent helpers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from htd_b200 import synth
+from oracle import cases, refshim, restate
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _edge_rois():
+    return torch.tensor([
+        [0, 10.3, 7.9, 60.2, 51.1],      # interior
+        [0, -20.0, -14.0, 30.0, 25.0],   # negative coordinates
+        [1, 100.0, 60.0, 400.0, 300.0],  # beyond the image
+        [1, 33.0, 21.0, 33.0, 21.0],     # zero area
+        [0, 0.0, 0.0, 159.0, 99.0],      # full image
+        [1, 50.0, 40.0, 52.5, 41.0],     # sub-bin
+        [0, 70.0, 30.0, 20.0, 10.0],     # inverted (x2 < x1)
+    ])
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+@pytest.mark.parametrize('scale', [1.0, 0.25])
+def test_c_roialign_equals_torchvision(dtype, scale):
+    from torchvision.ops import roi_align
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 25, 40, generator=g).to(dtype).requires_grad_(True)
+    rois = _edge_rois().to(dtype)
+    rois[:, 1:] /= (0.25 / scale) if scale != 1.0 else 4.0
+    rois[:, 1:] *= 1.0 if scale == 1.0 else 4.0
+    ya = restate.RoIAlign(7, scale, 0)(x, rois)
+    yb = roi_align(x, rois, (7, 7), scale, 0, True)
+    tol = 1e-12 if dtype == torch.float64 else 1e-6
+    assert (ya - yb).abs().max().item() <= tol
+    gy = torch.randn(ya.shape, generator=g).to(dtype)
+    ga, = torch.autograd.grad((ya * gy).sum(), x)
+    gb, = torch.autograd.grad((yb * gy).sum(), x)
+    assert (ga - gb).abs().max().item() <= tol * 10
+
+
+def test_bbox_overlaps_known_answers():
+    # doctest of iou2d_calculator.py:65-86 and the aligned IoU of tests/test_iou2d_calculator.py
+    b1 = torch.FloatTensor([[0, 0, 10, 10], [10, 10, 20, 20], [32, 32, 38, 42]])
+    b2 = torch.FloatTensor([[0, 0, 10, 20], [0, 10, 10, 19], [10, 10, 20, 20]])
+    ov = restate.bbox_overlaps(b1, b2)
+    assert ov.shape == (3, 3)
+    assert torch.allclose(ov.diag(), torch.tensor([0.5, 0.0, 0.0]))
+    assert ov[1, 2].item() == 1.0
+    empty = torch.empty(0, 4)
+    assert tuple(restate.bbox_overlaps(empty, b1).shape) == (0, 3)
+    assert tuple(restate.bbox_overlaps(b1, empty).shape) == (3, 0)
+
+
+def test_delta2bbox_golden():
+    # golden tensor of delta_xywh_bbox_coder.py:148-169
+    rois = torch.Tensor([[0., 0., 1., 1.], [0., 0., 1., 1.], [0., 0., 1., 1.], [5., 5., 5., 5.]])
+    deltas = torch.Tensor([[0., 0., 0., 0.], [1., 1., 1., 1.], [0., 0., 2., -1.],
+                           [0.7, -1.9, -0.5, 0.3]])
+    out = restate.delta2bbox(rois, deltas, (0., 0., 0., 0.), (1., 1., 1., 1.), max_shape=(32, 32))
+    want = torch.tensor([[0.0000, 0.0000, 1.0000, 1.0000], [0.1409, 0.1409, 2.8591, 2.8591],
+                         [0.0000, 0.3161, 4.1945, 0.6839], [5.0000, 5.0000, 5.0000, 5.0000]])
+    assert torch.allclose(out, want, atol=1e-4)
+    back = restate.bbox2delta(rois[:3], out[:3], (0., 0., 0., 0.), (1., 1., 1., 1.))
+    assert torch.isfinite(back).all()
+
+
+def test_levels_match_golden():
+    z = np.load(os.path.join(GOLD, 'levels.npz'))
+    rois = torch.from_numpy(z['rois'])
+    lv = restate.map_roi_levels(rois, 4)
+    assert np.array_equal(lv.numpy().astype(np.int8), z['levels'])
+    out = np.zeros(rois.shape[0], dtype=np.int64)
+    import ctypes
+    restate.lib().map_roi_levels_f32(ctypes.c_void_p(rois.data_ptr()),
+                                     out.ctypes.data_as(ctypes.c_void_p), rois.shape[0], 4,
+                                     ctypes.c_float(56.0))
+    assert np.array_equal(out.astype(np.int8), z['levels'])
+
+
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_masks_match_golden(name):
+    z = np.load(os.path.join(GOLD, f'masks_{name}.npz'))
+    c, x, pr, gts, shapes = cases.case_inputs(name)
+    r = cases._rois(pr)
+    masks = cases.graph_masks(restate.bbox_overlaps, restate.map_roi_levels(r, 4), r)
+    assert {f'{b}_{i}' for b, i in masks} == {k.split('|')[0] for k in z.files}
+    for (b, i), (idx, M, deg) in masks.items():
+        assert np.array_equal(idx.numpy(), z[f'{b}_{i}|idx'])
+        assert np.array_equal(np.packbits(M.numpy().astype(np.uint8), axis=1), z[f'{b}_{i}|bits'])
+        assert np.array_equal(deg.numpy().astype(np.int32), z[f'{b}_{i}|deg'])
+
+
+def _restate_outs(name, dt, which=('ext', 'head', 'train')):
+    c = cases.CASES[name]
+    head = restate.HTDRoIHead().to(dt)
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    outs = {}
+    if 'ext' in which:
+        outs.update(cases.run_extractors(head, name, dt))
+    if 'head' in which:
+        outs.update(cases.run_head(head, name, dt))
+    if 'train' in which:
+        outs.update(cases.run_train(
+            head, lambda h, *a: h.forward_train_sampled(*a),
+            lambda h, *a: h.simple_test_scores(*a), name, dt))
+    return outs
+
+
+@pytest.mark.parametrize('name,tag,dt,tol', [('small', 'f64', torch.float64, 1e-10),
+                                             ('small', 'f32', torch.float32, 2e-5),
+                                             ('mid', 'f32', torch.float32, 2e-5)])
+def test_restatement_matches_golden(name, tag, dt, tol):
+    fix = cases.load_fixture(os.path.join(GOLD, f'{name}_{tag}.npz'))
+    outs = _restate_outs(name, dt)
+    assert set(outs) == set(fix)
+    cases.compare_to_fixture(outs, fix, tol)
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference not present')
+def test_restatement_equals_reference_live():
+    """Runs the reference's own unmodified modules next to the restatement (fp32, 'small')."""
+    from oracle import ref_driver
+    c = cases.CASES['small']
+    ref = refshim.build_head()
+    synth.fill_params_(ref, c['scheme'], c['seed'])
+    assert sum(p.numel() for p in set(ref.parameters())) == 47189116
+    a = {}
+    a.update(cases.run_extractors(ref, 'small', torch.float32))
+    a.update(cases.run_head(ref, 'small', torch.float32))
+    b = _restate_outs('small', torch.float32, ('ext', 'head'))
+    assert set(ref.state_dict()) == set(restate.HTDRoIHead().state_dict())
+    for k in a:
+        assert cases.rel_err(b[k], a[k]) <= 1e-6, k
