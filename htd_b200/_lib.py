@@ -1,0 +1,115 @@
+"""ctypes binding of the C-ABI library ``libhtd_b200.so`` (include/htd_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+The product never imports ``oracle/``.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libhtd_b200.so')
+
+HTD_F32, HTD_BF16 = 0, 1
+MAX_LEVELS = 8
+_DT = {torch.float32: HTD_F32, torch.bfloat16: HTD_BF16}
+
+c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+
+
+class HtdLevel(ctypes.Structure):
+    _fields_ = [('data', c_void_p), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
+                ('spatial_scale', c_float), ('reserved', ctypes.c_int32)]
+
+
+# name -> argtypes; every function returns int (HTD_OK == 0) unless noted
+SIGNATURES = {
+    'htd_level_assign': [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p],
+    'htd_roi_footprints': [ctypes.POINTER(HtdLevel), c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                           c_int, c_void_p, c_void_p, c_void_p],
+    'htd_roi_align_fwd': [ctypes.POINTER(HtdLevel), c_int, c_int, c_int, c_int, c_void_p, c_int,
+                          c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    'htd_roi_align_bwd': [ctypes.POINTER(HtdLevel), c_int, c_int, c_int, c_int, c_void_p, c_int,
+                          c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                          c_void_p],
+    'htd_layout_convert': [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
+    'htd_ba_bin_mean': [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p],
+    'htd_ba_fuse_fwd': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                        c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    'htd_ba_fuse_bwd': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                        c_void_p, c_void_p],
+    'htd_bias_grad': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                      c_void_p],
+    'htd_iou_graph_build': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p],
+    'htd_pgraph_local_adj': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    'htd_pgraph_masked_softmax': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                                  c_void_p, c_void_p],
+    'htd_pgraph_softmax_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                               c_void_p],
+    'htd_pgraph_gemm': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                        c_int, c_int, c_int, c_void_p],
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m htd_b200.build` (nvcc, sm_100a). '
+                'htd_b200 has no CPU or PyTorch fallback.')
+        L = ctypes.CDLL(LIB_PATH)
+        L.htd_last_error.restype = ctypes.c_char_p
+        L.htd_abi_version.restype = c_int
+        for name, args in SIGNATURES.items():
+            if not hasattr(L, name):
+                continue
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        _lib = L
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().htd_last_error().decode(errors='replace')
+        raise RuntimeError(f'htd_b200 {what} failed (code {rc}): {msg}')
+
+
+def dt(t):
+    try:
+        return _DT[t.dtype if isinstance(t, torch.Tensor) else t]
+    except KeyError:
+        raise TypeError(f'htd_b200 supports float32 and bfloat16 tensors, got {t}') from None
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('htd_b200 ops run on CUDA tensors only (no CPU fallback); got a '
+                               f'{t.device} tensor')
+
+
+def make_levels(tensors_bhwc, scales):
+    """ctypes array of HtdLevel for channels-last [B,H,W,C] buffers."""
+    arr = (HtdLevel * len(tensors_bhwc))()
+    for i, (t, s) in enumerate(zip(tensors_bhwc, scales)):
+        arr[i].data = t.data_ptr()
+        arr[i].H = t.shape[1]
+        arr[i].W = t.shape[2]
+        arr[i].spatial_scale = float(s)
+        arr[i].reserved = 0
+    return arr

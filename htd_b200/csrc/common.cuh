@@ -1,0 +1,116 @@
+// Shared helpers for the htd_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/htd_b200.h"
+
+namespace htd {
+
+void set_error(const char* fmt, ...);
+
+#define HTD_CHECK_ARG(cond, ...)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            htd::set_error(__VA_ARGS__);                           \
+            return HTD_ERR_INVALID_ARGUMENT;                       \
+        }                                                          \
+    } while (0)
+
+#define HTD_CHECK_LAUNCH(name)                                                     \
+    do {                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess) {                                                  \
+            htd::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+            return HTD_ERR_CUDA;                                                   \
+        }                                                                          \
+    } while (0)
+
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------
+// A warp covers 256 channels of one pixel with 128-bit accesses; a lane owns 8 channels.  The
+// lane->channel map is a property of the KERNEL (all tensors it touches must agree):
+//   kSplit = true  (all-fp32 kernels): channels {4l..4l+3} and {128+4l..128+4l+3}, so each of
+//                  the two float4 accesses of a warp is one contiguous 512 B run;
+//   kSplit = false (any bf16 operand): channels {8l..8l+7}; bf16 moves one uint4 (512 B per
+//                  warp), fp32 moves two float4 at 8l and 8l+4.
+// `p` points at the 256-channel chunk, `nch` = channels left in it (multiple of 8) masks the
+// tail when C is not a multiple of 256.
+// ---------------------------------------------------------------------------------------------
+template <bool kSplit>
+__device__ __forceinline__ int lane_chan(int lane, int e) {
+    return kSplit ? ((e < 4) ? lane * 4 + e : 128 + lane * 4 + (e - 4)) : lane * 8 + e;
+}
+
+template <typename T, bool kSplit>
+struct Vec8;
+
+template <bool kSplit>
+struct Vec8<float, kSplit> {
+    static __device__ __forceinline__ void load(const float* __restrict__ p, int lane, int nch,
+                                                float (&v)[8]) {
+        const int c0 = kSplit ? lane * 4 : lane * 8, c1 = kSplit ? 128 + lane * 4 : lane * 8 + 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (c0 < nch) a = __ldg(reinterpret_cast<const float4*>(p + c0));
+        if (c1 < nch) b = __ldg(reinterpret_cast<const float4*>(p + c1));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* __restrict__ p, int lane, int nch,
+                                                 const float (&v)[8]) {
+        const int c0 = kSplit ? lane * 4 : lane * 8, c1 = kSplit ? 128 + lane * 4 : lane * 8 + 4;
+        if (c0 < nch) *reinterpret_cast<float4*>(p + c0) = make_float4(v[0], v[1], v[2], v[3]);
+        if (c1 < nch) *reinterpret_cast<float4*>(p + c1) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+template <bool kSplit>
+struct Vec8<__nv_bfloat16, kSplit> {
+    static_assert(!kSplit, "bf16 tensors use the contiguous lane->channel map");
+    static __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ p, int lane,
+                                                int nch, float (&v)[8]) {
+        const int c0 = lane * 8;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (c0 < nch) u = __ldg(reinterpret_cast<const uint4*>(p + c0));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* __restrict__ p, int lane, int nch,
+                                                 const float (&v)[8]) {
+        const int c0 = lane * 8;
+        if (c0 >= nch) return;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+template <typename A, typename B>
+struct SplitMap {
+    static constexpr bool value = false;
+};
+template <>
+struct SplitMap<float, float> {
+    static constexpr bool value = true;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline size_t dtype_size(int dt) { return dt == HTD_BF16 ? 2 : 4; }
+
+}  // namespace htd

@@ -1,0 +1,339 @@
+// Layout conversion and the Border-aware Adaptation (BA) fuse kernels.
+//
+// Reference path replaced: AdptRoIExtractor.forward, adaptative_roi_extractor.py:76-91 -
+//   atts = cat(atts).softmax(0); roi_feats = (atts * roi_feat).sum(0);
+//   roi_feats_enhance = RoIAlign_0(feats[0], rois); roi_feats_enhance[:, :, e:-e, e:-e] = 0
+//   return roi_feats + roi_feats_enhance
+// which materialises [4,P,256,7,7] twice (repeat + product) and runs RoIAlign on P2 twice; here
+// the four level samples R[l] come from ONE multi-level htd_roi_align_fwd launch (P2 sampled
+// once) and the softmax-weighted sum + border ring (+ the HTDBBoxHead residual adds,
+// htd_bbox_head.py:161-184) are one elementwise pass.
+#include "common.cuh"
+
+namespace htd {
+
+// ------------------------------------------------------------------------------------------
+// [N,R,S] -> [N,S,R] tiled transpose with dtype conversion
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_kernel(const TS* __restrict__ src,
+                                                        TD* __restrict__ dst, long long N, int R,
+                                                        int S, int tiles_r, int tiles_s) {
+    __shared__ float tile[32][33];
+    long long blk = blockIdx.x;
+    const int ts = (int)(blk % tiles_s);
+    blk /= tiles_s;
+    const int tr = (int)(blk % tiles_r);
+    const long long n = blk / tiles_r;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const TS* s = src + (size_t)n * R * S;
+    TD* d = dst + (size_t)n * R * S;
+    const int r0 = tr * 32, s0 = ts * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty + i * 8, c = s0 + tx;
+        if (r < R && c < S) tile[ty + i * 8][tx] = to_f<TS>(s[(size_t)r * S + c]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = s0 + ty + i * 8, r = r0 + tx;
+        if (r < R && c < S) d[(size_t)c * R + r] = from_f<TD>(tile[tx][ty + i * 8]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// BA kernels
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) bin_mean_kernel(const T* __restrict__ x, long long N, int PP,
+                                                       int C, float* __restrict__ mean) {
+    const long long n = blockIdx.x;
+    const T* xn = x + (size_t)n * PP * C;
+    const float inv = 1.f / (float)PP;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < PP; ++b) s += to_f<T>(xn[(size_t)b * C + c]);
+        mean[(size_t)n * C + c] = s * inv;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]) {
+    Vec8<T, false>::load(p, 0, 8, v);   // lane 0 of the contiguous map = 8 channels at p
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&v)[8]) {
+    Vec8<T, false>::store(p, 0, 8, v);
+}
+
+struct FuseParams {
+    const void* R;
+    const float* logits;
+    int L, K, P, C, ring_edge, B;
+    const void* add;
+    const float* bias;
+    const float* rois;
+    float* w;
+    void* out;
+};
+
+template <typename TR, typename TA, typename TO>
+__global__ void __launch_bounds__(256) ba_fuse_fwd_kernel(const FuseParams p) {
+    const int PP = p.P * p.P, C8 = p.C / 8;
+    const long long total = (long long)p.K * PP * C8;
+    const TR* R = static_cast<const TR*>(p.R);
+    const TA* add = static_cast<const TA*>(p.add);
+    TO* out = static_cast<TO*>(p.out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const long long kb = i / C8;
+        const int bin = (int)(kb % PP);
+        const int k = (int)(kb / PP);
+        // softmax over levels (L <= 8), recomputed per thread: L exps vs 8*L loads of R
+        float wl[HTD_MAX_LEVELS];
+        float mx = -INFINITY;
+        for (int l = 0; l < p.L; ++l) {
+            wl[l] = __ldg(p.logits + (size_t)l * p.K + k);
+            mx = fmaxf(mx, wl[l]);
+        }
+        float den = 0.f;
+        for (int l = 0; l < p.L; ++l) { wl[l] = expf(wl[l] - mx); den += wl[l]; }
+        const float inv = 1.f / den;
+        for (int l = 0; l < p.L; ++l) wl[l] *= inv;
+        if (bin == 0 && c8 == 0)
+            for (int l = 0; l < p.L; ++l) p.w[(size_t)l * p.K + k] = wl[l];
+        const int ph = bin / p.P, pw = bin % p.P, e0 = p.ring_edge;
+        float ring = 0.f;
+        if (e0 >= 0) {
+            const bool interior = (e0 > 0) && ph >= e0 && ph < p.P - e0 && pw >= e0 && pw < p.P - e0;
+            ring = interior ? 0.f : 1.f;
+        }
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const size_t off = ((size_t)k * PP + bin) * p.C + (size_t)c8 * 8;
+        for (int l = 0; l < p.L; ++l) {
+            float v[8];
+            ld8<TR>(R + (size_t)l * p.K * PP * p.C + off, v);
+            const float wv = wl[l] + (l == 0 ? ring : 0.f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(wv, v[e], acc[e]);
+        }
+        if (add) {
+            float v[8];
+            ld8<TA>(add + off, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        }
+        if (p.bias) {
+            const int b = (int)__ldg(p.rois + (size_t)k * 5);
+            if (b >= 0 && b < p.B) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += __ldg(p.bias + (size_t)b * p.C + c8 * 8 + e);
+            }
+        }
+        st8<TO>(out + off, acc);
+    }
+}
+
+template <typename TR, typename TG>
+__global__ void __launch_bounds__(256) ba_fuse_bwd_kernel(const TR* __restrict__ R,
+                                                          const TG* __restrict__ dout,
+                                                          const float* __restrict__ w, int L, int K,
+                                                          int PP, int C, float* __restrict__ da) {
+    __shared__ float s_part[HTD_MAX_LEVELS][8];
+    const int k = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n8 = PP * C / 8;
+    float dw[HTD_MAX_LEVELS];
+#pragma unroll
+    for (int l = 0; l < HTD_MAX_LEVELS; ++l) dw[l] = 0.f;
+    for (int i = tid; i < n8; i += 256) {
+        float g[8];
+        ld8<TG>(dout + ((size_t)k * n8 + i) * 8, g);
+#pragma unroll
+        for (int l = 0; l < HTD_MAX_LEVELS; ++l) {
+            if (l < L) {
+                float v[8];
+                ld8<TR>(R + (((size_t)l * K + k) * n8 + i) * 8, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dw[l] = fmaf(g[e], v[e], dw[l]);
+            }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < HTD_MAX_LEVELS; ++l) {
+        const float s = warp_sum(dw[l]);
+        if (lane == 0) s_part[l][warp] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float tot[HTD_MAX_LEVELS], mean = 0.f;
+        for (int l = 0; l < L; ++l) {
+            float s = 0.f;
+            for (int i = 0; i < 8; ++i) s += s_part[l][i];
+            tot[l] = s;
+            mean += w[(size_t)l * K + k] * s;
+        }
+        for (int l = 0; l < L; ++l) da[(size_t)l * K + k] = w[(size_t)l * K + k] * (tot[l] - mean);
+    }
+}
+
+// dbias, phase 1: block = 32 consecutive RoIs, thread = channel
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_partial_kernel(const T* __restrict__ g,
+                                                                const float* __restrict__ rois,
+                                                                int K, int PP, int C, int B,
+                                                                float* __restrict__ partial) {
+    const int kb = blockIdx.x;
+    float* part = partial + (size_t)kb * B * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        for (int b = 0; b < B; ++b) part[(size_t)b * C + c] = 0.f;
+        const int kend = min(K, (kb + 1) * 32);
+        for (int k = kb * 32; k < kend; ++k) {
+            const int b = (int)__ldg(rois + (size_t)k * 5);
+            if (b < 0 || b >= B) continue;
+            float s = 0.f;
+            for (int bin = 0; bin < PP; ++bin) s += to_f<T>(g[((size_t)k * PP + bin) * C + c]);
+            part[(size_t)b * C + c] += s;
+        }
+    }
+}
+
+__global__ void bias_grad_final_kernel(const float* __restrict__ partial, int nblk, int BC,
+                                       float* __restrict__ dbias) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BC) return;
+    float s = 0.f;
+    for (int kb = 0; kb < nblk; ++kb) s += partial[(size_t)kb * BC + i];
+    dbias[i] = s;
+}
+
+}  // namespace htd
+
+using namespace htd;
+
+#define DISPATCH2(dtA, dtB, CALL)                                              \
+    do {                                                                       \
+        if ((dtA) == HTD_F32 && (dtB) == HTD_F32) { CALL(float, float); }      \
+        else if ((dtA) == HTD_F32) { CALL(float, __nv_bfloat16); }             \
+        else if ((dtB) == HTD_F32) { CALL(__nv_bfloat16, float); }             \
+        else { CALL(__nv_bfloat16, __nv_bfloat16); }                           \
+    } while (0)
+
+static bool dt_ok(int d) { return d == HTD_F32 || d == HTD_BF16; }
+
+extern "C" {
+
+int htd_layout_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long N,
+                       int R, int S, htd_stream_t stream) {
+    HTD_CHECK_ARG(dt_ok(src_dtype) && dt_ok(dst_dtype), "htd_layout_convert: bad dtype");
+    HTD_CHECK_ARG(N >= 0 && R >= 1 && S >= 1, "htd_layout_convert: bad sizes");
+    if (N == 0) return HTD_OK;
+    HTD_CHECK_ARG(src && dst, "htd_layout_convert: null pointer");
+    const int tr = (R + 31) / 32, ts = (S + 31) / 32;
+    const long long blocks = N * tr * ts;
+    HTD_CHECK_ARG(blocks < 2147483647LL, "htd_layout_convert: tensor too large");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TS, TD)                                                                          \
+    transpose_kernel<TS, TD><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TS*>(src),   \
+                                                               static_cast<TD*>(dst), N, R, S, tr, ts)
+    DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+    HTD_CHECK_LAUNCH("htd_layout_convert");
+    return HTD_OK;
+}
+
+int htd_ba_bin_mean(const void* x, int x_dtype, long long N, int PP, int C, float* mean,
+                    htd_stream_t stream) {
+    HTD_CHECK_ARG(dt_ok(x_dtype) && N >= 0 && PP >= 1 && C >= 1, "htd_ba_bin_mean: bad arguments");
+    if (N == 0) return HTD_OK;
+    HTD_CHECK_ARG(x && mean && N < 2147483647LL, "htd_ba_bin_mean: null pointer / too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == HTD_F32)
+        bin_mean_kernel<float><<<(unsigned)N, 256, 0, st>>>(static_cast<const float*>(x), N, PP, C, mean);
+    else
+        bin_mean_kernel<__nv_bfloat16><<<(unsigned)N, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), N, PP, C, mean);
+    HTD_CHECK_LAUNCH("htd_ba_bin_mean");
+    return HTD_OK;
+}
+
+int htd_ba_fuse_fwd(const void* R, int r_dtype, const float* logits, int L, int K, int P, int C,
+                    int ring_edge, const void* add, int add_dtype, const float* bias,
+                    const float* rois, int B, float* w, void* out, int out_dtype,
+                    htd_stream_t stream) {
+    HTD_CHECK_ARG(dt_ok(r_dtype) && dt_ok(out_dtype) && (!add || dt_ok(add_dtype)),
+                  "htd_ba_fuse_fwd: bad dtype");
+    HTD_CHECK_ARG(L >= 1 && L <= HTD_MAX_LEVELS && K >= 0 && P >= 1 && P <= HTD_MAX_POOLED &&
+                      C >= 8 && C % 8 == 0,
+                  "htd_ba_fuse_fwd: bad sizes L=%d K=%d P=%d C=%d", L, K, P, C);
+    HTD_CHECK_ARG(!bias || (rois && B >= 1), "htd_ba_fuse_fwd: bias needs rois and B");
+    if (K == 0) return HTD_OK;
+    HTD_CHECK_ARG(R && logits && w && out, "htd_ba_fuse_fwd: null pointer");
+    // the residual `add` shares the dtype of R in every caller; keep the dispatch 2-way
+    HTD_CHECK_ARG(!add || add_dtype == r_dtype, "htd_ba_fuse_fwd: add must have the dtype of R");
+    FuseParams p{R, logits, L, K, P, C, ring_edge, B, add, bias, rois, w, out};
+    const long long total = (long long)K * P * P * (C / 8);
+    const unsigned blocks = (unsigned)((total + 255) / 256 < 148LL * 16 ? (total + 255) / 256 : 148LL * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TR, TO) ba_fuse_fwd_kernel<TR, TR, TO><<<blocks, 256, 0, st>>>(p)
+    DISPATCH2(r_dtype, out_dtype, CALL);
+#undef CALL
+    HTD_CHECK_LAUNCH("htd_ba_fuse_fwd");
+    return HTD_OK;
+}
+
+int htd_ba_fuse_bwd(const void* R, int r_dtype, const void* dout, int dout_dtype, const float* w,
+                    int L, int K, int PP, int C, float* da, htd_stream_t stream) {
+    HTD_CHECK_ARG(dt_ok(r_dtype) && dt_ok(dout_dtype), "htd_ba_fuse_bwd: bad dtype");
+    HTD_CHECK_ARG(L >= 1 && L <= HTD_MAX_LEVELS && K >= 0 && PP >= 1 && C >= 8 && C % 8 == 0,
+                  "htd_ba_fuse_bwd: bad sizes");
+    if (K == 0) return HTD_OK;
+    HTD_CHECK_ARG(R && dout && w && da, "htd_ba_fuse_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TR, TG)                                                                          \
+    ba_fuse_bwd_kernel<TR, TG><<<K, 256, 0, st>>>(static_cast<const TR*>(R),                  \
+                                                  static_cast<const TG*>(dout), w, L, K, PP, C, da)
+    DISPATCH2(r_dtype, dout_dtype, CALL);
+#undef CALL
+    HTD_CHECK_LAUNCH("htd_ba_fuse_bwd");
+    return HTD_OK;
+}
+
+int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, int C, int B,
+                  float* partial, float* dbias, htd_stream_t stream) {
+    HTD_CHECK_ARG(dt_ok(g_dtype) && K >= 0 && PP >= 1 && C >= 1 && B >= 1,
+                  "htd_bias_grad: bad arguments");
+    HTD_CHECK_ARG(dbias && (K == 0 || (g && rois && partial)), "htd_bias_grad: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nblk = (K + 31) / 32;
+    if (nblk > 0) {
+        if (g_dtype == HTD_F32)
+            bias_grad_partial_kernel<float><<<nblk, 256, 0, st>>>(static_cast<const float*>(g), rois,
+                                                                  K, PP, C, B, partial);
+        else
+            bias_grad_partial_kernel<__nv_bfloat16><<<nblk, 256, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(g), rois, K, PP, C, B, partial);
+        HTD_CHECK_LAUNCH("htd_bias_grad(partial)");
+    }
+    bias_grad_final_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(partial, nblk, B * C, dbias);
+    HTD_CHECK_LAUNCH("htd_bias_grad(final)");
+    return HTD_OK;
+}
+
+}  // extern "C"

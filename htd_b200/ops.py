@@ -1,0 +1,257 @@
+"""torch.autograd bindings of the C-ABI kernels (RoIAlign / BA part).
+
+PyTorch only provides device memory, the current stream and autograd plumbing here; all
+arithmetic of the path happens in ``libhtd_b200.so``.  Feature maps are handled as
+channels-last: a ``[B,C,H,W]`` tensor whose memory is ``[B,H,W,C]``; RoI features are returned as
+``[K,C,P,P]`` tensors with channels_last strides (values index exactly like the reference's
+NCHW tensors).
+"""
+import torch
+
+from . import _lib
+from ._lib import check, dt, lib, ptr, stream
+
+
+# ------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------
+def _is_cl(t):
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _convert(src, dst, N, R, S):
+    check(lib().htd_layout_convert(ptr(src), dt(src), ptr(dst), dt(dst), N, R, S, stream()),
+          'htd_layout_convert')
+
+
+class _ToChannelsLast(torch.autograd.Function):
+    """NCHW-contiguous -> channels-last (+ optional dtype change) with the transpose kernel."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        B, C, H, W = x.shape
+        out = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
+        _convert(x, out, B, C, H * W)
+        ctx.src_dtype = x.dtype
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, H, W = g.shape
+        if not _is_cl(g):
+            g = g.contiguous(memory_format=torch.channels_last)
+        out = torch.empty((B, C, H, W), dtype=ctx.src_dtype, device=g.device)
+        _convert(g, out, B, H * W, C)
+        return out, None
+
+
+def to_channels_last(x, dtype=None):
+    """Feature map in the layout the kernels read.  No copy if it already is channels-last in
+    the requested dtype."""
+    _lib.require_cuda(x)
+    dtype = dtype or x.dtype
+    if _is_cl(x) and x.dtype == dtype:
+        return x
+    if x.is_contiguous():
+        return _ToChannelsLast.apply(x, dtype)
+    return x.to(dtype).contiguous(memory_format=torch.channels_last)
+
+
+def _bhwc(x):
+    """[B,C,H,W] channels-last tensor -> its [B,H,W,C] memory view."""
+    return x.permute(0, 2, 3, 1)
+
+
+# ------------------------------------------------------------------------------------------
+# level assignment
+# ------------------------------------------------------------------------------------------
+def level_assign(rois, num_levels, finest_scale=56.0):
+    """int32 level per RoI (-1: NaN scale).  SingleRoIExtractor.map_roi_levels."""
+    _lib.require_cuda(rois)
+    rois = rois.detach().float().contiguous()
+    out = torch.empty(rois.shape[0], dtype=torch.int32, device=rois.device)
+    check(lib().htd_level_assign(ptr(rois), rois.shape[0], int(num_levels), float(finest_scale),
+                                 ptr(out), stream()), 'htd_level_assign')
+    return out
+
+
+def roi_footprints(feats_cl, scales, rois, roi_level, pooled, sampling_ratio, count=False):
+    L, K = len(feats_cl), rois.shape[0]
+    B = feats_cl[0].shape[0]
+    boxes = torch.empty((L, K, 4), dtype=torch.int32, device=rois.device)
+    cnt = torch.zeros(L, dtype=torch.int64, device=rois.device) if count else None
+    lv = _lib.make_levels([_bhwc(f) for f in feats_cl], scales)
+    check(lib().htd_roi_footprints(lv, L, B, ptr(rois), K, ptr(roi_level), pooled, sampling_ratio,
+                                   ptr(boxes), ptr(cnt), stream()), 'htd_roi_footprints')
+    return (boxes, cnt) if count else boxes
+
+
+# ------------------------------------------------------------------------------------------
+# multi-level RoIAlign
+# ------------------------------------------------------------------------------------------
+def _roi_align_bwd(feat_shapes, feat_dtype, scales, rois, boxes, pooled, sampling_ratio, dy,
+                   dy_per_level, scale=None, ring_edge=-1, addvec=None):
+    """Launch the gather backward; returns per-level dX as [B,C,H,W] channels-last tensors."""
+    dev = rois.device
+    L = len(feat_shapes)
+    B, C = feat_shapes[0][0], feat_shapes[0][1]
+    bufs = [torch.empty((B, s[2], s[3], C), dtype=feat_dtype, device=dev) for s in feat_shapes]
+    lv = _lib.make_levels(bufs, scales)
+    check(lib().htd_roi_align_bwd(lv, L, B, C, dt(feat_dtype), ptr(rois), rois.shape[0],
+                                  ptr(boxes), pooled, sampling_ratio, ptr(dy), dt(dy),
+                                  int(bool(dy_per_level)), ptr(scale), int(ring_edge), ptr(addvec),
+                                  stream()), 'htd_roi_align_bwd')
+    return [b.permute(0, 3, 1, 2) for b in bufs]
+
+
+def _bias_grad(g_kppc, rois, B):
+    K, PP, C = g_kppc.shape[0], g_kppc.shape[1] * g_kppc.shape[2], g_kppc.shape[3]
+    nblk = max((K + 31) // 32, 1)
+    partial = torch.empty((nblk, B, C), dtype=torch.float32, device=g_kppc.device)
+    dbias = torch.empty((B, C), dtype=torch.float32, device=g_kppc.device)
+    check(lib().htd_bias_grad(ptr(g_kppc), dt(g_kppc), ptr(rois), K, PP, C, B, ptr(partial),
+                              ptr(dbias), stream()), 'htd_bias_grad')
+    return dbias
+
+
+class _RoIAlignLevels(torch.autograd.Function):
+    """rois [K,5] + L channels-last maps -> [K,C,P,P] (roi_level given) or [L,K,C,P,P]."""
+
+    @staticmethod
+    def forward(ctx, rois, roi_level, bias, scales, pooled, sampling_ratio, out_dtype, *feats):
+        _lib.require_cuda(rois, *feats)
+        L, K = len(feats), rois.shape[0]
+        B, C = feats[0].shape[0], feats[0].shape[1]
+        for f in feats:
+            if not _is_cl(f) or f.dtype != feats[0].dtype or f.shape[:2] != feats[0].shape[:2]:
+                raise ValueError('feature maps must be channels-last, same dtype, same [B,C]')
+        rois = rois.detach().float().contiguous()
+        out_dtype = out_dtype or feats[0].dtype
+        lead = (K,) if roi_level is not None else (L, K)
+        out = torch.empty(lead + (pooled, pooled, C), dtype=out_dtype, device=rois.device)
+        bias_shape = None if bias is None else tuple(bias.shape)
+        bias_c = None if bias is None else bias.detach().reshape(B, C).float().contiguous()
+        lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
+        check(lib().htd_roi_align_fwd(lv, L, B, C, dt(feats[0]), ptr(rois), K, ptr(roi_level),
+                                      pooled, sampling_ratio, ptr(bias_c), ptr(out), dt(out),
+                                      stream()), 'htd_roi_align_fwd')
+        boxes = None
+        if any(ctx.needs_input_grad[7:]):      # footprint plan for the gather backward
+            boxes = roi_footprints(feats, scales, rois, roi_level, pooled, sampling_ratio)
+        ctx.save_for_backward(rois, roi_level, boxes)
+        ctx.cfg = (scales, pooled, sampling_ratio, [tuple(f.shape) for f in feats], feats[0].dtype,
+                   bias_shape, B)
+        return out.permute(0, 3, 1, 2) if roi_level is not None else out.permute(0, 1, 4, 2, 3)
+
+    @staticmethod
+    def backward(ctx, g):
+        rois, roi_level, boxes = ctx.saved_tensors
+        scales, pooled, sr, shapes, fdtype, bias_shape, B = ctx.cfg
+        single = roi_level is not None
+        g = (g.permute(0, 2, 3, 1) if single else g.permute(0, 1, 3, 4, 2)).contiguous()
+        dbias = None
+        grads = [None] * len(shapes)
+        if boxes is not None:
+            grads = _roi_align_bwd(shapes, fdtype, scales, rois, boxes, pooled, sr, g,
+                                   dy_per_level=not single)
+        if bias_shape is not None and ctx.needs_input_grad[2]:
+            gb = g if single else g.sum(0)
+            dbias = _bias_grad(gb, rois, B).reshape(bias_shape)
+        return (None, None, dbias, None, None, None, None) + tuple(grads)
+
+
+def roi_align_levels(feats_cl, rois, scales, pooled=7, sampling_ratio=0, roi_level=None, bias=None,
+                     out_dtype=None):
+    out = _RoIAlignLevels.apply(rois, roi_level, bias, tuple(float(s) for s in scales), int(pooled),
+                                int(sampling_ratio), out_dtype, *feats_cl)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# BA: multi-level sample + attention softmax + fuse (+ ring) in one autograd node
+# ------------------------------------------------------------------------------------------
+class _BAFunction(torch.autograd.Function):
+    """AdptRoIExtractor.forward (adaptative_roi_extractor.py:49-91), see csrc/layout_ba.cu.
+
+    Inputs: rois, conv1 weight [128,256,1,1] / bias, conv2 weight [1,128,1,1] / bias, optional
+    residual `add` [K,C,P,P] and SFA `bias` [B,C,1,1] (both folded into the fuse pass), then the
+    L channels-last maps.  Saves R (the L sampled maps) for the backward dot products.
+    """
+
+    @staticmethod
+    def forward(ctx, rois, w1, b1, w2, b2, add, bias, scales, pooled, sampling_ratio, edge, *feats):
+        _lib.require_cuda(rois, *feats)
+        L, K = len(feats), rois.shape[0]
+        B, C = feats[0].shape[0], feats[0].shape[1]
+        PP = pooled * pooled
+        dev = rois.device
+        rois = rois.detach().float().contiguous()
+        fdt = feats[0].dtype
+        R = torch.empty((L, K, pooled, pooled, C), dtype=fdt, device=dev)
+        lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
+        check(lib().htd_roi_align_fwd(lv, L, B, C, dt(fdt), ptr(rois), K, None, pooled,
+                                      sampling_ratio, None, ptr(R), dt(R), stream()),
+              'htd_roi_align_fwd(BA)')
+        m = torch.empty((L * K, C), dtype=torch.float32, device=dev)
+        check(lib().htd_ba_bin_mean(ptr(R), dt(R), L * K, PP, C, ptr(m), stream()),
+              'htd_ba_bin_mean')
+        # attention MLP on the pooled vectors: two plain library GEMMs ([L*K,256]x[256,128], x[128,1])
+        W1 = w1.detach().reshape(w1.shape[0], -1).float()
+        W2 = w2.detach().reshape(1, -1).float()
+        h = torch.tanh(torch.addmm(b1.detach().float(), m, W1.t()))
+        logits = torch.addmm(b2.detach().float(), h, W2.t()).reshape(L, K).contiguous()
+        wts = torch.empty((L, K), dtype=torch.float32, device=dev)
+        out = torch.empty((K, pooled, pooled, C), dtype=fdt, device=dev)
+        add_c = None
+        if add is not None:
+            add_c = add.detach().permute(0, 2, 3, 1).to(fdt).contiguous()
+        bias_c = None if bias is None else bias.detach().reshape(B, C).float().contiguous()
+        check(lib().htd_ba_fuse_fwd(ptr(R), dt(R), ptr(logits), L, K, pooled, C, int(edge),
+                                    ptr(add_c), dt(fdt), ptr(bias_c), ptr(rois), B, ptr(wts),
+                                    ptr(out), dt(out), stream()), 'htd_ba_fuse_fwd')
+        boxes = None
+        if any(ctx.needs_input_grad[11:]):
+            boxes = roi_footprints(feats, scales, rois, None, pooled, sampling_ratio)
+        ctx.save_for_backward(rois, R, m, h, wts, W1, W2, boxes)
+        ctx.cfg = (scales, pooled, sampling_ratio, edge, [tuple(f.shape) for f in feats], fdt, B,
+                   w1.shape, w2.shape, add is not None,
+                   None if bias is None else tuple(bias.shape))
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        rois, R, m, h, wts, W1, W2, boxes = ctx.saved_tensors
+        (scales, pooled, sr, edge, shapes, fdt, B, w1_shape, w2_shape, has_add,
+         bias_shape) = ctx.cfg
+        L, K = wts.shape
+        C = R.shape[-1]
+        PP = pooled * pooled
+        g = g.permute(0, 2, 3, 1).contiguous()
+        da = torch.empty((L, K), dtype=torch.float32, device=g.device)
+        check(lib().htd_ba_fuse_bwd(ptr(R), dt(R), ptr(g), dt(g), ptr(wts), L, K, PP, C, ptr(da),
+                                    stream()), 'htd_ba_fuse_bwd')
+        # backward of the tiny attention MLP (Appendix D of SURVEY.md), plain GEMMs
+        da_f = da.reshape(L * K, 1)
+        dW2 = (da_f * h).sum(0).reshape(w2_shape)
+        db2 = da_f.sum().reshape(1)
+        dpre = (da_f * W2) * (1.0 - h * h)
+        dW1 = (dpre.t() @ m).reshape(w1_shape)
+        db1 = dpre.sum(0)
+        dm = (dpre @ W1) * (1.0 / PP)                      # [L*K, C], gradient of the bin mean
+        grads = [None] * L
+        if boxes is not None:
+            grads = _roi_align_bwd(shapes, fdt, scales, rois, boxes, pooled, sr, g,
+                                   dy_per_level=False, scale=wts, ring_edge=edge,
+                                   addvec=dm.contiguous())
+        dadd = g.permute(0, 3, 1, 2) if (has_add and ctx.needs_input_grad[5]) else None
+        dbias = None
+        if bias_shape is not None and ctx.needs_input_grad[6]:
+            dbias = _bias_grad(g, rois, B).reshape(bias_shape)
+        return (None, dW1, db1, dW2, db2, dadd, dbias, None, None, None, None) + tuple(grads)
+
+
+def ba_extract(feats_cl, rois, scales, conv1, conv2, pooled=7, sampling_ratio=0, edge=1, add=None,
+               bias=None):
+    return _BAFunction.apply(rois, conv1.weight, conv1.bias, conv2.weight, conv2.bias, add, bias,
+                             tuple(float(s) for s in scales), int(pooled), int(sampling_ratio),
+                             int(edge), *feats_cl)

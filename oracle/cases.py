@@ -25,7 +25,8 @@ def case_inputs(name, dtype=torch.float32, device='cpu'):
     c = CASES[name]
     H, W = c['hw']
     x = [t.to(dtype).to(device) for t in synth.make_pyramid(c['B'], H, W, seed=1000 + c['seed'])]
-    props = [p.to(dtype).to(device) for p in synth.make_proposals(
+    pdt = dtype if dtype in (torch.float32, torch.float64) else torch.float32   # boxes stay fp32
+    props = [p.to(pdt).to(device) for p in synth.make_proposals(
         c['B'], c['K'], H, W, seed=1234 + c['seed'], min_scale=c['scales'][0],
         max_scale=c['scales'][1])]
     gts = synth.make_gt(c['B'], [p.float().cpu() for p in props], num_pos=c['P'],

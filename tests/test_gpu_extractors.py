@@ -1,0 +1,194 @@
+"""GPU parity tests (through the C-ABI) of level assignment, multi-level RoIAlign forward /
+atomic-free backward and the BA extractor, against the CPU oracle (fp64) on the same seeded
+inputs and against the golden fixtures generated from the reference.
+
+Tolerances (BASELINE.json north_star / SURVEY F12): indices bit-exact; fp32 features and
+gradients max|a-b|/max|b| <= 1e-5 against the fp64 oracle; bf16 <= 2e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from htd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+TOL_F32, TOL_BF16 = 1e-5, 2e-2
+ROI_LAYER = dict(type='RoIAlign', output_size=7, sampling_ratio=0)
+
+
+class _Ext(nn.Module):
+    def __init__(self):
+        super().__init__()
+        from htd_b200.roi_extractors import AdptRoIExtractor, SingleRoIExtractor
+        self.bbox_roi_extractor = nn.ModuleList([
+            SingleRoIExtractor(dict(ROI_LAYER), 256, [4, 8, 16, 32]),
+            AdptRoIExtractor(edge=1, roi_layer=dict(ROI_LAYER), out_channels=256,
+                             featmap_strides=[4, 8, 16, 32])])
+
+
+def _oracle_outs(name):
+    from oracle import cases, restate
+    c = cases.CASES[name]
+    head = restate.HTDRoIHead().double()
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    return cases.run_extractors(head, name, torch.float64)
+
+
+_ORACLE_CACHE = {}
+
+
+def oracle_outs(name):
+    if name not in _ORACLE_CACHE:
+        _ORACLE_CACHE[name] = _oracle_outs(name)
+    return _ORACLE_CACHE[name]
+
+
+def _product_outs(name, dtype):
+    from oracle import cases
+    c = cases.CASES[name]
+    ext = _Ext()
+    synth.fill_params_(ext, c['scheme'], c['seed'])
+    ext = ext.cuda()
+    return cases.run_extractors(ext, name, dtype, device='cuda')
+
+
+def test_level_assign_bit_exact_golden():
+    from htd_b200 import ops
+    z = np.load(os.path.join(GOLD, 'levels.npz'))
+    rois = torch.from_numpy(z['rois']).cuda()
+    lv = ops.level_assign(rois, 4, 56.0)
+    assert np.array_equal(lv.cpu().numpy().astype(np.int8), z['levels'])
+
+
+@pytest.mark.parametrize('name', ['small', 'mid'])
+def test_extractors_fp32_vs_fp64_oracle_and_golden(name):
+    from oracle import cases
+    got = _product_outs(name, torch.float32)
+    want = oracle_outs(name)
+    assert torch.equal(got['levels'].cpu(), want['levels'])
+    errs = {k: cases.rel_err(got[k], want[k]) for k in want if k != 'levels'}
+    bad = {k: v for k, v in errs.items() if not v <= TOL_F32}
+    assert not bad, bad
+    fix = cases.load_fixture(os.path.join(GOLD, f'{name}_f64.npz'))
+    cases.compare_to_fixture(got, fix, TOL_F32, names=set(want))
+    print({k: f'{v:.1e}' for k, v in errs.items()})
+
+
+@pytest.mark.parametrize('name', ['small'])
+def test_extractors_bf16(name):
+    from oracle import cases
+    got = _product_outs(name, torch.bfloat16)
+    want = oracle_outs(name)
+    errs = {k: cases.rel_err(got[k].float(), want[k]) for k in want if k != 'levels'}
+    bad = {k: v for k, v in errs.items() if not v <= TOL_BF16}
+    assert not bad, bad
+
+
+def test_backward_is_deterministic():
+    a = _product_outs('small', torch.float32)
+    b = _product_outs('small', torch.float32)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def _edge_rois(H, W, stride):
+    return torch.tensor([
+        [0, 10.3, 7.9, 60.2, 51.1], [0, -20.0, -14.0, 30.0, 25.0],
+        [1, W * stride - 30.0, H * stride - 20.0, W * stride + 90.0, H * stride + 70.0],
+        [1, 33.0, 21.0, 33.0, 21.0], [0, 0.0, 0.0, W * stride, H * stride],
+        [1, 50.0, 40.0, 52.5, 41.0], [0, 70.0, 30.0, 20.0, 10.0],
+        [0, -500.0, -500.0, -300.0, -300.0], [1, -1e4, -1e4, 1e4, 1e4],
+        [1, 3.0, 5.0, 3.0 + 7 * stride, 5.0 + 14 * stride]])
+
+
+@pytest.mark.parametrize('C,stride,sr', [(256, 4, 0), (64, 8, 0), (40, 16, 2), (512, 4, 0)])
+def test_roialign_module_edge_cases(C, stride, sr):
+    """mmcv.ops.RoIAlign drop-in: NCHW in, contiguous NCHW out; empty / degenerate / outside /
+    whole-image RoIs; C not a multiple of 256; fixed sampling_ratio."""
+    from htd_b200.roi_extractors import RoIAlign
+    from oracle import cases, restate
+    H, W = 23, 37
+    g = torch.Generator().manual_seed(C + stride)
+    x = torch.randn(2, C, H, W, generator=g)
+    rois = _edge_rois(H, W, stride)
+    if sr > 0:
+        rois = rois[(rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])]
+    xo = x.double().requires_grad_(True)
+    yo = restate.RoIAlign(7, 1.0 / stride, sr)(xo, rois.double())
+    dy = torch.randn(yo.shape, generator=g)
+    gxo, = torch.autograd.grad((yo * dy.double()).sum(), xo)
+    xg = x.cuda().requires_grad_(True)
+    layer = RoIAlign(7, 1.0 / stride, sr)
+    yg = layer(xg, rois.cuda())
+    assert yg.is_contiguous() and yg.shape == yo.shape
+    gxg, = torch.autograd.grad((yg * dy.cuda()).sum(), xg)
+    assert gxg.shape == x.shape
+    assert cases.rel_err(yg, yo) <= TOL_F32
+    assert cases.rel_err(gxg, gxo) <= TOL_F32
+    # empty roi set
+    ye = layer(xg, torch.zeros(0, 5, device='cuda'))
+    assert ye.shape == (0, C, 7, 7)
+
+
+def test_sfa_bias_fused_and_bias_grad():
+    from htd_b200 import ops
+    from oracle import cases
+    c, x, props, gts, shapes = cases.case_inputs('small', torch.float32, 'cuda')
+    rois = cases._rois(props)
+    ext = _Ext().cuda().bbox_roi_extractor[0]
+    bias = torch.randn(c['B'], 256, 1, 1, device='cuda', requires_grad=True)
+    xs = [t.clone().requires_grad_(True) for t in x[:4]]
+    y0 = ext(xs, rois)
+    y1 = ext(xs, rois, bias=bias)
+    want = y0 + bias[rois[:, 0].long()]
+    assert cases.rel_err(y1, want) <= 1e-6
+    dy = torch.randn_like(y1)
+    gb, = torch.autograd.grad((y1 * dy).sum(), bias)
+    wb = torch.zeros_like(bias).index_add_(0, rois[:, 0].long(), dy.sum((2, 3), keepdim=True))
+    assert cases.rel_err(gb, wb) <= 1e-5
+
+
+def test_layout_roundtrip():
+    from htd_b200 import ops
+    x = torch.randn(3, 72, 19, 45, device='cuda', requires_grad=True)
+    y = ops.to_channels_last(x, torch.float32)
+    assert y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, x)
+    g = torch.randn_like(x)
+    gx, = torch.autograd.grad((y * g).sum(), x)
+    assert torch.equal(gx, g) and gx.is_contiguous()
+    yb = ops.to_channels_last(x, torch.bfloat16)
+    assert torch.equal(yb, x.to(torch.bfloat16))
+
+
+def test_full_size_forward_properties():
+    """BASELINE config sizes (800x1333, 512 RoIs): linearity in the features and agreement of
+    the single-level extractor with the all-level sampler on the assigned level; oracle compare
+    on a bounded subset."""
+    from htd_b200 import ops
+    from oracle import cases, restate
+    x = [t.cuda() for t in synth.make_pyramid(1)[:4]]
+    props = synth.make_proposals(1, 512)
+    rois = cases._rois(props).cuda()
+    ext = _Ext().cuda()
+    e0 = ext.bbox_roi_extractor[0]
+    y = e0(x, rois)
+    y2 = e0([2.0 * t for t in x], rois)
+    assert cases.rel_err(y2, 2.0 * y) <= 1e-6
+    xcl = [ops.to_channels_last(t) for t in x]
+    allv = ops.roi_align_levels(xcl, rois, [0.25, 0.125, 0.0625, 0.03125])
+    lv = e0.map_roi_levels(rois, 4)
+    pick = allv[lv, torch.arange(rois.shape[0], device='cuda')]
+    assert torch.equal(pick, y)
+    sub = torch.arange(0, 512, 16)
+    ref = restate.SingleRoIExtractor()([t.cpu().double() for t in x], rois.cpu().double()[sub])
+    assert cases.rel_err(y[sub.cuda()], ref) <= TOL_F32
+
+
+def test_library_has_no_cpu_path():
+    from htd_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.level_assign(torch.zeros(4, 5), 4)
