@@ -18,6 +18,14 @@ _DT = {torch.float32: HTD_F32, torch.bfloat16: HTD_BF16}
 c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 
 
+class HtdGemmGroup(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('M', 'N', 'K', 'a_row', 'a_k0', 'b_row', 'b_k0',
+                                               'd_row', 'd_col', 'dt_row', 'dt_col', 'bias_off')]
+
+
+MAX_GROUPS = 64
+
+
 class HtdLevel(ctypes.Structure):
     _fields_ = [('data', c_void_p), ('H', ctypes.c_int32), ('W', ctypes.c_int32),
                 ('spatial_scale', c_float), ('reserved', ctypes.c_int32)]
@@ -41,18 +49,49 @@ SIGNATURES = {
                         c_void_p, c_void_p],
     'htd_bias_grad': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                       c_void_p],
-    'htd_iou_graph_build': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                            c_void_p, c_void_p],
-    'htd_pgraph_local_adj': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
-    'htd_pgraph_masked_softmax': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
-                                  c_void_p, c_void_p],
-    'htd_pgraph_softmax_bwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
-                               c_void_p],
-    'htd_pgraph_gemm': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                        c_int, c_int, c_int, c_void_p],
+    'htd_pgraph_plan': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                        c_void_p, c_void_p, c_void_p, c_void_p],
+    'htd_pgraph_pack': [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_void_p, c_int, c_int,
+                        c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p],
+    'htd_iou_graph_build': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                            c_ll, c_void_p],
+    'htd_pgraph_masked_softmax': [c_void_p, c_ll, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                  c_ll, c_void_p],
+    'htd_pgraph_softmax_bwd': [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_int, c_void_p,
+                               c_int, c_void_p, c_ll, c_void_p],
+    'htd_pgraph_group_transpose': [c_void_p, c_int, c_ll, c_void_p, c_int, c_float, c_float,
+                                   c_void_p, c_int, c_ll, c_void_p],
+    'htd_pgraph_segment_colsum': [c_void_p, c_int, c_ll, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    'htd_pgraph_gemm': [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int,
+                        c_void_p, c_int, c_ll, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_int,
+                        c_void_p],
 }
 
 _lib = None
+
+# kernels launched by each entry point (for the bench's `gpu_launches` count)
+KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2}
+LAUNCHES = {'total': 0, 'by_entry': {}}
+
+
+class _Counted:
+    """Thin proxy over the CDLL that counts kernel launches per C-ABI entry point."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if name not in SIGNATURES:
+            return fn
+        n = KERNELS_PER_CALL.get(name, 1)
+
+        def call(*args):
+            LAUNCHES['total'] += n
+            LAUNCHES['by_entry'][name] = LAUNCHES['by_entry'].get(name, 0) + n
+            return fn(*args)
+        setattr(self, name, call)
+        return call
 
 
 def lib():
@@ -67,11 +106,12 @@ def lib():
         L.htd_abi_version.restype = c_int
         for name, args in SIGNATURES.items():
             if not hasattr(L, name):
-                continue
+                raise RuntimeError(f'{LIB_PATH} does not export {name}: rebuild it '
+                                   '(`python -m htd_b200.build --force`)')
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = c_int
-        _lib = L
+        _lib = _Counted(L)
     return _lib
 
 
@@ -113,3 +153,49 @@ def make_levels(tensors_bhwc, scales):
         arr[i].spatial_scale = float(s)
         arr[i].reserved = 0
     return arr
+
+
+# ----------------------------------------------------------------------------------------------
+# optional per-kernel instrumentation used by bench.py (off by default: zero overhead)
+# ----------------------------------------------------------------------------------------------
+class KernelTimer:
+    """CUDA-event timing of individual launches on the current stream.  ``timer.time(name)`` is a
+    context manager; ``summary()`` (after a synchronize) gives {name: (launches, total_ms)}."""
+
+    def __init__(self):
+        self.events = {}
+
+    def time(self, name):
+        timer = self
+
+        class _Ctx:
+            def __enter__(self_):
+                self_.a = torch.cuda.Event(enable_timing=True)
+                self_.b = torch.cuda.Event(enable_timing=True)
+                self_.a.record()
+
+            def __exit__(self_, *exc):
+                self_.b.record()
+                timer.events.setdefault(name, []).append((self_.a, self_.b))
+                return False
+        return _Ctx()
+
+    def summary(self):
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+TIMER = None          # set to a KernelTimer to time launches
+ACCOUNT = None        # set to a list to collect (name, algorithmic bytes or flops) per launch
+_NULL = _Null()
+
+
+def timed(name):
+    return TIMER.time(name) if TIMER is not None else _NULL

@@ -1,0 +1,391 @@
+"""Box heads of the HTD RoI head - host-side mirror of the reference plugin surface.
+
+  BBoxHead            mmdet/models/roi_heads/bbox_heads/bbox_head.py
+  Shared2FCBBoxHead   .../convfc_bbox_head.py:176-189 (ConvFCBBoxHead with 2 shared FCs)
+  HTDBBoxHead         .../htd_bbox_head.py   (PGraph cls branch + BA/SFA reg branch)
+  GlobalContextHead   .../global_context_head.py:323-401 (SFA)
+
+Same constructor arguments, forward signatures and state-dict keys as the reference, so
+``configs/htd/*.py`` build them unchanged and released checkpoints load.  The dense library work
+(FC stacks, the 3x3 conv tower, GroupNorm) stays in cuBLAS/cuDNN through PyTorch; the graph part
+of HTDBBoxHead runs on this package's kernels (``htd_b200.pgraph``), and feature fusion is folded
+into the extraction kernels where the caller allows it.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.modules.utils import _pair
+
+from . import ops, pgraph
+from .core import accuracy, as_cfg, multiclass_nms
+from .registry import HEADS, build_bbox_coder, build_loss
+
+
+class ConvModule(nn.Module):
+    """The subset of mmcv.cnn.ConvModule the path uses: conv -> (GN) -> ReLU, bias='auto'
+    (no conv bias when a norm layer follows); sub-module names ``conv`` / ``gn`` as in mmcv."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias='auto',
+                 conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU')):
+        super().__init__()
+        if conv_cfg is not None:
+            raise NotImplementedError('plain Conv2d only')
+        with_norm = norm_cfg is not None
+        if bias == 'auto':
+            bias = not with_norm
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')
+        if bias:
+            nn.init.constant_(self.conv.bias, 0)
+        self.gn = None
+        if with_norm:
+            if norm_cfg['type'] != 'GN':
+                raise NotImplementedError('GroupNorm only (htd_bbox_head.py:48)')
+            self.gn = nn.GroupNorm(norm_cfg['num_groups'], out_channels)
+        self.with_act = act_cfg is not None
+
+    def forward(self, x):
+        x = self.conv(x)
+        if self.gn is not None:
+            x = self.gn(x)
+        return F.relu(x, inplace=True) if self.with_act else x
+
+
+@HEADS.register_module()
+class BBoxHead(nn.Module):
+    """bbox_head.py:12-335."""
+
+    def __init__(self, with_avg_pool=False, with_cls=True, with_reg=True, roi_feat_size=7,
+                 in_channels=256, num_classes=80,
+                 bbox_coder=dict(type='DeltaXYWHBBoxCoder', clip_border=True,
+                                 target_means=[0., 0., 0., 0.], target_stds=[0.1, 0.1, 0.2, 0.2]),
+                 reg_class_agnostic=False, reg_decoded_bbox=False,
+                 loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=False, loss_weight=1.0),
+                 loss_bbox=dict(type='SmoothL1Loss', beta=1.0, loss_weight=1.0)):
+        super().__init__()
+        assert with_cls or with_reg
+        self.with_avg_pool, self.with_cls, self.with_reg = with_avg_pool, with_cls, with_reg
+        self.roi_feat_size = _pair(roi_feat_size)
+        self.roi_feat_area = self.roi_feat_size[0] * self.roi_feat_size[1]
+        self.in_channels, self.num_classes = in_channels, num_classes
+        self.reg_class_agnostic, self.reg_decoded_bbox = reg_class_agnostic, reg_decoded_bbox
+        self.fp16_enabled = False
+        self.bbox_coder = build_bbox_coder(bbox_coder)
+        self.loss_cls = build_loss(loss_cls)
+        self.loss_bbox = build_loss(loss_bbox)
+        in_ch = in_channels
+        if with_avg_pool:
+            self.avg_pool = nn.AvgPool2d(self.roi_feat_size)
+        else:
+            in_ch *= self.roi_feat_area
+        if with_cls:
+            self.fc_cls = nn.Linear(in_ch, num_classes + 1)
+        if with_reg:
+            self.fc_reg = nn.Linear(in_ch, 4 if reg_class_agnostic else 4 * num_classes)
+
+    def init_weights(self):
+        if self.with_cls:
+            nn.init.normal_(self.fc_cls.weight, 0, 0.01)
+            nn.init.constant_(self.fc_cls.bias, 0)
+        if self.with_reg:
+            nn.init.normal_(self.fc_reg.weight, 0, 0.001)
+            nn.init.constant_(self.fc_reg.bias, 0)
+
+    def forward(self, x):
+        if self.with_avg_pool:
+            x = self.avg_pool(x)
+        x = x.reshape(x.size(0), -1)
+        return (self.fc_cls(x) if self.with_cls else None,
+                self.fc_reg(x) if self.with_reg else None)
+
+    # ---- targets / loss (bbox_head.py:85-186) -------------------------------------------------
+    def _get_target_single(self, pos_bboxes, neg_bboxes, pos_gt_bboxes, pos_gt_labels, cfg):
+        num_pos, num_neg = pos_bboxes.size(0), neg_bboxes.size(0)
+        n = num_pos + num_neg
+        labels = pos_bboxes.new_full((n,), self.num_classes, dtype=torch.long)
+        label_weights = pos_bboxes.new_zeros(n)
+        bbox_targets = pos_bboxes.new_zeros(n, 4)
+        bbox_weights = pos_bboxes.new_zeros(n, 4)
+        if num_pos > 0:
+            labels[:num_pos] = pos_gt_labels
+            pw = cfg.get('pos_weight', -1) if cfg is not None else -1
+            label_weights[:num_pos] = 1.0 if pw <= 0 else pw
+            bbox_targets[:num_pos] = pos_gt_bboxes if self.reg_decoded_bbox else \
+                self.bbox_coder.encode(pos_bboxes, pos_gt_bboxes).to(bbox_targets.dtype)
+            bbox_weights[:num_pos] = 1
+        if num_neg > 0:
+            label_weights[-num_neg:] = 1.0
+        return labels, label_weights, bbox_targets, bbox_weights
+
+    def get_targets(self, sampling_results, gt_bboxes, gt_labels, rcnn_train_cfg, concat=True):
+        cfg = as_cfg(rcnn_train_cfg)
+        outs = [self._get_target_single(r.pos_bboxes, r.neg_bboxes, r.pos_gt_bboxes,
+                                        r.pos_gt_labels, cfg) for r in sampling_results]
+        cols = list(zip(*outs))
+        return tuple(torch.cat(c, 0) for c in cols) if concat else tuple(list(c) for c in cols)
+
+    def loss(self, cls_score, bbox_pred, rois, labels, label_weights, bbox_targets, bbox_weights,
+             reduction_override=None):
+        losses = dict()
+        if cls_score is not None:
+            cls_score = cls_score.float()                      # force_fp32 (bbox_head.py:141)
+            avg_factor = max(torch.sum(label_weights > 0).float().item(), 1.)
+            if cls_score.numel() > 0:
+                losses['loss_cls'] = self.loss_cls(cls_score, labels, label_weights,
+                                                   avg_factor=avg_factor,
+                                                   reduction_override=reduction_override)
+                losses['acc'] = accuracy(cls_score, labels)
+        if bbox_pred is not None:
+            bbox_pred = bbox_pred.float()
+            pos = (labels >= 0) & (labels < self.num_classes)
+            if pos.any():
+                if self.reg_decoded_bbox:
+                    bbox_pred = self.bbox_coder.decode(rois[:, 1:], bbox_pred)
+                if self.reg_class_agnostic:
+                    pos_pred = bbox_pred.view(bbox_pred.size(0), 4)[pos]
+                else:
+                    pos_pred = bbox_pred.view(bbox_pred.size(0), -1, 4)[pos, labels[pos]]
+                losses['loss_bbox'] = self.loss_bbox(pos_pred, bbox_targets[pos].float(),
+                                                     bbox_weights[pos].float(),
+                                                     avg_factor=bbox_targets.size(0),
+                                                     reduction_override=reduction_override)
+            else:
+                losses['loss_bbox'] = bbox_pred[pos].sum()
+        return losses
+
+    # ---- decoding (bbox_head.py:188-335) ------------------------------------------------------
+    def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False,
+                   cfg=None):
+        if isinstance(cls_score, list):
+            cls_score = sum(cls_score) / float(len(cls_score))
+        scores = F.softmax(cls_score.float(), dim=1) if cls_score is not None else None
+        if bbox_pred is not None:
+            bboxes = self.bbox_coder.decode(rois[:, 1:].float(), bbox_pred.float(),
+                                            max_shape=img_shape)
+        else:
+            bboxes = rois[:, 1:].clone()
+            if img_shape is not None:
+                bboxes[:, [0, 2]] = bboxes[:, [0, 2]].clamp(min=0, max=img_shape[1])
+                bboxes[:, [1, 3]] = bboxes[:, [1, 3]].clamp(min=0, max=img_shape[0])
+        if rescale and bboxes.size(0) > 0:
+            if isinstance(scale_factor, float):
+                bboxes = bboxes / scale_factor
+            else:
+                sf = bboxes.new_tensor(scale_factor)
+                bboxes = (bboxes.view(bboxes.size(0), -1, 4) / sf).view(bboxes.size(0), -1)
+        if cfg is None:
+            return bboxes, scores
+        cfg = as_cfg(cfg)
+        return multiclass_nms(bboxes, scores, cfg.score_thr, cfg.nms, cfg.max_per_img)
+
+    def regress_by_class(self, rois, label, bbox_pred, img_meta):
+        assert rois.size(1) in (4, 5), repr(rois.shape)
+        bbox_pred = bbox_pred.float()
+        if not self.reg_class_agnostic:
+            label = label * 4
+            inds = torch.stack((label, label + 1, label + 2, label + 3), 1)
+            bbox_pred = torch.gather(bbox_pred, 1, inds)
+        assert bbox_pred.size(1) == 4
+        if rois.size(1) == 4:
+            return self.bbox_coder.decode(rois, bbox_pred, max_shape=img_meta['img_shape'])
+        boxes = self.bbox_coder.decode(rois[:, 1:], bbox_pred, max_shape=img_meta['img_shape'])
+        return torch.cat((rois[:, [0]], boxes), dim=1)
+
+    def refine_bboxes(self, rois, labels, bbox_preds, pos_is_gts, img_metas):
+        out = []
+        for i in range(len(img_metas)):
+            inds = torch.nonzero(rois[:, 0] == i, as_tuple=False).squeeze(dim=1)
+            boxes = self.regress_by_class(rois[inds, 1:], labels[inds], bbox_preds[inds],
+                                          img_metas[i])
+            keep = pos_is_gts[i].new_ones(inds.numel())
+            keep[:len(pos_is_gts[i])] = 1 - pos_is_gts[i]
+            out.append(boxes[keep.type(torch.bool)])
+        return out
+
+
+@HEADS.register_module()
+class ConvFCBBoxHead(BBoxHead):
+    """convfc_bbox_head.py:9-173 restricted to what HTD instantiates: shared FCs only."""
+
+    def __init__(self, num_shared_convs=0, num_shared_fcs=0, num_cls_convs=0, num_cls_fcs=0,
+                 num_reg_convs=0, num_reg_fcs=0, conv_out_channels=256, fc_out_channels=1024,
+                 conv_cfg=None, norm_cfg=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if num_shared_convs or num_cls_convs or num_cls_fcs or num_reg_convs or num_reg_fcs:
+            raise NotImplementedError('HTD stage 0 is Shared2FCBBoxHead (shared FCs only)')
+        assert num_shared_fcs > 0 and not self.with_avg_pool
+        self.num_shared_fcs, self.fc_out_channels = num_shared_fcs, fc_out_channels
+        self.shared_fcs = nn.ModuleList()
+        last = self.in_channels * self.roi_feat_area
+        for _ in range(num_shared_fcs):
+            self.shared_fcs.append(nn.Linear(last, fc_out_channels))
+            last = fc_out_channels
+        if self.with_cls:
+            self.fc_cls = nn.Linear(last, self.num_classes + 1)
+        if self.with_reg:
+            self.fc_reg = nn.Linear(last, 4 if self.reg_class_agnostic else 4 * self.num_classes)
+
+    def init_weights(self):
+        super().init_weights()
+        for m in self.shared_fcs:
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.constant_(m.bias, 0)
+
+    def forward(self, x):
+        x = x.flatten(1)
+        for fc in self.shared_fcs:
+            x = F.relu(fc(x))
+        return (self.fc_cls(x) if self.with_cls else None,
+                self.fc_reg(x) if self.with_reg else None)
+
+
+@HEADS.register_module()
+class Shared2FCBBoxHead(ConvFCBBoxHead):
+
+    def __init__(self, fc_out_channels=1024, *args, **kwargs):
+        super().__init__(num_shared_fcs=2, fc_out_channels=fc_out_channels, *args, **kwargs)
+
+
+@HEADS.register_module()
+class HTDBBoxHead(BBoxHead):
+    """htd_bbox_head.py:24-230.  cls branch: 2 FCs + PGraph; reg branch: RoI feature + SFA + BA
+    feature -> 4 convs (GN-36) -> avg-pool -> fc_reg."""
+
+    def __init__(self, num_shared_convs=0, num_shared_fcs=0, num_cls_convs=0, num_cls_fcs=2,
+                 num_reg_convs=4, num_reg_fcs=0, alpha=1, relpace=False, average=False, edge=1,
+                 conv_out_channels=256, fc_out_channels=1024, conv_cfg=None,
+                 norm_cfg=dict(type='GN', num_groups=36), *args, **kwargs):
+        kwargs.setdefault('with_avg_pool', True)
+        super().__init__(*args, **kwargs)
+        if relpace or average:
+            raise NotImplementedError('configs/htd use relpace=False, average=False')
+        self.num_cls_fcs, self.num_reg_convs = num_cls_fcs, num_reg_convs
+        self.alpha, self.relpace, self.average, self.edge = alpha, relpace, average, edge
+        self.conv_out_channels = self.fc_out_channels = 1024
+        self.gcn_in = self.gcn_out = 1024
+        self.norm_cfg = norm_cfg
+        self.fc_cls = nn.Linear(self.fc_out_channels, self.num_classes + 1)
+        self.fc_reg = nn.Linear(self.conv_out_channels, 4)
+        mid = self.middle_channel = 16 * 36
+        convs = []
+        for i in range(num_reg_convs):
+            cin = self.in_channels if i == 0 else mid
+            last = (i == num_reg_convs - 1)
+            convs.append(ConvModule(cin, 1024 if last else mid, 3, padding=1, conv_cfg=conv_cfg,
+                                    norm_cfg=None if last else norm_cfg, bias=False))
+        self.convs = nn.Sequential(*convs)
+        fcs = []
+        for i in range(num_cls_fcs):
+            fcs += [nn.Linear(self.in_channels * self.roi_feat_area if i == 0
+                              else self.fc_out_channels, self.fc_out_channels), nn.ReLU(inplace=True)]
+        self.fcs = nn.Sequential(*fcs)
+        self.avg_pool = nn.AvgPool2d(self.roi_feat_size)
+        for i in range(4):
+            setattr(self, f'graph_lvl{i}_cls', nn.Linear(self.gcn_in, self.gcn_out))
+        self.finest_scale = 56
+        self.last_plan = None            # GraphPlan of the latest forward (inspection / tests)
+
+    @property
+    def graph_layer_cls(self):
+        return [getattr(self, f'graph_lvl{i}_cls') for i in range(4)]
+
+    def init_weights(self):
+        super().init_weights()
+        nn.init.normal_(self.fc_cls.weight, 0, 0.01)
+        nn.init.normal_(self.fc_reg.weight, 0, 0.001)
+        for m in list(self.fcs.modules()) + self.graph_layer_cls:
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def map_roi_levels(self, rois, num_levels):
+        """htd_bbox_head.py:129-135 (bit-exact level index, int64 like the reference)."""
+        return ops.level_assign(rois, num_levels, self.finest_scale).long()
+
+    @staticmethod
+    def _img_index(rois, num_imgs):
+        return rois[:, 0].long().clamp_(0, num_imgs - 1)
+
+    def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
+                global_feat=None, num_imgs=None):
+        """Reference signature (htd_bbox_head.py:157).  ``num_imgs`` (optional) avoids the host
+        sync of ``int(max(rois[:,0])) + 1`` (:159); ``global_feat`` gives it otherwise."""
+        if num_imgs is None:
+            num_imgs = global_feat.size(0) if global_feat is not None \
+                else int(torch.max(rois[..., 0])) + 1
+        d = self.fc_out_channels
+        prototype = torch.cat((fc_cls_0.weight, fc_cls_0.bias.unsqueeze(1)), 1).detach()
+        # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool (:161-189)
+        if global_feat is not None:
+            g = global_feat.reshape(global_feat.size(0), -1)
+            x_reg = x_reg + g[self._img_index(pos_rois, g.size(0))][:, :, None, None]
+        x_reg = x_reg + self.alpha * enhanced_feat
+        x_reg = self.convs(x_reg.contiguous(memory_format=torch.channels_last))
+        x_reg = self.avg_pool(x_reg).reshape(x_reg.size(0), -1)
+        # ---- cls branch: fcs on x_cls and on x_cls + SFA.  fcs.0 is linear, so
+        # fcs.0(x + g (x) 1_49) = fcs.0(x) + g W_sum^T with W_sum = sum of W over the 49 bins:
+        # one [K,12544]x[12544,1024] GEMM instead of the reference's two (:164 and :192).
+        fc0, fc1 = self.fcs[0], self.fcs[2]
+        pre = fc0(x_cls.flatten(1))
+        x_c = F.relu(fc1(F.relu(pre)))
+        x_glb = None
+        if global_feat is not None:
+            w_sum = fc0.weight.view(d, self.in_channels, self.roi_feat_area).sum(-1)
+            corr = g.to(w_sum.dtype) @ w_sum.t()
+            x_glb = F.relu(fc1(F.relu(pre + corr[self._img_index(rois, g.size(0))])))
+        # ---- semantic vectors and the graph (:194-219)
+        sam = torch.mm(fc_cls_0(x_c).softmax(-1), prototype)
+        with torch.no_grad():
+            levels = ops.level_assign(rois, len(feat), self.finest_scale)
+            plan = pgraph.GraphPlan(rois, levels, num_imgs, len(feat), x_c.dtype)
+        self.last_plan = plan
+        layers = self.graph_layer_cls
+        refined = pgraph.pgraph_refine(x_c, sam, [m.weight for m in layers],
+                                       [m.bias for m in layers], plan)
+        feat_cls_new = (x_glb if x_glb is not None else x_c) + refined
+        cls_score = self.fc_cls(feat_cls_new) if self.with_cls else None
+        bbox_pred = self.fc_reg(x_reg) if self.with_reg else None
+        return cls_score, bbox_pred
+
+
+@HEADS.register_module()
+class GlobalContextHead(nn.Module):
+    """SFA, global_context_head.py:323-401: convs on the LAST pyramid level -> global average
+    pool -> [B,C,1,1] context vector (+ multi-label logits and BCE loss)."""
+
+    def __init__(self, num_ins, num_convs=4, in_channels=256, conv_out_channels=256,
+                 num_classes=81, loss_weight=1.0, conv_cfg=None, norm_cfg=None, conv_to_res=False):
+        super().__init__()
+        if conv_to_res:
+            raise NotImplementedError('HTD builds GlobalContextHead with conv_to_res=False')
+        self.num_ins, self.num_convs = num_ins, num_convs
+        self.in_channels, self.conv_out_channels = in_channels, conv_out_channels
+        self.num_classes, self.loss_weight = num_classes, loss_weight
+        self.fp16_enabled = False
+        self.convs = nn.ModuleList([
+            ConvModule(in_channels if i == 0 else conv_out_channels, conv_out_channels, 3,
+                       padding=1, conv_cfg=conv_cfg, norm_cfg=norm_cfg) for i in range(num_convs)])
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(conv_out_channels, num_classes)
+        self.criterion = nn.BCEWithLogitsLoss()
+
+    def init_weights(self):
+        nn.init.normal_(self.fc.weight, 0, 0.01)
+        nn.init.constant_(self.fc.bias, 0)
+
+    def forward(self, feats):
+        x = feats[-1]
+        w = self.convs[0].conv.weight
+        if x.dtype != w.dtype:
+            x = x.to(w.dtype)
+        for conv in self.convs:
+            x = conv(x)
+        x = self.pool(x)
+        return self.fc(x.reshape(x.size(0), -1)), x
+
+    def loss(self, pred, labels):
+        pred = pred.float()
+        targets = pred.new_zeros(pred.size())
+        for i, label in enumerate(labels):
+            targets[i, label.unique()] = 1.0
+        return self.loss_weight * self.criterion(pred, targets)

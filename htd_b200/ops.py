@@ -97,11 +97,41 @@ def _roi_align_bwd(feat_shapes, feat_dtype, scales, rois, boxes, pooled, samplin
     B, C = feat_shapes[0][0], feat_shapes[0][1]
     bufs = [torch.empty((B, s[2], s[3], C), dtype=feat_dtype, device=dev) for s in feat_shapes]
     lv = _lib.make_levels(bufs, scales)
-    check(lib().htd_roi_align_bwd(lv, L, B, C, dt(feat_dtype), ptr(rois), rois.shape[0],
-                                  ptr(boxes), pooled, sampling_ratio, ptr(dy), dt(dy),
-                                  int(bool(dy_per_level)), ptr(scale), int(ring_edge), ptr(addvec),
-                                  stream()), 'htd_roi_align_bwd')
+    name = 'roi_align_bwd(BA)' if scale is not None else 'roi_align_bwd(single)'
+    if _lib.ACCOUNT is not None:      # 49*C*b_out + fh*fw*C*4 per (RoI, level)
+        px = _count_pixels(bufs, scales, rois, boxes)
+        n_dy = dy.numel() * dy.element_size()
+        _lib.ACCOUNT.append((name, n_dy + px * C * 4))
+    with _lib.timed(name):
+        check(lib().htd_roi_align_bwd(lv, L, B, C, dt(feat_dtype), ptr(rois), rois.shape[0],
+                                      ptr(boxes), pooled, sampling_ratio, ptr(dy), dt(dy),
+                                      int(bool(dy_per_level)), ptr(scale), int(ring_edge),
+                                      ptr(addvec), stream()), 'htd_roi_align_bwd')
     return [b.permute(0, 3, 1, 2) for b in bufs]
+
+
+def _count_pixels(bufs_bhwc, scales, rois, boxes):
+    """Sum of footprint pixels fh*fw over all (level, RoI) of a footprint plan."""
+    bx = boxes.reshape(-1, 4).long()
+    h = (bx[:, 1] - bx[:, 0] + 1).clamp(min=0)
+    w = (bx[:, 3] - bx[:, 2] + 1).clamp(min=0)
+    return int((h * w).sum().item())
+
+
+def _fwd_launch(name, feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out):
+    L, K = len(feats), rois.shape[0]
+    B, C = feats[0].shape[0], feats[0].shape[1]
+    lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
+    if _lib.ACCOUNT is not None:      # fh*fw*C*b_in + 49*C*b_out + 20 per (RoI, level)
+        boxes = roi_footprints(feats, scales, rois, roi_level, pooled, sampling_ratio)
+        px = _count_pixels(None, scales, rois, boxes)
+        tasks = K if roi_level is not None else K * L
+        _lib.ACCOUNT.append((name, px * C * feats[0].element_size() +
+                             out.numel() * out.element_size() + 20 * tasks))
+    with _lib.timed(name):
+        check(lib().htd_roi_align_fwd(lv, L, B, C, dt(feats[0]), ptr(rois), K, ptr(roi_level),
+                                      pooled, sampling_ratio, ptr(bias_c), ptr(out), dt(out),
+                                      stream()), 'htd_roi_align_fwd')
 
 
 def _bias_grad(g_kppc, rois, B):
@@ -131,10 +161,8 @@ class _RoIAlignLevels(torch.autograd.Function):
         out = torch.empty(lead + (pooled, pooled, C), dtype=out_dtype, device=rois.device)
         bias_shape = None if bias is None else tuple(bias.shape)
         bias_c = None if bias is None else bias.detach().reshape(B, C).float().contiguous()
-        lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
-        check(lib().htd_roi_align_fwd(lv, L, B, C, dt(feats[0]), ptr(rois), K, ptr(roi_level),
-                                      pooled, sampling_ratio, ptr(bias_c), ptr(out), dt(out),
-                                      stream()), 'htd_roi_align_fwd')
+        _fwd_launch('roi_align_fwd(single)' if roi_level is not None else 'roi_align_fwd(all)',
+                    feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out)
         boxes = None
         if any(ctx.needs_input_grad[7:]):      # footprint plan for the gather backward
             boxes = roi_footprints(feats, scales, rois, roi_level, pooled, sampling_ratio)
@@ -188,10 +216,7 @@ class _BAFunction(torch.autograd.Function):
         rois = rois.detach().float().contiguous()
         fdt = feats[0].dtype
         R = torch.empty((L, K, pooled, pooled, C), dtype=fdt, device=dev)
-        lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
-        check(lib().htd_roi_align_fwd(lv, L, B, C, dt(fdt), ptr(rois), K, None, pooled,
-                                      sampling_ratio, None, ptr(R), dt(R), stream()),
-              'htd_roi_align_fwd(BA)')
+        _fwd_launch('roi_align_fwd(BA)', feats, scales, rois, None, pooled, sampling_ratio, None, R)
         m = torch.empty((L * K, C), dtype=torch.float32, device=dev)
         check(lib().htd_ba_bin_mean(ptr(R), dt(R), L * K, PP, C, ptr(m), stream()),
               'htd_ba_bin_mean')

@@ -1,0 +1,213 @@
+"""HTDRoIHead - host-side mirror of ``mmdet/models/roi_heads/htd_roi_head.py``.
+
+Two stages plus SFA:  stage 0 = SingleRoIExtractor + Shared2FCBBoxHead (common head), box
+refinement, stage 1 = SingleRoIExtractor (cls) + AdptRoIExtractor/BA (reg) + HTDBBoxHead
+(PGraph).  Same constructor arguments, method names, result-dict keys and loss keys as the
+reference.  Differences (documented in DESIGN.md):
+  * the pyramid is converted ONCE per call to the channels-last layout the kernels read and
+    shared by the three extractor calls (the reference re-reads NCHW maps 13 times);
+  * ``_fuse_global`` (htd_roi_head.py:133-141) is folded into the stage-0 extraction launch;
+  * stage-1 training gathers the positive prefix of EVERY image's block (the reference
+    hard-codes <= 2 images per GPU, htd_roi_head.py:157-170,180-182 - same result for B <= 2).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .core import as_cfg, bbox2result, bbox2roi
+from .registry import HEADS, build_assigner, build_head, build_roi_extractor, build_sampler
+
+
+@HEADS.register_module()
+class HTDRoIHead(nn.Module):
+
+    def __init__(self, num_stages, stage_loss_weights, with_global=False, bbox_roi_extractor=None,
+                 bbox_head=None, mask_roi_extractor=None, mask_head=None, shared_head=None,
+                 train_cfg=None, test_cfg=None, compute_dtype=None):
+        super().__init__()
+        assert bbox_roi_extractor is not None and bbox_head is not None
+        assert shared_head is None, 'Shared head is not supported'
+        if mask_head is not None or mask_roi_extractor is not None:
+            raise NotImplementedError('configs/htd define no mask branch')
+        self.num_stages = num_stages
+        self.stage_loss_weights = stage_loss_weights
+        self.with_global = with_global
+        self.train_cfg = as_cfg(train_cfg)
+        self.test_cfg = as_cfg(test_cfg)
+        self.compute_dtype = compute_dtype       # dtype of the channels-last pyramid copy
+        self.init_bbox_head(bbox_roi_extractor, bbox_head)
+        self.init_assigner_sampler()
+
+    with_bbox, with_mask, with_shared_head = True, False, False
+
+    def init_bbox_head(self, bbox_roi_extractor, bbox_head):
+        """htd_roi_head.py:42-71."""
+        self.bbox_roi_extractor = nn.ModuleList()
+        self.bbox_head = nn.ModuleList()
+        if not isinstance(bbox_roi_extractor, list):
+            bbox_roi_extractor = [bbox_roi_extractor for _ in range(self.num_stages)]
+        if not isinstance(bbox_head, list):
+            bbox_head = [bbox_head for _ in range(self.num_stages)]
+        assert len(bbox_roi_extractor) == len(bbox_head) == self.num_stages
+        for ext, head in zip(bbox_roi_extractor, bbox_head):
+            self.bbox_roi_extractor.append(build_roi_extractor(ext))
+            self.bbox_head.append(build_head(head))
+        if self.with_global:
+            self.glbctx_head = build_head(dict(
+                type='GlobalContextHead', num_ins=5, num_convs=4, in_channels=256,
+                conv_out_channels=256, num_classes=self.bbox_head[0].num_classes + 1,
+                loss_weight=3.0))
+
+    def init_assigner_sampler(self):
+        """htd_roi_head.py:101-111."""
+        self.bbox_assigner, self.bbox_sampler = [], []
+        if self.train_cfg is not None:
+            for cfg in self.train_cfg:
+                self.bbox_assigner.append(build_assigner(dict(cfg.assigner)))
+                self.bbox_sampler.append(build_sampler(dict(cfg.sampler), context=self))
+
+    def init_weights(self, pretrained=None):
+        for i in range(self.num_stages):
+            self.bbox_roi_extractor[i].init_weights()
+            self.bbox_head[i].init_weights()
+        if self.with_global:
+            self.glbctx_head.init_weights()
+
+    # ------------------------------------------------------------------------------------------
+    def _pyramid(self, x):
+        """Channels-last copy of the levels the extractors read, made once per call."""
+        n = self.bbox_roi_extractor[0].num_inputs
+        dtype = self.compute_dtype or x[0].dtype
+        return [ops.to_channels_last(f, dtype) for f in x[:n]]
+
+    def _fuse_global(self, roi_feats, global_feat, rois):
+        """htd_roi_head.py:133-141 as a broadcast add (equal whenever every image index is valid)."""
+        assert roi_feats.size(0) == rois.size(0)
+        g = global_feat.reshape(global_feat.size(0), -1)
+        return roi_feats + g[rois[:, 0].long()][:, :, None, None].to(roi_feats.dtype)
+
+    def _bbox_forward(self, stage, x, rois, global_feat=None, sampling_results=None,
+                      img_metas=None, x_cl=None):
+        """htd_roi_head.py:143-201."""
+        ext, enh = self.bbox_roi_extractor[0], self.bbox_roi_extractor[1]
+        if x_cl is None:
+            x_cl = self._pyramid(x)
+        g = global_feat if self.with_global else None
+        if stage == 0:
+            bbox_feats = ext(x_cl, rois, bias=g)          # RoIAlign + SFA add in one launch
+            cls_score, bbox_pred = self.bbox_head[0](bbox_feats)
+            return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
+        head = self.bbox_head[stage]
+        fc0 = self.bbox_head[0].fc_cls
+        nimg = g.size(0) if g is not None else None
+        if sampling_results:
+            pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
+            bbox_feats = ext(x_cl, rois)
+            enhanced = enh(x_cl, pos_rois)
+            idx, off = [], 0
+            for res in sampling_results:       # positives are the prefix of each image's block
+                idx.append(torch.arange(off, off + res.pos_bboxes.size(0), device=rois.device))
+                off += res.pos_bboxes.size(0) + res.neg_bboxes.size(0)
+            pos_idx = torch.cat(idx)
+            cls_score, bbox_pred = head(bbox_feats, bbox_feats[pos_idx], x_cl, rois, fc0, enhanced,
+                                        pos_rois, g, num_imgs=nimg or len(sampling_results))
+            full = cls_score.new_zeros(cls_score.size(0), 4).index_put((pos_idx,), bbox_pred)
+            return dict(cls_score=cls_score, bbox_pred=full)
+        bbox_feats = ext(x_cl, rois)
+        enhanced = enh(x_cl, rois)
+        cls_score, bbox_pred = head(bbox_feats, bbox_feats, x_cl, rois, fc0, enhanced, rois, g,
+                                    num_imgs=nimg)
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred)
+
+    def _bbox_forward_train(self, stage, x, sampling_results, gt_bboxes, gt_labels, rcnn_train_cfg,
+                            img_metas, global_feat=None, x_cl=None):
+        """htd_roi_head.py:203-215."""
+        rois = bbox2roi([res.bboxes for res in sampling_results])
+        res = self._bbox_forward(stage, x, rois, global_feat, sampling_results, img_metas, x_cl)
+        targets = self.bbox_head[stage].get_targets(sampling_results, gt_bboxes, gt_labels,
+                                                    rcnn_train_cfg)
+        loss = self.bbox_head[stage].loss(res['cls_score'], res['bbox_pred'], rois, *targets)
+        res.update(loss_bbox=loss, rois=rois, bbox_targets=targets)
+        return res
+
+    def _assign_sample(self, stage, proposal_list, gt_bboxes, gt_labels, gt_bboxes_ignore, x):
+        out = []
+        for j in range(len(proposal_list)):
+            a = self.bbox_assigner[stage].assign(proposal_list[j], gt_bboxes[j],
+                                                 gt_bboxes_ignore[j], gt_labels[j])
+            out.append(self.bbox_sampler[stage].sample(a, proposal_list[j], gt_bboxes[j],
+                                                       gt_labels[j]))
+        return out
+
+    def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                      gt_bboxes_ignore=None, gt_masks=None, sampling_fn=None):
+        """htd_roi_head.py:217-317.  ``sampling_fn(stage, proposal_list) -> list of sampling
+        results`` replaces the random assign+sample steps when given (deterministic benches and
+        parity tests; the reference's RandomSampler draws from the global torch RNG)."""
+        losses = dict()
+        num_imgs = len(img_metas)
+        if gt_bboxes_ignore is None:
+            gt_bboxes_ignore = [None] * num_imgs
+        x_cl = self._pyramid(x)
+
+        def sample(stage, props):
+            if sampling_fn is not None:
+                return sampling_fn(stage, props)
+            return self._assign_sample(stage, props, gt_bboxes, gt_labels, gt_bboxes_ignore, x)
+
+        samp = sample(0, proposal_list)
+        global_feat = None
+        if self.with_global:
+            mc_pred, global_feat = self.glbctx_head(x)
+            losses['loss_global'] = self.glbctx_head.loss(mc_pred, gt_labels)
+        res = self._bbox_forward_train(0, x, samp, gt_bboxes, gt_labels, self.train_cfg[0],
+                                       img_metas, global_feat, x_cl)
+        lw = self.stage_loss_weights[0]
+        for name, value in res['loss_bbox'].items():
+            losses[f's0.{name}'] = value * lw if 'loss' in name else value
+        roi_labels = res['bbox_targets'][0]
+        with torch.no_grad():
+            roi_labels = torch.where(roi_labels == self.bbox_head[0].num_classes,
+                                     res['cls_score'][:, :-1].argmax(1), roi_labels)
+            proposal_list = self.bbox_head[0].refine_bboxes(
+                res['rois'], roi_labels, res['bbox_pred'], [r.pos_is_gt for r in samp], img_metas)
+        samp = sample(1, proposal_list)
+        res = self._bbox_forward_train(1, x, samp, gt_bboxes, gt_labels, self.train_cfg[1],
+                                       img_metas, global_feat, x_cl)
+        lw = self.stage_loss_weights[1]
+        for name, value in res['loss_bbox'].items():
+            losses[f's1.{name}'] = value * lw if 'loss' in name else value
+        return losses
+
+    def simple_test_scores(self, x, proposal_list, img_metas):
+        """Body of simple_test up to (excluding) get_bboxes/NMS (htd_roi_head.py:319-366):
+        refined rois, stage-averaged cls_score, stage-1 bbox_pred."""
+        num_imgs = len(proposal_list)
+        rois = bbox2roi(proposal_list)
+        x_cl = self._pyramid(x)
+        global_feat = self.glbctx_head(x)[1] if self.with_global else None
+        r0 = self._bbox_forward(0, x, rois, global_feat, x_cl=x_cl)
+        n = tuple(len(p) for p in proposal_list)
+        cls0, bp0, rs = r0['cls_score'].split(n, 0), r0['bbox_pred'].split(n, 0), rois.split(n, 0)
+        label = [s[:, :-1].argmax(dim=1) for s in cls0]
+        rois = torch.cat([self.bbox_head[0].regress_by_class(rs[j], label[j], bp0[j], img_metas[j])
+                          for j in range(num_imgs)])
+        r1 = self._bbox_forward(1, x, rois, global_feat, x_cl=x_cl)
+        return rois, (r0['cls_score'] + r1['cls_score']) / 2.0, r1['bbox_pred']
+
+    def simple_test(self, x, proposal_list, img_metas, rescale=False):
+        """htd_roi_head.py:319-386."""
+        n = tuple(len(p) for p in proposal_list)
+        rois, cls_score, bbox_pred = self.simple_test_scores(x, proposal_list, img_metas)
+        rois, cls_score, bbox_pred = rois.split(n, 0), cls_score.split(n, 0), bbox_pred.split(n, 0)
+        results = []
+        for i in range(len(proposal_list)):
+            det_bbox, det_label = self.bbox_head[-1].get_bboxes(
+                rois[i], cls_score[i], bbox_pred[i], img_metas[i]['img_shape'],
+                img_metas[i].get('scale_factor', 1.0), rescale=rescale, cfg=self.test_cfg)
+            results.append(bbox2result(det_bbox, det_label, self.bbox_head[-1].num_classes))
+        return results
+
+    def aug_test(self, features, proposal_list, img_metas, rescale=False):
+        raise NotImplementedError('test-time augmentation is outside the accelerated path '
+                                  '(SURVEY.md §8: callers, next)')

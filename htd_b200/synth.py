@@ -139,3 +139,31 @@ def level_histogram(rois, finest_scale=56.0, num_levels=4):
     scale = torch.sqrt((rois[:, 2] - rois[:, 0]) * (rois[:, 3] - rois[:, 1]))
     lv = torch.floor(torch.log2(scale / finest_scale + 1e-6)).clamp(0, num_levels - 1).long()
     return torch.bincount(lv, minlength=num_levels).tolist()
+
+
+def make_sampling(bboxes, num_pos, gt):
+    """Synthetic sampling result in the reference's layout (positives first,
+    ``sampling_result.py:52-54``): the first ``num_pos`` rows of ``bboxes`` are the positives,
+    their targets come from ``make_gt``.  Duck-types ``core.SamplingResult``."""
+    from types import SimpleNamespace
+    n = min(num_pos, bboxes.size(0))
+    dev = bboxes.device
+    return SimpleNamespace(
+        pos_bboxes=bboxes[:n], neg_bboxes=bboxes[n:],
+        pos_gt_bboxes=gt['pos_gt_bboxes'][:n].to(device=dev, dtype=bboxes.dtype),
+        pos_gt_labels=gt['pos_gt_labels'][:n].to(dev),
+        pos_is_gt=torch.zeros(n, dtype=torch.uint8, device=dev), bboxes=bboxes)
+
+
+def sampled_forward_train(head, x, proposals, gts, img_shapes, num_pos=128):
+    """``HTDRoIHead.forward_train`` with the random assign+sample steps replaced by the
+    positives-first synthetic sampling above - the protocol of bench.py and of
+    the parity tests (oracle side: ``restate.HTDRoIHead.forward_train_sampled``)."""
+    metas = [dict(img_shape=s) for s in img_shapes]
+    dev = proposals[0].device
+    labels = [g['gt_labels_unique'].to(dev) for g in gts]
+
+    def sampling_fn(stage, plist):
+        return [make_sampling(p, num_pos, g) for p, g in zip(plist, gts)]
+
+    return head.forward_train(x, metas, proposals, None, labels, sampling_fn=sampling_fn)

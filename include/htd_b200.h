@@ -130,6 +130,99 @@ int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, 
                   float* partial /* workspace [ceil(K/32), B, C] fp32 */, float* dbias,
                   htd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * PGraph (HTDBBoxHead.forward graph loop, htd_bbox_head.py:195-219).
+ *
+ * RoIs are regrouped into "sorted space": a stable counting sort by key = level * B + image
+ * (row order inside a group = ascending original RoI index, i.e. the reference's boolean-mask
+ * order, htd_bbox_head.py:199-207).  Every LEVEL block starts on a multiple of `align` rows and
+ * every group on a multiple of HTD_GROUP_ALIGN rows (TMA needs 16-byte aligned K offsets); the
+ * gaps are pad rows (perm == -1) and are zero in every sorted-space buffer.  A group g with span
+ * (off, n) owns sorted rows [off, off+n); its n x n matrices (adjacency, similarity, attention)
+ * are stored as rows off..off+n-1, columns 0..n-1 of one [Npad, ld] buffer.
+ * ------------------------------------------------------------------------------------------ */
+#define HTD_MAX_GROUPS 64
+#define HTD_GROUP_ALIGN 8
+#define HTD_PLAN_ROW_CAPACITY(K, L, B, align) ((K) + (L) * (align) + (L) * (B) * HTD_GROUP_ALIGN)
+
+/* table layout (int32): [2*g + 0/1] = (off, n) of group g = level*B + image, g < L*B;
+ * [2*L*B + 2*l + 0/1] = (off, n) of level block l (n = rows from the block start to its last
+ * group row, inner pad rows included); [2*L*B + 2*L] = Npad (multiple of align). */
+#define HTD_PLAN_TABLE_INTS(L, B) (2 * (L) * (B) + 2 * (L) + 1)
+
+/* levels: [K] int32 from htd_level_assign (-1 rows and rows with image id outside [0,B) join no
+ * group).  Ncap >= HTD_PLAN_ROW_CAPACITY(K, L, B, align) rows of capacity.  Outputs (device): perm [Ncap] sorted row ->
+ * original index (-1 pad), pos [K] original -> sorted row (-1 none), rowspan [Ncap][2] = (off, n)
+ * of the row's group (n = 0 for pad rows), boxes [Ncap][4] = the row's (x1,y1,x2,y2), table. */
+int htd_pgraph_plan(const float* rois, const int32_t* levels, int K, int B, int L, int align,
+                    int Ncap, int32_t* perm, int32_t* pos, int32_t* rowspan, float* boxes,
+                    int32_t* table, htd_stream_t stream);
+
+/* Gather rows into sorted space with dtype conversion: v[p, c] = src[perm[p], c] (* [gate[perm[p],
+ * c] > 0] when gate != NULL; 0 for pad rows).  dst (nullable): [Npad, ldd] row-major, columns
+ * D..ldd-1 zero-filled.  dstT (nullable): [D, ldt], dstT[c, p] = v[p, c]. */
+int htd_pgraph_pack(const void* src, int src_dtype, long long lds, const void* gate,
+                    int gate_dtype, long long ldg, const int32_t* perm, int Npad, int D, void* dst,
+                    long long ldd, void* dstT, long long ldt, int dst_dtype, htd_stream_t stream);
+
+/* Local adjacency of every group (htd_bbox_head.py:207-210, bbox_overlaps =
+ * core/bbox/iou_calculators/iou2d_calculator.py:129-150):
+ *   M[p, j] = (IoU(box_p, box_{off+j}) > 0) or (off + j == p)          j < n
+ *   bits[p, j/32] bit j%32 = M (ldb uint32 words per row, zero-padded), deg[p] = sum_j M[p, j]
+ *   adj[p, j] = deg[p]^-1/2 * M[p, j] * deg[off+j]^-1/2  (0 for n <= j < ldn and for pad rows)
+ * IoU uses the reference's fp32 expression order; the mask is bit-exact. */
+int htd_iou_graph_build(const float* boxes, const int32_t* rowspan, int Npad, uint32_t* bits,
+                        int ldb, int32_t* deg, void* adj, int adj_dtype, long long ldn,
+                        htd_stream_t stream);
+
+/* Global attention (htd_bbox_head.py:211,215): out[p, j] = softmax_j((1 - M[p, j]) * S[p, j]),
+ * j < n - masked entries keep logit 0, NOT -inf; zeros for n <= j < ldo and pad rows. */
+int htd_pgraph_masked_softmax(const float* S, long long lds, const uint32_t* bits, int ldb,
+                              const int32_t* rowspan, int Npad, void* out, int out_dtype,
+                              long long ldo, htd_stream_t stream);
+
+/* Backward of the above: dS[p, j] = (1 - M[p, j]) * A[p, j] * (dA[p, j] - sum_j A[p, j] dA[p, j]),
+ * fp32, zeros beyond n / pad rows. */
+int htd_pgraph_softmax_bwd(const void* A, int a_dtype, long long lda, const float* dA,
+                           long long ldda, const uint32_t* bits, int ldb, const int32_t* rowspan,
+                           int Npad, float* dS, long long ldds, htd_stream_t stream);
+
+/* Per-group transpose / symmetrise: out[p, j] = alpha * in[p, j] + beta * in[off + j, p - off],
+ * j < n; zeros beyond n / pad rows. */
+int htd_pgraph_group_transpose(const void* in, int in_dtype, long long ldi, const int32_t* rowspan,
+                               int Npad, float alpha, float beta, void* out, int out_dtype,
+                               long long ldo, htd_stream_t stream);
+
+/* Column sums over row segments: out[s, c] = sum_{p in [seg[2s], seg[2s]+seg[2s+1])} x[p, c];
+ * seg is a DEVICE pointer (e.g. the level part of the plan table). */
+int htd_pgraph_segment_colsum(const void* x, int x_dtype, long long ldx, const int32_t* seg,
+                              int num_seg, int D, float* out, htd_stream_t stream);
+
+/* One problem of a grouped contraction D = A * B^T (both operands K-major / row-major [rows, K]). */
+typedef struct HtdGemmGroup {
+    int32_t M, N, K;
+    int32_t a_row, a_k0; /* A block origin: rows a_row.., K columns a_k0..   */
+    int32_t b_row, b_k0; /* B block origin: rows b_row.. (the N index), K columns b_k0.. */
+    int32_t d_row, d_col; /* D[(d_row + m), d_col + n]  (d_row + m goes through d_rowmap if given) */
+    int32_t dt_row, dt_col; /* DT[(dt_row + n), dt_col + m] */
+    int32_t bias_off;    /* bias[bias_off + n] added before relu (ignored when bias == NULL) */
+} HtdGemmGroup;
+
+/* Grouped GEMM for the PGraph contractions (htd_bbox_head.py:210-216 and their backward,
+ * SURVEY.md Appendix D).  ab_dtype HTD_BF16: tcgen05 tensor cores (TMA-fed, TMEM accumulators,
+ * fp32 accumulate); HTD_F32: exact-fp32 FFMA tiles (the fp32 parity configuration).  For BF16
+ * the K extent of at least ONE operand must be zero beyond the group's K up to the next multiple
+ * of 64 and the other finite (sorted-space buffers guarantee it); leading dimensions and the K
+ * offsets a_k0 / b_k0 must be multiples of 8 elements and base pointers 16-byte aligned.
+ * Outputs (either may be NULL): D [.., ldd] (d_dtype) with optional row scatter map
+ * (d_rowmap[d_row + m] < 0 drops the row), DT [.., ldt] (dt_dtype) = transposed copy.
+ * v = acc (+ bias[bias_off + n]) (relu) is what both receive. */
+int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void* B,
+                    long long b_rows, long long b_ld, int ab_dtype, const HtdGemmGroup* groups,
+                    int G, void* D, int d_dtype, long long ldd, const int32_t* d_rowmap, void* DT,
+                    int dt_dtype, long long ldt, const float* bias, int relu,
+                    htd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
