@@ -1,0 +1,364 @@
+"""bench.py - RoIs/sec of the HTD RoI head (fwd+bwd) on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): HTD R-50-FPN RoI head fwd+bwd, bf16, 2 images/GPU x 512 RoIs
+(128 positives/image), synthetic 800x1333 pyramid (P2..P6, 256 ch), random-init weights.  A step =
+``HTDRoIHead.forward_train`` (SFA -> stage 0 -> box refinement -> stage 1 with BA + PGraph) with
+the synthetic positives-first sampling of SURVEY.md 8(d), the 7 losses, and the backward pass down
+to the pyramid gradients and all 47.2M head-parameter gradients.  N > 1: one process per GPU
+(torchrun), each GPU its own images (weak scaling), NCCL all-reduce of the head gradients.
+
+value   device-resident inputs (fp32 NCHW pyramid already in HBM), CUDA-event timed, max over ranks
+e2e     same step through the plugin API from HOST buffers: pinned-host pyramid/proposals copied
+        H2D every step (double-buffered on a copy stream) and the losses read back D2H
+roofline  dominant own kernel (roi_align_bwd), algorithmic bytes of SURVEY 8(d) / live event time
+cpu_baseline  the CPU oracle port of the reference path on a bounded sample, rank 0, N = 1 only
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'RoIs/sec HTD RoI head fwd+bwd'
+UNIT = 'RoIs/s'
+IMGS, ROIS, POS = 2, 512, 128
+IMG_H, IMG_W = 800, 1333
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='htd_b200', choices=['htd_b200', 'reference'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), 'measured'
+    except Exception:
+        return 6650.0, 1400.0, 'fallback'
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (the reference itself is pure Python on
+# mmcv, absent here and on the GPU box - DESIGN.md "Oracle")
+# --------------------------------------------------------------------------------------------
+CPU_SAMPLE = dict(imgs=IMGS, rois=ROIS, pos=POS)      # the whole workload: a few seconds per step
+
+
+def cpu_step_factory():
+    import torch
+    from htd_b200 import synth
+    from oracle import restate
+    torch.set_num_threads(os.cpu_count() or 1)
+    s = CPU_SAMPLE
+    head = restate.HTDRoIHead()
+    synth.fill_params_(head, 'init', 0)
+    x = [t.requires_grad_(True) for t in synth.make_pyramid(s['imgs'], IMG_H, IMG_W)]
+    props = synth.make_proposals(s['imgs'], s['rois'], IMG_H, IMG_W)
+    gts = synth.make_gt(s['imgs'], props, num_pos=s['pos'])
+    shapes = [(IMG_H, IMG_W, 3)] * s['imgs']
+
+    def step():
+        for p in head.parameters():
+            p.grad = None
+        for t in x:
+            t.grad = None
+        losses = head.forward_train_sampled(x, props, gts, shapes, s['pos'])
+        sum(v for k, v in losses.items() if 'loss' in k).backward()
+        return float(losses['s1.loss_cls'])
+    return step, s['imgs'] * s['rois']
+
+
+def cpu_sample_desc():
+    s = CPU_SAMPLE
+    return (f"oracle port (oracle/restate.py + C RoIAlign, fp32, torch CPU) of the same step on "
+            f"{s['imgs']} image x {s['rois']} RoIs ({s['pos']} positives), 800x1333 pyramid")
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    step, rois_per_step = cpu_step_factory()
+    for _ in range(max(args.warmup, 0)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = rois_per_step * args.steps / dt
+    cores = os.cpu_count() or 1
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=dict(workload='HTD R-50-FPN RoI head fwd+bwd, CPU oracle port, bounded sample',
+                            imgs_per_step=CPU_SAMPLE['imgs'], rois_per_img=CPU_SAMPLE['rois'],
+                            positives_per_img=CPU_SAMPLE['pos'], pyramid='800x1333 P2-P6 x256ch'),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind='port',
+                                  sample=cpu_sample_desc()),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.QUERY}',
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for ln in open(self.path):
+                f = [t.strip() for t in ln.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
+        out['reasons'] = sorted(reasons)
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import htd_b200
+    from htd_b200 import _lib, synth
+    from htd_b200.parallel import GradAllReducer
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch N > 1 with: python -m torch.distributed.run --nnodes=1 '
+                             f'--nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py ...')
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: htd_b200 has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    hbm_peak, tc_peak, peak_kind = peaks()
+
+    # ---- model + synthetic inputs (each rank its own images: weak scaling) -------------------
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'init', 0)
+    head = head.to(dev).to(dtype)
+    head.compute_dtype = dtype
+    head.train()
+    img0 = rank * IMGS
+    pyr_host = [t.pin_memory() for t in synth.make_pyramid(IMGS, IMG_H, IMG_W, seed=1000 + img0)]
+    props_host = [p.pin_memory() for p in synth.make_proposals(IMGS, ROIS, IMG_H, IMG_W,
+                                                               seed=1234 + img0)]
+    gts = synth.make_gt(IMGS, props_host, num_pos=POS, seed=4321 + img0)
+    gts = [{k: v.to(dev) for k, v in g.items()} for g in gts]
+    shapes = [(IMG_H, IMG_W, 3)] * IMGS
+    x_dev = [t.to(dev).requires_grad_(True) for t in pyr_host]
+    props_dev = [p.to(dev) for p in props_host]
+    reducer = GradAllReducer(head.parameters(), world) if world > 1 else None
+    rois_per_step = IMGS * ROIS
+
+    def step(x, props):
+        for p in head.parameters():
+            p.grad = None
+        for t in x:
+            t.grad = None
+        losses = synth.sampled_forward_train(head, x, props, gts, shapes, POS)
+        total = sum(v for k, v in losses.items() if 'loss' in k)
+        total.backward()
+        if reducer is not None:
+            reducer.allreduce()
+        return losses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then one accounting step (algorithmic bytes / flops per launch) -------------
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, props_dev)
+    barrier()
+    _lib.ACCOUNT = []
+    step(x_dev, props_dev)
+    torch.cuda.synchronize()
+    account = _lib.ACCOUNT
+    _lib.ACCOUNT = None
+    pg_flops = head.bbox_head[1].last_plan.flops()
+    alg = {}
+    for name, nbytes in account:
+        alg.setdefault(name, []).append(nbytes)
+
+    # ---- timed region 1: device-resident inputs ----------------------------------------------
+    clocks = ClockSampler(local)
+    barrier()
+    _lib.TIMER = _lib.KernelTimer()
+    l0 = _lib.LAUNCHES['total']
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(x_dev, props_dev)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.LAUNCHES['total'] - l0
+    ksum = _lib.TIMER.summary()
+    _lib.TIMER = None
+    clk = clocks.stop()
+
+    # ---- timed region 2: end to end from host buffers (H2D double-buffered, D2H of the losses)
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pyr_host) + \
+        sum(p.numel() * p.element_size() for p in props_host)
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            xs = [t.to(dev, non_blocking=True) for t in pyr_host]
+            ps = [p.to(dev, non_blocking=True) for p in props_host]
+            evt = torch.cuda.Event()
+            evt.record(copy_stream)
+        return xs, ps, evt
+
+    def e2e_loop(n):
+        d2h = 0
+        nxt = upload()
+        for i in range(n):
+            xs, ps, evt = nxt
+            if i + 1 < n:
+                nxt = upload()
+            torch.cuda.current_stream().wait_event(evt)
+            for t in xs:
+                t.record_stream(torch.cuda.current_stream())
+                t.requires_grad_(True)
+            losses = step(xs, ps)
+            host = torch.stack([v.detach().float().reshape(()) for v in losses.values()]).cpu()
+            d2h = host.numel() * host.element_size()
+        return d2h
+
+    e2e_loop(2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d2h_bytes = e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    value = rois_per_step * world * args.steps / (ms * 1e-3)
+    value_e2e = rois_per_step * world * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the own kernels -----------------------------------------------------------
+    kernels = {}
+    for name, (n, tot_ms) in ksum.items():
+        per_step = alg.get(name)
+        if not per_step or n == 0:
+            continue
+        total_bytes = sum(per_step) * args.steps
+        gbs = total_bytes / (tot_ms * 1e-3) / 1e9
+        kernels[name] = dict(launches=n, avg_ms=tot_ms / n, alg_MB_per_launch=sum(per_step) / len(per_step) / 1e6,
+                             achieved_GBs=gbs, frac=gbs / hbm_peak, share_of_step=tot_ms / ms)
+    dom = max(kernels, key=lambda k: kernels[k]['share_of_step']) if kernels else None
+    roofline = None
+    if dom:
+        k = kernels[dom]
+        roofline = dict(bound='hbm', kernel=dom, achieved=k['achieved_GBs'], peak=hbm_peak,
+                        unit='GB/s', frac=k['frac'], traffic=None, peak_kind=peak_kind,
+                        avg_ms=k['avg_ms'], share_of_step=k['share_of_step'])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cstep, crois = cpu_step_factory()
+        cstep()                                   # warm-up (page-in, thread pools)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            cstep()
+        cdt = (time.perf_counter() - t0) / reps
+        cpu = dict(value=crois / cdt, unit=UNIT, cores=os.cpu_count() or 1, kind='port',
+                   sample=cpu_sample_desc() + f', {reps} timed passes of {cdt:.1f} s')
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic',
+                config=dict(workload='HTD R-50-FPN RoI head fwd+bwd, 2 images/GPU x 512 RoIs '
+                                     '(128 positives/img), 800x1333 pyramid P2-P6 x 256 ch, '
+                                     'random init',
+                            global_rois_per_step=rois_per_step * world,
+                            parallelism=f'dp{world}' + (' + NCCL grad all-reduce' if world > 1 else ''),
+                            l2='inputs larger than L2: 183 MB fp32 pyramid + 94 MB bf16 weights per step',
+                            pgraph_fwd_gflop=pg_flops / 1e9),
+                e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,
+                         d2h_bytes_per_step=d2h_bytes, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=launches, clocks=clk, roofline=roofline, kernels=kernels,
+                cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_gpu(a)
