@@ -36,11 +36,14 @@ SIGNATURES = {
     'htd_level_assign': [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p],
     'htd_roi_footprints': [ctypes.POINTER(HtdLevel), c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                            c_int, c_void_p, c_void_p, c_void_p],
+    'htd_roi_plan': [ctypes.POINTER(HtdLevel), c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int,
+                     c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p],
     'htd_roi_align_fwd': [ctypes.POINTER(HtdLevel), c_int, c_int, c_int, c_int, c_void_p, c_int,
-                          c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_int, c_void_p],
     'htd_roi_align_bwd': [ctypes.POINTER(HtdLevel), c_int, c_int, c_int, c_int, c_void_p, c_int,
-                          c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
-                          c_void_p],
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                          c_void_p, c_int, c_void_p, c_void_p],
     'htd_layout_convert': [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     'htd_ba_bin_mean': [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p],
     'htd_ba_fuse_fwd': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
@@ -70,7 +73,7 @@ SIGNATURES = {
 _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2}
+KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 
 
@@ -104,6 +107,8 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.htd_last_error.restype = ctypes.c_char_p
         L.htd_abi_version.restype = c_int
+        L.htd_roi_plan_rows_bound.restype = c_ll
+        L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
         for name, args in SIGNATURES.items():
             if not hasattr(L, name):
                 raise RuntimeError(f'{LIB_PATH} does not export {name}: rebuild it '

@@ -10,8 +10,13 @@
 //  * avg RoIAlign is separable:  Y[ph][pw][c] = sum_r sum_x Wy[ph][r] Wx[pw][x] F[r][x][c];
 //    every footprint pixel of a bin is read ONCE (128-bit channels-last loads) instead of up to
 //    4*gh*gw times.  Axis weights are computed in fp64 (roi_axis.h) and rounded to fp32.
-//  * forward: one warp per output bin, a lane owns 8 of the 256 channels of a chunk; work is a
-//    flat list of bins so a 200x200-pixel BA footprint on P2 is spread over 49 warps.
+//  * plan (htd_roi_plan): footprint box of every (level, RoI), an exclusive scan of their
+//    extents, and the separable axis-weight TABLES  wy[row][p], wx[col][p]  (fp64 arithmetic,
+//    rounded once to fp32) plus the pixel range of every bin.  Built once per extractor call and
+//    shared by forward and backward, so the hot kernels contain no coordinate math at all.
+//  * forward: one CTA per (RoI, level, output row ph), one warp per output bin; a lane owns 8 of
+//    the 256 channels of a chunk; weights come from the tables via warp shuffles.  A 200x200-pixel
+//    BA footprint on P2 is spread over 7 CTAs x 7 warps.
 //  * backward: one CTA per 8x8-pixel tile of dX; it scans the RoI footprint boxes of its image,
 //    compacts the intersecting RoIs IN INDEX ORDER (ballot + prefix), and accumulates
 //    Wy^T dY Wx for its 64 pixels x 256 channels in registers.  Every dX element is written
@@ -86,94 +91,257 @@ __global__ void footprint_kernel(const FootParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// plan: extents scan + axis-weight tables
+// ------------------------------------------------------------------------------------------
+constexpr int kTabW = HTD_MAX_POOLED;          // floats per table row (weights of the P bins)
+constexpr int kRangeInts = 4 * HTD_MAX_POOLED; // per entry: y lo[8], y hi[8], x lo[8], x hi[8]
+
+// offsets[e] = sum_{e' < e} (fh + fw) over all entries e = l*K + k; offsets[n] = total rows.
+__global__ void __launch_bounds__(1024) extent_scan_kernel(const int4* __restrict__ boxes, int n,
+                                                           int* __restrict__ offsets) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int e = base + tid;
+        int v = 0;
+        if (e < n) {
+            const int4 b = boxes[e];
+            if (b.y >= b.x && b.w >= b.z) v = (b.y - b.x + 1) + (b.w - b.z + 1);
+        }
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + (warp > 0 ? s_warp[warp - 1] : 0) + inc - v;
+        if (e < n) offsets[e] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = s_carry;
+}
+
+struct TableParams {
+    LevelDev lv[HTD_MAX_LEVELS];
+    int L, K, P, sr;
+    const float* rois;
+    const int4* boxes;
+    const int* offsets;
+    int* ranges;
+    float* weights;
+};
+
+__global__ void __launch_bounds__(128) weight_table_kernel(const TableParams p) {
+    __shared__ Axis s_axis[2];
+    const int e = blockIdx.x;
+    const int l = e / p.K, k = e % p.K;
+    const int4 box = p.boxes[e];
+    int* rg = p.ranges + (size_t)e * kRangeInts;
+    const int tid = threadIdx.x;
+    if (box.y < box.x || box.w < box.z) {           // RoI does not touch this level
+        if (tid < kRangeInts) rg[tid] = (tid / HTD_MAX_POOLED) % 2 == 0 ? 0 : -1;
+        return;
+    }
+    const float* r = p.rois + (size_t)k * 5;
+    if (tid == 0) s_axis[0] = make_axis(r[2], r[4], (double)p.lv[l].scale, p.P, p.lv[l].H, p.sr, 1);
+    if (tid == 32) s_axis[1] = make_axis(r[1], r[3], (double)p.lv[l].scale, p.P, p.lv[l].W, p.sr, 1);
+    __syncthreads();
+    if (tid < 2 * HTD_MAX_POOLED) {                 // per-bin pixel ranges
+        const int axis = tid / HTD_MAX_POOLED, pp = tid % HTD_MAX_POOLED;
+        int lo = 0, hi = -1;
+        if (pp < p.P) bin_range(s_axis[axis], pp, lo, hi);
+        rg[axis * 2 * HTD_MAX_POOLED + pp] = lo;
+        rg[axis * 2 * HTD_MAX_POOLED + HTD_MAX_POOLED + pp] = hi;
+    }
+    const int fh = box.y - box.x + 1, fw = box.w - box.z + 1;
+    float* tab = p.weights + (size_t)p.offsets[e] * kTabW;
+    for (int i = tid; i < (fh + fw) * kTabW; i += blockDim.x) {
+        const int row = i / kTabW, pp = i % kTabW;
+        float w = 0.f;
+        if (pp < p.P)
+            w = row < fh ? axis_weight(s_axis[0], pp, box.x + row)
+                         : axis_weight(s_axis[1], pp, box.z + (row - fh));
+        tab[i] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
 struct FwdParams {
     LevelDev lv[HTD_MAX_LEVELS];
-    int L, B, C, K, P, sr;
+    int L, B, C, K, P;
     const float* rois;
     const int* roi_level;
+    const int4* boxes;
+    const int* offsets;
+    const int* ranges;
+    const float* weights;
     const float* bias;
     void* out;
-    long long total_bins;
 };
 
-constexpr int kFwdWarps = 8;
-constexpr int kWChunk = 64;
+// Shared-memory staged forward.  One CTA per (RoI, level, output row ph), one warp per output
+// bin (ph, pw).  Every warp runs its OWN copy pipeline: lane 0 streams the bin's footprint -
+// each row segment is one contiguous run in channels-last memory - into a private
+// kFwdStages-deep ring with cp.async.bulk (UBLKCP) + mbarrier transaction counts, kFwdPx pixels
+// per stage, while the warp reduces the previous stage from shared memory.  No cross-warp
+// barrier, no idle spinning; bytes in flight are set by the rings, not by registers.
+constexpr int kFwdStages = 2;
+constexpr int kFwdPx = 8;
+
+template <typename TIn>
+__device__ __forceinline__ void ld_smem8(const TIn* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld_smem8<float>(const float* p, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld_smem8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__(kFwdWarps * 32) roi_align_fwd_kernel(const FwdParams p) {
-    constexpr bool kSplit = SplitMap<TIn, TOut>::value;
-    __shared__ float s_w[kFwdWarps][2][kWChunk];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long widx = (long long)blockIdx.x * kFwdWarps + warp;
-    if (widx >= p.total_bins) return;
-    const int PP = p.P * p.P;
-    const int bin = (int)(widx % PP);
-    const long long task = widx / PP;
+__global__ void __launch_bounds__(HTD_MAX_POOLED * 32) roi_align_fwd_kernel(const FwdParams p) {
+    extern __shared__ __align__(128) uint8_t fwd_smem[];
+    const int pw = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = p.P;
+    const int ph = (int)(blockIdx.x % P);
+    const long long task = blockIdx.x / P;
     int l, k;
     if (p.roi_level) { k = (int)task; l = p.roi_level[k]; }
     else { l = (int)(task / p.K); k = (int)(task % p.K); }
-    const float* r = p.rois + (size_t)k * 5;
-    const float x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
-    const int b = (int)r[0];
-    const int ph = bin / p.P, pw = bin % p.P;
+    const int b = (int)p.rois[(size_t)k * 5];
     const bool bvalid = (b >= 0 && b < p.B);
     const bool valid = bvalid && (l >= 0 && l < p.L);
+    const int PP = P * P;
+    const int cw = min(p.C, 256);                       // channels staged per pixel
+    const int stage_elems = kFwdPx * cw;
+    TIn* ring = reinterpret_cast<TIn*>(fwd_smem) + (size_t)pw * kFwdStages * stage_elems;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(
+                             fwd_smem + (size_t)P * kFwdStages * stage_elems * sizeof(TIn)) +
+                         pw * kFwdStages;
 
-    int H = 1, W = 1, r0 = 0, r1 = -1, c0 = 0, c1 = -1;
+    int H = 1, W = 1, ry0 = 0, ry1 = -1, cx0 = 0, cx1 = -1;
     const TIn* feat = nullptr;
-    Axis ay, ax;
+    const float* wyt = nullptr;
+    const float* wxt = nullptr;
     if (valid) {
-        H = p.lv[l].H; W = p.lv[l].W;
-        feat = static_cast<const TIn*>(p.lv[l].data);
-        const double sc = (double)p.lv[l].scale;
-        ay = make_axis(y1, y2, sc, p.P, H, p.sr, 1);
-        ax = make_axis(x1, x2, sc, p.P, W, p.sr, 1);
-        bin_range(ay, ph, r0, r1);
-        bin_range(ax, pw, c0, c1);
-        if (c1 < c0) r1 = r0 - 1;
+        const size_t e = (size_t)l * p.K + k;
+        const int4 box = p.boxes[e];
+        if (box.y >= box.x && box.w >= box.z) {
+            const int* rg = p.ranges + e * kRangeInts;
+            ry0 = rg[ph]; ry1 = rg[HTD_MAX_POOLED + ph];
+            cx0 = rg[2 * HTD_MAX_POOLED + pw]; cx1 = rg[3 * HTD_MAX_POOLED + pw];
+            const size_t off = (size_t)p.offsets[e];
+            const int fh = box.y - box.x + 1;
+            wyt = p.weights + (off + (ry0 - box.x)) * kTabW + ph;
+            wxt = p.weights + (off + fh + (cx0 - box.z)) * kTabW + pw;
+            H = p.lv[l].H; W = p.lv[l].W;
+            feat = static_cast<const TIn*>(p.lv[l].data);
+        }
     }
-    float* wy_s = s_w[warp][0];
-    float* wx_s = s_w[warp][1];
-    TOut* orow = static_cast<TOut*>(p.out) + ((size_t)task * PP + bin) * p.C;
+    const int ny = ry1 - ry0 + 1, nx = cx1 - cx0 + 1;
+    const int nseg = (nx + kFwdPx - 1) / kFwdPx;        // segments per footprint row
+    const int total = (ny > 0 && nx > 0) ? ny * nseg : 0;
+    TOut* orow = static_cast<TOut*>(p.out) + ((size_t)task * PP + ph * P + pw) * p.C;
 
+    if (total > 0) {
+        if (lane == 0) {
+            for (int s = 0; s < kFwdStages; ++s) mbar_init(full_bar + s, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    int tt = 0;                                         // stage uses so far (ring position / parity)
     for (int cb = 0; cb < p.C; cb += 256) {
         const int nch = min(256, p.C - cb);
+        const bool lane_on = lane * 8 < nch;
+        const uint32_t px_bytes = (uint32_t)(nch * sizeof(TIn));
+        // lane 0: stream segment t of this channel block into ring slot (tt0 + t) % stages
+        auto issue = [&](int t, int slot) {
+            const int y = ry0 + t / nseg, xs = cx0 + (t % nseg) * kFwdPx;
+            const int npx = min(kFwdPx, cx1 - xs + 1);
+            const TIn* src = feat + (((size_t)b * H + y) * W + xs) * p.C + cb;
+            TIn* dst = ring + (size_t)slot * stage_elems;
+            mbar_expect_tx(full_bar + slot, npx * px_bytes);
+            if (p.C <= 256) {
+                bulk_g2s(dst, src, npx * px_bytes, full_bar + slot);
+            } else {
+                for (int x = 0; x < npx; ++x)
+                    bulk_g2s(dst + (size_t)x * cw, src + (size_t)x * p.C, px_bytes, full_bar + slot);
+            }
+        };
+        if (lane == 0)
+            for (int t = 0; t < min(kFwdStages, total); ++t) issue(t, (tt + t) % kFwdStages);
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        for (int rr = r0; rr <= r1; rr += kWChunk) {
-            const int nr = min(kWChunk, r1 - rr + 1);
-            __syncwarp();
-            for (int j = lane; j < nr; j += 32) wy_s[j] = axis_weight(ay, ph, rr + j);
-            for (int cc = c0; cc <= c1; cc += kWChunk) {
-                const int nc = min(kWChunk, c1 - cc + 1);
-                __syncwarp();
-                for (int j = lane; j < nc; j += 32) wx_s[j] = axis_weight(ax, pw, cc + j);
-                __syncwarp();
-                for (int y = 0; y < nr; ++y) {
-                    const float wyv = wy_s[y];
-                    const TIn* rowp = feat + (((size_t)b * H + (rr + y)) * W + cc) * p.C + cb;
-#pragma unroll 4
-                    for (int x = 0; x < nc; ++x) {
-                        float v[8];
-                        Vec8<TIn, kSplit>::load(rowp + (size_t)x * p.C, lane, nch, v);
-                        const float w = wyv * wx_s[x];
+        float wy_l = 0.f, wx_l = 0.f;
+        int t = 0;
+        for (int y = 0; y < ny && total > 0; ++y) {
+            if ((y & 31) == 0) wy_l = (y + lane < ny) ? __ldg(wyt + (size_t)(y + lane) * kTabW) : 0.f;
+            const float wyv = __shfl_sync(0xffffffffu, wy_l, y & 31);
+            for (int j = 0; j < nseg; ++j, ++t, ++tt) {
+                const int xo = j * kFwdPx;                 // offset of the segment inside the bin
+                if ((xo & 31) == 0)
+                    wx_l = (xo + lane < nx) ? __ldg(wxt + (size_t)(xo + lane) * kTabW) : 0.f;
+                const int slot = tt % kFwdStages;
+                mbar_wait(full_bar + slot, (uint32_t)(tt / kFwdStages) & 1u);
+                if (wyv != 0.f) {
+                    const int npx = min(kFwdPx, nx - xo);
+                    const TIn* src = ring + (size_t)slot * stage_elems + lane * 8;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+                    for (int x = 0; x < kFwdPx; ++x) {
+                        if (x < npx) {
+                            const float w = wyv * __shfl_sync(0xffffffffu, wx_l, (xo + x) & 31);
+                            if (lane_on) {
+                                float v[8];
+                                ld_smem8<TIn>(src + (size_t)x * cw, v);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+                            }
+                        }
                     }
                 }
+                __syncwarp();                            // all lanes done with the slot
+                if (lane == 0 && t + kFwdStages < total) issue(t + kFwdStages, slot);
             }
         }
         if (p.bias && bvalid) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int c = lane_chan<kSplit>(lane, e);
+                const int c = lane * 8 + e;
                 if (c < nch) acc[e] += __ldg(p.bias + (size_t)b * p.C + cb + c);
             }
         }
-        Vec8<TOut, kSplit>::store(orow + cb, lane, nch, acc);
+        Vec8<TOut, false>::store(orow + cb, lane, nch, acc);
     }
 }
 
@@ -186,6 +354,9 @@ struct BwdParams {
     int L, B, C, K, P, sr;
     const float* rois;
     const int4* boxes;
+    const int* offsets;
+    const int* ranges;
+    const float* weights;
     const void* dy;
     int dy_per_level;
     const float* scale;
@@ -193,141 +364,248 @@ struct BwdParams {
     const float* addvec;
 };
 
-constexpr int kTile = 8;  // 8x8 pixels per CTA, one tile row per warp
+constexpr int kTile = 8;  // 8x8 pixels per CTA
+constexpr int kBwdWarps = 16;          // consumer warps: tile row (w & 7) x column half (w >> 3)
+constexpr int kBwdThreads = (kBwdWarps + 1) * 32;   // + 1 producer warp
+constexpr int kBwdChunk = kBwdWarps * 32;          // RoIs scanned per pass
+constexpr int kHalf = kTile / 2;      // pixels per consumer warp
 
+template <typename TDy>
+struct BwdStages {                     // dY ring depth: 25 KB (bf16) / 50 KB (fp32) per slot at P = 7
+    static constexpr int value = sizeof(TDy) == 2 ? 4 : 2;
+};
+
+// Backward gather.  One CTA per 8x8-pixel tile of dX.  Per chunk of 512 RoIs the 16 consumer warps
+// find the RoIs whose footprint box touches the tile and compact them in ascending index order.
+// The PRODUCER warp (warp 8) then resolves, for all hits of the chunk in parallel, which output
+// bins sample the tile (ranges table) and where the tile's rows/columns sit in the axis-weight
+// tables; per hit it streams - with cp.async.bulk (UBLKCP) + mbarrier transaction counts, several
+// hits ahead of the consumers - the tile's slices of the weight tables and the needed dY bins (per
+// bin row one contiguous run) into a ring of shared-memory slots.  Each consumer warp owns half a
+// tile row (4 pixels) and accumulates  sum_ph sum_pw wy[ph] wx[pw][x] dY[ph][pw][c]  for its 4 pixels x 256
+// channels in registers, reading shared memory only.  Every dX element is written exactly once:
+// no atomics, no memset, bit-reproducible.
 template <typename TDy, typename TDx>
-__global__ void __launch_bounds__(256) roi_align_bwd_kernel(const BwdParams p) {
-    constexpr bool kSplit = SplitMap<TDy, TDx>::value;
-    __shared__ float s_wy[2][HTD_MAX_POOLED][kTile];
-    __shared__ float s_wx[2][HTD_MAX_POOLED][kTile];
-    __shared__ int s_hits[256];
-    __shared__ int s_wcnt[8];
+__global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const BwdParams p) {
+    constexpr int kS = BwdStages<TDy>::value;
+    extern __shared__ __align__(128) uint8_t bwd_smem[];
+    __shared__ __align__(16) float s_wy[kS][kTile][kTabW];      // [slot][tile row][bin]
+    __shared__ __align__(16) float s_wx[kS][kTile][kTabW];      // [slot][tile col][bin]
+    __shared__ int4 s_meta[kBwdChunk];                  // per hit: k, bins, tile-relative ranges, y table row
+    __shared__ int s_xrow[kBwdChunk];                   // per hit: x table row of the first staged column
+    __shared__ int s_hits[kBwdChunk];
+    __shared__ int s_wcnt[2][kBwdWarps];                  // double-buffered by chunk parity
+    __shared__ uint64_t s_full[kS], s_empty[kS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool producer = (warp == kBwdWarps);
     int l = 0;
     while (l + 1 < p.L && (int)blockIdx.x >= p.tile_start[l + 1]) ++l;
     const int H = p.lv[l].H, W = p.lv[l].W;
-    const double sc = (double)p.lv[l].scale;
     const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
     int local = (int)blockIdx.x - p.tile_start[l];
     const int b = local / (tiles_x * tiles_y);
     local -= b * tiles_x * tiles_y;
     const int row0 = (local / tiles_x) * kTile, col0 = (local % tiles_x) * kTile;
-    const int PP = p.P * p.P;
-    const int row = row0 + warp;
+    const int P = p.P, PP = P * P;
+    const int trow = warp & 7, xh = (warp >> 3) * kHalf;   // consumers: tile row, first column
+    const int row = row0 + trow;
+    const int cw = min(p.C, 256);
     TDx* dx = static_cast<TDx*>(p.lv[l].data);
     const TDy* dy = static_cast<const TDy*>(p.dy);
     const int4* boxes = p.boxes + (size_t)l * p.K;
+    TDy* dybuf = reinterpret_cast<TDy*>(bwd_smem);          // [kS][PP * cw]
+    const size_t buf_elems = (size_t)PP * cw;
+
+    if (tid == 0) {
+        for (int s = 0; s < kS; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kBwdWarps); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    unsigned g = 0;                               // hits processed so far (slot / parity counter)
 
     for (int cb = 0; cb < p.C; cb += 256) {
         const int nch = min(256, p.C - cb);
-        float acc[kTile][8];
+        const bool lane_on = lane * 8 < nch;
+        float acc[kHalf][8];
 #pragma unroll
-        for (int x = 0; x < kTile; ++x)
+        for (int x = 0; x < kHalf; ++x)
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[x][e] = 0.f;
 
-        for (int k0 = 0; k0 < p.K; k0 += 256) {
-            // ---- find the RoIs of this chunk that touch the tile, in ascending index order
-            const int k = k0 + tid;
-            bool hit = false;
-            if (k < p.K) {
-                const int4 bx = __ldg(boxes + k);
-                hit = (bx.y >= bx.x) && bx.x <= row0 + kTile - 1 && bx.y >= row0 &&
-                      bx.z <= col0 + kTile - 1 && bx.w >= col0 &&
-                      ((int)__ldg(p.rois + (size_t)k * 5) == b);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) s_wcnt[warp] = __popc(bal);
-            __syncthreads();
-            int base = 0, nh = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const int c = s_wcnt[w];
-                if (w < warp) base += c;
-                nh += c;
-            }
-            if (hit) s_hits[base + __popc(bal & ((1u << lane) - 1u))] = k;
-            __syncthreads();
-
-            for (int h = 0; h < nh; ++h) {
-                const int kk = s_hits[h];
-                const int buf = h & 1;
-                if (tid < 2 * HTD_MAX_POOLED * kTile) {
-                    const int axis = tid / (HTD_MAX_POOLED * kTile);
-                    const int pp = (tid / kTile) % HTD_MAX_POOLED;
-                    const int j = tid % kTile;
-                    float wv = 0.f;
-                    if (pp < p.P) {
-                        const float* r = p.rois + (size_t)kk * 5;
-                        if (axis == 0) {
-                            Axis a = make_axis(r[2], r[4], sc, p.P, H, p.sr, 1);
-                            wv = axis_weight(a, pp, row0 + j);
-                        } else {
-                            Axis a = make_axis(r[1], r[3], sc, p.P, W, p.sr, 1);
-                            wv = axis_weight(a, pp, col0 + j);
-                        }
-                    }
-                    if (axis == 0) s_wy[buf][pp][j] = wv; else s_wx[buf][pp][j] = wv;
+        for (int k0 = 0, pass = 0; k0 < p.K; k0 += kBwdChunk, ++pass) {
+            int* wcnt = s_wcnt[pass & 1];
+            // ---- RoIs of this chunk that touch the tile, in ascending index order (consumers)
+            if (!producer) {
+                const int k = k0 + tid;
+                bool hit = false;
+                if (k < p.K) {
+                    const int4 bx = __ldg(boxes + k);
+                    hit = (bx.y >= bx.x) && bx.x <= row0 + kTile - 1 && bx.y >= row0 &&
+                          bx.z <= col0 + kTile - 1 && bx.w >= col0 &&
+                          ((int)__ldg(p.rois + (size_t)k * 5) == b);
                 }
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) wcnt[warp] = __popc(bal);
                 __syncthreads();
-                if (row < H) {
-                    const size_t dyk = (p.dy_per_level ? (size_t)l * p.K : 0) + kk;
-                    const float sbase = p.scale ? __ldg(p.scale + (size_t)l * p.K + kk) : 1.f;
-                    float av[8];
+                int base = 0;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) av[e] = 0.f;
-                    if (p.addvec) {
-                        const float* a = p.addvec + ((size_t)l * p.K + kk) * p.C + cb;
+                for (int w = 0; w < kBwdWarps; ++w)
+                    if (w < warp) base += wcnt[w];
+                if (hit) s_hits[base + __popc(bal & ((1u << lane) - 1u))] = k;
+            } else {
+                __syncthreads();
+            }
+            __syncthreads();
+            int nh = 0;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int c = lane_chan<kSplit>(lane, e);
-                            if (c < nch) av[e] = __ldg(a + c);
+            for (int w = 0; w < kBwdWarps; ++w) nh += wcnt[w];
+            if (nh == 0) continue;                // CTA-uniform
+
+            if (producer) {
+                // ---- metadata of all hits, lanes in parallel
+                for (int h = lane; h < nh; h += 32) {
+                    const int kk = s_hits[h];
+                    const size_t e = (size_t)l * p.K + kk;
+                    const int4 bx = __ldg(boxes + kk);
+                    const int off = __ldg(p.offsets + e);
+                    const int* rg = p.ranges + e * kRangeInts;
+                    int pa = 0, pb = -1, qa = 0, qb = -1;
+                    bool first = true;
+                    for (int pp = 0; pp < P; ++pp) {
+                        const int lo = __ldg(rg + pp), hi = __ldg(rg + HTD_MAX_POOLED + pp);
+                        if (hi >= lo && lo <= row0 + kTile - 1 && hi >= row0) {
+                            if (first) { pa = pp; first = false; }
+                            pb = pp;
                         }
                     }
-                    const int e0 = p.ring_edge;
-                    for (int ph = 0; ph < p.P; ++ph) {
-                        const float wyv = s_wy[buf][ph][warp];
-                        if (wyv == 0.f) continue;
-                        for (int pw = 0; pw < p.P; ++pw) {
-                            float cw[kTile];
-                            bool any = false;
-#pragma unroll
-                            for (int x = 0; x < kTile; ++x) {
-                                cw[x] = s_wx[buf][pw][x];
-                                any |= (cw[x] != 0.f);
-                            }
-                            if (!any) continue;
-                            float sv = sbase;
-                            if (e0 >= 0 && l == 0) {
-                                const bool interior = (e0 > 0) && ph >= e0 && ph < p.P - e0 &&
-                                                      pw >= e0 && pw < p.P - e0;
-                                if (!interior) sv += 1.f;
-                            }
-                            float v[8];
-                            Vec8<TDy, kSplit>::load(dy + ((dyk * PP + ph * p.P + pw) * p.C + cb),
-                                                    lane, nch, v);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = fmaf(sv, v[e], av[e]);
-#pragma unroll
-                            for (int x = 0; x < kTile; ++x) {
-                                const float wgt = wyv * cw[x];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) acc[x][e] = fmaf(wgt, v[e], acc[x][e]);
+                    first = true;
+                    for (int pp = 0; pp < P; ++pp) {
+                        const int lo = __ldg(rg + 2 * HTD_MAX_POOLED + pp);
+                        const int hi = __ldg(rg + 3 * HTD_MAX_POOLED + pp);
+                        if (hi >= lo && lo <= col0 + kTile - 1 && hi >= col0) {
+                            if (first) { qa = pp; first = false; }
+                            qb = pp;
+                        }
+                    }
+                    if (pb < pa || qb < qa) { pb = pa - 1; qb = qa - 1; }
+                    const int r_lo = max(bx.x, row0), r_hi = min(bx.y, row0 + kTile - 1);
+                    const int c_lo = max(bx.z, col0), c_hi = min(bx.w, col0 + kTile - 1);
+                    s_meta[h] = make_int4(kk, (pa & 0xff) | ((pb & 0xff) << 8) | ((qa & 0xff) << 16) | ((qb & 0xff) << 24),
+                                          (r_lo - row0) | ((r_hi - row0) << 8) | ((c_lo - col0) << 16) | ((c_hi - col0) << 24),
+                                          off + (r_lo - bx.x));
+                    s_xrow[h] = off + (bx.y - bx.x + 1) + (c_lo - bx.z);
+                }
+                __syncwarp();
+                // ---- stream hit h into slot (g + h) % kS
+                if (lane == 0) {
+                    for (int h = 0; h < nh; ++h) {
+                        const unsigned gi = g + h;
+                        const int slot = gi % kS;
+                        const int4 m = s_meta[h];
+                        const int kk = m.x;
+                        const int pa = (int)(signed char)(m.y & 0xff), pb = (int)(signed char)((m.y >> 8) & 0xff);
+                        const int qa = (int)(signed char)((m.y >> 16) & 0xff), qb = (int)(signed char)((m.y >> 24) & 0xff);
+                        const int rl = m.z & 0xff, rh = (m.z >> 8) & 0xff, cl = (m.z >> 16) & 0xff, ch = (m.z >> 24) & 0xff;
+                        const int nq = qb - qa + 1, np = pb - pa + 1;
+                        const uint32_t bin_bytes = (uint32_t)(nch * sizeof(TDy));
+                        const uint32_t wy_bytes = (uint32_t)(rh - rl + 1) * kTabW * 4u;
+                        const uint32_t wx_bytes = (uint32_t)(ch - cl + 1) * kTabW * 4u;
+                        const uint32_t dy_bytes = (np > 0 && nq > 0) ? (uint32_t)(np * nq) * bin_bytes : 0u;
+                        mbar_wait(&s_empty[slot], ((gi / kS) & 1u) ^ 1u);       // consumers left the slot
+                        mbar_expect_tx(&s_full[slot], wy_bytes + wx_bytes + dy_bytes);
+                        bulk_g2s(&s_wy[slot][rl][0], p.weights + (size_t)m.w * kTabW, wy_bytes, &s_full[slot]);
+                        bulk_g2s(&s_wx[slot][cl][0], p.weights + (size_t)s_xrow[h] * kTabW, wx_bytes, &s_full[slot]);
+                        if (dy_bytes) {
+                            const size_t dyk = (p.dy_per_level ? (size_t)l * p.K : 0) + kk;
+                            TDy* dst = dybuf + (size_t)slot * buf_elems;
+                            for (int ph = pa; ph <= pb; ++ph) {
+                                const TDy* src = dy + ((dyk * PP + ph * P + qa) * p.C + cb);
+                                if (p.C <= 256) {
+                                    bulk_g2s(dst, src, (uint32_t)nq * bin_bytes, &s_full[slot]);
+                                    dst += (size_t)nq * cw;
+                                } else {
+                                    for (int q = 0; q < nq; ++q, dst += cw)
+                                        bulk_g2s(dst, src + (size_t)q * p.C, bin_bytes, &s_full[slot]);
+                                }
                             }
                         }
                     }
                 }
-            }
-            __syncthreads();
-        }
-        if (row < H) {
+            } else {
+                // ===== consumers =====
+                for (int h = 0; h < nh; ++h) {
+                    const unsigned gi = g + h;
+                    const int slot = gi % kS;
+                    mbar_wait(&s_full[slot], (gi / kS) & 1u);
+                    const int4 m = s_meta[h];
+                    const int kk = m.x;
+                    const int pa = (int)(signed char)(m.y & 0xff), pb = (int)(signed char)((m.y >> 8) & 0xff);
+                    const int qa = (int)(signed char)((m.y >> 16) & 0xff), qb = (int)(signed char)((m.y >> 24) & 0xff);
+                    const int rl = m.z & 0xff, rh = (m.z >> 8) & 0xff, cl = (m.z >> 16) & 0xff, ch = (m.z >> 24) & 0xff;
+                    if (row < H && pb >= pa && trow >= rl && trow <= rh && xh <= ch && xh + kHalf - 1 >= cl) {
+                        const int nq = qb - qa + 1;
+                        const float sbase = p.scale ? __ldg(p.scale + (size_t)l * p.K + kk) : 1.f;
+                        float av[8];
 #pragma unroll
-            for (int x = 0; x < kTile; ++x) {
-                const int col = col0 + x;
+                        for (int e = 0; e < 8; ++e) av[e] = 0.f;
+                        if (p.addvec) {
+                            const float* a = p.addvec + ((size_t)l * p.K + kk) * p.C + cb;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int c = lane * 8 + e;
+                                if (c < nch) av[e] = __ldg(a + c);
+                            }
+                        }
+                        const int e0 = p.ring_edge;
+                        const TDy* src = dybuf + (size_t)slot * buf_elems + lane * 8;
+                        for (int ph = pa; ph <= pb; ++ph) {
+                            const float wyv = s_wy[slot][trow][ph];
+                            if (wyv == 0.f) continue;
+                            for (int pw = qa; pw <= qb; ++pw) {
+                                float cwt[kHalf];
+                                bool any = false;
+#pragma unroll
+                                for (int x = 0; x < kHalf; ++x) {
+                                    cwt[x] = (xh + x >= cl && xh + x <= ch) ? s_wx[slot][xh + x][pw] : 0.f;
+                                    any |= (cwt[x] != 0.f);
+                                }
+                                if (!any) continue;
+                                float sv = sbase;
+                                if (e0 >= 0 && l == 0) {
+                                    const bool interior = (e0 > 0) && ph >= e0 && ph < P - e0 &&
+                                                          pw >= e0 && pw < P - e0;
+                                    if (!interior) sv += 1.f;
+                                }
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                                if (lane_on) ld_smem8<TDy>(src + (size_t)((ph - pa) * nq + (pw - qa)) * cw, v);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) v[e] = fmaf(sv, v[e], av[e]);
+#pragma unroll
+                                for (int x = 0; x < kHalf; ++x) {
+                                    const float wgt = wyv * cwt[x];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) acc[x][e] = fmaf(wgt, v[e], acc[x][e]);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_empty[slot]);
+                }
+            }
+            g += (unsigned)nh;
+            __syncthreads();                      // s_hits / s_meta are rewritten by the next chunk
+        }
+        if (!producer && row < H) {
+#pragma unroll
+            for (int x = 0; x < kHalf; ++x) {
+                const int col = col0 + xh + x;
                 if (col < W)
-                    Vec8<TDx, kSplit>::store(dx + (((size_t)b * H + row) * W + col) * p.C + cb,
-                                             lane, nch, acc[x]);
+                    Vec8<TDx, false>::store(dx + (((size_t)b * H + row) * W + col) * p.C + cb,
+                                            lane, nch, acc[x]);
             }
         }
     }
@@ -389,9 +667,49 @@ int htd_roi_footprints(const HtdLevel* levels, int L, int B, const float* rois, 
     return HTD_OK;
 }
 
+long long htd_roi_plan_rows_bound(const HtdLevel* levels, int L, int K, int single_level) {
+    if (!levels || L < 1 || L > HTD_MAX_LEVELS || K < 0) return -1;
+    long long sum = 0, mx = 0;
+    for (int l = 0; l < L; ++l) {
+        const long long e = (long long)levels[l].H + levels[l].W;
+        sum += e;
+        if (e > mx) mx = e;
+    }
+    return (long long)K * (single_level ? mx : sum) + 1;
+}
+
+int htd_roi_plan(const HtdLevel* levels, int L, int B, const float* rois, int K,
+                 const int32_t* roi_level, int pooled, int sampling_ratio, int32_t* boxes,
+                 int32_t* offsets, int32_t* ranges, float* weights, long long rows_cap,
+                 unsigned long long* pixel_count, htd_stream_t stream) {
+    int rc = htd_roi_footprints(levels, L, B, rois, K, roi_level, pooled, sampling_ratio, boxes,
+                                pixel_count, stream);
+    if (rc) return rc;
+    if (K == 0) return HTD_OK;
+    HTD_CHECK_ARG(offsets && ranges && weights, "htd_roi_plan: null pointer");
+    const long long need = htd_roi_plan_rows_bound(levels, L, K, roi_level != nullptr);
+    HTD_CHECK_ARG(rows_cap >= need, "htd_roi_plan: weight table capacity %lld rows < bound %lld",
+                  rows_cap, need);
+    HTD_CHECK_ARG(need < 2147483647LL, "htd_roi_plan: table too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = L * K;
+    extent_scan_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const int4*>(boxes), n, offsets);
+    HTD_CHECK_LAUNCH("htd_roi_plan(scan)");
+    TableParams p;
+    rc = fill_levels(p.lv, levels, L, "htd_roi_plan");
+    if (rc) return rc;
+    p.L = L; p.K = K; p.P = pooled; p.sr = sampling_ratio;
+    p.rois = rois; p.boxes = reinterpret_cast<const int4*>(boxes); p.offsets = offsets;
+    p.ranges = ranges; p.weights = weights;
+    weight_table_kernel<<<n, 128, 0, st>>>(p);
+    HTD_CHECK_LAUNCH("htd_roi_plan(tables)");
+    return HTD_OK;
+}
+
 int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
                       const float* rois, int K, const int32_t* roi_level, int pooled,
-                      int sampling_ratio, const float* bias, void* out, int out_dtype,
+                      const int32_t* boxes, const int32_t* offsets, const int32_t* ranges,
+                      const float* weights, const float* bias, void* out, int out_dtype,
                       htd_stream_t stream) {
     FwdParams p;
     int rc = fill_levels(p.lv, levels, L, "htd_roi_align_fwd");
@@ -404,32 +722,50 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
                       (out_dtype == HTD_F32 || out_dtype == HTD_BF16),
                   "htd_roi_align_fwd: unsupported dtype in=%d out=%d", in_dtype, out_dtype);
     if (K == 0) return HTD_OK;
-    HTD_CHECK_ARG(rois && out, "htd_roi_align_fwd: null pointer");
-    p.L = L; p.B = B; p.C = C; p.K = K; p.P = pooled; p.sr = sampling_ratio;
+    HTD_CHECK_ARG(rois && out && boxes && offsets && ranges && weights,
+                  "htd_roi_align_fwd: null pointer");
+    p.L = L; p.B = B; p.C = C; p.K = K; p.P = pooled;
     p.rois = rois; p.roi_level = roi_level; p.bias = bias; p.out = out;
+    p.boxes = reinterpret_cast<const int4*>(boxes); p.offsets = offsets; p.ranges = ranges;
+    p.weights = weights;
     const long long tasks = roi_level ? (long long)K : (long long)K * L;
-    p.total_bins = tasks * pooled * pooled;
-    const long long blocks = (p.total_bins + kFwdWarps - 1) / kFwdWarps;
-    HTD_CHECK_ARG(blocks < 2147483647LL, "htd_roi_align_fwd: too many bins (%lld)", p.total_bins);
-    dim3 grid((unsigned)blocks), block(kFwdWarps * 32);
+    const long long blocks = tasks * pooled;
+    HTD_CHECK_ARG(blocks < 2147483647LL, "htd_roi_align_fwd: too many bins (%lld)", blocks * pooled);
+    dim3 grid((unsigned)blocks), block(pooled * 32);
     cudaStream_t st = (cudaStream_t)stream;
-    if (in_dtype == HTD_F32 && out_dtype == HTD_F32)
-        roi_align_fwd_kernel<float, float><<<grid, block, 0, st>>>(p);
-    else if (in_dtype == HTD_F32 && out_dtype == HTD_BF16)
-        roi_align_fwd_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(p);
-    else if (in_dtype == HTD_BF16 && out_dtype == HTD_F32)
-        roi_align_fwd_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(p);
-    else
-        roi_align_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(p);
+    const int cw = C < 256 ? C : 256;
+    const size_t smem = (size_t)pooled * kFwdStages * (kFwdPx * cw * dtype_size(in_dtype) +
+                                                       sizeof(uint64_t));
+#define HTD_FWD_LAUNCH(TI, TO)                                                                    \
+    do {                                                                                          \
+        static bool attr_done = false;                                                            \
+        if (!attr_done) {                                                                         \
+            cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_kernel<TI, TO>,                    \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                 HTD_MAX_POOLED * kFwdStages * (kFwdPx * 256 * (int)sizeof(TI) + 8)); \
+            if (e != cudaSuccess) {                                                               \
+                set_error("htd_roi_align_fwd: shared memory opt-in failed: %s",                   \
+                          cudaGetErrorString(e));                                                 \
+                return HTD_ERR_CUDA;                                                              \
+            }                                                                                     \
+            attr_done = true;                                                                     \
+        }                                                                                         \
+        roi_align_fwd_kernel<TI, TO><<<grid, block, smem, st>>>(p);                               \
+    } while (0)
+    if (in_dtype == HTD_F32 && out_dtype == HTD_F32) HTD_FWD_LAUNCH(float, float);
+    else if (in_dtype == HTD_F32 && out_dtype == HTD_BF16) HTD_FWD_LAUNCH(float, __nv_bfloat16);
+    else if (in_dtype == HTD_BF16 && out_dtype == HTD_F32) HTD_FWD_LAUNCH(__nv_bfloat16, float);
+    else HTD_FWD_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef HTD_FWD_LAUNCH
     HTD_CHECK_LAUNCH("htd_roi_align_fwd");
     return HTD_OK;
 }
 
 int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
-                      const float* rois, int K, const int32_t* boxes, int pooled,
-                      int sampling_ratio, const void* dy, int dy_dtype, int dy_per_level,
-                      const float* scale, int ring_edge, const float* addvec,
-                      htd_stream_t stream) {
+                      const float* rois, int K, const int32_t* boxes, const int32_t* offsets,
+                      const int32_t* ranges, const float* weights, int pooled, const void* dy,
+                      int dy_dtype, int dy_per_level, const float* scale, int ring_edge,
+                      const float* addvec, htd_stream_t stream) {
     BwdParams p;
     int rc = fill_levels(p.lv, grad_levels, L, "htd_roi_align_bwd");
     if (rc) return rc;
@@ -440,9 +776,11 @@ int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_d
     HTD_CHECK_ARG((dx_dtype == HTD_F32 || dx_dtype == HTD_BF16) &&
                       (dy_dtype == HTD_F32 || dy_dtype == HTD_BF16),
                   "htd_roi_align_bwd: unsupported dtype dx=%d dy=%d", dx_dtype, dy_dtype);
-    HTD_CHECK_ARG(K == 0 || (rois && boxes && dy), "htd_roi_align_bwd: null pointer");
-    p.L = L; p.B = B; p.C = C; p.K = K; p.P = pooled; p.sr = sampling_ratio;
+    HTD_CHECK_ARG(K == 0 || (rois && boxes && offsets && ranges && weights && dy),
+                  "htd_roi_align_bwd: null pointer");
+    p.L = L; p.B = B; p.C = C; p.K = K; p.P = pooled; p.sr = 0;
     p.rois = rois; p.boxes = reinterpret_cast<const int4*>(boxes); p.dy = dy;
+    p.offsets = offsets; p.ranges = ranges; p.weights = weights;
     p.dy_per_level = dy_per_level; p.scale = scale; p.ring_edge = ring_edge; p.addvec = addvec;
     long long total = 0;
     for (int l = 0; l < L; ++l) {
@@ -451,16 +789,31 @@ int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_d
     }
     for (int l = L; l <= HTD_MAX_LEVELS; ++l) p.tile_start[l] = (int)total;
     HTD_CHECK_ARG(total < 2147483647LL, "htd_roi_align_bwd: too many tiles (%lld)", total);
-    dim3 grid((unsigned)total), block(256);
+    dim3 grid((unsigned)total), block(kBwdThreads);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dy_dtype == HTD_F32 && dx_dtype == HTD_F32)
-        roi_align_bwd_kernel<float, float><<<grid, block, 0, st>>>(p);
-    else if (dy_dtype == HTD_F32 && dx_dtype == HTD_BF16)
-        roi_align_bwd_kernel<float, __nv_bfloat16><<<grid, block, 0, st>>>(p);
-    else if (dy_dtype == HTD_BF16 && dx_dtype == HTD_F32)
-        roi_align_bwd_kernel<__nv_bfloat16, float><<<grid, block, 0, st>>>(p);
-    else
-        roi_align_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, st>>>(p);
+    const int cw = C < 256 ? C : 256;
+    const size_t smem = (size_t)(dy_dtype == HTD_BF16 ? 4 : 2) * pooled * pooled * cw * dtype_size(dy_dtype);
+#define HTD_BWD_LAUNCH(TY, TX)                                                                    \
+    do {                                                                                          \
+        static bool attr_done = false;                                                            \
+        if (!attr_done) {                                                                         \
+            cudaError_t e = cudaFuncSetAttribute(                                                 \
+                roi_align_bwd_kernel<TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                BwdStages<TY>::value * HTD_MAX_POOLED * HTD_MAX_POOLED * 256 * (int)sizeof(TY));                     \
+            if (e != cudaSuccess) {                                                               \
+                set_error("htd_roi_align_bwd: shared memory opt-in failed: %s",                   \
+                          cudaGetErrorString(e));                                                 \
+                return HTD_ERR_CUDA;                                                              \
+            }                                                                                     \
+            attr_done = true;                                                                     \
+        }                                                                                         \
+        roi_align_bwd_kernel<TY, TX><<<grid, block, smem, st>>>(p);                               \
+    } while (0)
+    if (dy_dtype == HTD_F32 && dx_dtype == HTD_F32) HTD_BWD_LAUNCH(float, float);
+    else if (dy_dtype == HTD_F32 && dx_dtype == HTD_BF16) HTD_BWD_LAUNCH(float, __nv_bfloat16);
+    else if (dy_dtype == HTD_BF16 && dx_dtype == HTD_F32) HTD_BWD_LAUNCH(__nv_bfloat16, float);
+    else HTD_BWD_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef HTD_BWD_LAUNCH
     HTD_CHECK_LAUNCH("htd_roi_align_bwd");
     return HTD_OK;
 }

@@ -86,10 +86,39 @@ def roi_footprints(feats_cl, scales, rois, roi_level, pooled, sampling_ratio, co
     return (boxes, cnt) if count else boxes
 
 
+class RoIPlan:
+    """Sampling plan of one extractor call (htd_roi_plan): footprint boxes, table offsets, per-bin
+    pixel ranges and the separable axis-weight tables - shared by forward and backward."""
+
+    def __init__(self, feats_cl, scales, rois, roi_level, pooled, sampling_ratio):
+        L, K = len(feats_cl), rois.shape[0]
+        B = feats_cl[0].shape[0]
+        dev = rois.device
+        lv = _lib.make_levels([_bhwc(f) for f in feats_cl], scales)
+        rows = int(lib().htd_roi_plan_rows_bound(lv, L, K, int(roi_level is not None)))
+        self.boxes = torch.empty((L, K, 4), dtype=torch.int32, device=dev)
+        self.offsets = torch.empty(L * K + 1, dtype=torch.int32, device=dev)
+        self.ranges = torch.empty((L * K, 4 * 8), dtype=torch.int32, device=dev)
+        self.weights = torch.empty((rows, 8), dtype=torch.float32, device=dev)
+        self.pooled, self.sampling_ratio = pooled, sampling_ratio
+        check(lib().htd_roi_plan(lv, L, B, ptr(rois), K, ptr(roi_level), pooled, sampling_ratio,
+                                 ptr(self.boxes), ptr(self.offsets), ptr(self.ranges),
+                                 ptr(self.weights), rows, None, stream()), 'htd_roi_plan')
+
+    def tensors(self):
+        return self.boxes, self.offsets, self.ranges, self.weights
+
+    def pixels(self):
+        bx = self.boxes.reshape(-1, 4).long()
+        h = (bx[:, 1] - bx[:, 0] + 1).clamp(min=0)
+        w = (bx[:, 3] - bx[:, 2] + 1).clamp(min=0)
+        return int((h * w).sum().item())
+
+
 # ------------------------------------------------------------------------------------------
 # multi-level RoIAlign
 # ------------------------------------------------------------------------------------------
-def _roi_align_bwd(feat_shapes, feat_dtype, scales, rois, boxes, pooled, sampling_ratio, dy,
+def _roi_align_bwd(feat_shapes, feat_dtype, scales, rois, plan_tensors, pooled, dy,
                    dy_per_level, scale=None, ring_edge=-1, addvec=None):
     """Launch the gather backward; returns per-level dX as [B,C,H,W] channels-last tensors."""
     dev = rois.device
@@ -98,19 +127,20 @@ def _roi_align_bwd(feat_shapes, feat_dtype, scales, rois, boxes, pooled, samplin
     bufs = [torch.empty((B, s[2], s[3], C), dtype=feat_dtype, device=dev) for s in feat_shapes]
     lv = _lib.make_levels(bufs, scales)
     name = 'roi_align_bwd(BA)' if scale is not None else 'roi_align_bwd(single)'
+    boxes, offsets, ranges, weights = plan_tensors
     if _lib.ACCOUNT is not None:      # 49*C*b_out + fh*fw*C*4 per (RoI, level)
-        px = _count_pixels(bufs, scales, rois, boxes)
+        px = _count_pixels(boxes)
         n_dy = dy.numel() * dy.element_size()
         _lib.ACCOUNT.append((name, n_dy + px * C * 4))
     with _lib.timed(name):
         check(lib().htd_roi_align_bwd(lv, L, B, C, dt(feat_dtype), ptr(rois), rois.shape[0],
-                                      ptr(boxes), pooled, sampling_ratio, ptr(dy), dt(dy),
-                                      int(bool(dy_per_level)), ptr(scale), int(ring_edge),
+                                      ptr(boxes), ptr(offsets), ptr(ranges), ptr(weights), pooled, ptr(dy),
+                                      dt(dy), int(bool(dy_per_level)), ptr(scale), int(ring_edge),
                                       ptr(addvec), stream()), 'htd_roi_align_bwd')
     return [b.permute(0, 3, 1, 2) for b in bufs]
 
 
-def _count_pixels(bufs_bhwc, scales, rois, boxes):
+def _count_pixels(boxes):
     """Sum of footprint pixels fh*fw over all (level, RoI) of a footprint plan."""
     bx = boxes.reshape(-1, 4).long()
     h = (bx[:, 1] - bx[:, 0] + 1).clamp(min=0)
@@ -118,20 +148,25 @@ def _count_pixels(bufs_bhwc, scales, rois, boxes):
     return int((h * w).sum().item())
 
 
-def _fwd_launch(name, feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out):
+def _fwd_launch(name, feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out,
+                plan=None):
+    """Builds the sampling plan (unless given) and launches the forward gather; returns the plan."""
     L, K = len(feats), rois.shape[0]
     B, C = feats[0].shape[0], feats[0].shape[1]
     lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
+    if plan is None:
+        with _lib.timed('roi_plan'):
+            plan = RoIPlan(feats, scales, rois, roi_level, pooled, sampling_ratio)
     if _lib.ACCOUNT is not None:      # fh*fw*C*b_in + 49*C*b_out + 20 per (RoI, level)
-        boxes = roi_footprints(feats, scales, rois, roi_level, pooled, sampling_ratio)
-        px = _count_pixels(None, scales, rois, boxes)
         tasks = K if roi_level is not None else K * L
-        _lib.ACCOUNT.append((name, px * C * feats[0].element_size() +
+        _lib.ACCOUNT.append((name, plan.pixels() * C * feats[0].element_size() +
                              out.numel() * out.element_size() + 20 * tasks))
     with _lib.timed(name):
         check(lib().htd_roi_align_fwd(lv, L, B, C, dt(feats[0]), ptr(rois), K, ptr(roi_level),
-                                      pooled, sampling_ratio, ptr(bias_c), ptr(out), dt(out),
-                                      stream()), 'htd_roi_align_fwd')
+                                      pooled, ptr(plan.boxes), ptr(plan.offsets), ptr(plan.ranges),
+                                      ptr(plan.weights), ptr(bias_c), ptr(out), dt(out), stream()),
+              'htd_roi_align_fwd')
+    return plan
 
 
 def _bias_grad(g_kppc, rois, B):
@@ -161,26 +196,27 @@ class _RoIAlignLevels(torch.autograd.Function):
         out = torch.empty(lead + (pooled, pooled, C), dtype=out_dtype, device=rois.device)
         bias_shape = None if bias is None else tuple(bias.shape)
         bias_c = None if bias is None else bias.detach().reshape(B, C).float().contiguous()
-        _fwd_launch('roi_align_fwd(single)' if roi_level is not None else 'roi_align_fwd(all)',
-                    feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out)
-        boxes = None
-        if any(ctx.needs_input_grad[7:]):      # footprint plan for the gather backward
-            boxes = roi_footprints(feats, scales, rois, roi_level, pooled, sampling_ratio)
-        ctx.save_for_backward(rois, roi_level, boxes)
+        plan = _fwd_launch('roi_align_fwd(single)' if roi_level is not None else 'roi_align_fwd(all)',
+                           feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out)
+        ctx.with_dx = any(ctx.needs_input_grad[7:])
+        if ctx.with_dx:                        # the gather backward reuses the plan
+            ctx.save_for_backward(rois, roi_level, *plan.tensors())
+        else:
+            ctx.save_for_backward(rois, roi_level)
         ctx.cfg = (scales, pooled, sampling_ratio, [tuple(f.shape) for f in feats], feats[0].dtype,
                    bias_shape, B)
         return out.permute(0, 3, 1, 2) if roi_level is not None else out.permute(0, 1, 4, 2, 3)
 
     @staticmethod
     def backward(ctx, g):
-        rois, roi_level, boxes = ctx.saved_tensors
+        rois, roi_level = ctx.saved_tensors[:2]
         scales, pooled, sr, shapes, fdtype, bias_shape, B = ctx.cfg
         single = roi_level is not None
         g = (g.permute(0, 2, 3, 1) if single else g.permute(0, 1, 3, 4, 2)).contiguous()
         dbias = None
         grads = [None] * len(shapes)
-        if boxes is not None:
-            grads = _roi_align_bwd(shapes, fdtype, scales, rois, boxes, pooled, sr, g,
+        if ctx.with_dx:
+            grads = _roi_align_bwd(shapes, fdtype, scales, rois, ctx.saved_tensors[2:], pooled, g,
                                    dy_per_level=not single)
         if bias_shape is not None and ctx.needs_input_grad[2]:
             gb = g if single else g.sum(0)
@@ -216,7 +252,8 @@ class _BAFunction(torch.autograd.Function):
         rois = rois.detach().float().contiguous()
         fdt = feats[0].dtype
         R = torch.empty((L, K, pooled, pooled, C), dtype=fdt, device=dev)
-        _fwd_launch('roi_align_fwd(BA)', feats, scales, rois, None, pooled, sampling_ratio, None, R)
+        plan = _fwd_launch('roi_align_fwd(BA)', feats, scales, rois, None, pooled, sampling_ratio,
+                           None, R)
         m = torch.empty((L * K, C), dtype=torch.float32, device=dev)
         check(lib().htd_ba_bin_mean(ptr(R), dt(R), L * K, PP, C, ptr(m), stream()),
               'htd_ba_bin_mean')
@@ -234,10 +271,8 @@ class _BAFunction(torch.autograd.Function):
         check(lib().htd_ba_fuse_fwd(ptr(R), dt(R), ptr(logits), L, K, pooled, C, int(edge),
                                     ptr(add_c), dt(fdt), ptr(bias_c), ptr(rois), B, ptr(wts),
                                     ptr(out), dt(out), stream()), 'htd_ba_fuse_fwd')
-        boxes = None
-        if any(ctx.needs_input_grad[11:]):
-            boxes = roi_footprints(feats, scales, rois, None, pooled, sampling_ratio)
-        ctx.save_for_backward(rois, R, m, h, wts, W1, W2, boxes)
+        ctx.with_dx = any(ctx.needs_input_grad[11:])
+        ctx.save_for_backward(rois, R, m, h, wts, W1, W2, *(plan.tensors() if ctx.with_dx else ()))
         ctx.cfg = (scales, pooled, sampling_ratio, edge, [tuple(f.shape) for f in feats], fdt, B,
                    w1.shape, w2.shape, add is not None,
                    None if bias is None else tuple(bias.shape))
@@ -245,7 +280,7 @@ class _BAFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        rois, R, m, h, wts, W1, W2, boxes = ctx.saved_tensors
+        rois, R, m, h, wts, W1, W2 = ctx.saved_tensors[:7]
         (scales, pooled, sr, edge, shapes, fdt, B, w1_shape, w2_shape, has_add,
          bias_shape) = ctx.cfg
         L, K = wts.shape
@@ -264,8 +299,8 @@ class _BAFunction(torch.autograd.Function):
         db1 = dpre.sum(0)
         dm = (dpre @ W1) * (1.0 / PP)                      # [L*K, C], gradient of the bin mean
         grads = [None] * L
-        if boxes is not None:
-            grads = _roi_align_bwd(shapes, fdt, scales, rois, boxes, pooled, sr, g,
+        if ctx.with_dx:
+            grads = _roi_align_bwd(shapes, fdt, scales, rois, ctx.saved_tensors[7:], pooled, g,
                                    dy_per_level=False, scale=wts, ring_edge=edge,
                                    addvec=dm.contiguous())
         dadd = g.permute(0, 3, 1, 2) if (has_add and ctx.needs_input_grad[5]) else None

@@ -15,6 +15,8 @@
  *   htd_level_assign     SingleRoIExtractor.map_roi_levels
  *                        mmdet/models/roi_heads/roi_extractors/single_level_roi_extractor.py:32-51
  *                        (duplicate: bbox_heads/htd_bbox_head.py:129-135)
+ *   htd_roi_plan         the coordinate arithmetic of mmcv's roi_align kernels (sample grid,
+ *                        bilinear taps), hoisted out of the per-output-element loops
  *   htd_roi_align_fwd    mmcv ext_module.roi_align_forward as reached from
  *                        roi_extractors/base_roi_extractor.py:49-55, called at
  *                        single_level_roi_extractor.py:81-98 (per-level nonzero/gather/scatter
@@ -80,26 +82,42 @@ int htd_roi_footprints(const HtdLevel* levels, int L, int B, const float* rois, 
                        const int32_t* roi_level, int pooled, int sampling_ratio, int32_t* boxes,
                        unsigned long long* pixel_count, htd_stream_t stream);
 
-/* RoIAlign forward (aligned=True, avg).  roi_level != NULL: out[k] sampled from level
+/* Sampling plan shared by forward and backward, built once per extractor call:
+ *   boxes   [L*K][4]  footprint boxes as in htd_roi_footprints;
+ *   offsets [L*K+1]   exclusive scan of (fh + fw) over the entries e = l*K + k (table row offsets);
+ *   ranges  [L*K][4*HTD_MAX_POOLED]  per output bin p: first/last feature row (y lo[8], y hi[8]) and
+ *                     column (x lo[8], x hi[8]) it samples (hi < lo: empty bin);
+ *   weights [rows_cap][HTD_MAX_POOLED] fp32 separable axis weights: row offsets[e] + (r - row0)
+ *                     holds Wy[p][r] for the P bins, row offsets[e] + fh + (c - col0) holds Wx[p][c]
+ *                     (aligned=True, avg pooling; sampling_ratio 0 = adaptive ceil(roi/P) grid).
+ * rows_cap >= htd_roi_plan_rows_bound(levels, L, K, roi_level != NULL). */
+long long htd_roi_plan_rows_bound(const HtdLevel* levels, int L, int K, int single_level);
+int htd_roi_plan(const HtdLevel* levels, int L, int B, const float* rois, int K,
+                 const int32_t* roi_level, int pooled, int sampling_ratio, int32_t* boxes,
+                 int32_t* offsets, int32_t* ranges, float* weights, long long rows_cap,
+                 unsigned long long* pixel_count, htd_stream_t stream);
+
+/* RoIAlign forward (aligned=True, avg) from a plan.  roi_level != NULL: out[k] sampled from level
  * roi_level[k] (zeros when -1), out is [K, P, P, C].  roi_level == NULL: out is
  * [L, K, P, P, C], every RoI on every level.  bias (nullable): [B, C] fp32 added to every bin
  * of RoI k with batch index b (SFA fuse). */
 int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
                       const float* rois, int K, const int32_t* roi_level, int pooled,
-                      int sampling_ratio, const float* bias, void* out, int out_dtype,
+                      const int32_t* boxes, const int32_t* offsets, const int32_t* ranges,
+                      const float* weights, const float* bias, void* out, int out_dtype,
                       htd_stream_t stream);
 
-/* RoIAlign backward.  grad_levels[l].data receives dX_l [B,H,W,C] (fully written, zeros where
- * no RoI lands).  boxes from htd_roi_footprints with the same roi_level.  dy: [K,P,P,C], or
- * [L,K,P,P,C] when dy_per_level != 0.  Effective gradient of RoI k on level l, bin (ph,pw):
+/* RoIAlign backward from the same plan.  grad_levels[l].data receives dX_l [B,H,W,C] (fully
+ * written, zeros where no RoI lands).  dy: [K,P,P,C], or [L,K,P,P,C] when dy_per_level != 0.
+ * Effective gradient of RoI k on level l, bin (ph,pw):
  *     (scale[l*K+k] (1 if NULL) + ring(ph,pw)) * dy + addvec[(l*K+k)*C + c] (0 if NULL)
  * ring_edge < 0: ring == 0; ring_edge = e >= 0: on level 0 only, ring == 1 outside the interior
  * [e, P-e) x [e, P-e) (the BA border term, adaptative_roi_extractor.py:87-88). */
 int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
-                      const float* rois, int K, const int32_t* boxes, int pooled,
-                      int sampling_ratio, const void* dy, int dy_dtype, int dy_per_level,
-                      const float* scale, int ring_edge, const float* addvec,
-                      htd_stream_t stream);
+                      const float* rois, int K, const int32_t* boxes, const int32_t* offsets,
+                      const int32_t* ranges, const float* weights, int pooled, const void* dy,
+                      int dy_dtype, int dy_per_level, const float* scale, int ring_edge,
+                      const float* addvec, htd_stream_t stream);
 
 /* Layout / dtype conversion: src [N, R, S] -> dst [N, S, R] (NCHW->NHWC with R=C, S=H*W and
  * back with R=H*W, S=C).  dtypes HTD_F32 / HTD_BF16 independently for src and dst. */

@@ -58,29 +58,40 @@ def main():
         lv = ops.level_assign(rois, 4)
         K, P = rois.shape[0], pos_rois.shape[0]
         # ---- single level
-        boxes, cnt = ops.roi_footprints(x, scales, rois, lv, 7, 0, count=True)
-        px = int(cnt.sum().item())
+        plan = ops.RoIPlan(x, scales, rois, lv, 7, 0)
+        px = plan.pixels()
+        med, best = timeit(lambda: ops.RoIPlan(x, scales, rois, lv, 7, 0), a.iters, flush)
+        print(json.dumps(dict(kernel='roi_plan(single: footprints+scan+tables)', K=K, ms=med,
+                              ms_best=best)))
         by_f = px * C * bs + K * PP * C * bs + 20 * K
         by_b = K * PP * C * bs + px * C * 4
-        out = ops.roi_align_levels(x, rois, scales, roi_level=lv)
+        out = torch.empty(K, 7, 7, C, device=dev, dtype=dtype)
         g = torch.randn(K, 7, 7, C, device=dev).to(dtype)
         shapes = [tuple(t.shape) for t in x]
-        med, best = timeit(lambda: ops.roi_align_levels(x, rois, scales, roi_level=lv), a.iters, flush)
+        med, best = timeit(lambda: ops._fwd_launch('f', x, scales, rois, lv, 7, 0, None, out, plan=plan),
+                           a.iters, flush)
         print(json.dumps(dict(kernel='roi_align_fwd(single)', dtype=str(dtype), K=K, ms=med,
                               ms_best=best, alg_MB=by_f / 1e6, GBs=by_f / med / 1e6,
                               frac=by_f / med / 1e6 / PEAK, px_per_roi=px / K)))
-        med, best = timeit(lambda: ops._roi_align_bwd(shapes, dtype, scales, rois, boxes, 7, 0, g,
-                                                      False), a.iters, flush)
+        med, best = timeit(lambda: ops._roi_align_bwd(shapes, dtype, scales, rois, plan.tensors(), 7,
+                                                      g, False), a.iters, flush)
         dxb = sum(s[0] * s[2] * s[3] for s in shapes) * C * bs
         print(json.dumps(dict(kernel='roi_align_bwd(single)', dtype=str(dtype), K=K, ms=med,
                               ms_best=best, alg_MB=by_b / 1e6, GBs=by_b / med / 1e6,
                               frac=by_b / med / 1e6 / PEAK, dx_write_MB=dxb / 1e6,
                               dx_write_GBs=dxb / med / 1e6)))
         # ---- BA (all levels)
-        boxes, cnt = ops.roi_footprints(x, scales, pos_rois, None, 7, 0, count=True)
-        px = int(cnt.sum().item())
+        plan = ops.RoIPlan(x, scales, pos_rois, None, 7, 0)
+        px = plan.pixels()
+        bx = plan.boxes.long()
+        cnt = ((bx[..., 1] - bx[..., 0] + 1).clamp(min=0) * (bx[..., 3] - bx[..., 2] + 1).clamp(min=0)).sum(1)
+        med, best = timeit(lambda: ops.RoIPlan(x, scales, pos_rois, None, 7, 0), a.iters, flush)
+        print(json.dumps(dict(kernel='roi_plan(BA: footprints+scan+tables)', K=P, ms=med,
+                              ms_best=best)))
         by_f = px * C * bs + 4 * P * PP * C * bs + 20 * P
-        med, best = timeit(lambda: ops.roi_align_levels(x, pos_rois, scales), a.iters, flush)
+        outb = torch.empty(4, P, 7, 7, C, device=dev, dtype=dtype)
+        med, best = timeit(lambda: ops._fwd_launch('f', x, scales, pos_rois, None, 7, 0, None, outb,
+                                                   plan=plan), a.iters, flush)
         print(json.dumps(dict(kernel='roi_align_fwd(BA all levels)', dtype=str(dtype), K=P, ms=med,
                               ms_best=best, alg_MB=by_f / 1e6, GBs=by_f / med / 1e6,
                               frac=by_f / med / 1e6 / PEAK, px_per_roi=px / P,
@@ -89,8 +100,8 @@ def main():
         wts = torch.rand(4, P, device=dev)
         dm = torch.randn(4 * P, C, device=dev)
         by_b = P * PP * C * bs + px * C * 4
-        med, best = timeit(lambda: ops._roi_align_bwd(shapes, dtype, scales, pos_rois, boxes, 7, 0,
-                                                      gp, False, scale=wts, ring_edge=1, addvec=dm),
+        med, best = timeit(lambda: ops._roi_align_bwd(shapes, dtype, scales, pos_rois, plan.tensors(),
+                                                      7, gp, False, scale=wts, ring_edge=1, addvec=dm),
                            a.iters, flush)
         print(json.dumps(dict(kernel='roi_align_bwd(BA all levels)', dtype=str(dtype), K=P, ms=med,
                               ms_best=best, alg_MB=by_b / 1e6, GBs=by_b / med / 1e6,
