@@ -24,6 +24,10 @@ class HtdGemmGroup(ctypes.Structure):
 
 
 MAX_GROUPS = 64
+SCHED_SETS = 6
+SCHED_BYTES = SCHED_SETS * MAX_GROUPS * 48 + SCHED_SETS * (MAX_GROUPS + 1) * 4
+(SCHED_GROUP_ND, SCHED_GROUP_NN_S, SCHED_GROUP_NN_D, SCHED_GROUP_NS, SCHED_LEVEL_ND,
+ SCHED_LEVEL_DD) = range(6)
 
 
 class HtdLevel(ctypes.Structure):
@@ -65,6 +69,10 @@ SIGNATURES = {
     'htd_pgraph_group_transpose': [c_void_p, c_int, c_ll, c_void_p, c_int, c_float, c_float,
                                    c_void_p, c_int, c_ll, c_void_p],
     'htd_pgraph_segment_colsum': [c_void_p, c_int, c_ll, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    'htd_pgraph_schedule': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    'htd_pgraph_gemm_scheduled': [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int,
+                                  c_ll, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_int, c_ll,
+                                  c_void_p, c_int, c_void_p],
     'htd_pgraph_gemm': [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int,
                         c_void_p, c_int, c_ll, c_void_p, c_void_p, c_int, c_ll, c_void_p, c_int,
                         c_void_p],
@@ -107,6 +115,8 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.htd_last_error.restype = ctypes.c_char_p
         L.htd_abi_version.restype = c_int
+        L.htd_pgraph_max_tiles.restype = c_ll
+        L.htd_pgraph_max_tiles.argtypes = [c_int] * 9
         L.htd_roi_plan_rows_bound.restype = c_ll
         L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
         for name, args in SIGNATURES.items():

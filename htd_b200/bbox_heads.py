@@ -126,10 +126,14 @@ class BBoxHead(nn.Module):
 
     def loss(self, cls_score, bbox_pred, rois, labels, label_weights, bbox_targets, bbox_weights,
              reduction_override=None):
+        """bbox_head.py:141-186 in static-shape form: the reference selects the positive rows
+        with boolean masks (`.any()`, `.item()` host syncs, data-dependent shapes); here the same
+        sums are taken over ALL rows with the positive mask as a 0/1 factor and `avg_factor` kept
+        on the device - identical values, no host sync, capturable in a CUDA graph."""
         losses = dict()
         if cls_score is not None:
             cls_score = cls_score.float()                      # force_fp32 (bbox_head.py:141)
-            avg_factor = max(torch.sum(label_weights > 0).float().item(), 1.)
+            avg_factor = torch.sum(label_weights > 0).float().clamp(min=1.)
             if cls_score.numel() > 0:
                 losses['loss_cls'] = self.loss_cls(cls_score, labels, label_weights,
                                                    avg_factor=avg_factor,
@@ -137,20 +141,19 @@ class BBoxHead(nn.Module):
                 losses['acc'] = accuracy(cls_score, labels)
         if bbox_pred is not None:
             bbox_pred = bbox_pred.float()
-            pos = (labels >= 0) & (labels < self.num_classes)
-            if pos.any():
-                if self.reg_decoded_bbox:
-                    bbox_pred = self.bbox_coder.decode(rois[:, 1:], bbox_pred)
-                if self.reg_class_agnostic:
-                    pos_pred = bbox_pred.view(bbox_pred.size(0), 4)[pos]
-                else:
-                    pos_pred = bbox_pred.view(bbox_pred.size(0), -1, 4)[pos, labels[pos]]
-                losses['loss_bbox'] = self.loss_bbox(pos_pred, bbox_targets[pos].float(),
-                                                     bbox_weights[pos].float(),
-                                                     avg_factor=bbox_targets.size(0),
-                                                     reduction_override=reduction_override)
+            pos = ((labels >= 0) & (labels < self.num_classes)).to(bbox_pred.dtype)
+            if self.reg_decoded_bbox:
+                bbox_pred = self.bbox_coder.decode(rois[:, 1:], bbox_pred)
+            if self.reg_class_agnostic:
+                pred = bbox_pred.view(bbox_pred.size(0), 4)
             else:
-                losses['loss_bbox'] = bbox_pred[pos].sum()
+                idx = labels.clamp(0, self.num_classes - 1)
+                pred = bbox_pred.view(bbox_pred.size(0), -1, 4)[
+                    torch.arange(bbox_pred.size(0), device=bbox_pred.device), idx]
+            losses['loss_bbox'] = self.loss_bbox(pred, bbox_targets.float(),
+                                                 bbox_weights.float() * pos[:, None],
+                                                 avg_factor=bbox_targets.size(0),
+                                                 reduction_override=reduction_override)
         return losses
 
     # ---- decoding (bbox_head.py:188-335) ------------------------------------------------------
@@ -191,15 +194,26 @@ class BBoxHead(nn.Module):
         boxes = self.bbox_coder.decode(rois[:, 1:], bbox_pred, max_shape=img_meta['img_shape'])
         return torch.cat((rois[:, [0]], boxes), dim=1)
 
-    def refine_bboxes(self, rois, labels, bbox_preds, pos_is_gts, img_metas):
-        out = []
+    def refine_bboxes(self, rois, labels, bbox_preds, pos_is_gts, img_metas, num_per_img=None):
+        """bbox_head.py:227-303.  ``num_per_img`` (RoIs of every image, in order) replaces the
+        reference's per-image ``nonzero`` (host sync); ``pos_is_gts[i] is None`` means "no sampled
+        box of image i is a ground-truth box" and skips the boolean filter (static shapes)."""
+        out, off = [], 0
         for i in range(len(img_metas)):
-            inds = torch.nonzero(rois[:, 0] == i, as_tuple=False).squeeze(dim=1)
+            if num_per_img is not None:
+                inds = slice(off, off + num_per_img[i])
+                off += num_per_img[i]
+                n = num_per_img[i]
+            else:
+                inds = torch.nonzero(rois[:, 0] == i, as_tuple=False).squeeze(dim=1)
+                n = inds.numel()
             boxes = self.regress_by_class(rois[inds, 1:], labels[inds], bbox_preds[inds],
                                           img_metas[i])
-            keep = pos_is_gts[i].new_ones(inds.numel())
-            keep[:len(pos_is_gts[i])] = 1 - pos_is_gts[i]
-            out.append(boxes[keep.type(torch.bool)])
+            if pos_is_gts[i] is not None:
+                keep = pos_is_gts[i].new_ones(n)
+                keep[:len(pos_is_gts[i])] = 1 - pos_is_gts[i]
+                boxes = boxes[keep.type(torch.bool)]
+            out.append(boxes)
         return out
 
 
@@ -307,9 +321,10 @@ class HTDBBoxHead(BBoxHead):
         return rois[:, 0].long().clamp_(0, num_imgs - 1)
 
     def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
-                global_feat=None, num_imgs=None):
+                global_feat=None, num_imgs=None, max_rois_per_img=None):
         """Reference signature (htd_bbox_head.py:157).  ``num_imgs`` (optional) avoids the host
-        sync of ``int(max(rois[:,0])) + 1`` (:159); ``global_feat`` gives it otherwise."""
+        sync of ``int(max(rois[:,0])) + 1`` (:159); ``global_feat`` gives it otherwise.
+        ``max_rois_per_img`` (optional) bounds the PGraph group size (default: all RoIs)."""
         if num_imgs is None:
             num_imgs = global_feat.size(0) if global_feat is not None \
                 else int(torch.max(rois[..., 0])) + 1
@@ -337,7 +352,8 @@ class HTDBBoxHead(BBoxHead):
         sam = torch.mm(fc_cls_0(x_c).softmax(-1), prototype)
         with torch.no_grad():
             levels = ops.level_assign(rois, len(feat), self.finest_scale)
-            plan = pgraph.GraphPlan(rois, levels, num_imgs, len(feat), x_c.dtype)
+            plan = pgraph.GraphPlan(rois, levels, num_imgs, len(feat), x_c.dtype,
+                                    max_group=max_rois_per_img, d=d, ds=prototype.size(1))
         self.last_plan = plan
         layers = self.graph_layer_cls
         refined = pgraph.pgraph_refine(x_c, sam, [m.weight for m in layers],
@@ -386,6 +402,7 @@ class GlobalContextHead(nn.Module):
     def loss(self, pred, labels):
         pred = pred.float()
         targets = pred.new_zeros(pred.size())
-        for i, label in enumerate(labels):
-            targets[i, label.unique()] = 1.0
+        for i, label in enumerate(labels):          # multi-hot; duplicates are harmless, so the
+            if label.numel():                       # reference's `.unique()` (host sync) is not needed
+                targets[i].index_fill_(0, label.long(), 1.0)
         return self.loss_weight * self.criterion(pred, targets)

@@ -253,7 +253,7 @@ def _reduce(loss, weight, reduction, avg_factor):
     if avg_factor is None:
         return loss.mean() if reduction == 'mean' else loss.sum() if reduction == 'sum' else loss
     if reduction == 'mean':
-        return loss.sum() / avg_factor
+        return loss.sum() / avg_factor          # avg_factor: python number or 0-dim device tensor
     if reduction == 'none':
         return loss
     raise ValueError('avg_factor can not be used with reduction="sum"')

@@ -46,7 +46,27 @@ struct GemmParams {
     long long ldt;
     const float* bias;
     int relu;
+    const HtdGemmGroup* grp_dev;      // device-resident schedule (htd_pgraph_schedule); NULL: use grp[]
+    const int* tile_start_dev;
 };
+
+// blockIdx -> (group, local tile); false when the CTA is beyond the scheduled tiles
+__device__ __forceinline__ bool decode_tile(const GemmParams& p, HtdGemmGroup& grp, int& local) {
+    if (p.grp_dev != nullptr) {
+        const int total = p.tile_start_dev[HTD_MAX_GROUPS];
+        if ((int)blockIdx.x >= total) return false;
+        int g = 0;
+        while (g + 1 < HTD_MAX_GROUPS && (int)blockIdx.x >= p.tile_start_dev[g + 1]) ++g;
+        grp = p.grp_dev[g];
+        local = (int)blockIdx.x - p.tile_start_dev[g];
+    } else {
+        int g = 0;
+        while (g + 1 < p.G && (int)blockIdx.x >= p.tile_start[g + 1]) ++g;
+        grp = p.grp[g];
+        local = (int)blockIdx.x - p.tile_start[g];
+    }
+    return true;
+}
 
 // Shared epilogue: one thread owns output row m of its group and 32 consecutive columns n0.. of
 // it (v[j] = fp32 accumulators).  Applies bias / relu, then writes D (optionally through the
@@ -193,11 +213,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // ---- tile decode
-    int g = 0;
-    while (g + 1 < p.G && (int)blockIdx.x >= p.tile_start[g + 1]) ++g;
-    const HtdGemmGroup grp = p.grp[g];
-    const int local = (int)blockIdx.x - p.tile_start[g];
+    // ---- tile decode (uniform per CTA; surplus CTAs of a scheduled launch leave before any setup)
+    HtdGemmGroup grp;
+    int local;
+    if (!decode_tile(p, grp, local)) return;
     const int tiles_n = (grp.N + kBN - 1) / kBN;
     const int mt = local / tiles_n, nt = local % tiles_n;
     const int kblocks = (grp.K + kBK - 1) / kBK;
@@ -298,10 +317,9 @@ __global__ void __launch_bounds__(256) pgraph_gemm_f32_kernel(const float* __res
                                                               long long b_ld, const GemmParams p) {
     __shared__ float sA[kSK][kSM + 4];
     __shared__ float sB[kSK][kSN + 4];
-    int g = 0;
-    while (g + 1 < p.G && (int)blockIdx.x >= p.tile_start[g + 1]) ++g;
-    const HtdGemmGroup grp = p.grp[g];
-    const int local = (int)blockIdx.x - p.tile_start[g];
+    HtdGemmGroup grp;
+    int local;
+    if (!decode_tile(p, grp, local)) return;
     const int tiles_n = (grp.N + kSN - 1) / kSN;
     const int m0 = (local / tiles_n) * kSM, n0 = (local % tiles_n) * kSN;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -366,6 +384,51 @@ __global__ void __launch_bounds__(256) pgraph_gemm_f32_kernel(const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// device-side schedule of the six PGraph contraction shapes
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HTD_SCHED_SETS * HTD_MAX_GROUPS) schedule_kernel(
+    const int* __restrict__ table, int B, int L, int d, int ds, int bm, int bn,
+    HtdGemmGroup* __restrict__ groups, int* __restrict__ tile_start) {
+    __shared__ int s_tiles[HTD_SCHED_SETS][HTD_MAX_GROUPS];
+    const int set = threadIdx.x / HTD_MAX_GROUPS, g = threadIdx.x % HTD_MAX_GROUPS;
+    const int G = L * B;
+    HtdGemmGroup q;
+    q.M = q.N = q.K = 0;
+    q.a_row = q.a_k0 = q.b_row = q.b_k0 = q.d_row = q.d_col = q.dt_row = q.dt_col = q.bias_off = 0;
+    if (set < HTD_SCHED_LEVEL_ND) {
+        if (g < G) {
+            const int off = table[2 * g], n = table[2 * g + 1];
+            if (n > 0) {
+                q.a_row = off; q.d_row = off;
+                if (set == HTD_SCHED_GROUP_ND) { q.M = n; q.N = d; q.K = n; q.b_k0 = off; q.dt_col = off; }
+                else if (set == HTD_SCHED_GROUP_NN_S) { q.M = n; q.N = n; q.K = ds; q.b_row = off; }
+                else if (set == HTD_SCHED_GROUP_NN_D) { q.M = n; q.N = n; q.K = d; q.b_row = off; }
+                else { q.M = n; q.N = ds; q.K = n; q.b_k0 = off; }
+            }
+        }
+    } else if (g < L) {
+        const int loff = table[2 * G + 2 * g], ln = table[2 * G + 2 * g + 1];
+        if (ln > 0) {
+            if (set == HTD_SCHED_LEVEL_ND) {
+                q.M = ln; q.N = d; q.K = d; q.a_row = loff; q.b_row = g * d; q.d_row = loff;
+                q.dt_col = loff; q.bias_off = g * d;
+            } else {
+                q.M = d; q.N = d; q.K = ln; q.a_k0 = loff; q.b_k0 = loff; q.d_row = g * d;
+            }
+        }
+    }
+    groups[set * HTD_MAX_GROUPS + g] = q;
+    s_tiles[set][g] = ((q.M + bm - 1) / bm) * ((q.N + bn - 1) / bn);
+    __syncthreads();
+    if (g == 0) {
+        int acc = 0;
+        int* ts = tile_start + set * (HTD_MAX_GROUPS + 1);
+        for (int i = 0; i < HTD_MAX_GROUPS; ++i) { ts[i] = acc; acc += s_tiles[set][i]; }
+        ts[HTD_MAX_GROUPS] = acc;
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -408,50 +471,12 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
 
 using namespace htd;
 
-extern "C" int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void* B,
-                               long long b_rows, long long b_ld, int ab_dtype,
-                               const HtdGemmGroup* groups, int G, void* D, int d_dtype,
-                               long long ldd, const int32_t* d_rowmap, void* DT, int dt_dtype,
-                               long long ldt, const float* bias, int relu, htd_stream_t stream) {
-    HTD_CHECK_ARG(G >= 0 && G <= HTD_MAX_GROUPS, "htd_pgraph_gemm: G=%d exceeds %d", G, HTD_MAX_GROUPS);
-    if (G == 0) return HTD_OK;
-    HTD_CHECK_ARG(A && B && groups && (D || DT), "htd_pgraph_gemm: null pointer");
-    HTD_CHECK_ARG(ab_dtype == HTD_F32 || ab_dtype == HTD_BF16, "htd_pgraph_gemm: bad operand dtype");
-    HTD_CHECK_ARG((!D || d_dtype == HTD_F32 || d_dtype == HTD_BF16) &&
-                      (!DT || dt_dtype == HTD_F32 || dt_dtype == HTD_BF16),
-                  "htd_pgraph_gemm: bad output dtype");
-    HTD_CHECK_ARG(a_rows > 0 && b_rows > 0 && a_ld > 0 && b_ld > 0, "htd_pgraph_gemm: bad extents");
+static int launch_gemm(const void* A, long long a_rows, long long a_ld, const void* B,
+                       long long b_rows, long long b_ld, int ab_dtype, GemmParams& p,
+                       long long total, cudaStream_t st) {
     const bool tc = (ab_dtype == HTD_BF16);
-    const int bm = tc ? kBM : kSM, bn = tc ? kBN : kSN;
-    GemmParams p;
-    long long total = 0;
-    for (int g = 0; g < G; ++g) {
-        const HtdGemmGroup& q = groups[g];
-        HTD_CHECK_ARG(q.M >= 0 && q.N >= 0 && q.K >= 0 && q.a_row >= 0 && q.b_row >= 0 &&
-                          q.a_k0 >= 0 && q.b_k0 >= 0 && q.d_row >= 0 && q.d_col >= 0 &&
-                          q.dt_row >= 0 && q.dt_col >= 0,
-                      "htd_pgraph_gemm: malformed group %d", g);
-        HTD_CHECK_ARG(q.a_row + (long long)q.M <= a_rows && q.b_row + (long long)q.N <= b_rows &&
-                          q.a_k0 + (long long)q.K <= a_ld && q.b_k0 + (long long)q.K <= b_ld,
-                      "htd_pgraph_gemm: group %d exceeds the operand extents", g);
-        p.grp[g] = q;
-        p.tile_start[g] = (int)total;
-        total += (long long)((q.M + bm - 1) / bm) * ((q.N + bn - 1) / bn);
-    }
-    for (int g = G; g <= HTD_MAX_GROUPS; ++g) p.tile_start[g] = (int)total;
-    p.G = G;
-    p.D = D;
-    p.d_is_bf16 = (d_dtype == HTD_BF16);
-    p.ldd = ldd;
-    p.d_rowmap = d_rowmap;
-    p.DT = DT;
-    p.dt_is_bf16 = (dt_dtype == HTD_BF16);
-    p.ldt = ldt;
-    p.bias = bias;
-    p.relu = relu;
-    if (total == 0) return HTD_OK;
+    if (total <= 0) return HTD_OK;
     HTD_CHECK_ARG(total < 2147483647LL, "htd_pgraph_gemm: too many tiles");
-    cudaStream_t st = (cudaStream_t)stream;
     if (!tc) {
         pgraph_gemm_f32_kernel<<<(unsigned)total, 256, 0, st>>>(static_cast<const float*>(A), a_ld,
                                                                 static_cast<const float*>(B), b_ld, p);
@@ -461,11 +486,6 @@ extern "C" int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, 
     HTD_CHECK_ARG(a_ld % 8 == 0 && b_ld % 8 == 0,
                   "htd_pgraph_gemm: leading dimensions must be multiples of 8 (a_ld=%lld b_ld=%lld)",
                   a_ld, b_ld);
-    for (int g = 0; g < G; ++g)
-        HTD_CHECK_ARG(groups[g].a_k0 % 8 == 0 && groups[g].b_k0 % 8 == 0,
-                      "htd_pgraph_gemm: group %d: K offsets must be multiples of 8 (TMA needs "
-                      "16-byte aligned coordinates), got a_k0=%d b_k0=%d", g, groups[g].a_k0,
-                      groups[g].b_k0);
     HTD_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0,
                   "htd_pgraph_gemm: operands must be 16-byte aligned");
     CUtensorMap ma, mb;
@@ -487,4 +507,118 @@ extern "C" int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, 
     pgraph_gemm_kernel<<<(unsigned)total, kGemmThreads, kSmemBytes, st>>>(ma, mb, p);
     HTD_CHECK_LAUNCH("htd_pgraph_gemm(bf16)");
     return HTD_OK;
+}
+
+static int fill_common(GemmParams& p, const void* A, const void* B, int ab_dtype, long long a_rows,
+                       long long b_rows, long long a_ld, long long b_ld, void* D, int d_dtype,
+                       long long ldd, const int32_t* d_rowmap, void* DT, int dt_dtype, long long ldt,
+                       const float* bias, int relu) {
+    HTD_CHECK_ARG(A && B && (D || DT), "htd_pgraph_gemm: null pointer");
+    HTD_CHECK_ARG(ab_dtype == HTD_F32 || ab_dtype == HTD_BF16, "htd_pgraph_gemm: bad operand dtype");
+    HTD_CHECK_ARG((!D || d_dtype == HTD_F32 || d_dtype == HTD_BF16) &&
+                      (!DT || dt_dtype == HTD_F32 || dt_dtype == HTD_BF16),
+                  "htd_pgraph_gemm: bad output dtype");
+    HTD_CHECK_ARG(a_rows > 0 && b_rows > 0 && a_ld > 0 && b_ld > 0, "htd_pgraph_gemm: bad extents");
+    p.D = D;
+    p.d_is_bf16 = (d_dtype == HTD_BF16);
+    p.ldd = ldd;
+    p.d_rowmap = d_rowmap;
+    p.DT = DT;
+    p.dt_is_bf16 = (dt_dtype == HTD_BF16);
+    p.ldt = ldt;
+    p.bias = bias;
+    p.relu = relu;
+    p.grp_dev = nullptr;
+    p.tile_start_dev = nullptr;
+    p.G = 0;
+    return HTD_OK;
+}
+
+extern "C" int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void* B,
+                               long long b_rows, long long b_ld, int ab_dtype,
+                               const HtdGemmGroup* groups, int G, void* D, int d_dtype,
+                               long long ldd, const int32_t* d_rowmap, void* DT, int dt_dtype,
+                               long long ldt, const float* bias, int relu, htd_stream_t stream) {
+    HTD_CHECK_ARG(G >= 0 && G <= HTD_MAX_GROUPS, "htd_pgraph_gemm: G=%d exceeds %d", G, HTD_MAX_GROUPS);
+    if (G == 0) return HTD_OK;
+    HTD_CHECK_ARG(groups != nullptr, "htd_pgraph_gemm: null group table");
+    GemmParams p;
+    int rc = fill_common(p, A, B, ab_dtype, a_rows, b_rows, a_ld, b_ld, D, d_dtype, ldd, d_rowmap,
+                         DT, dt_dtype, ldt, bias, relu);
+    if (rc) return rc;
+    const bool tc = (ab_dtype == HTD_BF16);
+    const int bm = tc ? kBM : kSM, bn = tc ? kBN : kSN;
+    long long total = 0;
+    for (int g = 0; g < G; ++g) {
+        const HtdGemmGroup& q = groups[g];
+        HTD_CHECK_ARG(q.M >= 0 && q.N >= 0 && q.K >= 0 && q.a_row >= 0 && q.b_row >= 0 &&
+                          q.a_k0 >= 0 && q.b_k0 >= 0 && q.d_row >= 0 && q.d_col >= 0 &&
+                          q.dt_row >= 0 && q.dt_col >= 0,
+                      "htd_pgraph_gemm: malformed group %d", g);
+        HTD_CHECK_ARG(q.a_row + (long long)q.M <= a_rows && q.b_row + (long long)q.N <= b_rows &&
+                          q.a_k0 + (long long)q.K <= a_ld && q.b_k0 + (long long)q.K <= b_ld,
+                      "htd_pgraph_gemm: group %d exceeds the operand extents", g);
+        HTD_CHECK_ARG(!tc || (q.a_k0 % 8 == 0 && q.b_k0 % 8 == 0),
+                      "htd_pgraph_gemm: group %d: K offsets must be multiples of 8 (TMA needs "
+                      "16-byte aligned coordinates), got a_k0=%d b_k0=%d", g, q.a_k0, q.b_k0);
+        p.grp[g] = q;
+        p.tile_start[g] = (int)total;
+        total += (long long)((q.M + bm - 1) / bm) * ((q.N + bn - 1) / bn);
+    }
+    for (int g = G; g <= HTD_MAX_GROUPS; ++g) p.tile_start[g] = (int)total;
+    p.G = G;
+    return launch_gemm(A, a_rows, a_ld, B, b_rows, b_ld, ab_dtype, p, total, (cudaStream_t)stream);
+}
+
+extern "C" int htd_pgraph_schedule(const int32_t* table, int B, int L, int d, int ds, int ab_dtype,
+                                   void* sched, htd_stream_t stream) {
+    HTD_CHECK_ARG(table && sched, "htd_pgraph_schedule: null pointer");
+    HTD_CHECK_ARG(B >= 1 && L >= 1 && L * B <= HTD_MAX_GROUPS && d >= 1 && ds >= 1,
+                  "htd_pgraph_schedule: bad sizes B=%d L=%d d=%d ds=%d", B, L, d, ds);
+    HTD_CHECK_ARG(ab_dtype == HTD_F32 || ab_dtype == HTD_BF16, "htd_pgraph_schedule: bad dtype");
+    const bool tc = (ab_dtype == HTD_BF16);
+    HtdGemmGroup* groups = static_cast<HtdGemmGroup*>(sched);
+    int* tile_start = reinterpret_cast<int*>(groups + HTD_SCHED_SETS * HTD_MAX_GROUPS);
+    schedule_kernel<<<1, HTD_SCHED_SETS * HTD_MAX_GROUPS, 0, (cudaStream_t)stream>>>(
+        table, B, L, d, ds, tc ? kBM : kSM, tc ? kBN : kSN, groups, tile_start);
+    HTD_CHECK_LAUNCH("htd_pgraph_schedule");
+    return HTD_OK;
+}
+
+extern "C" long long htd_pgraph_max_tiles(int set, int K, int B, int L, int max_group, int Ncap,
+                                          int d, int ds, int ab_dtype) {
+    const bool tc = (ab_dtype == HTD_BF16);
+    const long long bm = tc ? kBM : kSM, bn = tc ? kBN : kSN;
+    auto cd = [](long long a, long long b) { return (a + b - 1) / b; };
+    const long long G = (long long)L * B;
+    const long long mrows = cd(K, bm) + G;           // sum over groups of ceil(n / bm)
+    switch (set) {
+        case HTD_SCHED_GROUP_ND: return mrows * cd(d, bn);
+        case HTD_SCHED_GROUP_NN_S:
+        case HTD_SCHED_GROUP_NN_D: return mrows * cd(max_group, bn);
+        case HTD_SCHED_GROUP_NS: return mrows * cd(ds, bn);
+        case HTD_SCHED_LEVEL_ND: return (cd(Ncap, bm) + L) * cd(d, bn);
+        case HTD_SCHED_LEVEL_DD: return (long long)L * cd(d, bm) * cd(d, bn);
+        default: return -1;
+    }
+}
+
+extern "C" int htd_pgraph_gemm_scheduled(const void* A, long long a_rows, long long a_ld,
+                                         const void* B, long long b_rows, long long b_ld,
+                                         int ab_dtype, const void* sched, int set,
+                                         long long max_tiles, void* D, int d_dtype, long long ldd,
+                                         const int32_t* d_rowmap, void* DT, int dt_dtype,
+                                         long long ldt, const float* bias, int relu,
+                                         htd_stream_t stream) {
+    HTD_CHECK_ARG(sched && set >= 0 && set < HTD_SCHED_SETS && max_tiles >= 0,
+                  "htd_pgraph_gemm_scheduled: bad schedule arguments");
+    GemmParams p;
+    int rc = fill_common(p, A, B, ab_dtype, a_rows, b_rows, a_ld, b_ld, D, d_dtype, ldd, d_rowmap,
+                         DT, dt_dtype, ldt, bias, relu);
+    if (rc) return rc;
+    const HtdGemmGroup* groups = static_cast<const HtdGemmGroup*>(sched);
+    const int* tile_start = reinterpret_cast<const int*>(groups + HTD_SCHED_SETS * HTD_MAX_GROUPS);
+    p.grp_dev = groups + set * HTD_MAX_GROUPS;
+    p.tile_start_dev = tile_start + set * (HTD_MAX_GROUPS + 1);
+    return launch_gemm(A, a_rows, a_ld, B, b_rows, b_ld, ab_dtype, p, max_tiles, (cudaStream_t)stream);
 }

@@ -29,9 +29,15 @@ def _round_up(a, b):
 
 
 class GraphPlan:
-    """Sorted-space layout + local graph of one batch of RoIs (no gradients involved)."""
+    """Sorted-space layout + local graph of one batch of RoIs (no gradients involved).
 
-    def __init__(self, rois, levels, num_imgs, num_levels, op_dtype):
+    Everything is sized from static bounds (K RoIs, ``max_group`` RoIs per (image, level) group at
+    most) and scheduled on the device, so building and using a plan involves NO host read and
+    the whole step can be captured in a CUDA graph; ``groups`` / ``level_blocks`` / ``Npad``
+    (inspection, tests) read the table lazily."""
+
+    def __init__(self, rois, levels, num_imgs, num_levels, op_dtype, max_group=None, d=1024,
+                 ds=1025):
         _lib.require_cuda(rois, levels)
         dev = rois.device
         rois = rois.detach().float().contiguous()
@@ -40,8 +46,12 @@ class GraphPlan:
         if L * B > _lib.MAX_GROUPS:
             raise ValueError(f'PGraph supports at most {_lib.MAX_GROUPS} (image, level) groups per '
                              f'call, got {L}x{B}')
-        ncap = K + L * ALIGN + L * B * GROUP_ALIGN
-        self.K, self.B, self.L, self.op_dtype = K, B, L, op_dtype
+        self.K, self.B, self.L, self.op_dtype, self.d, self.ds = K, B, L, op_dtype, d, ds
+        self.max_group = max(1, min(K, int(max_group) if max_group else K))
+        ncap = _round_up(K + L * ALIGN + L * B * GROUP_ALIGN, ALIGN)
+        self.Ncap = ncap
+        self.ldn = max(_round_up(self.max_group, ALIGN), ALIGN)
+        self.ldb = self.ldn // 32
         self.perm = torch.empty(ncap, dtype=torch.int32, device=dev)
         self.pos = torch.empty(K, dtype=torch.int32, device=dev)
         self.rowspan = torch.empty((ncap, 2), dtype=torch.int32, device=dev)
@@ -51,25 +61,45 @@ class GraphPlan:
         check(lib().htd_pgraph_plan(ptr(rois), ptr(levels), K, B, L, ALIGN, ncap, ptr(self.perm),
                                     ptr(self.pos), ptr(self.rowspan), ptr(self.boxes),
                                     ptr(self.table_dev), stream()), 'htd_pgraph_plan')
-        tab = self.table_dev.cpu().tolist()          # the one host read of the PGraph path
-        self.groups = [(g // B, g % B, tab[2 * g], tab[2 * g + 1]) for g in range(L * B)
-                       if tab[2 * g + 1] > 0]        # (level, image, off, n)
-        self.level_blocks = [(l, tab[2 * L * B + 2 * l], tab[2 * L * B + 2 * l + 1])
-                             for l in range(L) if tab[2 * L * B + 2 * l + 1] > 0]
         self.level_seg = self.table_dev[2 * L * B:2 * L * B + 2 * L]
-        self.Npad = tab[-1]
-        nmax = max([g[3] for g in self.groups], default=0)
-        self.ldn = max(_round_up(nmax, ALIGN), ALIGN)
-        self.ldb = self.ldn // 32
-        Np = self.Npad
-        self.bits = torch.empty((max(Np, 1), self.ldb), dtype=torch.int32, device=dev)
-        self.deg = torch.empty(max(Np, 1), dtype=torch.int32, device=dev)
-        self.adj = torch.empty((max(Np, 1), self.ldn), dtype=op_dtype, device=dev)
-        check(lib().htd_iou_graph_build(ptr(self.boxes), ptr(self.rowspan), Np, ptr(self.bits),
+        self.sched = torch.empty(_lib.SCHED_BYTES, dtype=torch.uint8, device=dev)
+        check(lib().htd_pgraph_schedule(ptr(self.table_dev), B, L, d, ds, dt(op_dtype),
+                                        ptr(self.sched), stream()), 'htd_pgraph_schedule')
+        self.max_tiles = [int(lib().htd_pgraph_max_tiles(s, K, B, L, self.max_group, ncap, d, ds,
+                                                         dt(op_dtype)))
+                          for s in range(_lib.SCHED_SETS)]
+        self.bits = torch.empty((ncap, self.ldb), dtype=torch.int32, device=dev)
+        self.deg = torch.empty(ncap, dtype=torch.int32, device=dev)
+        self.adj = torch.empty((ncap, self.ldn), dtype=op_dtype, device=dev)
+        check(lib().htd_iou_graph_build(ptr(self.boxes), ptr(self.rowspan), ncap, ptr(self.bits),
                                         self.ldb, ptr(self.deg), ptr(self.adj), dt(op_dtype),
                                         self.ldn, stream()), 'htd_iou_graph_build')
+        self._tab = None
 
-    # ---- inspection helpers (tests / parity of the "neighbour indices") ----------------------
+    # ---- inspection helpers: these DO read the table back (tests / accounting only) ------------
+    def _table(self):
+        if self._tab is None:
+            self._tab = self.table_dev.cpu().tolist()
+            if max([self._tab[2 * g + 1] for g in range(self.L * self.B)], default=0) > self.max_group:
+                raise RuntimeError('a PGraph group is larger than max_group - pass the real bound')
+        return self._tab
+
+    @property
+    def groups(self):
+        """(level, image, off, n) of every non-empty group."""
+        t, B = self._table(), self.B
+        return [(g // B, g % B, t[2 * g], t[2 * g + 1]) for g in range(self.L * B) if t[2 * g + 1] > 0]
+
+    @property
+    def level_blocks(self):
+        t, G = self._table(), self.L * self.B
+        return [(l, t[2 * G + 2 * l], t[2 * G + 2 * l + 1]) for l in range(self.L)
+                if t[2 * G + 2 * l + 1] > 0]
+
+    @property
+    def Npad(self):
+        return self._table()[-1]
+
     def group_mask(self, level, image):
         """(original RoI indices, dense 0/1 mask [n,n], degrees) of one group."""
         for l, b, off, n in self.groups:
@@ -84,6 +114,17 @@ class GraphPlan:
     def flops(self, d=1024, ds=1025):
         """Algorithmic forward flops: 4 n^2 d + 2 n^2 ds + 2 n d^2 per group."""
         return sum(4 * n * n * d + 2 * n * n * ds + 2 * n * d * d for _, _, _, n in self.groups)
+
+    def gemm(self, A, B, sset, D=None, ldd=0, rowmap=None, DT=None, ldt=0, bias=None, relu=False):
+        """One scheduled grouped contraction D = A B^T of descriptor set ``sset``."""
+        assert A.dtype == B.dtype and A.dim() == 2 and B.dim() == 2
+        with _lib.timed('pgraph_gemm'):
+            check(lib().htd_pgraph_gemm_scheduled(
+                ptr(A), A.shape[0], A.stride(0), ptr(B), B.shape[0], B.stride(0), dt(A),
+                ptr(self.sched), int(sset), self.max_tiles[sset], ptr(D),
+                dt(D) if D is not None else 0, int(ldd), ptr(rowmap), ptr(DT),
+                dt(DT) if DT is not None else 0, int(ldt), ptr(bias), int(bool(relu)), stream()),
+                'htd_pgraph_gemm_scheduled')
 
 
 def _groups_array(items):
@@ -133,15 +174,11 @@ class _PGraphFunction(torch.autograd.Function):
         dev = x.device
         K, d = x.shape
         ds = sam.shape[1]
-        Np, ldn = plan.Npad, plan.ldn
+        assert (d, ds) == (plan.d, plan.ds), 'plan was scheduled for other feature widths'
+        Np, ldn = plan.Ncap, plan.ldn
         L = plan.L
         need_grad = any(ctx.needs_input_grad[:4])
         refined = torch.zeros((K, d), dtype=x.dtype, device=dev)
-        if Np == 0:
-            ctx.empty = True
-            ctx.shapes = (x.shape, sam.shape, W.shape, b.shape, x.dtype, sam.dtype, W.dtype, b.dtype)
-            return refined
-        ctx.empty = False
         x = x.detach().contiguous()
         sam = sam.detach().contiguous()
         Wc = W.detach().to(op).contiguous().reshape(L * d, d)
@@ -151,29 +188,24 @@ class _PGraphFunction(torch.autograd.Function):
         _, XT = _pack(x, plan.perm, Np, want_rows=False, want_t=True, out_dtype=op)
         sam_s, samT = _pack(sam, plan.perm, Np, ldd=lds, want_rows=True, want_t=need_grad,
                             out_dtype=op)
-        G = plan.groups
+        # zero-initialised where a buffer is later read as an operand with pad rows / K tails
+        z = torch.zeros((3 if need_grad else 2, Np * d), dtype=op, device=dev)
+        Xm, XmT = z[0].view(Np, d), z[1].view(d, Np)
+        ZT = z[2].view(d, Np) if need_grad else None
         # ---- Xm = A_local X
-        Xm = torch.zeros((Np, d), dtype=op, device=dev)
-        XmT = torch.zeros((d, Np), dtype=op, device=dev)
-        _gemm(plan.adj, XT, [dict(M=n, N=d, K=n, a_row=off, b_k0=off, d_row=off, dt_col=off)
-                             for _, _, off, n in G], D=Xm, ldd=d, DT=XmT, ldt=Np)
+        plan.gemm(plan.adj, XT, _lib.SCHED_GROUP_ND, D=Xm, ldd=d, DT=XmT, ldt=Np)
         # ---- S = sam sam^T, A_g = softmax((1 - M) * S)
         S = torch.empty((Np, ldn), dtype=torch.float32, device=dev)
-        _gemm(sam_s, sam_s, [dict(M=n, N=n, K=ds, a_row=off, b_row=off, d_row=off)
-                             for _, _, off, n in G], D=S, ldd=ldn)
+        plan.gemm(sam_s, sam_s, _lib.SCHED_GROUP_NN_S, D=S, ldd=ldn)
         Ag = torch.empty((Np, ldn), dtype=op, device=dev)
         check(lib().htd_pgraph_masked_softmax(ptr(S), ldn, ptr(plan.bits), plan.ldb,
                                               ptr(plan.rowspan), Np, ptr(Ag), dt(op), ldn,
                                               stream()), 'htd_pgraph_masked_softmax')
         # ---- Z = A_g Xm
         Z = torch.zeros((Np, d), dtype=op, device=dev)
-        ZT = torch.zeros((d, Np), dtype=op, device=dev) if need_grad else None
-        _gemm(Ag, XmT, [dict(M=n, N=d, K=n, a_row=off, b_k0=off, d_row=off, dt_col=off)
-                        for _, _, off, n in G], D=Z, ldd=d, DT=ZT, ldt=Np)
+        plan.gemm(Ag, XmT, _lib.SCHED_GROUP_ND, D=Z, ldd=d, DT=ZT, ldt=Np)
         # ---- refined = relu(Z W_l^T + b_l), one problem per level block, scattered to RoI order
-        _gemm(Z, Wc, [dict(M=n, N=d, K=d, a_row=off, b_row=l * d, d_row=off, bias_off=l * d)
-                      for l, off, n in plan.level_blocks], D=refined, ldd=d, rowmap=plan.perm,
-              bias=bc, relu=True)
+        plan.gemm(Z, Wc, _lib.SCHED_LEVEL_ND, D=refined, ldd=d, rowmap=plan.perm, bias=bc, relu=True)
         if need_grad:
             ctx.plan = plan
             ctx.save_for_backward(refined, Xm, Ag, ZT, sam_s, samT, Wc)
@@ -182,19 +214,12 @@ class _PGraphFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dY):
-        if ctx.empty:
-            xs, ss, ws, bs, xd, sd, wd, bd = ctx.shapes
-            dev = dY.device
-            return (torch.zeros(xs, dtype=xd, device=dev), torch.zeros(ss, dtype=sd, device=dev),
-                    torch.zeros(ws, dtype=wd, device=dev), torch.zeros(bs, dtype=bd, device=dev),
-                    None)
         plan = ctx.plan
         refined, Xm, Ag, ZT, sam_s, samT, Wc = ctx.saved_tensors
         K, d, ds, xdt, sdt, wdt, bdt, wshape, bshape = ctx.meta
         op = plan.op_dtype
         dev = dY.device
-        Np, ldn, L = plan.Npad, plan.ldn, plan.L
-        G = plan.groups
+        Np, ldn, L = plan.Ncap, plan.ldn, plan.L
         dY = dY.contiguous()
         if dY.dtype != refined.dtype:
             dY = dY.to(refined.dtype)
@@ -205,28 +230,23 @@ class _PGraphFunction(torch.autograd.Function):
                                               ptr(db), stream()), 'htd_pgraph_segment_colsum')
         # dW_l = dU_l^T Z_l   (K = RoIs of the level block; both operands zero in the pad rows)
         dW = torch.zeros((L * d, d), dtype=torch.float32, device=dev)
-        _gemm(dUT, ZT, [dict(M=d, N=d, K=n, a_k0=off, b_k0=off, d_row=l * d)
-                        for l, off, n in plan.level_blocks], D=dW, ldd=d)
+        plan.gemm(dUT, ZT, _lib.SCHED_LEVEL_DD, D=dW, ldd=d)
         # dZ = dU W_l
         WT = torch.empty((L * d, d), dtype=op, device=dev)
         check(lib().htd_layout_convert(ptr(Wc), dt(Wc), ptr(WT), dt(WT), L, d, d, stream()),
               'htd_layout_convert(W^T)')
-        dZ = torch.zeros((Np, d), dtype=op, device=dev)
-        dZT = torch.zeros((d, Np), dtype=op, device=dev)
-        _gemm(dU, WT, [dict(M=n, N=d, K=d, a_row=off, b_row=l * d, d_row=off, dt_col=off)
-                       for l, off, n in plan.level_blocks], D=dZ, ldd=d, DT=dZT, ldt=Np)
+        z = torch.zeros((3, Np * d), dtype=op, device=dev)
+        dZ, dZT, dXmT = z[0].view(Np, d), z[1].view(d, Np), z[2].view(d, Np)
+        plan.gemm(dU, WT, _lib.SCHED_LEVEL_ND, D=dZ, ldd=d, DT=dZT, ldt=Np)
         # dXm = A_g^T dZ  (only its transpose is needed, as the operand of dX)
         AgT = torch.empty((Np, ldn), dtype=op, device=dev)
         check(lib().htd_pgraph_group_transpose(ptr(Ag), dt(Ag), ldn, ptr(plan.rowspan), Np, 0.0, 1.0,
                                                ptr(AgT), dt(AgT), ldn, stream()),
               'htd_pgraph_group_transpose(A_g)')
-        dXmT = torch.zeros((d, Np), dtype=op, device=dev)
-        _gemm(AgT, dZT, [dict(M=n, N=d, K=n, a_row=off, b_k0=off, dt_col=off)
-                         for _, _, off, n in G], DT=dXmT, ldt=Np)
+        plan.gemm(AgT, dZT, _lib.SCHED_GROUP_ND, DT=dXmT, ldt=Np)
         # dA_g = dZ Xm^T ; softmax backward ; dS symmetrised
         dAg = torch.empty((Np, ldn), dtype=torch.float32, device=dev)
-        _gemm(dZ, Xm, [dict(M=n, N=n, K=d, a_row=off, b_row=off, d_row=off)
-                       for _, _, off, n in G], D=dAg, ldd=ldn)
+        plan.gemm(dZ, Xm, _lib.SCHED_GROUP_NN_D, D=dAg, ldd=ldn)
         dS = torch.empty((Np, ldn), dtype=torch.float32, device=dev)
         check(lib().htd_pgraph_softmax_bwd(ptr(Ag), dt(Ag), ldn, ptr(dAg), ldn, ptr(plan.bits),
                                            plan.ldb, ptr(plan.rowspan), Np, ptr(dS), ldn, stream()),
@@ -237,11 +257,9 @@ class _PGraphFunction(torch.autograd.Function):
               'htd_pgraph_group_transpose(dS)')
         # dsam = (dS + dS^T) sam      dX = A_local dXm      (both scattered back to RoI order)
         dsam = torch.zeros((K, ds), dtype=sdt, device=dev)
-        _gemm(Ssym, samT, [dict(M=n, N=ds, K=n, a_row=off, b_k0=off, d_row=off)
-                           for _, _, off, n in G], D=dsam, ldd=ds, rowmap=plan.perm)
+        plan.gemm(Ssym, samT, _lib.SCHED_GROUP_NS, D=dsam, ldd=ds, rowmap=plan.perm)
         dx = torch.zeros((K, d), dtype=xdt, device=dev)
-        _gemm(plan.adj, dXmT, [dict(M=n, N=d, K=n, a_row=off, b_k0=off, d_row=off)
-                               for _, _, off, n in G], D=dx, ldd=d, rowmap=plan.perm)
+        plan.gemm(plan.adj, dXmT, _lib.SCHED_GROUP_ND, D=dx, ldd=d, rowmap=plan.perm)
         return dx, dsam, dW.reshape(wshape).to(wdt), db.reshape(bshape).to(bdt), None
 
 

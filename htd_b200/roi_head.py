@@ -104,15 +104,21 @@ class HTDRoIHead(nn.Module):
             pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
             bbox_feats = ext(x_cl, rois)
             enhanced = enh(x_cl, pos_rois)
-            idx, off = [], 0
-            for res in sampling_results:       # positives are the prefix of each image's block
-                idx.append(torch.arange(off, off + res.pos_bboxes.size(0), device=rois.device))
+            # positives are the prefix of each image's block: slices, not index tensors, so the
+            # gather and the scatter of bbox_pred (htd_roi_head.py:169-170,180-182) are plain copies
+            spans, off = [], 0
+            for res in sampling_results:
+                spans.append((off, res.pos_bboxes.size(0), res.neg_bboxes.size(0)))
                 off += res.pos_bboxes.size(0) + res.neg_bboxes.size(0)
-            pos_idx = torch.cat(idx)
-            cls_score, bbox_pred = head(bbox_feats, bbox_feats[pos_idx], x_cl, rois, fc0, enhanced,
-                                        pos_rois, g, num_imgs=nimg or len(sampling_results))
-            full = cls_score.new_zeros(cls_score.size(0), 4).index_put((pos_idx,), bbox_pred)
-            return dict(cls_score=cls_score, bbox_pred=full)
+            pos_feats = torch.cat([bbox_feats[o:o + npos] for o, npos, _ in spans], 0)
+            cls_score, bbox_pred = head(bbox_feats, pos_feats, x_cl, rois, fc0, enhanced,
+                                        pos_rois, g, num_imgs=nimg or len(sampling_results),
+                                        max_rois_per_img=max(p_ + n_ for _, p_, n_ in spans))
+            parts, o2 = [], 0
+            for _, npos, nneg in spans:
+                parts += [bbox_pred[o2:o2 + npos], bbox_pred.new_zeros(nneg, bbox_pred.size(1))]
+                o2 += npos
+            return dict(cls_score=cls_score, bbox_pred=torch.cat(parts, 0))
         bbox_feats = ext(x_cl, rois)
         enhanced = enh(x_cl, rois)
         cls_score, bbox_pred = head(bbox_feats, bbox_feats, x_cl, rois, fc0, enhanced, rois, g,
@@ -170,7 +176,8 @@ class HTDRoIHead(nn.Module):
             roi_labels = torch.where(roi_labels == self.bbox_head[0].num_classes,
                                      res['cls_score'][:, :-1].argmax(1), roi_labels)
             proposal_list = self.bbox_head[0].refine_bboxes(
-                res['rois'], roi_labels, res['bbox_pred'], [r.pos_is_gt for r in samp], img_metas)
+                res['rois'], roi_labels, res['bbox_pred'], [r.pos_is_gt for r in samp], img_metas,
+                num_per_img=[r.pos_bboxes.size(0) + r.neg_bboxes.size(0) for r in samp])
         samp = sample(1, proposal_list)
         res = self._bbox_forward_train(1, x, samp, gt_bboxes, gt_labels, self.train_cfg[1],
                                        img_metas, global_feat, x_cl)

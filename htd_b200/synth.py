@@ -152,7 +152,7 @@ def make_sampling(bboxes, num_pos, gt):
         pos_bboxes=bboxes[:n], neg_bboxes=bboxes[n:],
         pos_gt_bboxes=gt['pos_gt_bboxes'][:n].to(device=dev, dtype=bboxes.dtype),
         pos_gt_labels=gt['pos_gt_labels'][:n].to(dev),
-        pos_is_gt=torch.zeros(n, dtype=torch.uint8, device=dev), bboxes=bboxes)
+        pos_is_gt=None, bboxes=bboxes)      # None: no sampled box is a gt box (static shapes)
 
 
 def sampled_forward_train(head, x, proposals, gts, img_shapes, num_pos=128):

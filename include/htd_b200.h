@@ -241,6 +241,47 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
                     int dt_dtype, long long ldt, const float* bias, int relu,
                     htd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-side scheduling of the PGraph contractions: no host read of the plan table, so the whole
+ * head step can be captured in a CUDA graph.  htd_pgraph_schedule derives, from the plan table on
+ * the DEVICE, the problem descriptors of the six contraction shapes of the forward/backward pass
+ * (one HtdGemmGroup per (level, image) group or per level block) and their tile prefix sums for
+ * tiles of bm x bn outputs.  htd_pgraph_gemm_scheduled launches `max_tiles` CTAs (a static upper
+ * bound from htd_pgraph_max_tiles); CTAs beyond the real tile count exit at once.
+ *   set HTD_SCHED_GROUP_ND  : per group  M=n  N=d  K=n   a_row=off b_k0=off d_row=off dt_col=off
+ *   set HTD_SCHED_GROUP_NN_S: per group  M=n  N=n  K=ds  a_row=off b_row=off d_row=off
+ *   set HTD_SCHED_GROUP_NN_D: per group  M=n  N=n  K=d   a_row=off b_row=off d_row=off
+ *   set HTD_SCHED_GROUP_NS  : per group  M=n  N=ds K=n   a_row=off b_k0=off d_row=off
+ *   set HTD_SCHED_LEVEL_ND  : per level  M=ln N=d  K=d   a_row=loff b_row=l*d d_row=loff
+ *                                        dt_col=loff bias_off=l*d
+ *   set HTD_SCHED_LEVEL_DD  : per level  M=d  N=d  K=ln  a_k0=loff b_k0=loff d_row=l*d
+ * sched layout: groups [HTD_SCHED_SETS][HTD_MAX_GROUPS] then int32 tile_start
+ * [HTD_SCHED_SETS][HTD_MAX_GROUPS + 1]; HTD_SCHED_BYTES bytes in total. */
+#define HTD_SCHED_GROUP_ND 0
+#define HTD_SCHED_GROUP_NN_S 1
+#define HTD_SCHED_GROUP_NN_D 2
+#define HTD_SCHED_GROUP_NS 3
+#define HTD_SCHED_LEVEL_ND 4
+#define HTD_SCHED_LEVEL_DD 5
+#define HTD_SCHED_SETS 6
+#define HTD_SCHED_BYTES                                                     \
+    (HTD_SCHED_SETS * HTD_MAX_GROUPS * (int)sizeof(HtdGemmGroup) +         \
+     HTD_SCHED_SETS * (HTD_MAX_GROUPS + 1) * (int)sizeof(int32_t))
+
+int htd_pgraph_schedule(const int32_t* table, int B, int L, int d, int ds, int ab_dtype,
+                        void* sched, htd_stream_t stream);
+
+/* Static upper bound of the tile count of a set: K RoIs in total, groups of at most max_group
+ * RoIs, Ncap sorted rows of capacity. */
+long long htd_pgraph_max_tiles(int set, int K, int B, int L, int max_group, int Ncap, int d,
+                               int ds, int ab_dtype);
+
+int htd_pgraph_gemm_scheduled(const void* A, long long a_rows, long long a_ld, const void* B,
+                              long long b_rows, long long b_ld, int ab_dtype, const void* sched,
+                              int set, long long max_tiles, void* D, int d_dtype, long long ldd,
+                              const int32_t* d_rowmap, void* DT, int dt_dtype, long long ldt,
+                              const float* bias, int relu, htd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

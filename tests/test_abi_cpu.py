@@ -31,7 +31,8 @@ def test_every_declared_symbol_is_exported(cdll):
 def test_python_binding_covers_the_header():
     from htd_b200 import _lib
     missing = set(_declared()) - set(_lib.SIGNATURES) - {'htd_abi_version', 'htd_last_error',
-                                                             'htd_roi_plan_rows_bound'}
+                                                             'htd_roi_plan_rows_bound',
+                                                             'htd_pgraph_max_tiles'}
     assert not missing, missing
 
 
