@@ -35,11 +35,12 @@ IMG_H, IMG_W = 800, 1333
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='htd_b200', choices=['htd_b200', 'reference'])
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager steps instead of CUDA-graph replay')
     return ap.parse_args()
 
 
@@ -129,7 +130,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.QUERY}',
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '20'],
                 stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -171,6 +172,7 @@ class ClockSampler:
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+    os.environ.pop('NCCL_DEBUG', None)      # NCCL would print its version banner on stdout
     import htd_b200
     from htd_b200 import _lib, synth
     from htd_b200.parallel import GradAllReducer
@@ -210,7 +212,7 @@ def run_gpu(args):
     reducer = GradAllReducer(head.parameters(), world) if world > 1 else None
     rois_per_step = IMGS * ROIS
 
-    def step(x, props):
+    def eager_step(x, props):
         for p in head.parameters():
             p.grad = None
         for t in x:
@@ -227,35 +229,69 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up, then one accounting step (algorithmic bytes / flops per launch) -------------
+    # ---- warm-up (eager), one accounting step, one instrumented pass for per-kernel times -----
     for _ in range(max(args.warmup, 3)):
-        step(x_dev, props_dev)
+        eager_step(x_dev, props_dev)
     barrier()
     _lib.ACCOUNT = []
-    step(x_dev, props_dev)
+    l0 = _lib.LAUNCHES['total']
+    eager_step(x_dev, props_dev)
     torch.cuda.synchronize()
+    launches_per_step = _lib.LAUNCHES['total'] - l0
     account = _lib.ACCOUNT
     _lib.ACCOUNT = None
+    launches_per_step -= 0          # accounting adds no launches of the library
     pg_flops = head.bbox_head[1].last_plan.flops()
     alg = {}
     for name, nbytes in account:
         alg.setdefault(name, []).append(nbytes)
+    ksteps = min(args.steps, 10)
+    _lib.TIMER = _lib.KernelTimer()
+    ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ek0.record()
+    for _ in range(ksteps):
+        eager_step(x_dev, props_dev)
+    ek1.record()
+    torch.cuda.synchronize()
+    ksum = _lib.TIMER.summary()
+    _lib.TIMER = None
+    ms_eager = ek0.elapsed_time(ek1) / ksteps
 
+    # ---- the step as one CUDA graph (forward + losses + backward), replayed per step ---------
+    use_graph = not args.no_graph
+    if use_graph:
+        if reducer is not None:
+            reducer.remove()
+        from htd_b200.graphed import GraphedTrainStep
+        gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1)
+
+        def allreduce_grads():
+            if world == 1:
+                return
+            dist.all_reduce(gstep.flat_grad)       # one NCCL call over NVLink, in place
+            gstep.flat_grad.mul_(1.0 / world)
+
+        def step(x=None, props=None):
+            losses = gstep(x, props)
+            allreduce_grads()
+            return losses
+    else:
+        def step(x=None, props=None):
+            return eager_step(x if x is not None else x_dev, props if props is not None else props_dev)
+
+    for _ in range(3):
+        step()
     # ---- timed region 1: device-resident inputs ----------------------------------------------
     clocks = ClockSampler(local)
     barrier()
-    _lib.TIMER = _lib.KernelTimer()
-    l0 = _lib.LAUNCHES['total']
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        step(x_dev, props_dev)
+        step()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = _lib.LAUNCHES['total'] - l0
-    ksum = _lib.TIMER.summary()
-    _lib.TIMER = None
+    launches = launches_per_step * args.steps
     clk = clocks.stop()
 
     # ---- timed region 2: end to end from host buffers (H2D double-buffered, D2H of the losses)
@@ -277,11 +313,12 @@ def run_gpu(args):
         for i in range(n):
             xs, ps, evt = nxt
             if i + 1 < n:
-                nxt = upload()
+                nxt = upload()                      # next step's H2D overlaps this step's compute
             torch.cuda.current_stream().wait_event(evt)
             for t in xs:
                 t.record_stream(torch.cuda.current_stream())
-                t.requires_grad_(True)
+                if not use_graph:
+                    t.requires_grad_(True)
             losses = step(xs, ps)
             host = torch.stack([v.detach().float().reshape(()) for v in losses.values()]).cpu()
             d2h = host.numel() * host.element_size()
@@ -310,10 +347,11 @@ def run_gpu(args):
         per_step = alg.get(name)
         if not per_step or n == 0:
             continue
-        total_bytes = sum(per_step) * args.steps
+        total_bytes = sum(per_step) * ksteps
         gbs = total_bytes / (tot_ms * 1e-3) / 1e9
         kernels[name] = dict(launches=n, avg_ms=tot_ms / n, alg_MB_per_launch=sum(per_step) / len(per_step) / 1e6,
-                             achieved_GBs=gbs, frac=gbs / hbm_peak, share_of_step=tot_ms / ms)
+                             achieved_GBs=gbs, frac=gbs / hbm_peak,
+                             share_of_step=(tot_ms / ksteps) / (ms / args.steps))
     dom = max(kernels, key=lambda k: kernels[k]['share_of_step']) if kernels else None
     roofline = None
     if dom:
@@ -346,7 +384,12 @@ def run_gpu(args):
                             global_rois_per_step=rois_per_step * world,
                             parallelism=f'dp{world}' + (' + NCCL grad all-reduce' if world > 1 else ''),
                             l2='inputs larger than L2: 183 MB fp32 pyramid + 94 MB bf16 weights per step',
-                            pgraph_fwd_gflop=pg_flops / 1e9),
+                            pgraph_fwd_gflop=pg_flops / 1e9,
+                            execution=('CUDA graph replay of forward+losses+backward' if use_graph
+                                       else 'eager'),
+                            eager_ms_per_step=ms_eager,
+                            kernel_timing='CUDA events around each own launch in an eager pass of '
+                                          'the same step (events cannot be placed inside a graph)'),
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches, clocks=clk, roofline=roofline, kernels=kernels,

@@ -43,6 +43,9 @@ class ConvModule(nn.Module):
                 raise NotImplementedError('GroupNorm only (htd_bbox_head.py:48)')
             self.gn = nn.GroupNorm(norm_cfg['num_groups'], out_channels)
         self.with_act = act_cfg is not None
+        # channels-last weights: cuDNN then runs NHWC end to end instead of wrapping every conv
+        # in nchw<->nhwc conversion kernels (63 launches / 0.66 ms per step in the round-1 profile)
+        self.conv.to(memory_format=torch.channels_last)
 
     def forward(self, x):
         x = self.conv(x)
@@ -119,6 +122,29 @@ class BBoxHead(nn.Module):
 
     def get_targets(self, sampling_results, gt_bboxes, gt_labels, rcnn_train_cfg, concat=True):
         cfg = as_cfg(rcnn_train_cfg)
+        sizes = {(r.pos_bboxes.size(0), r.neg_bboxes.size(0)) for r in sampling_results}
+        if concat and len(sizes) == 1 and len(sampling_results) > 1 and min(next(iter(sizes))) > 0 \
+                and not self.reg_decoded_bbox:
+            # same (positives, negatives) in every image: one batched pass instead of a per-image
+            # loop (identical values; the op count no longer grows with images per GPU)
+            npos, nneg = next(iter(sizes))
+            nb, n = len(sampling_results), npos + nneg
+            pos = torch.stack([r.pos_bboxes for r in sampling_results])
+            gtb = torch.stack([r.pos_gt_bboxes for r in sampling_results])
+            lab = torch.stack([r.pos_gt_labels for r in sampling_results])
+            labels = pos.new_full((nb, n), self.num_classes, dtype=torch.long)
+            labels[:, :npos] = lab
+            pw = cfg.get('pos_weight', -1) if cfg is not None else -1
+            label_weights = pos.new_ones((nb, n))
+            if pw > 0:
+                label_weights[:, :npos] = pw
+            bbox_targets = pos.new_zeros((nb, n, 4))
+            bbox_targets[:, :npos] = self.bbox_coder.encode(
+                pos.reshape(-1, 4), gtb.reshape(-1, 4)).to(pos.dtype).view(nb, npos, 4)
+            bbox_weights = pos.new_zeros((nb, n, 4))
+            bbox_weights[:, :npos] = 1
+            return (labels.view(-1), label_weights.view(-1), bbox_targets.view(-1, 4),
+                    bbox_weights.view(-1, 4))
         outs = [self._get_target_single(r.pos_bboxes, r.neg_bboxes, r.pos_gt_bboxes,
                                         r.pos_gt_labels, cfg) for r in sampling_results]
         cols = list(zip(*outs))
@@ -198,6 +224,12 @@ class BBoxHead(nn.Module):
         """bbox_head.py:227-303.  ``num_per_img`` (RoIs of every image, in order) replaces the
         reference's per-image ``nonzero`` (host sync); ``pos_is_gts[i] is None`` means "no sampled
         box of image i is a ground-truth box" and skips the boolean filter (static shapes)."""
+        shapes = {tuple(m['img_shape'][:2]) for m in img_metas}
+        if num_per_img is not None and len(shapes) == 1 and all(g is None for g in pos_is_gts) \
+                and sum(num_per_img) == rois.size(0):
+            # one decode for the whole batch (same image shape, nothing to filter)
+            boxes = self.regress_by_class(rois[:, 1:], labels, bbox_preds, img_metas[0])
+            return list(boxes.split(list(num_per_img), 0))
         out, off = [], 0
         for i in range(len(img_metas)):
             if num_per_img is not None:

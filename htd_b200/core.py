@@ -95,14 +95,14 @@ class DeltaXYWHBBoxCoder:
         gw, gh = g[..., 2] - g[..., 0], g[..., 3] - g[..., 1]
         dx = ((g[..., 0] + g[..., 2]) * 0.5 - (p[..., 0] + p[..., 2]) * 0.5) / pw
         dy = ((g[..., 1] + g[..., 3]) * 0.5 - (p[..., 1] + p[..., 3]) * 0.5) / ph
-        deltas = torch.stack([dx, dy, torch.log(gw / pw), torch.log(gh / ph)], dim=-1)
-        return (deltas - deltas.new_tensor(self.means)) / deltas.new_tensor(self.stds)
+        cols = [dx, dy, torch.log(gw / pw), torch.log(gh / ph)]
+        # python-scalar means / stds: no host->device tensor upload (CUDA-graph capturable)
+        return torch.stack([(c - m) / sd for c, m, sd in zip(cols, self.means, self.stds)], dim=-1)
 
     def decode(self, bboxes, pred_bboxes, max_shape=None, wh_ratio_clip=16 / 1000):
         assert pred_bboxes.size(0) == bboxes.size(0)
-        d = pred_bboxes * pred_bboxes.new_tensor(self.stds).repeat(pred_bboxes.size(1) // 4) + \
-            pred_bboxes.new_tensor(self.means).repeat(pred_bboxes.size(1) // 4)
-        dx, dy, dw, dh = d[:, 0::4], d[:, 1::4], d[:, 2::4], d[:, 3::4]
+        d = pred_bboxes
+        dx, dy, dw, dh = (d[:, i::4] * self.stds[i] + self.means[i] for i in range(4))
         max_ratio = abs(math.log(wh_ratio_clip))
         dw = dw.clamp(min=-max_ratio, max=max_ratio)
         dh = dh.clamp(min=-max_ratio, max=max_ratio)

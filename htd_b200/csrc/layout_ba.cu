@@ -193,7 +193,9 @@ __global__ void __launch_bounds__(256) ba_fuse_bwd_kernel(const TR* __restrict__
     }
 }
 
-// dbias, phase 1: block = 32 consecutive RoIs, thread = channel
+// dbias, phase 1: block = kBiasRois consecutive RoIs, thread = channel
+constexpr int kBiasRois = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const T* __restrict__ g,
                                                                 const float* __restrict__ rois,
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const T* __restr
     float* part = partial + (size_t)kb * B * C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         for (int b = 0; b < B; ++b) part[(size_t)b * C + c] = 0.f;
-        const int kend = min(K, (kb + 1) * 32);
-        for (int k = kb * 32; k < kend; ++k) {
+        const int kend = min(K, (kb + 1) * kBiasRois);
+        for (int k = kb * kBiasRois; k < kend; ++k) {
             const int b = (int)__ldg(rois + (size_t)k * 5);
             if (b < 0 || b >= B) continue;
             float s = 0.f;
@@ -321,7 +323,7 @@ int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, 
                   "htd_bias_grad: bad arguments");
     HTD_CHECK_ARG(dbias && (K == 0 || (g && rois && partial)), "htd_bias_grad: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int nblk = (K + 31) / 32;
+    const int nblk = (K + kBiasRois - 1) / kBiasRois;
     if (nblk > 0) {
         if (g_dtype == HTD_F32)
             bias_grad_partial_kernel<float><<<nblk, 256, 0, st>>>(static_cast<const float*>(g), rois,

@@ -1,0 +1,96 @@
+"""CUDA-graph capture of the RoI-head training step.
+
+The step issues ~700 kernels of a few microseconds each (the library FC / conv / GroupNorm /
+loss glue around the own kernels), so eager execution is bound by host launch latency, not by
+the GPU.  Everything on the path is host-sync free and shape-static once the RoI
+counts are fixed (static-shape losses, device-scheduled PGraph), so forward + losses + backward
+are captured ONCE into a CUDA graph and replayed: one host call per step.
+
+    step = GraphedTrainStep(head, x, proposals, gts, img_shapes, num_pos)
+    losses = step(x_new, proposals_new, gts_new)      # copies into static buffers, replays
+    head.parameters() .grad / step.x[i].grad          # static gradient tensors, rewritten per replay
+
+Valid for the sampled-RoI protocol with fixed counts per image (``synth.sampled_forward_train``;
+bench.py).  A different (K, P) needs a new capture.
+"""
+import torch
+
+from . import synth
+
+
+class GraphedTrainStep:
+
+    def __init__(self, head, x, proposals, gts, img_shapes, num_pos, warmup=3, flat_grads=False):
+        """``flat_grads``: parameter gradients live in ONE flat buffer (``self.flat_grad``; every
+        ``p.grad`` is a view of it) that the captured step zeroes and accumulates into - the
+        data-parallel exchange is then a single all-reduce of that buffer, no packing copies."""
+        self.head, self.img_shapes, self.num_pos = head, img_shapes, num_pos
+        dev = x[0].device
+        self.flat_grad = None
+        if flat_grads:
+            params = list(head.parameters())
+            dtypes = {p.dtype for p in params}
+            assert len(dtypes) == 1, 'flat_grads needs a single parameter dtype'
+            self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype,
+                                         device=dev)
+            self._views, off = [], 0
+            for p in params:
+                self._views.append((p, self.flat_grad[off:off + p.numel()].view_as(p)))
+                off += p.numel()
+        self.x = [t.detach().clone().requires_grad_(True) for t in x]
+        self.proposals = [p.detach().clone() for p in proposals]
+        self.gts = [{k: v.detach().clone().to(dev) for k, v in g.items()} for g in gts]
+        self.losses = None
+        self.total = None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # warm-up off the capture stream
+            for _ in range(warmup):
+                self._zero()
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._zero()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            if self.flat_grad is not None:
+                self.flat_grad.zero_()
+            self._run()
+        torch.cuda.synchronize()
+
+    def _zero(self):
+        if self.flat_grad is not None:
+            self.flat_grad.zero_()                 # captured: part of every replay
+            for p, v in self._views:
+                p.grad = v
+        else:
+            for p in self.head.parameters():
+                p.grad = None
+        for t in self.x:
+            t.grad = None
+
+    def _run(self):
+        losses = synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
+                                             self.img_shapes, self.num_pos)
+        total = sum(v for k, v in losses.items() if 'loss' in k)
+        total.backward()
+        self.losses, self.total = losses, total
+
+    def load(self, x=None, proposals=None, gts=None, non_blocking=True):
+        """Copy new inputs (device or pinned-host tensors) into the static buffers."""
+        with torch.no_grad():
+            if x is not None:
+                for d, s in zip(self.x, x):
+                    d.copy_(s, non_blocking=non_blocking)
+            if proposals is not None:
+                for d, s in zip(self.proposals, proposals):
+                    d.copy_(s, non_blocking=non_blocking)
+            if gts is not None:
+                for d, s in zip(self.gts, gts):
+                    for k in d:
+                        d[k].copy_(s[k], non_blocking=non_blocking)
+
+    def __call__(self, x=None, proposals=None, gts=None):
+        self.load(x, proposals, gts)
+        self.graph.replay()
+        return self.losses

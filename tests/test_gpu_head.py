@@ -369,3 +369,42 @@ def test_forward_train_with_real_assigner_and_sampler_runs():
     with torch.no_grad():
         res = head.simple_test(x, [p[:200] for p in props], metas)
     assert len(res) == 2 and len(res[0]) == 80 and res[0][0].shape[1] == 5
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """The captured step (forward + losses + backward as ONE CUDA graph) reproduces the eager
+    step: same losses and gradients, also after the static input buffers are refilled."""
+    import htd_b200
+    from htd_b200.graphed import GraphedTrainStep
+    from oracle import cases
+    torch.backends.cudnn.enabled = True
+    name = 'small'
+    c = cases.CASES[name]
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    head = head.cuda().to(torch.bfloat16)
+    head.compute_dtype = torch.bfloat16
+    _, x, props, gts, shapes = cases.case_inputs(name, torch.float32, 'cuda')
+
+    def eager(xs, ps):
+        for p in head.parameters():
+            p.grad = None
+        xs = [t.clone().requires_grad_(True) for t in xs]
+        losses = synth.sampled_forward_train(head, xs, ps, gts, shapes, c['P'])
+        sum(v for k, v in losses.items() if 'loss' in k).backward()
+        return ({k: v.detach().clone() for k, v in losses.items()},
+                [p.grad.detach().clone() for p in head.parameters()], [t.grad.clone() for t in xs])
+
+    x2 = [t * 0.5 + 0.1 for t in x]
+    p2 = [p.flip(0).contiguous() for p in props]
+    want_a, want_b = eager(x, props), eager(x2, p2)
+    gstep = GraphedTrainStep(head, x, props, gts, shapes, c['P'])
+    for (xs, ps), want in (((x, props), want_a), ((x2, p2), want_b), ((x, props), want_a)):
+        losses = gstep(xs, ps)
+        torch.cuda.synchronize()
+        for k in want[0]:
+            assert torch.allclose(losses[k].float(), want[0][k].float(), rtol=2e-2, atol=1e-3), k
+        for g, w in zip([p.grad for p in head.parameters()], want[1]):
+            assert _l2(g.float(), w.float()) <= 2e-2
+        for g, w in zip([t.grad for t in gstep.x], want[2]):
+            assert _l2(g.float(), w.float()) <= 2e-2
