@@ -354,10 +354,17 @@ def run_gpu(args):
                              share_of_step=(tot_ms / ksteps) / (ms / args.steps))
     dom = max(kernels, key=lambda k: kernels[k]['share_of_step']) if kernels else None
     roofline = None
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
     if dom:
         k = kernels[dom]
         roofline = dict(bound='hbm', kernel=dom, achieved=k['achieved_GBs'], peak=hbm_peak,
-                        unit='GB/s', frac=k['frac'], traffic=None, peak_kind=peak_kind,
+                        unit='GB/s', frac=k['frac'], traffic=traffic, peak_kind=peak_kind,
+                        alg_bytes_per_launch=k['alg_MB_per_launch'] * 1e6,
                         avg_ms=k['avg_ms'], share_of_step=k['share_of_step'])
 
     if rank != 0:

@@ -278,7 +278,7 @@ class ConvFCBBoxHead(BBoxHead):
             nn.init.constant_(m.bias, 0)
 
     def forward(self, x):
-        x = x.flatten(1)
+        x = ops.flatten_roi_feats(x)
         for fc in self.shared_fcs:
             x = F.relu(fc(x))
         return (self.fc_cls(x) if self.with_cls else None,
@@ -349,8 +349,12 @@ class HTDBBoxHead(BBoxHead):
         return ops.level_assign(rois, num_levels, self.finest_scale).long()
 
     @staticmethod
-    def _img_index(rois, num_imgs):
-        return rois[:, 0].long().clamp_(0, num_imgs - 1)
+    def _img_onehot(rois, num_imgs, dtype):
+        """[K, B] one-hot of the RoIs' image index: per-image vectors are broadcast to RoIs as
+        ``onehot @ v`` - a tiny GEMM whose backward is a GEMM too, instead of advanced indexing
+        whose backward (indexing_backward_kernel) cost 0.75 ms per step in the round-1 profile."""
+        b = torch.arange(num_imgs, device=rois.device, dtype=rois.dtype)
+        return (rois[:, :1] == b[None, :]).to(dtype)
 
     def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
                 global_feat=None, num_imgs=None, max_rois_per_img=None):
@@ -365,21 +369,21 @@ class HTDBBoxHead(BBoxHead):
         # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool (:161-189)
         if global_feat is not None:
             g = global_feat.reshape(global_feat.size(0), -1)
-            x_reg = x_reg + g[self._img_index(pos_rois, g.size(0))][:, :, None, None]
+            x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
         x_reg = x_reg + self.alpha * enhanced_feat
         x_reg = self.convs(x_reg.contiguous(memory_format=torch.channels_last))
-        x_reg = self.avg_pool(x_reg).reshape(x_reg.size(0), -1)
+        x_reg = x_reg.mean((2, 3))            # AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:188-189)
         # ---- cls branch: fcs on x_cls and on x_cls + SFA.  fcs.0 is linear, so
         # fcs.0(x + g (x) 1_49) = fcs.0(x) + g W_sum^T with W_sum = sum of W over the 49 bins:
         # one [K,12544]x[12544,1024] GEMM instead of the reference's two (:164 and :192).
         fc0, fc1 = self.fcs[0], self.fcs[2]
-        pre = fc0(x_cls.flatten(1))
+        pre = fc0(ops.flatten_roi_feats(x_cls))
         x_c = F.relu(fc1(F.relu(pre)))
         x_glb = None
         if global_feat is not None:
             w_sum = fc0.weight.view(d, self.in_channels, self.roi_feat_area).sum(-1)
             corr = g.to(w_sum.dtype) @ w_sum.t()
-            x_glb = F.relu(fc1(F.relu(pre + corr[self._img_index(rois, g.size(0))])))
+            x_glb = F.relu(fc1(F.relu(pre + self._img_onehot(rois, g.size(0), corr.dtype) @ corr)))
         # ---- semantic vectors and the graph (:194-219)
         sam = torch.mm(fc_cls_0(x_c).softmax(-1), prototype)
         with torch.no_grad():

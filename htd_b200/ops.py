@@ -57,6 +57,37 @@ def to_channels_last(x, dtype=None):
     return x.to(dtype).contiguous(memory_format=torch.channels_last)
 
 
+class _FlattenRoIFeats(torch.autograd.Function):
+    """[K,C,P,P] RoI features with channels-last strides -> [K, C*P*P] in the reference's
+    flatten order (c*PP + bin), which the FC weights index (htd_bbox_head.py:191,
+    convfc_bbox_head.py:145).  Tiled transpose kernel in both directions instead of ATen's
+    strided copy (0.1 ms per 25 MB in the round-1 profile)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        K, C, P, Q = x.shape
+        out = torch.empty((K, C * P * Q), dtype=x.dtype, device=x.device)
+        _convert(x, out, K, P * Q, C)            # memory [K, PQ, C] -> [K, C, PQ]
+        ctx.shape = (K, C, P, Q)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        K, C, P, Q = ctx.shape
+        g = g.contiguous()
+        out = torch.empty((K, P, Q, C), dtype=g.dtype, device=g.device)
+        _convert(g, out, K, C, P * Q)            # [K, C, PQ] -> [K, PQ, C]
+        return out.permute(0, 3, 1, 2)
+
+
+def flatten_roi_feats(x):
+    """``x.flatten(1)`` for RoI features; uses the transpose kernel when ``x`` is a CUDA
+    channels-last tensor, plain flatten otherwise."""
+    if x.is_cuda and x.dim() == 4 and _is_cl(x) and x.dtype in _lib._DT and x.shape[1] > 1:
+        return _FlattenRoIFeats.apply(x)
+    return x.flatten(1)
+
+
 def _bhwc(x):
     """[B,C,H,W] channels-last tensor -> its [B,H,W,C] memory view."""
     return x.permute(0, 2, 3, 1)
