@@ -27,7 +27,7 @@
 
 namespace htd {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 6;
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;   // 3 x 32 KB: two CTAs per SM, so one tile's epilogue overlaps the other's MMAs
 constexpr int kTileBytes = kBM * kBK * 2;            // 16 KiB per operand tile
 constexpr int kGemmThreads = 192;
 constexpr int kTmemCols = 128;
@@ -198,7 +198,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) |
                             ((uint32_t)(kBM >> 4) << 24);
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
     pgraph_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
