@@ -23,6 +23,14 @@ class HtdGemmGroup(ctypes.Structure):
                                                'd_row', 'd_col', 'dt_row', 'dt_col', 'bias_off')]
 
 
+class HtdBwdSource(ctypes.Structure):
+    _fields_ = [('rois', c_void_p), ('boxes', c_void_p), ('offsets', c_void_p), ('ranges', c_void_p),
+                ('weights', c_void_p), ('dy', c_void_p), ('scale', c_void_p), ('addvec', c_void_p),
+                ('K', ctypes.c_int32), ('dy_per_level', ctypes.c_int32),
+                ('ring_edge', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+MAX_BWD_SOURCES = 4
 MAX_GROUPS = 64
 SCHED_SETS = 6
 SCHED_BYTES = SCHED_SETS * MAX_GROUPS * 48 + SCHED_SETS * (MAX_GROUPS + 1) * 4
@@ -48,6 +56,8 @@ SIGNATURES = {
     'htd_roi_align_bwd': [ctypes.POINTER(HtdLevel), c_int, c_int, c_int, c_int, c_void_p, c_int,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                           c_void_p, c_int, c_void_p, c_void_p],
+    'htd_roi_align_bwd_multi': [ctypes.POINTER(HtdLevel), c_int, c_int, c_int, c_int, c_int,
+                                ctypes.POINTER(HtdBwdSource), c_int, c_int, c_int, c_void_p],
     'htd_layout_convert': [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     'htd_ba_bin_mean': [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p],
     'htd_ba_fuse_fwd': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -348,21 +348,27 @@ __global__ void __launch_bounds__(HTD_MAX_POOLED * 32) roi_align_fwd_kernel(cons
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-struct BwdParams {
-    LevelDev lv[HTD_MAX_LEVELS];
-    int tile_start[HTD_MAX_LEVELS + 1];
-    int L, B, C, K, P, sr;
+struct BwdSource {                   // one extractor call whose gradient lands in dX
     const float* rois;
     const int4* boxes;
     const int* offsets;
     const int* ranges;
     const float* weights;
     const void* dy;
-    int dy_per_level;
     const float* scale;
-    int ring_edge;
     const float* addvec;
+    int K, dy_per_level, ring_edge;
 };
+
+struct BwdParams {
+    LevelDev lv[HTD_MAX_LEVELS];
+    int tile_start[HTD_MAX_LEVELS + 1];
+    int L, B, C, P, nsrc, nchw;
+    BwdSource src[HTD_MAX_BWD_SOURCES];
+};
+
+__device__ __forceinline__ void st_elem(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_elem(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 constexpr int kTile = 8;  // 8x8 pixels per CTA
 constexpr int kBwdWarps = 16;          // consumer warps: tile row (w & 7) x column half (w >> 3)
@@ -382,8 +388,8 @@ struct BwdStages {                     // dY ring depth: 25 KB (bf16) / 50 KB (f
 // tables; per hit it streams - with cp.async.bulk (UBLKCP) + mbarrier transaction counts, several
 // hits ahead of the consumers - the tile's slices of the weight tables and the needed dY bins (per
 // bin row one contiguous run) into a ring of shared-memory slots.  Each consumer warp owns half a
-// tile row (4 pixels) and accumulates  sum_ph sum_pw wy[ph] wx[pw][x] dY[ph][pw][c]  for its 4 pixels x 256
-// channels in registers, reading shared memory only.  Every dX element is written exactly once:
+// tile COLUMN (4 pixels) and works separably: t[c] = sum_pw wx[pw][col] dY[ph][pw][c] once per bin
+// row, then acc[r][c] += wy[ph][r] t[c] for its 4 rows - registers only, reading shared memory only.  Every dX element is written exactly once:
 // no atomics, no memset, bit-reproducible.
 template <typename TDy, typename TDx>
 __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const BwdParams p) {
@@ -393,6 +399,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
     __shared__ __align__(16) float s_wx[kS][kTile][kTabW];      // [slot][tile col][bin]
     __shared__ int4 s_meta[kBwdChunk];                  // per hit: k, bins, tile-relative ranges, y table row
     __shared__ int s_xrow[kBwdChunk];                   // per hit: x table row of the first staged column
+    __shared__ float s_scale[kBwdChunk];              // per hit: BA level weight (1 when unused)
+    __shared__ __align__(16) float s_av[kS][256];     // per slot: per-channel add vector of the hit
     __shared__ int s_hits[kBwdChunk];
     __shared__ int s_wcnt[2][kBwdWarps];                  // double-buffered by chunk parity
     __shared__ uint64_t s_full[kS], s_empty[kS];
@@ -408,12 +416,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
     local -= b * tiles_x * tiles_y;
     const int row0 = (local / tiles_x) * kTile, col0 = (local % tiles_x) * kTile;
     const int P = p.P, PP = P * P;
-    const int trow = warp & 7, xh = (warp >> 3) * kHalf;   // consumers: tile row, first column
-    const int row = row0 + trow;
+    const int tcol = warp & 7, rq = (warp >> 3) * kHalf;   // consumers: tile column, first of 4 rows
+    const int col = col0 + tcol;
     const int cw = min(p.C, 256);
     TDx* dx = static_cast<TDx*>(p.lv[l].data);
-    const TDy* dy = static_cast<const TDy*>(p.dy);
-    const int4* boxes = p.boxes + (size_t)l * p.K;
     TDy* dybuf = reinterpret_cast<TDy*>(bwd_smem);          // [kS][PP * cw]
     const size_t buf_elems = (size_t)PP * cw;
 
@@ -427,23 +433,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
     for (int cb = 0; cb < p.C; cb += 256) {
         const int nch = min(256, p.C - cb);
         const bool lane_on = lane * 8 < nch;
-        float acc[kHalf][8];
+        float acc[kHalf][8];                      // [row of the strip][channel of the lane]
 #pragma unroll
         for (int x = 0; x < kHalf; ++x)
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[x][e] = 0.f;
 
-        for (int k0 = 0, pass = 0; k0 < p.K; k0 += kBwdChunk, ++pass) {
+        int pass = 0;
+        for (int si = 0; si < p.nsrc; ++si) {
+        const BwdSource& q = p.src[si];
+        const TDy* dy = static_cast<const TDy*>(q.dy);
+        const int4* boxes = q.boxes + (size_t)l * q.K;
+        for (int k0 = 0; k0 < q.K; k0 += kBwdChunk, ++pass) {
             int* wcnt = s_wcnt[pass & 1];
             // ---- RoIs of this chunk that touch the tile, in ascending index order (consumers)
             if (!producer) {
                 const int k = k0 + tid;
                 bool hit = false;
-                if (k < p.K) {
+                if (k < q.K) {
                     const int4 bx = __ldg(boxes + k);
                     hit = (bx.y >= bx.x) && bx.x <= row0 + kTile - 1 && bx.y >= row0 &&
                           bx.z <= col0 + kTile - 1 && bx.w >= col0 &&
-                          ((int)__ldg(p.rois + (size_t)k * 5) == b);
+                          ((int)__ldg(q.rois + (size_t)k * 5) == b);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, hit);
                 if (lane == 0) wcnt[warp] = __popc(bal);
@@ -466,10 +477,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
                 // ---- metadata of all hits, lanes in parallel
                 for (int h = lane; h < nh; h += 32) {
                     const int kk = s_hits[h];
-                    const size_t e = (size_t)l * p.K + kk;
+                    const size_t e = (size_t)l * q.K + kk;
                     const int4 bx = __ldg(boxes + kk);
-                    const int off = __ldg(p.offsets + e);
-                    const int* rg = p.ranges + e * kRangeInts;
+                    const int off = __ldg(q.offsets + e);
+                    const int* rg = q.ranges + e * kRangeInts;
                     int pa = 0, pb = -1, qa = 0, qb = -1;
                     bool first = true;
                     for (int pp = 0; pp < P; ++pp) {
@@ -495,6 +506,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
                                           (r_lo - row0) | ((r_hi - row0) << 8) | ((c_lo - col0) << 16) | ((c_hi - col0) << 24),
                                           off + (r_lo - bx.x));
                     s_xrow[h] = off + (bx.y - bx.x + 1) + (c_lo - bx.z);
+                    s_scale[h] = q.scale ? __ldg(q.scale + e) : 1.f;
                 }
                 __syncwarp();
                 // ---- stream hit h into slot (g + h) % kS
@@ -513,11 +525,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
                         const uint32_t wx_bytes = (uint32_t)(ch - cl + 1) * kTabW * 4u;
                         const uint32_t dy_bytes = (np > 0 && nq > 0) ? (uint32_t)(np * nq) * bin_bytes : 0u;
                         mbar_wait(&s_empty[slot], ((gi / kS) & 1u) ^ 1u);       // consumers left the slot
-                        mbar_expect_tx(&s_full[slot], wy_bytes + wx_bytes + dy_bytes);
-                        bulk_g2s(&s_wy[slot][rl][0], p.weights + (size_t)m.w * kTabW, wy_bytes, &s_full[slot]);
-                        bulk_g2s(&s_wx[slot][cl][0], p.weights + (size_t)s_xrow[h] * kTabW, wx_bytes, &s_full[slot]);
+                        const uint32_t av_bytes = q.addvec ? (uint32_t)nch * 4u : 0u;
+                        mbar_expect_tx(&s_full[slot], wy_bytes + wx_bytes + dy_bytes + av_bytes);
+                        if (av_bytes)
+                            bulk_g2s(&s_av[slot][0], q.addvec + ((size_t)l * q.K + kk) * p.C + cb, av_bytes,
+                                     &s_full[slot]);
+                        bulk_g2s(&s_wy[slot][rl][0], q.weights + (size_t)m.w * kTabW, wy_bytes, &s_full[slot]);
+                        bulk_g2s(&s_wx[slot][cl][0], q.weights + (size_t)s_xrow[h] * kTabW, wx_bytes, &s_full[slot]);
                         if (dy_bytes) {
-                            const size_t dyk = (p.dy_per_level ? (size_t)l * p.K : 0) + kk;
+                            const size_t dyk = (q.dy_per_level ? (size_t)l * q.K : 0) + kk;
                             TDy* dst = dybuf + (size_t)slot * buf_elems;
                             for (int ph = pa; ph <= pb; ++ph) {
                                 const TDy* src = dy + ((dyk * PP + ph * P + qa) * p.C + cb);
@@ -543,52 +559,55 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
                     const int pa = (int)(signed char)(m.y & 0xff), pb = (int)(signed char)((m.y >> 8) & 0xff);
                     const int qa = (int)(signed char)((m.y >> 16) & 0xff), qb = (int)(signed char)((m.y >> 24) & 0xff);
                     const int rl = m.z & 0xff, rh = (m.z >> 8) & 0xff, cl = (m.z >> 16) & 0xff, ch = (m.z >> 24) & 0xff;
-                    if (row < H && pb >= pa && trow >= rl && trow <= rh && xh <= ch && xh + kHalf - 1 >= cl) {
+                    if (col < W && pb >= pa && tcol >= cl && tcol <= ch && rq <= rh && rq + kHalf - 1 >= rl) {
+                        // separable inside the tile: t[c] = sum_pw wx[pw][col] g(ph,pw)[c] once per bin
+                        // row, then acc[r][c] += wy[ph][r] t[c] for the warp's 4 rows
                         const int nq = qb - qa + 1;
-                        const float sbase = p.scale ? __ldg(p.scale + (size_t)l * p.K + kk) : 1.f;
+                        const float sbase = s_scale[h];
                         float av[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) av[e] = 0.f;
-                        if (p.addvec) {
-                            const float* a = p.addvec + ((size_t)l * p.K + kk) * p.C + cb;
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int c = lane * 8 + e;
-                                if (c < nch) av[e] = __ldg(a + c);
-                            }
-                        }
-                        const int e0 = p.ring_edge;
+                        if (q.addvec && lane_on) ld_smem8<float>(&s_av[slot][lane * 8], av);
+                        const int e0 = (l == 0) ? q.ring_edge : -1;
                         const TDy* src = dybuf + (size_t)slot * buf_elems + lane * 8;
                         for (int ph = pa; ph <= pb; ++ph) {
-                            const float wyv = s_wy[slot][trow][ph];
-                            if (wyv == 0.f) continue;
-                            for (int pw = qa; pw <= qb; ++pw) {
-                                float cwt[kHalf];
-                                bool any = false;
+                            float wyr[kHalf];
+                            bool anyr = false;
 #pragma unroll
-                                for (int x = 0; x < kHalf; ++x) {
-                                    cwt[x] = (xh + x >= cl && xh + x <= ch) ? s_wx[slot][xh + x][pw] : 0.f;
-                                    any |= (cwt[x] != 0.f);
-                                }
-                                if (!any) continue;
+                            for (int r = 0; r < kHalf; ++r) {
+                                wyr[r] = (rq + r >= rl && rq + r <= rh) ? s_wy[slot][rq + r][ph] : 0.f;
+                                anyr |= (wyr[r] != 0.f);
+                            }
+                            if (!anyr) continue;
+                            float t[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) t[e] = 0.f;
+                            float wsum = 0.f;
+                            for (int pw = qa; pw <= qb; ++pw) {
+                                const float wxv = s_wx[slot][tcol][pw];
+                                if (wxv == 0.f) continue;
                                 float sv = sbase;
-                                if (e0 >= 0 && l == 0) {
+                                if (e0 >= 0) {
                                     const bool interior = (e0 > 0) && ph >= e0 && ph < P - e0 &&
                                                           pw >= e0 && pw < P - e0;
                                     if (!interior) sv += 1.f;
                                 }
-                                float v[8];
+                                wsum += wxv;
+                                const float w = wxv * sv;
+                                if (lane_on) {
+                                    float v[8];
+                                    ld_smem8<TDy>(src + (size_t)((ph - pa) * nq + (pw - qa)) * cw, v);
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                                if (lane_on) ld_smem8<TDy>(src + (size_t)((ph - pa) * nq + (pw - qa)) * cw, v);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) v[e] = fmaf(sv, v[e], av[e]);
-#pragma unroll
-                                for (int x = 0; x < kHalf; ++x) {
-                                    const float wgt = wyv * cwt[x];
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e) acc[x][e] = fmaf(wgt, v[e], acc[x][e]);
+                                    for (int e = 0; e < 8; ++e) t[e] = fmaf(w, v[e], t[e]);
                                 }
+                            }
+                            if (wsum == 0.f) continue;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) t[e] = fmaf(wsum, av[e], t[e]);
+#pragma unroll
+                            for (int r = 0; r < kHalf; ++r) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(wyr[r], t[e], acc[r][e]);
                             }
                         }
                     }
@@ -599,13 +618,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
             g += (unsigned)nh;
             __syncthreads();                      // s_hits / s_meta are rewritten by the next chunk
         }
-        if (!producer && row < H) {
+        }
+        if (!producer && col < W) {
+            if (!p.nchw) {
 #pragma unroll
-            for (int x = 0; x < kHalf; ++x) {
-                const int col = col0 + xh + x;
-                if (col < W)
-                    Vec8<TDx, false>::store(dx + (((size_t)b * H + row) * W + col) * p.C + cb,
-                                            lane, nch, acc[x]);
+                for (int r = 0; r < kHalf; ++r) {
+                    const int row = row0 + rq + r;
+                    if (row < H)
+                        Vec8<TDx, false>::store(dx + (((size_t)b * H + row) * W + col) * p.C + cb,
+                                                lane, nch, acc[r]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = cb + lane * 8 + e;
+                    if (lane * 8 + e < nch) {
+#pragma unroll
+                        for (int r = 0; r < kHalf; ++r) {
+                            const int row = row0 + rq + r;
+                            if (row < H)
+                                st_elem(dx + (((size_t)b * p.C + c) * H + row) * W + col, acc[r][e]);
+                        }
+                    }
+                }
             }
         }
     }
@@ -761,27 +796,34 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     return HTD_OK;
 }
 
-int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
-                      const float* rois, int K, const int32_t* boxes, const int32_t* offsets,
-                      const int32_t* ranges, const float* weights, int pooled, const void* dy,
-                      int dy_dtype, int dy_per_level, const float* scale, int ring_edge,
-                      const float* addvec, htd_stream_t stream) {
+int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
+                            int dx_nchw, const HtdBwdSource* sources, int nsrc, int pooled,
+                            int dy_dtype, htd_stream_t stream) {
     BwdParams p;
     int rc = fill_levels(p.lv, grad_levels, L, "htd_roi_align_bwd");
     if (rc) return rc;
-    HTD_CHECK_ARG(K >= 0 && B >= 1 && pooled >= 1 && pooled <= HTD_MAX_POOLED,
-                  "htd_roi_align_bwd: bad sizes K=%d B=%d pooled=%d", K, B, pooled);
+    HTD_CHECK_ARG(B >= 1 && pooled >= 1 && pooled <= HTD_MAX_POOLED,
+                  "htd_roi_align_bwd: bad sizes B=%d pooled=%d", B, pooled);
     HTD_CHECK_ARG(C >= 8 && C % 8 == 0, "htd_roi_align_bwd: C=%d must be a positive multiple of 8",
                   C);
     HTD_CHECK_ARG((dx_dtype == HTD_F32 || dx_dtype == HTD_BF16) &&
                       (dy_dtype == HTD_F32 || dy_dtype == HTD_BF16),
                   "htd_roi_align_bwd: unsupported dtype dx=%d dy=%d", dx_dtype, dy_dtype);
-    HTD_CHECK_ARG(K == 0 || (rois && boxes && offsets && ranges && weights && dy),
-                  "htd_roi_align_bwd: null pointer");
-    p.L = L; p.B = B; p.C = C; p.K = K; p.P = pooled; p.sr = 0;
-    p.rois = rois; p.boxes = reinterpret_cast<const int4*>(boxes); p.dy = dy;
-    p.offsets = offsets; p.ranges = ranges; p.weights = weights;
-    p.dy_per_level = dy_per_level; p.scale = scale; p.ring_edge = ring_edge; p.addvec = addvec;
+    HTD_CHECK_ARG(nsrc >= 0 && nsrc <= HTD_MAX_BWD_SOURCES && (nsrc == 0 || sources),
+                  "htd_roi_align_bwd: need 0..%d sources, got %d", HTD_MAX_BWD_SOURCES, nsrc);
+    p.nsrc = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        const HtdBwdSource& q = sources[i];
+        HTD_CHECK_ARG(q.K >= 0, "htd_roi_align_bwd: source %d has K=%d", i, q.K);
+        if (q.K == 0) continue;
+        HTD_CHECK_ARG(q.rois && q.boxes && q.offsets && q.ranges && q.weights && q.dy,
+                      "htd_roi_align_bwd: source %d has a null pointer", i);
+        BwdSource& d = p.src[p.nsrc++];
+        d.rois = q.rois; d.boxes = reinterpret_cast<const int4*>(q.boxes); d.offsets = q.offsets;
+        d.ranges = q.ranges; d.weights = q.weights; d.dy = q.dy; d.scale = q.scale;
+        d.addvec = q.addvec; d.K = q.K; d.dy_per_level = q.dy_per_level; d.ring_edge = q.ring_edge;
+    }
+    p.L = L; p.B = B; p.C = C; p.P = pooled; p.nchw = dx_nchw ? 1 : 0;
     long long total = 0;
     for (int l = 0; l < L; ++l) {
         p.tile_start[l] = (int)total;
@@ -816,6 +858,19 @@ int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_d
 #undef HTD_BWD_LAUNCH
     HTD_CHECK_LAUNCH("htd_roi_align_bwd");
     return HTD_OK;
+}
+
+int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
+                      const float* rois, int K, const int32_t* boxes, const int32_t* offsets,
+                      const int32_t* ranges, const float* weights, int pooled, const void* dy,
+                      int dy_dtype, int dy_per_level, const float* scale, int ring_edge,
+                      const float* addvec, htd_stream_t stream) {
+    HtdBwdSource q;
+    q.rois = rois; q.boxes = boxes; q.offsets = offsets; q.ranges = ranges; q.weights = weights;
+    q.dy = dy; q.scale = scale; q.addvec = addvec; q.K = K; q.dy_per_level = dy_per_level;
+    q.ring_edge = ring_edge; q.reserved = 0;
+    return htd_roi_align_bwd_multi(grad_levels, L, B, C, dx_dtype, 0, &q, 1, pooled, dy_dtype,
+                                   stream);
 }
 
 }  // extern "C"

@@ -151,24 +151,123 @@ class RoIPlan:
 # ------------------------------------------------------------------------------------------
 def _roi_align_bwd(feat_shapes, feat_dtype, scales, rois, plan_tensors, pooled, dy,
                    dy_per_level, scale=None, ring_edge=-1, addvec=None):
-    """Launch the gather backward; returns per-level dX as [B,C,H,W] channels-last tensors."""
-    dev = rois.device
+    """Single-source gather backward; returns per-level dX as [B,C,H,W] channels-last tensors."""
+    src = dict(rois=rois, plan=plan_tensors, dy=dy, dy_per_level=dy_per_level, scale=scale,
+               ring_edge=ring_edge, addvec=addvec)
+    return _bwd_multi(feat_shapes, feat_dtype, False, scales, [src], pooled)
+
+
+def _bwd_multi(feat_shapes, out_dtype, nchw, scales, sources, pooled):
+    """ONE tile-gather launch for several extractor calls (htd_roi_align_bwd_multi).  ``sources``:
+    dicts with rois, plan (boxes, offsets, ranges, weights), dy, dy_per_level, scale, ring_edge,
+    addvec.  Returns per-level dX: [B,C,H,W] contiguous when ``nchw`` else channels-last views."""
+    dev = sources[0]['rois'].device
     L = len(feat_shapes)
     B, C = feat_shapes[0][0], feat_shapes[0][1]
-    bufs = [torch.empty((B, s[2], s[3], C), dtype=feat_dtype, device=dev) for s in feat_shapes]
-    lv = _lib.make_levels(bufs, scales)
-    name = 'roi_align_bwd(BA)' if scale is not None else 'roi_align_bwd(single)'
-    boxes, offsets, ranges, weights = plan_tensors
-    if _lib.ACCOUNT is not None:      # SURVEY 8(d): 49*C*b_out + fh*fw*C*4 per (RoI, level)
-        px = _count_pixels(boxes)
-        n_dy = dy.numel() * dy.element_size()
-        _lib.ACCOUNT.append((name, n_dy + px * C * 4))
+    if nchw:
+        bufs = [torch.empty((B, C, s[2], s[3]), dtype=out_dtype, device=dev) for s in feat_shapes]
+        lv = _lib.make_levels([b.permute(0, 2, 3, 1) for b in bufs], scales)   # H, W from dims 1, 2
+    else:
+        bufs = [torch.empty((B, s[2], s[3], C), dtype=out_dtype, device=dev) for s in feat_shapes]
+        lv = _lib.make_levels(bufs, scales)
+    arr = (_lib.HtdBwdSource * len(sources))()
+    name = 'roi_align_bwd(fused)' if len(sources) > 1 else (
+        'roi_align_bwd(BA)' if sources[0].get('scale') is not None else 'roi_align_bwd(single)')
+    acct = 0
+    for i, q in enumerate(sources):
+        boxes, offsets, ranges, weights = q['plan']
+        a = arr[i]
+        a.rois, a.boxes, a.offsets = q['rois'].data_ptr(), boxes.data_ptr(), offsets.data_ptr()
+        a.ranges, a.weights, a.dy = ranges.data_ptr(), weights.data_ptr(), q['dy'].data_ptr()
+        a.scale = q['scale'].data_ptr() if q.get('scale') is not None else None
+        a.addvec = q['addvec'].data_ptr() if q.get('addvec') is not None else None
+        a.K, a.dy_per_level = q['rois'].shape[0], int(bool(q.get('dy_per_level', False)))
+        a.ring_edge, a.reserved = int(q.get('ring_edge', -1)), 0
+        if _lib.ACCOUNT is not None:  # SURVEY 8(d): 49*C*b_dy + fh*fw*C*4 per (RoI, level)
+            acct += q['dy'].numel() * q['dy'].element_size() + _count_pixels(boxes) * C * 4
+    if _lib.ACCOUNT is not None:
+        _lib.ACCOUNT.append((name, acct))
+    dyt = sources[0]['dy'].dtype
+    assert all(q['dy'].dtype == dyt for q in sources), 'all gradient sources must share a dtype'
     with _lib.timed(name):
-        check(lib().htd_roi_align_bwd(lv, L, B, C, dt(feat_dtype), ptr(rois), rois.shape[0],
-                                      ptr(boxes), ptr(offsets), ptr(ranges), ptr(weights), pooled, ptr(dy),
-                                      dt(dy), int(bool(dy_per_level)), ptr(scale), int(ring_edge),
-                                      ptr(addvec), stream()), 'htd_roi_align_bwd')
-    return [b.permute(0, 3, 1, 2) for b in bufs]
+        check(lib().htd_roi_align_bwd_multi(lv, L, B, C, dt(out_dtype), int(bool(nchw)), arr,
+                                            len(sources), pooled, dt(dyt), stream()),
+              'htd_roi_align_bwd_multi')
+    return bufs if nchw else [b.permute(0, 3, 1, 2) for b in bufs]
+
+
+class GradSink:
+    """Deferred pyramid gradient: the extractor calls of one step park their backward inputs here
+    and the pyramid node gathers all of them in one launch (see ``make_pyramid``)."""
+
+    def __init__(self):
+        self.sources = []
+        self.scales = None
+        self.pooled = None
+
+
+class Pyramid(list):
+    """Channels-last feature maps of one step + the token / sink that defer their gradient."""
+    token = None
+    sink = None
+
+
+class _PyramidFn(torch.autograd.Function):
+    """NCHW maps -> channels-last maps in the compute dtype (one transpose+cast launch per level).
+    The outputs are NOT differentiable themselves: extractors that read them hang their autograd
+    edge on ``token`` and park (rois, plan, dY ...) in ``sink``; this node's backward then runs
+    ONE multi-source tile gather that writes dX directly as [B,C,H,W] in the input dtype - instead
+    of one gather + a full dX write per extractor call, autograd's dX additions and a transpose
+    back (the reference: 13 RoIAlign backward launches with atomics into zero-filled maps)."""
+
+    @staticmethod
+    def forward(ctx, dtype, sink, *xs):
+        outs = []
+        for x in xs:
+            B, C, H, W = x.shape
+            o = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
+            _convert(x, o, B, C, H * W)
+            outs.append(o.permute(0, 3, 1, 2))
+        token = torch.zeros(1, dtype=torch.float32, device=xs[0].device)
+        ctx.sink = sink
+        ctx.meta = ([tuple(x.shape) for x in xs], xs[0].dtype)
+        ctx.mark_non_differentiable(*outs)
+        return (token,) + tuple(outs)
+
+    @staticmethod
+    def backward(ctx, gtoken, *gouts):
+        shapes, xdtype = ctx.meta
+        sink = ctx.sink
+        if not sink.sources:
+            return (None, None) + tuple(torch.zeros(s, dtype=xdtype, device=gtoken.device)
+                                        for s in shapes)
+        # channels-last gather (512 B coalesced stores) + one transpose/cast pass back to the
+        # reference's NCHW layout; writing NCHW straight from the gather measured 30% slower
+        cl = _bwd_multi(shapes, sink.sources[0]['dy'].dtype, False, sink.scales, sink.sources,
+                        sink.pooled)
+        grads = []
+        for g, shp in zip(cl, shapes):
+            B, C, H, W = shp
+            o = torch.empty(shp, dtype=xdtype, device=g.device)
+            _convert(g, o, B, H * W, C)
+            grads.append(o)
+        sink.sources = []
+        return (None, None) + tuple(grads)
+
+
+def make_pyramid(xs, dtype=None):
+    """Feature maps in the layout the kernels read, converted once per step and shared by all
+    extractor calls.  Contiguous NCHW CUDA inputs get the deferred single-launch backward;
+    anything else falls back to per-call ``to_channels_last`` (immediate backward)."""
+    dtype = dtype or xs[0].dtype
+    if all(x.is_cuda and x.dim() == 4 and x.is_contiguous() and not _is_cl(x) for x in xs) and \
+            any(x.requires_grad for x in xs) and torch.is_grad_enabled():
+        sink = GradSink()
+        res = _PyramidFn.apply(dtype, sink, *xs)
+        pyr = Pyramid(res[1:])
+        pyr.token, pyr.sink = res[0], sink
+        return pyr
+    return Pyramid(to_channels_last(x, dtype) for x in xs)
 
 
 def _count_pixels(boxes):
@@ -214,7 +313,8 @@ class _RoIAlignLevels(torch.autograd.Function):
     """rois [K,5] + L channels-last maps -> [K,C,P,P] (roi_level given) or [L,K,C,P,P]."""
 
     @staticmethod
-    def forward(ctx, rois, roi_level, bias, scales, pooled, sampling_ratio, out_dtype, *feats):
+    def forward(ctx, rois, roi_level, bias, scales, pooled, sampling_ratio, out_dtype, token, sink,
+                *feats):
         _lib.require_cuda(rois, *feats)
         L, K = len(feats), rois.shape[0]
         B, C = feats[0].shape[0], feats[0].shape[1]
@@ -229,7 +329,9 @@ class _RoIAlignLevels(torch.autograd.Function):
         bias_c = None if bias is None else bias.detach().reshape(B, C).float().contiguous()
         plan = _fwd_launch('roi_align_fwd(single)' if roi_level is not None else 'roi_align_fwd(all)',
                            feats, scales, rois, roi_level, pooled, sampling_ratio, bias_c, out)
-        ctx.with_dx = any(ctx.needs_input_grad[7:])
+        ctx.deferred = token is not None and ctx.needs_input_grad[7]
+        ctx.sink = sink if ctx.deferred else None
+        ctx.with_dx = ctx.deferred or any(ctx.needs_input_grad[9:])
         if ctx.with_dx:                        # the gather backward reuses the plan
             ctx.save_for_backward(rois, roi_level, *plan.tensors())
         else:
@@ -246,19 +348,26 @@ class _RoIAlignLevels(torch.autograd.Function):
         g = (g.permute(0, 2, 3, 1) if single else g.permute(0, 1, 3, 4, 2)).contiguous()
         dbias = None
         grads = [None] * len(shapes)
-        if ctx.with_dx:
+        gtoken = None
+        if ctx.deferred:                       # park for the pyramid's single gather launch
+            ctx.sink.scales, ctx.sink.pooled = scales, pooled
+            ctx.sink.sources.append(dict(rois=rois, plan=tuple(ctx.saved_tensors[2:]), dy=g,
+                                         dy_per_level=not single))
+            gtoken = torch.zeros(1, dtype=torch.float32, device=g.device)
+        elif ctx.with_dx:
             grads = _roi_align_bwd(shapes, fdtype, scales, rois, ctx.saved_tensors[2:], pooled, g,
                                    dy_per_level=not single)
         if bias_shape is not None and ctx.needs_input_grad[2]:
             gb = g if single else g.sum(0)
             dbias = _bias_grad(gb, rois, B).reshape(bias_shape)
-        return (None, None, dbias, None, None, None, None) + tuple(grads)
+        return (None, None, dbias, None, None, None, None, gtoken, None) + tuple(grads)
 
 
 def roi_align_levels(feats_cl, rois, scales, pooled=7, sampling_ratio=0, roi_level=None, bias=None,
                      out_dtype=None):
     out = _RoIAlignLevels.apply(rois, roi_level, bias, tuple(float(s) for s in scales), int(pooled),
-                                int(sampling_ratio), out_dtype, *feats_cl)
+                                int(sampling_ratio), out_dtype, getattr(feats_cl, 'token', None),
+                                getattr(feats_cl, 'sink', None), *feats_cl)
     return out
 
 
@@ -274,7 +383,8 @@ class _BAFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, rois, w1, b1, w2, b2, add, bias, scales, pooled, sampling_ratio, edge, *feats):
+    def forward(ctx, rois, w1, b1, w2, b2, add, bias, scales, pooled, sampling_ratio, edge, token,
+                sink, *feats):
         _lib.require_cuda(rois, *feats)
         L, K = len(feats), rois.shape[0]
         B, C = feats[0].shape[0], feats[0].shape[1]
@@ -302,7 +412,9 @@ class _BAFunction(torch.autograd.Function):
         check(lib().htd_ba_fuse_fwd(ptr(R), dt(R), ptr(logits), L, K, pooled, C, int(edge),
                                     ptr(add_c), dt(fdt), ptr(bias_c), ptr(rois), B, ptr(wts),
                                     ptr(out), dt(out), stream()), 'htd_ba_fuse_fwd')
-        ctx.with_dx = any(ctx.needs_input_grad[11:])
+        ctx.deferred = token is not None and ctx.needs_input_grad[11]
+        ctx.sink = sink if ctx.deferred else None
+        ctx.with_dx = ctx.deferred or any(ctx.needs_input_grad[13:])
         ctx.save_for_backward(rois, R, m, h, wts, W1, W2, *(plan.tensors() if ctx.with_dx else ()))
         ctx.cfg = (scales, pooled, sampling_ratio, edge, [tuple(f.shape) for f in feats], fdt, B,
                    w1.shape, w2.shape, add is not None,
@@ -330,7 +442,14 @@ class _BAFunction(torch.autograd.Function):
         db1 = dpre.sum(0)
         dm = (dpre @ W1) * (1.0 / PP)                      # [L*K, C], gradient of the bin mean
         grads = [None] * L
-        if ctx.with_dx:
+        gtoken = None
+        if ctx.deferred:
+            ctx.sink.scales, ctx.sink.pooled = scales, pooled
+            ctx.sink.sources.append(dict(rois=rois, plan=tuple(ctx.saved_tensors[7:]), dy=g,
+                                         dy_per_level=False, scale=wts, ring_edge=edge,
+                                         addvec=dm.contiguous()))
+            gtoken = torch.zeros(1, dtype=torch.float32, device=g.device)
+        elif ctx.with_dx:
             grads = _roi_align_bwd(shapes, fdt, scales, rois, ctx.saved_tensors[7:], pooled, g,
                                    dy_per_level=False, scale=wts, ring_edge=edge,
                                    addvec=dm.contiguous())
@@ -338,11 +457,13 @@ class _BAFunction(torch.autograd.Function):
         dbias = None
         if bias_shape is not None and ctx.needs_input_grad[6]:
             dbias = _bias_grad(g, rois, B).reshape(bias_shape)
-        return (None, dW1, db1, dW2, db2, dadd, dbias, None, None, None, None) + tuple(grads)
+        return (None, dW1, db1, dW2, db2, dadd, dbias, None, None, None, None, gtoken, None) + \
+            tuple(grads)
 
 
 def ba_extract(feats_cl, rois, scales, conv1, conv2, pooled=7, sampling_ratio=0, edge=1, add=None,
                bias=None):
     return _BAFunction.apply(rois, conv1.weight, conv1.bias, conv2.weight, conv2.bias, add, bias,
                              tuple(float(s) for s in scales), int(pooled), int(sampling_ratio),
-                             int(edge), *feats_cl)
+                             int(edge), getattr(feats_cl, 'token', None),
+                             getattr(feats_cl, 'sink', None), *feats_cl)

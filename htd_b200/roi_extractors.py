@@ -90,6 +90,8 @@ class BaseRoIExtractor(nn.Module):
 
     def _prep(self, feats):
         scales = [l.spatial_scale for l in self.roi_layers[:len(feats)]]
+        if isinstance(feats, ops.Pyramid):      # converted once per step by the RoI head
+            return feats, scales
         return [ops.to_channels_last(f, self.compute_dtype) for f in feats], scales
 
 

@@ -78,7 +78,7 @@ class HTDRoIHead(nn.Module):
         """Channels-last copy of the levels the extractors read, made once per call."""
         n = self.bbox_roi_extractor[0].num_inputs
         dtype = self.compute_dtype or x[0].dtype
-        return [ops.to_channels_last(f, dtype) for f in x[:n]]
+        return ops.make_pyramid(list(x[:n]), dtype)
 
     def _fuse_global(self, roi_feats, global_feat, rois):
         """htd_roi_head.py:133-141 as a broadcast add (equal whenever every image index is valid)."""

@@ -119,6 +119,30 @@ int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_d
                       int dy_dtype, int dy_per_level, const float* scale, int ring_edge,
                       const float* addvec, htd_stream_t stream);
 
+/* Several extractor calls whose gradients land in the same pyramid (an HTD step has three: the
+ * stage-0 and stage-1 single-level extractions and the BA extraction), gathered in ONE pass over
+ * the tiles of dX.  Per source: the fields of htd_roi_align_bwd.  dx_nchw != 0 writes
+ * grad_levels[l].data as [B,C,H,W] (the layout the reference's FPN expects) instead of
+ * channels-last. */
+#define HTD_MAX_BWD_SOURCES 4
+typedef struct HtdBwdSource {
+    const float* rois;
+    const int32_t* boxes;
+    const int32_t* offsets;
+    const int32_t* ranges;
+    const float* weights;
+    const void* dy;
+    const float* scale;
+    const float* addvec;
+    int32_t K;
+    int32_t dy_per_level;
+    int32_t ring_edge;
+    int32_t reserved;
+} HtdBwdSource;
+int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
+                            int dx_nchw, const HtdBwdSource* sources, int nsrc, int pooled,
+                            int dy_dtype, htd_stream_t stream);
+
 /* Layout / dtype conversion: src [N, R, S] -> dst [N, S, R] (NCHW->NHWC with R=C, S=H*W and
  * back with R=H*W, S=C).  dtypes HTD_F32 / HTD_BF16 independently for src and dst. */
 int htd_layout_convert(const void* src, int src_dtype, void* dst, int dst_dtype, long long N,
