@@ -408,3 +408,67 @@ def test_cuda_graph_step_equals_eager_step():
             assert _l2(g.float(), w.float()) <= 2e-2
         for g, w in zip([t.grad for t in gstep.x], want[2]):
             assert _l2(g.float(), w.float()) <= 2e-2
+
+
+def test_three_images_generalised_stage1_vs_oracle():
+    """The reference hard-codes <= 2 images per GPU in stage 1 (htd_roi_head.py:157-170,180-182;
+    SURVEY F5).  Product and oracle both generalise to "positives are the prefix of every image's
+    block"; check B = 3 (unequal image content, 7+ PGraph groups) in fp32 against the fp64 oracle."""
+    import htd_b200
+    from oracle import cases, restate
+    torch.backends.cudnn.enabled = False
+    B, H, W, K, P = 3, 256, 320, 40, 10
+    x = [t for t in synth.make_pyramid(B, H, W, seed=77)]
+    props = synth.make_proposals(B, K, H, W, seed=78, min_scale=8.0, max_scale=400.0)
+    gts = synth.make_gt(B, props, num_pos=P, seed=79)
+    shapes = [(H, W, 3)] * B
+    oh = restate.HTDRoIHead().double()
+    synth.fill_params_(oh, 'n005', 3)
+    xo = [t.double().requires_grad_(True) for t in x]
+    lo = oh.forward_train_sampled(xo, [p.double() for p in props], gts, shapes, P)
+    go = torch.autograd.grad(sum(v for k, v in lo.items() if 'loss' in k), xo[:4])
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'n005', 3)
+    head = head.cuda()
+    xg = [t.cuda().requires_grad_(True) for t in x]
+    gg_t = [{k: v.cuda() for k, v in g.items()} for g in gts]
+    lg = synth.sampled_forward_train(head, xg, [p.cuda() for p in props], gg_t, shapes, P)
+    gg = torch.autograd.grad(sum(v for k, v in lg.items() if 'loss' in k), xg[:4])
+    for k in lo:
+        if k.endswith('.acc'):
+            assert abs(float(lg[k]) - float(lo[k])) < 1e-3, k
+        else:
+            assert cases.rel_err(lg[k].reshape(1), lo[k].reshape(1)) <= TOL_F32, k
+    for a, b in zip(gg, go):
+        assert cases.rel_err(a, b) <= 1e-4          # whole-head fp32 gradient
+    assert len(head.bbox_head[1].last_plan.groups) >= 6
+
+
+def test_inference_1000_proposals_full_size_properties():
+    """BASELINE config 4 shape: 1 image 800x1333, 1000 proposals, test branch (BA on all RoIs,
+    PGraph groups of up to several hundred RoIs), bf16.  Size-independent properties: finite
+    outputs, determinism, invariance of every RoI's scores to the ORDER of the proposals inside the
+    image (groups are sets: permuting RoIs permutes the rows of the result)."""
+    import htd_b200
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'n005', 5)
+    head = head.cuda().to(torch.bfloat16).eval()
+    head.compute_dtype = torch.bfloat16
+    x = [t.cuda() for t in synth.make_pyramid(1)]
+    props = [p.cuda() for p in synth.make_proposals(1, 1000)]
+    metas = [dict(img_shape=(800, 1333, 3), scale_factor=1.0)]
+    with torch.no_grad():
+        r1, s1, b1 = head.simple_test_scores(x, props, metas)
+        r2, s2, b2 = head.simple_test_scores(x, props, metas)
+        perm = torch.randperm(1000, generator=torch.Generator().manual_seed(0)).cuda()
+        r3, s3, b3 = head.simple_test_scores(x, [props[0][perm]], metas)
+    assert torch.isfinite(s1.float()).all() and torch.isfinite(b1.float()).all()
+    assert torch.equal(s1, s2) and torch.equal(b1, b2)
+    assert torch.equal(r3, r1[perm])
+    # sums inside a group run in a different order after the permutation: bf16 tolerance
+    den = s1.float().abs().max()
+    assert ((s3.float() - s1[perm].float()).abs().max() / den).item() <= 2e-2
+    sizes = [n for _, _, _, n in head.bbox_head[1].last_plan.groups]
+    assert sum(sizes) == 1000 and max(sizes) >= 200
+    res = head.simple_test(x, props, metas)
+    assert len(res) == 1 and len(res[0]) == 80
