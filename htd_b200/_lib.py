@@ -66,6 +66,10 @@ SIGNATURES = {
                         c_void_p, c_void_p],
     'htd_bias_grad': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                       c_void_p],
+    'htd_gn_relu_fwd': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                        c_void_p, c_void_p, c_void_p, c_void_p],
+    'htd_gn_relu_bwd': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                        c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_pgraph_plan': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_pgraph_pack': [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_void_p, c_int, c_int,
@@ -91,7 +95,8 @@ SIGNATURES = {
 _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3}
+KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
+                    'htd_gn_relu_bwd': 2}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 
 

@@ -22,6 +22,7 @@ from .registry import HEADS, build_bbox_coder, build_loss
 
 
 class ConvModule(nn.Module):
+    fused_gn = True      # class switch (diagnostics): GN + ReLU through csrc/gn_relu.cu
     """The subset of mmcv.cnn.ConvModule the path uses: conv -> (GN) -> ReLU, bias='auto'
     (no conv bias when a norm layer follows); sub-module names ``conv`` / ``gn`` as in mmcv."""
 
@@ -50,6 +51,11 @@ class ConvModule(nn.Module):
     def forward(self, x):
         x = self.conv(x)
         if self.gn is not None:
+            if self.with_act and x.is_cuda and (x.size(1) // self.gn.num_groups) % 8 == 0 \
+                    and ConvModule.fused_gn:
+                # GN + ReLU as one kernel (csrc/gn_relu.cu)
+                return ops.group_norm_relu(x, self.gn.weight, self.gn.bias, self.gn.num_groups,
+                                           self.gn.eps)
             x = self.gn(x)
         return F.relu(x, inplace=True) if self.with_act else x
 

@@ -467,3 +467,51 @@ def ba_extract(feats_cl, rois, scales, conv1, conv2, pooled=7, sampling_ratio=0,
                              tuple(float(s) for s in scales), int(pooled), int(sampling_ratio),
                              int(edge), getattr(feats_cl, 'token', None),
                              getattr(feats_cl, 'sink', None), *feats_cl)
+
+
+# ------------------------------------------------------------------------------------------
+# fused GroupNorm + ReLU (regression conv tower)
+# ------------------------------------------------------------------------------------------
+class _GroupNormReLU(torch.autograd.Function):
+    """relu(group_norm(x)) on channels-last [N,C,H,W] tensors: one launch forward, two backward
+    (csrc/gn_relu.cu) instead of ATen's moments / affine / relu / internal-gradients / backward /
+    parameter-reduction kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, groups, eps):
+        _lib.require_cuda(x, weight, bias)
+        if not _is_cl(x):
+            x = x.contiguous(memory_format=torch.channels_last)
+        N, C, H, W = x.shape
+        y = torch.empty_like(x)               # preserves channels_last
+        sdt = torch.float64 if x.dtype == torch.float32 else torch.float32
+        mean = torch.empty(N * groups, dtype=sdt, device=x.device)
+        rstd = torch.empty_like(mean)
+        gamma = weight.detach().float().contiguous()
+        beta = bias.detach().float().contiguous()
+        check(lib().htd_gn_relu_fwd(ptr(x), dt(x), N, H * W, C, int(groups), ptr(gamma), ptr(beta),
+                                    float(eps), ptr(y), ptr(mean), ptr(rstd), stream()),
+              'htd_gn_relu_fwd')
+        ctx.save_for_backward(x, mean, rstd, gamma, beta)
+        ctx.cfg = (int(groups), weight.dtype, bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, gamma, beta = ctx.saved_tensors
+        groups, wdt, bdt = ctx.cfg
+        N, C, H, W = x.shape
+        if not _is_cl(dy) or dy.dtype != x.dtype:
+            dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        part = torch.empty((2, max(N, 1), C), dtype=torch.float32, device=x.device)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty_like(dgamma)
+        check(lib().htd_gn_relu_bwd(ptr(x), ptr(dy), dt(x), ptr(mean), ptr(rstd), ptr(gamma),
+                                    ptr(beta), N, H * W, C, groups, ptr(dx), ptr(part), ptr(dgamma),
+                                    ptr(dbeta), stream()), 'htd_gn_relu_bwd')
+        return dx, dgamma.to(wdt), dbeta.to(bdt), None, None
+
+
+def group_norm_relu(x, weight, bias, groups, eps=1e-5):
+    return _GroupNormReLU.apply(x, weight, bias, groups, eps)

@@ -266,6 +266,21 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
                     htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
+ * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and
+ * (C / G) % 8 == 0; gamma / beta fp32; mean / rstd [N*G]: fp32 for HTD_BF16 tensors, fp64 for
+ * HTD_F32 tensors (the fp32 configuration computes its statistics and residuals in fp64).
+ *   y = relu((x - mean) * rstd * gamma + beta), mean / rstd per (n, group), biased variance + eps
+ * Backward recomputes the ReLU mask from x; part is a [2, N, C] fp32 workspace; dgamma / dbeta
+ * are fully written. */
+int htd_gn_relu_fwd(const void* x, int dtype, int N, int HW, int C, int G, const float* gamma,
+                    const float* beta, float eps, void* y, void* mean, void* rstd,
+                    htd_stream_t stream);
+int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, const void* rstd,
+                    const float* gamma, const float* beta, int N, int HW, int C, int G, void* dx,
+                    float* part, float* dgamma, float* dbeta, htd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Device-side scheduling of the PGraph contractions: no host read of the plan table, so the whole
  * head step can be captured in a CUDA graph.  htd_pgraph_schedule derives, from the plan table on
  * the DEVICE, the problem descriptors of the six contraction shapes of the forward/backward pass

@@ -192,3 +192,34 @@ def test_library_has_no_cpu_path():
     from htd_b200 import ops
     with pytest.raises(RuntimeError):
         ops.level_assign(torch.zeros(4, 5), 4)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('C,G,HW', [(576, 36, (7, 7)), (64, 8, (5, 3)), (96, 4, (7, 7))])
+def test_fused_group_norm_relu(dtype, tol, C, G, HW):
+    """csrc/gn_relu.cu against torch's fp64 GroupNorm + ReLU (forward, dx, dgamma, dbeta)."""
+    from htd_b200 import ops
+    from oracle import cases
+    g = torch.Generator().manual_seed(C + G)
+    N = 24
+    x = (torch.randn(N, C, *HW, generator=g) * 1.5 + 0.3).to(dtype)
+    w = (1.0 + 0.2 * torch.randn(C, generator=g)).to(dtype)
+    b = (0.2 * torch.randn(C, generator=g)).to(dtype)
+    dy = torch.randn(N, C, *HW, generator=g).to(dtype)
+    xo, wo, bo = (t.double().requires_grad_(True) for t in (x, w, b))
+    yo = torch.relu(torch.nn.functional.group_norm(xo, G, wo, bo, 1e-5))
+    go = torch.autograd.grad((yo * dy.double()).sum(), [xo, wo, bo])
+    xg = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wg, bg = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    yg = ops.group_norm_relu(xg, wg, bg, G)
+    gg = torch.autograd.grad((yg.float() * dy.cuda().float()).sum(), [xg, wg, bg])
+    assert yg.is_contiguous(memory_format=torch.channels_last)
+    assert cases.rel_err(yg.float(), yo) <= tol
+    # gradients: the ReLU mask is recomputed from x - in bf16 an activation within rounding of
+    # zero can flip, so compare dx in relative L2 there (max-norm in fp32)
+    for a, want, name in zip(gg, go, ('dx', 'dgamma', 'dbeta')):
+        if dtype == torch.float32:
+            assert cases.rel_err(a.float(), want) <= tol, name
+        else:
+            num = (a.double().cpu() - want).norm() / want.norm()
+            assert float(num) <= 3e-2, (name, float(num))

@@ -13,6 +13,8 @@ if dtype == torch.float32:
 c = cases.CASES[name]
 oh = restate.HTDRoIHead().double()
 synth.fill_params_(oh, c['scheme'], c['seed'])
+import htd_b200.bbox_heads as bh
+bh.ConvModule.fused_gn = os.environ.get('FUSED_GN', '1') == '1'
 head = htd_b200.build_htd_roi_head()
 synth.fill_params_(head, c['scheme'], c['seed'])
 head = head.cuda().to(dtype)
