@@ -259,11 +259,21 @@ def run_gpu(args):
 
     # ---- the step as one CUDA graph (forward + losses + backward), replayed per step ---------
     use_graph = not args.no_graph
+    gstep = None
     if use_graph:
         if reducer is not None:
             reducer.remove()
         from htd_b200.graphed import GraphedTrainStep
-        gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1)
+        try:
+            gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1)
+        except Exception as e:                     # never lose the measurement to a capture problem
+            print(f'[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager',
+                  file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
+            if world > 1:
+                reducer = GradAllReducer(head.parameters(), world)
+    if use_graph:
 
         def allreduce_grads():
             if world == 1:

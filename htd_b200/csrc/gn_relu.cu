@@ -198,19 +198,26 @@ __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_bwd_kernel(
     }
 }
 
-// backward, phase 2: dgamma[c] = sum_n part[0][n][c], dbeta[c] = sum_n part[1][n][c]
+// backward, phase 2: dgamma[c] = sum_n part[0][n][c], dbeta[c] = sum_n part[1][n][c].
+// block = 32 channels x 8 row slices (blockIdx.y selects dgamma / dbeta), fixed summation order.
 __global__ void __launch_bounds__(256) gn_param_reduce_kernel(const float* __restrict__ part, int N,
                                                               int C, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float a = 0.f, b = 0.f;
-    for (int n = 0; n < N; ++n) {
-        a += part[((size_t)0 * N + n) * C + c];
-        b += part[((size_t)1 * N + n) * C + c];
+    __shared__ float s_part[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const float* src = part + (size_t)blockIdx.y * N * C;
+    float a = 0.f;
+    if (c < C)
+        for (int n = ty; n < N; n += 8) a += src[(size_t)n * C + c];
+    s_part[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_part[i][tx];
+        (blockIdx.y == 0 ? dgamma : dbeta)[c] = t;
     }
-    dgamma[c] = a;
-    dbeta[c] = b;
 }
 
 static bool gn_args_ok(int N, int HW, int C, int G) {
@@ -275,7 +282,7 @@ int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, 
                 static_cast<const float*>(mean), static_cast<const float*>(rstd), gamma, beta, N, HW, C, G, static_cast<__nv_bfloat16*>(dx), part);
         HTD_CHECK_LAUNCH("htd_gn_relu_bwd");
     }
-    gn_param_reduce_kernel<<<(C + 255) / 256, 256, 0, st>>>(part, N, C, dgamma, dbeta);
+    gn_param_reduce_kernel<<<dim3((C + 31) / 32, 2), 256, 0, st>>>(part, N, C, dgamma, dbeta);
     HTD_CHECK_LAUNCH("htd_gn_relu_bwd(params)");
     return HTD_OK;
 }
