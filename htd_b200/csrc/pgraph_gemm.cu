@@ -10,14 +10,19 @@
 //     D[M,N] = A[M,K] * B[N,K]^T       (both operands K-major, bf16, fp32 accumulate)
 // executed here for ALL groups of the batch in one launch.
 //
-// Kernel structure (one CTA per 128x128 output tile, 192 threads):
-//   warp 0     TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A tile and a 128x64 B tile
-//              (128B swizzle) into a kStages-deep shared-memory ring, completion on mbarriers;
-//   warp 1     allocates 128 TMEM columns, then one elected lane issues tcgen05.mma
-//              (cta_group::1, kind::f16, M=128, N=128, K=16) four per k-block and releases the
-//              smem slot with tcgen05.commit; a final commit signals the epilogue;
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, convert, store D row-major
-//              (fp32 or bf16) and/or D^T (bf16, the K-major operand of the next contraction).
+// Kernel structure (persistent CTAs, one per SM, looping over 128x256 output tiles, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor 2D loads of a 128x64 A tile and a 256x64 B tile
+//              (128B swizzle) into a 4-stage shared-memory ring that runs across tile boundaries,
+//              completion on mbarriers;
+//   warp 1     allocates all 512 TMEM columns (two 256-column accumulators), then one elected lane
+//              issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=256, K=16) four per k-block,
+//              releases the smem slot with tcgen05.commit and signals "accumulator full";
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / ReLU, store D row-major
+//              (fp32 or bf16, optionally through a row scatter map) and/or D^T (the K-major
+//              operand of the next contraction), then "accumulator empty" - so the epilogue of
+//              tile i overlaps the MMAs of tile i+1.
+// The 128x256 tile halves the A-operand traffic per flop of a 128x128 tile (48 KB per 4.2 MFLOP):
+// with 128x128 tiles the L2 -> SM operand stream capped the kernel near 45% of the tensor peak.
 // Rows/columns of a tile that fall outside the group's M x N are computed on whatever the TMA
 // fetched (next group's rows or zero fill) and simply not stored; only the K extent must be
 // zero padded, which the packing kernels guarantee.
@@ -27,11 +32,14 @@
 
 namespace htd {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;   // 3 x 32 KB: two CTAs per SM, so one tile's epilogue overlaps the other's MMAs
-constexpr int kTileBytes = kBM * kBK * 2;            // 16 KiB per operand tile
+constexpr int kBM = 128, kBN = 256, kBK = 64, kStages = 4;
+constexpr int kATileBytes = kBM * kBK * 2;           // 16 KiB
+constexpr int kBTileBytes = kBN * kBK * 2;           // 32 KiB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;
 constexpr int kGemmThreads = 192;
-constexpr int kTmemCols = 128;
-constexpr int kSmemBytes = kStages * 2 * kTileBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kAccStages = 2;                        // TMEM accumulator double buffer
+constexpr int kTmemCols = kAccStages * kBN;          // 512: the whole tensor memory of the SM
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmParams {
     HtdGemmGroup grp[HTD_MAX_GROUPS];
@@ -50,22 +58,28 @@ struct GemmParams {
     const int* tile_start_dev;
 };
 
-// blockIdx -> (group, local tile); false when the CTA is beyond the scheduled tiles
-__device__ __forceinline__ bool decode_tile(const GemmParams& p, HtdGemmGroup& grp, int& local) {
+// tile index -> (group, local tile); total_tiles() bounds the persistent loops
+__device__ __forceinline__ int total_tiles(const GemmParams& p) {
+    return p.grp_dev != nullptr ? p.tile_start_dev[HTD_MAX_GROUPS] : p.tile_start[HTD_MAX_GROUPS];
+}
+__device__ __forceinline__ bool decode_tile_at(const GemmParams& p, int t, HtdGemmGroup& grp, int& local) {
     if (p.grp_dev != nullptr) {
-        const int total = p.tile_start_dev[HTD_MAX_GROUPS];
-        if ((int)blockIdx.x >= total) return false;
+        if (t >= p.tile_start_dev[HTD_MAX_GROUPS]) return false;
         int g = 0;
-        while (g + 1 < HTD_MAX_GROUPS && (int)blockIdx.x >= p.tile_start_dev[g + 1]) ++g;
+        while (g + 1 < HTD_MAX_GROUPS && t >= p.tile_start_dev[g + 1]) ++g;
         grp = p.grp_dev[g];
-        local = (int)blockIdx.x - p.tile_start_dev[g];
+        local = t - p.tile_start_dev[g];
     } else {
+        if (t >= p.tile_start[HTD_MAX_GROUPS]) return false;
         int g = 0;
-        while (g + 1 < p.G && (int)blockIdx.x >= p.tile_start[g + 1]) ++g;
+        while (g + 1 < p.G && t >= p.tile_start[g + 1]) ++g;
         grp = p.grp[g];
-        local = (int)blockIdx.x - p.tile_start[g];
+        local = t - p.tile_start[g];
     }
     return true;
+}
+__device__ __forceinline__ bool decode_tile(const GemmParams& p, HtdGemmGroup& grp, int& local) {
+    return decode_tile_at(p, (int)blockIdx.x, grp, local);
 }
 
 // Shared epilogue: one thread owns output row m of its group and 32 consecutive columns n0.. of
@@ -198,28 +212,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) |
                             ((uint32_t)(kBM >> 4) << 24);
 
-__global__ void __launch_bounds__(kGemmThreads, 2)
+// Persistent: one CTA per SM loops over output tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// Tile = 128 x 256 (one tcgen05.mma M128 N256 K16 per 16 K-elements); the accumulator is double
+// buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+__global__ void __launch_bounds__(kGemmThreads, 1)
     pgraph_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                        const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kStages * kTileBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + 2 * kStages * kTileBytes);
+    uint8_t* smem_b = smem + kStages * kATileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + kStages;        // [kAccStages]
+    uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;  // [kAccStages]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + kAccStages);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ---- tile decode (uniform per CTA; surplus CTAs of a scheduled launch leave before any setup)
-    HtdGemmGroup grp;
-    int local;
-    if (!decode_tile(p, grp, local)) return;
-    const int tiles_n = (grp.N + kBN - 1) / kBN;
-    const int mt = local / tiles_n, nt = local % tiles_n;
-    const int kblocks = (grp.K + kBK - 1) / kBK;
+    const int ntiles = total_tiles(p);
+    if ((int)blockIdx.x >= ntiles) return;                // uniform: surplus CTAs leave before setup
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -231,8 +243,11 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
                 mbar_init(full_bar + s, 1);
                 mbar_init(empty_bar + s, 1);
             }
-            mbar_init(tmem_full_bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int a = 0; a < kAccStages; ++a) {
+                mbar_init(tmem_full_bar + a, 1);
+                mbar_init(tmem_empty_bar + a, 4);          // one arrival per epilogue warp
+            }
+            fence_mbar_init();
         }
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -248,55 +263,88 @@ __global__ void __launch_bounds__(kGemmThreads, 2)
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(empty_bar + s, ph ^ 1u);
-                mbar_expect_tx(full_bar + s, 2 * kTileBytes);
-                tma_load_2d(&tmap_a, full_bar + s, smem_a + s * kTileBytes, grp.a_k0 + kb * kBK,
-                            grp.a_row + mt * kBM);
-                tma_load_2d(&tmap_b, full_bar + s, smem_b + s * kTileBytes, grp.b_k0 + kb * kBK,
-                            grp.b_row + nt * kBN);
+            unsigned it = 0;                              // k-blocks issued so far (ring position)
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                HtdGemmGroup grp;
+                int local;
+                decode_tile_at(p, t, grp, local);
+                const int tiles_n = (grp.N + kBN - 1) / kBN;
+                const int mt = local / tiles_n, nt = local % tiles_n;
+                const int kblocks = (grp.K + kBK - 1) / kBK;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(empty_bar + s, ((it / kStages) & 1u) ^ 1u);
+                    mbar_expect_tx(full_bar + s, kStageBytes);
+                    tma_load_2d(&tmap_a, full_bar + s, smem_a + s * kATileBytes, grp.a_k0 + kb * kBK,
+                                grp.a_row + mt * kBM);
+                    tma_load_2d(&tmap_b, full_bar + s, smem_b + s * kBTileBytes, grp.b_k0 + kb * kBK,
+                                grp.b_row + nt * kBN);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(full_bar + s, ph);
+            unsigned it = 0, lt = 0;                      // k-blocks / tiles consumed so far
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+                HtdGemmGroup grp;
+                int local;
+                decode_tile_at(p, t, grp, local);
+                const int kblocks = (grp.K + kBK - 1) / kBK;
+                const unsigned a = lt % kAccStages;
+                mbar_wait(tmem_empty_bar + a, ((lt / kAccStages) & 1u) ^ 1u);   // epilogue drained it
                 tcgen05_fence_after();
-                const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * kTileBytes));
-                const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + s * kTileBytes));
+                const uint32_t tmem_d = tmem_base + a * kBN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(full_bar + s, (it / kStages) & 1u);
+                    tcgen05_fence_after();
+                    const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * kATileBytes));
+                    const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + s * kBTileBytes));
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in >>4 units
-                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
-                              (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in >>4 units
+                        umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tcgen05_commit(empty_bar + s);       // frees the smem slot when the MMAs retire
                 }
-                tcgen05_commit(empty_bar + s);   // frees the smem slot when the MMAs retire
+                tcgen05_commit(tmem_full_bar + a);       // accumulator of this tile complete
             }
-            tcgen05_commit(tmem_full_bar);       // accumulator complete
         }
     } else {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        const int m = (kblocks > 0) ? mt * kBM + q * 32 + lane : grp.M;   // K == 0: nothing stored
+        unsigned lt = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+            HtdGemmGroup grp;
+            int local;
+            decode_tile_at(p, t, grp, local);
+            const int tiles_n = (grp.N + kBN - 1) / kBN;
+            const int mt = local / tiles_n, nt = local % tiles_n;
+            const int kblocks = (grp.K + kBK - 1) / kBK;
+            const unsigned a = lt % kAccStages;
+            mbar_wait(tmem_full_bar + a, (lt / kAccStages) & 1u);
+            tcgen05_fence_after();
+            const int m = (kblocks > 0) ? mt * kBM + q * 32 + lane : grp.M;   // K == 0: nothing stored
+            const int nvalid = grp.N - nt * kBN;                              // columns of this tile
 #pragma unroll 1
-        for (int ch = 0; ch < kBN / 32; ++ch) {
-            uint32_t v[32];
-            __syncwarp();      // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-            float f[32];
+            for (int ch = 0; ch < kBN / 32; ++ch) {
+                if (ch * 32 >= nvalid) break;                                  // warp-uniform
+                uint32_t v[32];
+                __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * kBN + (uint32_t)(ch * 32), v);
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            epilogue_store32(p, grp, m, nt * kBN + ch * 32, f);
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                epilogue_store32(p, grp, m, nt * kBN + ch * 32, f);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar + a);
         }
-        tcgen05_fence_before();
     }
+    tcgen05_fence_before();
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
@@ -446,7 +494,8 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long ld, const char* who) {
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long ld, int box_rows,
+                    const char* who) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("%s: cuTensorMapEncodeTiled is unavailable", who);
@@ -454,7 +503,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     }
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -489,9 +538,9 @@ static int launch_gemm(const void* A, long long a_rows, long long a_ld, const vo
     HTD_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0,
                   "htd_pgraph_gemm: operands must be 16-byte aligned");
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, a_rows, a_ld, "htd_pgraph_gemm(A)");
+    int rc = make_map(&ma, A, a_rows, a_ld, kBM, "htd_pgraph_gemm(A)");
     if (rc) return rc;
-    rc = make_map(&mb, B, b_rows, b_ld, "htd_pgraph_gemm(B)");
+    rc = make_map(&mb, B, b_rows, b_ld, kBN, "htd_pgraph_gemm(B)");
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
@@ -504,7 +553,15 @@ static int launch_gemm(const void* A, long long a_rows, long long a_ld, const vo
         }
         attr_set = true;
     }
-    pgraph_gemm_kernel<<<(unsigned)total, kGemmThreads, kSmemBytes, st>>>(ma, mb, p);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+            num_sms = 148;
+    }
+    const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);   // persistent CTAs
+    pgraph_gemm_kernel<<<grid, kGemmThreads, kSmemBytes, st>>>(ma, mb, p);
     HTD_CHECK_LAUNCH("htd_pgraph_gemm(bf16)");
     return HTD_OK;
 }

@@ -56,12 +56,24 @@ def main():
             torch.autograd.grad((out * dy).sum(), [x, sam] + W + b)
         t_f = timeit(fwd)
         t_fb = timeit(fwdbwd)
+        # the same forward as one CUDA graph: device time without host launch gaps
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fwd()
+        t_g = timeit(gr.replay)
         # only the contractions, timed per launch
         _lib.TIMER = _lib.KernelTimer()
         fwd(); torch.cuda.synchronize()
         n, tg = _lib.TIMER.summary().get('pgraph_gemm', (0, 0.0))
         _lib.TIMER = None
-        print(json.dumps(dict(N=N, dtype=a.dtype, fwd_ms=t_f, fwdbwd_ms=t_fb, fwd_gflop=fwd_flops / 1e9,
+        print(json.dumps(dict(N=N, dtype=a.dtype, fwd_ms=t_f, fwd_graph_ms=t_g, fwd_graph_tflops=fwd_flops / t_g / 1e9,
+                              fwd_graph_frac_of_burst_peak=fwd_flops / t_g / 1e9 / burst, fwdbwd_ms=t_fb, fwd_gflop=fwd_flops / 1e9,
                               fwd_tflops=fwd_flops / t_f / 1e9, gemm_launches=n, gemm_ms=tg,
                               gemm_tflops=fwd_flops / tg / 1e9 if tg else None,
                               frac_of_burst_peak=(fwd_flops / tg / 1e9 / burst) if tg else None,
