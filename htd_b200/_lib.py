@@ -66,6 +66,17 @@ SIGNATURES = {
                         c_void_p, c_void_p],
     'htd_bias_grad': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                       c_void_p],
+    'htd_bbox_targets': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                         ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_void_p],
+    'htd_bbox_decode': [c_void_p, c_int, c_void_p, c_int, c_int, ctypes.POINTER(c_float),
+                        ctypes.POINTER(c_float), c_float, c_int, c_float, c_float, c_void_p, c_int,
+                        c_void_p],
+    'htd_rcnn_loss_fwd': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p],
+    'htd_rcnn_loss_bwd': [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                          c_float, c_float, c_int, c_void_p],
     'htd_gn_relu_fwd': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_gn_relu_bwd': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
@@ -96,7 +107,7 @@ _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
 KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
-                    'htd_gn_relu_bwd': 2}
+                    'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 
 

@@ -128,6 +128,9 @@ class BBoxHead(nn.Module):
 
     def get_targets(self, sampling_results, gt_bboxes, gt_labels, rcnn_train_cfg, concat=True):
         cfg = as_cfg(rcnn_train_cfg)
+        if concat and self.fused_glue and not self.reg_decoded_bbox and sampling_results and \
+                sampling_results[0].pos_bboxes.is_cuda:
+            return self._get_targets_fused(sampling_results, cfg)
         sizes = {(r.pos_bboxes.size(0), r.neg_bboxes.size(0)) for r in sampling_results}
         if concat and len(sizes) == 1 and len(sampling_results) > 1 and min(next(iter(sizes))) > 0 \
                 and not self.reg_decoded_bbox:
@@ -156,6 +159,31 @@ class BBoxHead(nn.Module):
         cols = list(zip(*outs))
         return tuple(torch.cat(c, 0) for c in cols) if concat else tuple(list(c) for c in cols)
 
+    def _get_targets_fused(self, sampling_results, cfg):
+        """All images in ONE htd_bbox_targets launch: the gt of the positives is laid out in the
+        sampled-RoI order (positives are the prefix of each image's block)."""
+        dev = sampling_results[0].pos_bboxes.device
+        sizes = tuple((r.pos_bboxes.size(0), r.neg_bboxes.size(0)) for r in sampling_results)
+        key = (sizes, str(dev))
+        is_pos = BBoxHead._pos_mask_cache.get(key)
+        if is_pos is None:                      # depends on the counts only: built once, reused
+            m = torch.cat([torch.cat([torch.ones(p, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)])
+                           for p, n in sizes])
+            is_pos = BBoxHead._pos_mask_cache[key] = m.to(dev)
+        boxes = torch.cat([t for r in sampling_results for t in (r.pos_bboxes, r.neg_bboxes)], 0)
+        K = boxes.size(0)
+        gtb = boxes.new_zeros((K, 4), dtype=torch.float32)
+        gtl = torch.zeros(K, dtype=torch.long, device=dev)
+        off = 0
+        for r, (p, n) in zip(sampling_results, sizes):
+            if p:
+                gtb[off:off + p] = r.pos_gt_bboxes
+                gtl[off:off + p] = r.pos_gt_labels
+            off += p + n
+        pw = cfg.get('pos_weight', -1) if cfg is not None else -1
+        return ops.bbox_targets(boxes, gtb, gtl, is_pos, self.num_classes, pw, self.bbox_coder.means,
+                                self.bbox_coder.stds)
+
     def loss(self, cls_score, bbox_pred, rois, labels, label_weights, bbox_targets, bbox_weights,
              reduction_override=None):
         """bbox_head.py:141-186 in static-shape form: the reference selects the positive rows
@@ -163,6 +191,13 @@ class BBoxHead(nn.Module):
         sums are taken over ALL rows with the positive mask as a 0/1 factor and `avg_factor` kept
         on the device - identical values, no host sync, capturable in a CUDA graph."""
         losses = dict()
+        if self._fused_loss_ok(cls_score, bbox_pred, reduction_override):
+            # one kernel pair for CE + accuracy + smooth-L1 and their gradients (csrc/rcnn_glue.cu)
+            loss_cls, acc, loss_bbox = ops.rcnn_loss(
+                cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights,
+                self.num_classes, self.loss_bbox.beta, self.loss_cls.loss_weight,
+                self.loss_bbox.loss_weight)
+            return dict(loss_cls=loss_cls, acc=acc, loss_bbox=loss_bbox)
         if cls_score is not None:
             cls_score = cls_score.float()                      # force_fp32 (bbox_head.py:141)
             avg_factor = torch.sum(label_weights > 0).float().clamp(min=1.)
@@ -187,6 +222,18 @@ class BBoxHead(nn.Module):
                                                  avg_factor=bbox_targets.size(0),
                                                  reduction_override=reduction_override)
         return losses
+
+    def _fused_loss_ok(self, cls_score, bbox_pred, reduction_override):
+        from .core import CrossEntropyLoss, SmoothL1Loss
+        return (cls_score is not None and bbox_pred is not None and cls_score.is_cuda
+                and cls_score.numel() > 0 and self.reg_class_agnostic and not self.reg_decoded_bbox
+                and reduction_override is None and bbox_pred.size(-1) == 4
+                and type(self.loss_cls) is CrossEntropyLoss and type(self.loss_bbox) is SmoothL1Loss
+                and self.loss_cls.reduction == 'mean' and self.loss_bbox.reduction == 'mean'
+                and self.loss_cls.class_weight is None and self.fused_glue)
+
+    fused_glue = True        # class switch (diagnostics): targets / loss / decode via csrc/rcnn_glue.cu
+    _pos_mask_cache = {}
 
     # ---- decoding (bbox_head.py:188-335) ------------------------------------------------------
     def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False,
@@ -221,6 +268,9 @@ class BBoxHead(nn.Module):
             inds = torch.stack((label, label + 1, label + 2, label + 3), 1)
             bbox_pred = torch.gather(bbox_pred, 1, inds)
         assert bbox_pred.size(1) == 4
+        if self.fused_glue and rois.is_cuda and getattr(self.bbox_coder, 'clip_border', True):
+            return ops.bbox_decode(rois, bbox_pred, self.bbox_coder.means, self.bbox_coder.stds,
+                                   max_shape=img_meta['img_shape'])
         if rois.size(1) == 4:
             return self.bbox_coder.decode(rois, bbox_pred, max_shape=img_meta['img_shape'])
         boxes = self.bbox_coder.decode(rois[:, 1:], bbox_pred, max_shape=img_meta['img_shape'])

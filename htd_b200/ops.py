@@ -6,6 +6,8 @@ channels-last: a ``[B,C,H,W]`` tensor whose memory is ``[B,H,W,C]``; RoI feature
 ``[K,C,P,P]`` tensors with channels_last strides (values index exactly like the reference's
 NCHW tensors).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -515,3 +517,95 @@ class _GroupNormReLU(torch.autograd.Function):
 
 def group_norm_relu(x, weight, bias, groups, eps=1e-5):
     return _GroupNormReLU.apply(x, weight, bias, groups, eps)
+
+
+# ------------------------------------------------------------------------------------------
+# target / loss / decode glue (csrc/rcnn_glue.cu)
+# ------------------------------------------------------------------------------------------
+def _f4(v):
+    return (ctypes.c_float * 4)(*[float(t) for t in v])
+
+
+def bbox_targets(boxes, gt_boxes, gt_labels, is_pos, num_classes, pos_weight, means, stds):
+    """labels, label_weights, bbox_targets, bbox_weights of all sampled RoIs in one launch."""
+    _lib.require_cuda(boxes, gt_boxes, gt_labels, is_pos)
+    K = boxes.shape[0]
+    dev = boxes.device
+    boxes = boxes.detach().float().contiguous()
+    gt_boxes = gt_boxes.detach().float().contiguous()
+    gt_labels = gt_labels.detach().long().contiguous()
+    labels = torch.empty(K, dtype=torch.long, device=dev)
+    lw = torch.empty(K, dtype=torch.float32, device=dev)
+    bt = torch.empty((K, 4), dtype=torch.float32, device=dev)
+    bw = torch.empty((K, 4), dtype=torch.float32, device=dev)
+    check(lib().htd_bbox_targets(ptr(boxes), ptr(gt_boxes), ptr(gt_labels), ptr(is_pos), K,
+                                 int(num_classes), float(pos_weight), _f4(means), _f4(stds),
+                                 ptr(labels), ptr(lw), ptr(bt), ptr(bw), stream()),
+          'htd_bbox_targets')
+    return labels, lw, bt, bw
+
+
+def bbox_decode(rois, deltas, means, stds, max_shape=None, wh_ratio_clip=16 / 1000, clip=True):
+    """delta2bbox + clip for class-agnostic deltas; rois [K,4] or [K,5] -> same shape."""
+    _lib.require_cuda(rois, deltas)
+    K, rs = rois.shape
+    rois = rois.detach().float().contiguous()
+    deltas = deltas.detach()
+    if deltas.dtype not in _lib._DT:
+        deltas = deltas.float()
+    deltas = deltas.contiguous()
+    out = torch.empty((K, rs), dtype=torch.float32, device=rois.device)
+    do_clip = bool(clip and max_shape is not None)
+    mh, mw = (float(max_shape[0]), float(max_shape[1])) if do_clip else (0.0, 0.0)
+    check(lib().htd_bbox_decode(ptr(rois), rs, ptr(deltas), dt(deltas), K, _f4(means), _f4(stds),
+                                float(wh_ratio_clip), int(do_clip), mh, mw, ptr(out), rs, stream()),
+          'htd_bbox_decode')
+    return out
+
+
+class _RCNNLoss(torch.autograd.Function):
+    """BBoxHead.loss for class-agnostic regression (bbox_head.py:141-186): weighted softmax CE /
+    avg_factor, top-1 accuracy, smooth-L1 on positives / K - forward computes the (unnormalised)
+    gradients too, backward only scales them by the incoming loss gradients."""
+
+    @staticmethod
+    def forward(ctx, cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights,
+                num_classes, beta, w_cls, w_bbox):
+        _lib.require_cuda(cls_score, bbox_pred, labels)
+        K, C1 = cls_score.shape
+        dev = cls_score.device
+        cs = cls_score.detach().contiguous()
+        bp = bbox_pred.detach().to(cs.dtype).contiguous()
+        dcls = torch.empty_like(cs)
+        dbbox = torch.empty_like(bp)
+        nblk = max((K + 7) // 8, 1)
+        partial = torch.empty((nblk, 4), dtype=torch.float32, device=dev)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        check(lib().htd_rcnn_loss_fwd(ptr(cs), C1, ptr(bp), dt(cs), ptr(labels.contiguous()),
+                                      ptr(label_weights.float().contiguous()),
+                                      ptr(bbox_targets.float().contiguous()),
+                                      ptr(bbox_weights.float().contiguous()), K, int(num_classes),
+                                      float(beta), float(w_cls), float(w_bbox), ptr(dcls), ptr(dbbox),
+                                      ptr(partial), ptr(out4), stream()), 'htd_rcnn_loss_fwd')
+        ctx.save_for_backward(dcls, dbbox, out4)
+        ctx.cfg = (float(w_cls), float(w_bbox), K, cls_score.dtype, bbox_pred.dtype)
+        loss_cls, acc, loss_bbox = out4[0], out4[1:2], out4[2]
+        ctx.mark_non_differentiable(acc)
+        return loss_cls, acc, loss_bbox
+
+    @staticmethod
+    def backward(ctx, g_cls, g_acc, g_bbox):
+        dcls, dbbox, out4 = ctx.saved_tensors
+        w_cls, w_bbox, K, cdt, bdt = ctx.cfg
+        g_cls = None if g_cls is None else g_cls.detach().float().contiguous()
+        g_bbox = None if g_bbox is None else g_bbox.detach().float().contiguous()
+        check(lib().htd_rcnn_loss_bwd(ptr(dcls), dcls.numel(), ptr(dbbox), dbbox.numel(), dt(dcls),
+                                      ptr(g_cls), ptr(g_bbox), ptr(out4), w_cls, w_bbox, K, stream()),
+              'htd_rcnn_loss_bwd')
+        return dcls.to(cdt), dbbox.to(bdt), None, None, None, None, None, None, None, None
+
+
+def rcnn_loss(cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights, num_classes,
+              beta=1.0, w_cls=1.0, w_bbox=1.0):
+    return _RCNNLoss.apply(cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights,
+                           num_classes, beta, w_cls, w_bbox)

@@ -266,6 +266,40 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
                     htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Target / loss / decode glue, one kernel per job, no host sync.
+ *
+ * htd_bbox_targets: BBoxHead._get_target_single (bbox_head.py:85-118) for all sampled RoIs at
+ *   once.  boxes [K,4]; gt_boxes [K,4] / gt_labels [K] int64 valid on rows with is_pos[k] != 0;
+ *   labels[k] = gt label or num_classes (background); label_weights = pos_weight (1 if <= 0) or 1;
+ *   bbox_targets = DeltaXYWHBBoxCoder.encode (delta_xywh_bbox_coder.py:98-120) on positives, 0 else;
+ *   bbox_weights = 1 on positives.
+ * htd_bbox_decode: delta2bbox (delta_xywh_bbox_coder.py:123-204), class-agnostic [K,4] deltas;
+ *   rois rows of roi_stride 4 or 5 floats (5: batch index first, copied to out when out_stride 5);
+ *   clip != 0 clamps to [0,max_w] x [0,max_h].
+ * htd_rcnn_loss_fwd: BBoxHead.loss (bbox_head.py:141-186) for class-agnostic regression:
+ *   out4 = (w_cls * sum_k lw_k CE_k / max(#{lw > 0}, 1),  top-1 accuracy in %,
+ *           w_bbox * sum_{k positive} sum_j bw_kj smoothL1_beta(pred - target) / K,  1 / avg_factor);
+ *   dcls [K,num_cls1] / dbbox [K,4] receive the unnormalised gradients, partial is a
+ *   [ceil(K/8), 4] fp32 workspace.  htd_rcnn_loss_bwd scales them in place by the incoming
+ *   gradients g_cls / g_bbox (device scalars, NULL = 0). */
+int htd_bbox_targets(const float* boxes, const float* gt_boxes, const long long* gt_labels,
+                     const unsigned char* is_pos, int K, int num_classes, float pos_weight,
+                     const float* means4, const float* stds4, long long* labels,
+                     float* label_weights, float* bbox_targets, float* bbox_weights,
+                     htd_stream_t stream);
+int htd_bbox_decode(const float* rois, int roi_stride, const void* deltas, int delta_dtype, int K,
+                    const float* means4, const float* stds4, float wh_ratio_clip, int clip,
+                    float max_h, float max_w, float* out, int out_stride, htd_stream_t stream);
+int htd_rcnn_loss_fwd(const void* cls_score, int num_cls1, const void* bbox_pred, int dtype,
+                      const long long* labels, const float* label_weights,
+                      const float* bbox_targets, const float* bbox_weights, int K, int num_classes,
+                      float beta, float w_cls, float w_bbox, void* dcls, void* dbbox,
+                      float* partial, float* out4, htd_stream_t stream);
+int htd_rcnn_loss_bwd(void* dcls, long long ncls, void* dbbox, long long nbox, int dtype,
+                      const float* g_cls, const float* g_bbox, const float* out4, float w_cls,
+                      float w_bbox, int K, htd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
  * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and
  * (C / G) % 8 == 0; gamma / beta fp32; mean / rstd [N*G]: fp32 for HTD_BF16 tensors, fp64 for

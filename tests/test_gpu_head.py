@@ -472,3 +472,48 @@ def test_inference_1000_proposals_full_size_properties():
     assert sum(sizes) == 1000 and max(sizes) >= 200
     res = head.simple_test(x, props, metas)
     assert len(res) == 1 and len(res[0]) == 80
+
+
+def test_fused_targets_loss_decode_vs_torch_path():
+    """csrc/rcnn_glue.cu (targets, CE + accuracy + smooth-L1 with gradients, delta2bbox) against the
+    PyTorch statement of the same functions (BBoxHead with fused_glue = False) and the oracle."""
+    from htd_b200 import bbox_heads
+    from oracle import cases, restate
+    g = torch.Generator().manual_seed(3)
+    props = [p.cuda() for p in synth.make_proposals(2, 64, 320, 448, seed=5, min_scale=8, max_scale=300)]
+    gts = [{k: v.cuda() for k, v in d.items()} for d in synth.make_gt(2, [p.cpu() for p in props], num_pos=16)]
+    samp = [synth.make_sampling(p, 16, d) for p, d in zip(props, gts)]
+    head = bbox_heads.Shared2FCBBoxHead(in_channels=256, roi_feat_size=7, num_classes=80,
+                                        reg_class_agnostic=True).cuda()
+    cfg = dict(pos_weight=-1)
+    K = 128
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1e-2)):
+        cls = (2 * torch.randn(K, 81, generator=g)).cuda().to(dtype).requires_grad_(True)
+        reg = (0.5 * torch.randn(K, 4, generator=g)).cuda().to(dtype).requires_grad_(True)
+        rois = torch.cat([torch.cat([p.new_full((64, 1), i), p], 1) for i, p in enumerate(props)])
+        outs = {}
+        for fused in (True, False):
+            bbox_heads.BBoxHead.fused_glue = fused
+            try:
+                tg = head.get_targets(samp, None, None, cfg)
+                ls = head.loss(cls, reg, rois, *tg)
+                gr = torch.autograd.grad(ls['loss_cls'] * 1.7 + ls['loss_bbox'] * 0.3, [cls, reg])
+                dec = head.regress_by_class(rois, None, reg.detach() * 0.2, dict(img_shape=(320, 448, 3)))
+            finally:
+                bbox_heads.BBoxHead.fused_glue = True
+            outs[fused] = (tg, ls, gr, dec)
+        (tg_a, ls_a, gr_a, dec_a), (tg_b, ls_b, gr_b, dec_b) = outs[True], outs[False]
+        assert torch.equal(tg_a[0], tg_b[0]) and torch.equal(tg_a[1], tg_b[1]) and torch.equal(tg_a[3], tg_b[3])
+        assert cases.rel_err(tg_a[2], tg_b[2]) <= 1e-6
+        for k in ('loss_cls', 'loss_bbox', 'acc'):
+            assert cases.rel_err(ls_a[k].reshape(1).float(), ls_b[k].reshape(1).float()) <= tol, k
+        assert cases.rel_err(gr_a[0].float(), gr_b[0].float()) <= max(tol, 1e-5)
+        assert cases.rel_err(gr_a[1].float(), gr_b[1].float()) <= max(tol, 1e-5)
+        assert cases.rel_err(dec_a, dec_b) <= (1e-6 if dtype == torch.float32 else 1e-2)
+    # oracle (fp64) on the fp32 inputs
+    oh = restate.Shared2FCBBoxHead()
+    so = [restate.make_sampling(p.cpu().double(), 16, {k: v.cpu() for k, v in d.items()}) for p, d in zip(props, gts)]
+    tgo = oh.get_targets(so)
+    lo = oh.loss(cls.detach().cpu().double(), reg.detach().cpu().double(), rois.cpu().double(), *tgo)
+    # (last loop iteration was bf16: compare loosely)
+    assert abs(float(ls_a['loss_cls']) - float(lo['loss_cls'])) / float(lo['loss_cls']) <= 2e-2
