@@ -309,13 +309,25 @@ def run_gpu(args):
     h2d_bytes = sum(t.numel() * t.element_size() for t in pyr_host) + \
         sum(p.numel() * p.element_size() for p in props_host)
 
+    # one pinned staging buffer (pyramid levels + proposals back to back): ONE H2D copy per step
+    parts = list(pyr_host) + list(props_host)
+    sizes = [t.numel() for t in parts]
+    host_flat = torch.empty(sum(sizes), dtype=torch.float32).pin_memory()
+    off = 0
+    for t, n in zip(parts, sizes):
+        host_flat[off:off + n].copy_(t.reshape(-1))
+        off += n
+
     def upload():
         with torch.cuda.stream(copy_stream):
-            xs = [t.to(dev, non_blocking=True) for t in pyr_host]
-            ps = [p.to(dev, non_blocking=True) for p in props_host]
+            flat = host_flat.to(dev, non_blocking=True)
+            views, off = [], 0
+            for t, n in zip(parts, sizes):
+                views.append(flat[off:off + n].view(t.shape))
+                off += n
             evt = torch.cuda.Event()
             evt.record(copy_stream)
-        return xs, ps, evt
+        return views[:len(pyr_host)], views[len(pyr_host):], evt, flat
 
     def e2e_loop(n):
         """Per step: H2D of the step's inputs from pinned host memory (copy stream, one step
@@ -327,14 +339,13 @@ def run_gpu(args):
         seen = 0.0
         nxt = upload()
         for i in range(n):
-            xs, ps, evt = nxt
+            xs, ps, evt, flat = nxt
             if i + 1 < n:
                 nxt = upload()                      # next step's H2D overlaps this step's compute
             torch.cuda.current_stream().wait_event(evt)
-            for t in xs:
-                t.record_stream(torch.cuda.current_stream())
-                if not use_graph:
-                    t.requires_grad_(True)
+            flat.record_stream(torch.cuda.current_stream())
+            if not use_graph:
+                xs = [t.detach().requires_grad_(True) for t in xs]
             losses = step(xs, ps)
             dev_l = torch.stack([v.detach().float().reshape(()) for v in losses.values()])
             pinned[i & 1].copy_(dev_l, non_blocking=True)
