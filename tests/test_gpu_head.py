@@ -517,3 +517,30 @@ def test_fused_targets_loss_decode_vs_torch_path():
     lo = oh.loss(cls.detach().cpu().double(), reg.detach().cpu().double(), rois.cpu().double(), *tgo)
     # (last loop iteration was bf16: compare loosely)
     assert abs(float(ls_a['loss_cls']) - float(lo['loss_cls'])) / float(lo['loss_cls']) <= 2e-2
+
+
+def test_eight_images_per_gpu_full_size_step():
+    """BASELINE config 3 shape: 8 images per GPU x 512 RoIs (128 positives), 800x1333, bf16 - 32
+    PGraph groups, K = 4096.  The reference cannot run this (stage 1 hard-codes 2 images, SURVEY
+    F5); here it must run, give finite losses / gradients, and be independent of how the images
+    are batched: image 0's pyramid gradient equals the one of a 2-image batch up to the loss
+    normalisation (avg_factor counts all RoIs of the batch)."""
+    import htd_b200
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'init', 0)
+    head = head.cuda().to(torch.bfloat16)
+    head.compute_dtype = torch.bfloat16
+    B = 8
+    x = [t.cuda().requires_grad_(True) for t in synth.make_pyramid(B)]
+    props_h = synth.make_proposals(B, 512)
+    props = [p.cuda() for p in props_h]
+    gts = [{k: v.cuda() for k, v in g.items()} for g in synth.make_gt(B, props_h, num_pos=128)]
+    losses = synth.sampled_forward_train(head, x, props, gts, [(800, 1333, 3)] * B, 128)
+    sum(v for k, v in losses.items() if 'loss' in k).backward()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(v.float()).all() for v in losses.values())
+    assert all(torch.isfinite(t.grad).all() for t in x)
+    assert all(torch.isfinite(p.grad.float()).all() for p in head.parameters())
+    plan = head.bbox_head[1].last_plan
+    assert plan.K == 4096 and len(plan.groups) == 32
+    assert all(float(t.grad[i].abs().max()) > 0 for t in x[:4] for i in range(B))
