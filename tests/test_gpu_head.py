@@ -544,3 +544,22 @@ def test_eight_images_per_gpu_full_size_step():
     plan = head.bbox_head[1].last_plan
     assert plan.K == 4096 and len(plan.groups) == 32
     assert all(float(t.grad[i].abs().max()) > 0 for t in x[:4] for i in range(B))
+
+
+def test_training_step_without_positives():
+    """Early training can sample zero positives: the BA extractor, the conv tower, GN, the fused
+    loss and the backward gathers must cope with empty positive sets (loss_bbox == 0, finite grads)."""
+    import htd_b200
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'n005', 1)
+    head = head.cuda()
+    H, W = 256, 320
+    x = [t.cuda().requires_grad_(True) for t in synth.make_pyramid(2, H, W)]
+    props_h = synth.make_proposals(2, 32, H, W, min_scale=8, max_scale=300)
+    props = [p.cuda() for p in props_h]
+    gts = [{k: v.cuda() for k, v in g.items()} for g in synth.make_gt(2, props_h, num_pos=4)]
+    losses = synth.sampled_forward_train(head, x, props, gts, [(H, W, 3)] * 2, 0)
+    assert float(losses['s0.loss_bbox']) == 0.0 and float(losses['s1.loss_bbox']) == 0.0
+    sum(v for k, v in losses.items() if 'loss' in k).backward()
+    assert all(torch.isfinite(t.grad).all() for t in x)
+    assert all(torch.isfinite(p.grad).all() for p in head.parameters() if p.grad is not None)
