@@ -1,0 +1,89 @@
+"""Same-box GPU comparator: the reference's extraction pattern with
+torchvision's CUDA roi_align (the generic thread-per-output kernel with atomicAdd backward that
+mmcv's is derived from, merely compiled for sm_100) against this package's kernels on identical
+inputs - values must agree and the own kernels must be faster.  Timings are printed (-s) and kept
+in profiles/ by the round notes."""
+import json
+
+import pytest
+import torch
+
+from htd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _time(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def test_extractors_vs_torchvision_cuda_roi_align():
+    from torchvision.ops import roi_align
+    from htd_b200 import ops
+    from oracle import cases, restate
+    imgs, nroi, npos = 2, 512, 128
+    x = [t.cuda().requires_grad_(True) for t in synth.make_pyramid(imgs)[:4]]
+    props = synth.make_proposals(imgs, nroi)
+    rois = cases._rois(props).cuda()
+    pos_rois = cases._rois([p[:npos] for p in props]).cuda()
+    scales = [0.25, 0.125, 0.0625, 0.03125]
+    lv = restate.map_roi_levels(rois, 4)
+    g1 = torch.randn(rois.shape[0], 256, 7, 7, device='cuda')
+    g2 = torch.randn(4, pos_rois.shape[0], 256, 7, 7, device='cuda')
+
+    def tv_single():            # single_level_roi_extractor.py:81-98
+        out = x[0].new_zeros(rois.shape[0], 256, 7, 7)
+        for i in range(4):
+            inds = (lv == i).nonzero(as_tuple=False).squeeze(1)
+            if inds.numel():
+                out[inds] = roi_align(x[i], rois[inds], (7, 7), scales[i], 0, True)
+        return out
+
+    def tv_ba():                # the 4 all-RoI calls of adaptative_roi_extractor.py:71-74
+        return torch.stack([roi_align(x[i], pos_rois, (7, 7), scales[i], 0, True) for i in range(4)])
+
+    xcl = ops.make_pyramid([t for t in x], torch.float32)
+    lvl = ops.level_assign(rois, 4)
+
+    def own_single():
+        return ops.roi_align_levels(xcl, rois, scales, roi_level=lvl)
+
+    def own_ba():
+        return ops.roi_align_levels(xcl, pos_rois, scales)
+
+    res = {}
+    for name, ref_fn, own_fn, g in (('single', tv_single, own_single, g1), ('ba', tv_ba, own_ba, g2)):
+        a, b = ref_fn(), own_fn()
+        assert cases.rel_err(b, a) <= 1e-4, name     # fp32 torchvision is itself 1e-5..3e-5 from fp64
+        ga = torch.autograd.grad((a * g).sum(), x, allow_unused=True)
+
+        def ref_fb():
+            torch.autograd.grad((ref_fn() * g).sum(), x, allow_unused=True)
+
+        def own_fb():
+            xp = ops.make_pyramid([t for t in x], torch.float32)
+            out = ops.roi_align_levels(xp, rois if name == 'single' else pos_rois, scales,
+                                       roi_level=lvl if name == 'single' else None)
+            torch.autograd.grad((out * g).sum(), x, allow_unused=True)
+        xp = ops.make_pyramid([t for t in x], torch.float32)
+        out = ops.roi_align_levels(xp, rois if name == 'single' else pos_rois, scales,
+                                   roi_level=lvl if name == 'single' else None)
+        gb = torch.autograd.grad((out * g).sum(), x, allow_unused=True)
+        for u, v in zip(ga, gb):
+            if u is not None:
+                assert cases.rel_err(v, u) <= 2e-4, name
+        res[name] = dict(torchvision_fwd_ms=_time(ref_fn), own_fwd_ms=_time(own_fn),
+                         torchvision_fwdbwd_ms=_time(ref_fb), own_fwdbwd_ms=_time(own_fb))
+    print('COMPARATOR ' + json.dumps(res))
+    for name, r in res.items():
+        assert r['own_fwd_ms'] < r['torchvision_fwd_ms'], (name, r)
+        assert r['own_fwdbwd_ms'] < r['torchvision_fwdbwd_ms'], (name, r)
