@@ -87,3 +87,69 @@ def test_extractors_vs_torchvision_cuda_roi_align():
     for name, r in res.items():
         assert r['own_fwd_ms'] < r['torchvision_fwd_ms'], (name, r)
         assert r['own_fwdbwd_ms'] < r['torchvision_fwdbwd_ms'], (name, r)
+
+
+def test_full_step_vs_pytorch_eager_reference_on_gpu():
+    """The whole training step of the reference's algorithm as PyTorch-eager on the SAME GPU (the
+    oracle restatement moved to CUDA with torchvision's CUDA roi_align in place of the C RoIAlign -
+    what running the reference on this box amounts to), fp32, against this package's step (bf16,
+    eager and CUDA graph) on the bench workload.  Losses must agree; the package must be faster."""
+    import htd_b200
+    from htd_b200.graphed import GraphedTrainStep
+    from torchvision.ops import roi_align
+    from oracle import restate
+    imgs, nroi, npos = 2, 512, 128
+    shapes = [(800, 1333, 3)] * imgs
+    pyr = synth.make_pyramid(imgs)
+    props_h = synth.make_proposals(imgs, nroi)
+    gts_h = synth.make_gt(imgs, props_h, num_pos=npos)
+    props = [p.cuda() for p in props_h]
+    gts = [{k: v.cuda() for k, v in g.items()} for g in gts_h]
+
+    ref = restate.HTDRoIHead()
+    synth.fill_params_(ref, 'init', 0)
+    ref = ref.cuda()
+    orig = restate.RoIAlign.forward
+    restate.RoIAlign.forward = lambda self, x, rois: roi_align(
+        x, rois.to(x.dtype), self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+    try:
+        xr = [t.cuda().requires_grad_(True) for t in pyr]
+
+        def ref_step():
+            for p in ref.parameters():
+                p.grad = None
+            for t in xr:
+                t.grad = None
+            losses = ref.forward_train_sampled(xr, props, gts, shapes, npos)
+            sum(v for k, v in losses.items() if 'loss' in k).backward()
+            return losses
+        ref_losses = {k: float(v) for k, v in ref_step().items()}
+        t_ref = _time(ref_step, 5)
+    finally:
+        restate.RoIAlign.forward = orig
+
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'init', 0)
+    head = head.cuda().to(torch.bfloat16)
+    head.compute_dtype = torch.bfloat16
+    xg = [t.cuda().requires_grad_(True) for t in pyr]
+
+    def own_step():
+        for p in head.parameters():
+            p.grad = None
+        for t in xg:
+            t.grad = None
+        losses = synth.sampled_forward_train(head, xg, props, gts, shapes, npos)
+        sum(v for k, v in losses.items() if 'loss' in k).backward()
+        return losses
+    own_losses = {k: float(v) for k, v in own_step().items()}
+    t_eager = _time(own_step, 10)
+    gstep = GraphedTrainStep(head, xg, props, gts, shapes, npos)
+    t_graph = _time(lambda: gstep(), 20)
+    for k, v in ref_losses.items():
+        if 'loss' in k:
+            assert abs(own_losses[k] - v) <= 2e-2 * max(abs(v), 1e-3), (k, own_losses[k], v)
+    res = dict(rois=imgs * nroi, pytorch_eager_torchvision_fp32_ms=t_ref, own_bf16_eager_ms=t_eager,
+               own_bf16_graph_ms=t_graph)
+    print('COMPARATOR_STEP ' + json.dumps(res))
+    assert t_graph < t_eager < t_ref
