@@ -73,10 +73,14 @@ SIGNATURES = {
                         ctypes.POINTER(c_float), c_float, c_int, c_float, c_float, c_void_p, c_int,
                         c_void_p],
     'htd_rcnn_loss_fwd': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                          c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
-                          c_void_p, c_void_p],
+                          c_int, c_int, c_float, c_float, c_float, c_int, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p],
     'htd_rcnn_loss_bwd': [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
-                          c_float, c_float, c_int, c_void_p],
+                          c_float, c_float, c_int, c_int, c_void_p],
+    'htd_assign_sample': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                          c_void_p, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_float,
+                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_gn_relu_fwd': [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
                         c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_gn_relu_bwd': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,

@@ -185,7 +185,7 @@ class BBoxHead(nn.Module):
                                 self.bbox_coder.stds)
 
     def loss(self, cls_score, bbox_pred, rois, labels, label_weights, bbox_targets, bbox_weights,
-             reduction_override=None):
+             reduction_override=None, pad_rows=False):
         """bbox_head.py:141-186 in static-shape form: the reference selects the positive rows
         with boolean masks (`.any()`, `.item()` host syncs, data-dependent shapes); here the same
         sums are taken over ALL rows with the positive mask as a 0/1 factor and `avg_factor` kept
@@ -196,8 +196,10 @@ class BBoxHead(nn.Module):
             loss_cls, acc, loss_bbox = ops.rcnn_loss(
                 cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights,
                 self.num_classes, self.loss_bbox.beta, self.loss_cls.loss_weight,
-                self.loss_bbox.loss_weight)
+                self.loss_bbox.loss_weight, pad_rows=pad_rows)
             return dict(loss_cls=loss_cls, acc=acc, loss_bbox=loss_bbox)
+        if pad_rows:
+            raise NotImplementedError('pad rows (static-shape sampling) need the fused loss kernels')
         if cls_score is not None:
             cls_score = cls_score.float()                      # force_fp32 (bbox_head.py:141)
             avg_factor = torch.sum(label_weights > 0).float().clamp(min=1.)
@@ -413,10 +415,11 @@ class HTDBBoxHead(BBoxHead):
         return (rois[:, :1] == b[None, :]).to(dtype)
 
     def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
-                global_feat=None, num_imgs=None, max_rois_per_img=None):
+                global_feat=None, num_imgs=None, max_rois_per_img=None, row_valid=None):
         """Reference signature (htd_bbox_head.py:157).  ``num_imgs`` (optional) avoids the host
         sync of ``int(max(rois[:,0])) + 1`` (:159); ``global_feat`` gives it otherwise.
-        ``max_rois_per_img`` (optional) bounds the PGraph group size (default: all RoIs)."""
+        ``max_rois_per_img`` (optional) bounds the PGraph group size (default: all RoIs);
+        ``row_valid`` ([K] bool, optional) keeps pad rows of the static sampler out of the graph."""
         if num_imgs is None:
             num_imgs = global_feat.size(0) if global_feat is not None \
                 else int(torch.max(rois[..., 0])) + 1
@@ -444,6 +447,8 @@ class HTDBBoxHead(BBoxHead):
         sam = torch.mm(fc_cls_0(x_c).softmax(-1), prototype)
         with torch.no_grad():
             levels = ops.level_assign(rois, len(feat), self.finest_scale)
+            if row_valid is not None:
+                levels = torch.where(row_valid, levels, torch.full_like(levels, -1))
             plan = pgraph.GraphPlan(rois, levels, num_imgs, len(feat), x_c.dtype,
                                     max_group=max_rois_per_img, d=d, ds=prototype.size(1))
         self.last_plan = plan
@@ -490,6 +495,10 @@ class GlobalContextHead(nn.Module):
             x = conv(x)
         x = self.pool(x)
         return self.fc(x.reshape(x.size(0), -1)), x
+
+    def loss_multihot(self, pred, multihot):
+        """``loss`` with the multi-hot target given ([B,num_classes] bool; static shapes)."""
+        return self.loss_weight * self.criterion(pred.float(), multihot.float())
 
     def loss(self, pred, labels):
         pred = pred.float()

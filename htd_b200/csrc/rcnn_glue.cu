@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) bbox_targets_kernel(
     float* __restrict__ bbox_targets, float* __restrict__ bbox_weights) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
-    const bool pos = is_pos[k] != 0;
+    const bool pos = is_pos[k] == 1, pad = is_pos[k] == 2;
     float t[4] = {0.f, 0.f, 0.f, 0.f};
     if (pos) {
         const float4 p = *reinterpret_cast<const float4*>(boxes + (size_t)k * 4);
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) bbox_targets_kernel(
         t[3] = (logf(gh / ph) - m3) / s3;
     }
     labels[k] = pos ? gt_labels[k] : (long long)num_classes;
-    label_weights[k] = pos ? (pos_weight <= 0.f ? 1.f : pos_weight) : 1.f;
+    label_weights[k] = pos ? (pos_weight <= 0.f ? 1.f : pos_weight) : (pad ? 0.f : 1.f);
     const float w = pos ? 1.f : 0.f;
     *reinterpret_cast<float4*>(bbox_targets + (size_t)k * 4) = make_float4(t[0], t[1], t[2], t[3]);
     *reinterpret_cast<float4*>(bbox_weights + (size_t)k * 4) = make_float4(w, w, w, w);
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) rcnn_loss_rows_kernel(
     const T* __restrict__ cls_score, int num_cls1, const T* __restrict__ bbox_pred,
     const long long* __restrict__ labels, const float* __restrict__ label_weights,
     const float* __restrict__ bbox_targets, const float* __restrict__ bbox_weights, int K,
-    int num_classes, float beta, T* __restrict__ dcls, T* __restrict__ dbbox,
+    int num_classes, float beta, int pad_rows, T* __restrict__ dcls, T* __restrict__ dbbox,
     float* __restrict__ partial) {
     __shared__ float s_part[kLossWarps][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) rcnn_loss_rows_kernel(
             const float zl = (lab >= 0 && lab < num_cls1) ? ldv<T>(z + lab) : 0.f;
             ce = (lse - zl) * lw;
             cnt = lw > 0.f ? 1.f : 0.f;
-            hit = (amax == (int)lab) ? 1.f : 0.f;
+            hit = (amax == (int)lab && !(pad_rows && !(lw > 0.f))) ? 1.f : 0.f;
         }
         const bool pos = lab >= 0 && lab < num_classes;
         if (lane < 4) {
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(kLossWarps * 32) rcnn_loss_rows_kernel(
 // out[0] = loss_cls, out[1] = acc (%), out[2] = loss_bbox, out[3] = 1 / avg_factor
 __global__ void __launch_bounds__(256) rcnn_loss_final_kernel(const float* __restrict__ partial,
                                                               int nblk, int K, float w_cls,
-                                                              float w_bbox, float* __restrict__ out) {
+                                                              float w_bbox, int pad_rows,
+                                                              float* __restrict__ out) {
     __shared__ float s_red[4][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float a[4] = {0.f, 0.f, 0.f, 0.f};
@@ -186,8 +187,9 @@ __global__ void __launch_bounds__(256) rcnn_loss_final_kernel(const float* __res
         }
         const float avg = fmaxf(t[1], 1.f);
         out[0] = w_cls * t[0] / avg;
-        out[1] = K > 0 ? 100.f * t[2] / (float)K : 0.f;
-        out[2] = K > 0 ? w_bbox * t[3] / (float)K : 0.f;
+        const float rows = pad_rows ? avg : (float)K;
+        out[1] = K > 0 ? 100.f * t[2] / rows : 0.f;
+        out[2] = K > 0 ? w_bbox * t[3] / rows : 0.f;
         out[3] = 1.f / avg;
     }
 }
@@ -199,9 +201,10 @@ __global__ void __launch_bounds__(256) rcnn_loss_bwd_kernel(T* __restrict__ dcls
                                                             const float* __restrict__ g_cls,
                                                             const float* __restrict__ g_bbox,
                                                             const float* __restrict__ out, float w_cls,
-                                                            float w_bbox, int K) {
+                                                            float w_bbox, int K, int pad_rows) {
     const float sc = (g_cls ? *g_cls : 0.f) * w_cls * out[3];
-    const float sb = (g_bbox ? *g_bbox : 0.f) * w_bbox / (float)(K > 0 ? K : 1);
+    const float sb = (g_bbox ? *g_bbox : 0.f) * w_bbox *
+                     (pad_rows ? out[3] : 1.f / (float)(K > 0 ? K : 1));
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncls + nbox;
          i += (long long)gridDim.x * blockDim.x) {
         if (i < ncls) stv<T>(dcls + i, ldv<T>(dcls + i) * sc);
@@ -260,7 +263,7 @@ int htd_bbox_decode(const float* rois, int roi_stride, const void* deltas, int d
 int htd_rcnn_loss_fwd(const void* cls_score, int num_cls1, const void* bbox_pred, int dtype,
                       const long long* labels, const float* label_weights,
                       const float* bbox_targets, const float* bbox_weights, int K, int num_classes,
-                      float beta, float w_cls, float w_bbox, void* dcls, void* dbbox,
+                      float beta, float w_cls, float w_bbox, int pad_rows, void* dcls, void* dbbox,
                       float* partial, float* out4, htd_stream_t stream) {
     HTD_CHECK_ARG(K >= 0 && num_cls1 >= 2 && num_classes >= 1 && beta > 0.f,
                   "htd_rcnn_loss_fwd: bad arguments");
@@ -274,24 +277,24 @@ int htd_rcnn_loss_fwd(const void* cls_score, int num_cls1, const void* bbox_pred
         if (dtype == HTD_F32)
             rcnn_loss_rows_kernel<float><<<nblk, kLossWarps * 32, 0, st>>>(
                 static_cast<const float*>(cls_score), num_cls1, static_cast<const float*>(bbox_pred),
-                labels, label_weights, bbox_targets, bbox_weights, K, num_classes, beta,
+                labels, label_weights, bbox_targets, bbox_weights, K, num_classes, beta, pad_rows,
                 static_cast<float*>(dcls), static_cast<float*>(dbbox), partial);
         else
             rcnn_loss_rows_kernel<__nv_bfloat16><<<nblk, kLossWarps * 32, 0, st>>>(
                 static_cast<const __nv_bfloat16*>(cls_score), num_cls1,
                 static_cast<const __nv_bfloat16*>(bbox_pred), labels, label_weights, bbox_targets,
-                bbox_weights, K, num_classes, beta, static_cast<__nv_bfloat16*>(dcls),
+                bbox_weights, K, num_classes, beta, pad_rows, static_cast<__nv_bfloat16*>(dcls),
                 static_cast<__nv_bfloat16*>(dbbox), partial);
         HTD_CHECK_LAUNCH("htd_rcnn_loss_fwd(rows)");
     }
-    rcnn_loss_final_kernel<<<1, 256, 0, st>>>(partial, nblk, K, w_cls, w_bbox, out4);
+    rcnn_loss_final_kernel<<<1, 256, 0, st>>>(partial, nblk, K, w_cls, w_bbox, pad_rows, out4);
     HTD_CHECK_LAUNCH("htd_rcnn_loss_fwd(final)");
     return HTD_OK;
 }
 
 int htd_rcnn_loss_bwd(void* dcls, long long ncls, void* dbbox, long long nbox, int dtype,
                       const float* g_cls, const float* g_bbox, const float* out4, float w_cls,
-                      float w_bbox, int K, htd_stream_t stream) {
+                      float w_bbox, int K, int pad_rows, htd_stream_t stream) {
     HTD_CHECK_ARG(dtype == HTD_F32 || dtype == HTD_BF16, "htd_rcnn_loss_bwd: bad dtype");
     HTD_CHECK_ARG(ncls >= 0 && nbox >= 0 && out4, "htd_rcnn_loss_bwd: bad arguments");
     if (ncls + nbox == 0) return HTD_OK;
@@ -302,11 +305,11 @@ int htd_rcnn_loss_bwd(void* dcls, long long ncls, void* dbbox, long long nbox, i
     if (dtype == HTD_F32)
         rcnn_loss_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(dcls), ncls,
                                                             static_cast<float*>(dbbox), nbox, g_cls,
-                                                            g_bbox, out4, w_cls, w_bbox, K);
+                                                            g_bbox, out4, w_cls, w_bbox, K, pad_rows);
     else
         rcnn_loss_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
             static_cast<__nv_bfloat16*>(dcls), ncls, static_cast<__nv_bfloat16*>(dbbox), nbox, g_cls,
-            g_bbox, out4, w_cls, w_bbox, K);
+            g_bbox, out4, w_cls, w_bbox, K, pad_rows);
     HTD_CHECK_LAUNCH("htd_rcnn_loss_bwd");
     return HTD_OK;
 }

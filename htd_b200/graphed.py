@@ -10,22 +10,20 @@ are captured ONCE into a CUDA graph and replayed: one host call per step.
     losses = step(x_new, proposals_new, gts_new)      # copies into static buffers, replays
     head.parameters() .grad / step.x[i].grad          # static gradient tensors, rewritten per replay
 
-Valid for the sampled-RoI protocol with fixed counts per image (``synth.sampled_forward_train``;
-bench.py).  A different (K, P) needs a new capture.
+``GraphedTrainStep``: the sampled-RoI protocol with fixed counts per image
+(``synth.sampled_forward_train``; bench.py); a different (K, P) needs a new capture.
+``GraphedStaticTrainStep``: the complete step including assignment and sampling, static shapes.
 """
 import torch
 
 from . import synth
 
 
-class GraphedTrainStep:
+class _GraphedStep:
+    """Warm-up on a side stream, capture ``_zero`` + ``_run`` once, replay per step."""
 
-    def __init__(self, head, x, proposals, gts, img_shapes, num_pos, warmup=3, flat_grads=False):
-        """``flat_grads``: parameter gradients live in ONE flat buffer (``self.flat_grad``; every
-        ``p.grad`` is a view of it) that the captured step zeroes and accumulates into - the
-        data-parallel exchange is then a single all-reduce of that buffer, no packing copies."""
-        self.head, self.img_shapes, self.num_pos = head, img_shapes, num_pos
-        dev = x[0].device
+    def _init_grads(self, head, dev, flat_grads):
+        self.head = head
         self.flat_grad = None
         if flat_grads:
             params = list(head.parameters())
@@ -37,11 +35,10 @@ class GraphedTrainStep:
             for p in params:
                 self._views.append((p, self.flat_grad[off:off + p.numel()].view_as(p)))
                 off += p.numel()
-        self.x = [t.detach().clone().requires_grad_(True) for t in x]
-        self.proposals = [p.detach().clone() for p in proposals]
-        self.gts = [{k: v.detach().clone().to(dev) for k, v in g.items()} for g in gts]
         self.losses = None
         self.total = None
+
+    def _capture(self, dev, warmup):
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                 # warm-up off the capture stream
@@ -69,12 +66,29 @@ class GraphedTrainStep:
         for t in self.x:
             t.grad = None
 
-    def _run(self):
-        losses = synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
-                                             self.img_shapes, self.num_pos)
+    def _finish(self, losses):
         total = sum(v for k, v in losses.items() if 'loss' in k)
         total.backward()
         self.losses, self.total = losses, total
+
+
+class GraphedTrainStep(_GraphedStep):
+
+    def __init__(self, head, x, proposals, gts, img_shapes, num_pos, warmup=3, flat_grads=False):
+        """``flat_grads``: parameter gradients live in ONE flat buffer (``self.flat_grad``; every
+        ``p.grad`` is a view of it) that the captured step zeroes and accumulates into - the
+        data-parallel exchange is then a single all-reduce of that buffer, no packing copies."""
+        self.img_shapes, self.num_pos = img_shapes, num_pos
+        dev = x[0].device
+        self._init_grads(head, dev, flat_grads)
+        self.x = [t.detach().clone().requires_grad_(True) for t in x]
+        self.proposals = [p.detach().clone() for p in proposals]
+        self.gts = [{k: v.detach().clone().to(dev) for k, v in g.items()} for g in gts]
+        self._capture(dev, warmup)
+
+    def _run(self):
+        self._finish(synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
+                                                 self.img_shapes, self.num_pos))
 
     def load(self, x=None, proposals=None, gts=None, non_blocking=True):
         """Copy new inputs (device or pinned-host tensors) into the static buffers."""
@@ -92,5 +106,56 @@ class GraphedTrainStep:
 
     def __call__(self, x=None, proposals=None, gts=None):
         self.load(x, proposals, gts)
+        self.graph.replay()
+        return self.losses
+
+
+class GraphedStaticTrainStep(_GraphedStep):
+    """The REAL training step - ``HTDRoIHead.forward_train_static``: assign + sample on the
+    device (csrc/assign_sample.cu), both stages, losses, backward - as one CUDA graph.
+
+        step = GraphedStaticTrainStep(head, x, img_metas, proposals, gt_bboxes, gt_labels, num_gt)
+        losses = step(x=..., proposals=..., gt_bboxes=..., gt_labels=..., num_gt=...)
+
+    ``proposals`` [B,N,4], ``gt_bboxes`` [B,G,4], ``gt_labels`` [B,G], ``num_gt`` [B] int32 are
+    static buffers (``load`` copies new values in; G is the per-image gt capacity).  ``keys``:
+    two static tensors of uniform random numbers, or None to draw them inside the graph
+    (torch's CUDA generator is graph-aware: every replay gets fresh numbers)."""
+
+    def __init__(self, head, x, img_metas, proposals, gt_bboxes, gt_labels, num_gt, keys=None,
+                 warmup=3, flat_grads=False):
+        dev = x[0].device
+        self._init_grads(head, dev, flat_grads)
+        self.img_metas = img_metas
+        self.x = [t.detach().clone().requires_grad_(True) for t in x]
+        self.proposals = proposals.detach().clone()
+        self.gt_bboxes = gt_bboxes.detach().clone()
+        self.gt_labels = gt_labels.detach().clone()
+        self.num_gt = num_gt.detach().to(torch.int32).clone()
+        self.keys = None if keys is None else [k.detach().clone() for k in keys]
+        self._capture(dev, warmup)
+
+    def _run(self):
+        self._finish(self.head.forward_train_static(self.x, self.img_metas, self.proposals,
+                                                    self.gt_bboxes, self.gt_labels, self.num_gt,
+                                                    keys=self.keys))
+
+    def load(self, x=None, proposals=None, gt_bboxes=None, gt_labels=None, num_gt=None, keys=None,
+             non_blocking=True):
+        with torch.no_grad():
+            if x is not None:
+                for d, s in zip(self.x, x):
+                    d.copy_(s, non_blocking=non_blocking)
+            for d, s in ((self.proposals, proposals), (self.gt_bboxes, gt_bboxes),
+                         (self.gt_labels, gt_labels), (self.num_gt, num_gt)):
+                if s is not None:
+                    d.copy_(s, non_blocking=non_blocking)
+            if keys is not None:
+                assert self.keys is not None, 'captured with in-graph random keys'
+                for d, s in zip(self.keys, keys):
+                    d.copy_(s, non_blocking=non_blocking)
+
+    def __call__(self, **inputs):
+        self.load(**inputs)
         self.graph.replay()
         return self.losses

@@ -570,7 +570,7 @@ class _RCNNLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights,
-                num_classes, beta, w_cls, w_bbox):
+                num_classes, beta, w_cls, w_bbox, pad_rows=False):
         _lib.require_cuda(cls_score, bbox_pred, labels)
         K, C1 = cls_score.shape
         dev = cls_score.device
@@ -585,10 +585,12 @@ class _RCNNLoss(torch.autograd.Function):
                                       ptr(label_weights.float().contiguous()),
                                       ptr(bbox_targets.float().contiguous()),
                                       ptr(bbox_weights.float().contiguous()), K, int(num_classes),
-                                      float(beta), float(w_cls), float(w_bbox), ptr(dcls), ptr(dbbox),
-                                      ptr(partial), ptr(out4), stream()), 'htd_rcnn_loss_fwd')
+                                      float(beta), float(w_cls), float(w_bbox), int(bool(pad_rows)),
+                                      ptr(dcls), ptr(dbbox), ptr(partial), ptr(out4), stream()),
+              'htd_rcnn_loss_fwd')
         ctx.save_for_backward(dcls, dbbox, out4)
-        ctx.cfg = (float(w_cls), float(w_bbox), K, cls_score.dtype, bbox_pred.dtype)
+        ctx.cfg = (float(w_cls), float(w_bbox), K, cls_score.dtype, bbox_pred.dtype,
+                   int(bool(pad_rows)))
         loss_cls, acc, loss_bbox = out4[0], out4[1:2], out4[2]
         ctx.mark_non_differentiable(acc)
         return loss_cls, acc, loss_bbox
@@ -596,16 +598,75 @@ class _RCNNLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_cls, g_acc, g_bbox):
         dcls, dbbox, out4 = ctx.saved_tensors
-        w_cls, w_bbox, K, cdt, bdt = ctx.cfg
+        w_cls, w_bbox, K, cdt, bdt, pad_rows = ctx.cfg
         g_cls = None if g_cls is None else g_cls.detach().float().contiguous()
         g_bbox = None if g_bbox is None else g_bbox.detach().float().contiguous()
         check(lib().htd_rcnn_loss_bwd(ptr(dcls), dcls.numel(), ptr(dbbox), dbbox.numel(), dt(dcls),
-                                      ptr(g_cls), ptr(g_bbox), ptr(out4), w_cls, w_bbox, K, stream()),
-              'htd_rcnn_loss_bwd')
-        return dcls.to(cdt), dbbox.to(bdt), None, None, None, None, None, None, None, None
+                                      ptr(g_cls), ptr(g_bbox), ptr(out4), w_cls, w_bbox, K, pad_rows,
+                                      stream()), 'htd_rcnn_loss_bwd')
+        return dcls.to(cdt), dbbox.to(bdt), None, None, None, None, None, None, None, None, None
 
 
 def rcnn_loss(cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights, num_classes,
-              beta=1.0, w_cls=1.0, w_bbox=1.0):
+              beta=1.0, w_cls=1.0, w_bbox=1.0, pad_rows=False):
+    """``pad_rows``: rows with label weight 0 are pad rows of ``assign_sample`` (left out of the
+    accuracy; accuracy / loss_bbox are averaged over the real rows)."""
     return _RCNNLoss.apply(cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights,
-                           num_classes, beta, w_cls, w_bbox)
+                           num_classes, beta, w_cls, w_bbox, pad_rows)
+
+
+class StaticSample:
+    """Result of ``assign_sample``: ``num`` rows per image (positives, negatives, pad rows), all
+    device tensors of static shape.  ``rois`` [B*num,5]; ``kind`` [B*num] uint8 1/0/2 =
+    positive/negative/pad; ``gt_boxes`` [B*num,4] / ``gt_labels`` [B*num] / ``gt_index`` [B*num] of
+    the positives' matched gt; ``is_gt`` [B*num] row is an appended gt box; ``cand`` [B*num] index
+    into the reference's cat([gt_bboxes, bboxes]); ``counts`` [B,4] int32 = sampled positives,
+    sampled negatives, positive candidates, negative candidates."""
+    __slots__ = ('rois', 'kind', 'gt_boxes', 'gt_labels', 'gt_index', 'is_gt', 'cand', 'counts',
+                 'gt_inds', 'max_overlaps', 'num', 'num_pos', 'num_imgs')
+
+
+def assign_sample(props, gt_boxes, gt_labels, num_gt, keys, valid=None, pos_iou_thr=0.5,
+                  neg_iou_thr=0.5, min_pos_iou=0.5, match_low_quality=False,
+                  add_gt_as_proposals=True, num=512, pos_fraction=0.25, neg_pos_ub=-1,
+                  want_assignment=False):
+    """MaxIoUAssigner + RandomSampler of one stage for all images in one launch (csrc/
+    assign_sample.cu).  props [B,N,4], gt_boxes [B,G,4], gt_labels [B,G], num_gt [B] (device
+    int32), keys [B,G+N] uniform random numbers, valid [B,N] bool/uint8 or None."""
+    _lib.require_cuda(props, gt_boxes, gt_labels, num_gt, keys)
+    B, N = props.shape[:2]
+    G = gt_boxes.shape[1]
+    dev = props.device
+    assert gt_boxes.shape[0] == B and gt_labels.shape == (B, G) and keys.shape == (B, G + N), \
+        (props.shape, gt_boxes.shape, gt_labels.shape, keys.shape)
+    props = props.detach().float().contiguous()
+    gt_boxes = gt_boxes.detach().float().contiguous()
+    gt_labels = gt_labels.detach().long().contiguous()
+    num_gt = num_gt.detach().to(torch.int32).contiguous()
+    keys = keys.detach().float().contiguous()
+    if valid is not None:
+        assert valid.shape == (B, N)
+        valid = valid.detach().to(torch.uint8).contiguous()
+    K = B * num
+    s = StaticSample()
+    s.num, s.num_pos, s.num_imgs = int(num), int(num * pos_fraction), B
+    s.rois = torch.empty((K, 5), dtype=torch.float32, device=dev)
+    s.kind = torch.empty(K, dtype=torch.uint8, device=dev)
+    s.gt_boxes = torch.empty((K, 4), dtype=torch.float32, device=dev)
+    s.gt_labels = torch.empty(K, dtype=torch.long, device=dev)
+    s.is_gt = torch.empty(K, dtype=torch.uint8, device=dev)
+    s.cand = torch.empty(K, dtype=torch.int32, device=dev)
+    s.gt_index = torch.empty(K, dtype=torch.int32, device=dev)
+    s.counts = torch.empty((B, 4), dtype=torch.int32, device=dev)
+    s.gt_inds = torch.empty((B, G + N), dtype=torch.int32, device=dev) if want_assignment else None
+    s.max_overlaps = torch.empty((B, G + N), dtype=torch.float32, device=dev) \
+        if want_assignment else None
+    check(lib().htd_assign_sample(ptr(props), ptr(valid), B, N, ptr(gt_boxes), ptr(gt_labels),
+                                  ptr(num_gt), G, ptr(keys), float(pos_iou_thr), float(neg_iou_thr),
+                                  float(min_pos_iou), int(bool(match_low_quality)),
+                                  int(bool(add_gt_as_proposals)), int(num), s.num_pos,
+                                  float(neg_pos_ub), ptr(s.rois), ptr(s.kind), ptr(s.gt_boxes),
+                                  ptr(s.gt_labels), ptr(s.is_gt), ptr(s.cand), ptr(s.gt_index),
+                                  ptr(s.counts), ptr(s.gt_inds), ptr(s.max_overlaps), stream()),
+          'htd_assign_sample')
+    return s

@@ -18,6 +18,14 @@ from .core import as_cfg, bbox2result, bbox2roi
 from .registry import HEADS, build_assigner, build_head, build_roi_extractor, build_sampler
 
 
+class _StaticRows:
+    """Sampling-result view of one image of a static sample: the regression slots and the rest."""
+    __slots__ = ('pos_bboxes', 'neg_bboxes')
+
+    def __init__(self, pos_bboxes, neg_bboxes):
+        self.pos_bboxes, self.neg_bboxes = pos_bboxes, neg_bboxes
+
+
 @HEADS.register_module()
 class HTDRoIHead(nn.Module):
 
@@ -87,8 +95,9 @@ class HTDRoIHead(nn.Module):
         return roi_feats + g[rois[:, 0].long()][:, :, None, None].to(roi_feats.dtype)
 
     def _bbox_forward(self, stage, x, rois, global_feat=None, sampling_results=None,
-                      img_metas=None, x_cl=None):
-        """htd_roi_head.py:143-201."""
+                      img_metas=None, x_cl=None, row_valid=None):
+        """htd_roi_head.py:143-201.  ``row_valid`` ([K] bool, optional): False marks the pad rows of
+        the static-shape sampler; they are kept out of the PGraph groups."""
         ext, enh = self.bbox_roi_extractor[0], self.bbox_roi_extractor[1]
         if x_cl is None:
             x_cl = self._pyramid(x)
@@ -113,7 +122,8 @@ class HTDRoIHead(nn.Module):
             pos_feats = torch.cat([bbox_feats[o:o + npos] for o, npos, _ in spans], 0)
             cls_score, bbox_pred = head(bbox_feats, pos_feats, x_cl, rois, fc0, enhanced,
                                         pos_rois, g, num_imgs=nimg or len(sampling_results),
-                                        max_rois_per_img=max(p_ + n_ for _, p_, n_ in spans))
+                                        max_rois_per_img=max(p_ + n_ for _, p_, n_ in spans),
+                                        row_valid=row_valid)
             parts, o2 = [], 0
             for _, npos, nneg in spans:
                 parts += [bbox_pred[o2:o2 + npos], bbox_pred.new_zeros(nneg, bbox_pred.size(1))]
@@ -184,6 +194,82 @@ class HTDRoIHead(nn.Module):
         lw = self.stage_loss_weights[1]
         for name, value in res['loss_bbox'].items():
             losses[f's1.{name}'] = value * lw if 'loss' in name else value
+        return losses
+
+    def forward_train_static(self, x, img_metas, proposals, gt_bboxes, gt_labels, num_gt, keys=None):
+        """``forward_train`` (htd_roi_head.py:217-317) with static shapes and no host sync, so that
+        the whole step INCLUDING the assign + sample steps (:254-264, :300-310) is one CUDA graph.
+
+        ``proposals`` [B,N,4], ``gt_bboxes`` [B,G,4] / ``gt_labels`` [B,G] padded to G slots,
+        ``num_gt`` [B] int32 on the device; ``keys`` = two tensors [B,G+N] and [B,G+num] of
+        uniform random numbers (default: drawn here) that take the place of the reference
+        sampler's ``randperm``.  Every image contributes exactly ``sampler.num`` rows per stage:
+        positives, negatives, then pad rows (``ops.assign_sample``).  The first ``num *
+        pos_fraction`` rows of an image are the stage-1 regression rows; where an image has fewer
+        positives the remaining slots hold its first negatives, which the loss masks out - the
+        sampled set, its order and every loss / gradient equal the reference's.  Pad rows (an image
+        that cannot give ``num`` samples - usual in stage 1, where more than 128 refined boxes
+        are positive) are inert: no label weight, no box target, no PGraph group."""
+        B, N = proposals.shape[:2]
+        G = gt_bboxes.shape[1]
+        dev = proposals.device
+        losses = dict()
+        x_cl = self._pyramid(x)
+        global_feat = None
+        if self.with_global:
+            mc_pred, global_feat = self.glbctx_head(x)
+            real = torch.arange(G, device=dev)[None, :] < num_gt[:, None]
+            nc1 = mc_pred.size(1)
+            hot = (gt_labels[:, :, None] == torch.arange(nc1, device=dev)) & real[:, :, None]
+            losses['loss_global'] = self.glbctx_head.loss_multihot(mc_pred, hot.any(1))
+        cand, valid = proposals, None
+        self.last_static = []
+        for stage in range(self.num_stages):
+            cfg = self.train_cfg[stage]
+            a, s = dict(cfg.assigner), dict(cfg.sampler)
+            head = self.bbox_head[stage]
+            assert head.reg_class_agnostic and not head.reg_decoded_bbox and \
+                a.get('ignore_iof_thr', -1) <= 0 and a.get('gt_max_assign_all', True) and \
+                not isinstance(a['neg_iou_thr'], (tuple, list)), \
+                'forward_train_static covers the configs/htd settings'
+            k = keys[stage] if keys is not None else \
+                torch.rand((B, G + cand.shape[1]), device=dev, dtype=torch.float32)
+            S = ops.assign_sample(cand, gt_bboxes, gt_labels, num_gt, k, valid=valid,
+                                  pos_iou_thr=a['pos_iou_thr'], neg_iou_thr=a['neg_iou_thr'],
+                                  min_pos_iou=a.get('min_pos_iou', 0.),
+                                  match_low_quality=a.get('match_low_quality', True),
+                                  add_gt_as_proposals=s.get('add_gt_as_proposals', True),
+                                  num=s['num'], pos_fraction=s['pos_fraction'],
+                                  neg_pos_ub=s.get('neg_pos_ub', -1))
+            self.last_static.append(S)
+            num, npos = S.num, S.num_pos
+            rois = S.rois
+            row_valid = S.kind != 2
+            samp = None
+            if stage > 0:
+                r3 = rois.view(B, num, 5)
+                samp = [_StaticRows(r3[b, :npos, 1:], r3[b, npos:, 1:]) for b in range(B)]
+            res = self._bbox_forward(stage, x, rois, global_feat, samp, img_metas, x_cl,
+                                     row_valid=row_valid)
+            pw = cfg.get('pos_weight', -1)
+            targets = ops.bbox_targets(rois[:, 1:], S.gt_boxes, S.gt_labels, S.kind,
+                                       head.num_classes, pw, head.bbox_coder.means,
+                                       head.bbox_coder.stds)
+            loss = head.loss(res['cls_score'], res['bbox_pred'], rois, *targets, pad_rows=True)
+            lw = self.stage_loss_weights[stage]
+            for name, value in loss.items():
+                losses[f's{stage}.{name}'] = value * lw if 'loss' in name else value
+            if stage < self.num_stages - 1:
+                with torch.no_grad():                      # refine_bboxes (bbox_head.py:227-303):
+                    if len({tuple(m['img_shape'][:2]) for m in img_metas}) == 1:
+                        cand = head.regress_by_class(rois[:, 1:], None, res['bbox_pred'],
+                                                     img_metas[0]).view(B, num, 4)
+                    else:                                  # gt rows are masked, not dropped
+                        r3, bp = rois.view(B, num, 5), res['bbox_pred'].view(B, num, -1)
+                        cand = torch.stack([head.regress_by_class(r3[b, :, 1:], None, bp[b],
+                                                                  img_metas[b]) for b in range(B)])
+                    valid = (row_valid & (S.is_gt == 0)).view(B, num)
+                    self.last_refined = cand
         return losses
 
     def simple_test_scores(self, x, proposal_list, img_metas):

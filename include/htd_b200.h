@@ -272,7 +272,8 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
  *   once.  boxes [K,4]; gt_boxes [K,4] / gt_labels [K] int64 valid on rows with is_pos[k] != 0;
  *   labels[k] = gt label or num_classes (background); label_weights = pos_weight (1 if <= 0) or 1;
  *   bbox_targets = DeltaXYWHBBoxCoder.encode (delta_xywh_bbox_coder.py:98-120) on positives, 0 else;
- *   bbox_weights = 1 on positives.
+ *   bbox_weights = 1 on positives.  is_pos[k] == 2 marks a pad row of htd_assign_sample:
+ *   background label, label_weight 0, no box target.
  * htd_bbox_decode: delta2bbox (delta_xywh_bbox_coder.py:123-204), class-agnostic [K,4] deltas;
  *   rois rows of roi_stride 4 or 5 floats (5: batch index first, copied to out when out_stride 5);
  *   clip != 0 clamps to [0,max_w] x [0,max_h].
@@ -281,7 +282,11 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
  *           w_bbox * sum_{k positive} sum_j bw_kj smoothL1_beta(pred - target) / K,  1 / avg_factor);
  *   dcls [K,num_cls1] / dbbox [K,4] receive the unnormalised gradients, partial is a
  *   [ceil(K/8), 4] fp32 workspace.  htd_rcnn_loss_bwd scales them in place by the incoming
- *   gradients g_cls / g_bbox (device scalars, NULL = 0). */
+ *   gradients g_cls / g_bbox (device scalars, NULL = 0).
+ *   pad_rows != 0: rows with label_weight == 0 are the pad rows of htd_assign_sample (static
+ *   shapes), not samples - they are left out of the accuracy, and the accuracy / loss_bbox
+ *   denominators are the number of real rows max(#{lw > 0}, 1) instead of K (the reference's
+ *   `bbox_targets.size(0)` counts sampled RoIs only, bbox_head.py:176-183). */
 int htd_bbox_targets(const float* boxes, const float* gt_boxes, const long long* gt_labels,
                      const unsigned char* is_pos, int K, int num_classes, float pos_weight,
                      const float* means4, const float* stds4, long long* labels,
@@ -293,11 +298,44 @@ int htd_bbox_decode(const float* rois, int roi_stride, const void* deltas, int d
 int htd_rcnn_loss_fwd(const void* cls_score, int num_cls1, const void* bbox_pred, int dtype,
                       const long long* labels, const float* label_weights,
                       const float* bbox_targets, const float* bbox_weights, int K, int num_classes,
-                      float beta, float w_cls, float w_bbox, void* dcls, void* dbbox,
+                      float beta, float w_cls, float w_bbox, int pad_rows, void* dcls, void* dbbox,
                       float* partial, float* out4, htd_stream_t stream);
 int htd_rcnn_loss_bwd(void* dcls, long long ncls, void* dbbox, long long nbox, int dtype,
                       const float* g_cls, const float* g_bbox, const float* out4, float w_cls,
-                      float w_bbox, int K, htd_stream_t stream);
+                      float w_bbox, int K, int pad_rows, htd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Proposal -> gt assignment + random sampling of one RoI-head stage, all images in one launch,
+ * static output shapes, no host sync.  Replaces, per image,
+ * MaxIoUAssigner.assign (core/bbox/assigners/max_iou_assigner.py:84-212; float thresholds,
+ * gt_max_assign_all=True, no ignore regions), RandomSampler.sample (core/bbox/samplers/
+ * base_sampler.py:34-101, random_sampler.py:56-78) and SamplingResult (sampling_result.py), called
+ * from HTDRoIHead.forward_train (htd_roi_head.py:254-264,300-310).
+ *   props [B,N,4]; valid [B,N] (NULL = all) marks the proposals that take part; gt_boxes [B,G,4],
+ *   gt_labels [B,G] padded to G slots, num_gt [B] device integers.
+ *   Candidate index c in [0, G+N): gt slot c (a candidate iff add_gt_as_proposals and c < num_gt)
+ *   or proposal c - G - the reference's cat([gt_bboxes, bboxes]) order.  keys [B, G+N]: uniform
+ *   random numbers >= 0; a class with more members than wanted keeps those with the smallest
+ *   (key, c) - the distribution of randperm(n)[:want] - and, like the reference after `.unique()`,
+ *   lists them in ascending candidate order.
+ * Outputs, `num` rows per image = positives (<= num_pos), negatives, then pad rows:
+ *   rois [B*num,5] (image index first; pad rows are zero-area boxes at the origin),
+ *   kind [B*num] 1 positive / 0 negative / 2 pad, row_gt_boxes [B*num,4] / row_gt_labels [B*num] /
+ *   row_gt_index [B*num] the matched gt of positive rows (0 / 0 / -1 elsewhere), row_is_gt [B*num]
+ *   1 when the row is an appended gt box, row_cand [B*num] index into the reference's
+ *   cat([gt_bboxes[:num_gt], bboxes]) (-1 on pad rows), counts [B,4] = sampled positives, sampled
+ *   negatives, positive candidates, negative candidates.  Optional gt_inds / max_overlaps [B,G+N]:
+ *   the AssignResult after add_gt_ (-2 / 0 on slots that are no candidates). */
+#define HTD_MAX_GT 1024
+#define HTD_MAX_CANDIDATES 16384
+int htd_assign_sample(const float* props, const unsigned char* valid, int B, int N,
+                      const float* gt_boxes, const long long* gt_labels, const int32_t* num_gt,
+                      int G, const float* keys, float pos_iou_thr, float neg_iou_thr,
+                      float min_pos_iou, int match_low_quality, int add_gt_as_proposals, int num,
+                      int num_pos, float neg_pos_ub, float* rois, unsigned char* kind,
+                      float* row_gt_boxes, long long* row_gt_labels, unsigned char* row_is_gt,
+                      int32_t* row_cand, int32_t* row_gt_index, int32_t* counts, int32_t* gt_inds,
+                      float* max_overlaps, htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,

@@ -195,3 +195,195 @@ def compare_to_fixture(outs, fix, tol, names=None, sum_tol=None, floor=1e-9):
             bad.append((name, errs[name]))
     assert not bad, f'parity failures (tol {tol}): {bad[:12]}'
     return errs
+
+
+# ---------------------------------------------------------------------------------------------
+# assign + sample cases: seeded inputs shared by the generator of
+# tests/golden/assign_sample.npz (reference classes), the CPU tests of the restatement and the
+# GPU tests of csrc/assign_sample.cu.
+# ---------------------------------------------------------------------------------------------
+def _rcnn_cfg(iou, num=512, mlq=False, min_pos=None, ub=-1, add_gt=True, frac=0.25):
+    return dict(assigner=dict(type='MaxIoUAssigner', pos_iou_thr=iou, neg_iou_thr=iou,
+                              min_pos_iou=iou if min_pos is None else min_pos,
+                              match_low_quality=mlq, ignore_iof_thr=-1),
+                sampler=dict(type='RandomSampler', num=num, pos_fraction=frac, neg_pos_ub=ub,
+                             add_gt_as_proposals=add_gt))
+
+
+ASSIGN_CASES = {
+    # reference tests/test_assigner.py:14-36 (expected gt_inds [1,0,2,0]) and :66-83 (no gt)
+    'kat': dict(kind='kat', cfg=dict(
+        assigner=dict(type='MaxIoUAssigner', pos_iou_thr=0.5, neg_iou_thr=0.5),
+        sampler=dict(type='RandomSampler', num=4, pos_fraction=0.5, neg_pos_ub=-1,
+                     add_gt_as_proposals=False))),
+    # configs/htd/htd_resnet50_1x.py:122-138: stage 0 on RPN-like proposals
+    'stage0': dict(kind='synth', B=3, N=1000, G=16, gts=(7, 16, 1), jitter=0.25, near=0.15,
+                   seed=11, cfg=_rcnn_cfg(0.5)),
+    # :139-155: stage 1 on refined boxes - many positives, some proposals removed -> pad rows
+    'stage1': dict(kind='synth', B=3, N=512, G=16, gts=(5, 9, 3), jitter=0.08, near=0.6, seed=12,
+                   drop=0.05, cfg=_rcnn_cfg(0.6)),
+    'nogt': dict(kind='synth', B=2, N=300, G=8, gts=(0, 2), jitter=0.2, near=0.2, seed=13,
+                 cfg=_rcnn_cfg(0.5, num=128)),
+    'mlq': dict(kind='synth', B=2, N=700, G=24, gts=(24, 11), jitter=0.5, near=0.1, seed=14,
+                cfg=_rcnn_cfg(0.7, num=256, mlq=True, min_pos=0.3, ub=3, add_gt=False, frac=0.5)),
+    'few': dict(kind='synth', B=2, N=100, G=4, gts=(3, 4), jitter=0.2, near=0.3, seed=15,
+                cfg=_rcnn_cfg(0.5)),
+    # keys quantised to 1/8: many ties, broken by candidate index
+    'ties': dict(kind='synth', B=2, N=900, G=8, gts=(6, 8), jitter=0.2, near=0.3, seed=16,
+                 quant=8, cfg=_rcnn_cfg(0.5, num=256)),
+}
+
+
+def assign_case_inputs(name):
+    """Returns dict(props [B,N,4], valid [B,N] bool, gt_boxes [B,G,4], gt_labels [B,G],
+    num_gt [B] int32, keys [B,G+N] fp32, cfg).  CPU tensors."""
+    c = ASSIGN_CASES[name] if isinstance(name, str) else name
+    if c['kind'] == 'kat':
+        props = torch.tensor([[[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]],
+                              [[0, 0, 10, 10], [10, 10, 20, 20], [5, 5, 15, 15], [32, 32, 38, 42]]],
+                             dtype=torch.float32)
+        gt = torch.tensor([[[0, 0, 10, 9], [0, 10, 10, 19]], [[0, 0, 0, 0], [0, 0, 0, 0]]],
+                          dtype=torch.float32)
+        labels = torch.tensor([[2, 3], [0, 0]])
+        return dict(props=props, valid=torch.ones(2, 4, dtype=torch.bool), gt_boxes=gt,
+                    gt_labels=labels, num_gt=torch.tensor([2, 0], dtype=torch.int32),
+                    keys=torch.linspace(0.1, 0.9, 12).view(2, 6), cfg=c['cfg'])
+    g = torch.Generator().manual_seed(c['seed'])
+    B, N, G = c['B'], c['N'], c['G']
+    H, W = (float(v) for v in c.get('hw', (800, 1333)))
+    gt = torch.zeros(B, G, 4)
+    labels = torch.zeros(B, G, dtype=torch.long)
+    props = torch.zeros(B, N, 4)
+    for b in range(B):
+        ng = c['gts'][b]
+        wh = torch.exp(torch.rand(G, 2, generator=g) * 2.5 + 3.0)             # 20 .. 245 px
+        ctr = torch.rand(G, 2, generator=g) * torch.tensor([W, H])
+        box = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        box[:, 0::2] = box[:, 0::2].clamp(0, W)
+        box[:, 1::2] = box[:, 1::2].clamp(0, H)
+        gt[b, :ng] = box[:ng]
+        labels[b, :ng] = torch.randint(0, 80, (ng,), generator=g)
+        p = synth.make_proposals(1, N, int(H), int(W), seed=c['seed'] * 100 + b,
+                                 max_scale=min(800.0, H))[0]
+        near = int(N * c['near']) if ng > 0 else 0
+        if near:                                           # jittered copies of the gt boxes
+            src = box[:ng][torch.randint(0, ng, (near,), generator=g)]
+            swh = (src[:, 2:] - src[:, :2]).repeat(1, 2)
+            q = src + torch.randn(near, 4, generator=g) * c['jitter'] * swh
+            q = torch.stack([torch.min(q[:, 0], q[:, 2]), torch.min(q[:, 1], q[:, 3]),
+                             torch.max(q[:, 0], q[:, 2]), torch.max(q[:, 1], q[:, 3])], 1)
+            q[:, 0::2] = q[:, 0::2].clamp(0, W)
+            q[:, 1::2] = q[:, 1::2].clamp(0, H)
+            idx = torch.randperm(N, generator=g)[:near]
+            p[idx] = q
+            if ng > 1:                                     # exact duplicates: equal IoU maxima
+                p[idx[0]] = p[idx[1]]
+        props[b] = p
+    valid = torch.ones(B, N, dtype=torch.bool)
+    if c.get('drop'):
+        valid = torch.rand(B, N, generator=g) >= c['drop']
+    keys = torch.rand(B, G + N, generator=g)
+    if c.get('quant'):
+        keys = torch.floor(keys * c['quant']) / c['quant']
+    return dict(props=props, valid=valid, gt_boxes=gt, gt_labels=labels,
+                num_gt=torch.tensor(c['gts'], dtype=torch.int32), keys=keys, cfg=c['cfg'])
+
+
+def assign_static_layout(per_image, num, B):
+    """Lays per-image sampling results (namespaces with pos/neg fields in the reference's
+    candidate index space) out like htd_assign_sample: ``num`` rows per image, positives,
+    negatives, pad rows.  Integer tensors only (what must match bit for bit) + the boxes."""
+    K = B * num
+    out = dict(rois=torch.zeros(K, 5), kind=torch.full((K,), 2, dtype=torch.uint8),
+               gt_boxes=torch.zeros(K, 4), gt_labels=torch.zeros(K, dtype=torch.long),
+               gt_index=torch.full((K,), -1, dtype=torch.int32),
+               is_gt=torch.zeros(K, dtype=torch.uint8),
+               cand=torch.full((K,), -1, dtype=torch.int32),
+               counts=torch.zeros(B, 4, dtype=torch.int32))
+    for b, r in enumerate(per_image):
+        o = b * num
+        out['rois'][o:o + num, 0] = b
+        npos, nneg = r.pos_inds.numel(), r.neg_inds.numel()
+        out['rois'][o:o + npos + nneg, 1:] = r.bboxes
+        out['kind'][o:o + npos] = 1
+        out['kind'][o + npos:o + npos + nneg] = 0
+        out['gt_boxes'][o:o + npos] = r.pos_gt_bboxes
+        out['gt_labels'][o:o + npos] = r.pos_gt_labels
+        out['gt_index'][o:o + npos] = r.pos_assigned_gt_inds.to(torch.int32)
+        out['is_gt'][o:o + npos] = r.pos_is_gt
+        out['cand'][o:o + npos + nneg] = r.cand.to(torch.int32)
+        out['counts'][b] = torch.tensor([npos, nneg, r.npos_cand, r.nneg_cand], dtype=torch.int32)
+    return out
+
+
+def run_assign_case(name, image_fn):
+    """``image_fn(bboxes[n,4], gt_bboxes[g,4], gt_labels[g], keys[g+n or n], cfg, valid[n])`` ->
+    namespace (oracle/restate.assign_sample_image or the reference-backed equivalent)."""
+    d = assign_case_inputs(name)
+    B, N = d['props'].shape[:2]
+    G = d['gt_boxes'].shape[1]
+    add_gt = d['cfg']['sampler'].get('add_gt_as_proposals', True)
+    res = []
+    for b in range(B):
+        g = int(d['num_gt'][b])
+        keys = d['keys'][b]
+        keys = torch.cat([keys[:g], keys[G:]]) if (add_gt and g > 0) else keys[G:]
+        res.append(image_fn(d['props'][b], d['gt_boxes'][b, :g], d['gt_labels'][b, :g], keys,
+                            d['cfg'], d['valid'][b]))
+    return assign_static_layout(res, d['cfg']['sampler']['num'], B), res
+
+
+# full training step with assign + sample inside (forward_train, htd_roi_head.py:217-317)
+TRAIN_ASSIGNED = dict(kind='synth', B=2, N=200, G=6, gts=(4, 6), jitter=0.12, near=0.45, seed=17,
+                      hw=(320, 448), pyramid_seed=1000, scheme='n005', wseed=0, num=64,
+                      cfg=_rcnn_cfg(0.5, num=64))
+
+
+def train_assigned_inputs(dtype=torch.float32, device='cpu', n_props=None):
+    """x (pyramid), proposals [B,N,4], gt_boxes [B,G,4], gt_labels [B,G], num_gt [B], keys
+    (two tensors [B,G+N], [B,G+num]), cfgs (two rcnn stage cfgs), img_shapes.  ``n_props`` keeps
+    only the first proposals of every image (fewer than ``num``: pad rows in both stages)."""
+    c = TRAIN_ASSIGNED
+    d = assign_case_inputs(c)
+    if n_props is not None:
+        d['props'] = d['props'][:, :n_props].contiguous()
+        d['keys'] = d['keys'][:, :c['G'] + n_props].contiguous()
+    H, W = c['hw']
+    x = [t.to(dtype).to(device) for t in synth.make_pyramid(c['B'], H, W, seed=c['pyramid_seed'])]
+    g = torch.Generator().manual_seed(c['seed'] + 1)
+    keys1 = torch.rand(c['B'], c['G'] + c['num'], generator=g)
+    cfgs = [_rcnn_cfg(0.5, num=c['num']), _rcnn_cfg(0.6, num=c['num'])]
+    return dict(x=x, props=d['props'], gt_boxes=d['gt_boxes'], gt_labels=d['gt_labels'],
+                num_gt=d['num_gt'], keys=[d['keys'], keys1], cfgs=cfgs,
+                img_shapes=[(H, W, 3)] * c['B'])
+
+
+def run_train_assigned(train_fn, head, dtype=torch.float32, device='cpu', n_props=None):
+    """``train_fn(head, x, proposals(list), gt_bboxes(list), gt_labels(list), keys, cfgs,
+    img_shapes, G) -> (losses, info)``; returns the flat dict of losses, input / parameter
+    gradients and the sampled candidate indices (the fixture content)."""
+    d = train_assigned_inputs(dtype, n_props=n_props)
+    B, G = d['props'].shape[0], d['gt_boxes'].shape[1]
+    xs = [t.clone().to(device).requires_grad_(True) for t in d['x']]
+    ng = [int(v) for v in d['num_gt']]
+    losses, info = train_fn(head, xs, [d['props'][b].to(dtype).to(device) for b in range(B)],
+                            [d['gt_boxes'][b, :ng[b]].to(dtype).to(device) for b in range(B)],
+                            [d['gt_labels'][b, :ng[b]].to(device) for b in range(B)], d['keys'],
+                            d['cfgs'], d['img_shapes'], G)
+    head.zero_grad()
+    sum(v for k, v in losses.items() if 'loss' in k).backward()
+    out = {f'assigned.{k}': v.detach().reshape(-1).cpu() for k, v in losses.items()}
+    for i, t in enumerate(xs):
+        out[f'assigned.dx{i}'] = t.grad.cpu()
+    seen = set()
+    for k, p in head.named_parameters():
+        if p.grad is not None and id(p) not in seen:
+            seen.add(id(p))
+            out[f'assigned.grad.{k}'] = p.grad.cpu()
+    for st in (0, 1):
+        for b, r in enumerate(info[f'samp{st}']):
+            out[f'assigned.s{st}.cand{b}'] = r.cand.to(torch.int32).cpu() if hasattr(r, 'cand') \
+                else torch.cat([r.pos_inds, r.neg_inds]).to(torch.int32).cpu()
+            out[f'assigned.s{st}.npos{b}'] = torch.tensor([r.pos_bboxes.size(0)], dtype=torch.int32)
+    out['assigned.refined'] = torch.cat(info['refined']).cpu()
+    return out

@@ -4,6 +4,7 @@ of oracle/cases.py.  Run here (the authoring container); the fixtures travel, th
 does not.
 
     python -m oracle.gen_golden            # all cases, fp64 + fp32
+    python -m oracle.gen_golden assign     # only tests/golden/assign_sample.npz
 
 Fixtures hold, per tensor, a strided sample of <=1024 elements plus sum / abs-sum / max-abs
 (float tensors) or the full tensor (integer tensors: level indices, mask bitsets, degrees).
@@ -37,7 +38,34 @@ def boundary_rois():
     return torch.tensor(rows, dtype=torch.float32)
 
 
+def gen_assign_sample():
+    """tests/golden/assign_sample.npz: the reference's MaxIoUAssigner + RandomSampler (keys in place
+    of randperm) on oracle/cases.ASSIGN_CASES, in the static layout of htd_assign_sample."""
+    os.makedirs(OUT, exist_ok=True)
+    flat = {}
+    for name in cases.ASSIGN_CASES:
+        out, res = cases.run_assign_case(name, ref_driver.ref_assign_sample_image)
+        for k, v in out.items():
+            flat[f'{name}|{k}'] = v.numpy()
+        for b, r in enumerate(res):
+            flat[f'{name}|gt_inds{b}'] = r.gt_inds.numpy().astype(np.int32)
+            flat[f'{name}|max_overlaps{b}'] = r.max_overlaps.numpy()
+        print('assign', name, out['counts'].tolist())
+    np.savez_compressed(os.path.join(OUT, 'assign_sample.npz'), **flat)
+    # the reference's whole forward_train (its own assigners + samplers, keyed) on a small case
+    c = cases.TRAIN_ASSIGNED
+    head = refshim.build_head()
+    synth.fill_params_(head, c['scheme'], c['wseed'])
+    outs = cases.run_train_assigned(ref_driver.ref_forward_train_assigned, head)
+    path = os.path.join(OUT, 'train_assigned_f32.npz')
+    cases.save_fixture(path, outs)
+    print('train_assigned', len(outs), 'tensors ->', path, os.path.getsize(path) // 1024, 'KiB',
+          {k: float(v) for k, v in outs.items() if v.numel() == 1 and v.is_floating_point()})
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'assign':
+        return gen_assign_sample()
     os.makedirs(OUT, exist_ok=True)
     ns = refshim.load()
     torch.set_num_threads(os.cpu_count())
@@ -77,6 +105,7 @@ def main():
             cases.save_fixture(path, outs)
             print(name, tag, len(outs), 'tensors ->', path, os.path.getsize(path) // 1024, 'KiB',
                   {k: float(v) for k, v in outs.items() if k.startswith('train.') and v.numel() == 1})
+    gen_assign_sample()
 
 
 if __name__ == '__main__':

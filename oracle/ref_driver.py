@@ -69,3 +69,81 @@ def ref_simple_test_scores(head, x, proposals, img_shapes):
                           for j in range(len(proposals))])
     r1 = head._bbox_forward(1, x, new_rois, g)
     return new_rois, (r0['cls_score'] + r1['cls_score']) / 2.0, r1['bbox_pred']
+
+
+def ref_assign_sample_image(bboxes, gt_bboxes, gt_labels, keys, cfg, valid=None):
+    """One image through the REFERENCE's MaxIoUAssigner.assign + RandomSampler.sample (the calls of
+    htd_roi_head.py:254-264).  The only substitution: ``random_choice`` (randperm of the global
+    RNG) draws by the given keys (restate.choose_by_keys), so that the result is reproducible."""
+    from types import SimpleNamespace
+    from . import restate
+    ns = refshim.load()
+    a = {k: v for k, v in cfg['assigner'].items() if k != 'type'}
+    s = {k: v for k, v in cfg['sampler'].items() if k != 'type'}
+    assigner, sampler = ns.MaxIoUAssigner(**a), ns.RandomSampler(**s)
+    keep = torch.arange(bboxes.size(0)) if valid is None else torch.nonzero(valid).squeeze(1)
+    boxes = bboxes[keep]
+    g = gt_bboxes.size(0)
+    added = s.get('add_gt_as_proposals', True) and g > 0
+    src = torch.cat([torch.arange(g), keep + g]) if added else keep
+    ckeys = keys[src]
+    sampler.random_choice = lambda gallery, num: restate.choose_by_keys(gallery, num, ckeys)
+    ar = assigner.assign(boxes, gt_bboxes, None, gt_labels)
+    sr = sampler.sample(ar, boxes, gt_bboxes, gt_labels)
+    return SimpleNamespace(
+        pos_inds=sr.pos_inds, neg_inds=sr.neg_inds, pos_bboxes=sr.pos_bboxes,
+        neg_bboxes=sr.neg_bboxes, pos_is_gt=sr.pos_is_gt,
+        pos_assigned_gt_inds=sr.pos_assigned_gt_inds, pos_gt_bboxes=sr.pos_gt_bboxes,
+        pos_gt_labels=sr.pos_gt_labels if sr.pos_gt_labels is not None
+        else torch.zeros(0, dtype=torch.long),
+        bboxes=sr.bboxes, gt_inds=ar.gt_inds, max_overlaps=ar.max_overlaps,
+        cand=torch.cat([src[sr.pos_inds], src[sr.neg_inds]]),
+        npos_cand=int((ar.gt_inds > 0).sum()), nneg_cand=int((ar.gt_inds == 0).sum()))
+
+
+def ref_forward_train_assigned(head, x, proposals, gt_bboxes, gt_labels, keys, cfgs, img_shapes, G):
+    """The reference's own ``HTDRoIHead.forward_train`` (htd_roi_head.py:217-317), unmodified,
+    assigners and samplers included.  Only ``RandomSampler.random_choice`` is redirected to the
+    key rule (restate.choose_by_keys) through a wrapper around ``sampler.sample`` that knows which
+    (stage, image) is being sampled; ``keys`` as in restate.forward_train_assigned."""
+    from . import restate
+    img_metas = [dict(img_shape=s) for s in img_shapes]
+    rec = {0: [], 1: []}
+    keep0 = {}
+    refined = []
+    saved = []
+    for st in (0, 1):
+        sampler, assigner = head.bbox_sampler[st], head.bbox_assigner[st]
+        a, s = cfgs[st]['assigner'], cfgs[st]['sampler']
+        saved.append((sampler, sampler.num, sampler.pos_fraction))
+        sampler.num, sampler.pos_fraction = s['num'], s['pos_fraction']
+        assert (assigner.pos_iou_thr, assigner.neg_iou_thr, assigner.min_pos_iou,
+                assigner.match_low_quality) == (a['pos_iou_thr'], a['neg_iou_thr'],
+                                                a['min_pos_iou'], a['match_low_quality'])
+
+        def sample(assign_result, bboxes, gtb, gtl=None, _st=st, _sampler=sampler, **kw):
+            j = len(rec[_st])
+            k, ng = keys[_st][j], gtb.size(0)
+            if _st == 0:
+                pk = k[G:]
+            else:
+                pk = k[G:G + keep0[j].numel()][keep0[j]]
+                refined.append(bboxes)
+            ck = torch.cat([k[:ng], pk]) if (_sampler.add_gt_as_proposals and ng > 0) else pk
+            _sampler.random_choice = lambda gallery, num: restate.choose_by_keys(gallery, num, ck)
+            sr = type(_sampler).sample(_sampler, assign_result, bboxes, gtb, gtl, **kw)
+            if _st == 0:
+                keep0[j] = torch.cat([1 - sr.pos_is_gt,
+                                      sr.pos_is_gt.new_ones(sr.neg_bboxes.size(0))]).bool()
+            rec[_st].append(sr)
+            return sr
+        sampler.sample = sample
+    try:
+        losses = head.forward_train(x, img_metas, proposals, gt_bboxes, gt_labels)
+    finally:
+        for sampler, num, frac in saved:
+            sampler.num, sampler.pos_fraction = num, frac
+            del sampler.sample
+            if 'random_choice' in sampler.__dict__:
+                del sampler.random_choice
+    return losses, dict(samp0=rec[0], samp1=rec[1], refined=refined)

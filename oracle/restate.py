@@ -474,6 +474,96 @@ class HTDBBoxHead(BBoxHeadBase):
         return out + (masks,) if return_masks else out
 
 
+# --------------------------------------------------------------------------------------
+# assign + sample - checker of csrc/assign_sample.cu
+# --------------------------------------------------------------------------------------
+def max_iou_assign(bboxes, gt_bboxes, gt_labels, pos_iou_thr, neg_iou_thr, min_pos_iou=0.,
+                   match_low_quality=True):
+    """MaxIoUAssigner.assign / assign_wrt_overlaps (max_iou_assigner.py:84-212) without ignore
+    regions, float ``neg_iou_thr``, ``gt_max_assign_all=True``.  Returns (gt_inds int64 with
+    -1 ignore / 0 negative / i+1 positive, max_overlaps, labels)."""
+    overlaps = bbox_overlaps(gt_bboxes, bboxes)                       # :107
+    num_gts, num_bboxes = overlaps.size(0), overlaps.size(1)
+    gt_inds = overlaps.new_full((num_bboxes,), -1, dtype=torch.long)  # :142
+    if num_gts == 0 or num_bboxes == 0:                               # :146-161
+        max_overlaps = overlaps.new_zeros((num_bboxes,))
+        if num_gts == 0:
+            gt_inds[:] = 0
+        labels = overlaps.new_full((num_bboxes,), -1, dtype=torch.long)
+        return gt_inds, max_overlaps, labels
+    max_overlaps, argmax_overlaps = overlaps.max(dim=0)               # :165
+    gt_max_overlaps, _ = overlaps.max(dim=1)                          # :168
+    gt_inds[(max_overlaps >= 0) & (max_overlaps < neg_iou_thr)] = 0   # :171-173
+    pos = max_overlaps >= pos_iou_thr                                 # :181-182
+    gt_inds[pos] = argmax_overlaps[pos] + 1
+    if match_low_quality:                                             # :184-198
+        for i in range(num_gts):
+            if gt_max_overlaps[i] >= min_pos_iou:
+                gt_inds[overlaps[i, :] == gt_max_overlaps[i]] = i + 1
+    labels = gt_inds.new_full((num_bboxes,), -1)                      # :200-209
+    p = torch.nonzero(gt_inds > 0, as_tuple=False).squeeze(1)
+    if p.numel() > 0:
+        labels[p] = gt_labels[gt_inds[p] - 1]
+    return gt_inds, max_overlaps, labels
+
+
+def choose_by_keys(gallery, num, keys):
+    """Stand-in for RandomSampler.random_choice (random_sampler.py:31-54: ``gallery[randperm(n)
+    [:num]]``): the ``num`` members of ``gallery`` with the smallest (key, index).  Same
+    distribution for i.i.d. uniform keys; deterministic given the keys."""
+    k = keys[gallery].double() * (2.0 ** 40) + gallery.double()      # exact: keys are fp32 < 2
+    order = torch.argsort(k, stable=True)
+    return gallery[order[:num]]
+
+
+def assign_sample_image(bboxes, gt_bboxes, gt_labels, keys, cfg, valid=None):
+    """One image of HTDRoIHead.forward_train's assign + sample (htd_roi_head.py:254-264):
+    MaxIoUAssigner.assign, then BaseSampler.sample (base_sampler.py:34-101) with
+    RandomSampler._sample_pos/_sample_neg (random_sampler.py:56-78) drawing by ``keys`` (indexed
+    like cat([gt_bboxes, bboxes]) when gts are added, else like bboxes).  ``valid`` (optional bool
+    [n]) restricts the proposals that exist.  Returns a namespace with the SamplingResult fields
+    (sampling_result.py) plus ``pos_inds`` / ``neg_inds`` / ``gt_inds`` / ``max_overlaps``."""
+    a, s = cfg['assigner'], cfg['sampler']
+    bboxes = bboxes[:, :4]
+    keep = torch.arange(bboxes.size(0)) if valid is None else torch.nonzero(valid).squeeze(1)
+    boxes = bboxes[keep]
+    gt_inds, max_ov, _ = max_iou_assign(boxes, gt_bboxes, gt_labels, a['pos_iou_thr'],
+                                        a['neg_iou_thr'], a.get('min_pos_iou', 0.),
+                                        a.get('match_low_quality', True))
+    gt_flags = torch.zeros(boxes.size(0), dtype=torch.uint8)
+    g = gt_bboxes.size(0)
+    src = keep.clone()                       # index of every candidate in cat([gt, bboxes])
+    if s.get('add_gt_as_proposals', True) and g > 0:                  # base_sampler.py:73-81
+        boxes = torch.cat([gt_bboxes, boxes], 0)
+        gt_inds = torch.cat([torch.arange(1, g + 1), gt_inds])        # AssignResult.add_gt_
+        max_ov = torch.cat([max_ov.new_ones(g), max_ov])
+        gt_flags = torch.cat([torch.ones(g, dtype=torch.uint8), gt_flags])
+        src = torch.cat([torch.arange(g), keep + g])
+    ckeys = keys[src]
+    num_expected_pos = int(s['num'] * s['pos_fraction'])             # :83
+    pos_inds = torch.nonzero(gt_inds > 0, as_tuple=False).squeeze(1)
+    if pos_inds.numel() > num_expected_pos:
+        pos_inds = choose_by_keys(pos_inds, num_expected_pos, ckeys)
+    pos_inds = pos_inds.unique()                                      # :88
+    num_expected_neg = s['num'] - pos_inds.numel()
+    if s.get('neg_pos_ub', -1) >= 0:                                  # :91-95
+        num_expected_neg = min(num_expected_neg, int(s['neg_pos_ub'] * max(1, pos_inds.numel())))
+    neg_inds = torch.nonzero(gt_inds == 0, as_tuple=False).squeeze(1)
+    if neg_inds.numel() > num_expected_neg:
+        neg_inds = choose_by_keys(neg_inds, num_expected_neg, ckeys)
+    neg_inds = neg_inds.unique()
+    pos_assigned = gt_inds[pos_inds] - 1
+    return SimpleNamespace(
+        pos_inds=pos_inds, neg_inds=neg_inds, pos_bboxes=boxes[pos_inds],
+        neg_bboxes=boxes[neg_inds], pos_is_gt=gt_flags[pos_inds],
+        pos_assigned_gt_inds=pos_assigned,
+        pos_gt_bboxes=gt_bboxes.view(-1, 4)[pos_assigned] if g > 0 else gt_bboxes.new_zeros((0, 4)),
+        pos_gt_labels=gt_labels[pos_assigned] if g > 0 else gt_labels.new_zeros((0,)),
+        bboxes=torch.cat([boxes[pos_inds], boxes[neg_inds]]), gt_inds=gt_inds, max_overlaps=max_ov,
+        cand=torch.cat([src[pos_inds], src[neg_inds]]),
+        npos_cand=int((gt_inds > 0).sum()), nneg_cand=int((gt_inds == 0).sum()))
+
+
 def make_sampling(bboxes, num_pos, gt):
     """Synthetic SamplingResult (positives first, sampling_result.py:52-54): the first
     ``num_pos`` rows of ``bboxes`` are positives with the targets in ``gt``."""
@@ -553,6 +643,60 @@ class HTDRoIHead(nn.Module):
         for k, v in l1.items():
             losses[f's1.{k}'] = v * self.stage_loss_weights[1] if 'loss' in k else v
         return losses
+
+    def forward_train_assigned(self, x, proposals, gt_bboxes, gt_labels, keys, cfgs, img_shapes, G):
+        """htd_roi_head.py:217-317 INCLUDING the assign + sample steps (:254-264, :300-310), the
+        sampler drawing by ``keys`` instead of randperm.  ``keys[stage]`` [B, G + n_stage] is laid
+        out like htd_assign_sample's: G gt slots, then one key per stage candidate - for stage 1
+        the candidates are the stage-0 rows, of which refine_bboxes (bbox_head.py:227-303) drops
+        the gt boxes.  Assignment runs in fp32 like the reference.  Returns (losses, dict of the
+        per-stage sampling results and the refined boxes)."""
+        dt, dev = x[0].dtype, x[0].device
+        losses = {}
+        mc_pred, g = self.glbctx_head(x)
+        losses['loss_global'] = self.glbctx_head.loss(mc_pred, [l.unique() for l in gt_labels])
+        B = len(proposals)
+
+        def sample(stage, boxes, keep):
+            out = []
+            for b in range(B):
+                ng = gt_bboxes[b].size(0)
+                k = keys[stage][b]
+                pk = k[G:G + keep[b].numel()][keep[b].cpu()] if keep is not None else k[G:]
+                add = cfgs[stage]['sampler'].get('add_gt_as_proposals', True) and ng > 0
+                kb = torch.cat([k[:ng], pk]) if add else pk
+                r = assign_sample_image(boxes[b].detach().float().cpu(), gt_bboxes[b].float().cpu(),
+                                        gt_labels[b].cpu(), kb.cpu(), cfgs[stage])
+                for f, v in list(vars(r).items()):
+                    if torch.is_tensor(v):
+                        setattr(r, f, v.to(dev))
+                for f in ('pos_bboxes', 'neg_bboxes', 'pos_gt_bboxes', 'bboxes'):
+                    setattr(r, f, getattr(r, f).to(dt))
+                out.append(r)
+            return out
+
+        samp0 = sample(0, proposals, None)
+        rois = bbox2roi([r.bboxes for r in samp0])
+        res = self._bbox_forward(0, x, rois, g)
+        targets = self.bbox_head[0].get_targets(samp0)
+        l0 = self.bbox_head[0].loss(res['cls_score'], res['bbox_pred'], rois, *targets)
+        for k, v in l0.items():
+            losses[f's0.{k}'] = v * self.stage_loss_weights[0] if 'loss' in k else v
+        with torch.no_grad():
+            roi_labels = torch.where(targets[0] == 80, res['cls_score'][:, :-1].argmax(1),
+                                     targets[0])
+            refined = self.bbox_head[0].refine_bboxes(rois, roi_labels, res['bbox_pred'],
+                                                      [r.pos_is_gt for r in samp0], img_shapes)
+            keep = [torch.cat([1 - r.pos_is_gt, r.pos_is_gt.new_ones(r.neg_bboxes.size(0))]).bool()
+                    for r in samp0]
+        samp1 = sample(1, refined, keep)
+        rois = bbox2roi([r.bboxes for r in samp1])
+        res = self._bbox_forward(1, x, rois, g, samp1)
+        targets = self.bbox_head[1].get_targets(samp1)
+        l1 = self.bbox_head[1].loss(res['cls_score'], res['bbox_pred'], rois, *targets)
+        for k, v in l1.items():
+            losses[f's1.{k}'] = v * self.stage_loss_weights[1] if 'loss' in k else v
+        return losses, dict(samp0=samp0, samp1=samp1, refined=refined)
 
     def simple_test_scores(self, x, proposals, img_shapes):
         """htd_roi_head.py:319-366 up to (and excluding) get_bboxes/NMS: returns the refined

@@ -138,3 +138,90 @@ def test_restatement_equals_reference_live():
     assert set(ref.state_dict()) == set(restate.HTDRoIHead().state_dict())
     for k in a:
         assert cases.rel_err(b[k], a[k]) <= 1e-6, k
+
+
+# ---- assign + sample --------------------------------------------------------------
+def _assign_fixture():
+    z = np.load(os.path.join(GOLD, 'assign_sample.npz'))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize('name', list(cases.ASSIGN_CASES))
+def test_assign_sample_restatement_matches_reference_golden(name):
+    """oracle/restate.assign_sample_image == the reference's MaxIoUAssigner + RandomSampler
+    (tests/golden/assign_sample.npz, made by oracle/gen_golden.py from the reference classes):
+    every index, flag and count bit for bit, boxes exactly."""
+    fix = _assign_fixture()
+    out, res = cases.run_assign_case(name, restate.assign_sample_image)
+    for k, v in out.items():
+        assert np.array_equal(v.numpy(), fix[f'{name}|{k}']), (name, k)
+    for b, r in enumerate(res):
+        assert np.array_equal(r.gt_inds.numpy().astype(np.int32), fix[f'{name}|gt_inds{b}'])
+        assert np.array_equal(r.max_overlaps.numpy(), fix[f'{name}|max_overlaps{b}'])
+
+
+def test_assigner_known_answers_of_the_reference_tests():
+    """/root/reference/tests/test_assigner.py:14-36 (gt_inds [1,0,2,0]) and :66-83 (no gt ->
+    all background), through the restatement and in the committed fixture."""
+    fix = _assign_fixture()
+    assert fix['kat|gt_inds0'].tolist() == [1, 0, 2, 0]
+    assert fix['kat|gt_inds1'].tolist() == [0, 0, 0, 0]
+    d = cases.assign_case_inputs('kat')
+    gi, mo, lab = restate.max_iou_assign(d['props'][0], d['gt_boxes'][0], d['gt_labels'][0], 0.5, 0.5)
+    assert gi.tolist() == [1, 0, 2, 0] and lab.tolist() == [2, -1, 3, -1]
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference not present')
+def test_assign_sample_restatement_equals_reference_live():
+    from oracle import ref_driver
+    for name in cases.ASSIGN_CASES:
+        a, _ = cases.run_assign_case(name, ref_driver.ref_assign_sample_image)
+        b, _ = cases.run_assign_case(name, restate.assign_sample_image)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (name, k)
+
+
+def test_key_choice_has_the_distribution_of_randperm_prefix():
+    """choose_by_keys with i.i.d. uniform keys picks every member with probability num/n."""
+    g = torch.Generator().manual_seed(0)
+    gallery = torch.arange(3, 43)
+    hits = torch.zeros(50)
+    for _ in range(2000):
+        keys = torch.rand(50, generator=g)
+        hits[restate.choose_by_keys(gallery, 10, keys)] += 1
+    assert hits[:3].sum() == 0 and hits[43:].sum() == 0
+    assert (hits[3:43] / 2000 - 0.25).abs().max() < 0.05
+
+
+def _restate_train_assigned(dtype=torch.float32):
+    c = cases.TRAIN_ASSIGNED
+    own = restate.HTDRoIHead()
+    synth.fill_params_(own, c['scheme'], c['wseed'])
+    own = own.to(dtype)
+    return cases.run_train_assigned(lambda h, *a: h.forward_train_assigned(*a), own, dtype)
+
+
+def test_restated_forward_train_with_assigner_matches_reference_golden():
+    """restate.forward_train_assigned == the reference's unmodified HTDRoIHead.forward_train with
+    its own MaxIoUAssigner / RandomSampler (keys instead of randperm): sampled indices exactly,
+    losses and gradients to 1e-6 (tests/golden/train_assigned_f32.npz)."""
+    fix = cases.load_fixture(os.path.join(GOLD, 'train_assigned_f32.npz'))
+    outs = _restate_train_assigned()
+    assert set(outs) == set(fix)
+    cases.compare_to_fixture(outs, fix, 1e-6)
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference not present')
+def test_restated_forward_train_with_assigner_equals_reference_live():
+    from oracle import ref_driver
+    c = cases.TRAIN_ASSIGNED
+    ref = refshim.build_head()
+    synth.fill_params_(ref, c['scheme'], c['wseed'])
+    a = cases.run_train_assigned(ref_driver.ref_forward_train_assigned, ref)
+    b = _restate_train_assigned()
+    assert set(a) == set(b)
+    for k in a:
+        if a[k].is_floating_point():
+            assert cases.rel_err(b[k], a[k]) <= 1e-6, k
+        else:
+            assert torch.equal(a[k], b[k]), k
