@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager steps instead of CUDA-graph replay')
+    ap.add_argument('--no-static', action='store_true',
+                    help='skip the extra figure for the step with device-side assign + sample')
     return ap.parse_args()
 
 
@@ -366,6 +368,35 @@ def run_gpu(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- the COMPLETE step: assign + sample on the device, then the same two stages, one graph --
+    static = None
+    if world == 1 and use_graph and not args.no_static:
+        try:
+            from htd_b200.graphed import GraphedStaticTrainStep
+            nprop = 2000                               # configs/htd/htd_resnet50_1x.py:115-121
+            sp, sg, sl, sn = (t.to(dev) for t in synth.make_detection_batch(IMGS, nprop))
+            metas = [dict(img_shape=s_, scale_factor=1.0) for s_ in shapes]
+            sstep = GraphedStaticTrainStep(head, x_dev, metas, sp, sg, sl, sn)   # keys drawn in-graph
+            for _ in range(3):
+                sstep()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                sstep()
+            s1.record()
+            torch.cuda.synchronize()
+            sms = s0.elapsed_time(s1) / args.steps
+            cnt = [S.counts.tolist() for S in head.last_static]
+            static = dict(what='forward_train_static as one CUDA graph: MaxIoUAssigner + RandomSampler '
+                               'on the device (htd_assign_sample, random keys drawn in-graph), both '
+                               'stages, losses, backward', proposals_per_img=nprop,
+                          sampled_rois_per_step=rois_per_step, ms_per_step=sms,
+                          rois_per_s=rois_per_step / (sms * 1e-3),
+                          last_counts_pos_neg_per_img=[[c[:2] for c in st] for st in cnt])
+        except Exception as e:
+            print(f'[bench] static step failed ({type(e).__name__}: {e})', file=sys.stderr)
+
     # ---- max over ranks ------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -428,6 +459,7 @@ def run_gpu(args):
                             execution=('CUDA graph replay of forward+losses+backward' if use_graph
                                        else 'eager'),
                             eager_ms_per_step=ms_eager,
+                            full_step_with_sampling=static,
                             kernel_timing='CUDA events around each own launch in an eager pass of '
                                           'the same step (events cannot be placed inside a graph)'),
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,

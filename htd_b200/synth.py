@@ -85,6 +85,36 @@ def make_gt(num_imgs, proposals, num_pos=128, num_classes=80, seed=4321):
     return out
 
 
+def make_detection_batch(num_imgs, num_props=2000, num_gt=(7, 12), gt_capacity=32, img_h=800,
+                         img_w=1333, near=0.2, jitter=0.15, num_classes=80, seed=77):
+    """Inputs of the complete training step (``HTDRoIHead.forward_train_static``): RPN-like
+    proposals [B,N,4] of which a fraction ``near`` are jittered copies of the ground-truth boxes
+    (so that assignment finds positives), gt boxes [B,G,4] / labels [B,G] padded to
+    ``gt_capacity`` slots, and the per-image gt counts [B] (int32)."""
+    g = torch.Generator().manual_seed(seed)
+    B, N, G = num_imgs, num_props, gt_capacity
+    props = torch.stack(make_proposals(B, N, img_h, img_w, seed=seed * 31))
+    gt = torch.zeros(B, G, 4)
+    labels = torch.zeros(B, G, dtype=torch.long)
+    counts = torch.tensor([num_gt[b % len(num_gt)] for b in range(B)], dtype=torch.int32)
+    lim = torch.tensor([img_w, img_h, img_w, img_h], dtype=torch.float32)
+    for b in range(B):
+        ng = int(counts[b])
+        wh = torch.exp(torch.rand(ng, 2, generator=g) * 2.5 + 3.0)
+        ctr = torch.rand(ng, 2, generator=g) * lim[:2]
+        box = torch.min(torch.cat([ctr - wh / 2, ctr + wh / 2], 1).clamp(min=0), lim)
+        gt[b, :ng] = box
+        labels[b, :ng] = torch.randint(0, num_classes, (ng,), generator=g)
+        k = int(N * near)
+        if ng and k:
+            src = box[torch.randint(0, ng, (k,), generator=g)]
+            swh = (src[:, 2:] - src[:, :2]).repeat(1, 2)
+            q = src + torch.randn(k, 4, generator=g) * jitter * swh
+            q = torch.cat([torch.min(q[:, :2], q[:, 2:]), torch.max(q[:, :2], q[:, 2:])], 1)
+            props[b, torch.randperm(N, generator=g)[:k]] = torch.min(q.clamp(min=0), lim)
+    return props, gt, labels, counts
+
+
 def _gen_for(name, seed):
     return torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
 
