@@ -397,6 +397,31 @@ def run_gpu(args):
         except Exception as e:
             print(f'[bench] static step failed ({type(e).__name__}: {e})', file=sys.stderr)
 
+    # ---- the producer (FPN) emitting channels-last maps in the compute dtype -------
+    nhwc = None
+    if world == 1 and use_graph and not args.no_static and dtype == torch.bfloat16:
+        try:
+            from htd_b200.graphed import GraphedTrainStep
+            x_cl = [t.detach().to(dtype).contiguous(memory_format=torch.channels_last)
+                    .requires_grad_(True) for t in x_dev[:4]] + [x_dev[4]]     # P6: SFA input
+            cstep = GraphedTrainStep(head, x_cl, props_dev, gts, shapes, POS)
+            for _ in range(3):
+                cstep()
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(args.steps):
+                cstep()
+            c1.record()
+            torch.cuda.synchronize()
+            cms = c0.elapsed_time(c1) / args.steps
+            nhwc = dict(what='same step, pyramid handed over channels-last in bf16 (no layout / cast '
+                             'pass in either direction; dX returned channels-last bf16)',
+                        ms_per_step=cms, rois_per_s=rois_per_step / (cms * 1e-3))
+        except Exception as e:
+            print(f'[bench] channels-last pyramid step failed ({type(e).__name__}: {e})',
+                  file=sys.stderr)
+
     # ---- max over ranks ------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -460,6 +485,7 @@ def run_gpu(args):
                                        else 'eager'),
                             eager_ms_per_step=ms_eager,
                             full_step_with_sampling=static,
+                            channels_last_bf16_pyramid=nhwc,
                             kernel_timing='CUDA events around each own launch in an eager pass of '
                                           'the same step (events cannot be placed inside a graph)'),
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,

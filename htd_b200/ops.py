@@ -224,33 +224,44 @@ class _PyramidFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, dtype, sink, *xs):
-        outs = []
+        outs, is_cl = [], []
         for x in xs:
             B, C, H, W = x.shape
+            if _is_cl(x):
+                # producer already emits channels-last: no transpose; a cast only
+                # if its dtype is not the compute dtype
+                outs.append(x.detach() if x.dtype == dtype else x.detach().to(dtype))
+                is_cl.append(True)
+                continue
             o = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
             _convert(x, o, B, C, H * W)
             outs.append(o.permute(0, 3, 1, 2))
+            is_cl.append(False)
         token = torch.zeros(1, dtype=torch.float32, device=xs[0].device)
         ctx.sink = sink
-        ctx.meta = ([tuple(x.shape) for x in xs], xs[0].dtype)
+        ctx.meta = ([tuple(x.shape) for x in xs], [x.dtype for x in xs], is_cl)
         ctx.mark_non_differentiable(*outs)
         return (token,) + tuple(outs)
 
     @staticmethod
     def backward(ctx, gtoken, *gouts):
-        shapes, xdtype = ctx.meta
+        shapes, xdtypes, is_cl = ctx.meta
         sink = ctx.sink
         if not sink.sources:
-            return (None, None) + tuple(torch.zeros(s, dtype=xdtype, device=gtoken.device)
-                                        for s in shapes)
+            return (None, None) + tuple(torch.zeros(s, dtype=dt_, device=gtoken.device)
+                                        for s, dt_ in zip(shapes, xdtypes))
         # channels-last gather (512 B coalesced stores) + one transpose/cast pass back to the
         # reference's NCHW layout; writing NCHW straight from the gather measured 30% slower
         cl = _bwd_multi(shapes, sink.sources[0]['dy'].dtype, False, sink.scales, sink.sources,
                         sink.pooled)
         grads = []
-        for g, shp in zip(cl, shapes):
+        for g, shp, xdt, keep_cl in zip(cl, shapes, xdtypes, is_cl):
             B, C, H, W = shp
-            o = torch.empty(shp, dtype=xdtype, device=g.device)
+            if keep_cl:                            # gradient stays channels-last, like the input
+                assert g.shape == shp              # [B,C,H,W] view of the [B,H,W,C] gather buffer
+                grads.append(g if g.dtype == xdt else g.to(xdt))
+                continue
+            o = torch.empty(shp, dtype=xdt, device=g.device)
             _convert(g, o, B, H * W, C)
             grads.append(o)
         sink.sources = []
@@ -259,10 +270,11 @@ class _PyramidFn(torch.autograd.Function):
 
 def make_pyramid(xs, dtype=None):
     """Feature maps in the layout the kernels read, converted once per step and shared by all
-    extractor calls.  Contiguous NCHW CUDA inputs get the deferred single-launch backward;
-    anything else falls back to per-call ``to_channels_last`` (immediate backward)."""
+    extractor calls.  Contiguous NCHW or channels-last CUDA inputs get the deferred single-launch
+    backward (channels-last inputs are read in place and receive a channels-last gradient: no
+    layout pass at all); anything else falls back to per-call ``to_channels_last``."""
     dtype = dtype or xs[0].dtype
-    if all(x.is_cuda and x.dim() == 4 and x.is_contiguous() and not _is_cl(x) for x in xs) and \
+    if all(x.is_cuda and x.dim() == 4 and (x.is_contiguous() or _is_cl(x)) for x in xs) and \
             any(x.requires_grad for x in xs) and torch.is_grad_enabled():
         sink = GradSink()
         res = _PyramidFn.apply(dtype, sink, *xs)

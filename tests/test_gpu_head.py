@@ -563,3 +563,48 @@ def test_training_step_without_positives():
     sum(v for k, v in losses.items() if 'loss' in k).backward()
     assert all(torch.isfinite(t.grad).all() for t in x)
     assert all(torch.isfinite(p.grad).all() for p in head.parameters() if p.grad is not None)
+
+
+def test_channels_last_bf16_pyramid_is_read_in_place_and_gives_identical_results():
+    """when the producer hands the pyramid over channels-last in the compute dtype,
+    no layout / cast pass runs (the extractors read the caller's memory) and the gradient comes
+    back channels-last in that dtype; losses and gradients equal the NCHW-fp32-input path bit for
+    bit (same kernels on the same bf16 values)."""
+    import htd_b200
+    from htd_b200 import _lib
+    from oracle import cases
+    torch.backends.cudnn.enabled = True
+    name = 'small'
+    c = cases.CASES[name]
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    head = head.cuda().to(torch.bfloat16)
+    head.compute_dtype = torch.bfloat16
+    _, x, props, gts, shapes = cases.case_inputs(name, torch.float32, 'cuda')
+
+    def run(xs):
+        for p in head.parameters():
+            p.grad = None
+        n0 = dict(_lib.LAUNCHES['by_entry']).get('htd_layout_convert', 0)
+        losses = synth.sampled_forward_train(head, xs, props, gts, shapes, c['P'])
+        sum(v for k, v in losses.items() if 'loss' in k).backward()
+        n1 = dict(_lib.LAUNCHES['by_entry']).get('htd_layout_convert', 0)
+        return ({k: v.detach().float().clone() for k, v in losses.items()},
+                {k: p.grad.clone() for k, p in head.named_parameters() if p.grad is not None},
+                n1 - n0)
+    xa = [t.clone().requires_grad_(True) for t in x]
+    la, ga, na = run(xa)
+    # P2-P5 (what the extractors read) channels-last bf16; P6 feeds the SFA convs (cuDNN picks its
+    # algorithm by layout), so it stays as it is to keep the comparison bit-exact
+    xb = [t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+          for t in x[:4]] + [x[4].clone().requires_grad_(True)]
+    lb, gb, nb = run(xb)
+    assert nb == na - 2 * 4, (na, nb)          # 4 levels x (forward transpose + backward transpose)
+    for k in la:
+        assert torch.equal(la[k], lb[k]), k
+    for k in ga:
+        assert torch.equal(ga[k], gb[k]), k
+    for a, b in zip(xa[:4], xb[:4]):
+        assert b.grad.dtype == torch.bfloat16 and b.grad.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(a.grad, b.grad.float())
+    assert torch.equal(xa[4].grad, xb[4].grad)
