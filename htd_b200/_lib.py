@@ -77,6 +77,8 @@ SIGNATURES = {
                           c_void_p, c_void_p, c_void_p],
     'htd_rcnn_loss_bwd': [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                           c_float, c_float, c_int, c_int, c_void_p],
+    'htd_multiclass_nms': [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_int,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_assign_sample': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_float,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -111,7 +113,7 @@ _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
 KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
-                    'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2}
+                    'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2, 'htd_multiclass_nms': 4}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 
 
@@ -149,6 +151,8 @@ def lib():
         L.htd_pgraph_max_tiles.argtypes = [c_int] * 9
         L.htd_roi_plan_rows_bound.restype = c_ll
         L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
+        L.htd_multiclass_nms_workspace_bytes.restype = c_ll
+        L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
         for name, args in SIGNATURES.items():
             if not hasattr(L, name):
                 raise RuntimeError(f'{LIB_PATH} does not export {name}: rebuild it '

@@ -306,25 +306,14 @@ def accuracy(pred, target, topk=1):
 # post-processing (the step right after the path at inference)
 # ----------------------------------------------------------------------------------------------
 def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1):
-    """core/post_processing/bbox_nms.py:7-71 with the library batched NMS of torchvision."""
-    from torchvision.ops import batched_nms
-    num_classes = multi_scores.size(1) - 1
-    if multi_bboxes.shape[1] > 4:
-        bboxes = multi_bboxes.view(multi_scores.size(0), -1, 4)
-    else:
-        bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), num_classes, 4)
-    scores = multi_scores[:, :-1]
-    valid = scores > score_thr
-    bboxes = bboxes[valid]
-    scores = scores[valid]
-    labels = valid.nonzero(as_tuple=False)[:, 1]
-    if bboxes.numel() == 0:
-        return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
+    """core/post_processing/bbox_nms.py:7-71.  CUDA tensors: csrc/nms.cu (three launches, no host
+    sync until the final read of the detection count that sizes the returned tensors); CPU
+    tensors are not supported (no fallback)."""
     cfg = dict(nms_cfg)
     if cfg.pop('type', 'nms') != 'nms':
         raise NotImplementedError('only hard NMS is provided (configs/htd/htd_resnet50_1x.py:166)')
     thr = cfg.get('iou_threshold', cfg.get('iou_thr', 0.5))
-    keep = batched_nms(bboxes.float(), scores.float(), labels, thr)
-    if max_num > 0:
-        keep = keep[:max_num]
-    return torch.cat([bboxes[keep], scores[keep, None]], -1), labels[keep]
+    from . import ops
+    det, labels, count = ops.multiclass_nms(multi_bboxes, multi_scores, score_thr, thr, max_num)
+    n = int(count)                                   # the one host read: output sizes
+    return det[:n].to(multi_bboxes.dtype), labels[:n]

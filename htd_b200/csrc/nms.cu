@@ -1,0 +1,232 @@
+// Multi-class NMS of the test branch - the step right after the RoI head at inference
+// (SURVEY.md section 8 row f3): BBoxHead.get_bboxes -> multiclass_nms
+// (bbox_heads/bbox_head.py:188-225, core/post_processing/bbox_nms.py:7-71) -> mmcv.ops.batched_nms /
+// nms (mmcv-full 1.2.1, un-vendored; published algorithm restated in oracle/restate.py):
+//   * candidates = all (RoI k, class c) with score[k,c] > score_thr, in row-major (k, c) order;
+//   * boxes are shifted by c * (max coordinate over the candidates + 1) so that one class-agnostic
+//     NMS separates the classes (the shift is done in fp32 and changes the IoU bits: kept);
+//   * greedy NMS in descending score order, suppress when IoU > iou_thr, IoU = inter / (Sa + Sb - inter);
+//   * the survivors in descending score order, first max_num of them.
+// The reference does this with masked_select / nonzero / sort / a bit-matrix kernel and a host-side
+// reduction.  Here: three small kernels, no host sync, static output shapes, ties in the score
+// broken by the candidate index (k * C + c) - the order of a stable sort.
+#include "common.cuh"
+
+namespace htd {
+
+constexpr int kNmsThreads = 256;
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+// ws_f[0] = max coordinate, ws_n[c] = candidates of class c, ws_n[C + c] = survivors of class c
+__global__ void nms_init_kernel(float* ws_f, int* ws_n, int C) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ws_n[i] = 0;
+    if (threadIdx.x == 0) ws_f[0] = -INFINITY;
+}
+
+// one CTA per class: candidate RoIs in ascending k, global max coordinate
+__global__ void __launch_bounds__(kNmsThreads) nms_collect_kernel(
+    const float* __restrict__ boxes, int box_classes, const float* __restrict__ scores, int K, int C,
+    float score_thr, int* __restrict__ cand_k, int* __restrict__ ws_n, float* __restrict__ ws_f) {
+    __shared__ int s_warp[kNmsThreads / 32];
+    __shared__ int s_base;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0;
+    float mx = -INFINITY;
+    __syncthreads();
+    for (int k0 = 0; k0 < K; k0 += kNmsThreads) {
+        const int k = k0 + tid;
+        const bool ok = k < K && scores[(size_t)k * (C + 1) + c] > score_thr;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; ++w) off += s_warp[w];
+        if (ok) {
+            cand_k[(size_t)c * K + off + __popc(m & ((1u << lane) - 1u))] = k;
+            const float4 b = *reinterpret_cast<const float4*>(
+                boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+            mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < kNmsThreads / 32; ++w) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0 && mx > -INFINITY) atomic_max_float(ws_f, mx);
+    if (tid == 0) ws_n[c] = s_base;
+}
+
+// mmcv nms IoU (offset 0) on the shifted boxes, plain IEEE fp32 operations in that order
+__device__ __forceinline__ float nms_iou(const float4 a, const float4 b) {
+    const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+    const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+    const float w = fmaxf(__fsub_rn(right, left), 0.f), h = fmaxf(__fsub_rn(bottom, top), 0.f);
+    const float inter = __fmul_rn(w, h);
+    const float sa = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+    const float sb = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
+}
+
+// one CTA per class: order by (score desc, k asc) by rank counting, greedy suppression, survivors
+// (still in that order) to kept_k / kept_score
+__global__ void __launch_bounds__(kNmsThreads) nms_class_kernel(
+    const float* __restrict__ boxes, int box_classes, const float* __restrict__ scores, int K, int C,
+    float iou_thr, const int* __restrict__ cand_k, int* __restrict__ ws_n,
+    const float* __restrict__ ws_f, int* __restrict__ kept_k, float* __restrict__ kept_score) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    const int n = ws_n[c];
+    if (n == 0) return;
+    float4* s_box = reinterpret_cast<float4*>(smem);                 // [n] sorted, shifted
+    float* s_score = reinterpret_cast<float*>(s_box + K);            // [n] sorted
+    int* s_k = reinterpret_cast<int*>(s_score + K);                  // [n] sorted
+    float* u_score = reinterpret_cast<float*>(s_k + K);              // [n] unsorted
+    unsigned char* s_supp = reinterpret_cast<unsigned char*>(u_score + K);
+    __shared__ int s_cnt;
+    const float shift = __fmul_rn((float)c, __fadd_rn(ws_f[0], 1.f));       // idxs * (max + 1)
+    const int* ck = cand_k + (size_t)c * K;
+    for (int j = tid; j < n; j += kNmsThreads) u_score[j] = scores[(size_t)ck[j] * (C + 1) + c];
+    __syncthreads();
+    for (int j = tid; j < n; j += kNmsThreads) {
+        const float sj = u_score[j];
+        int rank = 0;
+        for (int i = 0; i < n; ++i) {
+            const float si = u_score[i];
+            rank += (si > sj) || (si == sj && i < j);            // candidates are in ascending k
+        }
+        const int k = ck[j];
+        const float4 b = *reinterpret_cast<const float4*>(
+            boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+        s_box[rank] = make_float4(__fadd_rn(b.x, shift), __fadd_rn(b.y, shift),
+                                  __fadd_rn(b.z, shift), __fadd_rn(b.w, shift));
+        s_score[rank] = sj;
+        s_k[rank] = k;
+        s_supp[rank] = 0;
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = 0; i < n; ++i) {
+        if (!s_supp[i]) {                                          // uniform: read after the barrier
+            const float4 bi = s_box[i];
+            for (int j = i + 1 + tid; j < n; j += kNmsThreads)
+                if (!s_supp[j] && nms_iou(bi, s_box[j]) > iou_thr) s_supp[j] = 1;
+        }
+        __syncthreads();
+    }
+    // compact the survivors in order (single warp; n is small)
+    if (tid < 32) {
+        int base = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + tid;
+            const bool keep = j < n && !s_supp[j];
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int r = base + __popc(m & ((1u << tid) - 1u));
+                kept_k[(size_t)c * K + r] = s_k[j];
+                kept_score[(size_t)c * K + r] = s_score[j];
+            }
+            base += __popc(m);
+        }
+        if (tid == 0) ws_n[C + c] = base;
+    }
+}
+
+// every survivor finds its global rank by (score desc, k * C + c asc); ranks < max_num are written
+__global__ void __launch_bounds__(kNmsThreads) nms_merge_kernel(
+    const float* __restrict__ boxes, int box_classes, int K, int C, const int* __restrict__ ws_n,
+    const int* __restrict__ kept_k, const float* __restrict__ kept_score, int max_num,
+    float* __restrict__ det, long long* __restrict__ labels, int* __restrict__ count) {
+    const int c = blockIdx.y;
+    const int n = ws_n[C + c];
+    if (blockIdx.x == 0 && c == 0 && threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < C; ++i) t += ws_n[C + i];
+        count[0] = min(t, max_num);
+    }
+    for (int r = blockIdx.x * kNmsThreads + threadIdx.x; r < n; r += gridDim.x * kNmsThreads) {
+        const float s = kept_score[(size_t)c * K + r];
+        const int k = kept_k[(size_t)c * K + r];
+        const long long flat = (long long)k * C + c;
+        int rank = 0;
+        for (int c2 = 0; c2 < C && rank < max_num; ++c2) {
+            const int n2 = ws_n[C + c2];
+            const float* ks = kept_score + (size_t)c2 * K;
+            const int* kk = kept_k + (size_t)c2 * K;
+            for (int i = 0; i < n2; ++i) {                        // a class's survivors are sorted:
+                const float s2 = ks[i];                           // stop at the first worse one
+                if (s2 > s || (s2 == s && (long long)kk[i] * C + c2 < flat)) ++rank;
+                else if (s2 < s) break;
+            }
+        }
+        if (rank < max_num) {
+            const float4 b = *reinterpret_cast<const float4*>(
+                boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+            float* o = det + (size_t)rank * 5;
+            o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = s;
+            labels[rank] = c;
+        }
+    }
+}
+
+}  // namespace htd
+
+using namespace htd;
+
+extern "C" {
+
+long long htd_multiclass_nms_workspace_bytes(int K, int C) {
+    // cand_k, kept_k (int), kept_score (float): [C, K] each; counters [2C] ints; 1 float (16 B slot)
+    return (long long)C * K * 12 + (long long)C * 8 + 16;
+}
+
+int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores, int K, int C,
+                       float score_thr, float iou_thr, int max_num, float* det, long long* labels,
+                       int32_t* count, void* workspace, htd_stream_t stream) {
+    HTD_CHECK_ARG(K >= 0 && K <= HTD_NMS_MAX_ROIS && C >= 1 && C <= HTD_NMS_MAX_CLASSES &&
+                      (box_classes == 1 || box_classes == C) && max_num >= 1 && score_thr >= 0.f,
+                  "htd_multiclass_nms: bad arguments K=%d (<= %d) C=%d (<= %d) box_classes=%d "
+                  "max_num=%d score_thr=%g (>= 0)", K, HTD_NMS_MAX_ROIS, C, HTD_NMS_MAX_CLASSES,
+                  box_classes, max_num, (double)score_thr);
+    HTD_CHECK_ARG(det && labels && count && workspace && (K == 0 || (boxes && scores)),
+                  "htd_multiclass_nms: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* w = static_cast<char*>(workspace);
+    float* ws_f = reinterpret_cast<float*>(w);
+    int* ws_n = reinterpret_cast<int*>(w + 16);
+    int* cand_k = ws_n + 2 * C;
+    int* kept_k = cand_k + (size_t)C * K;
+    float* kept_score = reinterpret_cast<float*>(kept_k + (size_t)C * K);
+    nms_init_kernel<<<1, 256, 0, st>>>(ws_f, ws_n, C);
+    HTD_CHECK_LAUNCH("htd_multiclass_nms(init)");
+    if (K > 0) {
+        nms_collect_kernel<<<C, kNmsThreads, 0, st>>>(boxes, box_classes, scores, K, C, score_thr,
+                                                      cand_k, ws_n, ws_f);
+        HTD_CHECK_LAUNCH("htd_multiclass_nms(collect)");
+        const size_t smem = (size_t)K * (16 + 4 + 4 + 4 + 1);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 HTD_NMS_MAX_ROIS * 29);
+            attr_done = true;
+        }
+        nms_class_kernel<<<C, kNmsThreads, smem, st>>>(boxes, box_classes, scores, K, C, iou_thr,
+                                                       cand_k, ws_n, ws_f, kept_k, kept_score);
+        HTD_CHECK_LAUNCH("htd_multiclass_nms(class)");
+    }
+    const int bx = K > 0 ? (K + kNmsThreads - 1) / kNmsThreads : 1;
+    nms_merge_kernel<<<dim3(bx, C), kNmsThreads, 0, st>>>(boxes, box_classes, K, C, ws_n, kept_k,
+                                                          kept_score, max_num, det, labels, count);
+    HTD_CHECK_LAUNCH("htd_multiclass_nms(merge)");
+    return HTD_OK;
+}
+
+}  // extern "C"

@@ -682,3 +682,27 @@ def assign_sample(props, gt_boxes, gt_labels, num_gt, keys, valid=None, pos_iou_
                                   ptr(s.counts), ptr(s.gt_inds), ptr(s.max_overlaps), stream()),
           'htd_assign_sample')
     return s
+
+
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num):
+    """multiclass_nms (core/post_processing/bbox_nms.py:7-71) with hard NMS on the device, no host
+    sync: returns det [max_num,5], labels [max_num] (int64) and count [1] (int32, device); rows
+    >= count are unspecified.  multi_bboxes [K,4] or [K,C*4], multi_scores [K,C+1]."""
+    _lib.require_cuda(multi_bboxes, multi_scores)
+    K, C1 = multi_scores.shape
+    C = C1 - 1
+    bc = multi_bboxes.shape[1] // 4
+    assert bc in (1, C), multi_bboxes.shape
+    dev = multi_scores.device
+    boxes = multi_bboxes.detach().float().contiguous()
+    scores = multi_scores.detach().float().contiguous()
+    max_num = int(max_num) if max_num > 0 else max(K * C, 1)
+    det = torch.empty((max_num, 5), dtype=torch.float32, device=dev)
+    labels = torch.empty(max_num, dtype=torch.long, device=dev)
+    count = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(lib().htd_multiclass_nms_workspace_bytes(K, C)), dtype=torch.uint8,
+                     device=dev)
+    check(lib().htd_multiclass_nms(ptr(boxes), bc, ptr(scores), K, C, float(score_thr),
+                                   float(iou_thr), max_num, ptr(det), ptr(labels), ptr(count),
+                                   ptr(ws), stream()), 'htd_multiclass_nms')
+    return det, labels, count

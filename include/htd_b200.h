@@ -338,6 +338,24 @@ int htd_assign_sample(const float* props, const unsigned char* valid, int B, int
                       float* max_overlaps, htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Multi-class NMS of the test branch: multiclass_nms
+ * (core/post_processing/bbox_nms.py:7-71, called from BBoxHead.get_bboxes, bbox_heads/
+ * bbox_head.py:188-225) on top of mmcv.ops.batched_nms / nms (mmcv-full 1.2.1, un-vendored).
+ *   boxes [K,4] (box_classes == 1, class-agnostic regression) or [K,C,4] (box_classes == C);
+ *   scores [K,C+1], last column = background (ignored).  Candidates are the (k, c) with
+ *   score > score_thr; their boxes are shifted by c * (max candidate coordinate + 1) in fp32 as
+ *   batched_nms does; greedy suppression in descending score order when IoU > iou_thr; output =
+ *   the survivors in descending score order (ties: ascending k*C + c), the first max_num.
+ *   det [max_num,5] (x1,y1,x2,y2,score) and labels [max_num] are written for rows < count[0];
+ *   workspace: htd_multiclass_nms_workspace_bytes(K, C) bytes.  No host sync, three launches. */
+#define HTD_NMS_MAX_ROIS 4096
+#define HTD_NMS_MAX_CLASSES 1024
+long long htd_multiclass_nms_workspace_bytes(int K, int C);
+int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores, int K, int C,
+                       float score_thr, float iou_thr, int max_num, float* det, long long* labels,
+                       int32_t* count, void* workspace, htd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
  * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and
  * (C / G) % 8 == 0; gamma / beta fp32; mean / rstd [N*G]: fp32 for HTD_BF16 tensors, fp64 for

@@ -387,3 +387,44 @@ def run_train_assigned(train_fn, head, dtype=torch.float32, device='cpu', n_prop
             out[f'assigned.s{st}.npos{b}'] = torch.tensor([r.pos_bboxes.size(0)], dtype=torch.int32)
     out['assigned.refined'] = torch.cat(info['refined']).cpu()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-class NMS cases
+# ---------------------------------------------------------------------------------------------
+NMS_CASES = {
+    # configs/htd/htd_resnet50_1x.py:164-168: 1000 RoIs, 80 classes, class-agnostic boxes
+    'htd': dict(K=1000, C=80, per_class=False, score_thr=0.05, iou_thr=0.5, max_num=100, seed=41,
+                dup=0.5, temp=3.0),
+    'perclass': dict(K=300, C=20, per_class=True, score_thr=0.05, iou_thr=0.5, max_num=100, seed=42,
+                     dup=0.4, temp=2.5),
+    'dense_all': dict(K=400, C=6, per_class=False, score_thr=0.01, iou_thr=0.3, max_num=-1, seed=43,
+                      dup=0.9, temp=1.0),
+    'empty': dict(K=64, C=80, per_class=False, score_thr=0.9, iou_thr=0.5, max_num=100, seed=44,
+                  dup=0.0, temp=0.1),
+    'ties': dict(K=500, C=10, per_class=False, score_thr=0.05, iou_thr=0.5, max_num=200, seed=45,
+                 dup=0.6, temp=2.0, quant=32),
+}
+
+
+def nms_case_inputs(name):
+    """(multi_bboxes [K,4] or [K,C*4], multi_scores [K,C+1]) on the CPU + the case dict."""
+    c = NMS_CASES[name]
+    g = torch.Generator().manual_seed(c['seed'])
+    K, C = c['K'], c['C']
+    ctr = torch.rand(K, 2, generator=g) * torch.tensor([1333.0, 800.0])
+    wh = torch.exp(torch.rand(K, 2, generator=g) * 2.5 + 3.0)
+    boxes = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+    nd = int(K * c['dup'])
+    if nd:                                             # clusters of near-duplicates
+        src = boxes[torch.randint(0, K - nd, (nd,), generator=g)]
+        boxes[K - nd:] = src + torch.randn(nd, 4, generator=g) * 0.06 * (src[:, 2:] - src[:, :2]).repeat(1, 2)
+    lim = torch.tensor([1333.0, 800.0, 1333.0, 800.0])
+    boxes = torch.min(boxes.clamp(min=0), lim)
+    scores = torch.softmax(torch.randn(K, C + 1, generator=g) * c['temp'], 1)
+    if c.get('quant'):
+        scores = torch.floor(scores * c['quant']) / c['quant']
+    if c['per_class']:
+        boxes = (boxes[:, None, :] + torch.randn(K, C, 4, generator=g) * 2.0).reshape(K, C * 4)
+        boxes = torch.min(boxes.clamp(min=0), lim.repeat(C))
+    return boxes, scores, c

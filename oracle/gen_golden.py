@@ -63,9 +63,26 @@ def gen_assign_sample():
           {k: float(v) for k, v in outs.items() if v.numel() == 1 and v.is_floating_point()})
 
 
+def gen_nms():
+    """tests/golden/nms.npz: the reference's own multiclass_nms (bbox_nms.py:7-71; its mmcv
+    batched_nms realised by torchvision.ops.nms in oracle/refshim.py) on oracle/cases.NMS_CASES."""
+    ns = refshim.load()
+    flat = {}
+    for name in cases.NMS_CASES:
+        boxes, scores, c = cases.nms_case_inputs(name)
+        dets, labels = ns.multiclass_nms(boxes, scores, c['score_thr'],
+                                         dict(type='nms', iou_threshold=c['iou_thr']), c['max_num'])
+        flat[f'{name}|dets'] = dets.numpy()
+        flat[f'{name}|labels'] = labels.numpy()
+        print('nms', name, tuple(dets.shape))
+    np.savez_compressed(os.path.join(OUT, 'nms.npz'), **flat)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'assign':
         return gen_assign_sample()
+    if len(sys.argv) > 1 and sys.argv[1] == 'nms':
+        return gen_nms()
     os.makedirs(OUT, exist_ok=True)
     ns = refshim.load()
     torch.set_num_threads(os.cpu_count())
@@ -106,6 +123,7 @@ def main():
             print(name, tag, len(outs), 'tensors ->', path, os.path.getsize(path) // 1024, 'KiB',
                   {k: float(v) for k, v in outs.items() if k.startswith('train.') and v.numel() == 1})
     gen_assign_sample()
+    gen_nms()
 
 
 if __name__ == '__main__':

@@ -147,6 +147,21 @@ class _RoIAlign(nn.Module):
 _LOADED = None
 
 
+def _batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    """mmcv.ops.nms.batched_nms of mmcv-full 1.2.1 for type='nms' below split_thr: coordinate
+    shift per class, then the nms op - here torchvision.ops.nms, the same greedy algorithm."""
+    from torchvision.ops import nms
+    cfg = dict(nms_cfg)
+    assert cfg.pop('type', 'nms') == 'nms'
+    thr = cfg.get('iou_threshold', cfg.get('iou_thr'))
+    if class_agnostic:
+        b = boxes
+    else:
+        b = boxes + (idxs.to(boxes) * (boxes.max() + 1))[:, None]
+    keep = nms(b, scores, thr)
+    return torch.cat([boxes[keep], scores[keep, None]], -1), keep
+
+
 def load():
     """Import the reference modules; returns a namespace of the classes/functions used."""
     global _LOADED
@@ -155,8 +170,9 @@ def load():
     if not available():
         raise RuntimeError(f'reference tree not found at {REF}')
     mmcv = _mod('mmcv', path='/nonexistent', __version__='1.2.1')
-    _mod('mmcv.ops', RoIAlign=_RoIAlign)
+    _mod('mmcv.ops', path='/nonexistent', RoIAlign=_RoIAlign)
     mmcv.ops = sys.modules['mmcv.ops']
+    _mod('mmcv.ops.nms', batched_nms=_batched_nms)
     _mod('mmcv.cnn', path='/nonexistent', ConvModule=_ConvModule, normal_init=_normal_init,
          xavier_init=_xavier_init)
     _mod('mmcv.cnn.bricks', ConvModule=_ConvModule, build_plugin_layer=None)
@@ -200,7 +216,8 @@ def load():
     core.build_bbox_coder = bb.build_bbox_coder
     core.build_assigner = bb.build_assigner
     core.build_sampler = bb.build_sampler
-    core.multiclass_nms = None
+    pp = imp('mmdet.core.post_processing.bbox_nms')
+    core.multiclass_nms = pp.multiclass_nms
     core.merge_aug_bboxes = None
     core.merge_aug_masks = None
     sys.modules['mmdet.core.bbox'].demodata = imp('mmdet.core.bbox.demodata')
@@ -237,7 +254,8 @@ def load():
         delta2bbox=coder.delta2bbox, bbox2delta=coder.bbox2delta,
         DeltaXYWHBBoxCoder=coder.DeltaXYWHBBoxCoder, MaxIoUAssigner=mia.MaxIoUAssigner,
         RandomSampler=rs.RandomSampler, SamplingResult=sr.SamplingResult,
-        AssignResult=ar.AssignResult, CrossEntropyLoss=ce.CrossEntropyLoss,
+        AssignResult=ar.AssignResult, multiclass_nms=pp.multiclass_nms,
+        CrossEntropyLoss=ce.CrossEntropyLoss,
         SmoothL1Loss=sl1.SmoothL1Loss, accuracy=acc.accuracy, RoIAlign=_RoIAlign)
     _LOADED = ns
     return ns

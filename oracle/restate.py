@@ -475,6 +475,61 @@ class HTDBBoxHead(BBoxHeadBase):
 
 
 # --------------------------------------------------------------------------------------
+# multi-class NMS - checker of csrc/nms.cu
+# --------------------------------------------------------------------------------------
+def nms_greedy(boxes, scores, iou_thr):
+    """mmcv.ops.nms (mmcv-full 1.2.1, un-vendored; the same published algorithm as
+    torchvision.ops.nms, against which tests/test_oracle_cpu.py pins this function): visit boxes
+    in descending score order (stable: ties keep index order), keep a box unless an earlier kept
+    box has IoU > iou_thr with it; IoU = inter / (Sa + Sb - inter), fp32, offset 0.  Returns the
+    kept indices in visiting order."""
+    b = boxes.detach().float().cpu().numpy()
+    order = torch.argsort(scores.detach().float().cpu(), descending=True, stable=True).numpy()
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    supp = np.zeros(len(b), dtype=bool)
+    keep = []
+    for pos, i in enumerate(order):
+        if supp[i]:
+            continue
+        keep.append(int(i))
+        rest = order[pos + 1:]
+        w = np.maximum(np.minimum(b[i, 2], b[rest, 2]) - np.maximum(b[i, 0], b[rest, 0]),
+                       np.float32(0))
+        h = np.maximum(np.minimum(b[i, 3], b[rest, 3]) - np.maximum(b[i, 1], b[rest, 1]),
+                       np.float32(0))
+        inter = w * h
+        with np.errstate(divide='ignore', invalid='ignore'):
+            iou = inter / (area[i] + area[rest] - inter)
+        supp[rest[iou > np.float32(iou_thr)]] = True
+    return torch.tensor(keep, dtype=torch.long)
+
+
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num=-1):
+    """core/post_processing/bbox_nms.py:7-71 with nms_cfg = dict(type='nms', iou_threshold=...)
+    and mmcv's batched_nms (class_agnostic=False, fewer than split_thr boxes): shift the boxes of
+    class c by c * (max coordinate + 1), one NMS over all of them, ``dets`` in descending score
+    order, first ``max_num``.  Returns (dets [n,5], labels [n])."""
+    num_classes = multi_scores.size(1) - 1
+    if multi_bboxes.shape[1] > 4:
+        bboxes = multi_bboxes.view(multi_scores.size(0), -1, 4)
+    else:
+        bboxes = multi_bboxes[:, None].expand(multi_scores.size(0), num_classes, 4)
+    scores = multi_scores[:, :-1]
+    valid = scores > score_thr
+    bboxes = bboxes[valid]
+    scores = scores[valid]
+    labels = valid.nonzero(as_tuple=False)[:, 1]
+    if bboxes.numel() == 0:
+        return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
+    max_coordinate = bboxes.max()
+    offsets = labels.to(bboxes) * (max_coordinate + 1)
+    keep = nms_greedy(bboxes + offsets[:, None], scores, iou_thr)
+    if max_num > 0:
+        keep = keep[:max_num]
+    return torch.cat([bboxes[keep], scores[keep, None]], -1), labels[keep]
+
+
+# --------------------------------------------------------------------------------------
 # assign + sample (SURVEY §8 f2) - checker of csrc/assign_sample.cu
 # --------------------------------------------------------------------------------------
 def max_iou_assign(bboxes, gt_bboxes, gt_labels, pos_iou_thr, neg_iou_thr, min_pos_iou=0.,

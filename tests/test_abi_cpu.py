@@ -32,7 +32,8 @@ def test_python_binding_covers_the_header():
     from htd_b200 import _lib
     missing = set(_declared()) - set(_lib.SIGNATURES) - {'htd_abi_version', 'htd_last_error',
                                                              'htd_roi_plan_rows_bound',
-                                                             'htd_pgraph_max_tiles'}
+                                                             'htd_pgraph_max_tiles',
+                                                             'htd_multiclass_nms_workspace_bytes'}
     assert not missing, missing
 
 

@@ -1,0 +1,62 @@
+"""GPU parity tests (through the C-ABI) of the multi-class NMS kernels (SURVEY §8 f3,
+csrc/nms.cu): the detections and their order must equal, bit for bit, the fixture written by the
+reference's own multiclass_nms (tests/golden/nms.npz) and the CPU restatement."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from htd_b200 import core, ops
+from oracle import cases, restate
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.mark.parametrize('name', list(cases.NMS_CASES))
+def test_multiclass_nms_matches_reference_golden(name):
+    z = np.load(os.path.join(GOLD, 'nms.npz'))
+    boxes, scores, c = cases.nms_case_inputs(name)
+    dets, labels = core.multiclass_nms(boxes.cuda(), scores.cuda(), c['score_thr'],
+                                       dict(type='nms', iou_threshold=c['iou_thr']), c['max_num'])
+    assert np.array_equal(dets.cpu().numpy(), z[f'{name}|dets']), name
+    assert np.array_equal(labels.cpu().numpy(), z[f'{name}|labels']), name
+
+
+def test_multiclass_nms_matches_restatement_random_sizes():
+    g = torch.Generator().manual_seed(7)
+    for K, C, per_class in ((1, 1, False), (37, 3, True), (1000, 80, False), (2048, 5, False)):
+        cases.NMS_CASES['_t'] = dict(K=K, C=C, per_class=per_class, score_thr=0.02, iou_thr=0.45,
+                                     max_num=150, seed=int(torch.randint(0, 1000, (1,), generator=g)),
+                                     dup=0.5, temp=2.0)
+        try:
+            boxes, scores, c = cases.nms_case_inputs('_t')
+        finally:
+            del cases.NMS_CASES['_t']
+        want_d, want_l = restate.multiclass_nms(boxes, scores, c['score_thr'], c['iou_thr'], c['max_num'])
+        det, lab, cnt = ops.multiclass_nms(boxes.cuda(), scores.cuda(), c['score_thr'], c['iou_thr'],
+                                           c['max_num'])
+        n = int(cnt)
+        assert n == want_d.size(0), (K, C, n, want_d.size(0))
+        assert torch.equal(det[:n].cpu(), want_d) and torch.equal(lab[:n].cpu(), want_l), (K, C)
+
+
+def test_simple_test_returns_reference_format_through_the_nms_kernel():
+    """HTDRoIHead.simple_test (htd_roi_head.py:319-386): per image a list of num_classes arrays
+    [n_c,5], at most max_per_img detections, scores descending within the NMS output."""
+    import htd_b200
+    from htd_b200 import synth
+    head = htd_b200.build_htd_roi_head().cuda()
+    head.init_weights()
+    head.eval()
+    H, W = 256, 320
+    x = [t.cuda() for t in synth.make_pyramid(2, H, W)]
+    props = [p.cuda() for p in synth.make_proposals(2, 200, H, W, min_scale=8, max_scale=300)]
+    metas = [dict(img_shape=(H, W, 3), scale_factor=1.0) for _ in props]
+    with torch.no_grad():
+        res = head.simple_test(x, props, metas)
+    assert len(res) == 2
+    for per_img in res:
+        assert len(per_img) == 80 and all(a.shape[1] == 5 for a in per_img)
+        assert sum(a.shape[0] for a in per_img) <= 100

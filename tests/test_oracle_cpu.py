@@ -225,3 +225,25 @@ def test_restated_forward_train_with_assigner_equals_reference_live():
             assert cases.rel_err(b[k], a[k]) <= 1e-6, k
         else:
             assert torch.equal(a[k], b[k]), k
+
+
+# ---- multi-class NMS ----------------------------------------------------------------
+@pytest.mark.parametrize('name', list(cases.NMS_CASES))
+def test_nms_restatement_matches_reference_golden(name):
+    """restate.multiclass_nms == the reference's multiclass_nms (tests/golden/nms.npz): the same
+    detections in the same order, boxes and scores bit for bit."""
+    z = np.load(os.path.join(GOLD, 'nms.npz'))
+    boxes, scores, c = cases.nms_case_inputs(name)
+    dets, labels = restate.multiclass_nms(boxes, scores, c['score_thr'], c['iou_thr'], c['max_num'])
+    assert np.array_equal(dets.numpy(), z[f'{name}|dets']) and \
+        np.array_equal(labels.numpy(), z[f'{name}|labels'])
+
+
+def test_nms_restatement_equals_torchvision_nms():
+    """The greedy NMS of the restatement against the library implementation of the same published
+    algorithm (torchvision.ops.nms, CPU) on clustered boxes."""
+    from torchvision.ops import nms
+    boxes, scores, c = cases.nms_case_inputs('htd')
+    s = scores[:, 3] + torch.arange(scores.size(0)) * 1e-7
+    for thr in (0.3, 0.5, 0.7):
+        assert torch.equal(restate.nms_greedy(boxes, s, thr), nms(boxes, s, thr))
