@@ -422,6 +422,35 @@ def run_gpu(args):
             print(f'[bench] channels-last pyramid step failed ({type(e).__name__}: {e})',
                   file=sys.stderr)
 
+    # ---- inference: 1 image x 1000 proposals, both stages + decode + NMS ----
+    infer = None
+    if world == 1 and not args.no_static:
+        try:
+            head.eval()
+            ip = [synth.make_proposals(1, 1000, IMG_H, IMG_W, seed=999)[0].to(dev)]
+            ix = [t[:1].detach() for t in x_dev]
+            imeta = [dict(img_shape=shapes[0], scale_factor=1.0)]
+            with torch.no_grad():
+                for _ in range(3):
+                    head.simple_test(ix, ip, imeta)
+                torch.cuda.synchronize()
+                i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                nrep = min(args.steps, 20)
+                i0.record()
+                for _ in range(nrep):
+                    head.simple_test(ix, ip, imeta)
+                i1.record()
+                torch.cuda.synchronize()
+            ims = i0.elapsed_time(i1) / nrep
+            infer = dict(what='HTDRoIHead.simple_test, 1 image x 1000 proposals: SFA, both stages (BA on '
+                              'all 1000 RoIs, PGraph), decode, multi-class NMS (htd_multiclass_nms), '
+                              'results to numpy; eager', ms_per_image=ims,
+                         rois_per_s=1000 / (ims * 1e-3))
+            head.train()
+        except Exception as e:
+            head.train()
+            print(f'[bench] inference figure failed ({type(e).__name__}: {e})', file=sys.stderr)
+
     # ---- max over ranks ------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -486,6 +515,7 @@ def run_gpu(args):
                             eager_ms_per_step=ms_eager,
                             full_step_with_sampling=static,
                             channels_last_bf16_pyramid=nhwc,
+                            inference=infer,
                             kernel_timing='CUDA events around each own launch in an eager pass of '
                                           'the same step (events cannot be placed inside a graph)'),
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,
