@@ -87,6 +87,8 @@ SIGNATURES = {
                         c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_gn_relu_bwd': [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                         c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'htd_relu_mean_fwd': [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    'htd_relu_mean_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     'htd_pgraph_plan': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                         c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_pgraph_pack': [c_void_p, c_int, c_ll, c_void_p, c_int, c_ll, c_void_p, c_int, c_int,

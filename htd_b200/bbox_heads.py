@@ -415,11 +415,13 @@ class HTDBBoxHead(BBoxHead):
         return (rois[:, :1] == b[None, :]).to(dtype)
 
     def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
-                global_feat=None, num_imgs=None, max_rois_per_img=None, row_valid=None):
+                global_feat=None, num_imgs=None, max_rois_per_img=None, row_valid=None,
+                x_cls_flat=None):
         """Reference signature (htd_bbox_head.py:157).  ``num_imgs`` (optional) avoids the host
         sync of ``int(max(rois[:,0])) + 1`` (:159); ``global_feat`` gives it otherwise.
         ``max_rois_per_img`` (optional) bounds the PGraph group size (default: all RoIs);
-        ``row_valid`` ([K] bool, optional) keeps pad rows of the static sampler out of the graph."""
+        ``row_valid`` ([K] bool, optional) keeps pad rows of the static sampler out of the graph;
+        ``x_cls_flat`` (optional) is ``x_cls`` already flattened (``ops.flatten_with_prefix``)."""
         if num_imgs is None:
             num_imgs = global_feat.size(0) if global_feat is not None \
                 else int(torch.max(rois[..., 0])) + 1
@@ -430,13 +432,22 @@ class HTDBBoxHead(BBoxHead):
             g = global_feat.reshape(global_feat.size(0), -1)
             x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
         x_reg = x_reg + self.alpha * enhanced_feat
-        x_reg = self.convs(x_reg.contiguous(memory_format=torch.channels_last))
-        x_reg = x_reg.mean((2, 3))            # AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:188-189)
+        x_reg = x_reg.contiguous(memory_format=torch.channels_last)
+        last = self.convs[-1] if len(self.convs) else None
+        if last is not None and last.gn is None and last.with_act and x_reg.is_cuda and \
+                ConvModule.fused_gn and last.conv.out_channels % 8 == 0:
+            for m in self.convs[:-1]:
+                x_reg = m(x_reg)
+            # last conv -> ReLU -> AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:109-113,188-189):
+            # activation and pool in one pass over the largest activation of the head
+            x_reg = ops.relu_mean_pool(last.conv(x_reg))
+        else:
+            x_reg = self.convs(x_reg).mean((2, 3))
         # ---- cls branch: fcs on x_cls and on x_cls + SFA.  fcs.0 is linear, so
         # fcs.0(x + g (x) 1_49) = fcs.0(x) + g W_sum^T with W_sum = sum of W over the 49 bins:
         # one [K,12544]x[12544,1024] GEMM instead of the reference's two (:164 and :192).
         fc0, fc1 = self.fcs[0], self.fcs[2]
-        pre = fc0(ops.flatten_roi_feats(x_cls))
+        pre = fc0(x_cls_flat if x_cls_flat is not None else ops.flatten_roi_feats(x_cls))
         x_c = F.relu(fc1(F.relu(pre)))
         x_glb = None
         if global_feat is not None:

@@ -220,6 +220,66 @@ __global__ void __launch_bounds__(256) gn_param_reduce_kernel(const float* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// ReLU + global average pool of the last tower conv (htd_bbox_head.py:109-113 ConvModule without a
+// norm layer, then avg_pool :188-189): y[n,c] = mean_hw relu(x[n,hw,c]) in one pass, and its
+// backward dx[n,hw,c] = x > 0 ? g[n,c] / HW : 0 in one pass (ATen: relu, mean, expand/div,
+// threshold_backward - four passes over the largest activation of the head).
+// One thread per (n, 8-channel chunk); consecutive threads read consecutive 16 / 32 bytes.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) relu_mean_fwd_kernel(const T* __restrict__ x, int N, int HW,
+                                                            int C, T* __restrict__ y) {
+    const int chunks = C / 8;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)N * chunks) return;
+    const int n = (int)(i / chunks), c0 = (int)(i % chunks) * 8;
+    const T* px = x + (size_t)n * HW * C + c0;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int hw = 0; hw < HW; ++hw) {
+        float v[8];
+        ld8<T>(px + (size_t)hw * C, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += fmaxf(v[e], 0.f);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = acc[e] / (float)HW;
+    st8<T>(y + (size_t)n * C + c0, acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) relu_mean_bwd_kernel(const T* __restrict__ x,
+                                                            const T* __restrict__ g, int N, int HW,
+                                                            int C, T* __restrict__ dx) {
+    const int chunks = C / 8;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)N * chunks) return;
+    const int n = (int)(i / chunks), c0 = (int)(i % chunks) * 8;
+    float gv[8];
+    ld8<T>(g + (size_t)n * C + c0, gv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gv[e] = gv[e] / (float)HW;
+    if (sizeof(T) == 2) {               // ATen rounds the expanded gradient to the tensor dtype
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t[e] = __bfloat162float(__float2bfloat16_rn(gv[e]));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gv[e] = t[e];
+    }
+    const T* px = x + (size_t)n * HW * C + c0;
+    T* pd = dx + (size_t)n * HW * C + c0;
+    for (int hw = 0; hw < HW; ++hw) {
+        float v[8], o[8];
+        ld8<T>(px + (size_t)hw * C, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = v[e] > 0.f ? gv[e] : 0.f;
+        st8<T>(pd + (size_t)hw * C, o);
+    }
+}
+
 static bool gn_args_ok(int N, int HW, int C, int G) {
     return N >= 0 && HW >= 1 && C >= 8 && G >= 1 && C % G == 0 && (C / G) % 8 == 0;
 }
@@ -284,6 +344,47 @@ int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, 
     }
     gn_param_reduce_kernel<<<dim3((C + 31) / 32, 2), 256, 0, st>>>(part, N, C, dgamma, dbeta);
     HTD_CHECK_LAUNCH("htd_gn_relu_bwd(params)");
+    return HTD_OK;
+}
+
+int htd_relu_mean_fwd(const void* x, int dtype, int N, int HW, int C, void* y, htd_stream_t stream) {
+    HTD_CHECK_ARG(N >= 0 && HW >= 1 && C >= 8 && C % 8 == 0, "htd_relu_mean_fwd: need C %% 8 == 0 "
+                  "(N=%d HW=%d C=%d)", N, HW, C);
+    HTD_CHECK_ARG(dtype == HTD_F32 || dtype == HTD_BF16, "htd_relu_mean_fwd: bad dtype");
+    if (N == 0) return HTD_OK;
+    HTD_CHECK_ARG(x && y, "htd_relu_mean_fwd: null pointer");
+    const long long items = (long long)N * (C / 8);
+    const unsigned blocks = (unsigned)((items + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == HTD_F32)
+        relu_mean_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), N, HW, C,
+                                                            static_cast<float*>(y));
+    else
+        relu_mean_fwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), N, HW, C, static_cast<__nv_bfloat16*>(y));
+    HTD_CHECK_LAUNCH("htd_relu_mean_fwd");
+    return HTD_OK;
+}
+
+int htd_relu_mean_bwd(const void* x, const void* g, int dtype, int N, int HW, int C, void* dx,
+                      htd_stream_t stream) {
+    HTD_CHECK_ARG(N >= 0 && HW >= 1 && C >= 8 && C % 8 == 0, "htd_relu_mean_bwd: need C %% 8 == 0 "
+                  "(N=%d HW=%d C=%d)", N, HW, C);
+    HTD_CHECK_ARG(dtype == HTD_F32 || dtype == HTD_BF16, "htd_relu_mean_bwd: bad dtype");
+    if (N == 0) return HTD_OK;
+    HTD_CHECK_ARG(x && g && dx, "htd_relu_mean_bwd: null pointer");
+    const long long items = (long long)N * (C / 8);
+    const unsigned blocks = (unsigned)((items + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == HTD_F32)
+        relu_mean_bwd_kernel<float><<<blocks, 256, 0, st>>>(
+            static_cast<const float*>(x), static_cast<const float*>(g), N, HW, C,
+            static_cast<float*>(dx));
+    else
+        relu_mean_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(g), N, HW, C,
+            static_cast<__nv_bfloat16*>(dx));
+    HTD_CHECK_LAUNCH("htd_relu_mean_bwd");
     return HTD_OK;
 }
 

@@ -82,6 +82,46 @@ class _FlattenRoIFeats(torch.autograd.Function):
         return out.permute(0, 3, 1, 2)
 
 
+class _FlattenWithPrefix(torch.autograd.Function):
+    """(flatten_roi_feats(x), cat of the row spans of x) with ONE gradient tensor: the stage-1 head
+    reads the same RoI features twice - flattened for the cls branch and, as the positive prefix of
+    every image's block, for the reg branch (htd_roi_head.py:157-170).  Plain autograd answers
+    with two zero-filled full-size gradients (one per slice) and their additions; here the
+    flatten-backward tensor is the gradient and the spans are added into it in place."""
+
+    @staticmethod
+    def forward(ctx, x, spans):
+        K, C, P, Q = x.shape
+        flat = torch.empty((K, C * P * Q), dtype=x.dtype, device=x.device)
+        _convert(x, flat, K, P * Q, C)
+        pos = torch.cat([x[o:o + n] for o, n in spans], 0) if spans else x[:0]
+        ctx.shape, ctx.spans = (K, C, P, Q), tuple(spans)
+        return flat, pos
+
+    @staticmethod
+    def backward(ctx, g_flat, g_pos):
+        K, C, P, Q = ctx.shape
+        g_flat = g_flat.contiguous()
+        out = torch.empty((K, P, Q, C), dtype=g_flat.dtype, device=g_flat.device)
+        _convert(g_flat, out, K, C, P * Q)
+        out = out.permute(0, 3, 1, 2)
+        off = 0
+        for o, n in ctx.spans:
+            if n:
+                out[o:o + n] += g_pos[off:off + n].to(out.dtype)
+            off += n
+        return out, None
+
+
+def flatten_with_prefix(x, spans):
+    """x [K,C,P,P] channels-last RoI features, spans = [(first row, rows)] -> (x flattened in the
+    reference's c*PP+bin order [K, C*P*P], the span rows [sum rows, C, P, P])."""
+    _lib.require_cuda(x)
+    if not _is_cl(x):
+        x = x.contiguous(memory_format=torch.channels_last)
+    return _FlattenWithPrefix.apply(x, spans)
+
+
 def flatten_roi_feats(x):
     """``x.flatten(1)`` for RoI features; uses the transpose kernel when ``x`` is a CUDA
     channels-last tensor, plain flatten otherwise."""
@@ -529,6 +569,37 @@ class _GroupNormReLU(torch.autograd.Function):
 
 def group_norm_relu(x, weight, bias, groups, eps=1e-5):
     return _GroupNormReLU.apply(x, weight, bias, groups, eps)
+
+
+class _ReLUMeanPool(torch.autograd.Function):
+    """mean over (H, W) of relu(x) for a channels-last [N,C,H,W] tensor -> [N,C]: one pass forward,
+    one pass backward (csrc/gn_relu.cu) instead of relu / mean / expand-div / threshold_backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_cuda(x)
+        if not _is_cl(x):
+            x = x.contiguous(memory_format=torch.channels_last)
+        N, C, H, W = x.shape
+        y = torch.empty((N, C), dtype=x.dtype, device=x.device)
+        check(lib().htd_relu_mean_fwd(ptr(x), dt(x), N, H * W, C, ptr(y), stream()),
+              'htd_relu_mean_fwd')
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        N, C, H, W = x.shape
+        g = g.to(x.dtype).contiguous()
+        dx = torch.empty_like(x)
+        check(lib().htd_relu_mean_bwd(ptr(x), ptr(g), dt(x), N, H * W, C, ptr(dx), stream()),
+              'htd_relu_mean_bwd')
+        return dx
+
+
+def relu_mean_pool(x):
+    return _ReLUMeanPool.apply(x)
 
 
 # ------------------------------------------------------------------------------------------

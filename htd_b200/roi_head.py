@@ -119,11 +119,12 @@ class HTDRoIHead(nn.Module):
             for res in sampling_results:
                 spans.append((off, res.pos_bboxes.size(0), res.neg_bboxes.size(0)))
                 off += res.pos_bboxes.size(0) + res.neg_bboxes.size(0)
-            pos_feats = torch.cat([bbox_feats[o:o + npos] for o, npos, _ in spans], 0)
+            # one autograd node for both uses of bbox_feats (flattened cls input, positive rows)
+            flat, pos_feats = ops.flatten_with_prefix(bbox_feats, [(o, n_) for o, n_, _ in spans])
             cls_score, bbox_pred = head(bbox_feats, pos_feats, x_cl, rois, fc0, enhanced,
                                         pos_rois, g, num_imgs=nimg or len(sampling_results),
                                         max_rois_per_img=max(p_ + n_ for _, p_, n_ in spans),
-                                        row_valid=row_valid)
+                                        row_valid=row_valid, x_cls_flat=flat)
             parts, o2 = [], 0
             for _, npos, nneg in spans:
                 parts += [bbox_pred[o2:o2 + npos], bbox_pred.new_zeros(nneg, bbox_pred.size(1))]

@@ -370,6 +370,13 @@ int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, 
                     const float* gamma, const float* beta, int N, int HW, int C, int G, void* dx,
                     float* part, float* dgamma, float* dbeta, htd_stream_t stream);
 
+/* ReLU + global average pool of the last tower conv (ConvModule without norm, htd_bbox_head.py:
+ * 109-113, then avg_pool :188-189), channels-last x [N, HW, C], C % 8 == 0:
+ *   y[n,c] = mean_hw relu(x[n,hw,c]);   dx[n,hw,c] = x[n,hw,c] > 0 ? g[n,c] / HW : 0. */
+int htd_relu_mean_fwd(const void* x, int dtype, int N, int HW, int C, void* y, htd_stream_t stream);
+int htd_relu_mean_bwd(const void* x, const void* g, int dtype, int N, int HW, int C, void* dx,
+                      htd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Device-side scheduling of the PGraph contractions: no host read of the plan table, so the whole
  * head step can be captured in a CUDA graph.  htd_pgraph_schedule derives, from the plan table on
