@@ -60,6 +60,39 @@ class ConvModule(nn.Module):
         return F.relu(x, inplace=True) if self.with_act else x
 
 
+def _pad8(n):
+    return (-n) % 8
+
+
+def linear_aligned(m, x):
+    """``m(x)`` for an nn.Linear.  cuBLAS has no fast bf16 kernel for an output width that is not
+    a multiple of 8 elements (fc_cls: 81, fc_reg: 4 - rows of 162 / 8 bytes; it falls back to
+    sm_75-era kernels, 22 us for a 0.17 GFLOP product): the weight is zero-padded to the next
+    multiple of 8 rows and the result sliced.  Values are unchanged; fp32 runs the plain call."""
+    n = m.out_features
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and n % 8 and BBoxHead.aligned_small_fc):
+        return m(x)
+    w = F.pad(m.weight, (0, 0, 0, _pad8(n)))
+    b = F.pad(m.bias, (0, _pad8(n))) if m.bias is not None else None
+    return F.linear(x, w, b)[:, :n]
+
+
+def cls_reg_outputs(head, x):
+    """(fc_cls(x), fc_reg(x)) of a head whose two output layers read the same input: ONE GEMM
+    over the concatenated (and 8-aligned) weights in bf16, the plain calls otherwise."""
+    if not (head.with_cls and head.with_reg and x.is_cuda and x.dtype == torch.bfloat16
+            and BBoxHead.aligned_small_fc):
+        return (head.fc_cls(x) if head.with_cls else None, head.fc_reg(x) if head.with_reg else None)
+    nc, nr = head.fc_cls.out_features, head.fc_reg.out_features
+    pad = _pad8(nc + nr)
+    w = torch.cat([head.fc_cls.weight, head.fc_reg.weight], 0)
+    b = torch.cat([head.fc_cls.bias, head.fc_reg.bias], 0)
+    if pad:
+        w, b = F.pad(w, (0, 0, 0, pad)), F.pad(b, (0, pad))
+    out = F.linear(x, w, b)
+    return out[:, :nc], out[:, nc:nc + nr]
+
+
 @HEADS.register_module()
 class BBoxHead(nn.Module):
     """bbox_head.py:12-335."""
@@ -104,8 +137,7 @@ class BBoxHead(nn.Module):
         if self.with_avg_pool:
             x = self.avg_pool(x)
         x = x.reshape(x.size(0), -1)
-        return (self.fc_cls(x) if self.with_cls else None,
-                self.fc_reg(x) if self.with_reg else None)
+        return cls_reg_outputs(self, x)
 
     # ---- targets / loss (bbox_head.py:85-186) -------------------------------------------------
     def _get_target_single(self, pos_bboxes, neg_bboxes, pos_gt_bboxes, pos_gt_labels, cfg):
@@ -235,6 +267,7 @@ class BBoxHead(nn.Module):
                 and self.loss_cls.class_weight is None and self.fused_glue)
 
     fused_glue = True        # class switch (diagnostics): targets / loss / decode via csrc/rcnn_glue.cu
+    aligned_small_fc = True  # class switch (diagnostics): 8-aligned fc_cls / fc_reg GEMMs in bf16
     _pos_mask_cache = {}
 
     # ---- decoding (bbox_head.py:188-335) ------------------------------------------------------
@@ -339,8 +372,7 @@ class ConvFCBBoxHead(BBoxHead):
         x = ops.flatten_roi_feats(x)
         for fc in self.shared_fcs:
             x = F.relu(fc(x))
-        return (self.fc_cls(x) if self.with_cls else None,
-                self.fc_reg(x) if self.with_reg else None)
+        return cls_reg_outputs(self, x)
 
 
 @HEADS.register_module()
@@ -457,7 +489,7 @@ class HTDBBoxHead(BBoxHead):
             corr = F.linear(g49, fc0.weight)
             x_glb = F.relu(fc1(F.relu(pre + self._img_onehot(rois, g.size(0), corr.dtype) @ corr)))
         # ---- semantic vectors and the graph (:194-219)
-        sam = torch.mm(fc_cls_0(x_c).softmax(-1), prototype)
+        sam = torch.mm(linear_aligned(fc_cls_0, x_c).softmax(-1), prototype)
         with torch.no_grad():
             levels = ops.level_assign(rois, len(feat), self.finest_scale)
             if row_valid is not None:
@@ -469,8 +501,8 @@ class HTDBBoxHead(BBoxHead):
         refined = pgraph.pgraph_refine(x_c, sam, [m.weight for m in layers],
                                        [m.bias for m in layers], plan)
         feat_cls_new = (x_glb if x_glb is not None else x_c) + refined
-        cls_score = self.fc_cls(feat_cls_new) if self.with_cls else None
-        bbox_pred = self.fc_reg(x_reg) if self.with_reg else None
+        cls_score = linear_aligned(self.fc_cls, feat_cls_new) if self.with_cls else None
+        bbox_pred = linear_aligned(self.fc_reg, x_reg) if self.with_reg else None
         return cls_score, bbox_pred
 
 
