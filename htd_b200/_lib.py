@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libhtd_b200.so')
+LIB_PATH = os.environ.get('HTD_B200_LIB') or os.path.join(_HERE, '_lib', 'libhtd_b200.so')
 
 HTD_F32, HTD_BF16 = 0, 1
 MAX_LEVELS = 8

@@ -205,8 +205,14 @@ struct FwdParams {
 // kFwdStages-deep ring with cp.async.bulk (UBLKCP) + mbarrier transaction counts, kFwdPx pixels
 // per stage, while the warp reduces the previous stage from shared memory.  No cross-warp
 // barrier, no idle spinning; bytes in flight are set by the rings, not by registers.
-constexpr int kFwdStages = 2;
-constexpr int kFwdPx = 8;
+#ifndef HTD_FWD_STAGES
+#define HTD_FWD_STAGES 2
+#endif
+#ifndef HTD_FWD_PX
+#define HTD_FWD_PX 8
+#endif
+constexpr int kFwdStages = HTD_FWD_STAGES;
+constexpr int kFwdPx = HTD_FWD_PX;
 
 template <typename TIn>
 __device__ __forceinline__ void ld_smem8(const TIn* p, float (&v)[8]);
