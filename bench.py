@@ -41,6 +41,9 @@ def parse():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager steps instead of CUDA-graph replay')
+    ap.add_argument('--overlap', action='store_true',
+                    help='N > 1: all-reduce the stage-1 gradients on a side stream while the replay '
+                         'still runs the rest of backward (measured: no gain, see DESIGN.md)')
     ap.add_argument('--no-static', action='store_true',
                     help='skip the extra figure for the step with device-side assign + sample')
     return ap.parse_args()
@@ -267,7 +270,9 @@ def run_gpu(args):
             reducer.remove()
         from htd_b200.graphed import GraphedTrainStep
         try:
-            gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1)
+            gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1,
+                                     early_modules=[head.bbox_head[1], head.bbox_roi_extractor[1]]
+                                     if world > 1 and args.overlap else None)
         except Exception as e:                     # never lose the measurement to a capture problem
             print(f'[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager',
                   file=sys.stderr)
@@ -277,11 +282,23 @@ def run_gpu(args):
                 reducer = GradAllReducer(head.parameters(), world)
     if use_graph:
 
+        comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
         def allreduce_grads():
             if world == 1:
                 return
-            dist.all_reduce(gstep.flat_grad)       # one NCCL call over NVLink, in place
-            gstep.flat_grad.mul_(1.0 / world)
+            if gstep.early_event is None:
+                dist.all_reduce(gstep.flat_grad, op=dist.ReduceOp.AVG)   # one NCCL call, in place
+                return
+            # the stage-1 head / BA gradients (2/3 of the bytes) are complete long before the
+            # replay ends: their all-reduce starts on a side stream as soon as the in-graph event
+            # fires and overlaps the stage-0 backward and the RoIAlign gather; the rest follows
+            cur = torch.cuda.current_stream()
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(gstep.early_event)
+                dist.all_reduce(gstep.early_grad, op=dist.ReduceOp.AVG)
+            dist.all_reduce(gstep.late_grad, op=dist.ReduceOp.AVG)
+            cur.wait_stream(comm_stream)
 
         def step(x=None, props=None):
             losses = gstep(x, props)
@@ -507,7 +524,10 @@ def run_gpu(args):
                                      '(128 positives/img), 800x1333 pyramid P2-P6 x 256 ch, '
                                      'random init',
                             global_rois_per_step=rois_per_step * world,
-                            parallelism=f'dp{world}' + (' + NCCL grad all-reduce' if world > 1 else ''),
+                            parallelism=f'dp{world}' + (' + NCCL grad all-reduce' + (
+                                ' (stage-1 part overlapped with the rest of backward)'
+                                if gstep is not None and gstep.early_event is not None else '')
+                                if world > 1 else ''),
                             l2='inputs larger than L2: 183 MB fp32 pyramid + 94 MB bf16 weights per step',
                             pgraph_fwd_gflop=pg_flops / 1e9,
                             execution=('CUDA graph replay of forward+losses+backward' if use_graph

@@ -22,19 +22,52 @@ from . import synth
 class _GraphedStep:
     """Warm-up on a side stream, capture ``_zero`` + ``_run`` once, replay per step."""
 
-    def _init_grads(self, head, dev, flat_grads):
+    def _init_grads(self, head, dev, flat_grads, early_modules=None):
+        """``early_modules`` (with ``flat_grads``): modules whose parameter gradients are complete
+        before backward ends (stage-1 head and BA extractor: backward reaches them first).  Their
+        gradients are laid out first in the flat buffer (``self.early_grad``; the rest is
+        ``self.late_grad``) and ``self.early_event`` - an EXTERNAL CUDA event recorded inside the
+        graph once the last of them has accumulated - lets the data-parallel exchange of that part
+        start on another stream while the replay is still running the rest of backward."""
         self.head = head
-        self.flat_grad = None
+        self.flat_grad = self.early_grad = self.late_grad = self.early_event = None
         if flat_grads:
             params = list(head.parameters())
+            early = []
+            if early_modules:
+                ids = set()
+                for m in early_modules:
+                    for p in m.parameters():
+                        if id(p) not in ids:
+                            ids.add(id(p))
+                            early.append(p)
+                params = early + [p for p in params if id(p) not in ids]
             dtypes = {p.dtype for p in params}
             assert len(dtypes) == 1, 'flat_grads needs a single parameter dtype'
             self.flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=params[0].dtype,
                                          device=dev)
             self._views, off = [], 0
             for p in params:
-                self._views.append((p, self.flat_grad[off:off + p.numel()].view_as(p)))
+                # same strides as the parameter (conv weights are channels-last): AccumulateGrad
+                # then accumulates in place instead of re-laying the gradient out
+                dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last)
+                v = torch.as_strided(self.flat_grad, p.size(), p.stride(), off) if dense \
+                    else self.flat_grad[off:off + p.numel()].view_as(p)
+                self._views.append((p, v))
                 off += p.numel()
+            if early:
+                n_early = sum(p.numel() for p in early)
+                self.early_grad, self.late_grad = self.flat_grad[:n_early], self.flat_grad[n_early:]
+                self.early_event = torch.cuda.Event(external=True)
+                self._early_seen, self.early_fired = 0, 0
+
+                def hook(_p, n=len(early)):
+                    self._early_seen += 1
+                    if self._early_seen == n:
+                        self._early_seen = 0
+                        self.early_fired += 1
+                        self.early_event.record()     # captured as an event-record node
+                self._early_handles = [p.register_post_accumulate_grad_hook(hook) for p in early]
         self.losses = None
         self.total = None
 
@@ -47,6 +80,8 @@ class _GraphedStep:
                 self._run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if self.early_event is not None:
+            assert self.early_fired == warmup, 'an early module has a parameter without gradient'
         self._zero()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -74,13 +109,15 @@ class _GraphedStep:
 
 class GraphedTrainStep(_GraphedStep):
 
-    def __init__(self, head, x, proposals, gts, img_shapes, num_pos, warmup=3, flat_grads=False):
+    def __init__(self, head, x, proposals, gts, img_shapes, num_pos, warmup=3, flat_grads=False,
+                 early_modules=None):
         """``flat_grads``: parameter gradients live in ONE flat buffer (``self.flat_grad``; every
         ``p.grad`` is a view of it) that the captured step zeroes and accumulates into - the
-        data-parallel exchange is then a single all-reduce of that buffer, no packing copies."""
+        data-parallel exchange is then an all-reduce of that buffer, no packing copies.
+        ``early_modules``: see ``_init_grads``."""
         self.img_shapes, self.num_pos = img_shapes, num_pos
         dev = x[0].device
-        self._init_grads(head, dev, flat_grads)
+        self._init_grads(head, dev, flat_grads, early_modules)
         self.x = [t.detach().clone().requires_grad_(True) for t in x]
         self.proposals = [p.detach().clone() for p in proposals]
         self.gts = [{k: v.detach().clone().to(dev) for k, v in g.items()} for g in gts]

@@ -608,3 +608,45 @@ def test_channels_last_bf16_pyramid_is_read_in_place_and_gives_identical_results
         assert b.grad.dtype == torch.bfloat16 and b.grad.is_contiguous(memory_format=torch.channels_last)
         assert torch.equal(a.grad, b.grad.float())
     assert torch.equal(xa[4].grad, xb[4].grad)
+
+
+def test_graph_step_early_gradient_event_orders_a_side_stream():
+    """GraphedTrainStep(early_modules=...): the external event recorded inside the graph lets a
+    side stream read the stage-1 gradients while the replay is still running; what it reads must
+    be the final values (this is what the data-parallel bench overlaps its first all-reduce on)."""
+    import htd_b200
+    from htd_b200.graphed import GraphedTrainStep
+    from oracle import cases
+    torch.backends.cudnn.enabled = True
+    name = 'small'
+    c = cases.CASES[name]
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    head = head.cuda().to(torch.bfloat16)
+    head.compute_dtype = torch.bfloat16
+    _, x, props, gts, shapes = cases.case_inputs(name, torch.float32, 'cuda')
+    step = GraphedTrainStep(head, x, props, gts, shapes, c['P'], flat_grads=True,
+                            early_modules=[head.bbox_head[1], head.bbox_roi_extractor[1]])
+    n_early = sum(p.numel() for m in (head.bbox_head[1], head.bbox_roi_extractor[1])
+                  for p in m.parameters())
+    assert step.early_grad.numel() == n_early and step.late_grad.numel() > 0
+    side = torch.cuda.Stream()
+    snap = torch.empty_like(step.early_grad)
+    for _ in range(3):
+        step()
+        with torch.cuda.stream(side):
+            side.wait_event(step.early_event)
+            snap.copy_(step.early_grad)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        assert torch.equal(snap, step.early_grad) and float(snap.float().abs().sum()) > 0
+    # same gradients as the plain (per-parameter) graph step
+    ref = GraphedTrainStep(head, x, props, gts, shapes, c['P'])
+    ref()
+    torch.cuda.synchronize()
+    got = {k: p.grad.clone() for k, p in head.named_parameters()}
+    step()
+    torch.cuda.synchronize()
+    views = {id(p): v for p, v in step._views}
+    for k, p in head.named_parameters():
+        assert torch.equal(views[id(p)], got[k]), k
