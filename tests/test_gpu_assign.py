@@ -337,3 +337,42 @@ def test_forward_train_static_bf16_graph_matches_eager_with_fresh_keys():
             assert torch.allclose(a.grad.float(), b.float(), rtol=2e-2, atol=1e-5 * float(b.abs().max()) + 1e-12)
         for S, cnt in zip(head.last_static, e[3]):
             assert torch.equal(S.counts, cnt)
+
+
+def test_assign_sample_edge_cases():
+    """No gt slots at all, no proposals, gt counts beyond the capacity, everything invalid."""
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(3)
+    props = torch.rand(2, 50, 4, generator=g) * 100
+    props[..., 2:] += props[..., :2] + 1
+    # G == 0: every proposal is a negative (max_iou_assigner.py:146-153)
+    S = ops.assign_sample(props.to(dev), torch.zeros(2, 0, 4, device=dev),
+                          torch.zeros(2, 0, dtype=torch.long, device=dev),
+                          torch.zeros(2, dtype=torch.int32, device=dev),
+                          torch.rand(2, 50, generator=g).to(dev), num=32, pos_fraction=0.25)
+    assert S.counts.cpu().tolist() == [[0, 32, 0, 50], [0, 32, 0, 50]]
+    assert (S.kind == 0).all() and (S.cand >= 0).all()
+    # N == 0 with gts: only the gt boxes are sampled, the rest is padding
+    gt = torch.tensor([[[0., 0., 10., 10.], [5., 5., 30., 40.], [0., 0., 0., 0.]]] * 2)
+    S = ops.assign_sample(torch.zeros(2, 0, 4, device=dev), gt.to(dev),
+                          torch.tensor([[1, 2, 0]] * 2, device=dev),
+                          torch.tensor([2, 5], dtype=torch.int32, device=dev),       # 5 > capacity 3
+                          torch.rand(2, 3, generator=g).to(dev), num=8, pos_fraction=0.5)
+    c = S.counts.cpu().tolist()
+    assert c[0] == [2, 0, 2, 0] and c[1] == [3, 0, 3, 0]
+    k = S.kind.view(2, 8).cpu()
+    assert k[0].tolist() == [1, 1, 2, 2, 2, 2, 2, 2] and k[1].tolist() == [1, 1, 1, 2, 2, 2, 2, 2]
+    assert S.is_gt.view(2, 8)[0, :2].all() and (S.rois.view(2, 8, 5)[:, 3:, 1:] == 0).all()
+    # all proposals masked out and gts not added: nothing but padding
+    S = ops.assign_sample(props.to(dev), gt.to(dev), torch.tensor([[1, 2, 0]] * 2, device=dev),
+                          torch.tensor([2, 2], dtype=torch.int32, device=dev),
+                          torch.rand(2, 53, generator=g).to(dev),
+                          valid=torch.zeros(2, 50, dtype=torch.bool, device=dev),
+                          add_gt_as_proposals=False, num=16)
+    assert (S.kind == 2).all() and S.counts.cpu().abs().sum() == 0
+    # B == 0
+    S = ops.assign_sample(torch.zeros(0, 5, 4, device=dev), torch.zeros(0, 2, 4, device=dev),
+                          torch.zeros(0, 2, dtype=torch.long, device=dev),
+                          torch.zeros(0, dtype=torch.int32, device=dev),
+                          torch.zeros(0, 7, device=dev), num=16)
+    assert S.rois.shape == (0, 5)

@@ -60,3 +60,21 @@ def test_simple_test_returns_reference_format_through_the_nms_kernel():
     for per_img in res:
         assert len(per_img) == 80 and all(a.shape[1] == 5 for a in per_img)
         assert sum(a.shape[0] for a in per_img) <= 100
+
+
+def test_multiclass_nms_edge_cases():
+    dev = 'cuda'
+    det, lab, cnt = ops.multiclass_nms(torch.zeros(0, 4, device=dev), torch.zeros(0, 81, device=dev),
+                                       0.05, 0.5, 100)
+    assert int(cnt) == 0 and det.shape == (100, 5)
+    # identical boxes, identical scores: the first (lowest index) survives per class
+    boxes = torch.tensor([[10., 10., 50., 50.]] * 4, device=dev)
+    scores = torch.tensor([[0.4, 0.3, 0.3]] * 4, device=dev)
+    d, l = core.multiclass_nms(boxes, scores, 0.05, dict(type='nms', iou_threshold=0.5), 10)
+    assert d.shape == (2, 5) and l.tolist() == [0, 1] and d[:, 4].tolist() == pytest.approx([0.4, 0.3])
+    # zero-area boxes: IoU is 0/0 = nan, never above the threshold - nothing is suppressed
+    z = torch.tensor([[5., 5., 5., 5.]] * 3, device=dev)
+    s = torch.tensor([[0.9, 0.1], [0.8, 0.2], [0.7, 0.3]], device=dev)
+    d, l = core.multiclass_nms(z, s, 0.05, dict(type='nms', iou_threshold=0.5), 10)
+    wd, wl = restate.multiclass_nms(z.cpu(), s.cpu(), 0.05, 0.5, 10)
+    assert torch.equal(d.cpu(), wd) and torch.equal(l.cpu(), wl) and d.shape[0] == 3
