@@ -366,7 +366,9 @@ def run_gpu(args):
             if not use_graph:
                 xs = [t.detach().requires_grad_(True) for t in xs]
             losses = step(xs, ps)
-            dev_l = torch.stack([v.detach().float().reshape(()) for v in losses.values()])
+            # the captured step leaves the 7 losses stacked in one device vector (part of the graph)
+            dev_l = gstep.loss_vec if use_graph else \
+                torch.stack([v.detach().float().reshape(()) for v in losses.values()])
             pinned[i & 1].copy_(dev_l, non_blocking=True)
             done[i & 1].record()
             if i > 0:

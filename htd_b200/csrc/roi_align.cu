@@ -382,9 +382,15 @@ constexpr int kBwdThreads = (kBwdWarps + 1) * 32;   // + 1 producer warp
 constexpr int kBwdChunk = kBwdWarps * 32;          // RoIs scanned per pass
 constexpr int kHalf = kTile / 2;      // pixels per consumer warp
 
+#ifndef HTD_BWD_STAGES_BF16
+#define HTD_BWD_STAGES_BF16 4
+#endif
+#ifndef HTD_BWD_STAGES_F32
+#define HTD_BWD_STAGES_F32 2
+#endif
 template <typename TDy>
 struct BwdStages {                     // dY ring depth: 25 KB (bf16) / 50 KB (fp32) per slot at P = 7
-    static constexpr int value = sizeof(TDy) == 2 ? 4 : 2;
+    static constexpr int value = sizeof(TDy) == 2 ? HTD_BWD_STAGES_BF16 : HTD_BWD_STAGES_F32;
 };
 
 // Backward gather.  One CTA per 8x8-pixel tile of dX.  Per chunk of 512 RoIs the 16 consumer warps
@@ -840,7 +846,8 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
     dim3 grid((unsigned)total), block(kBwdThreads);
     cudaStream_t st = (cudaStream_t)stream;
     const int cw = C < 256 ? C : 256;
-    const size_t smem = (size_t)(dy_dtype == HTD_BF16 ? 4 : 2) * pooled * pooled * cw * dtype_size(dy_dtype);
+    const size_t smem = (size_t)(dy_dtype == HTD_BF16 ? HTD_BWD_STAGES_BF16 : HTD_BWD_STAGES_F32) *
+                        pooled * pooled * cw * dtype_size(dy_dtype);
 #define HTD_BWD_LAUNCH(TY, TX)                                                                    \
     do {                                                                                          \
         static bool attr_done = false;                                                            \

@@ -105,6 +105,8 @@ class _GraphedStep:
         total = sum(v for k, v in losses.items() if 'loss' in k)
         total.backward()
         self.losses, self.total = losses, total
+        # all loss / accuracy scalars in ONE device vector (dict order): one D2H per step
+        self.loss_vec = torch.stack([v.detach().float().reshape(()) for v in losses.values()])
 
 
 class GraphedTrainStep(_GraphedStep):
