@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(kAsThreads) assign_sample_kernel(const AsParam
     // ---- select `want` members of a class by smallest (key, index); emit in index order
     auto select_and_emit = [&](const bool positives, const int have, const int want, const int base) {
         auto member = [&](int c) { return positives ? s_ind[c] > 0 : s_ind[c] == 0; };
-        unsigned T = 0xffffffffu;
+        unsigned T = 0u;                                        // want == 0: nothing is below T
         int rem = 0;                                            // members with key == T to take
         const bool all = want >= have;
-        if (!all) {                                             // 4 x 8-bit radix select of the
+        if (!all && want > 0) {                                 // 4 x 8-bit radix select of the
             unsigned prefix = 0u;                               // want-th smallest key
             int remaining = want;
             for (int pass = 3; pass >= 0; --pass) {

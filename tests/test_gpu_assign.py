@@ -376,3 +376,25 @@ def test_assign_sample_edge_cases():
                           torch.zeros(0, dtype=torch.int32, device=dev),
                           torch.zeros(0, 7, device=dev), num=16)
     assert S.rois.shape == (0, 5)
+
+
+@pytest.mark.parametrize('ub,frac', [(0, 0.25), (-1, 0.0), (0, 0.0)])
+def test_assign_sample_with_nothing_wanted_from_a_class(ub, frac):
+    """neg_pos_ub = 0 (no negatives wanted) / pos_fraction = 0 (no positives wanted) while that
+    class has candidates: nothing of it may be drawn (base_sampler.py:83-97)."""
+    cases.ASSIGN_CASES['_z'] = dict(kind='synth', B=2, N=300, G=8, gts=(5, 8), jitter=0.15,
+                                    near=0.4, seed=51,
+                                    cfg=cases._rcnn_cfg(0.5, num=64, ub=ub, frac=frac))
+    try:
+        d = cases.assign_case_inputs('_z')
+        ref, _ = cases.run_assign_case('_z', restate.assign_sample_image)
+    finally:
+        del cases.ASSIGN_CASES['_z']
+    out = _run_kernel(d)
+    _check(out, {k: v.numpy() for k, v in ref.items()}, f'ub{ub}_frac{frac}')
+    c = out.counts.cpu()
+    assert (c[:, 2] > 0).all() and (c[:, 3] > 0).all()
+    if frac == 0.0:
+        assert (c[:, 0] == 0).all()
+    if ub == 0:
+        assert (c[:, 1] == 0).all()
