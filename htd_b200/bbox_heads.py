@@ -459,22 +459,7 @@ class HTDBBoxHead(BBoxHead):
                 else int(torch.max(rois[..., 0])) + 1
         d = self.fc_out_channels
         prototype = torch.cat((fc_cls_0.weight, fc_cls_0.bias.unsqueeze(1)), 1).detach()
-        # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool (:161-189)
-        if global_feat is not None:
-            g = global_feat.reshape(global_feat.size(0), -1)
-            x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
-        x_reg = x_reg + self.alpha * enhanced_feat
-        x_reg = x_reg.contiguous(memory_format=torch.channels_last)
-        last = self.convs[-1] if len(self.convs) else None
-        if last is not None and last.gn is None and last.with_act and x_reg.is_cuda and \
-                ConvModule.fused_gn and last.conv.out_channels % 8 == 0:
-            for m in self.convs[:-1]:
-                x_reg = m(x_reg)
-            # last conv -> ReLU -> AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:109-113,188-189):
-            # activation and pool in one pass over the largest activation of the head
-            x_reg = ops.relu_mean_pool(last.conv(x_reg))
-        else:
-            x_reg = self.convs(x_reg).mean((2, 3))
+        g = global_feat.reshape(global_feat.size(0), -1) if global_feat is not None else None
         # ---- cls branch: fcs on x_cls and on x_cls + SFA.  fcs.0 is linear, so
         # fcs.0(x + g (x) 1_49) = fcs.0(x) + g W_sum^T with W_sum = sum of W over the 49 bins:
         # one [K,12544]x[12544,1024] GEMM instead of the reference's two (:164 and :192).
@@ -500,6 +485,25 @@ class HTDBBoxHead(BBoxHead):
         layers = self.graph_layer_cls
         refined = pgraph.pgraph_refine(x_c, sam, [m.weight for m in layers],
                                        [m.bias for m in layers], plan)
+        # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool (:161-189).  It is
+        # independent of the cls branch above; it comes second so that a BA extraction running on a
+        # side stream (``enhanced_feat`` given as a callable that joins it) overlaps all of the above
+        if global_feat is not None:
+            x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
+        if callable(enhanced_feat):
+            enhanced_feat = enhanced_feat()
+        x_reg = x_reg + self.alpha * enhanced_feat
+        x_reg = x_reg.contiguous(memory_format=torch.channels_last)
+        last = self.convs[-1] if len(self.convs) else None
+        if last is not None and last.gn is None and last.with_act and x_reg.is_cuda and \
+                ConvModule.fused_gn and last.conv.out_channels % 8 == 0:
+            for m in self.convs[:-1]:
+                x_reg = m(x_reg)
+            # last conv -> ReLU -> AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:109-113,188-189):
+            # activation and pool in one pass over the largest activation of the head
+            x_reg = ops.relu_mean_pool(last.conv(x_reg))
+        else:
+            x_reg = self.convs(x_reg).mean((2, 3))
         feat_cls_new = (x_glb if x_glb is not None else x_c) + refined
         cls_score = linear_aligned(self.fc_cls, feat_cls_new) if self.with_cls else None
         bbox_pred = linear_aligned(self.fc_reg, x_reg) if self.with_reg else None

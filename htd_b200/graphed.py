@@ -126,8 +126,15 @@ class GraphedTrainStep(_GraphedStep):
         self._capture(dev, warmup)
 
     def _run(self):
-        self._finish(synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
-                                                 self.img_shapes, self.num_pos))
+        # the early-gradient event is recorded on ONE stream: keep the whole step on it
+        prev = self.head.overlap_ba
+        if self.early_event is not None:
+            self.head.overlap_ba = False
+        try:
+            self._finish(synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
+                                                     self.img_shapes, self.num_pos))
+        finally:
+            self.head.overlap_ba = prev
 
     def load(self, x=None, proposals=None, gts=None, non_blocking=True):
         """Copy new inputs (device or pinned-host tensors) into the static buffers."""

@@ -82,6 +82,14 @@ class HTDRoIHead(nn.Module):
             self.glbctx_head.init_weights()
 
     # ------------------------------------------------------------------------------------------
+    overlap_ba = True        # class switch (diagnostics): BA extraction on a side stream in training
+
+    def _side_stream(self, device):
+        st = getattr(self, '_side', None)
+        if st is None or st.device != device:
+            st = self._side = torch.cuda.Stream(device=device)
+        return st
+
     def _pyramid(self, x):
         """Channels-last copy of the levels the extractors read, made once per call."""
         n = self.bbox_roi_extractor[0].num_inputs
@@ -111,8 +119,23 @@ class HTDRoIHead(nn.Module):
         nimg = g.size(0) if g is not None else None
         if sampling_results:
             pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
+            if self.overlap_ba and rois.is_cuda:
+                # BA extraction (plan, 4-level gather, attention, fuse: latency-bound kernels) on a
+                # side stream next to the single-level extraction, the cls-branch GEMMs and the
+                # PGraph; the head joins the stream where it first needs the result.  Inside a CUDA
+                # graph this becomes a parallel branch; autograd mirrors it in backward.
+                cur, side = torch.cuda.current_stream(), self._side_stream(rois.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    enh_out = enh(x_cl, pos_rois)
+
+                def enhanced():
+                    cur.wait_stream(side)
+                    enh_out.record_stream(cur)
+                    return enh_out
+            else:
+                enhanced = enh(x_cl, pos_rois)
             bbox_feats = ext(x_cl, rois)
-            enhanced = enh(x_cl, pos_rois)
             # positives are the prefix of each image's block: slices, not index tensors, so the
             # gather and the scatter of bbox_pred (htd_roi_head.py:169-170,180-182) are plain copies
             spans, off = [], 0
