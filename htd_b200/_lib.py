@@ -27,7 +27,7 @@ class HtdBwdSource(ctypes.Structure):
     _fields_ = [('rois', c_void_p), ('boxes', c_void_p), ('offsets', c_void_p), ('ranges', c_void_p),
                 ('weights', c_void_p), ('dy', c_void_p), ('scale', c_void_p), ('addvec', c_void_p),
                 ('K', ctypes.c_int32), ('dy_per_level', ctypes.c_int32),
-                ('ring_edge', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('ring_edge', ctypes.c_int32), ('addvec_dtype', ctypes.c_int32)]
 
 
 MAX_BWD_SOURCES = 4
@@ -155,6 +155,8 @@ def lib():
         L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
         L.htd_multiclass_nms_workspace_bytes.restype = c_ll
         L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
+        L.htd_debug_set_bwd_trace.restype = None
+        L.htd_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
         for name, args in SIGNATURES.items():
             if not hasattr(L, name):
                 raise RuntimeError(f'{LIB_PATH} does not export {name}: rebuild it '

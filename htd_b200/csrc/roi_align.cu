@@ -22,6 +22,8 @@
 //    Wy^T dY Wx for its 64 pixels x 256 channels in registers.  Every dX element is written
 //    exactly once: no atomics, no memset, bit-reproducible.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "roi_axis.h"
@@ -29,6 +31,7 @@
 namespace htd {
 
 static thread_local char g_err[512] = "";
+static unsigned long long* g_bwd_trace = nullptr;    // see htd_debug_set_bwd_trace
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -173,13 +176,22 @@ __global__ void __launch_bounds__(128) weight_table_kernel(const TableParams p) 
     }
     const int fh = box.y - box.x + 1, fw = box.w - box.z + 1;
     float* tab = p.weights + (size_t)p.offsets[e] * kTabW;
-    for (int i = tid; i < (fh + fw) * kTabW; i += blockDim.x) {
+    const int n = (fh + fw) * kTabW;
+    for (int base = 0; base < n; base += blockDim.x) {      // uniform trip count: shuffles below
+        const int i = base + tid;
         const int row = i / kTabW, pp = i % kTabW;
         float w = 0.f;
-        if (pp < p.P)
+        if (i < n && pp < p.P)
             w = row < fh ? axis_weight(s_axis[0], pp, box.x + row)
                          : axis_weight(s_axis[1], pp, box.z + (row - fh));
-        tab[i] = w;
+        // the 8 entries of a table row sit in 8 consecutive lanes: with pooled < 8 the last entry
+        // carries the row sum (the rank-1 add-vector term of the tensor-pipe backward reads it)
+        float sum = w;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        if (p.P < kTabW && pp == kTabW - 1) w = sum;
+        if (i < n) tab[i] = w;
     }
 }
 
@@ -362,14 +374,15 @@ struct BwdSource {                   // one extractor call whose gradient lands 
     const float* weights;
     const void* dy;
     const float* scale;
-    const float* addvec;
-    int K, dy_per_level, ring_edge;
+    const float* addvec;             // fp32, or bf16 when av_bf16 (tensor-pipe kernel only)
+    int K, dy_per_level, ring_edge, av_bf16;
 };
 
 struct BwdParams {
     LevelDev lv[HTD_MAX_LEVELS];
     int tile_start[HTD_MAX_LEVELS + 1];
     int L, B, C, P, nsrc, nchw;
+    unsigned long long* trace;       // diagnostics: per-CTA {t0, t1, hits, blocks, smid, level} or null
     BwdSource src[HTD_MAX_BWD_SOURCES];
 };
 
@@ -419,11 +432,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool producer = (warp == kBwdWarps);
+    // coarse levels first: their tiles collect the most RoIs and must not form the tail of the grid
+    const int bid = (int)(gridDim.x - 1 - blockIdx.x);
     int l = 0;
-    while (l + 1 < p.L && (int)blockIdx.x >= p.tile_start[l + 1]) ++l;
+    while (l + 1 < p.L && bid >= p.tile_start[l + 1]) ++l;
     const int H = p.lv[l].H, W = p.lv[l].W;
     const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
-    int local = (int)blockIdx.x - p.tile_start[l];
+    int local = bid - p.tile_start[l];
     const int b = local / (tiles_x * tiles_y);
     local -= b * tiles_x * tiles_y;
     const int row0 = (local / tiles_x) * kTile, col0 = (local % tiles_x) * kTile;
@@ -658,6 +673,465 @@ __global__ void __launch_bounds__(kBwdThreads, 1) roi_align_bwd_kernel(const Bwd
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// backward, bf16 dY: the per-hit contraction on the tensor pipe
+// ------------------------------------------------------------------------------------------
+// For one (tile, RoI) hit the scalar kernel above evaluates
+//     dX[px][c] += sum_{bin} wy[row(px)][ph(bin)] * wx[col(px)][pw(bin)] * sv(bin) * dY[bin][c]
+// with 16 warps that each re-read every staged bin.  The sum is a [64 px x bins] x [bins x 256 ch]
+// product, so this kernel keeps the tile-gather structure - hits compacted in index order, a
+// producer warp's bulk-copy ring, one write per dX element, no atomics - and does the per-hit
+// contraction with warp-level bf16 MMAs (m16n8k16, fp32 accumulators):
+//   * scan: ALL chunks of ALL sources are scanned in one batch (counts per (chunk, warp), one
+//     exclusive scan, records written in ascending (source, index) order); the thread that found
+//     a hit also resolves its bins / table rows, so the producer only streams;
+//   * K index of a staged bin = ph_rel * 8 + pw_rel (8 slots per bin row, so a K step of 16 is two
+//     bin rows and the A fragment of a lane needs just wx[col][qa + 2t .. +1] once per hit and
+//     wy[row][ph] of two rows per step); unused slots carry weight 0;
+//   * ring of K-step BLOCKS (16 bin rows = 8448 B): a hit takes ceil(np / 2) consecutive blocks,
+//     ONE full barrier (its first block's) and one producer wait (on its last block); the producer
+//     places every needed bin as its own 512 B row at a 528 B pitch (one bulk copy per bin, lanes
+//     in parallel), which makes the transposing ldmatrix of the B fragments bank-conflict free;
+//   * a consumer warp owns 2 tile rows x 8 columns (M = 16) x 256 / kCG channels;
+//   * the BA add vector is one more K row (slot 7 of the hit's first block, bf16) with weight
+//     rowsum(wy) * colsum(wx) - the sums are entry 7 of the plan's table rows; with pooled == 8
+//     it stays the fp32 rank-1 FMA term;
+//   * the interpolation weights are rounded to bf16 (2^-9 relative) - inside the 2e-2 bf16 gate;
+//     fp32 dY keeps the exact scalar kernel.
+// Measured cost model at the BASELINE sizes (tools/trace_bwd.py, 2848 tiles, 44.8 k hits, 65.4 k
+// blocks): t_tile = 12 us + 0.7 us * hits + 0.6 us * blocks with two CTAs per SM.
+constexpr int kMmaRowBytes = 256 * 2 + 16;               // one bin: 256 bf16 + 16 B pad
+constexpr int kMmaBlockBytes = 16 * kMmaRowBytes;        // one K step: two bin rows x 8 slots (8448)
+constexpr int kStagePitch = 256 + 8;                     // floats per pixel in the store staging
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kHitCap = 1024;          // hit records of one batch (>= RoIs per chunk)
+
+// kCG = channel groups: 4 * kCG consumer warps, each 2 tile rows x 8 columns x (256 / kCG) channels
+template <typename TDx, int kR, int kMinCtas, int kCG>
+__global__ void __launch_bounds__((4 * kCG + 1) * 32, kMinCtas) roi_align_bwd_mma_kernel(const BwdParams p) {
+    typedef __nv_bfloat16 TDy;
+    constexpr int kW = 4 * kCG;                // consumer warps
+    constexpr int kChunk = kW * 32;            // RoIs scanned per chunk
+    constexpr int kThreads = kChunk + 32;      // + 1 producer warp
+    constexpr int kCW = 256 / kCG;             // channels per consumer warp
+    constexpr int kNT = kCW / 8;               // n-tiles (8 channels) per consumer warp
+    // chunks scanned per batch: 5 bits of rank each in a 64-bit word, 128 (chunk, warp) counts
+    constexpr int kBatchChunks = (128 / kW) < 12 ? (128 / kW) : 12;
+    // ring of kR K-step blocks (16 bin rows each); a hit takes ceil(np / 2) consecutive blocks, so
+    // the ring holds many small hits or a few large ones.  Tables live in a ring of kR per-hit slots.
+    extern __shared__ __align__(128) uint8_t bwd_smem[];
+    __shared__ __align__(16) float s_wy[kR][kTile][kTabW];      // [table slot][tile row][bin]
+    __shared__ __align__(16) float s_wx[kR][kTile][kTabW];      // [table slot][tile col][bin]
+    __shared__ int4 s_meta[kHitCap];    // per hit: k | source << 28, bins, tile-relative ranges, y table row
+    __shared__ int s_xrow[kHitCap];     // per hit: x table row of the first staged column
+    __shared__ float s_scale[kHitCap];  // per hit: BA level weight (1 when unused)
+    __shared__ __align__(16) float s_av[kR][256];
+    __shared__ int s_cnt[kBatchChunks * kW + 1];       // per (chunk, warp) counts -> bases
+    __shared__ uint64_t s_full[kR], s_empty[kR];        // per block
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool producer = (warp == kW);
+    // coarse levels first: their tiles collect the most RoIs and must not form the tail of the grid
+    const int bid = (int)(gridDim.x - 1 - blockIdx.x);
+    int l = 0;
+    while (l + 1 < p.L && bid >= p.tile_start[l + 1]) ++l;
+    const int H = p.lv[l].H, W = p.lv[l].W;
+    const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
+    int local = bid - p.tile_start[l];
+    const int b = local / (tiles_x * tiles_y);
+    local -= b * tiles_x * tiles_y;
+    const int row0 = (local / tiles_x) * kTile, col0 = (local % tiles_x) * kTile;
+    const int P = p.P, PP = P * P;
+    const int C = p.C;                                     // <= 256, multiple of 64 (host check)
+    TDx* dx = static_cast<TDx*>(p.lv[l].data);
+    const uint32_t ring_u32 = smem_u32(bwd_smem);
+    unsigned long long t_start = 0ull;
+    if (p.trace && tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+
+    // the ring is read beyond the copied rows (K slots of weight 0): make it finite once
+    for (int i = tid; i < kR * kMmaBlockBytes / 16; i += kThreads)
+        reinterpret_cast<uint4*>(bwd_smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int s = 0; s < kR; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kW); }
+        fence_mbar_init();
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    unsigned g = 0, gb = 0;                       // hits / blocks streamed so far (ring positions, parities)
+    unsigned fullph = 0;                          // consumers: phase bit of every full barrier
+
+    // consumer roles: pixel group (tile rows 2*pg, 2*pg+1) x channel group (64 channels)
+    const int pg = warp & 3, cg = warp >> 2;
+    const int gid = lane >> 2, tq = lane & 3;      // mma fragment coordinates
+    const int r0 = 2 * pg, r1 = r0 + 1;
+    const bool cg_on = cg * kCW < C;
+    // ldmatrix lane address inside a slot: matrix m = lane >> 3 -> K half (m & 1), n-tile (m >> 1)
+    const uint32_t ld_off = (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * kMmaRowBytes +
+                                       (cg * kCW + (lane >> 4) * 8) * 2);
+    float acc[kNT][4];
+#pragma unroll
+    for (int j = 0; j < kNT; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+
+    // chunks of all sources, numbered consecutively: chunk c -> (source, first RoI)
+    int total_chunks = 0;
+    for (int si = 0; si < p.nsrc; ++si) total_chunks += (p.src[si].K + kChunk - 1) / kChunk;
+
+    for (int c_begin = 0; c_begin < total_chunks;) {
+        // ---- scan: up to kBatchChunks chunks at once.  Pass 1 counts the RoIs whose footprint box
+        // touches the tile per (chunk, warp); the records are then written in ascending (source,
+        // index) order, so the accumulation order - and the result - is fixed.
+        const int nb = min(kBatchChunks, total_chunks - c_begin);
+        unsigned hitmask = 0;
+        unsigned long long ranks = 0ull;          // 5 bits per chunk: rank of the lane's hit in its warp
+        if (!producer) {
+            int si = 0, c = c_begin;
+            while (c >= (p.src[si].K + kChunk - 1) / kChunk) { c -= (p.src[si].K + kChunk - 1) / kChunk; ++si; }
+            for (int j = 0; j < nb; ++j) {
+                const BwdSource& q = p.src[si];
+                const int k = c * kChunk + tid;
+                bool hit = false;
+                if (k < q.K) {
+                    const int4 bx = __ldg(q.boxes + (size_t)l * q.K + k);
+                    hit = (bx.y >= bx.x) && bx.x <= row0 + kTile - 1 && bx.y >= row0 &&
+                          bx.z <= col0 + kTile - 1 && bx.w >= col0 &&
+                          ((int)__ldg(q.rois + (size_t)k * 5) == b);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_cnt[j * kW + warp] = __popc(bal);
+                if (hit) {
+                    hitmask |= 1u << j;
+                    ranks |= (unsigned long long)__popc(bal & ((1u << lane) - 1u)) << (5 * j);
+                }
+                if (++c >= (q.K + kChunk - 1) / kChunk) { c = 0; ++si; }
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {                           // exclusive scan of the nb * 16 counts, in place
+            const int n = nb * kW;
+            int v[4], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = lane * 4 + i;
+                v[i] = idx < n ? s_cnt[idx] : 0;
+                sum += v[i];
+            }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            int run = inc - sum;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = lane * 4 + i;
+                if (idx < n) s_cnt[idx] = run;
+                run += v[i];
+            }
+            if (lane == 31) s_cnt[n] = inc;
+        }
+        __syncthreads();
+        // chunks that fit the record table (the first always does); the rest is rescanned
+        int nbf = 1;
+        while (nbf < nb && s_cnt[(nbf + 1) * kW] <= kHitCap) ++nbf;
+        const int nh = s_cnt[nbf * kW];
+        if (!producer && hitmask) {
+            int si = 0, c = c_begin;
+            while (c >= (p.src[si].K + kChunk - 1) / kChunk) { c -= (p.src[si].K + kChunk - 1) / kChunk; ++si; }
+            for (int j = 0; j < nbf; ++j) {
+                const BwdSource& q = p.src[si];
+                if ((hitmask >> j) & 1u) {
+                    const int kk = c * kChunk + tid;
+                    const int pos = s_cnt[j * kW + warp] + (int)((ranks >> (5 * j)) & 31ull);
+                    const size_t e = (size_t)l * q.K + kk;
+                    const int4 bx = __ldg(q.boxes + e);
+                    const int off = __ldg(q.offsets + e);
+                    const float sc = q.scale ? __ldg(q.scale + e) : 1.f;
+                    const int4* rg = reinterpret_cast<const int4*>(q.ranges + e * kRangeInts);
+                    int lo[8], hi[8];
+                    int pa = 0, pb = -1, qa = 0, qb = -1;
+                    {
+                        const int4 a0 = __ldg(rg), a1 = __ldg(rg + 1), h0 = __ldg(rg + 2), h1 = __ldg(rg + 3);
+                        lo[0] = a0.x; lo[1] = a0.y; lo[2] = a0.z; lo[3] = a0.w; lo[4] = a1.x; lo[5] = a1.y; lo[6] = a1.z; lo[7] = a1.w;
+                        hi[0] = h0.x; hi[1] = h0.y; hi[2] = h0.z; hi[3] = h0.w; hi[4] = h1.x; hi[5] = h1.y; hi[6] = h1.z; hi[7] = h1.w;
+                        bool first = true;
+#pragma unroll
+                        for (int pp = 0; pp < HTD_MAX_POOLED; ++pp)
+                            if (pp < P && hi[pp] >= lo[pp] && lo[pp] <= row0 + kTile - 1 && hi[pp] >= row0) {
+                                if (first) { pa = pp; first = false; }
+                                pb = pp;
+                            }
+                    }
+                    {
+                        const int4 a0 = __ldg(rg + 4), a1 = __ldg(rg + 5), h0 = __ldg(rg + 6), h1 = __ldg(rg + 7);
+                        lo[0] = a0.x; lo[1] = a0.y; lo[2] = a0.z; lo[3] = a0.w; lo[4] = a1.x; lo[5] = a1.y; lo[6] = a1.z; lo[7] = a1.w;
+                        hi[0] = h0.x; hi[1] = h0.y; hi[2] = h0.z; hi[3] = h0.w; hi[4] = h1.x; hi[5] = h1.y; hi[6] = h1.z; hi[7] = h1.w;
+                        bool first = true;
+#pragma unroll
+                        for (int pp = 0; pp < HTD_MAX_POOLED; ++pp)
+                            if (pp < P && hi[pp] >= lo[pp] && lo[pp] <= col0 + kTile - 1 && hi[pp] >= col0) {
+                                if (first) { qa = pp; first = false; }
+                                qb = pp;
+                            }
+                    }
+                    if (pb < pa || qb < qa) { pb = pa - 1; qb = qa - 1; }
+                    const int r_lo = max(bx.x, row0), r_hi = min(bx.y, row0 + kTile - 1);
+                    const int c_lo = max(bx.z, col0), c_hi = min(bx.w, col0 + kTile - 1);
+                    s_meta[pos] = make_int4(kk | (si << 28),
+                                            (pa & 0xff) | ((pb & 0xff) << 8) | ((qa & 0xff) << 16) | ((qb & 0xff) << 24),
+                                            (r_lo - row0) | ((r_hi - row0) << 8) | ((c_lo - col0) << 16) | ((c_hi - col0) << 24),
+                                            off + (r_lo - bx.x));
+                    s_xrow[pos] = off + (bx.y - bx.x + 1) + (c_lo - bx.z);
+                    s_scale[pos] = sc;
+                }
+                if (++c >= (q.K + kChunk - 1) / kChunk) { c = 0; ++si; }
+            }
+        }
+        c_begin += nbf;
+        __syncthreads();
+        if (nh == 0) continue;                    // CTA-uniform
+
+        if (producer) {
+            // ---- stream the hits block by block: lane 0 the tables (with the first block), all
+            // lanes the bins of the block's two bin rows
+            for (int h = 0; h < nh; ++h) {
+                const int4 m = s_meta[h];
+                const int pa = (int)(signed char)(m.y & 0xff), pb = (int)(signed char)((m.y >> 8) & 0xff);
+                const int qa = (int)(signed char)((m.y >> 16) & 0xff), qb = (int)(signed char)((m.y >> 24) & 0xff);
+                const int nq = qb - qa + 1, np = pb - pa + 1;
+                if (np <= 0 || nq <= 0) continue;
+                const int kk = m.x & 0x0fffffff;
+                const BwdSource& q = p.src[(unsigned)m.x >> 28];
+                const int ts = g % kR;
+                const uint32_t bin_bytes = (uint32_t)C * 2u;
+                const TDy* dy = static_cast<const TDy*>(q.dy);
+                const size_t dyk = (q.dy_per_level ? (size_t)l * q.K : 0) + kk;
+                const int nst = (np + 1) >> 1;
+                // pooled < 8: K slot 7 of the first block is free and takes the add vector as a bf16
+                // row (weight rowsum * colsum); otherwise it travels as fp32 for the FMA form
+                const bool av_row = q.addvec != nullptr && P < kTabW;
+                const bool av_cvt = av_row && !q.av_bf16;      // fp32 add vector: converted here
+                float4 av0 = make_float4(0.f, 0.f, 0.f, 0.f), av1 = av0;
+                if (av_cvt && lane * 8 < C) {
+                    const float4* ap = reinterpret_cast<const float4*>(q.addvec + ((size_t)l * q.K + kk) * C + lane * 8);
+                    av0 = __ldg(ap);
+                    av1 = __ldg(ap + 1);
+                }
+                uint64_t* full0 = &s_full[gb % kR];        // ONE full barrier per hit: its first block's
+                // consumers release the blocks hit by hit and in order: when the LAST block of the
+                // range is free, the earlier ones are too - one wait per hit
+                if (lane == 0) {
+                    const unsigned last = gb + nst - 1;
+                    mbar_wait(&s_empty[last % kR], ((last / kR) & 1u) ^ 1u);
+                }
+                if (av_cvt) {
+                    __syncwarp();
+                    if (lane * 8 < C)
+                        *reinterpret_cast<uint4*>(bwd_smem + (size_t)(gb % kR) * kMmaBlockBytes + 7 * kMmaRowBytes + lane * 16) =
+                            make_uint4(pack_bf16x2(av0.x, av0.y), pack_bf16x2(av0.z, av0.w),
+                                       pack_bf16x2(av1.x, av1.y), pack_bf16x2(av1.z, av1.w));
+                    __syncwarp();                          // ordered before lane 0's arrive below
+                }
+                if (lane == 0) {
+                    const int rl = m.z & 0xff, rh = (m.z >> 8) & 0xff, cl = (m.z >> 16) & 0xff, ch = (m.z >> 24) & 0xff;
+                    const uint32_t wy_bytes = (uint32_t)(rh - rl + 1) * kTabW * 4u;
+                    const uint32_t wx_bytes = (uint32_t)(ch - cl + 1) * kTabW * 4u;
+                    const uint32_t av_bytes = !q.addvec ? 0u : !av_row ? (uint32_t)C * 4u : q.av_bf16 ? bin_bytes : 0u;
+                    mbar_expect_tx(full0, (uint32_t)(np * nq) * bin_bytes + wy_bytes + wx_bytes + av_bytes);
+                    if (av_bytes && !av_row)
+                        bulk_g2s(&s_av[ts][0], q.addvec + ((size_t)l * q.K + kk) * C, av_bytes, full0);
+                    if (av_bytes && av_row)                  // bf16 add vector: straight into K slot 7
+                        bulk_g2s(bwd_smem + (size_t)(gb % kR) * kMmaBlockBytes + 7 * kMmaRowBytes,
+                                 reinterpret_cast<const TDy*>(q.addvec) + ((size_t)l * q.K + kk) * C,
+                                 av_bytes, full0);
+                    bulk_g2s(&s_wy[ts][rl][0], q.weights + (size_t)m.w * kTabW, wy_bytes, full0);
+                    bulk_g2s(&s_wx[ts][cl][0], q.weights + (size_t)s_xrow[h] * kTabW, wx_bytes, full0);
+                }
+                __syncwarp();
+                const TDy* src0 = dy + (dyk * PP + pa * P + qa) * C;
+                for (int i = lane; i < np * nq; i += 32) {
+                    const int pr = i / nq, qr = i - pr * nq;
+                    const int blk = (gb + (pr >> 1)) % kR;
+                    bulk_g2s(bwd_smem + (size_t)blk * kMmaBlockBytes + ((pr & 1) * 8 + qr) * kMmaRowBytes,
+                             src0 + (size_t)(pr * P + qr) * C, bin_bytes, full0);
+                }
+                gb += (unsigned)nst;
+                ++g;
+            }
+        } else {
+            // ===== consumers =====
+            for (int h = 0; h < nh; ++h) {
+                const int4 m = s_meta[h];
+                const int pa = (int)(signed char)(m.y & 0xff), pb = (int)(signed char)((m.y >> 8) & 0xff);
+                const int qa = (int)(signed char)((m.y >> 16) & 0xff), qb = (int)(signed char)((m.y >> 24) & 0xff);
+                if (pb < pa || qb < qa) continue;
+                const int nst = (pb - pa + 2) >> 1;
+                const int ts = g % kR;
+                const int rl = m.z & 0xff, rh = (m.z >> 8) & 0xff;
+                const bool work = cg_on && r0 <= rh && r1 >= rl;        // warp-uniform
+                // one wait per hit (its first block's barrier counts all bytes of the hit).  A warp
+                // without work waits all the same: the wait keeps its release from running a whole
+                // ring cycle ahead of slower warps.  Only first blocks' barriers ever complete, so
+                // their phase is tracked per barrier.
+                const int blk0 = gb % kR;
+                mbar_wait(&s_full[blk0], (fullph >> blk0) & 1u);
+                fullph ^= 1u << blk0;
+                if (work) {
+                    const BwdSource& q = p.src[(unsigned)m.x >> 28];
+                    const int e0 = (l == 0) ? q.ring_edge : -1;
+                    const bool av_row = q.addvec != nullptr && P < kTabW;     // K slot 7 of block 0
+                    const bool av_fma = q.addvec != nullptr && !av_row;
+                    const int cl = (m.z >> 16) & 0xff, ch = (m.z >> 24) & 0xff;
+                    const float sbase = s_scale[h];
+                    const bool colok = gid >= cl && gid <= ch;
+                    const bool rok0 = r0 >= rl && r0 <= rh, rok1 = r1 >= rl && r1 <= rh;
+                    const int pw0 = qa + 2 * tq, pw1 = pw0 + 1;
+                    // BA border ring on the finest level: bins outside the interior count twice
+                    const bool pin0 = e0 > 0 && pw0 >= e0 && pw0 < P - e0;
+                    const bool pin1 = e0 > 0 && pw1 >= e0 && pw1 < P - e0;
+                    // column factors of the lane's two K slots: b* for a border bin row, i* inside
+                    float wx0 = 0.f, wx1 = 0.f, b0 = 0.f, b1 = 0.f, i0 = 0.f, i1 = 0.f;
+                    float w70 = 0.f, w71 = 0.f, rs0 = 0.f, rs1 = 0.f;
+                    for (int st = 0; st < nst; ++st) {
+                        const int blk = (gb + st) % kR;
+                        const int ph = pa + 2 * st;
+                        if (st == 0) {
+                            wx0 = (colok && pw0 <= qb) ? s_wx[ts][gid][pw0 & 7] : 0.f;
+                            wx1 = (colok && pw1 <= qb) ? s_wx[ts][gid][pw1 & 7] : 0.f;
+                            const float u0 = wx0 * sbase, u1 = wx1 * sbase;
+                            b0 = e0 >= 0 ? u0 + wx0 : u0;
+                            b1 = e0 >= 0 ? u1 + wx1 : u1;
+                            i0 = pin0 ? u0 : b0;
+                            i1 = pin1 ? u1 : b1;
+                            if (av_row && tq == 3) {         // the lane holding K slot 7: rowsum * colsum
+                                const float cs = colok ? s_wx[ts][gid][kTabW - 1] : 0.f;
+                                w70 = rok0 ? s_wy[ts][r0][kTabW - 1] * cs : 0.f;
+                                w71 = rok1 ? s_wy[ts][r1][kTabW - 1] * cs : 0.f;
+                            }
+                        }
+                        const bool hb = ph + 1 <= pb;
+                        const int phb = hb ? ph + 1 : ph;
+                        const float wya0 = rok0 ? s_wy[ts][r0][ph] : 0.f;
+                        const float wya1 = rok1 ? s_wy[ts][r1][ph] : 0.f;
+                        const float wyb0 = (hb && rok0) ? s_wy[ts][r0][phb] : 0.f;
+                        const float wyb1 = (hb && rok1) ? s_wy[ts][r1][phb] : 0.f;
+                        if (av_fma) {
+                            rs0 += wya0 + wyb0;
+                            rs1 += wya1 + wyb1;
+                        }
+                        const bool ina = e0 > 0 && ph >= e0 && ph < P - e0;
+                        const bool inb = e0 > 0 && phb >= e0 && phb < P - e0;
+                        const float xa0 = ina ? i0 : b0, xa1 = ina ? i1 : b1;
+                        const float xb0 = inb ? i0 : b0, xb1 = inb ? i1 : b1;
+                        float h0 = wya0 * xa1, h1 = wya1 * xa1;
+                        if (st == 0 && av_row && tq == 3) { h0 = w70; h1 = w71; }
+                        uint32_t a[4];
+                        a[0] = pack_bf16x2(wya0 * xa0, h0);
+                        a[1] = pack_bf16x2(wya1 * xa0, h1);
+                        a[2] = pack_bf16x2(wyb0 * xb0, wyb0 * xb1);
+                        a[3] = pack_bf16x2(wyb1 * xb0, wyb1 * xb1);
+                        if (__any_sync(0xffffffffu, (a[0] | a[1] | a[2] | a[3]) != 0u)) {
+                            const uint32_t base = ring_u32 + (uint32_t)blk * kMmaBlockBytes + ld_off;
+#pragma unroll
+                            for (int jj = 0; jj < kNT / 2; ++jj) {
+                                uint32_t bf[4];
+                                ldmatrix_x4_trans(base + jj * 32u, bf);
+                                mma_bf16_16816(acc[2 * jj], a, bf[0], bf[1]);
+                                mma_bf16_16816(acc[2 * jj + 1], a, bf[2], bf[3]);
+                            }
+                        }
+                        if (st == nst - 1 && av_fma) {
+                            float cs = wx0 + wx1;             // column sum over the staged bin columns
+                            cs += __shfl_xor_sync(0xffffffffu, cs, 1);
+                            cs += __shfl_xor_sync(0xffffffffu, cs, 2);
+                            const float w0 = rs0 * cs, w1 = rs1 * cs;
+                            const float* av = &s_av[ts][cg * kCW + 2 * tq];
+#pragma unroll
+                            for (int j = 0; j < kNT; ++j) {
+                                const float2 v = *reinterpret_cast<const float2*>(av + j * 8);
+                                acc[j][0] = fmaf(w0, v.x, acc[j][0]);
+                                acc[j][1] = fmaf(w0, v.y, acc[j][1]);
+                                acc[j][2] = fmaf(w1, v.x, acc[j][2]);
+                                acc[j][3] = fmaf(w1, v.y, acc[j][3]);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0)
+                    for (int st = 0; st < nst; ++st) mbar_arrive(&s_empty[(gb + st) % kR]);
+                gb += (unsigned)nst;
+                ++g;
+            }
+        }
+        if (c_begin < total_chunks) __syncthreads();      // the record table is rewritten by the next batch
+    }
+
+    // ---- every dX element of the tile is written once: accumulators -> staging -> 128-bit stores
+    __syncthreads();                              // all copies consumed: the ring is free
+    float* stage = reinterpret_cast<float*>(bwd_smem);      // [64 px][kStagePitch]
+    if (!producer && cg_on) {
+#pragma unroll
+        for (int j = 0; j < kNT; ++j) {
+            const int c = cg * kCW + j * 8 + 2 * tq;
+            *reinterpret_cast<float2*>(stage + (r0 * kTile + gid) * kStagePitch + c) =
+                make_float2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<float2*>(stage + (r1 * kTile + gid) * kStagePitch + c) =
+                make_float2(acc[j][2], acc[j][3]);
+        }
+    }
+    __syncthreads();
+    if (p.trace && tid == 0) {
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        unsigned long long* rec = p.trace + (size_t)blockIdx.x * 6;
+        rec[0] = t_start; rec[1] = t_end; rec[2] = g; rec[3] = gb; rec[4] = smid; rec[5] = (unsigned)l;
+    }
+    if (!producer && lane * 8 < C) {
+#pragma unroll
+        for (int i = 0; i < 64 / kW; ++i) {
+            const int px = i * kW + warp;
+            const int row = row0 + (px >> 3), col = col0 + (px & 7);
+            if (row < H && col < W) {
+                float v[8];
+                ld_smem8<float>(stage + px * kStagePitch + lane * 8, v);
+                if (!p.nchw) {
+                    Vec8<TDx, false>::store(dx + (((size_t)b * H + row) * W + col) * C, lane, C, v);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        st_elem(dx + (((size_t)b * C + lane * 8 + e) * H + row) * W + col, v[e]);
+                }
+            }
+        }
+    }
+}
+
 static int fill_levels(LevelDev* dst, const HtdLevel* src, int L, const char* who) {
     HTD_CHECK_ARG(src != nullptr && L >= 1 && L <= HTD_MAX_LEVELS, "%s: need 1..%d levels, got %d",
                   who, HTD_MAX_LEVELS, L);
@@ -681,6 +1155,7 @@ using namespace htd;
 extern "C" {
 
 int htd_abi_version(void) { return HTD_ABI_VERSION; }
+void htd_debug_set_bwd_trace(unsigned long long* records) { g_bwd_trace = records; }
 const char* htd_last_error(void) { return g_err; }
 
 int htd_level_assign(const float* rois, int K, int num_levels, float finest_scale,
@@ -824,6 +1299,7 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
     HTD_CHECK_ARG(nsrc >= 0 && nsrc <= HTD_MAX_BWD_SOURCES && (nsrc == 0 || sources),
                   "htd_roi_align_bwd: need 0..%d sources, got %d", HTD_MAX_BWD_SOURCES, nsrc);
     p.nsrc = 0;
+    int any_av_bf16 = 0;
     for (int i = 0; i < nsrc; ++i) {
         const HtdBwdSource& q = sources[i];
         HTD_CHECK_ARG(q.K >= 0, "htd_roi_align_bwd: source %d has K=%d", i, q.K);
@@ -833,9 +1309,16 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
         BwdSource& d = p.src[p.nsrc++];
         d.rois = q.rois; d.boxes = reinterpret_cast<const int4*>(q.boxes); d.offsets = q.offsets;
         d.ranges = q.ranges; d.weights = q.weights; d.dy = q.dy; d.scale = q.scale;
-        d.addvec = q.addvec; d.K = q.K; d.dy_per_level = q.dy_per_level; d.ring_edge = q.ring_edge;
+        d.addvec = static_cast<const float*>(q.addvec); d.K = q.K; d.dy_per_level = q.dy_per_level;
+        d.ring_edge = q.ring_edge;
+        d.av_bf16 = (q.addvec != nullptr && q.addvec_dtype == HTD_BF16) ? 1 : 0;
+        HTD_CHECK_ARG(q.addvec == nullptr || q.addvec_dtype == HTD_F32 || q.addvec_dtype == HTD_BF16,
+                      "htd_roi_align_bwd: source %d has addvec_dtype=%d", i, q.addvec_dtype);
+        any_av_bf16 |= d.av_bf16;
     }
     p.L = L; p.B = B; p.C = C; p.P = pooled; p.nchw = dx_nchw ? 1 : 0;
+    p.trace = g_bwd_trace;
+
     long long total = 0;
     for (int l = 0; l < L; ++l) {
         p.tile_start[l] = (int)total;
@@ -864,6 +1347,53 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
         }                                                                                         \
         roi_align_bwd_kernel<TY, TX><<<grid, block, smem, st>>>(p);                               \
     } while (0)
+    // bf16 dY: tensor-pipe contraction per hit (roi_align_bwd_mma_kernel).  HTD_BWD_KERNEL selects
+    // for measurements: "scalar" = the FFMA kernel, "mma1".."mma5" = warp layouts / ring depths below.
+    static int variant = -1;
+    if (variant < 0) {
+        const char* ev = getenv("HTD_BWD_KERNEL");
+        variant = !ev ? 3 : !strcmp(ev, "scalar") ? 0 : !strcmp(ev, "mma1") ? 1 : !strcmp(ev, "mma2") ? 2 :
+                  !strcmp(ev, "mma3") ? 3 : !strcmp(ev, "mma4") ? 4 : !strcmp(ev, "mma5") ? 5 : 3;
+    }
+    const bool mma = dy_dtype == HTD_BF16 && variant != 0 && C % 64 == 0 && C <= 256;
+    HTD_CHECK_ARG(!any_av_bf16 || (mma && pooled < kTabW),
+                  "htd_roi_align_bwd: a bf16 addvec needs bf16 dy, pooled < %d, C %% 64 == 0, C <= 256 "
+                  "(and HTD_BWD_KERNEL != scalar)", kTabW);
+    if (mma) {
+#define HTD_BWD_MMA_LAUNCH(TX, S, N, G)                                                           \
+    do {                                                                                          \
+        static bool attr_done = false;                                                            \
+        if (!attr_done) {                                                                         \
+            cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_mma_kernel<TX, S, N, G>,           \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                 S * kMmaBlockBytes);                              \
+            if (e != cudaSuccess) {                                                               \
+                set_error("htd_roi_align_bwd: shared memory opt-in failed: %s",                   \
+                          cudaGetErrorString(e));                                                 \
+                return HTD_ERR_CUDA;                                                              \
+            }                                                                                     \
+            attr_done = true;                                                                     \
+        }                                                                                         \
+        roi_align_bwd_mma_kernel<TX, S, N, G>                                                     \
+            <<<grid, (4 * G + 1) * 32, S * kMmaBlockBytes, st>>>(p);                               \
+    } while (0)
+#define HTD_BWD_MMA_VARIANT(S, N, G)                                                              \
+    do {                                                                                          \
+        if (dx_dtype == HTD_F32) HTD_BWD_MMA_LAUNCH(float, S, N, G);                              \
+        else HTD_BWD_MMA_LAUNCH(__nv_bfloat16, S, N, G);                                          \
+    } while (0)
+        switch (variant) {
+            case 1: HTD_BWD_MMA_VARIANT(12, 1, 4); break;    // 16 warps x 64 ch, 12 blocks
+            case 2: HTD_BWD_MMA_VARIANT(8, 2, 4); break;     // same, 8 blocks, 2 CTAs / SM
+            case 4: HTD_BWD_MMA_VARIANT(8, 2, 1); break;     // 4 warps x 256 ch, 8 blocks, 2 CTAs / SM
+            case 5: HTD_BWD_MMA_VARIANT(12, 1, 2); break;    // 8 warps x 128 ch, 12 blocks
+            default: HTD_BWD_MMA_VARIANT(8, 2, 2); break;    // 8 warps x 128 ch, 8 blocks, 2 CTAs / SM
+        }
+#undef HTD_BWD_MMA_VARIANT
+#undef HTD_BWD_MMA_LAUNCH
+        HTD_CHECK_LAUNCH("htd_roi_align_bwd(mma)");
+        return HTD_OK;
+    }
     if (dy_dtype == HTD_F32 && dx_dtype == HTD_F32) HTD_BWD_LAUNCH(float, float);
     else if (dy_dtype == HTD_F32 && dx_dtype == HTD_BF16) HTD_BWD_LAUNCH(float, __nv_bfloat16);
     else if (dy_dtype == HTD_BF16 && dx_dtype == HTD_F32) HTD_BWD_LAUNCH(__nv_bfloat16, float);
@@ -881,7 +1411,7 @@ int htd_roi_align_bwd(const HtdLevel* grad_levels, int L, int B, int C, int dx_d
     HtdBwdSource q;
     q.rois = rois; q.boxes = boxes; q.offsets = offsets; q.ranges = ranges; q.weights = weights;
     q.dy = dy; q.scale = scale; q.addvec = addvec; q.K = K; q.dy_per_level = dy_per_level;
-    q.ring_edge = ring_edge; q.reserved = 0;
+    q.ring_edge = ring_edge; q.addvec_dtype = HTD_F32;
     return htd_roi_align_bwd_multi(grad_levels, L, B, C, dx_dtype, 0, &q, 1, pooled, dy_dtype,
                                    stream);
 }

@@ -8,6 +8,8 @@ NCHW tensors).
 """
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib
@@ -222,9 +224,15 @@ def _bwd_multi(feat_shapes, out_dtype, nchw, scales, sources, pooled):
         a.rois, a.boxes, a.offsets = q['rois'].data_ptr(), boxes.data_ptr(), offsets.data_ptr()
         a.ranges, a.weights, a.dy = ranges.data_ptr(), weights.data_ptr(), q['dy'].data_ptr()
         a.scale = q['scale'].data_ptr() if q.get('scale') is not None else None
-        a.addvec = q['addvec'].data_ptr() if q.get('addvec') is not None else None
+        av = q.get('addvec')
+        if av is not None and q['dy'].dtype == torch.bfloat16 and pooled < 8 and C % 64 == 0 \
+                and C <= 256 and os.environ.get('HTD_BWD_KERNEL') != 'scalar':
+            # the tensor-pipe gather takes the add vector as one more bf16 K row of the hit
+            av = q['_addvec_bf16'] = av.to(torch.bfloat16)
+        a.addvec = av.data_ptr() if av is not None else None
+        a.addvec_dtype = dt(av.dtype) if av is not None else 0
         a.K, a.dy_per_level = q['rois'].shape[0], int(bool(q.get('dy_per_level', False)))
-        a.ring_edge, a.reserved = int(q.get('ring_edge', -1)), 0
+        a.ring_edge = int(q.get('ring_edge', -1))
         if _lib.ACCOUNT is not None:  # 49*C*b_dy + fh*fw*C*4 per (RoI, level)
             acct += q['dy'].numel() * q['dy'].element_size() + _count_pixels(boxes) * C * 4
     if _lib.ACCOUNT is not None:

@@ -133,15 +133,20 @@ typedef struct HtdBwdSource {
     const float* weights;
     const void* dy;
     const float* scale;
-    const float* addvec;
+    const void* addvec;       /* fp32, or bf16 when addvec_dtype == HTD_BF16 */
     int32_t K;
     int32_t dy_per_level;
     int32_t ring_edge;
-    int32_t reserved;
+    int32_t addvec_dtype;     /* HTD_F32 (0) | HTD_BF16: bf16 needs dy bf16, pooled < 8, C % 64 == 0, C <= 256 */
 } HtdBwdSource;
 int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
                             int dx_nchw, const HtdBwdSource* sources, int nsrc, int pooled,
                             int dy_dtype, htd_stream_t stream);
+
+/* Diagnostics (tools/trace_bwd.py): when `records` is non-null the bf16 backward gather writes per
+ * CTA six uint64 {globaltimer at start, at end, hits, K-step blocks, SM id, level} at
+ * records[6 * blockIdx]; pass NULL to switch it off.  Not part of the reference's interface. */
+void htd_debug_set_bwd_trace(unsigned long long* records);
 
 /* Layout / dtype conversion: src [N, R, S] -> dst [N, S, R] (NCHW->NHWC with R=C, S=H*W and
  * back with R=H*W, S=C).  dtypes HTD_F32 / HTD_BF16 independently for src and dst. */

@@ -33,7 +33,8 @@ def test_python_binding_covers_the_header():
     missing = set(_declared()) - set(_lib.SIGNATURES) - {'htd_abi_version', 'htd_last_error',
                                                              'htd_roi_plan_rows_bound',
                                                              'htd_pgraph_max_tiles',
-                                                             'htd_multiclass_nms_workspace_bytes'}
+                                                             'htd_multiclass_nms_workspace_bytes',
+                                                             'htd_debug_set_bwd_trace'}
     assert not missing, missing
 
 
