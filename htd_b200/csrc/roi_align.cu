@@ -32,6 +32,7 @@ namespace htd {
 
 static thread_local char g_err[512] = "";
 static unsigned long long* g_bwd_trace = nullptr;    // see htd_debug_set_bwd_trace
+static int g_bwd_variant = -1;                       // see htd_debug_set_bwd_variant
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -1156,6 +1157,7 @@ extern "C" {
 
 int htd_abi_version(void) { return HTD_ABI_VERSION; }
 void htd_debug_set_bwd_trace(unsigned long long* records) { g_bwd_trace = records; }
+void htd_debug_set_bwd_variant(int variant) { g_bwd_variant = variant; }
 const char* htd_last_error(void) { return g_err; }
 
 int htd_level_assign(const float* rois, int K, int num_levels, float finest_scale,
@@ -1349,12 +1351,13 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
     } while (0)
     // bf16 dY: tensor-pipe contraction per hit (roi_align_bwd_mma_kernel).  HTD_BWD_KERNEL selects
     // for measurements: "scalar" = the FFMA kernel, "mma1".."mma5" = warp layouts / ring depths below.
-    static int variant = -1;
-    if (variant < 0) {
+    static int env_variant = -1;
+    if (env_variant < 0) {
         const char* ev = getenv("HTD_BWD_KERNEL");
-        variant = !ev ? 3 : !strcmp(ev, "scalar") ? 0 : !strcmp(ev, "mma1") ? 1 : !strcmp(ev, "mma2") ? 2 :
-                  !strcmp(ev, "mma3") ? 3 : !strcmp(ev, "mma4") ? 4 : !strcmp(ev, "mma5") ? 5 : 3;
+        env_variant = !ev ? 3 : !strcmp(ev, "scalar") ? 0 : !strcmp(ev, "mma1") ? 1 : !strcmp(ev, "mma2") ? 2 :
+                      !strcmp(ev, "mma3") ? 3 : !strcmp(ev, "mma4") ? 4 : !strcmp(ev, "mma5") ? 5 : 3;
     }
+    const int variant = (g_bwd_variant >= 0 && g_bwd_variant <= 5) ? g_bwd_variant : env_variant;
     const bool mma = dy_dtype == HTD_BF16 && variant != 0 && C % 64 == 0 && C <= 256;
     HTD_CHECK_ARG(!any_av_bf16 || (mma && pooled < kTabW),
                   "htd_roi_align_bwd: a bf16 addvec needs bf16 dy, pooled < %d, C %% 64 == 0, C <= 256 "

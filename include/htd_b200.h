@@ -89,7 +89,10 @@ int htd_roi_footprints(const HtdLevel* levels, int L, int B, const float* rois, 
  *                     column (x lo[8], x hi[8]) it samples (hi < lo: empty bin);
  *   weights [rows_cap][HTD_MAX_POOLED] fp32 separable axis weights: row offsets[e] + (r - row0)
  *                     holds Wy[p][r] for the P bins, row offsets[e] + fh + (c - col0) holds Wx[p][c]
- *                     (aligned=True, avg pooling; sampling_ratio 0 = adaptive ceil(roi/P) grid).
+ *                     (aligned=True, avg pooling; sampling_ratio 0 = adaptive ceil(roi/P) grid);
+ *                     with pooled < HTD_MAX_POOLED the last entry of every row holds the sum of
+ *                     the row's P weights (read by the bf16 backward's add-vector term), the
+ *                     entries P .. HTD_MAX_POOLED-2 are 0.
  * rows_cap >= htd_roi_plan_rows_bound(levels, L, K, roi_level != NULL). */
 long long htd_roi_plan_rows_bound(const HtdLevel* levels, int L, int K, int single_level);
 int htd_roi_plan(const HtdLevel* levels, int L, int B, const float* rois, int K,
@@ -147,6 +150,11 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
  * CTA six uint64 {globaltimer at start, at end, hits, K-step blocks, SM id, level} at
  * records[6 * blockIdx]; pass NULL to switch it off.  Not part of the reference's interface. */
 void htd_debug_set_bwd_trace(unsigned long long* records);
+
+/* Diagnostics / tests: kernel used for bf16 dy by htd_roi_align_bwd(_multi).  0 = the scalar FFMA
+ * gather (also the fp32 path), 1..5 = warp layouts / ring depths of the tensor-pipe gather (3 is
+ * the default), -1 = back to the default (or the HTD_BWD_KERNEL environment variable). */
+void htd_debug_set_bwd_variant(int variant);
 
 /* Layout / dtype conversion: src [N, R, S] -> dst [N, S, R] (NCHW->NHWC with R=C, S=H*W and
  * back with R=H*W, S=C).  dtypes HTD_F32 / HTD_BF16 independently for src and dst. */

@@ -34,7 +34,8 @@ def test_python_binding_covers_the_header():
                                                              'htd_roi_plan_rows_bound',
                                                              'htd_pgraph_max_tiles',
                                                              'htd_multiclass_nms_workspace_bytes',
-                                                             'htd_debug_set_bwd_trace'}
+                                                             'htd_debug_set_bwd_trace',
+                                                             'htd_debug_set_bwd_variant'}
     assert not missing, missing
 
 
