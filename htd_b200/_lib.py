@@ -157,6 +157,8 @@ def lib():
         L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
         L.htd_debug_set_bwd_trace.restype = None
         L.htd_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
+        L.htd_roi_align_bwd_uses_tensor_pipe.restype = c_int
+        L.htd_roi_align_bwd_uses_tensor_pipe.argtypes = [c_int, c_int, c_int]
         L.htd_debug_set_bwd_variant.restype = None
         L.htd_debug_set_bwd_variant.argtypes = [c_int]
         for name, args in SIGNATURES.items():

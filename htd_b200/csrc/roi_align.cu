@@ -1285,6 +1285,24 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     return HTD_OK;
 }
 
+// bf16 dY: tensor-pipe contraction per hit (roi_align_bwd_mma_kernel).  HTD_BWD_KERNEL (or
+// htd_debug_set_bwd_variant) selects for measurements: "scalar" = the FFMA kernel, "mma1".."mma5" =
+// the warp layouts / ring depths listed at the launch below; default mma3.
+static int bwd_variant() {
+    static int env_variant = -1;
+    if (env_variant < 0) {
+        const char* ev = getenv("HTD_BWD_KERNEL");
+        env_variant = !ev ? 3 : !strcmp(ev, "scalar") ? 0 : !strcmp(ev, "mma1") ? 1 : !strcmp(ev, "mma2") ? 2 :
+                      !strcmp(ev, "mma3") ? 3 : !strcmp(ev, "mma4") ? 4 : !strcmp(ev, "mma5") ? 5 : 3;
+    }
+    return (g_bwd_variant >= 0 && g_bwd_variant <= 5) ? g_bwd_variant : env_variant;
+}
+
+int htd_roi_align_bwd_uses_tensor_pipe(int C, int pooled, int dy_dtype) {
+    (void)pooled;
+    return (dy_dtype == HTD_BF16 && bwd_variant() != 0 && C % 64 == 0 && C >= 64 && C <= 256) ? 1 : 0;
+}
+
 int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, int dx_dtype,
                             int dx_nchw, const HtdBwdSource* sources, int nsrc, int pooled,
                             int dy_dtype, htd_stream_t stream) {
@@ -1349,16 +1367,8 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
         }                                                                                         \
         roi_align_bwd_kernel<TY, TX><<<grid, block, smem, st>>>(p);                               \
     } while (0)
-    // bf16 dY: tensor-pipe contraction per hit (roi_align_bwd_mma_kernel).  HTD_BWD_KERNEL selects
-    // for measurements: "scalar" = the FFMA kernel, "mma1".."mma5" = warp layouts / ring depths below.
-    static int env_variant = -1;
-    if (env_variant < 0) {
-        const char* ev = getenv("HTD_BWD_KERNEL");
-        env_variant = !ev ? 3 : !strcmp(ev, "scalar") ? 0 : !strcmp(ev, "mma1") ? 1 : !strcmp(ev, "mma2") ? 2 :
-                      !strcmp(ev, "mma3") ? 3 : !strcmp(ev, "mma4") ? 4 : !strcmp(ev, "mma5") ? 5 : 3;
-    }
-    const int variant = (g_bwd_variant >= 0 && g_bwd_variant <= 5) ? g_bwd_variant : env_variant;
-    const bool mma = dy_dtype == HTD_BF16 && variant != 0 && C % 64 == 0 && C <= 256;
+    const int variant = bwd_variant();
+    const bool mma = htd_roi_align_bwd_uses_tensor_pipe(C, pooled, dy_dtype) != 0;
     HTD_CHECK_ARG(!any_av_bf16 || (mma && pooled < kTabW),
                   "htd_roi_align_bwd: a bf16 addvec needs bf16 dy, pooled < %d, C %% 64 == 0, C <= 256 "
                   "(and HTD_BWD_KERNEL != scalar)", kTabW);

@@ -225,8 +225,8 @@ def _bwd_multi(feat_shapes, out_dtype, nchw, scales, sources, pooled):
         a.ranges, a.weights, a.dy = ranges.data_ptr(), weights.data_ptr(), q['dy'].data_ptr()
         a.scale = q['scale'].data_ptr() if q.get('scale') is not None else None
         av = q.get('addvec')
-        if av is not None and q['dy'].dtype == torch.bfloat16 and pooled < 8 and C % 64 == 0 \
-                and C <= 256 and os.environ.get('HTD_BWD_KERNEL') != 'scalar':
+        if av is not None and pooled < 8 and \
+                lib().htd_roi_align_bwd_uses_tensor_pipe(int(C), int(pooled), dt(q['dy'].dtype)):
             # the tensor-pipe gather takes the add vector as one more bf16 K row of the hit
             av = q['_addvec_bf16'] = av.to(torch.bfloat16)
         a.addvec = av.data_ptr() if av is not None else None

@@ -146,6 +146,12 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
                             int dx_nchw, const HtdBwdSource* sources, int nsrc, int pooled,
                             int dy_dtype, htd_stream_t stream);
 
+/* 1 when htd_roi_align_bwd(_multi) with these sizes runs the bf16 tensor-pipe gather (bf16 dy, C a
+ * multiple of 64 in 64..256, not switched off by HTD_BWD_KERNEL=scalar / htd_debug_set_bwd_variant),
+ * else 0 (the exact scalar gather).  A bf16 add vector (addvec_dtype == HTD_BF16) is accepted only
+ * when this returns 1 and pooled < HTD_MAX_POOLED. */
+int htd_roi_align_bwd_uses_tensor_pipe(int C, int pooled, int dy_dtype);
+
 /* Diagnostics (tools/trace_bwd.py): when `records` is non-null the bf16 backward gather writes per
  * CTA six uint64 {globaltimer at start, at end, hits, K-step blocks, SM id, level} at
  * records[6 * blockIdx]; pass NULL to switch it off.  Not part of the reference's interface. */
