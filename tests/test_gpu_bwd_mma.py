@@ -34,22 +34,23 @@ def _rand_rois(K, B, H, W, gen, smin=8., smax=None):
                         (cx + w / 2).clamp(0, W), (cy + h / 2).clamp(0, H)], 1)
 
 
-def _sources(shapes, rois, pos, C, gen, with_ba=True):
+def _sources(shapes, rois, pos, C, gen, with_ba=True, pooled=7):
     """Three sources as in a training step: two single-level extractions and the BA extraction."""
+    P = pooled
     dev = 'cuda'
     x = [torch.empty(s, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
          for s in shapes]
     rois, pos = rois.to(dev), pos.to(dev)
     lv = ops.level_assign(rois, 4)
-    ps = ops.RoIPlan(x, SCALES, rois, lv, 7, 0)
-    g1 = torch.randn(rois.shape[0], 7, 7, C, generator=gen).to(dev).to(torch.bfloat16)
-    g2 = torch.randn(rois.shape[0], 7, 7, C, generator=gen).to(dev).to(torch.bfloat16)
+    ps = ops.RoIPlan(x, SCALES, rois, lv, P, 0)
+    g1 = torch.randn(rois.shape[0], P, P, C, generator=gen).to(dev).to(torch.bfloat16)
+    g2 = torch.randn(rois.shape[0], P, P, C, generator=gen).to(dev).to(torch.bfloat16)
     src = [dict(rois=rois, plan=ps.tensors(), dy=g1, dy_per_level=False),
            dict(rois=rois, plan=ps.tensors(), dy=g2, dy_per_level=False)]
     keep = [ps]
     if with_ba:
-        pb = ops.RoIPlan(x, SCALES, pos, None, 7, 0)
-        gp = torch.randn(pos.shape[0], 7, 7, C, generator=gen).to(dev).to(torch.bfloat16)
+        pb = ops.RoIPlan(x, SCALES, pos, None, P, 0)
+        gp = torch.randn(pos.shape[0], P, P, C, generator=gen).to(dev).to(torch.bfloat16)
         src.append(dict(rois=pos, plan=pb.tensors(), dy=gp, dy_per_level=False,
                         scale=torch.rand(4, pos.shape[0], generator=gen).to(dev), ring_edge=1,
                         addvec=torch.randn(4 * pos.shape[0], C, generator=gen).to(dev)))
@@ -66,11 +67,11 @@ def _fp32(src):
     return out
 
 
-def _run(shapes, dtype, nchw, src, variant):
+def _run(shapes, dtype, nchw, src, variant, pooled=7):
     L = _lib.lib()
     L.htd_debug_set_bwd_variant(variant)
     try:
-        out = ops._bwd_multi(shapes, dtype, nchw, SCALES, [dict(q) for q in src], 7)
+        out = ops._bwd_multi(shapes, dtype, nchw, SCALES, [dict(q) for q in src], pooled)
         torch.cuda.synchronize()
     finally:
         L.htd_debug_set_bwd_variant(-1)
@@ -116,6 +117,21 @@ def test_mma_more_hits_than_the_record_table_rescans():
     assert _err(got, ref) <= TOL
     got4 = _run(shapes, torch.bfloat16, False, src, 4)
     assert _err(got4, ref) <= TOL
+
+
+@pytest.mark.parametrize('pooled', [2, 3, 8])
+def test_mma_other_output_sizes(pooled):
+    """pooled == 8 fills all eight K slots of a bin row, so the BA add vector takes the fp32 rank-1
+    form instead of K slot 7; small grids leave most slots at weight 0."""
+    gen = torch.Generator().manual_seed(20 + pooled)
+    B, C, H, W = 2, 256, 40, 56
+    shapes = _pyramid_shapes(B, C, H, W)
+    rois = _rand_rois(300, B, H * 4, W * 4, gen)
+    pos = _rand_rois(48, B, H * 4, W * 4, gen)
+    src, keep = _sources(shapes, rois, pos, C, gen, pooled=pooled)
+    ref = _run(shapes, torch.float32, False, _fp32(src), 0, pooled)
+    for variant in (3, 4):
+        assert _err(_run(shapes, torch.bfloat16, False, src, variant, pooled), ref) <= TOL
 
 
 @pytest.mark.parametrize('C', [64, 128, 192])
