@@ -210,6 +210,8 @@ struct FwdParams {
     const float* weights;
     const float* bias;
     void* out;
+    int region;     // bytes of the staging region in dynamic shared memory (barriers follow it)
+    int strip;      // 1: stage the whole bin-row strip of a small RoI at once (see the kernel)
 };
 
 // Shared-memory staged forward.  One CTA per (RoI, level, output row ph), one warp per output
@@ -226,6 +228,12 @@ struct FwdParams {
 #endif
 constexpr int kFwdStages = HTD_FWD_STAGES;
 constexpr int kFwdPx = HTD_FWD_PX;
+constexpr int kFwdStripBytes = 72 * 1024;      // strip-path staging budget (>= the bf16 rings)
+inline int fwd_smem_max(int elem) {
+    int region = HTD_MAX_POOLED * kFwdStages * kFwdPx * 256 * elem;
+    if (region < kFwdStripBytes) region = kFwdStripBytes;
+    return region + HTD_MAX_POOLED * kFwdStages * 8;
+}
 
 template <typename TIn>
 __device__ __forceinline__ void ld_smem8(const TIn* p, float (&v)[8]);
@@ -263,11 +271,10 @@ __global__ void __launch_bounds__(HTD_MAX_POOLED * 32) roi_align_fwd_kernel(cons
     const int cw = min(p.C, 256);                       // channels staged per pixel
     const int stage_elems = kFwdPx * cw;
     TIn* ring = reinterpret_cast<TIn*>(fwd_smem) + (size_t)pw * kFwdStages * stage_elems;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(
-                             fwd_smem + (size_t)P * kFwdStages * stage_elems * sizeof(TIn)) +
-                         pw * kFwdStages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(fwd_smem + p.region);
+    uint64_t* full_bar = bars + pw * kFwdStages;
 
-    int H = 1, W = 1, ry0 = 0, ry1 = -1, cx0 = 0, cx1 = -1;
+    int H = 1, W = 1, ry0 = 0, ry1 = -1, cx0 = 0, cx1 = -1, bz = 0, bw = -1;
     const TIn* feat = nullptr;
     const float* wyt = nullptr;
     const float* wxt = nullptr;
@@ -284,12 +291,71 @@ __global__ void __launch_bounds__(HTD_MAX_POOLED * 32) roi_align_fwd_kernel(cons
             wxt = p.weights + (off + fh + (cx0 - box.z)) * kTabW + pw;
             H = p.lv[l].H; W = p.lv[l].W;
             feat = static_cast<const TIn*>(p.lv[l].data);
+            bz = box.z; bw = box.w;
         }
     }
     const int ny = ry1 - ry0 + 1, nx = cx1 - cx0 + 1;
+    TOut* orow = static_cast<TOut*>(p.out) + ((size_t)task * PP + ph * P + pw) * p.C;
+
+    // ---- strip path (small RoIs: every single-level extraction, the coarse levels of BA): the
+    // footprint rows of this bin row over the RoI's full width fit the staging region, so they are
+    // fetched with ONE bulk copy per row, all in flight at once (one memory latency per CTA instead
+    // of one per ring turn, and pixels shared by neighbouring bins are read once); the seven warps
+    // then reduce their bins from the shared strip in the same order as the ring path (same bits).
+    const int nxs = bw - bz + 1;
+    if (p.strip && p.C <= 256 && ny > 0 && nxs > 0 &&
+        (size_t)ny * nxs * p.C * sizeof(TIn) <= (size_t)p.region) {           // CTA-uniform
+        TIn* sbuf = reinterpret_cast<TIn*>(fwd_smem);
+        const uint32_t row_bytes = (uint32_t)(nxs * p.C * sizeof(TIn));
+        if (threadIdx.x == 0) {
+            mbar_init(bars, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (pw == 0) {
+            if (lane == 0) mbar_expect_tx(bars, (uint32_t)ny * row_bytes);
+            __syncwarp();
+            for (int r = lane; r < ny; r += 32)
+                bulk_g2s(sbuf + (size_t)r * nxs * p.C,
+                         feat + (((size_t)b * H + ry0 + r) * W + bz) * p.C, row_bytes, bars);
+        }
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const bool lane_on = lane * 8 < p.C;
+        mbar_wait(bars, 0u);                              // every warp: no exit with copies in flight
+        if (nx > 0) {
+            float wy_l = 0.f, wx_l = 0.f;
+            for (int y = 0; y < ny; ++y) {
+                if ((y & 31) == 0) wy_l = (y + lane < ny) ? __ldg(wyt + (size_t)(y + lane) * kTabW) : 0.f;
+                const float wyv = __shfl_sync(0xffffffffu, wy_l, y & 31);
+                if (wyv == 0.f) continue;
+                const TIn* src = sbuf + ((size_t)y * nxs + (cx0 - bz)) * p.C + lane * 8;
+                for (int x = 0; x < nx; ++x) {
+                    if ((x & 31) == 0) wx_l = (x + lane < nx) ? __ldg(wxt + (size_t)(x + lane) * kTabW) : 0.f;
+                    const float w = wyv * __shfl_sync(0xffffffffu, wx_l, x & 31);
+                    if (lane_on) {
+                        float v[8];
+                        ld_smem8<TIn>(src + (size_t)x * p.C, v);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+                    }
+                }
+            }
+        }
+        if (p.bias && bvalid) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = lane * 8 + e;
+                if (c < p.C) acc[e] += __ldg(p.bias + (size_t)b * p.C + c);
+            }
+        }
+        Vec8<TOut, false>::store(orow, lane, p.C, acc);
+        return;
+    }
+
     const int nseg = (nx + kFwdPx - 1) / kFwdPx;        // segments per footprint row
     const int total = (ny > 0 && nx > 0) ? ny * nseg : 0;
-    TOut* orow = static_cast<TOut*>(p.out) + ((size_t)task * PP + ph * P + pw) * p.C;
 
     if (total > 0) {
         if (lane == 0) {
@@ -1258,15 +1324,25 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     dim3 grid((unsigned)blocks), block(pooled * 32);
     cudaStream_t st = (cudaStream_t)stream;
     const int cw = C < 256 ? C : 256;
-    const size_t smem = (size_t)pooled * kFwdStages * (kFwdPx * cw * dtype_size(in_dtype) +
-                                                       sizeof(uint64_t));
+    // staging region: the per-warp rings, or at least kFwdStripBytes for the strip path (three CTAs
+    // of 72 KB + barriers per SM); HTD_FWD_KERNEL=ring switches the strip path off (measurements)
+    static int strip_on = -1;
+    if (strip_on < 0) {
+        const char* ev = getenv("HTD_FWD_KERNEL");
+        strip_on = (ev && !strcmp(ev, "ring")) ? 0 : 1;
+    }
+    size_t region = (size_t)pooled * kFwdStages * kFwdPx * cw * dtype_size(in_dtype);
+    if (strip_on && region < (size_t)kFwdStripBytes) region = kFwdStripBytes;
+    p.region = (int)region;
+    p.strip = strip_on;
+    const size_t smem = region + (size_t)pooled * kFwdStages * sizeof(uint64_t);
 #define HTD_FWD_LAUNCH(TI, TO)                                                                    \
     do {                                                                                          \
         static bool attr_done = false;                                                            \
         if (!attr_done) {                                                                         \
             cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_kernel<TI, TO>,                    \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                                 HTD_MAX_POOLED * kFwdStages * (kFwdPx * 256 * (int)sizeof(TI) + 8)); \
+                                                 fwd_smem_max((int)sizeof(TI)));                  \
             if (e != cudaSuccess) {                                                               \
                 set_error("htd_roi_align_fwd: shared memory opt-in failed: %s",                   \
                           cudaGetErrorString(e));                                                 \
