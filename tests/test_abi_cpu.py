@@ -56,6 +56,44 @@ def test_struct_layout_matches_header():
     from htd_b200 import _lib
     assert ctypes.sizeof(_lib.HtdGemmGroup) == 48
     assert ctypes.sizeof(_lib.HtdLevel) == 24
+    assert ctypes.sizeof(_lib.HtdBwdSource) == 8 * 8 + 4 * 4       # 8 pointers + K, dy_per_level, ring_edge, addvec_dtype
+
+
+def test_backward_kernel_choice_is_a_host_decision(cdll):
+    """htd_roi_align_bwd_uses_tensor_pipe: bf16 dy with C a multiple of 64 in 64..256 takes the
+    tensor-pipe gather unless it is switched off; everything else the exact scalar gather."""
+    f = cdll.htd_roi_align_bwd_uses_tensor_pipe
+    F32, BF16 = 0, 1
+    assert f(256, 7, BF16) == 1 and f(64, 7, BF16) == 1 and f(128, 8, BF16) == 1
+    assert f(256, 7, F32) == 0                     # fp32 gradients: exact kernel
+    assert f(96, 7, BF16) == 0 and f(320, 7, BF16) == 0 and f(32, 7, BF16) == 0
+    cdll.htd_debug_set_bwd_variant(0)
+    try:
+        assert f(256, 7, BF16) == 0
+    finally:
+        cdll.htd_debug_set_bwd_variant(-1)
+    assert f(256, 7, BF16) == 1
+
+
+def test_backward_source_validation_without_gpu(cdll):
+    """A malformed add-vector dtype, and a bf16 add vector on a path that cannot take it, are
+    rejected before anything is launched."""
+    from htd_b200 import _lib
+    cdll.htd_last_error.restype = ctypes.c_char_p
+    lv = (_lib.HtdLevel * 1)()
+    lv[0].data, lv[0].H, lv[0].W, lv[0].spatial_scale = 0x1000, 8, 8, 0.25   # never dereferenced
+    src = (_lib.HtdBwdSource * 1)()
+    q = src[0]
+    q.rois = q.boxes = q.offsets = q.ranges = q.weights = q.dy = q.addvec = 0x1000
+    q.K, q.dy_per_level, q.ring_edge = 4, 0, -1
+    q.addvec_dtype = 7
+    rc = cdll.htd_roi_align_bwd_multi(lv, 1, 1, 256, 1, 0, src, 1, 7, 1, None)
+    assert rc == 1 and b'addvec_dtype' in cdll.htd_last_error()
+    q.addvec_dtype = 1                                        # bf16 add vector with fp32 gradients
+    rc = cdll.htd_roi_align_bwd_multi(lv, 1, 1, 256, 0, 0, src, 1, 7, 0, None)
+    assert rc == 1 and b'bf16 addvec' in cdll.htd_last_error()
+    rc = cdll.htd_roi_align_bwd_multi(lv, 1, 1, 256, 1, 0, src, 1, 8, 1, None)    # pooled == 8
+    assert rc == 1 and b'bf16 addvec' in cdll.htd_last_error()
 
 
 def test_product_does_not_import_the_oracle():
