@@ -79,6 +79,8 @@ SIGNATURES = {
                           c_float, c_float, c_int, c_int, c_void_p],
     'htd_multiclass_nms': [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'htd_multiclass_soft_nms': [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float,
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_assign_sample': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_float,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -155,6 +157,8 @@ def lib():
         L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
         L.htd_multiclass_nms_workspace_bytes.restype = c_ll
         L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
+        L.htd_multiclass_soft_nms_workspace_bytes.restype = c_ll
+        L.htd_multiclass_soft_nms_workspace_bytes.argtypes = [c_int, c_int]
         L.htd_debug_set_bwd_trace.restype = None
         L.htd_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
         L.htd_roi_align_bwd_uses_tensor_pipe.restype = c_int

@@ -310,10 +310,22 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1):
     sync until the final read of the detection count that sizes the returned tensors); CPU
     tensors are not supported (no fallback)."""
     cfg = dict(nms_cfg)
-    if cfg.pop('type', 'nms') != 'nms':
-        raise NotImplementedError('only hard NMS is provided (configs/htd/htd_resnet50_1x.py:166)')
-    thr = cfg.get('iou_threshold', cfg.get('iou_thr', 0.5))
+    kind = cfg.pop('type', 'nms')
+    if kind not in ('nms', 'soft_nms'):
+        raise NotImplementedError(f'nms type {kind!r}: configs/htd use nms (htd_resnet50_1x.py:166) '
+                                  'and soft_nms (htd_resnet101_2x.py:298)')
     from . import ops
-    det, labels, count = ops.multiclass_nms(multi_bboxes, multi_scores, score_thr, thr, max_num)
+    soft = None
+    if kind == 'soft_nms':
+        # mmcv.ops.soft_nms defaults: iou_threshold 0.3, sigma 0.5, min_score 1e-3, method 'linear',
+        # offset 0 (`iou_thr` is its deprecated alias of `iou_threshold`)
+        thr = cfg.get('iou_threshold', cfg.get('iou_thr', 0.3))
+        if cfg.get('offset', 0) != 0:
+            raise NotImplementedError('soft_nms with offset != 0')
+        soft = dict(min_score=cfg.get('min_score', 1e-3), method=cfg.get('method', 'linear'))
+    else:
+        thr = cfg.get('iou_threshold', cfg.get('iou_thr', 0.5))
+    det, labels, count = ops.multiclass_nms(multi_bboxes, multi_scores, score_thr, thr, max_num,
+                                            soft=soft)
     n = int(count)                                   # the one host read: output sizes
     return det[:n].to(multi_bboxes.dtype), labels[:n]

@@ -177,6 +177,223 @@ __global__ void __launch_bounds__(kNmsThreads) nms_merge_kernel(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Soft-NMS variant (configs/htd/htd_resnet101_2x.py:298: nms=dict(type='soft_nms', iou_thr=0.5,
+// min_score=0.05); dispatch mmdet/core/post_processing/bbox_nms.py:61 -> mmcv.ops.batched_nms ->
+// mmcv.ops.soft_nms, mmcv-full 1.2.1, un-vendored: published algorithm restated literally in
+// oracle/soft_nms_ref.c).  The reference loop is sequential: pick the FIRST maximum of the current
+// array, swap it to the front, decay every later score by its overlap with the pick, and drop a box
+// that falls below min_score by overwriting it with the last box.  Which of two equal scores is
+// picked first depends on that swap / overwrite history, so the whole process is reproduced as it
+// is - by ONE CTA whose 1024 threads do each of its inner passes in parallel:
+//   argmax   (score, lowest position) reduction over the live range;
+//   decay    all later boxes at once (plain IEEE fp32 in the reference's operation order);
+//   removal  the reference's "overwrite with the last box" scan equals an unstable compaction:
+//            with m survivors behind the pick, the k-th dead slot among the first m (ascending) is
+//            filled by the k-th live box counted from the end - block scan + one gather.
+// Picks come out in descending score order, so the loop stops after max_num picks (the reference
+// computes all of them and then slices).  No host sync, one launch.
+// ------------------------------------------------------------------------------------------
+constexpr int kSoftThreads = 1024;
+
+struct SoftNmsWs {
+    float4* box;      // shifted boxes (boxes_for_nms), current order
+    float* score;
+    float* area;
+    int* id;          // k * C + c of the candidate
+    int* tmp;         // filler positions
+    int* roi_off;     // [K + 1] exclusive scan of candidates per RoI
+};
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                                  // s_warp reuse
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_warp[lane] = wi - w;                        // exclusive warp offsets
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(kSoftThreads) soft_nms_kernel(
+    const float* __restrict__ boxes, int box_classes, const float* __restrict__ scores, int K, int C,
+    float score_thr, float iou_thr, float min_score, int method, int max_num, SoftNmsWs ws,
+    float* __restrict__ det, long long* __restrict__ labels, int* __restrict__ count) {
+    __shared__ int s_warp[33];
+    __shared__ float s_red_f[32];
+    __shared__ int s_red_i[32];
+    __shared__ float4 s_pick;
+    __shared__ float s_pick_area;
+    __shared__ int s_any;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C1 = C + 1;
+
+    // ---- candidates in row-major (k, c) order + the largest coordinate among them ------------
+    const int per = (K + kSoftThreads - 1) / kSoftThreads;       // contiguous RoIs per thread
+    const int k_lo = min(tid * per, K), k_hi = min(k_lo + per, K);
+    int mine = 0;
+    float mx = -INFINITY;
+    for (int k = k_lo; k < k_hi; ++k) {
+        int cnt = 0;
+        for (int c = 0; c < C; ++c)
+            if (scores[(size_t)k * C1 + c] > score_thr) {
+                ++cnt;
+                const float4 b = *reinterpret_cast<const float4*>(
+                    boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+                mx = fmaxf(mx, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+            }
+        mine += cnt;
+    }
+    int n = 0;
+    int off = block_exclusive_scan(mine, s_warp, n);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_red_f[warp] = mx;
+    __syncthreads();
+    mx = s_red_f[0];
+    for (int w = 1; w < kSoftThreads / 32; ++w) mx = fmaxf(mx, s_red_f[w]);
+    const float shift1 = __fadd_rn(mx, 1.f);                      // max_coordinate + 1
+    for (int k = k_lo; k < k_hi; ++k)
+        for (int c = 0; c < C; ++c) {
+            const float sc = scores[(size_t)k * C1 + c];
+            if (sc > score_thr) {
+                const float4 b = *reinterpret_cast<const float4*>(
+                    boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+                const float sh = __fmul_rn((float)c, shift1);     // idxs.to(boxes) * (max + 1)
+                const float4 q = make_float4(__fadd_rn(b.x, sh), __fadd_rn(b.y, sh),
+                                             __fadd_rn(b.z, sh), __fadd_rn(b.w, sh));
+                ws.box[off] = q;
+                ws.score[off] = sc;
+                ws.area[off] = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));
+                ws.id[off] = k * C + c;
+                ++off;
+            }
+        }
+    __syncthreads();
+
+    // ---- the sequential selection loop ----------------------------------------------------------
+    int i = 0;
+    for (; i < n && i < max_num; ++i) {
+        // first maximum of score[i..n)
+        float best = -INFINITY;
+        int bpos = 0x7fffffff;
+        for (int p = i + tid; p < n; p += kSoftThreads) {
+            const float v = ws.score[p];
+            if (bpos == 0x7fffffff || v > best) { best = v; bpos = p; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+            if (op != 0x7fffffff && (bpos == 0x7fffffff || ov > best || (ov == best && op < bpos))) {
+                best = ov;
+                bpos = op;
+            }
+        }
+        if (lane == 0) { s_red_f[warp] = best; s_red_i[warp] = bpos; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kSoftThreads / 32; ++w) {
+                const float ov = s_red_f[w];
+                const int op = s_red_i[w];
+                if (op != 0x7fffffff && (bpos == 0x7fffffff || ov > best || (ov == best && op < bpos))) {
+                    best = ov;
+                    bpos = op;
+                }
+            }
+            // swap the pick to position i, emit it
+            const float4 pb = ws.box[bpos];
+            const float pa = ws.area[bpos];
+            const int pid = ws.id[bpos];
+            ws.box[bpos] = ws.box[i];
+            ws.score[bpos] = ws.score[i];
+            ws.area[bpos] = ws.area[i];
+            ws.id[bpos] = ws.id[i];
+            ws.box[i] = pb;
+            ws.score[i] = best;
+            ws.area[i] = pa;
+            ws.id[i] = pid;
+            s_pick = pb;
+            s_pick_area = pa;
+            s_any = 0;
+            const int k = pid / C, c = pid - k * C;
+            const float4 ob = *reinterpret_cast<const float4*>(
+                boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+            float* o = det + (size_t)i * 5;
+            o[0] = ob.x; o[1] = ob.y; o[2] = ob.z; o[3] = ob.w; o[4] = best;
+            labels[i] = c;
+        }
+        __syncthreads();
+        // decay the later boxes; each thread owns a contiguous segment (same split as the scan)
+        const int rem = n - i - 1;
+        const int seg = (rem + kSoftThreads - 1) / kSoftThreads;
+        const int r_lo = min(tid * seg, rem), r_hi = min(r_lo + seg, rem);
+        const float4 a = s_pick;
+        const float iarea = s_pick_area;
+        int live = 0;
+        for (int r = r_lo; r < r_hi; ++r) {
+            const int p = i + 1 + r;
+            const float4 b = ws.box[p];
+            const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+            const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+            const float inter = __fmul_rn(w, h);
+            const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, ws.area[p]), inter));
+            float weight = 1.f;
+            if (ovr >= iou_thr) weight = method == 0 ? 0.f : __fsub_rn(1.f, ovr);
+            const float ns = __fmul_rn(ws.score[p], weight);
+            ws.score[p] = ns;
+            live += !(ns < min_score);
+        }
+        if (live != r_hi - r_lo) s_any = 1;                      // benign race: all write 1
+        __syncthreads();
+        if (!s_any) continue;                                    // uniform
+        // ---- removals: unstable compaction of [i+1, n) ------------------------------------------
+        int m = 0;
+        const int before = block_exclusive_scan(live, s_warp, m);
+        int lb = before;                                         // live boxes before r
+        for (int r = r_lo; r < r_hi; ++r) {
+            const bool lv = !(ws.score[i + 1 + r] < min_score);
+            if (lv && r >= m) ws.tmp[m - lb - 1] = i + 1 + r;    // rank from the end = live after r
+            lb += lv;
+        }
+        __syncthreads();
+        lb = before;
+        for (int r = r_lo; r < r_hi && r < m; ++r) {
+            const int p = i + 1 + r;
+            const bool lv = !(ws.score[p] < min_score);
+            if (!lv) {
+                const int src = ws.tmp[r - lb];                  // dead slots before r = r - lb
+                ws.box[p] = ws.box[src];
+                ws.score[p] = ws.score[src];
+                ws.area[p] = ws.area[src];
+                ws.id[p] = ws.id[src];
+            }
+            lb += lv;
+        }
+        n = i + 1 + m;
+        __syncthreads();
+    }
+    if (tid == 0) count[0] = i;
+}
+
 }  // namespace htd
 
 using namespace htd;
@@ -226,6 +443,43 @@ int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores,
     nms_merge_kernel<<<dim3(bx, C), kNmsThreads, 0, st>>>(boxes, box_classes, K, C, ws_n, kept_k,
                                                           kept_score, max_num, det, labels, count);
     HTD_CHECK_LAUNCH("htd_multiclass_nms(merge)");
+    return HTD_OK;
+}
+
+
+long long htd_multiclass_soft_nms_workspace_bytes(int K, int C) {
+    // box (16) + score + area + id + tmp (4 each) per candidate slot, K*C slots; roi_off unused tail
+    return (long long)K * C * 32 + 64;
+}
+
+int htd_multiclass_soft_nms(const float* boxes, int box_classes, const float* scores, int K, int C,
+                            float score_thr, float iou_thr, float min_score, int method,
+                            int max_num, float* det, long long* labels, int32_t* count,
+                            void* workspace, htd_stream_t stream) {
+    HTD_CHECK_ARG(K >= 0 && K <= HTD_NMS_MAX_ROIS && C >= 1 && C <= HTD_NMS_MAX_CLASSES &&
+                      (box_classes == 1 || box_classes == C) && max_num >= 1 && score_thr >= 0.f,
+                  "htd_multiclass_soft_nms: bad arguments K=%d (<= %d) C=%d (<= %d) box_classes=%d "
+                  "max_num=%d score_thr=%g (>= 0)", K, HTD_NMS_MAX_ROIS, C, HTD_NMS_MAX_CLASSES,
+                  box_classes, max_num, (double)score_thr);
+    HTD_CHECK_ARG(method == 0 || method == 1,
+                  "htd_multiclass_soft_nms: method must be 0 (naive) or 1 (linear, the mmcv "
+                  "default the HTD configs use); gaussian is not provided");
+    HTD_CHECK_ARG(det && labels && count && workspace && (K == 0 || (boxes && scores)),
+                  "htd_multiclass_soft_nms: null pointer");
+    HTD_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "htd_multiclass_soft_nms: workspace must be 16-byte aligned");
+    const size_t slots = (size_t)K * C;
+    char* w = static_cast<char*>(workspace);
+    SoftNmsWs ws;
+    ws.box = reinterpret_cast<float4*>(w);
+    ws.score = reinterpret_cast<float*>(w + slots * 16);
+    ws.area = ws.score + slots;
+    ws.id = reinterpret_cast<int*>(ws.area + slots);
+    ws.tmp = ws.id + slots;
+    ws.roi_off = nullptr;
+    soft_nms_kernel<<<1, kSoftThreads, 0, (cudaStream_t)stream>>>(
+        boxes, box_classes, scores, K, C, score_thr, iou_thr, min_score, method, max_num, ws, det,
+        labels, count);
+    HTD_CHECK_LAUNCH("htd_multiclass_soft_nms");
     return HTD_OK;
 }
 

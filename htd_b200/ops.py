@@ -763,10 +763,11 @@ def assign_sample(props, gt_boxes, gt_labels, num_gt, keys, valid=None, pos_iou_
     return s
 
 
-def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num):
-    """multiclass_nms (core/post_processing/bbox_nms.py:7-71) with hard NMS on the device, no host
-    sync: returns det [max_num,5], labels [max_num] (int64) and count [1] (int32, device); rows
-    >= count are unspecified.  multi_bboxes [K,4] or [K,C*4], multi_scores [K,C+1]."""
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num, soft=None):
+    """multiclass_nms (core/post_processing/bbox_nms.py:7-71) on the device, no host sync: returns
+    det [max_num,5], labels [max_num] (int64) and count [1] (int32, device); rows >= count are
+    unspecified.  multi_bboxes [K,4] or [K,C*4], multi_scores [K,C+1].  ``soft`` = None: hard NMS;
+    dict(min_score=..., method='linear'|'naive'): mmcv's soft_nms (htd_multiclass_soft_nms)."""
     _lib.require_cuda(multi_bboxes, multi_scores)
     K, C1 = multi_scores.shape
     C = C1 - 1
@@ -779,6 +780,18 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num):
     det = torch.empty((max_num, 5), dtype=torch.float32, device=dev)
     labels = torch.empty(max_num, dtype=torch.long, device=dev)
     count = torch.empty(1, dtype=torch.int32, device=dev)
+    if soft is not None:
+        method = {'naive': 0, 'linear': 1}.get(soft.get('method', 'linear'))
+        if method is None:
+            raise NotImplementedError("soft_nms method 'gaussian' is not provided (configs/htd use "
+                                      "the mmcv default 'linear')")
+        ws = torch.empty(int(lib().htd_multiclass_soft_nms_workspace_bytes(K, C)),
+                         dtype=torch.uint8, device=dev)
+        check(lib().htd_multiclass_soft_nms(ptr(boxes), bc, ptr(scores), K, C, float(score_thr),
+                                            float(iou_thr), float(soft.get('min_score', 1e-3)),
+                                            method, max_num, ptr(det), ptr(labels), ptr(count),
+                                            ptr(ws), stream()), 'htd_multiclass_soft_nms')
+        return det, labels, count
     ws = torch.empty(int(lib().htd_multiclass_nms_workspace_bytes(K, C)), dtype=torch.uint8,
                      device=dev)
     check(lib().htd_multiclass_nms(ptr(boxes), bc, ptr(scores), K, C, float(score_thr),

@@ -119,6 +119,36 @@ def _gen_for(name, seed):
     return torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
 
 
+def _alternating(n, dtype=torch.float32):
+    return torch.where(torch.arange(n) % 2 == 0, 1.0, -1.0).to(dtype)
+
+
+def _stable_value(name, p, z):
+    """Parameter value of the 'stable' scheme (see ``fill_params_``); z ~ N(0,1) of p's shape."""
+    relu_fc = ('shared_fcs.' in name or '.fcs.' in name or 'graph_lvl' in name)
+    if name.endswith('gn.weight'):
+        return 1.0 + 0.05 * z
+    if name.endswith('gn.bias'):                      # GN output has unit variance: +-6 sigma
+        return 6.0 * _alternating(p.shape[0]) + 0.1 * z
+    if 'glbctx_head.convs' in name:                   # SFA: conv + bias + ReLU
+        return 3.0 * _alternating(p.shape[0]) + 0.1 * z if name.endswith('bias') else 0.005 * z
+    if relu_fc and name.endswith('bias'):
+        return 1.5 * _alternating(p.shape[0]) + 0.05 * z
+    if relu_fc:
+        return (0.001 if p.shape[1] > 2048 else 0.006) * z
+    if 'convs.3.conv.weight' in name:                 # last tower conv: no bias, no norm -> ReLU
+        return 0.005 * z + 0.001 * _alternating(p.shape[0]).view(-1, 1, 1, 1)
+    if name.endswith('fc_reg.weight'):
+        return 0.001 * z
+    if name.endswith('fc_cls.weight') or name.endswith('glbctx_head.fc.weight'):
+        return 0.01 * z
+    if name.endswith('bias'):
+        return 0.01 * z
+    if p.dim() == 4 and p.shape[-1] == 3:             # tower convs followed by GroupNorm
+        return math.sqrt(2.0 / (p.shape[0] * 9)) * z
+    return 0.05 * z                                   # BA attention convs
+
+
 def fill_params_(module, scheme='n005', seed=0):
     """Deterministically (re)initialise every parameter of ``module`` from its state-dict
     name, so the reference head (oracle side) and this package's head (product side) get
@@ -127,7 +157,12 @@ def fill_params_(module, scheme='n005', seed=0):
     scheme 'n005': every tensor ~ N(0, 0.05) (GroupNorm weight 1 + N(0, 0.05)); makes the
     PGraph softmax non-trivial.  scheme 'init': magnitudes of the reference's
     own initialisers (normal 0.01 / 0.001 for fc_cls / fc_reg, xavier-uniform Linear,
-    kaiming-normal conv, zero biases) - ``htd_bbox_head.py:136-145``.
+    kaiming-normal conv, zero biases) - ``htd_bbox_head.py:136-145``.  scheme 'stable'
+    ("gate-stable"): every ReLU on the path gets a pre-activation whose sign is fixed by a large
+    alternating bias (FC / SFA conv bias, GroupNorm beta; the bias-free last tower conv gets a
+    per-output-channel mean shift of its weights) with small weights around it, so that bf16 / fp32
+    rounding cannot flip a gate - end-to-end gradients can then be gated in the max-norm like the
+    forward values (a flipped gate changes a gradient element by 100 %, whatever the arithmetic).
     """
     seen = set()
     with torch.no_grad():
@@ -159,6 +194,8 @@ def fill_params_(module, scheme='n005', seed=0):
                 else:
                     fan_out = p.shape[0] * p[0][0].numel()
                     v = math.sqrt(2.0 / fan_out) * z
+            elif scheme == 'stable':
+                v = _stable_value(name, p, z)
             else:
                 raise ValueError(scheme)
             p.copy_(v.to(p.dtype))

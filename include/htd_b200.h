@@ -374,6 +374,22 @@ int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores,
                        float score_thr, float iou_thr, int max_num, float* det, long long* labels,
                        int32_t* count, void* workspace, htd_stream_t stream);
 
+/* Soft-NMS form of the same step: nms=dict(type='soft_nms', iou_thr=0.5, min_score=0.05) of
+ * configs/htd/htd_resnet101_2x.py:298 (and the three other R-101 / X-101 configs), dispatched at
+ * mmdet/core/post_processing/bbox_nms.py:61 to mmcv.ops.batched_nms -> mmcv.ops.soft_nms
+ * (mmcv-full 1.2.1, un-vendored; algorithm restated in oracle/soft_nms_ref.c).  Same candidates
+ * and coordinate shift as above; then mmcv's sequential loop reproduced exactly (first maximum
+ * of the current order, swap to the front, linear decay `score *= 1 - iou` where iou >= iou_thr
+ * (method 1; method 0: naive = score 0), removal below min_score by overwriting with the last
+ * box), so detections, decayed scores, labels AND the order among equal scores are the
+ * reference's.  det [max_num,5] holds the un-shifted boxes and the decayed scores; rows <
+ * count[0] are written.  One launch (one CTA), no host sync; the loop ends after max_num picks. */
+long long htd_multiclass_soft_nms_workspace_bytes(int K, int C);
+int htd_multiclass_soft_nms(const float* boxes, int box_classes, const float* scores, int K, int C,
+                            float score_thr, float iou_thr, float min_score, int method,
+                            int max_num, float* det, long long* labels, int32_t* count,
+                            void* workspace, htd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
  * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and

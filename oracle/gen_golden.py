@@ -5,6 +5,7 @@ does not.
 
     python -m oracle.gen_golden            # all cases, fp64 + fp32
     python -m oracle.gen_golden assign     # only tests/golden/assign_sample.npz
+    python -m oracle.gen_golden case c2    # only the module / head / training fixtures of one case
 
 Fixtures hold, per tensor, a strided sample of <=1024 elements plus sum / abs-sum / max-abs
 (float tensors) or the full tensor (integer tensors: level indices, mask bitsets, degrees).
@@ -76,6 +77,18 @@ def gen_nms():
         flat[f'{name}|labels'] = labels.numpy()
         print('nms', name, tuple(dets.shape))
     np.savez_compressed(os.path.join(OUT, 'nms.npz'), **flat)
+    # soft-NMS (configs/htd/htd_resnet101_2x.py:298): the reference's multiclass_nms with its own
+    # nms_cfg; mmcv's soft_nms op = the literal restatement oracle/soft_nms_ref.c (mmcv is absent)
+    flat = {}
+    for name in cases.NMS_CASES:
+        boxes, scores, c = cases.nms_case_inputs(name)
+        dets, labels = ns.multiclass_nms(boxes, scores, c['score_thr'],
+                                         dict(type='soft_nms', iou_thr=c['iou_thr'],
+                                              min_score=c['score_thr']), c['max_num'])
+        flat[f'{name}|dets'] = dets.numpy()
+        flat[f'{name}|labels'] = labels.numpy()
+        print('soft_nms', name, tuple(dets.shape))
+    np.savez_compressed(os.path.join(OUT, 'nms_soft.npz'), **flat)
 
 
 def main():
@@ -86,9 +99,19 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ns = refshim.load()
     torch.set_num_threads(os.cpu_count())
-    # --- level assignment (bit-exact integer fixture) --------------------------------------
     ext = ns.SingleRoIExtractor(dict(type='RoIAlign', output_size=7, sampling_ratio=0), 256,
                                 [4, 8, 16, 32])
+    only = sys.argv[2:] if len(sys.argv) > 2 and sys.argv[1] == 'case' else None
+    if only is None:
+        gen_levels(ext)
+    gen_cases(ns, ext, only)
+    if only is None:
+        gen_assign_sample()
+        gen_nms()
+
+
+def gen_levels(ext):
+    # --- level assignment (bit-exact integer fixture) --------------------------------------
     props = synth.make_proposals(8, 512, seed=99)
     rois = torch.cat([torch.cat([p.new_full((p.size(0), 1), i), p], 1)
                       for i, p in enumerate(props)], 0)
@@ -97,8 +120,12 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'levels.npz'), rois=rois.numpy(),
                         levels=lv.numpy().astype(np.int8))
     print('levels:', torch.bincount(lv).tolist())
+
+
+def gen_cases(ns, ext, only=None):
+    names = [n for n in cases.CASES if only is None or n in only]
     # --- graph masks (bit-exact) --------------------------------------------------------------
-    for name in cases.CASES:
+    for name in names:
         c, x, pr, gts, shapes = cases.case_inputs(name)
         r = cases._rois(pr)
         masks = cases.graph_masks(ns.bbox_overlaps, ext.map_roi_levels(r, 4), r)
@@ -109,7 +136,8 @@ def main():
             flat[f'{b}_{i}|deg'] = deg.numpy().astype(np.int32)
         np.savez_compressed(os.path.join(OUT, f'masks_{name}.npz'), **flat)
     # --- module / head / training fixtures ----------------------------------------------------
-    for name, c in cases.CASES.items():
+    for name in names:
+        c = cases.CASES[name]
         for dt, tag in ((torch.float64, 'f64'), (torch.float32, 'f32')):
             head = refshim.build_head(double=(dt == torch.float64))
             synth.fill_params_(head, c['scheme'], c['seed'])
@@ -122,8 +150,6 @@ def main():
             cases.save_fixture(path, outs)
             print(name, tag, len(outs), 'tensors ->', path, os.path.getsize(path) // 1024, 'KiB',
                   {k: float(v) for k, v in outs.items() if k.startswith('train.') and v.numel() == 1})
-    gen_assign_sample()
-    gen_nms()
 
 
 if __name__ == '__main__':

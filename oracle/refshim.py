@@ -148,16 +148,26 @@ _LOADED = None
 
 
 def _batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
-    """mmcv.ops.nms.batched_nms of mmcv-full 1.2.1 for type='nms' below split_thr: coordinate
-    shift per class, then the nms op - here torchvision.ops.nms, the same greedy algorithm."""
+    """mmcv.ops.nms.batched_nms of mmcv-full 1.2.1 below split_thr: coordinate shift per class,
+    then the nms op named by the config - type='nms': torchvision.ops.nms (the same greedy
+    algorithm); type='soft_nms': mmcv's sequential soft-NMS loop as restated in
+    oracle/soft_nms_ref.c (mmcv is not installed; `iou_thr` is mmcv's deprecated alias of
+    `iou_threshold`); the returned scores are the op's (`dets[:, -1]`)."""
     from torchvision.ops import nms
     cfg = dict(nms_cfg)
-    assert cfg.pop('type', 'nms') == 'nms'
-    thr = cfg.get('iou_threshold', cfg.get('iou_thr'))
+    kind = cfg.pop('type', 'nms')
+    cfg.pop('split_thr', None)
+    class_agnostic = cfg.pop('class_agnostic', class_agnostic)
+    thr = cfg.pop('iou_threshold', cfg.pop('iou_thr', None))
     if class_agnostic:
         b = boxes
     else:
         b = boxes + (idxs.to(boxes) * (boxes.max() + 1))[:, None]
+    if kind == 'soft_nms':
+        from . import restate
+        dets, keep = restate.soft_nms(b, scores, 0.3 if thr is None else thr, **cfg)
+        return torch.cat([boxes[keep], dets[:, 4:5].to(boxes)], -1), keep
+    assert kind == 'nms' and not cfg, (kind, cfg)
     keep = nms(b, scores, thr)
     return torch.cat([boxes[keep], scores[keep, None]], -1), keep
 

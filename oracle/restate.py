@@ -504,11 +504,80 @@ def nms_greedy(boxes, scores, iou_thr):
     return torch.tensor(keep, dtype=torch.long)
 
 
-def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num=-1):
+def soft_nms(boxes, scores, iou_threshold=0.3, sigma=0.5, min_score=1e-3, method='linear', offset=0):
+    """mmcv.ops.soft_nms of mmcv-full 1.2.1 (un-vendored dependency, README.md:11): the published
+    sequential loop, restated literally in oracle/soft_nms_ref.c.  Returns (dets [m,5], inds [m])
+    in selection order; dets hold the boxes as given and the decayed scores."""
+    n = boxes.size(0)
+    b = boxes.detach().to(torch.float32).contiguous().cpu()
+    s = scores.detach().to(torch.float32).contiguous().cpu()
+    dets = torch.empty((n, 5), dtype=torch.float32)
+    inds = torch.empty(n, dtype=torch.int64)
+    fn = lib().oracle_soft_nms
+    fn.restype = ctypes.c_longlong
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_float,
+                   ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                   ctypes.c_void_p]
+    m = fn(_ptr(b), _ptr(s), n, float(iou_threshold), float(sigma), float(min_score),
+           {'naive': 0, 'linear': 1, 'gaussian': 2}[method], int(offset), _ptr(dets), _ptr(inds))
+    return dets[:m], inds[:m]
+
+
+def soft_nms_vectorised(boxes, scores, iou_threshold, sigma, min_score, method='linear',
+                        max_out=-1):
+    """The same loop with every inner pass as one array operation - the formulation the CUDA kernel
+    uses (csrc/nms.cu): first-occurrence argmax, swap, decay of all later boxes at once, and the
+    'overwrite with the last box' removals as ONE unstable compaction: with m survivors among the
+    boxes after position i, the k-th dead slot (ascending) among the first m is filled by the k-th
+    live box from the end (descending).  Checked against the literal loop in tests/test_oracle_cpu."""
+    import numpy as np
+    b = boxes.detach().cpu().numpy().astype(np.float32).copy()
+    sc = scores.detach().cpu().numpy().astype(np.float32).copy()
+    area = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])).astype(np.float32)
+    ind = np.arange(b.shape[0], dtype=np.int64)
+    n = b.shape[0]
+    dets, keep = [], []
+    i = 0
+    while i < n and (max_out < 0 or i < max_out):
+        mp = i + int(np.argmax(sc[i:n]))               # numpy: first occurrence of the maximum
+        for arr in (b, sc, area, ind):
+            arr[[i, mp]] = arr[[mp, i]]
+        dets.append(np.concatenate([b[i], sc[i:i + 1]]))
+        keep.append(ind[i])
+        r = slice(i + 1, n)
+        w = np.maximum(np.float32(0), np.minimum(b[i, 2], b[r, 2]) - np.maximum(b[i, 0], b[r, 0]))
+        h = np.maximum(np.float32(0), np.minimum(b[i, 3], b[r, 3]) - np.maximum(b[i, 1], b[r, 1]))
+        inter = (w * h).astype(np.float32)
+        ovr = (inter / ((area[i] + area[r]).astype(np.float32) - inter)).astype(np.float32)
+        if method == 'linear':
+            wt = np.where(ovr >= np.float32(iou_threshold), np.float32(1) - ovr, np.float32(1))
+        elif method == 'naive':
+            wt = np.where(ovr >= np.float32(iou_threshold), np.float32(0), np.float32(1))
+        else:
+            wt = np.exp(-(ovr * ovr) / np.float32(sigma)).astype(np.float32)
+        sc[r] = (sc[r] * wt.astype(np.float32)).astype(np.float32)
+        live = sc[r] >= np.float32(min_score)
+        m = int(live.sum())
+        holes = np.nonzero(~live[:m])[0]
+        fill = np.nonzero(live[m:])[0][::-1] + m
+        for arr in (b, sc, area, ind):
+            v = arr[r]
+            v[holes] = v[fill]
+        n = i + 1 + m
+        i += 1
+    if not dets:
+        return torch.zeros((0, 5)), torch.zeros((0,), dtype=torch.long)
+    return torch.from_numpy(np.stack(dets)), torch.from_numpy(np.asarray(keep, dtype=np.int64))
+
+
+def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num=-1, nms_type='nms',
+                   min_score=1e-3, sigma=0.5, method='linear'):
     """core/post_processing/bbox_nms.py:7-71 with nms_cfg = dict(type='nms', iou_threshold=...)
     and mmcv's batched_nms (class_agnostic=False, fewer than split_thr boxes): shift the boxes of
     class c by c * (max coordinate + 1), one NMS over all of them, ``dets`` in descending score
-    order, first ``max_num``.  Returns (dets [n,5], labels [n])."""
+    order, first ``max_num``.  ``nms_type='soft_nms'`` (configs/htd/htd_resnet101_2x.py:298):
+    mmcv's soft_nms on the shifted boxes, scores replaced by the decayed ones (batched_nms returns
+    ``dets[:, -1]``).  Returns (dets [n,5], labels [n])."""
     num_classes = multi_scores.size(1) - 1
     if multi_bboxes.shape[1] > 4:
         bboxes = multi_bboxes.view(multi_scores.size(0), -1, 4)
@@ -523,6 +592,12 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num=-1):
         return multi_bboxes.new_zeros((0, 5)), multi_bboxes.new_zeros((0,), dtype=torch.long)
     max_coordinate = bboxes.max()
     offsets = labels.to(bboxes) * (max_coordinate + 1)
+    if nms_type == 'soft_nms':
+        dets, keep = soft_nms(bboxes + offsets[:, None], scores, iou_thr, sigma, min_score, method)
+        if max_num > 0:
+            dets, keep = dets[:max_num], keep[:max_num]
+        return torch.cat([bboxes[keep], dets[:, 4:5].to(bboxes)], -1), labels[keep]
+    assert nms_type == 'nms', nms_type
     keep = nms_greedy(bboxes + offsets[:, None], scores, iou_thr)
     if max_num > 0:
         keep = keep[:max_num]

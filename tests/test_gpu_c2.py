@@ -1,0 +1,178 @@
+"""GPU parity (through the C-ABI) at the BENCHMARKED size and with gate-stable weights.
+
+`c2` is BASELINE.json configs[1] - 2 images x 512 RoIs (128 positives / image), 800x1333 pyramid -
+the size bench.py measures: P2 rows of 336 px, footprints of up to ~200 x 330 pixels, PGraph groups of
+~250 RoIs; `small_s` is the small case with the same weights.  Both use the 'stable' weight scheme
+(htd_b200/synth.py): every ReLU gate is decided by a large bias, so rounding cannot flip a gate
+and END-TO-END gradients are compared in the max-norm, like forward values:
+
+    fp32  forward <= 1e-5 of the fp64 oracle (and of the fixture written by the reference itself);
+    bf16  forward AND every gradient tensor <= 2e-2, cuDNN / cuBLAS in their default (bench) setting.
+
+The oracle (oracle/restate.py, fp64, CPU) runs live on the same seeded inputs - full tensors, all
+RoIs - and tests/golden/{c2,small_s}_f64.npz hold samples of the reference's own run.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from htd_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+TOL_F32, TOL_BF16 = 1e-5, 2e-2
+NAMES = ['small_s', 'c2']
+
+_ORACLE = {}
+
+
+def _oracle(name, what):
+    from oracle import cases, restate
+    key = (name, what)
+    if key not in _ORACLE:
+        torch.set_num_threads(os.cpu_count() or 1)
+        c = cases.CASES[name]
+        head = restate.HTDRoIHead().double()
+        synth.fill_params_(head, c['scheme'], c['seed'])
+        if what == 'ext':
+            _ORACLE[key] = cases.run_extractors(head, name, torch.float64)
+        elif what == 'head':
+            _ORACLE[key] = cases.run_head(head, name, torch.float64)
+        else:
+            _ORACLE[key] = cases.run_train(
+                head, lambda h, *a: h.forward_train_sampled(*a),
+                lambda h, *a: h.simple_test_scores(*a), name, torch.float64)
+    return _ORACLE[key]
+
+
+def _product(name, dtype):
+    import htd_b200
+    from oracle import cases
+    c = cases.CASES[name]
+    # fp32: IEEE fp32 library math (no TF32; ATen's native convolution, see test_gpu_head.py);
+    # bf16: cuDNN / cuBLAS as the bench runs them
+    torch.backends.cudnn.enabled = dtype != torch.float32
+    torch.backends.cudnn.allow_tf32 = dtype != torch.float32
+    torch.backends.cuda.matmul.allow_tf32 = dtype != torch.float32
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    head = head.cuda().to(dtype)
+    head.compute_dtype = dtype
+    return head
+
+
+@pytest.fixture(autouse=True)
+def _restore_backends():
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+             torch.backends.cudnn.enabled)
+    yield
+    (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+     torch.backends.cudnn.enabled) = saved
+
+
+def _errs(got, want):
+    from oracle import cases
+    out = {}
+    scale = max(float(v.abs().max()) for k, v in want.items() if '.d' in k or 'dx' in k)
+    for k, w in want.items():
+        if k.endswith('.acc'):
+            continue
+        g = got[k].float() if got[k].is_floating_point() else got[k]
+        if float(w.abs().max()) <= 1e-12 * scale:          # identically zero (d conv2.bias)
+            out[k] = float(g.abs().max()) / scale
+        else:
+            out[k] = cases.rel_err(g, w)
+    return out
+
+
+def _report(errs, tol, what):
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print(what, 'worst:', {k: f'{v:.2e}' for k, v in worst})
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, (what, tol, bad)
+
+
+def _train_fn(head, xs, props, gts, shapes, P):
+    return synth.sampled_forward_train(head, xs, props, gts, shapes, P)
+
+
+def _test_fn(head, x, props, shapes):
+    return head.simple_test_scores(x, props, [dict(img_shape=s) for s in shapes])
+
+
+@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)])
+def test_extractors_all_rois(name, dtype, tol):
+    """SingleRoIExtractor and the BA extractor: outputs over ALL RoIs, dX of every level and the
+    attention-parameter gradients against the fp64 oracle; level indices bit-exact; fp32 also
+    against the fixture written by the reference's own modules."""
+    from oracle import cases
+    got = cases.run_extractors(_product(name, dtype), name, dtype, 'cuda')
+    want = _oracle(name, 'ext')
+    assert torch.equal(got['levels'].cpu(), want['levels'])
+    errs = _errs({k: v for k, v in got.items() if k != 'levels'},
+                 {k: v for k, v in want.items() if k != 'levels'})
+    _report(errs, tol, f'{name} extractors {dtype}')
+    if dtype == torch.float32:
+        fix = cases.load_fixture(os.path.join(GOLD, f'{name}_f64.npz'))
+        cases.compare_to_fixture(got, fix, TOL_F32, names=set(want))
+
+
+@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)])
+def test_htd_bbox_head_forward_and_all_gradients(name, dtype, tol):
+    """HTDBBoxHead (FC stacks, PGraph, conv tower): scores, box deltas and the gradient of every
+    input and parameter (stage-0 fc_cls included) against the fp64 oracle, max-norm."""
+    from oracle import cases
+    got = cases.run_head(_product(name, dtype), name, dtype, 'cuda')
+    want = _oracle(name, 'head')
+    _report(_errs(got, want), tol, f'{name} head {dtype}')
+    if dtype == torch.float32:
+        fix = cases.load_fixture(os.path.join(GOLD, f'{name}_f64.npz'))
+        cases.compare_to_fixture(got, fix, TOL_F32, names=set(want))
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_full_step_bf16_losses_and_all_gradients(name):
+    """The benchmarked numeric configuration - bf16, cuDNN / cuBLAS on, the complete sampled
+    forward_train + backward and the test branch: the 7 losses, the test-branch scores and EVERY
+    gradient tensor (pyramid levels, all 47.2 M parameters) <= 2e-2 of the fp64 oracle."""
+    from oracle import cases
+    got = cases.run_train(_product(name, torch.bfloat16), _train_fn, _test_fn, name,
+                          torch.bfloat16, 'cuda')
+    want = _oracle(name, 'train')
+    assert set(got) == set(want)
+    for k in want:
+        if k.endswith('.acc'):      # share of arg-max hits, in percent: one RoI of K may differ
+            assert abs(float(got[k]) - float(want[k])) <= 100.0 / 48 + 1e-3, k
+    _report(_errs(got, want), TOL_BF16, f'{name} step bf16')
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_full_step_fp32(name):
+    """fp32 step: forward quantities (losses, test-branch scores / deltas / refined RoIs) <= 1e-5
+    of the fp64 oracle and of the reference's own fixture.  Gradients: 1e-5, or 64x the deviation
+    of the reference's OWN fp32 run from its fp64 run on that tensor where that is larger (GroupNorm
+    backward behind the average pool cancels most of its input: an fp32 arithmetic limit that the
+    reference shares) - gates are stable here, so no ReLU flips are involved."""
+    from oracle import cases
+    got = cases.run_train(_product(name, torch.float32), _train_fn, _test_fn, name,
+                          torch.float32, 'cuda')
+    want = _oracle(name, 'train')
+    errs = _errs(got, want)
+    fix64 = cases.load_fixture(os.path.join(GOLD, f'{name}_f64.npz'))
+    fix32 = cases.load_fixture(os.path.join(GOLD, f'{name}_f32.npz'))
+    bad = {}
+    for k, e in errs.items():
+        ref_dev = float(np.abs(fix32[k]['sample'] - fix64[k]['sample']).max() /
+                        max(float(fix64[k]['maxabs']), 1e-9)) if k in fix32 else 0.0
+        tol = TOL_F32 if k.startswith('test.') or 'loss' in k else max(TOL_F32, 64 * ref_dev)
+        if not e <= tol:
+            bad[k] = (e, tol)
+    print(f'{name} step fp32 worst:', {k: f'{v:.2e}' for k, v in
+                                       sorted(errs.items(), key=lambda kv: -kv[1])[:6]})
+    assert not bad, bad
+    cases.compare_to_fixture({k: v for k, v in got.items() if k.startswith('test.') or 'loss' in k},
+                             fix64, TOL_F32)

@@ -188,16 +188,27 @@ def _pgraph_oracle(x, sam, rois, W, b, num_imgs):
     return refined, [getattr(head, f'graph_lvl{i}_cls') for i in range(4)]
 
 
+PGRAPH_SETS = {
+    # images, RoIs / image, (H, W), (min, max) scale, least size of the largest group
+    'mixed150': (2, 150, (512, 640), (8, 700), 20),
+    'c2_512': (2, 512, (800, 1333), (16, 800), 230),          # bench size: groups of ~250 RoIs
+    'one1000': (1, 1000, (800, 1333), (113, 223), 900),       # config-4 stress: one dense group
+}
+
+
+@pytest.mark.parametrize('rset', list(PGRAPH_SETS))
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, TOL_F32), (torch.bfloat16, TOL_BF16)])
-def test_pgraph_function_isolated(dtype, tol):
+def test_pgraph_function_isolated(dtype, tol, rset):
     """The PGraph autograd node alone (plan + IoU graph + 4 forward / 7 backward grouped GEMMs +
     softmax) against the fp64 restatement on the SAME (dtype-rounded) inputs.  Biases of +-4 keep
     every ReLU gate away from zero so bf16 rounding cannot flip gates: the comparison isolates
-    the kernels' arithmetic (bf16: tcgen05 path)."""
+    the kernels' arithmetic (bf16: tcgen05 path).  RoI sets: a small mixed one, the benchmarked
+    2 x 512 proposals (groups of ~250) and 1000 proposals of one image forced onto one level."""
     from htd_b200 import ops, pgraph
     from oracle import cases
     g = torch.Generator().manual_seed(11)
-    props = synth.make_proposals(2, 150, 512, 640, seed=77, min_scale=8, max_scale=700)
+    nimg, per, (H_, W_), (smin, smax), biggest = PGRAPH_SETS[rset]
+    props = synth.make_proposals(nimg, per, H_, W_, seed=77, min_scale=smin, max_scale=smax)
     rois = cases._rois(props)
     K = rois.shape[0]
     x = torch.randn(K, 1024, generator=g).to(dtype)
@@ -209,14 +220,14 @@ def test_pgraph_function_isolated(dtype, tol):
     dy = torch.randn(K, 1024, generator=g).to(dtype)
     # oracle, fp64, from the rounded inputs
     xo, so = x.double().requires_grad_(True), sam.double().requires_grad_(True)
-    ref, layers = _pgraph_oracle(xo, so, rois.double(), W.double(), b.double(), 2)
+    ref, layers = _pgraph_oracle(xo, so, rois.double(), W.double(), b.double(), nimg)
     params = [p for m in layers for p in (m.weight, m.bias)]
     go = torch.autograd.grad((ref * dy.double()).sum(), [xo, so] + params)
     # product
     xg, sg = x.cuda().requires_grad_(True), sam.cuda().requires_grad_(True)
     Wg = [W[i].cuda().requires_grad_(True) for i in range(4)]
     bg = [b[i].cuda().requires_grad_(True) for i in range(4)]
-    plan = pgraph.GraphPlan(rois.cuda(), ops.level_assign(rois.cuda(), 4), 2, 4, dtype)
+    plan = pgraph.GraphPlan(rois.cuda(), ops.level_assign(rois.cuda(), 4), nimg, 4, dtype)
     out = pgraph.pgraph_refine(xg, sg, Wg, bg, plan)
     gg = torch.autograd.grad((out.float() * dy.cuda().float()).sum(), [xg, sg] + Wg + bg)
     errs = {'refined': cases.rel_err(out.float(), ref), 'dx': cases.rel_err(gg[0].float(), go[0]),
@@ -227,7 +238,7 @@ def test_pgraph_function_isolated(dtype, tol):
     print({k: f'{v:.1e}' for k, v in errs.items()})
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, bad
-    assert plan.flops() > 0 and len(plan.groups) >= 6
+    assert plan.flops() > 0 and max(n for _, _, _, n in plan.groups) >= biggest
 
 # ----------------------------------------------------------------------------------------------
 # HTDBBoxHead (PGraph + BA/SFA reg branch) and the full head

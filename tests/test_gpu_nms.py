@@ -42,6 +42,69 @@ def test_multiclass_nms_matches_restatement_random_sizes():
         assert torch.equal(det[:n].cpu(), want_d) and torch.equal(lab[:n].cpu(), want_l), (K, C)
 
 
+@pytest.mark.parametrize('name', list(cases.NMS_CASES))
+def test_multiclass_soft_nms_matches_reference_golden(name):
+    """nms=dict(type='soft_nms', iou_thr=..., min_score=...) (configs/htd/htd_resnet101_2x.py:298):
+    boxes, decayed scores, labels and the ORDER (tied scores included) equal the fixture written by
+    the reference's multiclass_nms bit for bit."""
+    z = np.load(os.path.join(GOLD, 'nms_soft.npz'))
+    boxes, scores, c = cases.nms_case_inputs(name)
+    dets, labels = core.multiclass_nms(boxes.cuda(), scores.cuda(), c['score_thr'],
+                                       dict(type='soft_nms', iou_thr=c['iou_thr'],
+                                            min_score=c['score_thr']), c['max_num'])
+    assert np.array_equal(dets.cpu().numpy(), z[f'{name}|dets']), name
+    assert np.array_equal(labels.cpu().numpy(), z[f'{name}|labels']), name
+
+
+def test_multiclass_soft_nms_matches_restatement_random_sizes():
+    g = torch.Generator().manual_seed(9)
+    for K, C, per_class, max_num, quant in ((1, 1, False, 10, None), (37, 3, True, -1, 8),
+                                            (1000, 80, False, 100, None), (2048, 5, False, 300, 16),
+                                            (600, 4, False, -1, None)):
+        cases.NMS_CASES['_t'] = dict(K=K, C=C, per_class=per_class, score_thr=0.05, iou_thr=0.5,
+                                     max_num=max_num, dup=0.6, temp=2.0,
+                                     seed=int(torch.randint(0, 1000, (1,), generator=g)))
+        if quant:
+            cases.NMS_CASES['_t']['quant'] = quant
+        try:
+            boxes, scores, c = cases.nms_case_inputs('_t')
+        finally:
+            del cases.NMS_CASES['_t']
+        for method in ('linear', 'naive'):
+            want_d, want_l = restate.multiclass_nms(boxes, scores, 0.05, 0.5, max_num,
+                                                    nms_type='soft_nms', min_score=0.05, method=method)
+            d, l = core.multiclass_nms(boxes.cuda(), scores.cuda(), 0.05,
+                                       dict(type='soft_nms', iou_threshold=0.5, min_score=0.05,
+                                            method=method), max_num)
+            assert d.shape == want_d.shape, (K, C, method, d.shape, want_d.shape)
+            assert torch.equal(d.cpu(), want_d) and torch.equal(l.cpu(), want_l), (K, C, method)
+
+
+def test_simple_test_with_the_r101_soft_nms_test_cfg():
+    """BASELINE config 4 (R-101-DCN) post-processing: simple_test with the real test_cfg of
+    configs/htd/htd_resnet101_2x.py:292-300 (soft_nms) == the restatement on the head's own scores."""
+    import htd_b200
+    from htd_b200 import synth
+    head = htd_b200.build_htd_roi_head().cuda()
+    synth.fill_params_(head, 'n005', 2)
+    head.eval()
+    head.test_cfg = htd_b200.core.as_cfg(dict(score_thr=0.05, max_per_img=100,
+                                              nms=dict(type='soft_nms', iou_thr=0.5, min_score=0.05)))
+    H, W = 256, 320
+    x = [t.cuda() for t in synth.make_pyramid(1, H, W)]
+    props = [p.cuda() for p in synth.make_proposals(1, 300, H, W, min_scale=8, max_scale=300)]
+    metas = [dict(img_shape=(H, W, 3), scale_factor=1.0)]
+    with torch.no_grad():
+        res = head.simple_test(x, props, metas)
+        rois, cls_score, bbox_pred = head.simple_test_scores(x, props, metas)
+        boxes, scores = head.bbox_head[-1].get_bboxes(rois, cls_score, bbox_pred, (H, W, 3), 1.0)
+    wd, wl = restate.multiclass_nms(boxes.cpu(), scores.cpu(), 0.05, 0.5, 100, nms_type='soft_nms',
+                                    min_score=0.05)
+    assert sum(a.shape[0] for a in res[0]) == wd.shape[0] > 0
+    for c in range(80):
+        assert np.array_equal(res[0][c], wd[wl == c].numpy()), c
+
+
 def test_simple_test_returns_reference_format_through_the_nms_kernel():
     """HTDRoIHead.simple_test (htd_roi_head.py:319-386): per image a list of num_classes arrays
     [n_c,5], at most max_per_img detections, scores descending within the NMS output."""

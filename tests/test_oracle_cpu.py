@@ -115,7 +115,9 @@ def _restate_outs(name, dt, which=('ext', 'head', 'train')):
 
 @pytest.mark.parametrize('name,tag,dt,tol', [('small', 'f64', torch.float64, 1e-10),
                                              ('small', 'f32', torch.float32, 2e-5),
-                                             ('mid', 'f32', torch.float32, 2e-5)])
+                                             ('mid', 'f32', torch.float32, 2e-5),
+                                             ('small_s', 'f64', torch.float64, 1e-10),
+                                             ('c2', 'f64', torch.float64, 1e-10)])
 def test_restatement_matches_golden(name, tag, dt, tol):
     fix = cases.load_fixture(os.path.join(GOLD, f'{name}_{tag}.npz'))
     outs = _restate_outs(name, dt)
@@ -237,6 +239,43 @@ def test_nms_restatement_matches_reference_golden(name):
     dets, labels = restate.multiclass_nms(boxes, scores, c['score_thr'], c['iou_thr'], c['max_num'])
     assert np.array_equal(dets.numpy(), z[f'{name}|dets']) and \
         np.array_equal(labels.numpy(), z[f'{name}|labels'])
+
+
+@pytest.mark.parametrize('name', list(cases.NMS_CASES))
+def test_soft_nms_restatement_matches_reference_golden(name):
+    """restate.multiclass_nms(nms_type='soft_nms') == the reference's multiclass_nms called with
+    the R-101 configs' nms_cfg (tests/golden/nms_soft.npz; mmcv's op = oracle/soft_nms_ref.c)."""
+    z = np.load(os.path.join(GOLD, 'nms_soft.npz'))
+    boxes, scores, c = cases.nms_case_inputs(name)
+    dets, labels = restate.multiclass_nms(boxes, scores, c['score_thr'], c['iou_thr'], c['max_num'],
+                                          nms_type='soft_nms', min_score=c['score_thr'])
+    assert np.array_equal(dets.numpy(), z[f'{name}|dets']) and \
+        np.array_equal(labels.numpy(), z[f'{name}|labels'])
+
+
+def test_soft_nms_parallel_formulation_equals_the_literal_loop():
+    """The per-pass array formulation the CUDA kernel uses (first-occurrence argmax, decay of all
+    later boxes at once, removals as ONE unstable compaction) selects exactly what the literal
+    sequential loop selects - tied scores included - and stops early consistently."""
+    g = torch.Generator().manual_seed(0)
+    for trial in range(24):
+        n = int(torch.randint(1, 400, (1,), generator=g))
+        ctr = torch.rand(n, 2, generator=g) * 200
+        wh = torch.rand(n, 2, generator=g) * 80 + 5
+        b = torch.cat([ctr - wh / 2, ctr + wh / 2], 1)
+        s = torch.rand(n, generator=g)
+        if trial % 2:
+            s = torch.floor(s * 16) / 16 + 0.05           # many exact ties
+        for method in ('linear', 'naive'):
+            d1, k1 = restate.soft_nms(b, s, 0.5, 0.5, 0.1, method)
+            d2, k2 = restate.soft_nms_vectorised(b, s, 0.5, 0.5, 0.1, method)
+            assert torch.equal(k1, k2) and torch.equal(d1, d2.float()), (trial, method)
+            _, k3 = restate.soft_nms_vectorised(b, s, 0.5, 0.5, 0.1, method, max_out=7)
+            assert torch.equal(k1[:7], k3)
+    # hand-checked: two identical boxes, linear decay 1 - IoU = 0 -> the second is dropped
+    b = torch.tensor([[0., 0., 10., 10.], [0., 0., 10., 10.], [20., 20., 30., 30.]])
+    d, k = restate.soft_nms(b, torch.tensor([0.9, 0.8, 0.7]), 0.5, 0.5, 0.05)
+    assert k.tolist() == [0, 2] and d[:, 4].tolist() == pytest.approx([0.9, 0.7])
 
 
 def test_nms_restatement_equals_torchvision_nms():
