@@ -30,6 +30,9 @@ METRIC = 'RoIs/sec HTD RoI head fwd+bwd'
 UNIT = 'RoIs/s'
 IMGS, ROIS, POS = 2, 512, 128
 IMG_H, IMG_W = 800, 1333
+# BASELINE.json configs[1]; the SAME string in both arms (the driver compares them)
+WORKLOAD = ('HTD R-50-FPN RoI head fwd+bwd, 2 images/GPU x 512 RoIs (128 positives/img), '
+            '800x1333 pyramid P2-P6 x 256 ch, random init')
 
 
 def parse():
@@ -111,9 +114,10 @@ def run_reference(args):
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * dt / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload='HTD R-50-FPN RoI head fwd+bwd, CPU oracle port, bounded sample',
-                            imgs_per_step=CPU_SAMPLE['imgs'], rois_per_img=CPU_SAMPLE['rois'],
-                            positives_per_img=CPU_SAMPLE['pos'], pyramid='800x1333 P2-P6 x256ch'),
+                config=dict(workload=WORKLOAD,
+                            global_rois_per_step=rois_per_step,
+                            execution='CPU oracle port (oracle/restate.py + C RoIAlign), fp32, '
+                                      'torch CPU, every step = the whole workload of one GPU'),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind='port',
                                   sample=cpu_sample_desc()),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -125,59 +129,250 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions: an NVML polling thread (2 ms period;
+    the timed regions last 0.1-0.3 s, `nvidia-smi -lms` delivered a single sample there), with the
+    nvidia-smi loop as the fallback when NVML cannot be loaded."""
     QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(suffix='.csv')
-        self.proc = None
+        import threading
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.proc = self.thread = None
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.QUERY}',
-                 '--format=csv,noheader,nounits', '-lms', '20'],
-                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[gpu_index]) if vis and vis.split(',')[gpu_index].isdigit() \
+                else gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': pynvml.nvmlClocksThrottleReasonSwPowerCap}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mx.append(mx)
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for nm, b in bits.items():
+                            if r & b:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.how = 'nvml'
         except Exception:
-            self.proc = None
+            self.how = 'nvidia-smi'
+            self.path = tempfile.mktemp(suffix='.csv')
+            try:
+                self.proc = subprocess.Popen(
+                    ['nvidia-smi', f'--id={gpu_index}', f'--query-gpu={self.QUERY}',
+                     '--format=csv,noheader,nounits', '-lms', '10'],
+                    stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+            except Exception:
+                self.proc = None
 
     def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        try:
-            for ln in open(self.path):
-                f = [t.strip() for t in ln.split(',')]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, f[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), samples=len(sm))
-        out['reasons'] = sorted(reasons)
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, how=self.how)
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            try:
+                for ln in open(self.path):
+                    f = [t.strip() for t in ln.split(',')]
+                    if len(f) < 9:
+                        continue
+                    try:
+                        self.sm.append(float(f[1]))
+                        self.mx.append(float(f[2]))
+                    except ValueError:
+                        continue
+                    for nm, v in zip(names, f[5:9]):
+                        if v.lower().startswith('active'):
+                            self.reasons.add(nm)
+                os.unlink(self.path)
+            except Exception:
+                pass
+        if self.sm:
+            sm = sorted(self.sm)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(self.mx), samples=len(sm))
+        out['reasons'] = sorted(self.reasons)
         return out
+
+
+
+# --------------------------------------------------------------------------------------------
+# north_star evidence measured in the same run (N = 1): tensor-pipe roofline of the PGraph
+# aggregation, the RoIAlign / BA gather sweep (BASELINE config 5), the same-box GPU comparator
+# --------------------------------------------------------------------------------------------
+def _median_ms(fn, iters, flush):
+    import torch
+    ts = []
+    for i in range(iters + 3):
+        flush.fill_(float(i))                      # > L2: every timed launch starts cold
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def pgraph_tensor_roofline(dev, flush):
+    """The PGraph aggregation contraction A[n,n] x X[n,1024] (htd_bbox_head.py:213,216) of ONE dense
+    group of n RoIs (BASELINE config 4 stress) on the tcgen05 kernel: 2 n^2 d flops / CUDA-event
+    time of the launch / measured bf16 peak (burst: the kernel is timed alone)."""
+    import torch
+    from htd_b200 import pgraph
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            pk = json.load(f)
+        burst, sust = float(pk['bf16_tflops']), float(pk.get('bf16_tflops_sustained', pk['bf16_tflops']))
+    except Exception:
+        burst, sust = 1667.0, 1408.7
+    out = []
+    d = 1024
+    for n in (1000, 4096):
+        npad = (n + 63) // 64 * 64
+        A = torch.zeros(npad, npad, device=dev, dtype=torch.bfloat16)
+        A[:n, :n] = torch.randn(n, n, device=dev).to(torch.bfloat16)
+        XT = torch.zeros(d, npad, device=dev, dtype=torch.bfloat16)
+        XT[:, :n] = torch.randn(d, n, device=dev).to(torch.bfloat16)
+        D = torch.empty(npad, d, device=dev, dtype=torch.bfloat16)
+        grp = [dict(M=n, N=d, K=n)]
+        ms = _median_ms(lambda: pgraph._gemm(A, XT, grp, D=D, ldd=d), 20, flush)
+        tf = 2.0 * n * n * d / (ms * 1e-3) / 1e12
+        out.append(dict(n=n, flops=2 * n * n * d, ms=ms, achieved=tf, unit='TFLOP/s', peak=burst,
+                        frac=tf / burst, frac_of_sustained=tf / sust))
+    return dict(bound='tensor', kernel='pgraph_gemm_kernel (tcgen05, A_local.X / A_global.Xm)',
+                peak_kind='measured burst (MEASURED_PEAKS.json bf16_tflops)', sizes=out)
+
+
+def gather_sweep(dev, flush, hbm_peak):
+    """BASELINE config 5: RoIAlign / BA gather sweep over the RoI count (2 images, 256 ch, 7x7 bins,
+    P2-P5, bf16): algorithmic bytes of SURVEY 8(d) / event time / measured HBM peak per kernel."""
+    import torch
+    from htd_b200 import ops, synth
+    scales = [0.25, 0.125, 0.0625, 0.03125]
+    C, PP, bs = 256, 49, 2
+    x = [ops.to_channels_last(t.to(dev), torch.bfloat16) for t in synth.make_pyramid(2)[:4]]
+    shapes = [tuple(t.shape) for t in x]
+    rows = []
+    for per in (128, 512, 2048):
+        props = synth.make_proposals(2, per)
+        rois = torch.cat([torch.cat([p.new_full((p.size(0), 1), i), p], 1)
+                          for i, p in enumerate(props)]).to(dev)
+        pos = torch.cat([torch.cat([p.new_full((per // 4, 1), i), p[:per // 4]], 1)
+                         for i, p in enumerate(props)]).to(dev)
+        lv = ops.level_assign(rois, 4)
+        K, P = rois.shape[0], pos.shape[0]
+        plan = ops.RoIPlan(x, scales, rois, lv, 7, 0)
+        px = plan.pixels()
+        out = torch.empty(K, 7, 7, C, device=dev, dtype=torch.bfloat16)
+        g = torch.randn(K, 7, 7, C, device=dev).to(torch.bfloat16)
+
+        def fwd_single():
+            pl = ops.RoIPlan(x, scales, rois, lv, 7, 0)         # plan time is inside the figure
+            ops._fwd_launch('f', x, scales, rois, lv, 7, 0, None, out, plan=pl)
+        by = px * C * bs + K * PP * C * bs + 20 * K
+        ms = _median_ms(fwd_single, 10, flush)
+        rows.append(dict(rois=K, kernel='fwd single (plan included)', ms=ms,
+                         frac=by / ms / 1e6 / hbm_peak))
+        by = K * PP * C * bs + px * C * 4
+        ms = _median_ms(lambda: ops._roi_align_bwd(shapes, torch.bfloat16, scales, rois,
+                                                   plan.tensors(), 7, g, False), 10, flush)
+        rows.append(dict(rois=K, kernel='bwd single', ms=ms, frac=by / ms / 1e6 / hbm_peak))
+        planb = ops.RoIPlan(x, scales, pos, None, 7, 0)
+        pxb = planb.pixels()
+        outb = torch.empty(4, P, 7, 7, C, device=dev, dtype=torch.bfloat16)
+
+        def fwd_ba():
+            pl = ops.RoIPlan(x, scales, pos, None, 7, 0)
+            ops._fwd_launch('f', x, scales, pos, None, 7, 0, None, outb, plan=pl)
+        by = pxb * C * bs + 4 * P * PP * C * bs + 20 * P
+        ms = _median_ms(fwd_ba, 10, flush)
+        rows.append(dict(rois=P, kernel='fwd BA all levels (plan included)', ms=ms,
+                         frac=by / ms / 1e6 / hbm_peak))
+        gp = torch.randn(P, 7, 7, C, device=dev).to(torch.bfloat16)
+        wts = torch.rand(4, P, device=dev)
+        dm = torch.randn(4 * P, C, device=dev)
+        by = P * PP * C * bs + pxb * C * 4
+        ms = _median_ms(lambda: ops._roi_align_bwd(shapes, torch.bfloat16, scales, pos,
+                                                   planb.tensors(), 7, gp, False, scale=wts,
+                                                   ring_edge=1, addvec=dm), 10, flush)
+        rows.append(dict(rois=P, kernel='bwd BA all levels', ms=ms, frac=by / ms / 1e6 / hbm_peak))
+    return dict(what='BASELINE config 5: gather sweep, bf16, 2 images, fraction of the measured HBM '
+                     'roofline (algorithmic bytes of SURVEY 8d; L2 flushed before every launch)',
+                rows=[dict(r, ms=round(r['ms'], 4), frac=round(r['frac'], 3)) for r in rows])
+
+
+def gpu_comparator(dev, pyr_host, props_host, gts, shapes):
+    """Same-box GPU comparator: the reference's algorithm as PyTorch-eager CUDA with
+    torchvision's CUDA roi_align (the generic thread-per-output / atomicAdd kernel mmcv's is derived
+    from), fp32 as the reference runs it.  A reported baseline like the CPU arm: it executes the
+    oracle's restatement (the one other leg of bench.py that may), never the product."""
+    import torch
+    from torchvision.ops import roi_align
+    from htd_b200 import synth
+    from oracle import restate
+    ref = restate.HTDRoIHead()
+    synth.fill_params_(ref, 'init', 0)
+    ref = ref.to(dev)
+    orig = restate.RoIAlign.forward
+    restate.RoIAlign.forward = lambda self, x, rois: roi_align(
+        x, rois.to(x.dtype), self.output_size, self.spatial_scale, self.sampling_ratio, self.aligned)
+    try:
+        xr = [t.to(dev).requires_grad_(True) for t in pyr_host]
+        props = [p.to(dev) for p in props_host]
+
+        def step():
+            for p in ref.parameters():
+                p.grad = None
+            for t in xr:
+                t.grad = None
+            losses = ref.forward_train_sampled(xr, props, gts, shapes, POS)
+            sum(v for k, v in losses.items() if 'loss' in k).backward()
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        reps = 5
+        for _ in range(reps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+    finally:
+        restate.RoIAlign.forward = orig
+    return dict(what='reference algorithm as PyTorch-eager CUDA (oracle restatement on the GPU, '
+                     'torchvision CUDA roi_align with atomicAdd backward), fp32, same workload',
+                ms_per_step=ms, rois_per_s=IMGS * ROIS / (ms * 1e-3))
 
 
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    os.environ.pop('NCCL_DEBUG', None)      # NCCL would print its version banner on stdout
+    if os.environ.get('NCCL_DEBUG'):        # keep NCCL's log (rank / transport evidence), but on
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stderr: stdout is the JSON line
     import htd_b200
     from htd_b200 import _lib, synth
     from htd_b200.parallel import GradAllReducer
@@ -321,7 +516,6 @@ def run_gpu(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = launches_per_step * args.steps
-    clk = clocks.stop()
 
     # ---- timed region 2: end to end from host buffers (H2D double-buffered, D2H of the losses)
     copy_stream = torch.cuda.Stream(device=dev)
@@ -386,6 +580,7 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    clk = clocks.stop()                     # sampled over both timed regions
 
     # ---- the COMPLETE step: assign + sample on the device, then the same two stages, one graph --
     static = None
@@ -470,6 +665,26 @@ def run_gpu(args):
             head.train()
             print(f'[bench] inference figure failed ({type(e).__name__}: {e})', file=sys.stderr)
 
+    # ---- north_star evidence in the driver-visible line (N = 1 only) ----------------------------
+    roofline_tensor = sweep = comparator = None
+    if world == 1 and not args.no_static:
+        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+        for name, fn in (('roofline_tensor', lambda: pgraph_tensor_roofline(dev, flush)),
+                         ('sweep', lambda: gather_sweep(dev, flush, hbm_peak)),
+                         ('comparator', lambda: gpu_comparator(dev, pyr_host, props_host, gts, shapes))):
+            try:
+                val = fn()
+            except Exception as e:
+                print(f'[bench] {name} failed ({type(e).__name__}: {e})', file=sys.stderr)
+                val = None
+            if name == 'roofline_tensor':
+                roofline_tensor = val
+            elif name == 'sweep':
+                sweep = val
+            else:
+                comparator = val
+        del flush
+
     # ---- max over ranks ------------------------------------------------------------------------
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -491,16 +706,23 @@ def run_gpu(args):
                              share_of_step=(tot_ms / ksteps) / (ms / args.steps))
     dom = max(kernels, key=lambda k: kernels[k]['share_of_step']) if kernels else None
     roofline = None
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_ncu_traffic.json')) as f:
-            traffic = json.load(f).get(dom)
-    except Exception:
-        pass
+    traffic = traffic_src = None
+    for fn_ in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', fn_)) as f:
+                traffic = json.load(f).get(dom)
+            if traffic is not None:
+                traffic_src = (f'profiles/{fn_}: dram__bytes_read.sum + dram__bytes_write.sum of one '
+                               'ncu --set full capture of this kernel on this workload (not '
+                               're-measured in this run: ncu cannot run inside the bench)')
+                break
+        except Exception:
+            pass
     if dom:
         k = kernels[dom]
         roofline = dict(bound='hbm', kernel=dom, achieved=k['achieved_GBs'], peak=hbm_peak,
-                        unit='GB/s', frac=k['frac'], traffic=traffic, peak_kind=peak_kind,
+                        unit='GB/s', frac=k['frac'], traffic=traffic, traffic_source=traffic_src,
+                        peak_kind=peak_kind,
                         alg_bytes_per_launch=k['alg_MB_per_launch'] * 1e6,
                         avg_ms=k['avg_ms'], share_of_step=k['share_of_step'])
 
@@ -522,9 +744,7 @@ def run_gpu(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic',
-                config=dict(workload='HTD R-50-FPN RoI head fwd+bwd, 2 images/GPU x 512 RoIs '
-                                     '(128 positives/img), 800x1333 pyramid P2-P6 x 256 ch, '
-                                     'random init',
+                config=dict(workload=WORKLOAD,
                             global_rois_per_step=rois_per_step * world,
                             parallelism=f'dp{world}' + (' + NCCL grad all-reduce' + (
                                 ' (stage-1 part overlapped with the rest of backward)'
@@ -543,6 +763,7 @@ def run_gpu(args):
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches, clocks=clk, roofline=roofline, kernels=kernels,
+                roofline_tensor=roofline_tensor, sweep_config5=sweep, gpu_comparator=comparator,
                 cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -76,7 +76,7 @@ SIGNATURES = {
                           c_int, c_int, c_float, c_float, c_float, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p],
     'htd_rcnn_loss_bwd': [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
-                          c_float, c_float, c_int, c_int, c_void_p],
+                          c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'htd_multiclass_nms': [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_int,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_multiclass_soft_nms': [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float,

@@ -197,11 +197,19 @@ class BBoxHead(nn.Module):
         dev = sampling_results[0].pos_bboxes.device
         sizes = tuple((r.pos_bboxes.size(0), r.neg_bboxes.size(0)) for r in sampling_results)
         key = (sizes, str(dev))
-        is_pos = BBoxHead._pos_mask_cache.get(key)
-        if is_pos is None:                      # depends on the counts only: built once, reused
+        cache = BBoxHead._pos_mask_cache
+        is_pos = cache.get(key)
+        if is_pos is None:
+            # depends on the counts only.  Fixed-count protocols (bench, CUDA graphs) hit the cache
+            # every step; with the reference's random sampler the counts change almost every
+            # iteration, so the cache is bounded (least recently used entry dropped)
             m = torch.cat([torch.cat([torch.ones(p, dtype=torch.uint8), torch.zeros(n, dtype=torch.uint8)])
                            for p, n in sizes])
-            is_pos = BBoxHead._pos_mask_cache[key] = m.to(dev)
+            is_pos = cache[key] = m.to(dev)
+            while len(cache) > BBoxHead._pos_mask_cache_max:
+                cache.pop(next(iter(cache)))
+        else:
+            cache[key] = cache.pop(key)         # most recently used last
         boxes = torch.cat([t for r in sampling_results for t in (r.pos_bboxes, r.neg_bboxes)], 0)
         K = boxes.size(0)
         gtb = boxes.new_zeros((K, 4), dtype=torch.float32)
@@ -269,6 +277,7 @@ class BBoxHead(nn.Module):
     fused_glue = True        # class switch (diagnostics): targets / loss / decode via csrc/rcnn_glue.cu
     aligned_small_fc = True  # class switch (diagnostics): 8-aligned fc_cls / fc_reg GEMMs in bf16
     _pos_mask_cache = {}
+    _pos_mask_cache_max = 16
 
     # ---- decoding (bbox_head.py:188-335) ------------------------------------------------------
     def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False,

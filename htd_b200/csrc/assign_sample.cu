@@ -307,12 +307,8 @@ int htd_assign_sample(const float* props, const unsigned char* valid, int B, int
     p.row_is_gt = row_is_gt; p.row_cand = row_cand; p.row_gt_index = row_gt_index;
     p.counts = counts; p.gt_inds = gt_inds; p.max_ov = max_overlaps;
     const size_t smem = (size_t)G * 16 + (size_t)(G + N) * 8 + (size_t)G * 4;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(assign_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             HTD_MAX_GT * 20 + HTD_MAX_CANDIDATES * 8);
-        attr_done = true;
-    }
+    HTD_SMEM_OPTIN(assign_sample_kernel, HTD_MAX_GT * 20 + HTD_MAX_CANDIDATES * 8,
+                   "htd_assign_sample");
     assign_sample_kernel<<<B, kAsThreads, smem, (cudaStream_t)stream>>>(p);
     HTD_CHECK_LAUNCH("htd_assign_sample");
     return HTD_OK;

@@ -5,11 +5,27 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/htd_b200.h"
 
 namespace htd {
 
 void set_error(const char* fmt, ...);
+
+// SM count of the CURRENT device, cached per device (a process may drive several GPUs)
+inline int sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cache[dev & 63].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+            v = 148;
+        cache[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
 
 #define HTD_CHECK_ARG(cond, ...)                                   \
     do {                                                           \
@@ -17,6 +33,28 @@ void set_error(const char* fmt, ...);
             htd::set_error(__VA_ARGS__);                           \
             return HTD_ERR_INVALID_ARGUMENT;                       \
         }                                                          \
+    } while (0)
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory ONCE PER DEVICE (the attribute is
+// per device: a process-wide flag would leave a second GPU driven by the same process without it)
+// and thread-safely (autograd worker threads); a failure is reported, not ignored.  Pass a
+// templated kernel in parentheses.
+#define HTD_SMEM_OPTIN(func, bytes, who)                                                         \
+    do {                                                                                         \
+        static std::atomic<unsigned long long> done__{0ull};                                     \
+        int dev__ = 0;                                                                           \
+        cudaGetDevice(&dev__);                                                                   \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                   \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                                 \
+            cudaError_t oe__ = cudaFuncSetAttribute(                                             \
+                func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));                \
+            if (oe__ != cudaSuccess) {                                                           \
+                htd::set_error("%s: cannot reserve %d B of shared memory: %s", who, (int)(bytes), \
+                               cudaGetErrorString(oe__));                                        \
+                return HTD_ERR_CUDA;                                                             \
+            }                                                                                    \
+            done__.fetch_or(bit__, std::memory_order_release);                                   \
+        }                                                                                        \
     } while (0)
 
 #define HTD_CHECK_LAUNCH(name)                                                     \

@@ -429,12 +429,7 @@ int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores,
                                                       cand_k, ws_n, ws_f);
         HTD_CHECK_LAUNCH("htd_multiclass_nms(collect)");
         const size_t smem = (size_t)K * (16 + 4 + 4 + 4 + 1);
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(nms_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 HTD_NMS_MAX_ROIS * 29);
-            attr_done = true;
-        }
+        HTD_SMEM_OPTIN(nms_class_kernel, HTD_NMS_MAX_ROIS * 29, "htd_multiclass_nms");
         nms_class_kernel<<<C, kNmsThreads, smem, st>>>(boxes, box_classes, scores, K, C, iou_thr,
                                                        cand_k, ws_n, ws_f, kept_k, kept_score);
         HTD_CHECK_LAUNCH("htd_multiclass_nms(class)");

@@ -542,24 +542,8 @@ static int launch_gemm(const void* A, long long a_rows, long long a_ld, const vo
     if (rc) return rc;
     rc = make_map(&mb, B, b_rows, b_ld, kBN, "htd_pgraph_gemm(B)");
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pgraph_gemm_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-        if (e != cudaSuccess) {
-            set_error("htd_pgraph_gemm: cannot reserve %d B of shared memory: %s", kSmemBytes,
-                      cudaGetErrorString(e));
-            return HTD_ERR_CUDA;
-        }
-        attr_set = true;
-    }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
-            num_sms = 148;
-    }
+    HTD_SMEM_OPTIN(pgraph_gemm_kernel, kSmemBytes, "htd_pgraph_gemm");
+    const int num_sms = sm_count();
     const unsigned grid = (unsigned)(total < num_sms ? total : num_sms);   // persistent CTAs
     pgraph_gemm_kernel<<<grid, kGemmThreads, kSmemBytes, st>>>(ma, mb, p);
     HTD_CHECK_LAUNCH("htd_pgraph_gemm(bf16)");

@@ -194,10 +194,14 @@ __global__ void __launch_bounds__(256) rcnn_loss_final_kernel(const float* __res
     }
 }
 
-// dcls *= g_cls * w_cls / avg_factor ; dbbox *= g_bbox * w_bbox / K   (g_* are device scalars)
+// dcls_out = dcls * g_cls * w_cls / avg_factor ; dbbox_out = dbbox * g_bbox * w_bbox / K  (g_* are
+// device scalars).  The saved unnormalised gradients are only READ, so the node can run backward
+// more than once (retain_graph) without scaling them twice.
 template <typename T>
-__global__ void __launch_bounds__(256) rcnn_loss_bwd_kernel(T* __restrict__ dcls, long long ncls,
-                                                            T* __restrict__ dbbox, long long nbox,
+__global__ void __launch_bounds__(256) rcnn_loss_bwd_kernel(const T* __restrict__ dcls, long long ncls,
+                                                            const T* __restrict__ dbbox, long long nbox,
+                                                            T* __restrict__ dcls_out,
+                                                            T* __restrict__ dbbox_out,
                                                             const float* __restrict__ g_cls,
                                                             const float* __restrict__ g_bbox,
                                                             const float* __restrict__ out, float w_cls,
@@ -207,8 +211,8 @@ __global__ void __launch_bounds__(256) rcnn_loss_bwd_kernel(T* __restrict__ dcls
                      (pad_rows ? out[3] : 1.f / (float)(K > 0 ? K : 1));
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncls + nbox;
          i += (long long)gridDim.x * blockDim.x) {
-        if (i < ncls) stv<T>(dcls + i, ldv<T>(dcls + i) * sc);
-        else stv<T>(dbbox + (i - ncls), ldv<T>(dbbox + (i - ncls)) * sb);
+        if (i < ncls) stv<T>(dcls_out + i, ldv<T>(dcls + i) * sc);
+        else stv<T>(dbbox_out + (i - ncls), ldv<T>(dbbox + (i - ncls)) * sb);
     }
 }
 
@@ -292,23 +296,26 @@ int htd_rcnn_loss_fwd(const void* cls_score, int num_cls1, const void* bbox_pred
     return HTD_OK;
 }
 
-int htd_rcnn_loss_bwd(void* dcls, long long ncls, void* dbbox, long long nbox, int dtype,
+int htd_rcnn_loss_bwd(const void* dcls, long long ncls, const void* dbbox, long long nbox, int dtype,
                       const float* g_cls, const float* g_bbox, const float* out4, float w_cls,
-                      float w_bbox, int K, int pad_rows, htd_stream_t stream) {
+                      float w_bbox, int K, int pad_rows, void* dcls_out, void* dbbox_out,
+                      htd_stream_t stream) {
     HTD_CHECK_ARG(dtype == HTD_F32 || dtype == HTD_BF16, "htd_rcnn_loss_bwd: bad dtype");
     HTD_CHECK_ARG(ncls >= 0 && nbox >= 0 && out4, "htd_rcnn_loss_bwd: bad arguments");
     if (ncls + nbox == 0) return HTD_OK;
-    HTD_CHECK_ARG(dcls && dbbox, "htd_rcnn_loss_bwd: null pointer");
+    HTD_CHECK_ARG(dcls && dbbox && dcls_out && dbbox_out, "htd_rcnn_loss_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = ncls + nbox;
     const unsigned blocks = (unsigned)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
     if (dtype == HTD_F32)
-        rcnn_loss_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float*>(dcls), ncls,
-                                                            static_cast<float*>(dbbox), nbox, g_cls,
-                                                            g_bbox, out4, w_cls, w_bbox, K, pad_rows);
+        rcnn_loss_bwd_kernel<float><<<blocks, 256, 0, st>>>(
+            static_cast<const float*>(dcls), ncls, static_cast<const float*>(dbbox), nbox,
+            static_cast<float*>(dcls_out), static_cast<float*>(dbbox_out), g_cls, g_bbox, out4, w_cls,
+            w_bbox, K, pad_rows);
     else
         rcnn_loss_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-            static_cast<__nv_bfloat16*>(dcls), ncls, static_cast<__nv_bfloat16*>(dbbox), nbox, g_cls,
+            static_cast<const __nv_bfloat16*>(dcls), ncls, static_cast<const __nv_bfloat16*>(dbbox),
+            nbox, static_cast<__nv_bfloat16*>(dcls_out), static_cast<__nv_bfloat16*>(dbbox_out), g_cls,
             g_bbox, out4, w_cls, w_bbox, K, pad_rows);
     HTD_CHECK_LAUNCH("htd_rcnn_loss_bwd");
     return HTD_OK;

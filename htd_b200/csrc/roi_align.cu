@@ -1338,18 +1338,8 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     const size_t smem = region + (size_t)pooled * kFwdStages * sizeof(uint64_t);
 #define HTD_FWD_LAUNCH(TI, TO)                                                                    \
     do {                                                                                          \
-        static bool attr_done = false;                                                            \
-        if (!attr_done) {                                                                         \
-            cudaError_t e = cudaFuncSetAttribute(roi_align_fwd_kernel<TI, TO>,                    \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                                 fwd_smem_max((int)sizeof(TI)));                  \
-            if (e != cudaSuccess) {                                                               \
-                set_error("htd_roi_align_fwd: shared memory opt-in failed: %s",                   \
-                          cudaGetErrorString(e));                                                 \
-                return HTD_ERR_CUDA;                                                              \
-            }                                                                                     \
-            attr_done = true;                                                                     \
-        }                                                                                         \
+        HTD_SMEM_OPTIN((roi_align_fwd_kernel<TI, TO>), fwd_smem_max((int)sizeof(TI)),             \
+                       "htd_roi_align_fwd");                                                      \
         roi_align_fwd_kernel<TI, TO><<<grid, block, smem, st>>>(p);                               \
     } while (0)
     if (in_dtype == HTD_F32 && out_dtype == HTD_F32) HTD_FWD_LAUNCH(float, float);
@@ -1429,18 +1419,9 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
                         pooled * pooled * cw * dtype_size(dy_dtype);
 #define HTD_BWD_LAUNCH(TY, TX)                                                                    \
     do {                                                                                          \
-        static bool attr_done = false;                                                            \
-        if (!attr_done) {                                                                         \
-            cudaError_t e = cudaFuncSetAttribute(                                                 \
-                roi_align_bwd_kernel<TY, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                BwdStages<TY>::value * HTD_MAX_POOLED * HTD_MAX_POOLED * 256 * (int)sizeof(TY));                     \
-            if (e != cudaSuccess) {                                                               \
-                set_error("htd_roi_align_bwd: shared memory opt-in failed: %s",                   \
-                          cudaGetErrorString(e));                                                 \
-                return HTD_ERR_CUDA;                                                              \
-            }                                                                                     \
-            attr_done = true;                                                                     \
-        }                                                                                         \
+        HTD_SMEM_OPTIN((roi_align_bwd_kernel<TY, TX>),                                            \
+                       BwdStages<TY>::value * HTD_MAX_POOLED * HTD_MAX_POOLED * 256 *             \
+                           (int)sizeof(TY), "htd_roi_align_bwd");                                 \
         roi_align_bwd_kernel<TY, TX><<<grid, block, smem, st>>>(p);                               \
     } while (0)
     const int variant = bwd_variant();
@@ -1451,18 +1432,8 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
     if (mma) {
 #define HTD_BWD_MMA_LAUNCH(TX, S, N, G)                                                           \
     do {                                                                                          \
-        static bool attr_done = false;                                                            \
-        if (!attr_done) {                                                                         \
-            cudaError_t e = cudaFuncSetAttribute(roi_align_bwd_mma_kernel<TX, S, N, G>,           \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                                 S * kMmaBlockBytes);                              \
-            if (e != cudaSuccess) {                                                               \
-                set_error("htd_roi_align_bwd: shared memory opt-in failed: %s",                   \
-                          cudaGetErrorString(e));                                                 \
-                return HTD_ERR_CUDA;                                                              \
-            }                                                                                     \
-            attr_done = true;                                                                     \
-        }                                                                                         \
+        HTD_SMEM_OPTIN((roi_align_bwd_mma_kernel<TX, S, N, G>), S * kMmaBlockBytes,               \
+                       "htd_roi_align_bwd(mma)");                                                 \
         roi_align_bwd_mma_kernel<TX, S, N, G>                                                     \
             <<<grid, (4 * G + 1) * 32, S * kMmaBlockBytes, st>>>(p);                               \
     } while (0)

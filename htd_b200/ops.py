@@ -255,6 +255,17 @@ class GradSink:
         self.scales = None
         self.pooled = None
 
+    def park(self, scales, pooled, source):
+        """One gather launch serves every parked source, so they must agree on the spatial scales
+        and the pooled size (extractors sharing a Pyramid with different ``output_size`` or
+        ``featmap_strides`` would otherwise get a silently wrong dX)."""
+        if self.sources and (tuple(self.scales) != tuple(scales) or self.pooled != pooled):
+            raise RuntimeError(
+                'extractors that share one Pyramid must use the same featmap_strides and '
+                f'output_size: parked {self.scales} / {self.pooled}, got {scales} / {pooled}')
+        self.scales, self.pooled = scales, pooled
+        self.sources.append(source)
+
 
 class Pyramid(list):
     """Channels-last feature maps of one step + the token / sink that defer their gradient."""
@@ -412,9 +423,8 @@ class _RoIAlignLevels(torch.autograd.Function):
         grads = [None] * len(shapes)
         gtoken = None
         if ctx.deferred:                       # park for the pyramid's single gather launch
-            ctx.sink.scales, ctx.sink.pooled = scales, pooled
-            ctx.sink.sources.append(dict(rois=rois, plan=tuple(ctx.saved_tensors[2:]), dy=g,
-                                         dy_per_level=not single))
+            ctx.sink.park(scales, pooled, dict(rois=rois, plan=tuple(ctx.saved_tensors[2:]), dy=g,
+                                               dy_per_level=not single))
             gtoken = torch.zeros(1, dtype=torch.float32, device=g.device)
         elif ctx.with_dx:
             grads = _roi_align_bwd(shapes, fdtype, scales, rois, ctx.saved_tensors[2:], pooled, g,
@@ -506,10 +516,9 @@ class _BAFunction(torch.autograd.Function):
         grads = [None] * L
         gtoken = None
         if ctx.deferred:
-            ctx.sink.scales, ctx.sink.pooled = scales, pooled
-            ctx.sink.sources.append(dict(rois=rois, plan=tuple(ctx.saved_tensors[7:]), dy=g,
-                                         dy_per_level=False, scale=wts, ring_edge=edge,
-                                         addvec=dm.contiguous()))
+            ctx.sink.park(scales, pooled, dict(rois=rois, plan=tuple(ctx.saved_tensors[7:]), dy=g,
+                                               dy_per_level=False, scale=wts, ring_edge=edge,
+                                               addvec=dm.contiguous()))
             gtoken = torch.zeros(1, dtype=torch.float32, device=g.device)
         elif ctx.with_dx:
             grads = _roi_align_bwd(shapes, fdt, scales, rois, ctx.saved_tensors[7:], pooled, g,
@@ -672,10 +681,14 @@ class _RCNNLoss(torch.autograd.Function):
         nblk = max((K + 7) // 8, 1)
         partial = torch.empty((nblk, 4), dtype=torch.float32, device=dev)
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
-        check(lib().htd_rcnn_loss_fwd(ptr(cs), C1, ptr(bp), dt(cs), ptr(labels.contiguous()),
-                                      ptr(label_weights.float().contiguous()),
-                                      ptr(bbox_targets.float().contiguous()),
-                                      ptr(bbox_weights.float().contiguous()), K, int(num_classes),
+        # converted copies are bound to locals: ptr() keeps only the address, and a temporary
+        # would be freed (and its block reused by the next conversion) before the launch
+        lab_c = labels.contiguous()
+        lw_c = label_weights.float().contiguous()
+        bt_c = bbox_targets.float().contiguous()
+        bw_c = bbox_weights.float().contiguous()
+        check(lib().htd_rcnn_loss_fwd(ptr(cs), C1, ptr(bp), dt(cs), ptr(lab_c), ptr(lw_c),
+                                      ptr(bt_c), ptr(bw_c), K, int(num_classes),
                                       float(beta), float(w_cls), float(w_bbox), int(bool(pad_rows)),
                                       ptr(dcls), ptr(dbbox), ptr(partial), ptr(out4), stream()),
               'htd_rcnn_loss_fwd')
@@ -692,10 +705,11 @@ class _RCNNLoss(torch.autograd.Function):
         w_cls, w_bbox, K, cdt, bdt, pad_rows = ctx.cfg
         g_cls = None if g_cls is None else g_cls.detach().float().contiguous()
         g_bbox = None if g_bbox is None else g_bbox.detach().float().contiguous()
+        gc, gb = torch.empty_like(dcls), torch.empty_like(dbbox)   # saved buffers stay untouched
         check(lib().htd_rcnn_loss_bwd(ptr(dcls), dcls.numel(), ptr(dbbox), dbbox.numel(), dt(dcls),
                                       ptr(g_cls), ptr(g_bbox), ptr(out4), w_cls, w_bbox, K, pad_rows,
-                                      stream()), 'htd_rcnn_loss_bwd')
-        return dcls.to(cdt), dbbox.to(bdt), None, None, None, None, None, None, None, None, None
+                                      ptr(gc), ptr(gb), stream()), 'htd_rcnn_loss_bwd')
+        return gc.to(cdt), gb.to(bdt), None, None, None, None, None, None, None, None, None
 
 
 def rcnn_loss(cls_score, bbox_pred, labels, label_weights, bbox_targets, bbox_weights, num_classes,

@@ -5,11 +5,20 @@ detector in MMDistributedDataParallel, ``mmdet/apis/train.py:72-80``, NCCL backe
 only their image's pyramid and PGraph groups never span images (htd_bbox_head.py:198-202).
 
 ``GradAllReducer`` buckets the parameters in reverse registration order (~backward order) and
-launches an asynchronous ``all_reduce`` for a bucket as soon as the last gradient of that bucket
-has been accumulated, so NCCL traffic over NVLink overlaps the rest of the backward pass;
-``allreduce()`` after ``backward()`` waits, averages and scatters the results back into
-``p.grad``.  Works with any torch.distributed backend (gloo in the CPU tests).
+launches an asynchronous ``all_reduce`` for a bucket once the last gradient of that bucket AND of
+every earlier bucket has been accumulated, so NCCL traffic over NVLink overlaps the rest of the
+backward pass while every rank issues its collectives in the SAME order (NCCL pairs collectives
+by issue order: a rank-dependent order - e.g. one rank with no positive RoI, whose BA attention
+parameters finish at a different time or not at all - would pair buckets of different sizes).
+``allreduce()`` after ``backward()`` launches what is left in index order, waits, averages and
+writes the results back into ``p.grad``.  Gradient accumulation works as with DDP: every backward
+pass but the last runs under ``no_sync()`` (hooks off), so each rank issues exactly one collective
+per bucket and step; a second un-declared backward is reported instead of silently issuing a
+rank-dependent number of collectives.  Works with any torch.distributed backend (gloo in the CPU
+tests).
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -36,9 +45,25 @@ class GradAllReducer:
         for bi, b in enumerate(self.buckets):
             for p in b:
                 self._bucket_of[id(p)] = bi
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._reset()
+
+    def _reset(self):
         self._pending = [len(b) for b in self.buckets]
         self._inflight = {}
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._next = 0              # buckets [0, _next) have been launched, in index order
+        self._stale = False         # a gradient changed after its bucket was launched
+        self._sync = True
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Backward passes inside this context only accumulate into ``p.grad`` (no collective is
+        launched); the last backward of the step runs outside it, then ``allreduce()``."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
 
     def _launch(self, bi):
         bucket = self.buckets[bi]
@@ -48,17 +73,33 @@ class GradAllReducer:
         self._inflight[bi] = (flat, work)
 
     def _on_grad(self, p):
+        if not self._sync:
+            return
         bi = self._bucket_of[id(p)]
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            self._launch(bi)
+        if self._pending[bi] < 0 or bi < self._next:
+            # a second backward() outside no_sync() before allreduce(): what was launched for this
+            # bucket is out of date (reported in allreduce())
+            self._stale = True
+            return
+        # fixed issue order: bucket i only after buckets 0..i-1
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._launch(self._next)
+            self._next += 1
 
     def allreduce(self):
-        """Finish the step: launch buckets whose gradients never all arrived (unused
-        parameters), wait for every bucket, average, write back."""
-        for bi in range(len(self.buckets)):
-            if bi not in self._inflight:
-                self._launch(bi)
+        """Finish the step: launch the buckets that were not launched from the hooks (gradients
+        that arrived late or never - unused parameters) in index order, wait for every bucket,
+        average, write back."""
+        if self._stale:
+            for _, work in self._inflight.values():
+                work.wait()
+            self._reset()
+            raise RuntimeError('GradAllReducer: more than one backward() since the last allreduce(); '
+                               'run all but the last one under `with reducer.no_sync():`')
+        for bi in range(self._next, len(self.buckets)):
+            self._launch(bi)
+        self._next = len(self.buckets)
         inv = 1.0 / self.world
         for bi, bucket in enumerate(self.buckets):
             flat, work = self._inflight[bi]
@@ -73,8 +114,7 @@ class GradAllReducer:
                 else:
                     p.grad.copy_(view)
                 off += n
-        self._inflight.clear()
-        self._pending = [len(b) for b in self.buckets]
+        self._reset()
 
     def remove(self):
         for h in self._hooks:

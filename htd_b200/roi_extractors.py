@@ -150,7 +150,13 @@ class AdptRoIExtractor(BaseRoIExtractor):
             return ops.roi_align_levels(feats_cl, rois, scales, l0.output_size[0],
                                         l0.sampling_ratio)[0]
         if rois.size(0) == 0:
-            return feats[0].new_zeros(0, self.out_channels, *l0.output_size)
+            # no RoI on this rank: the result is empty but stays attached to the attention
+            # parameters (zero gradients instead of none), as the reference's `0 * sum(params)` does
+            # (single_level_roi_extractor.py:96-98) - every data-parallel rank then reduces the
+            # same set of gradients in the same order
+            out = feats[0].new_zeros(0, self.out_channels, *l0.output_size)
+            return out + 0 * sum(p.sum() for p in (self.conv1.weight, self.conv1.bias,
+                                                   self.conv2.weight, self.conv2.bias)).to(out.dtype)
         if roi_scale_factor is not None:
             rois = self.roi_rescale(rois, roi_scale_factor)
         return ops.ba_extract(feats_cl, rois, scales, self.conv1, self.conv2, l0.output_size[0],

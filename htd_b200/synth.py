@@ -140,6 +140,11 @@ def _stable_value(name, p, z):
         return 0.005 * z + 0.001 * _alternating(p.shape[0]).view(-1, 1, 1, 1)
     if name.endswith('fc_reg.weight'):
         return 0.001 * z
+    if name.endswith('bbox_head.0.fc_cls.weight'):
+        # stage-0 classifier = the PGraph prototype (htd_bbox_head.py:158,194): logits of O(3) make
+        # the semantic vectors `sam` differ between RoIs by far more than a bf16 ulp, so the global
+        # graph softmax - and the gradient that reaches this layer through it - is well resolved
+        return 0.1 * z
     if name.endswith('fc_cls.weight') or name.endswith('glbctx_head.fc.weight'):
         return 0.01 * z
     if name.endswith('bias'):

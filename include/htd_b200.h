@@ -300,8 +300,9 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
  *   out4 = (w_cls * sum_k lw_k CE_k / max(#{lw > 0}, 1),  top-1 accuracy in %,
  *           w_bbox * sum_{k positive} sum_j bw_kj smoothL1_beta(pred - target) / K,  1 / avg_factor);
  *   dcls [K,num_cls1] / dbbox [K,4] receive the unnormalised gradients, partial is a
- *   [ceil(K/8), 4] fp32 workspace.  htd_rcnn_loss_bwd scales them in place by the incoming
- *   gradients g_cls / g_bbox (device scalars, NULL = 0).
+ *   [ceil(K/8), 4] fp32 workspace.  htd_rcnn_loss_bwd writes them, scaled by the incoming
+ *   gradients g_cls / g_bbox (device scalars, NULL = 0), to dcls_out / dbbox_out; the saved
+ *   buffers are only read, so the backward may run more than once.
  *   pad_rows != 0: rows with label_weight == 0 are the pad rows of htd_assign_sample (static
  *   shapes), not samples - they are left out of the accuracy, and the accuracy / loss_bbox
  *   denominators are the number of real rows max(#{lw > 0}, 1) instead of K (the reference's
@@ -319,9 +320,10 @@ int htd_rcnn_loss_fwd(const void* cls_score, int num_cls1, const void* bbox_pred
                       const float* bbox_targets, const float* bbox_weights, int K, int num_classes,
                       float beta, float w_cls, float w_bbox, int pad_rows, void* dcls, void* dbbox,
                       float* partial, float* out4, htd_stream_t stream);
-int htd_rcnn_loss_bwd(void* dcls, long long ncls, void* dbbox, long long nbox, int dtype,
+int htd_rcnn_loss_bwd(const void* dcls, long long ncls, const void* dbbox, long long nbox, int dtype,
                       const float* g_cls, const float* g_bbox, const float* out4, float w_cls,
-                      float w_bbox, int K, int pad_rows, htd_stream_t stream);
+                      float w_bbox, int K, int pad_rows, void* dcls_out, void* dbbox_out,
+                      htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Proposal -> gt assignment + random sampling of one RoI-head stage, all images in one launch,

@@ -222,7 +222,8 @@ def test_pgraph_function_isolated(dtype, tol, rset):
     xo, so = x.double().requires_grad_(True), sam.double().requires_grad_(True)
     ref, layers = _pgraph_oracle(xo, so, rois.double(), W.double(), b.double(), nimg)
     params = [p for m in layers for p in (m.weight, m.bias)]
-    go = torch.autograd.grad((ref * dy.double()).sum(), [xo, so] + params)
+    go = torch.autograd.grad((ref * dy.double()).sum(), [xo, so] + params, allow_unused=True)
+    go = [torch.zeros_like(p) if q is None else q for q, p in zip(go, [xo, so] + params)]
     # product
     xg, sg = x.cuda().requires_grad_(True), sam.cuda().requires_grad_(True)
     Wg = [W[i].cuda().requires_grad_(True) for i in range(4)]

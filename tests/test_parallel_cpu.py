@@ -65,6 +65,71 @@ def test_bucketed_grad_allreduce_world2(tmp_path):
     assert all((g == 0).all() for g in g0[len(want):])      # unused params: zero, not missing
 
 
+def _worker_uneven(rank, world, port, out_dir):
+    """Rank 1 never uses `side` (a rank without positive RoIs never runs the BA attention convs):
+    its gradients are missing there, so the hooks fire in a different pattern on the two ranks.
+    The collectives must still pair bucket by bucket; then a step with two backward passes before
+    the exchange (gradient accumulation)."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from htd_b200.parallel import GradAllReducer
+    torch.manual_seed(0)
+    trunk = nn.Linear(30, 200)
+    side = nn.Linear(200, 200)                    # registered between the two: a middle bucket
+    top = nn.Linear(200, 3)
+    params = list(trunk.parameters()) + list(side.parameters()) + list(top.parameters())
+    red = GradAllReducer(params, world, bucket_mb=0.05)
+    assert len(red.buckets) >= 3
+    data = torch.randn(4, 30, generator=torch.Generator().manual_seed(2 + rank))
+
+    def loss(scale=1.0):
+        h = torch.relu(trunk(data))
+        if rank == 0:
+            h = h + side(h)
+        return top(h).pow(2).sum() * scale
+    for p in params:
+        p.grad = None
+    loss().backward()
+    red.allreduce()
+    g_single = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    with red.no_sync():                           # accumulation: two backward passes, one exchange
+        loss(0.25).backward()
+    loss(0.75).backward()
+    red.allreduce()
+    torch.save(dict(single=g_single, accum=[p.grad.clone() for p in params]),
+               os.path.join(out_dir, f'u{rank}.pt'))
+    dist.destroy_process_group()
+
+
+def test_collectives_pair_when_a_rank_misses_gradients_and_with_accumulation(tmp_path):
+    world = 2
+    mp.spawn(_worker_uneven, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / 'u0.pt'), torch.load(tmp_path / 'u1.pt')
+    for a, b in zip(r0['single'], r1['single']):
+        assert torch.equal(a, b)                                  # both ranks hold the same average
+    # reference in one process
+    torch.manual_seed(0)
+    trunk, side, top = nn.Linear(30, 200), nn.Linear(200, 200), nn.Linear(200, 3)
+    params = list(trunk.parameters()) + list(side.parameters()) + list(top.parameters())
+    want = [torch.zeros_like(p) for p in params]
+    for rank in range(2):
+        data = torch.randn(4, 30, generator=torch.Generator().manual_seed(2 + rank))
+        for p in params:
+            p.grad = None
+        h = torch.relu(trunk(data))
+        if rank == 0:
+            h = h + side(h)
+        top(h).pow(2).sum().backward()
+        want = [w + (p.grad if p.grad is not None else 0) / 2 for w, p in zip(want, params)]
+    for a, w in zip(r0['single'], want):
+        assert torch.allclose(a, w, rtol=1e-5, atol=1e-6)
+    for a, b, w in zip(r0['accum'], r1['accum'], want):           # 0.25 + 0.75 of the same loss
+        assert torch.equal(a, b) and torch.allclose(a, w, rtol=1e-5, atol=1e-6)
+
+
 def test_shard_images_covers_everything():
     from htd_b200.parallel import shard_images
     for n, w in ((16, 8), (5, 2), (3, 4), (0, 2)):
