@@ -23,6 +23,16 @@ class HtdGemmGroup(ctypes.Structure):
                                                'd_row', 'd_col', 'dt_row', 'dt_col', 'bias_off')]
 
 
+class HtdDenseGemm(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ('kind', 'M', 'N', 'K', 'P', 'Cin', 'Cout', 'pooled',
+                                               'd_dtype', 'relu', 'splits', 'reserved')] + \
+               [(n, c_void_p) for n in ('A', 'B', 'D', 'D2', 'bias', 'row_bias', 'row_class', 'gate')] + \
+               [(n, ctypes.c_longlong) for n in ('lda', 'ldb', 'ldd', 'ldg', 'ld_row_bias')]
+
+
+(DENSE_NT, DENSE_NN, DENSE_TN, DENSE_CONV_FPROP, DENSE_CONV_DGRAD, DENSE_CONV_WGRAD) = range(6)
+
+
 class HtdBwdSource(ctypes.Structure):
     _fields_ = [('rois', c_void_p), ('boxes', c_void_p), ('offsets', c_void_p), ('ranges', c_void_p),
                 ('weights', c_void_p), ('dy', c_void_p), ('scale', c_void_p), ('addvec', c_void_p),
@@ -81,6 +91,9 @@ SIGNATURES = {
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_multiclass_soft_nms': [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_float, c_float,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'htd_dense_gemm': [ctypes.POINTER(HtdDenseGemm), c_void_p, c_ll, c_void_p],
+    'htd_gate_colsum': [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p,
+                        c_void_p, c_void_p],
     'htd_assign_sample': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_float,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -116,7 +129,7 @@ SIGNATURES = {
 _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
+KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
                     'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2, 'htd_multiclass_nms': 4}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 
@@ -159,6 +172,8 @@ def lib():
         L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
         L.htd_multiclass_soft_nms_workspace_bytes.restype = c_ll
         L.htd_multiclass_soft_nms_workspace_bytes.argtypes = [c_int, c_int]
+        L.htd_dense_gemm_workspace_bytes.restype = c_ll
+        L.htd_dense_gemm_workspace_bytes.argtypes = [ctypes.POINTER(HtdDenseGemm)]
         L.htd_debug_set_bwd_trace.restype = None
         L.htd_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
         L.htd_roi_align_bwd_uses_tensor_pipe.restype = c_int

@@ -1,0 +1,624 @@
+// Dense bf16 contractions of the HTD head on the 5th-generation tensor cores: the FC stacks
+// (convfc_bbox_head.py:141-148, htd_bbox_head.py:114-121,191-192,227-228) and the 3x3 regression
+// conv tower on 7x7 RoI maps (htd_bbox_head.py:75-113,186) - forward, data gradient and weight
+// gradient - which the reference leaves to cuBLAS / cuDNN.
+//
+// One persistent kernel (one CTA per SM, 192 threads) serves six problem kinds; they differ only
+// in how the TMA producer addresses the two operands and in the major-ness bits of the UMMA
+// descriptors - the pipeline is the one of csrc/pgraph_gemm.cu:
+//   warp 0     TMA producer: cp.async.bulk.tensor (2-D or 4-D boxes, 128-byte swizzle) into a
+//              4-stage shared-memory ring (16 KB A + 32 KB B per stage), mbarrier completion;
+//   warp 1     allocates the 512 TMEM columns (two accumulators), one lane issues
+//              tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = bn <= 256, K = 16) x 4 per stage,
+//              tcgen05.commit releases the stage / publishes the accumulator;
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / per-row-class bias / ReLU / ReLU
+//              gate of the backward pass, store row-major or transposed, bf16 or fp32, or fp32
+//              split-K partials - overlapped with the MMAs of the next tile.
+//
+// Kinds (D is always [M rows = TMEM lanes, N columns]):
+//   NT  D = A[M,K] . B[N,K]^T                  both K-major            FC forward
+//   NN  D = A[M,K] . B[K,N]                    B MN-major              FC data gradient
+//   TN  D = A[K,M]^T . B[K,N]                  both MN-major           FC weight gradient
+//   CONV_FPROP  D[co, pix] = sum_{tap,ci} W[co,tap,ci] . X[pix (+) tap, ci]
+//               A = weights [Cout, 9*Cin] K-major; B = activations [P,7,7,Cin] through a 4-D box
+//               (64 ch, 7, 7, 5 RoIs) whose start is shifted by the tap: the halo is the TMA
+//               unit's out-of-bounds zero fill; N tile = 5 RoIs = 245 pixels of UMMA N = 256;
+//               stored transposed -> Y [P,7,7,Cout] channels-last.
+//   CONV_DGRAD  D[ci, pix] = sum_{tap,co} W[co,tap,ci] . dY[pix (-) tap, co]
+//               A = the same weight matrix read MN-major (columns tap*Cin + ci, rows co);
+//               B = dY through the 4-D box with the mirrored shift; stored transposed -> dX.
+//   CONV_WGRAD  D[co, (tap,ci)] = sum_pix dY[pix, co] . X[pix (+) tap, ci]
+//               A = dY [P*49, Cout] MN-major, B = X through the shifted 4-D box, MN-major; one
+//               k-block = one RoI (49 k rows; rows 49..63 of the stage stay zero); split-K over RoIs.
+#include "tc05.cuh"
+
+namespace htd {
+
+constexpr int kDBM = 128, kDBK = 64, kDStages = 4;
+constexpr int kDATile = kDBM * kDBK * 2;             // 16 KiB
+constexpr int kDBTile = 256 * kDBK * 2;              // 32 KiB (bn <= 256)
+constexpr int kDStage = kDATile + kDBTile;
+constexpr int kDThreads = 192;
+constexpr int kDSmem = kDStages * kDStage + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kChunk = 64 * 128;                     // one 64-element MN chunk x 64 k rows
+constexpr int kRoisPerTile = 5, kPP = 49;
+
+struct DenseParams {
+    int kind;
+    int M, N;                     // output extents (conv fprop/dgrad: N = P * 49 pixels)
+    int kblocks, splits, kb_per_split;
+    int tiles_m, tiles_n, bn;
+    int a_mn, b_mn;
+    unsigned stage_tx;
+    int Cin;                      // conv: channels of one tap in the weight matrix columns
+    int kc_per_tap;               // conv fprop/dgrad: 64-channel chunks per tap
+    int nt_per_tap;               // conv wgrad: N tiles per tap
+    int zero_fill;                // conv wgrad: stage tails must read as zero
+    // epilogue
+    int transposed;
+    void* D;
+    int d_bf16;
+    long long ldd;
+    void* D2;                     // second output: v + row_bias[row_class[m], n]  (same dtype / ld)
+    const float* bias;            // [N]
+    const float* row_bias;        // [R, N]
+    const int* row_class;         // [M]
+    long long ld_rb;
+    int relu;
+    const __nv_bfloat16* gate;    // [M, N] (row-major) or [N, M] (transposed): v *= gate > 0
+    long long ldg;
+    float* partial;               // [splits, M, N] fp32 (splits > 1)
+};
+
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kDThreads, 1)
+    dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                      const __grid_constant__ CUtensorMap map_b, const DenseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kDStages * kDATile;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDStages * kDStage);
+    uint64_t* empty_bar = full_bar + kDStages;
+    uint64_t* tfull_bar = empty_bar + kDStages;       // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_split = p.tiles_m * p.tiles_n;
+    const int nwork = per_split * p.splits;
+    if ((int)blockIdx.x >= nwork) return;
+
+    if (p.zero_fill) {                                // uniform
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < kDStages * kDStage / 16; i += kDThreads)
+            z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();                          // generic-proxy zeros -> visible to UMMA / TMA
+    }
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_map(&map_a);
+        tc::prefetch_map(&map_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < kDStages; ++s) {
+                mbar_init(full_bar + s, 1);
+                mbar_init(empty_bar + s, 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(tfull_bar + a, 1);
+                mbar_init(tempty_bar + a, 4);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc(tmem_slot, 512);
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int sp = w / per_split, rem = w - sp * per_split;
+                const int nt = rem / p.tiles_m, mt = rem - nt * p.tiles_m;
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % kDStages;
+                    mbar_wait(empty_bar + s, ((it / kDStages) & 1u) ^ 1u);
+                    mbar_expect_tx(full_bar + s, p.stage_tx);
+                    uint8_t* sa = smem_a + s * kDATile;
+                    uint8_t* sb = smem_b + s * kDBTile;
+                    uint64_t* bar = full_bar + s;
+                    switch (p.kind) {
+                        case HTD_DENSE_NT:
+                            tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mt * kDBM);
+                            tc::tma_load_2d(&map_b, bar, sb, kb * kDBK, nt * p.bn);
+                            break;
+                        case HTD_DENSE_NN:
+                            tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mt * kDBM);
+                            for (int c = 0; c * 64 < p.bn; ++c)
+                                tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
+                            break;
+                        case HTD_DENSE_TN:
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mt * kDBM + c * 64, kb * kDBK);
+                            for (int c = 0; c * 64 < p.bn; ++c)
+                                tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
+                            break;
+                        case HTD_DENSE_CONV_FPROP: {
+                            const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
+                            tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, mt * kDBM);
+                            tc::tma_load_4d(&map_b, bar, sb, kc * 64, tap % 3 - 1, tap / 3 - 1,
+                                            nt * kRoisPerTile);
+                            break;
+                        }
+                        case HTD_DENSE_CONV_DGRAD: {
+                            const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk,
+                                                tap * p.Cin + mt * kDBM + c * 64, kc * 64);
+                            tc::tma_load_4d(&map_b, bar, sb, kc * 64, 1 - tap % 3, 1 - tap / 3,
+                                            nt * kRoisPerTile);
+                            break;
+                        }
+                        default: {   // HTD_DENSE_CONV_WGRAD: k-block = RoI kb
+                            const int tap = nt / p.nt_per_tap, nn = nt - tap * p.nt_per_tap;
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mt * kDBM + c * 64, kb * kPP);
+                            for (int c = 0; c * 64 < p.bn; ++c)
+                                tc::tma_load_4d(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64,
+                                                tap % 3 - 1, tap / 3 - 1, kb);
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc(kDBM, p.bn, p.a_mn, p.b_mn);
+            unsigned it = 0, lt = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++lt) {
+                const int sp = w / per_split;
+                const int kb0 = sp * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+                const unsigned a = lt & 1u;
+                mbar_wait(tempty_bar + a, ((lt >> 1) & 1u) ^ 1u);
+                tc::fence_after();
+                const uint32_t tmem_d = tmem_base + a * 256;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % kDStages;
+                    mbar_wait(full_bar + s, (it / kDStages) & 1u);
+                    tc::fence_after();
+                    const uint32_t sa = smem_u32(smem_a + s * kDATile);
+                    const uint32_t sb = smem_u32(smem_b + s * kDBTile);
+#pragma unroll
+                    for (int k = 0; k < kDBK / 16; ++k) {
+                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
+                                                   : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
+                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
+                                                   : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
+                        tc::umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc::commit(empty_bar + s);
+                }
+                tc::commit(tfull_bar + a);
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        unsigned lt = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++lt) {
+            const int sp = w / per_split, rem = w - sp * per_split;
+            const int nt = rem / p.tiles_m, mt = rem - nt * p.tiles_m;
+            const int kb0 = sp * p.kb_per_split;
+            const bool has_k = kb0 < p.kblocks;
+            const unsigned a = lt & 1u;
+            mbar_wait(tfull_bar + a, (lt >> 1) & 1u);
+            tc::fence_after();
+            const int m = mt * kDBM + q * 32 + lane;
+            // columns of this tile and where they go
+            int nvalid, col0;
+            if (p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD) {
+                col0 = nt * kRoisPerTile * kPP;
+                nvalid = min(kRoisPerTile * kPP, p.N - col0);
+            } else if (p.kind == HTD_DENSE_CONV_WGRAD) {
+                const int tap = nt / p.nt_per_tap, nn = nt - tap * p.nt_per_tap;
+                col0 = tap * p.Cin + nn * p.bn;
+                nvalid = min(p.bn, p.Cin - nn * p.bn);
+            } else {
+                col0 = nt * p.bn;
+                nvalid = min(p.bn, p.N - col0);
+            }
+            const bool row_ok = m < p.M && has_k;
+            const int rcls = (row_ok && p.row_class != nullptr) ? p.row_class[m] : 0;
+#pragma unroll 1
+            for (int ch = 0; ch * 32 < nvalid; ++ch) {
+                uint32_t v[32];
+                __syncwarp();
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256 + (uint32_t)(ch * 32), v);
+                if (!row_ok) continue;
+                const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
+                const int n0 = col0 + ch * 32;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.splits > 1) {                                // fp32 partial, finished later
+                    float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
+                    if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) o[j] = f[j];
+                    }
+                    continue;
+                }
+                if (p.transposed) {                                // out[(n), m]: lanes = channels
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + (size_t)n0 * p.ldd + m;
+                    const __nv_bfloat16* g = p.gate ? p.gate + (size_t)n0 * p.ldg + m : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc) {
+                            float x = f[j];
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            if (g && !(__bfloat162float(g[(size_t)j * p.ldg]) > 0.f)) x = 0.f;
+                            o[(size_t)j * p.ldd] = __float2bfloat16_rn(x);
+                        }
+                    continue;
+                }
+                // row-major: bias, second output with the per-row-class bias, relu, gate
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc) f[j] += __ldg(p.bias + n0 + j);
+                }
+                if (p.D2 != nullptr) {
+                    const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
+                    __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc) {
+                            float x = f[j] + __ldg(rb + j);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            o2[j] = __float2bfloat16_rn(x);
+                        }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.gate != nullptr) {
+                    const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
+                }
+                const size_t base = (size_t)m * p.ldd + n0;
+                if (p.d_bf16) {
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
+                    if (nc == 32 && (base & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint32_t u[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                                u[t] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                            *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* o = static_cast<float*>(p.D) + base;
+                    if (nc == 32 && (base & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) o[j] = f[j];
+                    }
+                }
+            }
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + a);
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// split-K finish: sum the fp32 partials in split order (deterministic), then the same epilogue
+// (bias, per-row-class second output, relu, gate), 4 columns per thread
+__global__ void __launch_bounds__(256) dense_finish_kernel(const DenseParams p) {
+    const long long quads = ((long long)p.N + 3) / 4;
+    const long long total = (long long)p.M * quads;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / quads), n0 = (int)(i - (long long)m * quads) * 4;
+        const int nc = min(4, p.N - n0);
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s = 0; s < p.splits; ++s) {
+            const float* src = p.partial + ((size_t)s * p.M + m) * p.N + n0;
+            for (int j = 0; j < nc; ++j) f[j] += src[j];
+        }
+        if (p.bias != nullptr)
+            for (int j = 0; j < nc; ++j) f[j] += __ldg(p.bias + n0 + j);
+        if (p.D2 != nullptr) {
+            const float* rb = p.row_bias + (size_t)p.row_class[m] * p.ld_rb + n0;
+            __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
+            for (int j = 0; j < nc; ++j) {
+                float x = f[j] + __ldg(rb + j);
+                if (p.relu) x = fmaxf(x, 0.f);
+                o2[j] = __float2bfloat16_rn(x);
+            }
+        }
+        if (p.relu)
+            for (int j = 0; j < nc; ++j) f[j] = fmaxf(f[j], 0.f);
+        if (p.gate != nullptr)
+            for (int j = 0; j < nc; ++j)
+                if (!(__bfloat162float(p.gate[(size_t)m * p.ldg + n0 + j]) > 0.f)) f[j] = 0.f;
+        const size_t base = (size_t)m * p.ldd + n0;
+        if (p.d_bf16) {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
+            for (int j = 0; j < nc; ++j) o[j] = __float2bfloat16_rn(f[j]);
+        } else {
+            float* o = static_cast<float*>(p.D) + base;
+            for (int j = 0; j < nc; ++j) o[j] = f[j];
+        }
+    }
+}
+
+// dz = dy * [y > 0] (optional) and the column sums of dz (the bias gradient), deterministic:
+// grid (column blocks of 64, row chunks) -> partial [chunks, N]; a second pass adds the chunks.
+constexpr int kCsRows = 64;
+__global__ void __launch_bounds__(256) gate_colsum_kernel(
+    const __nv_bfloat16* __restrict__ dy, long long ld_dy, const __nv_bfloat16* __restrict__ y,
+    long long ld_y, int rows, int N, __nv_bfloat16* __restrict__ dz, long long ld_dz,
+    float* __restrict__ partial) {
+    __shared__ float s_sum[4][64];
+    const int c = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    const int r0 = blockIdx.y * kCsRows;
+    float acc = 0.f;
+    if (c < N)
+        for (int r = r0 + rg; r < min(r0 + kCsRows, rows); r += 4) {
+            float v = __bfloat162float(dy[(size_t)r * ld_dy + c]);
+            if (y != nullptr && !(__bfloat162float(y[(size_t)r * ld_y + c]) > 0.f)) v = 0.f;
+            if (dz != nullptr) dz[(size_t)r * ld_dz + c] = __float2bfloat16_rn(v);
+            acc += v;
+        }
+    s_sum[rg][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (rg == 0 && c < N)
+        partial[(size_t)blockIdx.y * N + c] =
+            (s_sum[0][threadIdx.x] + s_sum[1][threadIdx.x]) + (s_sum[2][threadIdx.x] + s_sum[3][threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
+                                                           int chunks, int N, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float acc = 0.f;
+    for (int k = 0; k < chunks; ++k) acc += partial[(size_t)k * N + c];
+    out[c] = acc;
+}
+
+}  // namespace htd
+
+using namespace htd;
+
+static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParams& p, cudaStream_t st) {
+    const long long nwork = (long long)p.tiles_m * p.tiles_n * p.splits;
+    if (nwork <= 0 || p.kblocks <= 0) return HTD_OK;
+    HTD_CHECK_ARG(nwork < 2147483647LL, "htd_dense_gemm: too many tiles");
+    HTD_SMEM_OPTIN(dense_gemm_kernel, kDSmem, "htd_dense_gemm");
+    const int sms = sm_count();
+    const unsigned grid = (unsigned)(nwork < sms ? nwork : sms);
+    dense_gemm_kernel<<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
+    HTD_CHECK_LAUNCH("htd_dense_gemm");
+    if (p.splits > 1) {
+        const long long quads = (long long)p.M * ((p.N + 3) / 4);
+        const unsigned blocks = (unsigned)((quads + 255) / 256 < 8LL * sms ? (quads + 255) / 256 : 8LL * sms);
+        dense_finish_kernel<<<blocks, 256, 0, st>>>(p);
+        HTD_CHECK_LAUNCH("htd_dense_gemm(finish)");
+    }
+    return HTD_OK;
+}
+
+static int pick_splits(long long tiles, int kblocks, int want, int sms) {
+    if (want > 0) return want < kblocks ? want : (kblocks > 0 ? kblocks : 1);
+    // fill the machine: as many k slices as fit one wave, at least 4 k-blocks each
+    int s = 1;
+    while (tiles * (s * 2) <= sms && kblocks / (s * 2) >= 4) s *= 2;
+    if (tiles * s < sms && tiles * (s + 1) <= sms && kblocks / (s + 1) >= 4) {
+        // non-power-of-two refinement (e.g. 45 tiles -> 3 splits)
+        while (tiles * (s + 1) <= sms && kblocks / (s + 1) >= 4) ++s;
+    }
+    return s;
+}
+
+extern "C" {
+
+// fills the launch parameters (and, with `maps`, the tensor maps) of one problem
+static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, CUtensorMap* mb,
+                       bool maps) {
+    HTD_CHECK_ARG(g != nullptr, "htd_dense_gemm: null descriptor");
+    HTD_CHECK_ARG(g->kind >= HTD_DENSE_NT && g->kind <= HTD_DENSE_CONV_WGRAD,
+                  "htd_dense_gemm: bad kind %d", g->kind);
+    HTD_CHECK_ARG(g->d_dtype == HTD_F32 || g->d_dtype == HTD_BF16, "htd_dense_gemm: bad output dtype");
+    if (maps) {
+        HTD_CHECK_ARG(g->A && g->B && g->D, "htd_dense_gemm: null pointer");
+        HTD_CHECK_ARG((((uintptr_t)g->A | (uintptr_t)g->B | (uintptr_t)g->D) & 15) == 0,
+                      "htd_dense_gemm: operands must be 16-byte aligned");
+    }
+    const int sms = sm_count();
+    memset(&p, 0, sizeof(p));
+    p.kind = g->kind;
+    p.D = g->D;
+    p.d_bf16 = g->d_dtype == HTD_BF16;
+    p.ldd = g->ldd;
+    p.bias = g->bias;
+    p.relu = g->relu;
+    p.gate = static_cast<const __nv_bfloat16*>(g->gate);
+    p.ldg = g->ldg;
+    p.D2 = g->D2;
+    p.row_bias = g->row_bias;
+    p.row_class = g->row_class;
+    p.ld_rb = g->ld_row_bias;
+    HTD_CHECK_ARG(!g->D2 || (g->row_bias && g->row_class && g->d_dtype == HTD_BF16),
+                  "htd_dense_gemm: D2 needs row_bias, row_class and a bf16 output");
+    int rc;
+    if (g->kind <= HTD_DENSE_TN) {
+        const long long M = g->M, N = g->N, K = g->K;
+        HTD_CHECK_ARG(M > 0 && N > 0 && K > 0 && g->lda > 0 && g->ldb > 0 && g->ldd >= N,
+                      "htd_dense_gemm: bad extents M=%lld N=%lld K=%lld", M, N, K);
+        HTD_CHECK_ARG(g->lda % 8 == 0 && g->ldb % 8 == 0,
+                      "htd_dense_gemm: operand row pitches must be multiples of 8 elements");
+        p.M = (int)M;
+        p.N = (int)N;
+        p.bn = N >= 256 ? 256 : (int)((N + 15) / 16 * 16);
+        p.tiles_m = (int)((M + kDBM - 1) / kDBM);
+        p.tiles_n = (int)((N + p.bn - 1) / p.bn);
+        p.kblocks = (int)((K + kDBK - 1) / kDBK);
+        p.a_mn = g->kind == HTD_DENSE_TN;
+        p.b_mn = g->kind != HTD_DENSE_NT;
+        // K-major B: one box of bn rows; MN-major B: whole 64-column chunks (bn may end inside one)
+        p.stage_tx = (unsigned)(kDATile + (p.b_mn ? (p.bn + 63) / 64 * kChunk : p.bn * kDBK * 2));
+        if (maps) {
+            // every tile tail (rows beyond M / N, columns beyond K, k rows beyond K) is zero-filled
+            // by the TMA unit: nothing to pad on the caller's side
+            if (!p.a_mn) rc = tc::make_map_2d(ma, g->A, M, K, g->lda, kDBM, "htd_dense_gemm(A)");
+            else rc = tc::make_map_2d(ma, g->A, K, M, g->lda, kDBK, "htd_dense_gemm(A^T)");
+            if (rc) return rc;
+            if (!p.b_mn) rc = tc::make_map_2d(mb, g->B, N, K, g->ldb, p.bn, "htd_dense_gemm(B)");
+            else rc = tc::make_map_2d(mb, g->B, K, N, g->ldb, kDBK, "htd_dense_gemm(B^T)");
+            if (rc) return rc;
+        }
+    } else {
+        const long long P = g->P, Cin = g->Cin, Cout = g->Cout;
+        HTD_CHECK_ARG(P > 0 && Cin > 0 && Cout > 0 && Cin % 64 == 0 && Cout % 64 == 0,
+                      "htd_dense_gemm(conv): P=%lld Cin=%lld Cout=%lld (channels must be multiples of 64)",
+                      P, Cin, Cout);
+        HTD_CHECK_ARG(g->pooled == 7, "htd_dense_gemm(conv): 7x7 RoI maps only (pooled=%d)", g->pooled);
+        HTD_CHECK_ARG(!g->bias && !g->D2, "htd_dense_gemm(conv): no bias / second output");
+        if (g->kind == HTD_DENSE_CONV_FPROP) {
+            // A = W [Cout, 9*Cin], B = X [P,7,7,Cin] -> D^T = Y [P*49, Cout]
+            p.M = (int)Cout; p.N = (int)(P * kPP); p.bn = 256; p.Cin = (int)Cin;
+            p.kc_per_tap = (int)(Cin / 64); p.kblocks = 9 * p.kc_per_tap;
+            p.tiles_m = (int)((Cout + kDBM - 1) / kDBM);
+            p.tiles_n = (int)((P + kRoisPerTile - 1) / kRoisPerTile);
+            p.a_mn = 0; p.b_mn = 0; p.transposed = 1;
+            p.stage_tx = (unsigned)(kDATile + kRoisPerTile * kPP * 128);
+            HTD_CHECK_ARG(g->ldd >= Cout && g->d_dtype == HTD_BF16, "htd_dense_gemm(conv fprop): bad output");
+            if (maps) {
+                rc = tc::make_map_2d(ma, g->A, Cout, 9 * Cin, 9 * Cin, kDBM, "htd_dense_gemm(conv W)");
+                if (rc) return rc;
+                rc = tc::make_map_roi(mb, g->B, P, 7, Cin, kRoisPerTile, "htd_dense_gemm(conv X)");
+                if (rc) return rc;
+            }
+        } else if (g->kind == HTD_DENSE_CONV_DGRAD) {
+            // A = W [Cout rows, 9*Cin cols] read MN-major, B = dY [P,7,7,Cout] -> D^T = dX [P*49, Cin]
+            p.M = (int)Cin; p.N = (int)(P * kPP); p.bn = 256; p.Cin = (int)Cin;
+            p.kc_per_tap = (int)(Cout / 64); p.kblocks = 9 * p.kc_per_tap;
+            p.tiles_m = (int)((Cin + kDBM - 1) / kDBM);
+            p.tiles_n = (int)((P + kRoisPerTile - 1) / kRoisPerTile);
+            p.a_mn = 1; p.b_mn = 0; p.transposed = 1;
+            p.stage_tx = (unsigned)(kDATile + kRoisPerTile * kPP * 128);
+            HTD_CHECK_ARG(g->ldd >= Cin && g->d_dtype == HTD_BF16, "htd_dense_gemm(conv dgrad): bad output");
+            if (maps) {
+                rc = tc::make_map_2d(ma, g->A, Cout, 9 * Cin, 9 * Cin, kDBK, "htd_dense_gemm(conv W^T)");
+                if (rc) return rc;
+                rc = tc::make_map_roi(mb, g->B, P, 7, Cout, kRoisPerTile, "htd_dense_gemm(conv dY)");
+                if (rc) return rc;
+            }
+        } else {
+            // A = dY [P*49, Cout] MN-major, B = X [P,7,7,Cin] MN-major -> D = dW [Cout, 9*Cin]
+            p.M = (int)Cout; p.N = (int)(9 * Cin); p.Cin = (int)Cin;
+            p.bn = Cin % 256 == 0 ? 256 : (Cin % 192 == 0 ? 192 : (Cin % 128 == 0 ? 128 : 64));
+            p.nt_per_tap = (int)(Cin / p.bn);
+            p.tiles_m = (int)((Cout + kDBM - 1) / kDBM);
+            p.tiles_n = 9 * p.nt_per_tap;
+            p.kblocks = (int)P;
+            p.a_mn = 1; p.b_mn = 1; p.zero_fill = 1;
+            p.stage_tx = (unsigned)((2 + p.bn / 64) * kPP * 128);
+            HTD_CHECK_ARG(g->ldd >= 9 * Cin, "htd_dense_gemm(conv wgrad): bad output pitch");
+            HTD_CHECK_ARG(!g->gate && !g->relu, "htd_dense_gemm(conv wgrad): plain output only");
+            if (maps) {
+                rc = tc::make_map_2d(ma, g->A, P * kPP, Cout, Cout, kPP, "htd_dense_gemm(conv dY^T)");
+                if (rc) return rc;
+                rc = tc::make_map_roi(mb, g->B, P, 7, Cin, 1, "htd_dense_gemm(conv X^T)");
+                if (rc) return rc;
+            }
+        }
+    }
+    const long long tiles = (long long)p.tiles_m * p.tiles_n;
+    const bool can_split = !p.transposed;
+    p.splits = can_split ? pick_splits(tiles, p.kblocks, g->splits, sms) : 1;
+    p.kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
+    p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;      // no empty slice
+    return HTD_OK;
+}
+
+long long htd_dense_gemm_workspace_bytes(const HtdDenseGemm* g) {
+    DenseParams p;
+    if (dense_setup(g, p, nullptr, nullptr, false) != HTD_OK) return -1;
+    return p.splits > 1 ? (long long)p.splits * p.M * p.N * 4 : 0;
+}
+
+int htd_dense_gemm(const HtdDenseGemm* g, void* workspace, long long workspace_bytes,
+                   htd_stream_t stream) {
+    DenseParams p;
+    CUtensorMap ma, mb;
+    int rc = dense_setup(g, p, &ma, &mb, true);
+    if (rc) return rc;
+    if (p.splits > 1) {
+        const long long need = (long long)p.splits * p.M * p.N * 4;
+        HTD_CHECK_ARG(workspace && workspace_bytes >= need,
+                      "htd_dense_gemm: split-K needs a workspace of %lld bytes (got %lld)", need,
+                      workspace_bytes);
+        p.partial = static_cast<float*>(workspace);
+    }
+    return dense_launch(ma, mb, p, (cudaStream_t)stream);
+}
+
+int htd_gate_colsum(const void* dy, long long ld_dy, const void* y, long long ld_y, int rows, int N,
+                    void* dz, long long ld_dz, float* partial, float* out, htd_stream_t stream) {
+    HTD_CHECK_ARG(rows >= 0 && N > 0 && dy && partial && out, "htd_gate_colsum: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = (rows + kCsRows - 1) / kCsRows;
+    if (chunks > 0) {
+        gate_colsum_kernel<<<dim3((N + 63) / 64, chunks), 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(dy), ld_dy, static_cast<const __nv_bfloat16*>(y), ld_y,
+            rows, N, static_cast<__nv_bfloat16*>(dz), ld_dz, partial);
+        HTD_CHECK_LAUNCH("htd_gate_colsum");
+    }
+    colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, chunks, N, out);
+    HTD_CHECK_LAUNCH("htd_gate_colsum(final)");
+    return HTD_OK;
+}
+
+}  // extern "C"

@@ -285,6 +285,57 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
                     htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Dense bf16 contractions of the head on the tcgen05 tensor cores:
+ * the FC stacks (convfc_bbox_head.py:141-148 `shared_fcs`, htd_bbox_head.py:114-121,191-192 `fcs`,
+ * :227-228 fc_cls / fc_reg) and the 3x3 regression conv tower on the 7x7 RoI maps
+ * (htd_bbox_head.py:75-113,186), forward + data gradient + weight gradient - the work the
+ * reference hands to cuBLAS (torch.nn.Linear) and cuDNN (mmcv ConvModule -> nn.Conv2d).
+ * All operands bf16, fp32 accumulation in TMEM; D is [M, N]:
+ *   HTD_DENSE_NT  D = A[M,K] . B[N,K]^T            lda, ldb = row pitch of the [.,K] matrices
+ *   HTD_DENSE_NN  D = A[M,K] . B[K,N]              ldb = row pitch of the [K,N] matrix
+ *   HTD_DENSE_TN  D = A[K,M]^T . B[K,N]            lda, ldb = row pitches of the [K,.] matrices
+ *   HTD_DENSE_CONV_FPROP  A = W [Cout,3,3,Cin] (a channels-last conv weight), B = X [P,7,7,Cin]
+ *                         -> D = Y [P,7,7,Cout]  (stride 1, padding 1, no bias)
+ *   HTD_DENSE_CONV_DGRAD  A = W, B = dY [P,7,7,Cout] -> D = dX [P,7,7,Cin]
+ *   HTD_DENSE_CONV_WGRAD  A = dY [P,7,7,Cout], B = X [P,7,7,Cin] -> D = dW [Cout,3,3,Cin]
+ * Row pitches must be multiples of 8 elements, base pointers 16-byte aligned; nothing has to be
+ * padded (the TMA unit zero-fills every tile tail).  Epilogue (GEMM kinds; conv kinds take relu /
+ * gate only, on the channels-last output):  v = acc + bias[n];  D2[m,n] = act(v +
+ * row_bias[row_class[m], n]) (optional second output, bf16, pitch ldd - htd_bbox_head.py:161-164:
+ * the FC of `x + global_feat` shares the product with the FC of `x`);  D[m,n] = act(v) * [gate[m,n]
+ * > 0] (gate = the forward activation of the layer whose ReLU the gradient passes).
+ * splits: 0 = choose (fill the SMs), n > 0 = n k-slices; partial sums go through `workspace`
+ * (htd_dense_gemm_workspace_bytes) and are added in slice order: results are deterministic.
+ * htd_gate_colsum: dz = dy * [y > 0] (y, dz optional) and out[n] = sum_m dz[m,n] - the bias
+ * gradient of an FC layer and its ReLU backward in one pass; partial: [ceil(rows/64), N] fp32. */
+#define HTD_DENSE_NT 0
+#define HTD_DENSE_NN 1
+#define HTD_DENSE_TN 2
+#define HTD_DENSE_CONV_FPROP 3
+#define HTD_DENSE_CONV_DGRAD 4
+#define HTD_DENSE_CONV_WGRAD 5
+typedef struct HtdDenseGemm {
+    int32_t kind;
+    int32_t M, N, K;              /* GEMM kinds */
+    int32_t P, Cin, Cout, pooled; /* conv kinds: RoIs, channels, map size (7) */
+    int32_t d_dtype, relu, splits, reserved;
+    const void* A;
+    const void* B;
+    void* D;
+    void* D2;
+    const float* bias;
+    const float* row_bias;
+    const int32_t* row_class;
+    const void* gate;
+    long long lda, ldb, ldd, ldg, ld_row_bias;
+} HtdDenseGemm;
+long long htd_dense_gemm_workspace_bytes(const HtdDenseGemm* g);
+int htd_dense_gemm(const HtdDenseGemm* g, void* workspace, long long workspace_bytes,
+                   htd_stream_t stream);
+int htd_gate_colsum(const void* dy, long long ld_dy, const void* y, long long ld_y, int rows, int N,
+                    void* dz, long long ld_dz, float* partial, float* out, htd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Target / loss / decode glue, one kernel per job, no host sync.
  *
  * htd_bbox_targets: BBoxHead._get_target_single (bbox_head.py:85-118) for all sampled RoIs at

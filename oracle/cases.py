@@ -20,7 +20,7 @@ CASES = {
     'mid': dict(B=1, hw=(512, 640), K=96, P=24, scales=(8.0, 900.0), scheme='init', seed=1),
     # gate-stable weights (synth.fill_params_ 'stable'): no ReLU gate can flip under bf16 / fp32
     # rounding, so END-TO-END gradients are gated in the max-norm (2e-2 bf16) like forward values
-    'small_s': dict(B=2, hw=(320, 448), K=48, P=12, scales=(8.0, 600.0), scheme='stable', seed=0),
+    'small_s': dict(B=2, hw=(320, 448), K=64, P=24, scales=(8.0, 600.0), scheme='stable', seed=0),
     # BASELINE.json configs[1] = the benchmarked size: 2 images x 512 RoIs (128 positives),
     # 800x1333 pyramid (P2 rows of 336 px: the wide-footprint paths only occur at this size)
     'c2': dict(B=2, hw=(800, 1333), K=512, P=128, scales=(16.0, 800.0), scheme='stable', seed=0),
