@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.modules.utils import _pair
 
-from . import ops, pgraph
+from . import dense, ops, pgraph
 from .core import accuracy, as_cfg, multiclass_nms
 from .registry import HEADS, build_bbox_coder, build_loss
 
@@ -48,8 +48,20 @@ class ConvModule(nn.Module):
         # in nchw<->nhwc conversion kernels (63 launches / 0.66 ms per step in the round-1 profile)
         self.conv.to(memory_format=torch.channels_last)
 
+    own_dense = True     # class switch (diagnostics): 3x3 tower convs through csrc/dense_gemm.cu
+
+    def _conv(self, x):
+        c = self.conv
+        if ConvModule.own_dense and c.bias is None and c.kernel_size == (3, 3) and \
+                c.padding == (1, 1) and c.stride == (1, 1) and c.dilation == (1, 1) and \
+                c.groups == 1 and x.dim() == 4 and x.shape[2:] == (7, 7) and \
+                c.in_channels % 64 == 0 and c.out_channels % 64 == 0 and dense.usable(x, c.weight):
+            # implicit-GEMM 3x3 conv on the tcgen05 tensor cores (bf16; halo = TMA zero fill)
+            return dense.conv3x3(x, c.weight)
+        return c(x)
+
     def forward(self, x):
-        x = self.conv(x)
+        x = self._conv(x)
         if self.gn is not None:
             if self.with_act and x.is_cuda and (x.size(1) // self.gn.num_groups) % 8 == 0 \
                     and ConvModule.fused_gn:
@@ -64,12 +76,25 @@ def _pad8(n):
     return (-n) % 8
 
 
+def fc(m, x, relu=False):
+    """``act(m(x))`` for an nn.Linear: bf16 CUDA tensors run the package's own tcgen05 GEMMs
+    (forward with bias / ReLU in the epilogue, data and weight gradient, bias gradient fused with
+    the ReLU backward - csrc/dense_gemm.cu); anything else (the fp32 parity configuration) the
+    library call."""
+    if BBoxHead.own_dense and x.dim() == 2 and dense.usable(x, m.weight):
+        return dense.linear(x, m.weight, m.bias, relu)
+    y = m(x)
+    return F.relu(y) if relu else y
+
+
 def linear_aligned(m, x):
     """``m(x)`` for an nn.Linear.  cuBLAS has no fast bf16 kernel for an output width that is not
     a multiple of 8 elements (fc_cls: 81, fc_reg: 4 - rows of 162 / 8 bytes; it falls back to
     sm_75-era kernels, 22 us for a 0.17 GFLOP product): the weight is zero-padded to the next
     multiple of 8 rows and the result sliced.  Values are unchanged; fp32 runs the plain call."""
     n = m.out_features
+    if BBoxHead.own_dense and x.dim() == 2 and dense.usable(x, m.weight):
+        return dense.linear(x, m.weight, m.bias, False)      # any N: the TMA unit pads the tiles
     if not (x.is_cuda and x.dtype == torch.bfloat16 and n % 8 and BBoxHead.aligned_small_fc):
         return m(x)
     w = F.pad(m.weight, (0, 0, 0, _pad8(n)))
@@ -87,6 +112,9 @@ def cls_reg_outputs(head, x):
     pad = _pad8(nc + nr)
     w = torch.cat([head.fc_cls.weight, head.fc_reg.weight], 0)
     b = torch.cat([head.fc_cls.bias, head.fc_reg.bias], 0)
+    if BBoxHead.own_dense and x.dim() == 2 and dense.usable(x, w):
+        out = dense.linear(x, w, b, False)
+        return out[:, :nc], out[:, nc:nc + nr]
     if pad:
         w, b = F.pad(w, (0, 0, 0, pad)), F.pad(b, (0, pad))
     out = F.linear(x, w, b)
@@ -274,6 +302,7 @@ class BBoxHead(nn.Module):
                 and self.loss_cls.reduction == 'mean' and self.loss_bbox.reduction == 'mean'
                 and self.loss_cls.class_weight is None and self.fused_glue)
 
+    own_dense = True         # class switch (diagnostics): FC layers through csrc/dense_gemm.cu (bf16)
     fused_glue = True        # class switch (diagnostics): targets / loss / decode via csrc/rcnn_glue.cu
     aligned_small_fc = True  # class switch (diagnostics): 8-aligned fc_cls / fc_reg GEMMs in bf16
     _pos_mask_cache = {}
@@ -379,8 +408,8 @@ class ConvFCBBoxHead(BBoxHead):
 
     def forward(self, x):
         x = ops.flatten_roi_feats(x)
-        for fc in self.shared_fcs:
-            x = F.relu(fc(x))
+        for m in self.shared_fcs:
+            x = fc(m, x, relu=True)
         return cls_reg_outputs(self, x)
 
 
@@ -473,17 +502,34 @@ class HTDBBoxHead(BBoxHead):
         # fcs.0(x + g (x) 1_49) = fcs.0(x) + g W_sum^T with W_sum = sum of W over the 49 bins:
         # one [K,12544]x[12544,1024] GEMM instead of the reference's two (:164 and :192).
         fc0, fc1 = self.fcs[0], self.fcs[2]
-        pre = fc0(x_cls_flat if x_cls_flat is not None else ops.flatten_roi_feats(x_cls))
-        x_c = F.relu(fc1(F.relu(pre)))
+        x_flat = x_cls_flat if x_cls_flat is not None else ops.flatten_roi_feats(x_cls)
         x_glb = None
-        if global_feat is not None:
-            # g (x) 1_49 through fcs.0's weight: a [B, 12544] x [12544, 1024] GEMM that reads W once
-            # (summing W over the 49 bins first is a 25 MB strided reduction - 54 us in ATen)
+        if BBoxHead.own_dense and global_feat is not None and dense.usable(x_flat, fc0.weight):
+            # both FC inputs of the reference from ONE product: the epilogue of the fcs.0 GEMM
+            # writes relu(v) and relu(v + corr[image of the RoI]); fcs.2 then runs once on the
+            # 2K stacked rows
             g49 = g.to(fc0.weight.dtype).repeat_interleave(self.roi_feat_area, dim=1)
-            corr = F.linear(g49, fc0.weight)
-            x_glb = F.relu(fc1(F.relu(pre + self._img_onehot(rois, g.size(0), corr.dtype) @ corr)))
+            corr = dense.linear(g49, fc0.weight, None, False)
+            h = dense.linear_dual(x_flat, fc0.weight, fc0.bias, corr, rois[:, 0])
+            both = fc(fc1, h, relu=True)
+            K_ = x_flat.size(0)
+            x_c, x_glb = both[:K_], both[K_:]
+        else:
+            pre = fc(fc0, x_flat)
+            x_c = fc(fc1, F.relu(pre), relu=True)
+            if global_feat is not None:
+                # g (x) 1_49 through fcs.0's weight: a [B, 12544] x [12544, 1024] GEMM that reads W
+                # once (summing W over the 49 bins first is a 25 MB strided reduction)
+                g49 = g.to(fc0.weight.dtype).repeat_interleave(self.roi_feat_area, dim=1)
+                corr = F.linear(g49, fc0.weight)
+                x_glb = fc(fc1, F.relu(pre + self._img_onehot(rois, g.size(0), corr.dtype) @ corr),
+                           relu=True)
         # ---- semantic vectors and the graph (:194-219)
-        sam = torch.mm(linear_aligned(fc_cls_0, x_c).softmax(-1), prototype)
+        probs = linear_aligned(fc_cls_0, x_c).softmax(-1)
+        if BBoxHead.own_dense and dense.usable(probs, prototype):
+            sam = dense.mm(probs, prototype)
+        else:
+            sam = torch.mm(probs, prototype)
         with torch.no_grad():
             levels = ops.level_assign(rois, len(feat), self.finest_scale)
             if row_valid is not None:

@@ -501,6 +501,11 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
         set_error("%s: cuTensorMapEncodeTiled is unavailable", who);
         return HTD_ERR_CUDA;
     }
+    static thread_local bool ctx_bound = false;     // see tc05.cuh: driver call on a fresh thread
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};

@@ -139,6 +139,14 @@ inline int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64
         set_error("%s: cuTensorMapEncodeTiled is unavailable", who);
         return HTD_ERR_CUDA;
     }
+    // the driver entry point needs a current context on THIS thread; an autograd worker thread
+    // whose first CUDA call is this one has none yet (CUDA_ERROR_INVALID_CONTEXT): bind the
+    // primary context through the runtime once per thread
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                      dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

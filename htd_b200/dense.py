@@ -143,6 +143,92 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class _LinearDual(torch.autograd.Function):
+    """H [2M, N]: H[:M] = relu(x w^T + b), H[M:] = relu(x w^T + b + corr[cls[m]]) - the two FC inputs
+    of HTDBBoxHead (`fcs(x_cls)` and `fcs(x_cls + global_feat)`, htd_bbox_head.py:161-164,191-192)
+    from one product: the second output is written by the same epilogue (D2 / row_bias)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, corr, cls):
+        x2, w2 = _rows2d(x.detach()), _rows2d(w.detach())
+        M, K = x2.shape
+        N = w2.shape[0]
+        assert N % 8 == 0
+        H = torch.empty((2 * M, N), dtype=BF16, device=x.device)
+        rb = corr.detach().float().contiguous()
+        rc = cls.detach().to(torch.int32).contiguous()
+        gemm(_lib.DENSE_NT, x2, w2, H[:M], M=M, N=N, K=K, lda=x2.stride(0), ldb=w2.stride(0), ldd=N,
+             bias=b.detach().float().contiguous(), relu=True, D2=H[M:], row_bias=rb, row_class=rc,
+             name='fc_fwd')
+        ctx.save_for_backward(x2, w2, H, rc)
+        ctx.meta = (b.dtype, corr.dtype, corr.shape[0])
+        return H
+
+    @staticmethod
+    def backward(ctx, dH):
+        x2, w2, H, rc = ctx.saved_tensors
+        bdt, cdt, R = ctx.meta
+        M, K = x2.shape
+        N = w2.shape[0]
+        dH = dH if dH.dtype == BF16 else dH.to(BF16)
+        dzb = dH[M:] * (H[M:] > 0)
+        dz = (dH[:M] * (H[:M] > 0) + dzb).contiguous()
+        # d corr[r] = sum of dzb over the rows of class r: a [R, M] x [M, N] product (TN kind)
+        Rp = (R + 7) // 8 * 8
+        onehot = (rc[:, None] == torch.arange(Rp, device=rc.device, dtype=rc.dtype)[None, :]).to(BF16)
+        dcorr = torch.empty((R, N), dtype=torch.float32, device=dH.device)
+        gemm(_lib.DENSE_TN, onehot, dzb, dcorr, M=R, N=N, K=M, lda=Rp, ldb=N, ldd=N, name='fc_small')
+        _, db = gate_colsum(dz, None)
+        dx = torch.empty((M, K), dtype=BF16, device=dH.device)
+        gemm(_lib.DENSE_NN, dz, w2, dx, M=M, N=K, K=N, lda=N, ldb=w2.stride(0), ldd=K, name='fc_dgrad')
+        dw = torch.empty((N, K), dtype=BF16, device=dH.device)
+        gemm(_lib.DENSE_TN, dz, x2, dw, M=N, N=K, K=M, lda=N, ldb=x2.stride(0), ldd=K, name='fc_wgrad')
+        return dx, dw, db.to(bdt), dcorr.to(cdt), None
+
+
+def linear_dual(x, w, b, corr, cls):
+    return _LinearDual.apply(x, w, b, corr, cls)
+
+
+class _MatMul(torch.autograd.Function):
+    """c = a @ b for [M,K] x [K,N] bf16 (b read MN-major)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a2, b2 = _rows2d(a.detach()), _rows2d(b.detach())
+        M, K = a2.shape
+        N = b2.shape[1]
+        ldc = (N + 7) // 8 * 8
+        c = torch.empty((M, ldc), dtype=BF16, device=a.device)[:, :N]
+        gemm(_lib.DENSE_NN, a2, b2, c, M=M, N=N, K=K, lda=a2.stride(0), ldb=b2.stride(0), ldd=ldc,
+             name='fc_small')
+        ctx.save_for_backward(a2, b2)
+        return c
+
+    @staticmethod
+    def backward(ctx, dc):
+        a2, b2 = ctx.saved_tensors
+        M, K = a2.shape
+        N = b2.shape[1]
+        dc = _rows2d(dc if dc.dtype == BF16 else dc.to(BF16))
+        da = db = None
+        if ctx.needs_input_grad[0]:          # da = dc b^T : [M,N] x [K,N]^T
+            lda_ = (K + 7) // 8 * 8
+            da = torch.empty((M, lda_), dtype=BF16, device=dc.device)[:, :K]
+            gemm(_lib.DENSE_NT, dc, b2, da, M=M, N=K, K=N, lda=dc.stride(0), ldb=b2.stride(0), ldd=lda_,
+                 name='fc_small')
+        if ctx.needs_input_grad[1]:          # db = a^T dc
+            ldb_ = (N + 7) // 8 * 8
+            db = torch.empty((K, ldb_), dtype=BF16, device=dc.device)[:, :N]
+            gemm(_lib.DENSE_TN, a2, dc, db, M=K, N=N, K=M, lda=a2.stride(0), ldb=dc.stride(0), ldd=ldb_,
+                 name='fc_small')
+        return da, db
+
+
+def mm(a, b):
+    return _MatMul.apply(a, b)
+
+
 def linear(x, w, b=None, relu=False):
     """``act(F.linear(x, w, b))`` for bf16 CUDA tensors on the own kernels ([M,K] x [N,K])."""
     return _Linear.apply(x, w, b, bool(relu))
