@@ -556,7 +556,7 @@ class HTDBBoxHead(BBoxHead):
                 x_reg = m(x_reg)
             # last conv -> ReLU -> AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:109-113,188-189):
             # activation and pool in one pass over the largest activation of the head
-            x_reg = ops.relu_mean_pool(last.conv(x_reg))
+            x_reg = ops.relu_mean_pool(last._conv(x_reg))
         else:
             x_reg = self.convs(x_reg).mean((2, 3))
         feat_cls_new = (x_glb if x_glb is not None else x_c) + refined
