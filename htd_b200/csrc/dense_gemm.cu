@@ -7,9 +7,10 @@
 // in how the TMA producer addresses the two operands and in the major-ness bits of the UMMA
 // descriptors - the pipeline is the one of csrc/pgraph_gemm.cu:
 //   warp 0     TMA producer: cp.async.bulk.tensor (2-D or 4-D boxes, 128-byte swizzle) into a
-//              4-stage shared-memory ring (16 KB A + 32 KB B per stage), mbarrier completion;
-//   warp 1     allocates the 512 TMEM columns (two accumulators), one lane issues
-//              tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = bn <= 256, K = 16) x 4 per stage,
+//              3-stage shared-memory ring (2 x 16 KB A + 32 KB B per stage), mbarrier completion;
+//   warp 1     allocates the 512 TMEM columns (two 128 x 256 accumulators = one 256-row super tile
+//              whose halves share every B stage), one lane issues tcgen05.mma.cta_group::1.kind::f16
+//              (M = 128, N = bn <= 256, K = 16), 4 per stage and accumulator,
 //              tcgen05.commit releases the stage / publishes the accumulator;
 //   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / per-row-class bias / ReLU / ReLU
 //              gate of the backward pass, store row-major or transposed, bf16 or fp32, or fp32
@@ -34,8 +35,10 @@
 
 namespace htd {
 
-constexpr int kDBM = 128, kDBK = 64, kDStages = 4;
-constexpr int kDATile = kDBM * kDBK * 2;             // 16 KiB
+constexpr int kDBM = 128, kDBK = 64, kDStages = 3;
+constexpr int kDTileM = 2 * kDBM;                    // rows of a super tile: two accumulators
+constexpr int kDAHalf = kDBM * kDBK * 2;             // 16 KiB: one 128-row half of the A stage
+constexpr int kDATile = 2 * kDAHalf;                 // 32 KiB
 constexpr int kDBTile = 256 * kDBK * 2;              // 32 KiB (bn <= 256)
 constexpr int kDStage = kDATile + kDBTile;
 constexpr int kDThreads = 192;
@@ -43,7 +46,7 @@ constexpr int kDSmem = kDStages * kDStage + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kChunk = 64 * 128;                     // one 64-element MN chunk x 64 k rows
 // conv fprop / dgrad N tile: 4 RoIs as two halves of 2 RoIs (98 rows) whose second half starts at
 // row 104 (a multiple of 8: the 128-byte swizzle phase of a TMA destination) -> UMMA N = 208
-constexpr int kRoisPerTile = 4, kPP = 49, kHalfRows = 104, kConvBN = 208;
+constexpr int kPP = 49, kRoisPerTile = 5;
 
 struct DenseParams {
     int kind;
@@ -51,7 +54,7 @@ struct DenseParams {
     int kblocks, splits, kb_per_split;
     int tiles_m, tiles_n, bn;
     int a_mn, b_mn;
-    unsigned stage_tx;
+    unsigned a_half_tx, b_tx;     // bytes landing per stage: per 128-row half of A, for B
     int Cin;                      // conv: channels of one tap in the weight matrix columns
     int kc_per_tap;               // conv fprop/dgrad: 64-channel chunks per tap
     int nt_per_tap;               // conv wgrad: N tiles per tap
@@ -76,47 +79,30 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// One work item of a CTA: its tile, and how the B operand reaches it
+// One work item: a 256-row super tile (two 128-row accumulators that share every B stage) or, at
+// the ragged end of M, a 128-row tile.
 struct DenseWork {
     int sp, nt, mt;
-    bool store;      // false: phantom (odd tile count) - computes its partner's tile, stores nothing
-    bool share;      // B halves exchanged by multicast inside the CTA pair
+    bool two;        // rows m0 + 128 .. exist: second accumulator in use
 };
 
-// kCl = 1: one CTA per work item.  kCl = 2: clusters of two CTAs walk the tiles of a k-slice in
-// pairs (m fastest); when both tiles of a pair have the same B tile (same n-tile) each CTA fetches
-// HALF of it and multicasts it to both - the L2 -> SM operand stream, which bounds the 1-CTA
-// kernel near 45 % of the tensor peak, shrinks by a third.  Stages are released cluster-wide
-// (every tcgen05.commit arrives on both CTAs' empty barriers), so the two rings run in lockstep.
-template <int kCl>
-__device__ __forceinline__ bool dense_work(const DenseParams& p, int item, int rank, DenseWork& wk) {
+__device__ __forceinline__ bool dense_work(const DenseParams& p, int item, DenseWork& wk) {
     const int per_split = p.tiles_m * p.tiles_n;
-    if (kCl == 1) {
-        if (item >= per_split * p.splits) return false;
-        wk.sp = item / per_split;
-        const int rem = item - wk.sp * per_split;
-        wk.nt = rem / p.tiles_m;
-        wk.mt = rem - wk.nt * p.tiles_m;
-        wk.store = true;
-        wk.share = false;
-        return true;
-    }
-    const int pps = (per_split + 1) / 2;                  // pairs per k-slice
-    if (item >= pps * p.splits) return false;
-    wk.sp = item / pps;
-    const int jj = item - wk.sp * pps;
-    const int w0 = 2 * jj, w1 = 2 * jj + 1;
-    const bool two = w1 < per_split;
-    wk.share = !two || (w0 / p.tiles_m == w1 / p.tiles_m);
-    int w = rank == 0 ? w0 : w1;
-    wk.store = w < per_split;
-    if (!wk.store) w = w0;                                // phantom: mirror the partner
-    wk.nt = w / p.tiles_m;
-    wk.mt = w - wk.nt * p.tiles_m;
+    if (item >= per_split * p.splits) return false;
+    wk.sp = item / per_split;
+    const int rem = item - wk.sp * per_split;
+    wk.nt = rem / p.tiles_m;
+    wk.mt = rem - wk.nt * p.tiles_m;
+    wk.two = p.M - wk.mt * kDTileM > kDBM;
     return true;
 }
 
-template <int kCl>
+// Why 256 x 256 per CTA: the kernel is bound by the L2 -> SM operand delivery (about 35-40 B per
+// clock and SM with all SMs loading; ncu: tensor pipe 36 % busy with 128 x 256 tiles and 48 KB
+// per k-block, profiles/r02_dense_notes.md).  Two accumulators of 128 x 256 (all 512 TMEM columns)
+// that share one B stage need 64 KB per k-block for twice the flops - a third less traffic per
+// flop, the same ratio a cta_group::2 pair has.  Ragged 128-row tiles keep the double-buffered
+// accumulator (their epilogue overlaps the next tile's MMAs); a 256-row tile's epilogue does not.
 __global__ void __launch_bounds__(kDThreads, 1)
     dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b, const DenseParams p) {
@@ -127,13 +113,12 @@ __global__ void __launch_bounds__(kDThreads, 1)
     uint8_t* smem_b = smem + kDStages * kDATile;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDStages * kDStage);
     uint64_t* empty_bar = full_bar + kDStages;
-    uint64_t* tfull_bar = empty_bar + kDStages;       // [2]
+    uint64_t* tfull_bar = empty_bar + kDStages;       // [2] accumulator slots
     uint64_t* tempty_bar = tfull_bar + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = kCl > 1 ? (int)tc::cluster_ctarank() : 0;
-    const int first = (int)blockIdx.x / kCl, stride = (int)gridDim.x / kCl;   // host: grid <= items
+    const int first = (int)blockIdx.x, stride = (int)gridDim.x;
 
     if (p.zero_fill) {                                // uniform
         uint4* z = reinterpret_cast<uint4*>(smem);
@@ -149,7 +134,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
         if (lane == 0) {
             for (int s = 0; s < kDStages; ++s) {
                 mbar_init(full_bar + s, 1);
-                mbar_init(empty_bar + s, kCl);        // one tcgen05.commit per CTA of the cluster
+                mbar_init(empty_bar + s, 1);
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(tfull_bar + a, 1);
@@ -162,95 +147,83 @@ __global__ void __launch_bounds__(kDThreads, 1)
     }
     tc::fence_before();
     __syncthreads();
-    if (kCl > 1) tc::cluster_sync_all();              // peer barriers initialised / buffers zeroed
     tc::fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nb_chunks = (p.bn + 63) / 64;           // MN-major B: 64-column chunks of the tile
-    const int half_chunks = (nb_chunks + 1) / 2;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             unsigned it = 0;
             DenseWork wk;
-            for (int item = first; dense_work<kCl>(p, item, rank, wk); item += stride) {
-                const int nt = wk.nt, mt = wk.mt;
+            for (int item = first; dense_work(p, item, wk); item += stride) {
+                const int nt = wk.nt, m0 = wk.mt * kDTileM;
                 const int kb0 = wk.sp * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                // which part of B this CTA fetches, and for whom
-                const bool mc = kCl > 1 && wk.share;
-                const uint16_t mask = 3;
-                const int h0 = mc ? rank : 0, h1 = mc ? rank + 1 : 2;       // halves [h0, h1)
+                const int halves = wk.two ? 2 : 1;
+                const unsigned tx = p.b_tx + halves * p.a_half_tx;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kDStages;
                     mbar_wait(empty_bar + s, ((it / kDStages) & 1u) ^ 1u);
-                    mbar_expect_tx(full_bar + s, p.stage_tx);
-                    uint8_t* sa = smem_a + s * kDATile;
+                    mbar_expect_tx(full_bar + s, tx);
                     uint8_t* sb = smem_b + s * kDBTile;
                     uint64_t* bar = full_bar + s;
-                    // ---- A: this CTA's own rows
                     int tap = 0, kc = 0;
-                    switch (p.kind) {
-                        case HTD_DENSE_NT:
-                        case HTD_DENSE_NN:
-                            tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mt * kDBM);
-                            break;
-                        case HTD_DENSE_TN:
-                            for (int c = 0; c < 2; ++c)
-                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mt * kDBM + c * 64, kb * kDBK);
-                            break;
-                        case HTD_DENSE_CONV_FPROP:
-                            tap = kb / p.kc_per_tap; kc = kb - tap * p.kc_per_tap;
-                            tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, mt * kDBM);
-                            break;
-                        case HTD_DENSE_CONV_DGRAD:
-                            tap = kb / p.kc_per_tap; kc = kb - tap * p.kc_per_tap;
-                            for (int c = 0; c < 2; ++c)
-                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk,
-                                                tap * p.Cin + mt * kDBM + c * 64, kc * 64);
-                            break;
-                        default:   // HTD_DENSE_CONV_WGRAD: k-block = RoI kb
-                            for (int c = 0; c < 2; ++c)
-                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mt * kDBM + c * 64, kb * kPP);
-                            break;
+                    if (p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD) {
+                        tap = kb / p.kc_per_tap;
+                        kc = kb - tap * p.kc_per_tap;
                     }
-                    // ---- B: halves [h0, h1) of the tile (both halves, or one half multicast)
-                    for (int h = h0; h < h1; ++h) {
+                    // ---- A: one or two 128-row halves
+                    for (int hh = 0; hh < halves; ++hh) {
+                        uint8_t* sa = smem_a + s * kDATile + hh * kDAHalf;
+                        const int mh = m0 + hh * kDBM;
                         switch (p.kind) {
-                            case HTD_DENSE_NT: {          // K-major rows: two boxes of bn/2 rows
-                                uint8_t* d = sb + h * (p.bn / 2) * 128;
-                                const int r = nt * p.bn + h * (p.bn / 2);
-                                if (mc) tc::tma_load_2d_mc(&map_b, bar, d, kb * kDBK, r, mask);
-                                else tc::tma_load_2d(&map_b, bar, d, kb * kDBK, r);
-                                break;
-                            }
+                            case HTD_DENSE_NT:
                             case HTD_DENSE_NN:
+                                tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mh);
+                                break;
                             case HTD_DENSE_TN:
-                                for (int c = h * half_chunks; c < min((h + 1) * half_chunks, nb_chunks); ++c) {
-                                    if (mc) tc::tma_load_2d_mc(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK, mask);
-                                    else tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
-                                }
+                                for (int c = 0; c < 2; ++c)
+                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kDBK);
                                 break;
                             case HTD_DENSE_CONV_FPROP:
-                            case HTD_DENSE_CONV_DGRAD: {  // 2 RoIs (98 rows) per half, halves 104 rows apart
-                                uint8_t* d = sb + h * kHalfRows * 128;
-                                const int dx = p.kind == HTD_DENSE_CONV_FPROP ? tap % 3 - 1 : 1 - tap % 3;
-                                const int dy = p.kind == HTD_DENSE_CONV_FPROP ? tap / 3 - 1 : 1 - tap / 3;
-                                const int roi = nt * kRoisPerTile + h * (kRoisPerTile / 2);
-                                if (mc) tc::tma_load_4d_mc(&map_b, bar, d, kc * 64, dx, dy, roi, mask);
-                                else tc::tma_load_4d(&map_b, bar, d, kc * 64, dx, dy, roi);
+                                tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, mh);
                                 break;
-                            }
-                            default: {                    // conv wgrad: X chunks through the shifted box
-                                const int tp = nt / p.nt_per_tap, nn = nt - tp * p.nt_per_tap;
-                                for (int c = h * half_chunks; c < min((h + 1) * half_chunks, nb_chunks); ++c) {
-                                    if (mc) tc::tma_load_4d_mc(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64,
-                                                               tp % 3 - 1, tp / 3 - 1, kb, mask);
-                                    else tc::tma_load_4d(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64,
-                                                         tp % 3 - 1, tp / 3 - 1, kb);
-                                }
+                            case HTD_DENSE_CONV_DGRAD:
+                                for (int c = 0; c < 2; ++c)
+                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
+                                                    kc * 64);
                                 break;
-                            }
+                            default:   // HTD_DENSE_CONV_WGRAD: k-block = RoI kb
+                                for (int c = 0; c < 2; ++c)
+                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kPP);
+                                break;
+                        }
+                    }
+                    // ---- B: one tile, shared by both halves
+                    switch (p.kind) {
+                        case HTD_DENSE_NT:
+                            tc::tma_load_2d(&map_b, bar, sb, kb * kDBK, nt * p.bn);
+                            break;
+                        case HTD_DENSE_NN:
+                        case HTD_DENSE_TN:
+                            for (int c = 0; c < nb_chunks; ++c)
+                                tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
+                            break;
+                        case HTD_DENSE_CONV_FPROP:
+                            tc::tma_load_4d(&map_b, bar, sb, kc * 64, tap % 3 - 1, tap / 3 - 1,
+                                            nt * kRoisPerTile);
+                            break;
+                        case HTD_DENSE_CONV_DGRAD:
+                            tc::tma_load_4d(&map_b, bar, sb, kc * 64, 1 - tap % 3, 1 - tap / 3,
+                                            nt * kRoisPerTile);
+                            break;
+                        default: {
+                            const int tp = nt / p.nt_per_tap, nn = nt - tp * p.nt_per_tap;
+                            for (int c = 0; c < nb_chunks; ++c)
+                                tc::tma_load_4d(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64, tp % 3 - 1,
+                                                tp / 3 - 1, kb);
+                            break;
                         }
                     }
                 }
@@ -260,15 +233,17 @@ __global__ void __launch_bounds__(kDThreads, 1)
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc(kDBM, p.bn, p.a_mn, p.b_mn);
-            unsigned it = 0, lt = 0;
+            unsigned it = 0, uses[2] = {0u, 0u}, nsingle = 0;
             DenseWork wk;
-            for (int item = first; dense_work<kCl>(p, item, rank, wk); item += stride, ++lt) {
+            for (int item = first; dense_work(p, item, wk); item += stride) {
                 const int kb0 = wk.sp * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                const unsigned a = lt & 1u;
-                mbar_wait(tempty_bar + a, ((lt >> 1) & 1u) ^ 1u);
+                // accumulator slots: a 256-row tile takes both, a 128-row tile alternates
+                const unsigned s0 = wk.two ? 0u : (nsingle++ & 1u);
+                mbar_wait(tempty_bar + s0, (uses[s0] & 1u) ^ 1u);
+                if (wk.two) mbar_wait(tempty_bar + 1, (uses[1] & 1u) ^ 1u);
                 tc::fence_after();
-                const uint32_t tmem_d = tmem_base + a * 256;
+                const uint32_t acc0 = tmem_base + s0 * 256, acc1 = tmem_base + 256;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kDStages;
                     mbar_wait(full_bar + s, (it / kDStages) & 1u);
@@ -277,37 +252,43 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     const uint32_t sb = smem_u32(smem_b + s * kDBTile);
 #pragma unroll
                     for (int k = 0; k < kDBK / 16; ++k) {
-                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
-                                                   : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
                         const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
                                                    : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
-                        tc::umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
+                                                   : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
+                        const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+                        tc::umma_bf16(acc0, ad, bd, idesc, acc);
+                        if (wk.two) {
+                            const uint64_t ad1 = p.a_mn ? tc::desc_mnmajor(sa + kDAHalf + k * 2048, kChunk)
+                                                        : tc::desc_kmajor(sa + kDAHalf) + (uint64_t)(2 * k);
+                            tc::umma_bf16(acc1, ad1, bd, idesc, acc);
+                        }
                     }
-                    if (kCl > 1) tc::commit_mc(empty_bar + s, 3);   // frees the stage in both CTAs
-                    else tc::commit(empty_bar + s);
+                    tc::commit(empty_bar + s);
                 }
-                tc::commit(tfull_bar + a);
+                tc::commit(tfull_bar + s0);
+                ++uses[s0];
+                if (wk.two) {
+                    tc::commit(tfull_bar + 1);
+                    ++uses[1];
+                }
             }
         }
     } else {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        unsigned lt = 0;
+        unsigned uses[2] = {0u, 0u}, nsingle = 0;
         DenseWork wk;
-        for (int item = first; dense_work<kCl>(p, item, rank, wk); item += stride, ++lt) {
-            const int sp = wk.sp, nt = wk.nt, mt = wk.mt;
+        for (int item = first; dense_work(p, item, wk); item += stride) {
+            const int sp = wk.sp, nt = wk.nt;
             const int kb0 = sp * p.kb_per_split;
             const bool has_k = kb0 < p.kblocks;
-            const unsigned a = lt & 1u;
-            mbar_wait(tfull_bar + a, (lt >> 1) & 1u);
-            tc::fence_after();
-            const int m = mt * kDBM + q * 32 + lane;
             const bool conv_t = p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD;
             // columns of this tile and where they go
             int nvalid, col0;
             if (conv_t) {
                 col0 = nt * kRoisPerTile * kPP;                  // first pixel of the tile
-                nvalid = kHalfRows + 2 * kPP;                    // accumulator columns in use (202)
+                nvalid = min(kRoisPerTile * kPP, p.N - col0);
             } else if (p.kind == HTD_DENSE_CONV_WGRAD) {
                 const int tap = nt / p.nt_per_tap, nn = nt - tap * p.nt_per_tap;
                 col0 = tap * p.Cin + nn * p.bn;
@@ -316,119 +297,119 @@ __global__ void __launch_bounds__(kDThreads, 1)
                 col0 = nt * p.bn;
                 nvalid = min(p.bn, p.N - col0);
             }
-            const bool row_ok = m < p.M && has_k && wk.store;
-            const int rcls = (row_ok && p.row_class != nullptr) ? p.row_class[m] : 0;
+            const unsigned s0 = wk.two ? 0u : (nsingle++ & 1u);
+            for (int hh = 0; hh < (wk.two ? 2 : 1); ++hh) {
+                const unsigned slot = hh == 0 ? s0 : 1u;
+                mbar_wait(tfull_bar + slot, uses[slot] & 1u);
+                ++uses[slot];
+                tc::fence_after();
+                const int m = wk.mt * kDTileM + hh * kDBM + q * 32 + lane;
+                const bool row_ok = m < p.M && has_k;
+                const int rcls = (row_ok && p.row_class != nullptr) ? p.row_class[m] : 0;
 #pragma unroll 1
-            for (int ch = 0; ch * 32 < nvalid && wk.store; ++ch) {
-                uint32_t v[32];
-                __syncwarp();
-                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256 + (uint32_t)(ch * 32), v);
-                if (!row_ok) continue;
-                const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
-                const int n0 = col0 + ch * 32;
-                float f[32];
+                for (int ch = 0; ch * 32 < nvalid; ++ch) {
+                    uint32_t v[32];
+                    __syncwarp();
+                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
+                    if (!row_ok) continue;
+                    const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
+                    const int n0 = col0 + ch * 32;
+                    float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (conv_t) {
-                    // out[pixel, m]: lanes = channels.  Accumulator column c holds pixel c of the
-                    // tile for c < 98 (RoIs 0, 1) and pixel c - 6 for 104 <= c < 202 (RoIs 2, 3)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int c = ch * 32 + j;
-                        const int px = c < 2 * kPP ? c : c - (kHalfRows - 2 * kPP);
-                        const bool ok = (c < 2 * kPP || (c >= kHalfRows && c < kHalfRows + 2 * kPP)) &&
-                                        col0 + px < p.N;
-                        if (ok) {
-                            float x = f[j];
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            const size_t o = (size_t)(col0 + px);
-                            if (p.gate && !(__bfloat162float(p.gate[o * p.ldg + m]) > 0.f)) x = 0.f;
-                            static_cast<__nv_bfloat16*>(p.D)[o * p.ldd + m] = __float2bfloat16_rn(x);
-                        }
-                    }
-                    continue;
-                }
-                if (p.splits > 1) {                                // fp32 partial, finished later
-                    float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
-                    if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (conv_t) {                                      // out[pixel, m]: lanes = channels
+                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + (size_t)n0 * p.ldd + m;
+                        const __nv_bfloat16* g = p.gate ? p.gate + (size_t)n0 * p.ldg + m : nullptr;
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < nc) o[j] = f[j];
-                    }
-                    continue;
-                }
-                // row-major: bias, second output with the per-row-class bias, relu, gate
-                if (p.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nc) f[j] += __ldg(p.bias + n0 + j);
-                }
-                if (p.D2 != nullptr) {
-                    const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
-                    __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nc) {
-                            float x = f[j] + __ldg(rb + j);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            o2[j] = __float2bfloat16_rn(x);
-                        }
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                if (p.gate != nullptr) {
-                    const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
-                }
-                const size_t base = (size_t)m * p.ldd + n0;
-                if (p.d_bf16) {
-                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
-                    if (nc == 32 && (base & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint32_t u[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                                u[t] = *reinterpret_cast<uint32_t*>(&h);
+                            if (j < nc) {
+                                float x = f[j];
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                if (g && !(__bfloat162float(g[(size_t)j * p.ldg]) > 0.f)) x = 0.f;
+                                o[(size_t)j * p.ldd] = __float2bfloat16_rn(x);
                             }
-                            *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
+                        continue;
+                    }
+                    if (p.splits > 1) {                                // fp32 partial, finished later
+                        float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
+                        if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nc) o[j] = f[j];
+                        }
+                        continue;
+                    }
+                    // row-major: bias, second output with the per-row-class bias, relu, gate
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) f[j] += __ldg(p.bias + n0 + j);
+                    }
+                    if (p.D2 != nullptr) {
+                        const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
+                        __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) {
+                                float x = f[j] + __ldg(rb + j);
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                o2[j] = __float2bfloat16_rn(x);
+                            }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    if (p.gate != nullptr) {
+                        const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
+                    }
+                    const size_t base = (size_t)m * p.ldd + n0;
+                    if (p.d_bf16) {
+                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
+                        if (nc == 32 && (base & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                uint32_t u[4];
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                                    u[t] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                                *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
                         }
                     } else {
+                        float* o = static_cast<float*>(p.D) + base;
+                        if (nc == 32 && (base & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
-                    }
-                } else {
-                    float* o = static_cast<float*>(p.D) + base;
-                    if (nc == 32 && (base & 3) == 0) {
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) o[j] = f[j];
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nc) o[j] = f[j];
+                        }
                     }
                 }
+                tc::fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + slot);
             }
-            tc::fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + a);
         }
     }
     tc::fence_before();
     __syncthreads();
-    // no CTA may leave while its peer can still multicast into it or arrive on its barriers
-    if (kCl > 1) tc::cluster_sync_all();
     if (warp == 1) {
         tc::fence_after();
         tc::tmem_dealloc(tmem_base, 512);
@@ -513,47 +494,15 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 
 using namespace htd;
 
-static int g_dense_cluster = -1;      // -1: from the environment (HTD_DENSE_CLUSTER=1|2), default 2
-
 static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParams& p, cudaStream_t st) {
     const long long per_split = (long long)p.tiles_m * p.tiles_n;
     if (per_split <= 0 || p.kblocks <= 0) return HTD_OK;
-    HTD_CHECK_ARG(per_split * p.splits < 2147483647LL, "htd_dense_gemm: too many tiles");
-    if (g_dense_cluster < 0) {
-        const char* ev = getenv("HTD_DENSE_CLUSTER");
-        g_dense_cluster = (ev && ev[0] == '1') ? 1 : 2;
-    }
+    const long long items = per_split * p.splits;
+    HTD_CHECK_ARG(items < 2147483647LL, "htd_dense_gemm: too many tiles");
+    HTD_SMEM_OPTIN(dense_gemm_kernel, kDSmem, "htd_dense_gemm");
     const int sms = sm_count();
-    // CTA pairs (B halves multicast) whenever there are at least two tiles per k-slice
-    const bool pair = g_dense_cluster == 2 && per_split >= 2;
-    if (!pair) {
-        HTD_SMEM_OPTIN(dense_gemm_kernel<1>, kDSmem, "htd_dense_gemm");
-        const long long items = per_split * p.splits;
-        const unsigned grid = (unsigned)(items < sms ? items : sms);
-        dense_gemm_kernel<1><<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
-    } else {
-        HTD_SMEM_OPTIN(dense_gemm_kernel<2>, kDSmem, "htd_dense_gemm");
-        const long long items = (per_split + 1) / 2 * p.splits;
-        const long long clusters = items < sms / 2 ? items : sms / 2;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)(2 * clusters));
-        cfg.blockDim = dim3(kDThreads);
-        cfg.dynamicSmemBytes = kDSmem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2;
-        attr.val.clusterDim.y = 1;
-        attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, dense_gemm_kernel<2>, ma, mb, p);
-        if (e != cudaSuccess) {
-            set_error("htd_dense_gemm: cluster launch failed: %s", cudaGetErrorString(e));
-            return HTD_ERR_CUDA;
-        }
-    }
+    const unsigned grid = (unsigned)(items < sms ? items : sms);
+    dense_gemm_kernel<<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
     HTD_CHECK_LAUNCH("htd_dense_gemm");
     if (p.splits > 1) {
         const long long quads = (long long)p.M * ((p.N + 3) / 4);
@@ -615,20 +564,21 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
         p.M = (int)M;
         p.N = (int)N;
         p.bn = N >= 256 ? 256 : (int)((N + 15) / 16 * 16);
-        p.tiles_m = (int)((M + kDBM - 1) / kDBM);
+        p.tiles_m = (int)((M + kDTileM - 1) / kDTileM);
         p.tiles_n = (int)((N + p.bn - 1) / p.bn);
         p.kblocks = (int)((K + kDBK - 1) / kDBK);
         p.a_mn = g->kind == HTD_DENSE_TN;
         p.b_mn = g->kind != HTD_DENSE_NT;
         // K-major B: one box of bn rows; MN-major B: whole 64-column chunks (bn may end inside one)
-        p.stage_tx = (unsigned)(kDATile + (p.b_mn ? (p.bn + 63) / 64 * kChunk : p.bn * kDBK * 2));
+        p.a_half_tx = (unsigned)kDAHalf;
+        p.b_tx = (unsigned)(p.b_mn ? (p.bn + 63) / 64 * kChunk : p.bn * kDBK * 2);
         if (maps) {
             // every tile tail (rows beyond M / N, columns beyond K, k rows beyond K) is zero-filled
             // by the TMA unit: nothing to pad on the caller's side
             if (!p.a_mn) rc = tc::make_map_2d(ma, g->A, M, K, g->lda, kDBM, "htd_dense_gemm(A)");
             else rc = tc::make_map_2d(ma, g->A, K, M, g->lda, kDBK, "htd_dense_gemm(A^T)");
             if (rc) return rc;
-            if (!p.b_mn) rc = tc::make_map_2d(mb, g->B, N, K, g->ldb, p.bn / 2, "htd_dense_gemm(B)");
+            if (!p.b_mn) rc = tc::make_map_2d(mb, g->B, N, K, g->ldb, p.bn, "htd_dense_gemm(B)");
             else rc = tc::make_map_2d(mb, g->B, K, N, g->ldb, kDBK, "htd_dense_gemm(B^T)");
             if (rc) return rc;
         }
@@ -641,32 +591,32 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
         HTD_CHECK_ARG(!g->bias && !g->D2, "htd_dense_gemm(conv): no bias / second output");
         if (g->kind == HTD_DENSE_CONV_FPROP) {
             // A = W [Cout, 9*Cin], B = X [P,7,7,Cin] -> D^T = Y [P*49, Cout]
-            p.M = (int)Cout; p.N = (int)(P * kPP); p.bn = kConvBN; p.Cin = (int)Cin;
+            p.M = (int)Cout; p.N = (int)(P * kPP); p.bn = 256; p.Cin = (int)Cin;
             p.kc_per_tap = (int)(Cin / 64); p.kblocks = 9 * p.kc_per_tap;
-            p.tiles_m = (int)((Cout + kDBM - 1) / kDBM);
+            p.tiles_m = (int)((Cout + kDTileM - 1) / kDTileM);
             p.tiles_n = (int)((P + kRoisPerTile - 1) / kRoisPerTile);
             p.a_mn = 0; p.b_mn = 0; p.transposed = 1;
-            p.stage_tx = (unsigned)(kDATile + kRoisPerTile * kPP * 128);   // 2 boxes of 2 RoIs
+            p.a_half_tx = (unsigned)kDAHalf; p.b_tx = (unsigned)(kRoisPerTile * kPP * 128);
             HTD_CHECK_ARG(g->ldd >= Cout && g->d_dtype == HTD_BF16, "htd_dense_gemm(conv fprop): bad output");
             if (maps) {
                 rc = tc::make_map_2d(ma, g->A, Cout, 9 * Cin, 9 * Cin, kDBM, "htd_dense_gemm(conv W)");
                 if (rc) return rc;
-                rc = tc::make_map_roi(mb, g->B, P, 7, Cin, kRoisPerTile / 2, "htd_dense_gemm(conv X)");
+                rc = tc::make_map_roi(mb, g->B, P, 7, Cin, kRoisPerTile, "htd_dense_gemm(conv X)");
                 if (rc) return rc;
             }
         } else if (g->kind == HTD_DENSE_CONV_DGRAD) {
             // A = W [Cout rows, 9*Cin cols] read MN-major, B = dY [P,7,7,Cout] -> D^T = dX [P*49, Cin]
-            p.M = (int)Cin; p.N = (int)(P * kPP); p.bn = kConvBN; p.Cin = (int)Cin;
+            p.M = (int)Cin; p.N = (int)(P * kPP); p.bn = 256; p.Cin = (int)Cin;
             p.kc_per_tap = (int)(Cout / 64); p.kblocks = 9 * p.kc_per_tap;
-            p.tiles_m = (int)((Cin + kDBM - 1) / kDBM);
+            p.tiles_m = (int)((Cin + kDTileM - 1) / kDTileM);
             p.tiles_n = (int)((P + kRoisPerTile - 1) / kRoisPerTile);
             p.a_mn = 1; p.b_mn = 0; p.transposed = 1;
-            p.stage_tx = (unsigned)(kDATile + kRoisPerTile * kPP * 128);   // 2 boxes of 2 RoIs
+            p.a_half_tx = (unsigned)kDAHalf; p.b_tx = (unsigned)(kRoisPerTile * kPP * 128);
             HTD_CHECK_ARG(g->ldd >= Cin && g->d_dtype == HTD_BF16, "htd_dense_gemm(conv dgrad): bad output");
             if (maps) {
                 rc = tc::make_map_2d(ma, g->A, Cout, 9 * Cin, 9 * Cin, kDBK, "htd_dense_gemm(conv W^T)");
                 if (rc) return rc;
-                rc = tc::make_map_roi(mb, g->B, P, 7, Cout, kRoisPerTile / 2, "htd_dense_gemm(conv dY)");
+                rc = tc::make_map_roi(mb, g->B, P, 7, Cout, kRoisPerTile, "htd_dense_gemm(conv dY)");
                 if (rc) return rc;
             }
         } else {
@@ -674,11 +624,11 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             p.M = (int)Cout; p.N = (int)(9 * Cin); p.Cin = (int)Cin;
             p.bn = Cin % 256 == 0 ? 256 : (Cin % 192 == 0 ? 192 : (Cin % 128 == 0 ? 128 : 64));
             p.nt_per_tap = (int)(Cin / p.bn);
-            p.tiles_m = (int)((Cout + kDBM - 1) / kDBM);
+            p.tiles_m = (int)((Cout + kDTileM - 1) / kDTileM);
             p.tiles_n = 9 * p.nt_per_tap;
             p.kblocks = (int)P;
             p.a_mn = 1; p.b_mn = 1; p.zero_fill = 1;
-            p.stage_tx = (unsigned)((2 + p.bn / 64) * kPP * 128);
+            p.a_half_tx = (unsigned)(2 * kPP * 128); p.b_tx = (unsigned)(p.bn / 64 * kPP * 128);
             HTD_CHECK_ARG(g->ldd >= 9 * Cin, "htd_dense_gemm(conv wgrad): bad output pitch");
             HTD_CHECK_ARG(!g->gate && !g->relu, "htd_dense_gemm(conv wgrad): plain output only");
             if (maps) {
