@@ -7,10 +7,9 @@
 // in how the TMA producer addresses the two operands and in the major-ness bits of the UMMA
 // descriptors - the pipeline is the one of csrc/pgraph_gemm.cu:
 //   warp 0     TMA producer: cp.async.bulk.tensor (2-D or 4-D boxes, 128-byte swizzle) into a
-//              3-stage shared-memory ring (2 x 16 KB A + 32 KB B per stage), mbarrier completion;
-//   warp 1     allocates the 512 TMEM columns (two 128 x 256 accumulators = one 256-row super tile
-//              whose halves share every B stage), one lane issues tcgen05.mma.cta_group::1.kind::f16
-//              (M = 128, N = bn <= 256, K = 16), 4 per stage and accumulator,
+//              4-stage shared-memory ring (16 KB A + 32 KB B per stage), mbarrier completion;
+//   warp 1     allocates the 512 TMEM columns (two accumulators), one lane issues
+//              tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = bn <= 256, K = 16) x 4 per stage,
 //              tcgen05.commit releases the stage / publishes the accumulator;
 //   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, bias / per-row-class bias / ReLU / ReLU
 //              gate of the backward pass, store row-major or transposed, bf16 or fp32, or fp32
@@ -35,26 +34,14 @@
 
 namespace htd {
 
-// kDSuper = 1: 256-row super tiles (two accumulators sharing each B stage, 3 stages of 64 KB);
-// kDSuper = 0: 128-row tiles, 4 stages of 48 KB, double-buffered accumulator.  Measured (round 2,
-// profiles/r02_dense_notes.md): the super tile does NOT pay - the kernel is bound by the shared-
-// memory port (TMA fill + UMMA operand reads of an SS-mode MMA), and both accumulators re-read B.
-#ifndef HTD_DENSE_SUPER
-#define HTD_DENSE_SUPER 0
-#endif
-constexpr int kDSuper = HTD_DENSE_SUPER;
-constexpr int kDBM = 128, kDBK = 64, kDStages = kDSuper ? 3 : 4;
-constexpr int kDTileM = (kDSuper ? 2 : 1) * kDBM;    // rows of a work item
-constexpr int kDAHalf = kDBM * kDBK * 2;             // 16 KiB: one 128-row half of the A stage
-constexpr int kDATile = (kDSuper ? 2 : 1) * kDAHalf;
+constexpr int kDBM = 128, kDBK = 64, kDStages = 4;
+constexpr int kDATile = kDBM * kDBK * 2;             // 16 KiB
 constexpr int kDBTile = 256 * kDBK * 2;              // 32 KiB (bn <= 256)
 constexpr int kDStage = kDATile + kDBTile;
 constexpr int kDThreads = 192;
 constexpr int kDSmem = kDStages * kDStage + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kChunk = 64 * 128;                     // one 64-element MN chunk x 64 k rows
-// conv fprop / dgrad N tile: 4 RoIs as two halves of 2 RoIs (98 rows) whose second half starts at
-// row 104 (a multiple of 8: the 128-byte swizzle phase of a TMA destination) -> UMMA N = 208
-constexpr int kPP = 49, kRoisPerTile = 5;
+constexpr int kRoisPerTile = 5, kPP = 49;
 
 struct DenseParams {
     int kind;
@@ -62,7 +49,7 @@ struct DenseParams {
     int kblocks, splits, kb_per_split;
     int tiles_m, tiles_n, bn;
     int a_mn, b_mn;
-    unsigned a_half_tx, b_tx;     // bytes landing per stage: per 128-row half of A, for B
+    unsigned stage_tx;
     int Cin;                      // conv: channels of one tap in the weight matrix columns
     int kc_per_tap;               // conv fprop/dgrad: 64-channel chunks per tap
     int nt_per_tap;               // conv wgrad: N tiles per tap
@@ -87,30 +74,6 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// One work item: a 256-row super tile (two 128-row accumulators that share every B stage) or, at
-// the ragged end of M, a 128-row tile.
-struct DenseWork {
-    int sp, nt, mt;
-    bool two;        // rows m0 + 128 .. exist: second accumulator in use
-};
-
-__device__ __forceinline__ bool dense_work(const DenseParams& p, int item, DenseWork& wk) {
-    const int per_split = p.tiles_m * p.tiles_n;
-    if (item >= per_split * p.splits) return false;
-    wk.sp = item / per_split;
-    const int rem = item - wk.sp * per_split;
-    wk.nt = rem / p.tiles_m;
-    wk.mt = rem - wk.nt * p.tiles_m;
-    wk.two = kDSuper && p.M - wk.mt * kDTileM > kDBM;
-    return true;
-}
-
-// Why 256 x 256 per CTA: the kernel is bound by the L2 -> SM operand delivery (about 35-40 B per
-// clock and SM with all SMs loading; ncu: tensor pipe 36 % busy with 128 x 256 tiles and 48 KB
-// per k-block, profiles/r02_dense_notes.md).  Two accumulators of 128 x 256 (all 512 TMEM columns)
-// that share one B stage need 64 KB per k-block for twice the flops - a third less traffic per
-// flop, the same ratio a cta_group::2 pair has.  Ragged 128-row tiles keep the double-buffered
-// accumulator (their epilogue overlaps the next tile's MMAs); a 256-row tile's epilogue does not.
 __global__ void __launch_bounds__(kDThreads, 1)
     dense_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                       const __grid_constant__ CUtensorMap map_b, const DenseParams p) {
@@ -121,12 +84,14 @@ __global__ void __launch_bounds__(kDThreads, 1)
     uint8_t* smem_b = smem + kDStages * kDATile;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDStages * kDStage);
     uint64_t* empty_bar = full_bar + kDStages;
-    uint64_t* tfull_bar = empty_bar + kDStages;       // [2] accumulator slots
+    uint64_t* tfull_bar = empty_bar + kDStages;       // [2]
     uint64_t* tempty_bar = tfull_bar + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int first = (int)blockIdx.x, stride = (int)gridDim.x;
+    const int per_split = p.tiles_m * p.tiles_n;
+    const int nwork = per_split * p.splits;
+    if ((int)blockIdx.x >= nwork) return;
 
     if (p.zero_fill) {                                // uniform
         uint4* z = reinterpret_cast<uint4*>(smem);
@@ -157,80 +122,62 @@ __global__ void __launch_bounds__(kDThreads, 1)
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nb_chunks = (p.bn + 63) / 64;           // MN-major B: 64-column chunks of the tile
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             unsigned it = 0;
-            DenseWork wk;
-            for (int item = first; dense_work(p, item, wk); item += stride) {
-                const int nt = wk.nt, m0 = wk.mt * kDTileM;
-                const int kb0 = wk.sp * p.kb_per_split;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int sp = w / per_split, rem = w - sp * per_split;
+                const int nt = rem / p.tiles_m, mt = rem - nt * p.tiles_m;
+                const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                const int halves = wk.two ? 2 : 1;
-                const unsigned tx = p.b_tx + halves * p.a_half_tx;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kDStages;
                     mbar_wait(empty_bar + s, ((it / kDStages) & 1u) ^ 1u);
-                    mbar_expect_tx(full_bar + s, tx);
+                    mbar_expect_tx(full_bar + s, p.stage_tx);
+                    uint8_t* sa = smem_a + s * kDATile;
                     uint8_t* sb = smem_b + s * kDBTile;
                     uint64_t* bar = full_bar + s;
-                    int tap = 0, kc = 0;
-                    if (p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD) {
-                        tap = kb / p.kc_per_tap;
-                        kc = kb - tap * p.kc_per_tap;
-                    }
-                    // ---- A: one or two 128-row halves
-                    for (int hh = 0; hh < halves; ++hh) {
-                        uint8_t* sa = smem_a + s * kDATile + hh * kDAHalf;
-                        const int mh = m0 + hh * kDBM;
-                        switch (p.kind) {
-                            case HTD_DENSE_NT:
-                            case HTD_DENSE_NN:
-                                tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mh);
-                                break;
-                            case HTD_DENSE_TN:
-                                for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kDBK);
-                                break;
-                            case HTD_DENSE_CONV_FPROP:
-                                tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, mh);
-                                break;
-                            case HTD_DENSE_CONV_DGRAD:
-                                for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
-                                                    kc * 64);
-                                break;
-                            default:   // HTD_DENSE_CONV_WGRAD: k-block = RoI kb
-                                for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kPP);
-                                break;
-                        }
-                    }
-                    // ---- B: one tile, shared by both halves
                     switch (p.kind) {
                         case HTD_DENSE_NT:
+                            tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mt * kDBM);
                             tc::tma_load_2d(&map_b, bar, sb, kb * kDBK, nt * p.bn);
                             break;
                         case HTD_DENSE_NN:
-                        case HTD_DENSE_TN:
-                            for (int c = 0; c < nb_chunks; ++c)
+                            tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mt * kDBM);
+                            for (int c = 0; c * 64 < p.bn; ++c)
                                 tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
                             break;
-                        case HTD_DENSE_CONV_FPROP:
+                        case HTD_DENSE_TN:
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mt * kDBM + c * 64, kb * kDBK);
+                            for (int c = 0; c * 64 < p.bn; ++c)
+                                tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
+                            break;
+                        case HTD_DENSE_CONV_FPROP: {
+                            const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
+                            tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, mt * kDBM);
                             tc::tma_load_4d(&map_b, bar, sb, kc * 64, tap % 3 - 1, tap / 3 - 1,
                                             nt * kRoisPerTile);
                             break;
-                        case HTD_DENSE_CONV_DGRAD:
+                        }
+                        case HTD_DENSE_CONV_DGRAD: {
+                            const int tap = kb / p.kc_per_tap, kc = kb - tap * p.kc_per_tap;
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk,
+                                                tap * p.Cin + mt * kDBM + c * 64, kc * 64);
                             tc::tma_load_4d(&map_b, bar, sb, kc * 64, 1 - tap % 3, 1 - tap / 3,
                                             nt * kRoisPerTile);
                             break;
-                        default: {
-                            const int tp = nt / p.nt_per_tap, nn = nt - tp * p.nt_per_tap;
-                            for (int c = 0; c < nb_chunks; ++c)
-                                tc::tma_load_4d(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64, tp % 3 - 1,
-                                                tp / 3 - 1, kb);
+                        }
+                        default: {   // HTD_DENSE_CONV_WGRAD: k-block = RoI kb
+                            const int tap = nt / p.nt_per_tap, nn = nt - tap * p.nt_per_tap;
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mt * kDBM + c * 64, kb * kPP);
+                            for (int c = 0; c * 64 < p.bn; ++c)
+                                tc::tma_load_4d(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64,
+                                                tap % 3 - 1, tap / 3 - 1, kb);
                             break;
                         }
                     }
@@ -241,17 +188,15 @@ __global__ void __launch_bounds__(kDThreads, 1)
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = tc::make_idesc(kDBM, p.bn, p.a_mn, p.b_mn);
-            unsigned it = 0, uses[2] = {0u, 0u}, nsingle = 0;
-            DenseWork wk;
-            for (int item = first; dense_work(p, item, wk); item += stride) {
-                const int kb0 = wk.sp * p.kb_per_split;
+            unsigned it = 0, lt = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++lt) {
+                const int sp = w / per_split;
+                const int kb0 = sp * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                // accumulator slots: a 256-row tile takes both, a 128-row tile alternates
-                const unsigned s0 = wk.two ? 0u : (nsingle++ & 1u);
-                mbar_wait(tempty_bar + s0, (uses[s0] & 1u) ^ 1u);
-                if (wk.two) mbar_wait(tempty_bar + 1, (uses[1] & 1u) ^ 1u);
+                const unsigned a = lt & 1u;
+                mbar_wait(tempty_bar + a, ((lt >> 1) & 1u) ^ 1u);
                 tc::fence_after();
-                const uint32_t acc0 = tmem_base + s0 * 256, acc1 = tmem_base + 256;
+                const uint32_t tmem_d = tmem_base + a * 256;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int s = it % kDStages;
                     mbar_wait(full_bar + s, (it / kDStages) & 1u);
@@ -260,42 +205,34 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     const uint32_t sb = smem_u32(smem_b + s * kDBTile);
 #pragma unroll
                     for (int k = 0; k < kDBK / 16; ++k) {
-                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
-                                                   : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
                         const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
                                                    : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
-                        const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-                        tc::umma_bf16(acc0, ad, bd, idesc, acc);
-                        if (wk.two) {
-                            const uint64_t ad1 = p.a_mn ? tc::desc_mnmajor(sa + kDAHalf + k * 2048, kChunk)
-                                                        : tc::desc_kmajor(sa + kDAHalf) + (uint64_t)(2 * k);
-                            tc::umma_bf16(acc1, ad1, bd, idesc, acc);
-                        }
+                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
+                                                   : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
+                        tc::umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     tc::commit(empty_bar + s);
                 }
-                tc::commit(tfull_bar + s0);
-                ++uses[s0];
-                if (wk.two) {
-                    tc::commit(tfull_bar + 1);
-                    ++uses[1];
-                }
+                tc::commit(tfull_bar + a);
             }
         }
     } else {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        unsigned uses[2] = {0u, 0u}, nsingle = 0;
-        DenseWork wk;
-        for (int item = first; dense_work(p, item, wk); item += stride) {
-            const int sp = wk.sp, nt = wk.nt;
+        unsigned lt = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++lt) {
+            const int sp = w / per_split, rem = w - sp * per_split;
+            const int nt = rem / p.tiles_m, mt = rem - nt * p.tiles_m;
             const int kb0 = sp * p.kb_per_split;
             const bool has_k = kb0 < p.kblocks;
-            const bool conv_t = p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD;
+            const unsigned a = lt & 1u;
+            mbar_wait(tfull_bar + a, (lt >> 1) & 1u);
+            tc::fence_after();
+            const int m = mt * kDBM + q * 32 + lane;
             // columns of this tile and where they go
             int nvalid, col0;
-            if (conv_t) {
-                col0 = nt * kRoisPerTile * kPP;                  // first pixel of the tile
+            if (p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD) {
+                col0 = nt * kRoisPerTile * kPP;
                 nvalid = min(kRoisPerTile * kPP, p.N - col0);
             } else if (p.kind == HTD_DENSE_CONV_WGRAD) {
                 const int tap = nt / p.nt_per_tap, nn = nt - tap * p.nt_per_tap;
@@ -305,115 +242,107 @@ __global__ void __launch_bounds__(kDThreads, 1)
                 col0 = nt * p.bn;
                 nvalid = min(p.bn, p.N - col0);
             }
-            const unsigned s0 = wk.two ? 0u : (nsingle++ & 1u);
-            for (int hh = 0; hh < (wk.two ? 2 : 1); ++hh) {
-                const unsigned slot = hh == 0 ? s0 : 1u;
-                mbar_wait(tfull_bar + slot, uses[slot] & 1u);
-                ++uses[slot];
-                tc::fence_after();
-                const int m = wk.mt * kDTileM + hh * kDBM + q * 32 + lane;
-                const bool row_ok = m < p.M && has_k;
-                const int rcls = (row_ok && p.row_class != nullptr) ? p.row_class[m] : 0;
+            const bool row_ok = m < p.M && has_k;
+            const int rcls = (row_ok && p.row_class != nullptr) ? p.row_class[m] : 0;
 #pragma unroll 1
-                for (int ch = 0; ch * 32 < nvalid; ++ch) {
-                    uint32_t v[32];
-                    __syncwarp();
-                    tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
-                    if (!row_ok) continue;
-                    const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
-                    const int n0 = col0 + ch * 32;
-                    float f[32];
+            for (int ch = 0; ch * 32 < nvalid; ++ch) {
+                uint32_t v[32];
+                __syncwarp();
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256 + (uint32_t)(ch * 32), v);
+                if (!row_ok) continue;
+                const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
+                const int n0 = col0 + ch * 32;
+                float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (conv_t) {                                      // out[pixel, m]: lanes = channels
-                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + (size_t)n0 * p.ldd + m;
-                        const __nv_bfloat16* g = p.gate ? p.gate + (size_t)n0 * p.ldg + m : nullptr;
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.splits > 1) {                                // fp32 partial, finished later
+                    float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
+                    if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < nc) {
-                                float x = f[j];
-                                if (p.relu) x = fmaxf(x, 0.f);
-                                if (g && !(__bfloat162float(g[(size_t)j * p.ldg]) > 0.f)) x = 0.f;
-                                o[(size_t)j * p.ldd] = __float2bfloat16_rn(x);
-                            }
-                        continue;
+                            if (j < nc) o[j] = f[j];
                     }
-                    if (p.splits > 1) {                                // fp32 partial, finished later
-                        float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
-                        if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
+                    continue;
+                }
+                if (p.transposed) {                                // out[(n), m]: lanes = channels
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + (size_t)n0 * p.ldd + m;
+                    const __nv_bfloat16* g = p.gate ? p.gate + (size_t)n0 * p.ldg + m : nullptr;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) o[j] = f[j];
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc) {
+                            float x = f[j];
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            if (g && !(__bfloat162float(g[(size_t)j * p.ldg]) > 0.f)) x = 0.f;
+                            o[(size_t)j * p.ldd] = __float2bfloat16_rn(x);
                         }
-                        continue;
-                    }
-                    // row-major: bias, second output with the per-row-class bias, relu, gate
-                    if (p.bias != nullptr) {
+                    continue;
+                }
+                // row-major: bias, second output with the per-row-class bias, relu, gate
+                if (p.bias != nullptr) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) f[j] += __ldg(p.bias + n0 + j);
-                    }
-                    if (p.D2 != nullptr) {
-                        const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
-                        __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc) f[j] += __ldg(p.bias + n0 + j);
+                }
+                if (p.D2 != nullptr) {
+                    const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
+                    __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) {
-                                float x = f[j] + __ldg(rb + j);
-                                if (p.relu) x = fmaxf(x, 0.f);
-                                o2[j] = __float2bfloat16_rn(x);
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc) {
+                            float x = f[j] + __ldg(rb + j);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            o2[j] = __float2bfloat16_rn(x);
+                        }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.gate != nullptr) {
+                    const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
+                }
+                const size_t base = (size_t)m * p.ldd + n0;
+                if (p.d_bf16) {
+                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
+                    if (nc == 32 && (base & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint32_t u[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                                u[t] = *reinterpret_cast<uint32_t*>(&h);
                             }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (p.gate != nullptr) {
-                        const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
-                    }
-                    const size_t base = (size_t)m * p.ldd + n0;
-                    if (p.d_bf16) {
-                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
-                        if (nc == 32 && (base & 7) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint32_t u[4];
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                                    u[t] = *reinterpret_cast<uint32_t*>(&h);
-                                }
-                                *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
+                            *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
                         }
                     } else {
-                        float* o = static_cast<float*>(p.D) + base;
-                        if (nc == 32 && (base & 3) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* o = static_cast<float*>(p.D) + base;
+                    if (nc == 32 && (base & 3) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) o[j] = f[j];
-                        }
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nc) o[j] = f[j];
                     }
                 }
-                tc::fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar + slot);
             }
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + a);
         }
     }
     tc::fence_before();
@@ -503,13 +432,12 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 using namespace htd;
 
 static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParams& p, cudaStream_t st) {
-    const long long per_split = (long long)p.tiles_m * p.tiles_n;
-    if (per_split <= 0 || p.kblocks <= 0) return HTD_OK;
-    const long long items = per_split * p.splits;
-    HTD_CHECK_ARG(items < 2147483647LL, "htd_dense_gemm: too many tiles");
+    const long long nwork = (long long)p.tiles_m * p.tiles_n * p.splits;
+    if (nwork <= 0 || p.kblocks <= 0) return HTD_OK;
+    HTD_CHECK_ARG(nwork < 2147483647LL, "htd_dense_gemm: too many tiles");
     HTD_SMEM_OPTIN(dense_gemm_kernel, kDSmem, "htd_dense_gemm");
     const int sms = sm_count();
-    const unsigned grid = (unsigned)(items < sms ? items : sms);
+    const unsigned grid = (unsigned)(nwork < sms ? nwork : sms);
     dense_gemm_kernel<<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
     HTD_CHECK_LAUNCH("htd_dense_gemm");
     if (p.splits > 1) {
@@ -523,13 +451,14 @@ static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParam
 
 static int pick_splits(long long tiles, int kblocks, int want, int sms) {
     if (want > 0) return want < kblocks ? want : (kblocks > 0 ? kblocks : 1);
-    // Split K only where it pays for the extra launch of the finishing pass: a long K loop
-    // (>= 32 k-blocks) on a grid that would leave more than half of the SMs idle.  Then as many
-    // slices as fit one wave, at least 8 k-blocks each.
-    if (kblocks < 32 || tiles * 2 > sms) return 1;
-    int s = (int)(sms / tiles);
-    while (s > 1 && kblocks / s < 8) --s;
-    return s < 1 ? 1 : s;
+    // fill the machine: as many k slices as fit one wave, at least 4 k-blocks each
+    int s = 1;
+    while (tiles * (s * 2) <= sms && kblocks / (s * 2) >= 4) s *= 2;
+    if (tiles * s < sms && tiles * (s + 1) <= sms && kblocks / (s + 1) >= 4) {
+        // non-power-of-two refinement (e.g. 45 tiles -> 3 splits)
+        while (tiles * (s + 1) <= sms && kblocks / (s + 1) >= 4) ++s;
+    }
+    return s;
 }
 
 extern "C" {
@@ -572,14 +501,13 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
         p.M = (int)M;
         p.N = (int)N;
         p.bn = N >= 256 ? 256 : (int)((N + 15) / 16 * 16);
-        p.tiles_m = (int)((M + kDTileM - 1) / kDTileM);
+        p.tiles_m = (int)((M + kDBM - 1) / kDBM);
         p.tiles_n = (int)((N + p.bn - 1) / p.bn);
         p.kblocks = (int)((K + kDBK - 1) / kDBK);
         p.a_mn = g->kind == HTD_DENSE_TN;
         p.b_mn = g->kind != HTD_DENSE_NT;
         // K-major B: one box of bn rows; MN-major B: whole 64-column chunks (bn may end inside one)
-        p.a_half_tx = (unsigned)kDAHalf;
-        p.b_tx = (unsigned)(p.b_mn ? (p.bn + 63) / 64 * kChunk : p.bn * kDBK * 2);
+        p.stage_tx = (unsigned)(kDATile + (p.b_mn ? (p.bn + 63) / 64 * kChunk : p.bn * kDBK * 2));
         if (maps) {
             // every tile tail (rows beyond M / N, columns beyond K, k rows beyond K) is zero-filled
             // by the TMA unit: nothing to pad on the caller's side
@@ -601,10 +529,10 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             // A = W [Cout, 9*Cin], B = X [P,7,7,Cin] -> D^T = Y [P*49, Cout]
             p.M = (int)Cout; p.N = (int)(P * kPP); p.bn = 256; p.Cin = (int)Cin;
             p.kc_per_tap = (int)(Cin / 64); p.kblocks = 9 * p.kc_per_tap;
-            p.tiles_m = (int)((Cout + kDTileM - 1) / kDTileM);
+            p.tiles_m = (int)((Cout + kDBM - 1) / kDBM);
             p.tiles_n = (int)((P + kRoisPerTile - 1) / kRoisPerTile);
             p.a_mn = 0; p.b_mn = 0; p.transposed = 1;
-            p.a_half_tx = (unsigned)kDAHalf; p.b_tx = (unsigned)(kRoisPerTile * kPP * 128);
+            p.stage_tx = (unsigned)(kDATile + kRoisPerTile * kPP * 128);
             HTD_CHECK_ARG(g->ldd >= Cout && g->d_dtype == HTD_BF16, "htd_dense_gemm(conv fprop): bad output");
             if (maps) {
                 rc = tc::make_map_2d(ma, g->A, Cout, 9 * Cin, 9 * Cin, kDBM, "htd_dense_gemm(conv W)");
@@ -616,10 +544,10 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             // A = W [Cout rows, 9*Cin cols] read MN-major, B = dY [P,7,7,Cout] -> D^T = dX [P*49, Cin]
             p.M = (int)Cin; p.N = (int)(P * kPP); p.bn = 256; p.Cin = (int)Cin;
             p.kc_per_tap = (int)(Cout / 64); p.kblocks = 9 * p.kc_per_tap;
-            p.tiles_m = (int)((Cin + kDTileM - 1) / kDTileM);
+            p.tiles_m = (int)((Cin + kDBM - 1) / kDBM);
             p.tiles_n = (int)((P + kRoisPerTile - 1) / kRoisPerTile);
             p.a_mn = 1; p.b_mn = 0; p.transposed = 1;
-            p.a_half_tx = (unsigned)kDAHalf; p.b_tx = (unsigned)(kRoisPerTile * kPP * 128);
+            p.stage_tx = (unsigned)(kDATile + kRoisPerTile * kPP * 128);
             HTD_CHECK_ARG(g->ldd >= Cin && g->d_dtype == HTD_BF16, "htd_dense_gemm(conv dgrad): bad output");
             if (maps) {
                 rc = tc::make_map_2d(ma, g->A, Cout, 9 * Cin, 9 * Cin, kDBK, "htd_dense_gemm(conv W^T)");
@@ -632,11 +560,11 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             p.M = (int)Cout; p.N = (int)(9 * Cin); p.Cin = (int)Cin;
             p.bn = Cin % 256 == 0 ? 256 : (Cin % 192 == 0 ? 192 : (Cin % 128 == 0 ? 128 : 64));
             p.nt_per_tap = (int)(Cin / p.bn);
-            p.tiles_m = (int)((Cout + kDTileM - 1) / kDTileM);
+            p.tiles_m = (int)((Cout + kDBM - 1) / kDBM);
             p.tiles_n = 9 * p.nt_per_tap;
             p.kblocks = (int)P;
             p.a_mn = 1; p.b_mn = 1; p.zero_fill = 1;
-            p.a_half_tx = (unsigned)(2 * kPP * 128); p.b_tx = (unsigned)(p.bn / 64 * kPP * 128);
+            p.stage_tx = (unsigned)((2 + p.bn / 64) * kPP * 128);
             HTD_CHECK_ARG(g->ldd >= 9 * Cin, "htd_dense_gemm(conv wgrad): bad output pitch");
             HTD_CHECK_ARG(!g->gate && !g->relu, "htd_dense_gemm(conv wgrad): plain output only");
             if (maps) {
