@@ -30,7 +30,8 @@
 //               B = dY through the 4-D box with the mirrored shift; stored transposed -> dX.
 //   CONV_WGRAD  D[co, (tap,ci)] = sum_pix dY[pix, co] . X[pix (+) tap, ci]
 //               A = dY [P*49, Cout] MN-major, B = X through the shifted 4-D box, MN-major; one
-//               k-block = one RoI (49 k rows; rows 49..63 of the stage stay zero); split-K over RoIs.
+//               k-block = two RoIs (98 k rows; rows 98..111 of the 112-row stage stay zero); split-K
+//               over RoIs.
 #include "tc05.cuh"
 
 namespace htd {
@@ -50,7 +51,15 @@ constexpr int kDATile = (kDSuper ? 2 : 1) * kDAHalf;
 constexpr int kDBTile = 256 * kDBK * 2;              // 32 KiB (bn <= 256)
 constexpr int kDStage = kDATile + kDBTile;
 constexpr int kDThreads = 192;
-constexpr int kDSmem = kDStages * kDStage + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kDMaxStages = 4;
+// conv wgrad stages hold 2 RoIs = 98 k rows padded to 112 (7 K=16 steps): chunks of 14 KB
+constexpr int kWgRois = 2, kWgRows = 112, kWgChunk = kWgRows * 128;
+constexpr int kWgStage = (2 + 4) * kWgChunk;         // A: 2 chunks, B: up to 4 chunks (bn <= 256)
+// ring: 4 x 48 KB for the GEMM / fprop / dgrad kinds, 3 x 70 KB (bn = 192) or 2 x 84 KB (bn = 256)
+// for conv wgrad
+constexpr int kDRingBytes = 3 * 5 * kWgChunk > kDStages * kDStage ? 3 * 5 * kWgChunk : kDStages * kDStage;
+static_assert(2 * kWgStage <= kDRingBytes && kDRingBytes + 1280 <= 232448, "shared-memory ring");
+constexpr int kDSmem = kDRingBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kChunk = 64 * 128;                     // one 64-element MN chunk x 64 k rows
 // conv fprop / dgrad N tile: 4 RoIs as two halves of 2 RoIs (98 rows) whose second half starts at
 // row 104 (a multiple of 8: the 128-byte swizzle phase of a TMA destination) -> UMMA N = 208
@@ -63,6 +72,9 @@ struct DenseParams {
     int tiles_m, tiles_n, bn;
     int a_mn, b_mn;
     unsigned a_half_tx, b_tx;     // bytes landing per stage: per 128-row half of A, for B
+    int nstages, a_bytes, stage_bytes;   // ring geometry: stages, bytes of the A part, of a stage
+    int chunk_bytes, ksteps;      // MN-major chunk pitch (k rows * 128 B), K=16 steps per stage
+    int rois_per_kb;              // conv wgrad: RoIs (49 k rows each) per k-block
     int Cin;                      // conv: channels of one tap in the weight matrix columns
     int kc_per_tap;               // conv fprop/dgrad: 64-channel chunks per tap
     int nt_per_tap;               // conv wgrad: N tiles per tap
@@ -117,11 +129,11 @@ __global__ void __launch_bounds__(kDThreads, 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kDStages * kDATile;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDStages * kDStage);
-    uint64_t* empty_bar = full_bar + kDStages;
-    uint64_t* tfull_bar = empty_bar + kDStages;       // [2] accumulator slots
+    // stage s = [A part | B part] at smem + s * stage_bytes (sizes are multiples of 1024 B)
+    const int nst = p.nstages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDRingBytes);
+    uint64_t* empty_bar = full_bar + kDMaxStages;
+    uint64_t* tfull_bar = empty_bar + kDMaxStages;    // [2] accumulator slots
     uint64_t* tempty_bar = tfull_bar + 2;             // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -130,7 +142,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
 
     if (p.zero_fill) {                                // uniform
         uint4* z = reinterpret_cast<uint4*>(smem);
-        for (int i = threadIdx.x; i < kDStages * kDStage / 16; i += kDThreads)
+        for (int i = threadIdx.x; i < kDRingBytes / 16; i += kDThreads)
             z[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();                          // generic-proxy zeros -> visible to UMMA / TMA
     }
@@ -140,7 +152,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < kDStages; ++s) {
+            for (int s = 0; s < kDMaxStages; ++s) {
                 mbar_init(full_bar + s, 1);
                 mbar_init(empty_bar + s, 1);
             }
@@ -171,10 +183,11 @@ __global__ void __launch_bounds__(kDThreads, 1)
                 const int halves = wk.two ? 2 : 1;
                 const unsigned tx = p.b_tx + halves * p.a_half_tx;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % kDStages;
-                    mbar_wait(empty_bar + s, ((it / kDStages) & 1u) ^ 1u);
+                    const int s = it % nst;
+                    mbar_wait(empty_bar + s, ((it / nst) & 1u) ^ 1u);
                     mbar_expect_tx(full_bar + s, tx);
-                    uint8_t* sb = smem_b + s * kDBTile;
+                    uint8_t* stage = smem + s * p.stage_bytes;
+                    uint8_t* sb = stage + p.a_bytes;
                     uint64_t* bar = full_bar + s;
                     int tap = 0, kc = 0;
                     if (p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD) {
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     }
                     // ---- A: one or two 128-row halves
                     for (int hh = 0; hh < halves; ++hh) {
-                        uint8_t* sa = smem_a + s * kDATile + hh * kDAHalf;
+                        uint8_t* sa = stage + hh * kDAHalf;
                         const int mh = m0 + hh * kDBM;
                         switch (p.kind) {
                             case HTD_DENSE_NT:
@@ -202,9 +215,10 @@ __global__ void __launch_bounds__(kDThreads, 1)
                                     tc::tma_load_2d(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
                                                     kc * 64);
                                 break;
-                            default:   // HTD_DENSE_CONV_WGRAD: k-block = RoI kb
+                            default:   // HTD_DENSE_CONV_WGRAD: k-block = rois_per_kb RoIs
                                 for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kPP);
+                                    tc::tma_load_2d(&map_a, bar, sa + c * p.chunk_bytes, mh + c * 64,
+                                                    kb * p.rois_per_kb * kPP);
                                 break;
                         }
                     }
@@ -229,8 +243,8 @@ __global__ void __launch_bounds__(kDThreads, 1)
                         default: {
                             const int tp = nt / p.nt_per_tap, nn = nt - tp * p.nt_per_tap;
                             for (int c = 0; c < nb_chunks; ++c)
-                                tc::tma_load_4d(&map_b, bar, sb + c * kChunk, nn * p.bn + c * 64, tp % 3 - 1,
-                                                tp / 3 - 1, kb);
+                                tc::tma_load_4d(&map_b, bar, sb + c * p.chunk_bytes, nn * p.bn + c * 64,
+                                                tp % 3 - 1, tp / 3 - 1, kb * p.rois_per_kb);
                             break;
                         }
                     }
@@ -252,22 +266,23 @@ __global__ void __launch_bounds__(kDThreads, 1)
                 if (wk.two) mbar_wait(tempty_bar + 1, (uses[1] & 1u) ^ 1u);
                 tc::fence_after();
                 const uint32_t acc0 = tmem_base + s0 * 256, acc1 = tmem_base + 256;
+                const uint32_t chunk = (uint32_t)p.chunk_bytes;
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % kDStages;
-                    mbar_wait(full_bar + s, (it / kDStages) & 1u);
+                    const int s = it % nst;
+                    mbar_wait(full_bar + s, (it / nst) & 1u);
                     tc::fence_after();
-                    const uint32_t sa = smem_u32(smem_a + s * kDATile);
-                    const uint32_t sb = smem_u32(smem_b + s * kDBTile);
-#pragma unroll
-                    for (int k = 0; k < kDBK / 16; ++k) {
-                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
+                    const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
+                    const uint32_t sb = sa + (uint32_t)p.a_bytes;
+#pragma unroll 1
+                    for (int k = 0; k < p.ksteps; ++k) {
+                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, chunk)
                                                    : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
-                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
+                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, chunk)
                                                    : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
                         const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
                         tc::umma_bf16(acc0, ad, bd, idesc, acc);
                         if (wk.two) {
-                            const uint64_t ad1 = p.a_mn ? tc::desc_mnmajor(sa + kDAHalf + k * 2048, kChunk)
+                            const uint64_t ad1 = p.a_mn ? tc::desc_mnmajor(sa + kDAHalf + k * 2048, chunk)
                                                         : tc::desc_kmajor(sa + kDAHalf) + (uint64_t)(2 * k);
                             tc::umma_bf16(acc1, ad1, bd, idesc, acc);
                         }
@@ -549,6 +564,8 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
     const int sms = sm_count();
     memset(&p, 0, sizeof(p));
     p.kind = g->kind;
+    p.nstages = kDStages; p.a_bytes = kDATile; p.stage_bytes = kDStage;
+    p.chunk_bytes = kChunk; p.ksteps = kDBK / 16; p.rois_per_kb = 1;
     p.D = g->D;
     p.d_bf16 = g->d_dtype == HTD_BF16;
     p.ldd = g->ldd;
@@ -634,15 +651,23 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             p.nt_per_tap = (int)(Cin / p.bn);
             p.tiles_m = (int)((Cout + kDTileM - 1) / kDTileM);
             p.tiles_n = 9 * p.nt_per_tap;
-            p.kblocks = (int)P;
+            // k-block = 2 RoIs = 98 k rows in stages of 112 rows (7 K=16 steps; rows 98..111 stay zero)
+            p.rois_per_kb = kWgRois;
+            p.kblocks = (int)((P + kWgRois - 1) / kWgRois);
             p.a_mn = 1; p.b_mn = 1; p.zero_fill = 1;
-            p.a_half_tx = (unsigned)(2 * kPP * 128); p.b_tx = (unsigned)(p.bn / 64 * kPP * 128);
+            p.chunk_bytes = kWgChunk; p.ksteps = kWgRows / 16;
+            p.a_bytes = 2 * kWgChunk;
+            p.stage_bytes = (2 + p.bn / 64) * kWgChunk;
+            p.nstages = kDRingBytes / p.stage_bytes < kDMaxStages ? kDRingBytes / p.stage_bytes : kDMaxStages;
+            p.a_half_tx = (unsigned)(2 * kWgRois * kPP * 128);
+            p.b_tx = (unsigned)(p.bn / 64 * kWgRois * kPP * 128);
+            static_assert(!kDSuper, "conv wgrad stage geometry assumes 128-row tiles");
             HTD_CHECK_ARG(g->ldd >= 9 * Cin, "htd_dense_gemm(conv wgrad): bad output pitch");
             HTD_CHECK_ARG(!g->gate && !g->relu, "htd_dense_gemm(conv wgrad): plain output only");
             if (maps) {
-                rc = tc::make_map_2d(ma, g->A, P * kPP, Cout, Cout, kPP, "htd_dense_gemm(conv dY^T)");
+                rc = tc::make_map_2d(ma, g->A, P * kPP, Cout, Cout, kWgRois * kPP, "htd_dense_gemm(conv dY^T)");
                 if (rc) return rc;
-                rc = tc::make_map_roi(mb, g->B, P, 7, Cin, 1, "htd_dense_gemm(conv X^T)");
+                rc = tc::make_map_roi(mb, g->B, P, 7, Cin, kWgRois, "htd_dense_gemm(conv X^T)");
                 if (rc) return rc;
             }
         }
