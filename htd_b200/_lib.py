@@ -25,7 +25,7 @@ class HtdGemmGroup(ctypes.Structure):
 
 class HtdDenseGemm(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ('kind', 'M', 'N', 'K', 'P', 'Cin', 'Cout', 'pooled',
-                                               'd_dtype', 'relu', 'splits', 'reserved')] + \
+                                               'd_dtype', 'relu', 'splits', 'bias_dtype')] + \
                [(n, c_void_p) for n in ('A', 'B', 'D', 'D2', 'bias', 'row_bias', 'row_class', 'gate')] + \
                [(n, ctypes.c_longlong) for n in ('lda', 'ldb', 'ldd', 'ldg', 'ld_row_bias')]
 
@@ -93,7 +93,11 @@ SIGNATURES = {
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_dense_gemm': [ctypes.POINTER(HtdDenseGemm), c_void_p, c_ll, c_void_p],
     'htd_gate_colsum': [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_ll, c_void_p,
-                        c_void_p, c_void_p],
+                        c_void_p, c_int, c_void_p],
+    'htd_dual_gate': [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                      c_void_p, c_int, c_void_p],
+    'htd_add3': [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                 c_void_p, c_void_p],
     'htd_assign_sample': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_float,
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -129,7 +133,7 @@ SIGNATURES = {
 _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
+KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_dual_gate': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
                     'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2, 'htd_multiclass_nms': 4}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 

@@ -239,15 +239,14 @@ class BBoxHead(nn.Module):
         else:
             cache[key] = cache.pop(key)         # most recently used last
         boxes = torch.cat([t for r in sampling_results for t in (r.pos_bboxes, r.neg_bboxes)], 0)
-        K = boxes.size(0)
-        gtb = boxes.new_zeros((K, 4), dtype=torch.float32)
-        gtl = torch.zeros(K, dtype=torch.long, device=dev)
-        off = 0
-        for r, (p, n) in zip(sampling_results, sizes):
-            if p:
-                gtb[off:off + p] = r.pos_gt_bboxes
-                gtl[off:off + p] = r.pos_gt_labels
-            off += p + n
+        # gt of the positives in the sampled-RoI order; the rows of the negatives are never read
+        # (is_pos == 0), so a cached zero block fills them: one cat per tensor instead of a fill and
+        # a slice copy per image
+        zb, zl = BBoxHead._zero_rows(max(n for _, n in sizes), dev)
+        gtb = torch.cat([t for r, (p, n) in zip(sampling_results, sizes)
+                         for t in (r.pos_gt_bboxes.float(), zb[:n])], 0)
+        gtl = torch.cat([t for r, (p, n) in zip(sampling_results, sizes)
+                         for t in (r.pos_gt_labels.long(), zl[:n])], 0)
         pw = cfg.get('pos_weight', -1) if cfg is not None else -1
         return ops.bbox_targets(boxes, gtb, gtl, is_pos, self.num_classes, pw, self.bbox_coder.means,
                                 self.bbox_coder.stds)
@@ -307,6 +306,16 @@ class BBoxHead(nn.Module):
     aligned_small_fc = True  # class switch (diagnostics): 8-aligned fc_cls / fc_reg GEMMs in bf16
     _pos_mask_cache = {}
     _pos_mask_cache_max = 16
+    _zero_cache = {}
+
+    @staticmethod
+    def _zero_rows(n, dev):
+        z = BBoxHead._zero_cache.get(str(dev))
+        if z is None or z[0].size(0) < n:
+            m = max(n, 2048)
+            z = BBoxHead._zero_cache[str(dev)] = (torch.zeros((m, 4), dtype=torch.float32, device=dev),
+                                                  torch.zeros(m, dtype=torch.long, device=dev))
+        return z
 
     # ---- decoding (bbox_head.py:188-335) ------------------------------------------------------
     def get_bboxes(self, rois, cls_score, bbox_pred, img_shape, scale_factor, rescale=False,
@@ -543,12 +552,18 @@ class HTDBBoxHead(BBoxHead):
         # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool (:161-189).  It is
         # independent of the cls branch above; it comes second so that a BA extraction running on a
         # side stream (``enhanced_feat`` given as a callable that joins it) overlaps all of the above
-        if global_feat is not None:
-            x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
         if callable(enhanced_feat):
             enhanced_feat = enhanced_feat()
-        x_reg = x_reg + self.alpha * enhanced_feat
-        x_reg = x_reg.contiguous(memory_format=torch.channels_last)
+        if BBoxHead.own_dense and dense.usable(x_reg, enhanced_feat) and x_reg.size(1) % 8 == 0 and \
+                (g is None or g.dtype == x_reg.dtype):
+            # x_reg + global_feat[image] + alpha * BA in ONE pass (csrc/dense_gemm.cu add3_kernel)
+            # instead of a one-hot GEMM, three elementwise launches and their backward ops
+            x_reg = dense.add3(x_reg, enhanced_feat, g, pos_rois, self.alpha)
+        else:
+            if global_feat is not None:
+                x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
+            x_reg = x_reg + self.alpha * enhanced_feat
+            x_reg = x_reg.contiguous(memory_format=torch.channels_last)
         last = self.convs[-1] if len(self.convs) else None
         if last is not None and last.gn is None and last.with_act and x_reg.is_cuda and \
                 ConvModule.fused_gn and last.conv.out_channels % 8 == 0:

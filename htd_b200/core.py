@@ -43,13 +43,21 @@ def as_cfg(obj):
 # ----------------------------------------------------------------------------------------------
 def bbox2roi(bbox_list):
     """core/bbox/transforms.py:58-77 - [K,5] = (image index, x1, y1, x2, y2)."""
-    parts = []
-    for img_id, b in enumerate(bbox_list):
-        if b.size(0) > 0:
-            parts.append(torch.cat([b.new_full((b.size(0), 1), img_id), b[:, :4]], dim=-1))
-        else:
-            parts.append(b.new_zeros((0, 5)))
-    return torch.cat(parts, 0)
+    sizes = tuple(int(b.size(0)) for b in bbox_list)
+    b0 = bbox_list[0]
+    key = (sizes, str(b0.device), b0.dtype)
+    idx = _ROI_INDEX_CACHE.get(key)
+    if idx is None:                     # the image-index column depends on the counts only
+        if len(_ROI_INDEX_CACHE) > 64:
+            _ROI_INDEX_CACHE.clear()
+        col = torch.cat([torch.full((n, 1), float(i)) for i, n in enumerate(sizes)]) if sum(sizes) \
+            else torch.zeros((0, 1))
+        idx = _ROI_INDEX_CACHE[key] = col.to(device=b0.device, dtype=b0.dtype)
+    boxes = torch.cat([b[:, :4] for b in bbox_list], 0) if len(bbox_list) > 1 else b0[:, :4]
+    return torch.cat([idx, boxes], dim=1)
+
+
+_ROI_INDEX_CACHE = {}
 
 
 def bbox2result(bboxes, labels, num_classes):

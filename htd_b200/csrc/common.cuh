@@ -68,6 +68,21 @@ inline int sm_count() {
 
 constexpr int kWarp = 32;
 
+// scalar load / store of a tensor element as float (fp32 or bf16 tensors)
+template <typename T>
+__device__ __forceinline__ float ldv(const T* p);
+template <>
+__device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void stv(T* p, float v);
+template <>
+__device__ __forceinline__ void stv<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+
 // ---------------------------------------------------------------------------------------------
 // A warp covers 256 channels of one pixel with 128-bit accesses; a lane owns 8 channels.  The
 // lane->channel map is a property of the KERNEL (all tensors it touches must agree):

@@ -85,7 +85,8 @@ struct DenseParams {
     int d_bf16;
     long long ldd;
     void* D2;                     // second output: v + row_bias[row_class[m], n]  (same dtype / ld)
-    const float* bias;            // [N]
+    const void* bias;             // [N] fp32, or bf16 when bias_bf16
+    int bias_bf16;
     const float* row_bias;        // [R, N]
     const int* row_class;         // [M]
     long long ld_rb;
@@ -273,8 +274,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     tc::fence_after();
                     const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
                     const uint32_t sb = sa + (uint32_t)p.a_bytes;
-#pragma unroll 1
-                    for (int k = 0; k < p.ksteps; ++k) {
+                    auto mma_step = [&](int k) {
                         const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, chunk)
                                                    : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
                         const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, chunk)
@@ -286,6 +286,13 @@ __global__ void __launch_bounds__(kDThreads, 1)
                                                         : tc::desc_kmajor(sa + kDAHalf) + (uint64_t)(2 * k);
                             tc::umma_bf16(acc1, ad1, bd, idesc, acc);
                         }
+                    };
+                    if (p.ksteps == kDBK / 16) {          // the common stage: 64 k = 4 steps, unrolled
+#pragma unroll
+                        for (int k = 0; k < kDBK / 16; ++k) mma_step(k);
+                    } else {
+#pragma unroll 1
+                        for (int k = 0; k < p.ksteps; ++k) mma_step(k);
                     }
                     tc::commit(empty_bar + s);
                 }
@@ -368,9 +375,17 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     }
                     // row-major: bias, second output with the per-row-class bias, relu, gate
                     if (p.bias != nullptr) {
+                        if (p.bias_bf16) {
+                            const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(p.bias) + n0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) f[j] += __ldg(p.bias + n0 + j);
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nc) f[j] += __bfloat162float(bb[j]);
+                        } else {
+                            const float* bb = static_cast<const float*>(p.bias) + n0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nc) f[j] += __ldg(bb + j);
+                        }
                     }
                     if (p.D2 != nullptr) {
                         const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
@@ -454,7 +469,9 @@ __global__ void __launch_bounds__(256) dense_finish_kernel(const DenseParams p) 
             for (int j = 0; j < nc; ++j) f[j] += src[j];
         }
         if (p.bias != nullptr)
-            for (int j = 0; j < nc; ++j) f[j] += __ldg(p.bias + n0 + j);
+            for (int j = 0; j < nc; ++j)
+                f[j] += p.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[n0 + j])
+                                    : __ldg(static_cast<const float*>(p.bias) + n0 + j);
         if (p.D2 != nullptr) {
             const float* rb = p.row_bias + (size_t)p.row_class[m] * p.ld_rb + n0;
             __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
@@ -504,13 +521,92 @@ __global__ void __launch_bounds__(256) gate_colsum_kernel(
         partial[(size_t)blockIdx.y * N + c] =
             (s_sum[0][threadIdx.x] + s_sum[1][threadIdx.x]) + (s_sum[2][threadIdx.x] + s_sum[3][threadIdx.x]);
 }
+// out[j][c] = sum over chunks of partial[chunk][j][c], j < nvec (fixed order), fp32 or bf16 output
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
-                                                           int chunks, int N, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+                                                           int chunks, int nvec, int N,
+                                                           void* __restrict__ out, int out_bf16) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (c >= N) return;
     float acc = 0.f;
-    for (int k = 0; k < chunks; ++k) acc += partial[(size_t)k * N + c];
-    out[c] = acc;
+    for (int k = 0; k < chunks; ++k) acc += partial[((size_t)k * nvec + j) * N + c];
+    if (out_bf16) static_cast<__nv_bfloat16*>(out)[(size_t)j * N + c] = __float2bfloat16_rn(acc);
+    else static_cast<float*>(out)[(size_t)j * N + c] = acc;
+}
+
+// Backward glue of the dual-output FC (dense.linear_dual, htd_bbox_head.py:161-164,191-192): with
+// H = [relu(v); relu(v + corr[cls])] and dH its gradient,
+//   dz[m]   = dH[m] * [H[m] > 0] + dH[M + m] * [H[M + m] > 0]          (gradient of v)
+//   partial[chunk][0][c]     = column sums of dz            -> bias gradient
+//   partial[chunk][1 + r][c] = column sums of dH[M + m] * [H[M + m] > 0] over rows of class r
+// One pass over the four [M, N] operands instead of ~14 elementwise / compare / one-hot launches.
+__global__ void __launch_bounds__(256) dual_gate_kernel(
+    const __nv_bfloat16* __restrict__ dH, const __nv_bfloat16* __restrict__ H,
+    const int* __restrict__ cls, int M, int N, int R, __nv_bfloat16* __restrict__ dz,
+    float* __restrict__ partial) {
+    extern __shared__ float s_acc[];                 // [4 row groups][1 + R][64]
+    const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int c = blockIdx.x * 64 + cl;
+    const int r0 = blockIdx.y * kCsRows;
+    float acc[1 + 8];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+    if (c < N)
+        for (int r = r0 + rg; r < min(r0 + kCsRows, M); r += 4) {
+            const size_t ia = (size_t)r * N + c, ib = (size_t)(M + r) * N + c;
+            const float a = __bfloat162float(H[ia]) > 0.f ? __bfloat162float(dH[ia]) : 0.f;
+            const float b = __bfloat162float(H[ib]) > 0.f ? __bfloat162float(dH[ib]) : 0.f;
+            const float z = a + b;
+            dz[ia] = __float2bfloat16_rn(z);
+            acc[0] += z;
+            const int k = cls[r];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j == k) acc[1 + j] += b;
+        }
+    for (int j = 0; j <= R; ++j) s_acc[(rg * (1 + R) + j) * 64 + cl] = acc[j];
+    __syncthreads();
+    if (rg == 0 && c < N)
+        for (int j = 0; j <= R; ++j) {
+            float t = 0.f;
+            for (int g = 0; g < 4; ++g) t += s_acc[(g * (1 + R) + j) * 64 + cl];
+            partial[((size_t)blockIdx.y * (1 + R) + j) * N + c] = t;
+        }
+}
+
+// out[p, px, c] = a[p, px, c] + alpha * b[p, px, c] + g[img[p], c]  (channels-last RoI maps): the
+// regression-branch input of HTDBBoxHead (x_reg + global_feat + alpha * BA, htd_bbox_head.py:163,184)
+__global__ void __launch_bounds__(256) add3_kernel(const __nv_bfloat16* __restrict__ a,
+                                                   const __nv_bfloat16* __restrict__ b, float alpha,
+                                                   const __nv_bfloat16* __restrict__ g,
+                                                   const float* __restrict__ rois, int P, int PP, int C,
+                                                   int B, __nv_bfloat16* __restrict__ out) {
+    const long long n8 = (long long)P * PP * C / 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 8;
+        const int c = (int)(e % C);
+        const int roi = (int)(e / ((long long)PP * C));
+        const uint4 ua = *reinterpret_cast<const uint4*>(a + e);
+        const uint4 ub = *reinterpret_cast<const uint4*>(b + e);
+        uint4 ug = make_uint4(0u, 0u, 0u, 0u);
+        if (g != nullptr) {
+            const int img = (int)rois[(size_t)roi * 5];
+            if (img >= 0 && img < B) ug = *reinterpret_cast<const uint4*>(g + (size_t)img * C + c);
+        }
+        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w},
+                       wg[4] = {ug.x, ug.y, ug.z, ug.w};
+        uint32_t wo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float lo = __uint_as_float(wa[t] << 16) + alpha * __uint_as_float(wb[t] << 16) +
+                             __uint_as_float(wg[t] << 16);
+            const float hi = __uint_as_float(wa[t] & 0xffff0000u) + alpha * __uint_as_float(wb[t] & 0xffff0000u) +
+                             __uint_as_float(wg[t] & 0xffff0000u);
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            wo[t] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(out + e) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+    }
 }
 
 }  // namespace htd
@@ -570,6 +666,7 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
     p.d_bf16 = g->d_dtype == HTD_BF16;
     p.ldd = g->ldd;
     p.bias = g->bias;
+    p.bias_bf16 = g->bias_dtype == HTD_BF16;
     p.relu = g->relu;
     p.gate = static_cast<const __nv_bfloat16*>(g->gate);
     p.ldg = g->ldg;
@@ -703,7 +800,8 @@ int htd_dense_gemm(const HtdDenseGemm* g, void* workspace, long long workspace_b
 }
 
 int htd_gate_colsum(const void* dy, long long ld_dy, const void* y, long long ld_y, int rows, int N,
-                    void* dz, long long ld_dz, float* partial, float* out, htd_stream_t stream) {
+                    void* dz, long long ld_dz, float* partial, void* out, int out_dtype,
+                    htd_stream_t stream) {
     HTD_CHECK_ARG(rows >= 0 && N > 0 && dy && partial && out, "htd_gate_colsum: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int chunks = (rows + kCsRows - 1) / kCsRows;
@@ -713,8 +811,43 @@ int htd_gate_colsum(const void* dy, long long ld_dy, const void* y, long long ld
             rows, N, static_cast<__nv_bfloat16*>(dz), ld_dz, partial);
         HTD_CHECK_LAUNCH("htd_gate_colsum");
     }
-    colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, chunks, N, out);
+    colsum_final_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, chunks, 1, N, out,
+                                                          out_dtype == HTD_BF16);
     HTD_CHECK_LAUNCH("htd_gate_colsum(final)");
+    return HTD_OK;
+}
+
+int htd_dual_gate(const void* dH, const void* H, const int32_t* cls, int M, int N, int R, void* dz,
+                  float* partial, void* out, int out_dtype, htd_stream_t stream) {
+    HTD_CHECK_ARG(M >= 0 && N > 0 && R >= 1 && R <= 8 && dH && H && cls && dz && partial && out,
+                  "htd_dual_gate: bad arguments (M=%d N=%d R=%d, R <= 8)", M, N, R);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = (M + kCsRows - 1) / kCsRows;
+    if (chunks > 0) {
+        dual_gate_kernel<<<dim3((N + 63) / 64, chunks), 256, (size_t)4 * (1 + R) * 64 * sizeof(float), st>>>(
+            static_cast<const __nv_bfloat16*>(dH), static_cast<const __nv_bfloat16*>(H), cls, M, N, R,
+            static_cast<__nv_bfloat16*>(dz), partial);
+        HTD_CHECK_LAUNCH("htd_dual_gate");
+    }
+    colsum_final_kernel<<<dim3((N + 255) / 256, 1 + R), 256, 0, st>>>(partial, chunks, 1 + R, N, out,
+                                                                      out_dtype == HTD_BF16);
+    HTD_CHECK_LAUNCH("htd_dual_gate(final)");
+    return HTD_OK;
+}
+
+int htd_add3(const void* a, const void* b, float alpha, const void* g, const float* rois, int P,
+             int PP, int C, int B, void* out, htd_stream_t stream) {
+    HTD_CHECK_ARG(P >= 0 && PP > 0 && C > 0 && C % 8 == 0 && (g == nullptr || (rois != nullptr && B > 0)),
+                  "htd_add3: bad arguments (C must be a multiple of 8)");
+    if (P == 0) return HTD_OK;
+    HTD_CHECK_ARG(a && b && out, "htd_add3: null pointer");
+    const long long n8 = (long long)P * PP * C / 8;
+    const int sms = sm_count();
+    const unsigned blocks = (unsigned)((n8 + 255) / 256 < 8LL * sms ? (n8 + 255) / 256 : 8LL * sms);
+    add3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), alpha,
+        static_cast<const __nv_bfloat16*>(g), rois, P, PP, C, B, static_cast<__nv_bfloat16*>(out));
+    HTD_CHECK_LAUNCH("htd_add3");
     return HTD_OK;
 }
 

@@ -67,7 +67,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // one warp per (n, g); work items of a group: (pixel, 8-channel chunk), strided over the lanes
 template <typename T>
 __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_fwd_kernel(
-    const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const T* __restrict__ x, const T* __restrict__ gamma, const T* __restrict__ beta,
     int N, int HW, int C, int G, float eps, T* __restrict__ y,
     typename GnAcc<T>::type* __restrict__ mean_out, typename GnAcc<T>::type* __restrict__ rstd_out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_fwd_kernel(
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = g * cpg + c0 + e;
-            const acc_t pre = ((acc_t)v[e] - mean_a) * rstd_a * (acc_t)__ldg(gamma + c) + (acc_t)__ldg(beta + c);
+            const acc_t pre = ((acc_t)v[e] - mean_a) * rstd_a * (acc_t)ldv<T>(gamma + c) + (acc_t)ldv<T>(beta + c);
             v[e] = fmaxf((float)pre, 0.f);
         }
         st8<T>(yg + (size_t)pix * C + c0, v);
@@ -116,8 +116,8 @@ template <typename T>
 __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_bwd_kernel(
     const T* __restrict__ x, const T* __restrict__ dy,
     const typename GnAcc<T>::type* __restrict__ mean_in,
-    const typename GnAcc<T>::type* __restrict__ rstd_in, const float* __restrict__ gamma,
-    const float* __restrict__ beta, int N, int HW, int C, int G, T* __restrict__ dx,
+    const typename GnAcc<T>::type* __restrict__ rstd_in, const T* __restrict__ gamma,
+    const T* __restrict__ beta, int N, int HW, int C, int G, T* __restrict__ dx,
     float* __restrict__ part) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * kGnWarps + warp;
@@ -146,10 +146,10 @@ __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_bwd_kernel(
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = g * cpg + c0 + e;
-            const acc_t ga = (acc_t)__ldg(gamma + c);
+            const acc_t ga = (acc_t)ldv<T>(gamma + c);
             const acc_t xh = ((acc_t)v[e] - mean) * rstd;
             // same expression as the forward pass: the ReLU mask is reproduced exactly
-            const float de = (float)(xh * ga + (acc_t)__ldg(beta + c)) > 0.f ? d[e] : 0.f;
+            const float de = (float)(xh * ga + (acc_t)ldv<T>(beta + c)) > 0.f ? d[e] : 0.f;
             s1 += (acc_t)de * ga;
             s2 += (acc_t)de * ga * xh;
             if (fixed_chunk) { pg[e] += (float)((acc_t)de * xh); pb[e] += de; }
@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_bwd_kernel(
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = g * cpg + c0 + e;
-            const acc_t ga = (acc_t)__ldg(gamma + c);
+            const acc_t ga = (acc_t)ldv<T>(gamma + c);
             const acc_t xh = ((acc_t)v[e] - mean) * rstd;
-            const float de = (float)(xh * ga + (acc_t)__ldg(beta + c)) > 0.f ? d[e] : 0.f;
+            const float de = (float)(xh * ga + (acc_t)ldv<T>(beta + c)) > 0.f ? d[e] : 0.f;
             v[e] = (float)(rstd * ((acc_t)de * ga - s1 - xh * s2));
         }
         st8<T>(dxg + (size_t)pix * C + c0, v);
@@ -200,9 +200,10 @@ __global__ void __launch_bounds__(kGnWarps * 32) gn_relu_bwd_kernel(
 
 // backward, phase 2: dgamma[c] = sum_n part[0][n][c], dbeta[c] = sum_n part[1][n][c].
 // block = 32 channels x 8 row slices (blockIdx.y selects dgamma / dbeta), fixed summation order.
+template <typename T>
 __global__ void __launch_bounds__(256) gn_param_reduce_kernel(const float* __restrict__ part, int N,
-                                                              int C, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta) {
+                                                              int C, T* __restrict__ dgamma,
+                                                              T* __restrict__ dbeta) {
     __shared__ float s_part[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) gn_param_reduce_kernel(const float* __res
         float t = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += s_part[i][tx];
-        (blockIdx.y == 0 ? dgamma : dbeta)[c] = t;
+        stv<T>((blockIdx.y == 0 ? dgamma : dbeta) + c, t);
     }
 }
 
@@ -290,8 +291,8 @@ using namespace htd;
 
 extern "C" {
 
-int htd_gn_relu_fwd(const void* x, int dtype, int N, int HW, int C, int G, const float* gamma,
-                    const float* beta, float eps, void* y, void* mean, void* rstd,
+int htd_gn_relu_fwd(const void* x, int dtype, int N, int HW, int C, int G, const void* gamma,
+                    const void* beta, float eps, void* y, void* mean, void* rstd,
                     htd_stream_t stream) {
     HTD_CHECK_ARG(gn_args_ok(N, HW, C, G), "htd_gn_relu_fwd: need C %% G == 0 and (C/G) %% 8 == 0 "
                   "(N=%d HW=%d C=%d G=%d)", N, HW, C, G);
@@ -303,19 +304,21 @@ int htd_gn_relu_fwd(const void* x, int dtype, int N, int HW, int C, int G, const
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == HTD_F32)
         gn_relu_fwd_kernel<float><<<blocks, kGnWarps * 32, 0, st>>>(
-            static_cast<const float*>(x), gamma, beta, N, HW, C, G, eps, static_cast<float*>(y),
+            static_cast<const float*>(x), static_cast<const float*>(gamma),
+            static_cast<const float*>(beta), N, HW, C, G, eps, static_cast<float*>(y),
             static_cast<double*>(mean), static_cast<double*>(rstd));
     else
         gn_relu_fwd_kernel<__nv_bfloat16><<<blocks, kGnWarps * 32, 0, st>>>(
-            static_cast<const __nv_bfloat16*>(x), gamma, beta, N, HW, C, G, eps,
+            static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(gamma),
+            static_cast<const __nv_bfloat16*>(beta), N, HW, C, G, eps,
             static_cast<__nv_bfloat16*>(y), static_cast<float*>(mean), static_cast<float*>(rstd));
     HTD_CHECK_LAUNCH("htd_gn_relu_fwd");
     return HTD_OK;
 }
 
 int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, const void* rstd,
-                    const float* gamma, const float* beta, int N, int HW, int C, int G, void* dx,
-                    float* part, float* dgamma, float* dbeta, htd_stream_t stream) {
+                    const void* gamma, const void* beta, int N, int HW, int C, int G, void* dx,
+                    float* part, void* dgamma, void* dbeta, htd_stream_t stream) {
     HTD_CHECK_ARG(gn_args_ok(N, HW, C, G), "htd_gn_relu_bwd: need C %% G == 0 and (C/G) %% 8 == 0 "
                   "(N=%d HW=%d C=%d G=%d)", N, HW, C, G);
     HTD_CHECK_ARG(dtype == HTD_F32 || dtype == HTD_BF16, "htd_gn_relu_bwd: bad dtype");
@@ -334,15 +337,23 @@ int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, 
         if (dtype == HTD_F32)
             gn_relu_bwd_kernel<float><<<blocks, kGnWarps * 32, 0, st>>>(
                 static_cast<const float*>(x), static_cast<const float*>(dy),
-                static_cast<const double*>(mean), static_cast<const double*>(rstd), gamma, beta,
+                static_cast<const double*>(mean), static_cast<const double*>(rstd),
+                static_cast<const float*>(gamma), static_cast<const float*>(beta),
                 N, HW, C, G, static_cast<float*>(dx), part);
         else
             gn_relu_bwd_kernel<__nv_bfloat16><<<blocks, kGnWarps * 32, 0, st>>>(
                 static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy),
-                static_cast<const float*>(mean), static_cast<const float*>(rstd), gamma, beta, N, HW, C, G, static_cast<__nv_bfloat16*>(dx), part);
+                static_cast<const float*>(mean), static_cast<const float*>(rstd),
+                static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), N, HW,
+                C, G, static_cast<__nv_bfloat16*>(dx), part);
         HTD_CHECK_LAUNCH("htd_gn_relu_bwd");
     }
-    gn_param_reduce_kernel<<<dim3((C + 31) / 32, 2), 256, 0, st>>>(part, N, C, dgamma, dbeta);
+    if (dtype == HTD_F32)
+        gn_param_reduce_kernel<float><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(
+            part, N, C, static_cast<float*>(dgamma), static_cast<float*>(dbeta));
+    else
+        gn_param_reduce_kernel<__nv_bfloat16><<<dim3((C + 31) / 32, 2), 256, 0, st>>>(
+            part, N, C, static_cast<__nv_bfloat16*>(dgamma), static_cast<__nv_bfloat16*>(dbeta));
     HTD_CHECK_LAUNCH("htd_gn_relu_bwd(params)");
     return HTD_OK;
 }

@@ -10,19 +10,6 @@
 
 namespace htd {
 
-template <typename T>
-__device__ __forceinline__ float ldv(const T* p);
-template <>
-__device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
-template <>
-__device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-template <typename T>
-__device__ __forceinline__ void stv(T* p, float v);
-template <>
-__device__ __forceinline__ void stv<float>(float* p, float v) { *p = v; }
-template <>
-__device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-
 // ------------------------------------------------------------------------------------------
 // targets: labels / label_weights / bbox_targets / bbox_weights of every sampled RoI
 // ------------------------------------------------------------------------------------------

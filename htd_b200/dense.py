@@ -50,6 +50,7 @@ def gemm(kind, A, B, D, M=0, N=0, K=0, lda=0, ldb=0, ldd=0, bias=None, relu=Fals
     g.kind, g.M, g.N, g.K = int(kind), int(M), int(N), int(K)
     g.P, g.Cin, g.Cout, g.pooled = int(P), int(Cin), int(Cout), 7
     g.d_dtype, g.relu, g.splits = _lib.dt(D), int(bool(relu)), int(splits)
+    g.bias_dtype = _lib.dt(bias) if bias is not None else 0
     g.A, g.B, g.D = A.data_ptr(), B.data_ptr(), D.data_ptr()
     g.D2 = D2.data_ptr() if D2 is not None else None
     g.bias = bias.data_ptr() if bias is not None else None
@@ -80,18 +81,18 @@ def _rows2d(t):
     return t
 
 
-def gate_colsum(dy, y=None, want_dz=True):
-    """(dz, colsum): dz = dy * [y > 0] (dy itself when y is None) and the column sums of dz (fp32)."""
+def gate_colsum(dy, y=None, want_dz=True, out_dtype=torch.float32):
+    """(dz, colsum): dz = dy * [y > 0] (dy itself when y is None) and the column sums of dz."""
     dy = _rows2d(dy)
     rows, N = dy.shape
     dz = None
     if y is not None and want_dz:
         dz = torch.empty((rows, (N + 7) // 8 * 8), dtype=BF16, device=dy.device)[:, :N]
     part = torch.empty(((rows + 63) // 64 or 1, N), dtype=torch.float32, device=dy.device)
-    out = torch.empty(N, dtype=torch.float32, device=dy.device)
+    out = torch.empty(N, dtype=out_dtype, device=dy.device)
     check(lib().htd_gate_colsum(_p(dy), dy.stride(0), _p(y), y.stride(0) if y is not None else 0,
                                 rows, N, _p(dz), dz.stride(0) if dz is not None else 0, _p(part),
-                                _p(out), stream()), 'htd_gate_colsum')
+                                _p(out), _lib.dt(out), stream()), 'htd_gate_colsum')
     return (dz if dz is not None else dy), out
 
 
@@ -108,7 +109,7 @@ class _Linear(torch.autograd.Function):
         N = w2.shape[0]
         ldy = (N + 7) // 8 * 8
         y = torch.empty((M, ldy), dtype=BF16, device=x.device)[:, :N]
-        bf = b.detach().float().contiguous() if b is not None else None
+        bf = b.detach().contiguous() if b is not None else None      # bf16 or fp32: read as it is
         gemm(_lib.DENSE_NT, x2, w2, y, M=M, N=N, K=K, lda=x2.stride(0), ldb=w2.stride(0), ldd=ldy,
              bias=bf, relu=relu, name='fc_fwd')
         ctx.relu = relu
@@ -126,9 +127,10 @@ class _Linear(torch.autograd.Function):
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
         db = None
         if ctx.relu or need_db:
-            dz, colsum = gate_colsum(dy, y if ctx.relu else None)
+            dz, colsum = gate_colsum(dy, y if ctx.relu else None,
+                                     out_dtype=ctx.bdtype if ctx.bdtype in _lib._DT else torch.float32)
             if need_db:
-                db = colsum.to(ctx.bdtype)
+                db = colsum if colsum.dtype == ctx.bdtype else colsum.to(ctx.bdtype)
         else:
             dz = _rows2d(dy)
         dx = dw = None
@@ -158,7 +160,7 @@ class _LinearDual(torch.autograd.Function):
         rb = corr.detach().float().contiguous()
         rc = cls.detach().to(torch.int32).contiguous()
         gemm(_lib.DENSE_NT, x2, w2, H[:M], M=M, N=N, K=K, lda=x2.stride(0), ldb=w2.stride(0), ldd=N,
-             bias=b.detach().float().contiguous(), relu=True, D2=H[M:], row_bias=rb, row_class=rc,
+             bias=b.detach().contiguous(), relu=True, D2=H[M:], row_bias=rb, row_class=rc,
              name='fc_fwd')
         ctx.save_for_backward(x2, w2, H, rc)
         ctx.meta = (b.dtype, corr.dtype, corr.shape[0])
@@ -171,14 +173,14 @@ class _LinearDual(torch.autograd.Function):
         M, K = x2.shape
         N = w2.shape[0]
         dH = dH if dH.dtype == BF16 else dH.to(BF16)
-        dzb = dH[M:] * (H[M:] > 0)
-        dz = (dH[:M] * (H[:M] > 0) + dzb).contiguous()
-        # d corr[r] = sum of dzb over the rows of class r: a [R, M] x [M, N] product (TN kind)
-        Rp = (R + 7) // 8 * 8
-        onehot = (rc[:, None] == torch.arange(Rp, device=rc.device, dtype=rc.dtype)[None, :]).to(BF16)
-        dcorr = torch.empty((R, N), dtype=torch.float32, device=dH.device)
-        gemm(_lib.DENSE_TN, onehot, dzb, dcorr, M=R, N=N, K=M, lda=Rp, ldb=N, ldd=N, name='fc_small')
-        _, db = gate_colsum(dz, None)
+        dH = dH.contiguous()
+        # one pass: gradient of the shared pre-activation, bias gradient, gradient of corr per class
+        dz = torch.empty((M, N), dtype=BF16, device=dH.device)
+        part = torch.empty(((M + 63) // 64 or 1, 1 + R, N), dtype=torch.float32, device=dH.device)
+        sums = torch.empty((1 + R, N), dtype=torch.float32, device=dH.device)
+        check(lib().htd_dual_gate(_p(dH), _p(H), _p(rc), M, N, R, _p(dz), _p(part), _p(sums),
+                                  _lib.dt(sums), stream()), 'htd_dual_gate')
+        db, dcorr = sums[0], sums[1:]
         dx = torch.empty((M, K), dtype=BF16, device=dH.device)
         gemm(_lib.DENSE_NN, dz, w2, dx, M=M, N=K, K=N, lda=N, ldb=w2.stride(0), ldd=K, name='fc_dgrad')
         dw = torch.empty((N, K), dtype=BF16, device=dH.device)
@@ -227,6 +229,45 @@ class _MatMul(torch.autograd.Function):
 
 def mm(a, b):
     return _MatMul.apply(a, b)
+
+
+class _Add3(torch.autograd.Function):
+    """a + alpha * b + g[image of the RoI] on channels-last RoI maps in one pass (the regression
+    branch input of HTDBBoxHead, htd_bbox_head.py:163,184); backward: the same gradient for a, alpha
+    times it for b, and its per-image sum (htd_bias_grad) for g."""
+
+    @staticmethod
+    def forward(ctx, a, b, g, rois, alpha):
+        P, C, S, S2 = a.shape
+        ac = a.detach() if a.is_contiguous(memory_format=torch.channels_last) else \
+            a.detach().contiguous(memory_format=torch.channels_last)
+        bc = b.detach() if b.is_contiguous(memory_format=torch.channels_last) else \
+            b.detach().contiguous(memory_format=torch.channels_last)
+        out = torch.empty((P, S, S2, C), dtype=BF16, device=a.device)
+        gc = g.detach().reshape(g.shape[0], C).contiguous() if g is not None else None
+        r = rois.detach().float().contiguous()
+        check(lib().htd_add3(_p(ac), _p(bc), float(alpha), _p(gc), _p(r), P, S * S2, C,
+                             gc.shape[0] if gc is not None else 0, _p(out), stream()), 'htd_add3')
+        ctx.alpha = float(alpha)
+        ctx.gshape = None if g is None else tuple(g.shape)
+        ctx.save_for_backward(r)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops
+        r, = ctx.saved_tensors
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dg = None
+        if ctx.gshape is not None and ctx.needs_input_grad[2]:
+            dg = ops._bias_grad(dy.permute(0, 2, 3, 1), r, ctx.gshape[0]).reshape(ctx.gshape).to(dy.dtype)
+        db = dy if ctx.alpha == 1.0 else dy * ctx.alpha
+        return dy, db, dg, None, None
+
+
+def add3(a, b, g, rois, alpha=1.0):
+    return _Add3.apply(a, b, g, rois, alpha)
 
 
 def linear(x, w, b=None, relu=False):

@@ -558,8 +558,9 @@ class _GroupNormReLU(torch.autograd.Function):
         sdt = torch.float64 if x.dtype == torch.float32 else torch.float32
         mean = torch.empty(N * groups, dtype=sdt, device=x.device)
         rstd = torch.empty_like(mean)
-        gamma = weight.detach().float().contiguous()
-        beta = bias.detach().float().contiguous()
+        # affine parameters in the tensor dtype (no conversion launches in the bf16 configuration)
+        gamma = weight.detach().to(x.dtype).contiguous()
+        beta = bias.detach().to(x.dtype).contiguous()
         check(lib().htd_gn_relu_fwd(ptr(x), dt(x), N, H * W, C, int(groups), ptr(gamma), ptr(beta),
                                     float(eps), ptr(y), ptr(mean), ptr(rstd), stream()),
               'htd_gn_relu_fwd')
@@ -576,7 +577,7 @@ class _GroupNormReLU(torch.autograd.Function):
             dy = dy.to(x.dtype).contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         part = torch.empty((2, max(N, 1), C), dtype=torch.float32, device=x.device)
-        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dgamma = torch.empty(C, dtype=x.dtype, device=x.device)
         dbeta = torch.empty_like(dgamma)
         check(lib().htd_gn_relu_bwd(ptr(x), ptr(dy), dt(x), ptr(mean), ptr(rstd), ptr(gamma),
                                     ptr(beta), N, H * W, C, groups, ptr(dx), ptr(part), ptr(dgamma),

@@ -180,7 +180,9 @@ class _PGraphFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[:4])
         refined = torch.zeros((K, d), dtype=x.dtype, device=dev)
         x = x.detach().contiguous()
-        sam = sam.detach().contiguous()
+        sam = sam.detach()
+        if sam.stride(1) != 1:
+            sam = sam.contiguous()          # the pack kernel takes any row pitch
         Wc = W.detach().to(op).contiguous().reshape(L * d, d)
         bc = b.detach().float().contiguous().reshape(L * d)
         lds = _round_up(ds, ALIGN)
@@ -229,7 +231,8 @@ class _PGraphFunction(torch.autograd.Function):
         check(lib().htd_pgraph_segment_colsum(ptr(dU), dt(dU), d, ptr(plan.level_seg), L, d,
                                               ptr(db), stream()), 'htd_pgraph_segment_colsum')
         # dW_l = dU_l^T Z_l   (K = RoIs of the level block; both operands zero in the pad rows)
-        dW = torch.zeros((L * d, d), dtype=torch.float32, device=dev)
+        # weight gradient straight in the parameter dtype (no fp32 buffer + cast of 4 x d x d)
+        dW = torch.zeros((L * d, d), dtype=wdt if wdt in _lib._DT else torch.float32, device=dev)
         plan.gemm(dUT, ZT, _lib.SCHED_LEVEL_DD, D=dW, ldd=d)
         # dZ = dU W_l
         WT = torch.empty((L * d, d), dtype=op, device=dev)

@@ -306,8 +306,9 @@ int htd_pgraph_gemm(const void* A, long long a_rows, long long a_ld, const void*
  * > 0] (gate = the forward activation of the layer whose ReLU the gradient passes).
  * splits: 0 = choose (fill the SMs), n > 0 = n k-slices; partial sums go through `workspace`
  * (htd_dense_gemm_workspace_bytes) and are added in slice order: results are deterministic.
- * htd_gate_colsum: dz = dy * [y > 0] (y, dz optional) and out[n] = sum_m dz[m,n] - the bias
- * gradient of an FC layer and its ReLU backward in one pass; partial: [ceil(rows/64), N] fp32. */
+ * htd_gate_colsum: dz = dy * [y > 0] (y, dz optional) and out[n] = sum_m dz[m,n] (out_dtype) -
+ * the bias gradient of an FC layer and its ReLU backward in one pass; partial: [ceil(rows/64), N]
+ * fp32. */
 #define HTD_DENSE_NT 0
 #define HTD_DENSE_NN 1
 #define HTD_DENSE_TN 2
@@ -318,12 +319,12 @@ typedef struct HtdDenseGemm {
     int32_t kind;
     int32_t M, N, K;              /* GEMM kinds */
     int32_t P, Cin, Cout, pooled; /* conv kinds: RoIs, channels, map size (7) */
-    int32_t d_dtype, relu, splits, reserved;
+    int32_t d_dtype, relu, splits, bias_dtype; /* bias_dtype: HTD_F32 (default) or HTD_BF16 */
     const void* A;
     const void* B;
     void* D;
     void* D2;
-    const float* bias;
+    const void* bias;
     const float* row_bias;
     const int32_t* row_class;
     const void* gate;
@@ -333,7 +334,19 @@ long long htd_dense_gemm_workspace_bytes(const HtdDenseGemm* g);
 int htd_dense_gemm(const HtdDenseGemm* g, void* workspace, long long workspace_bytes,
                    htd_stream_t stream);
 int htd_gate_colsum(const void* dy, long long ld_dy, const void* y, long long ld_y, int rows, int N,
-                    void* dz, long long ld_dz, float* partial, float* out, htd_stream_t stream);
+                    void* dz, long long ld_dz, float* partial, void* out, int out_dtype,
+                    htd_stream_t stream);
+/* Backward glue of the dual-output FC (D / D2 above): dH, H [2M, N] bf16 (rows M.. = the D2 part),
+ * cls [M] < R <= 8.  dz [M, N] = dH_a * [H_a > 0] + dH_b * [H_b > 0]; out [1 + R, N] (out_dtype):
+ * row 0 = column sums of dz (bias gradient), row 1 + r = column sums of dH_b * [H_b > 0] over the
+ * rows of class r (gradient of row_bias).  partial: [ceil(M/64), 1 + R, N] fp32. */
+int htd_dual_gate(const void* dH, const void* H, const int32_t* cls, int M, int N, int R, void* dz,
+                  float* partial, void* out, int out_dtype, htd_stream_t stream);
+/* out = a + alpha * b + g[image(roi)] on channels-last bf16 RoI maps [P, PP, C] (g [B, C] or NULL,
+ * rois [P, 5] give the image index): the regression-branch input of HTDBBoxHead
+ * (htd_bbox_head.py:163,184: x_reg + global_feat + alpha * enhanced_feat). */
+int htd_add3(const void* a, const void* b, float alpha, const void* g, const float* rois, int P,
+             int PP, int C, int B, void* out, htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Target / loss / decode glue, one kernel per job, no host sync.
@@ -446,17 +459,17 @@ int htd_multiclass_soft_nms(const float* boxes, int box_classes, const float* sc
 /* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
  * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and
- * (C / G) % 8 == 0; gamma / beta fp32; mean / rstd [N*G]: fp32 for HTD_BF16 tensors, fp64 for
+ * (C / G) % 8 == 0; gamma / beta / dgamma / dbeta in the tensor dtype; mean / rstd [N*G]: fp32 for HTD_BF16 tensors, fp64 for
  * HTD_F32 tensors (the fp32 configuration computes its statistics and residuals in fp64).
  *   y = relu((x - mean) * rstd * gamma + beta), mean / rstd per (n, group), biased variance + eps
  * Backward recomputes the ReLU mask from x; part is a [2, N, C] fp32 workspace; dgamma / dbeta
  * are fully written. */
-int htd_gn_relu_fwd(const void* x, int dtype, int N, int HW, int C, int G, const float* gamma,
-                    const float* beta, float eps, void* y, void* mean, void* rstd,
+int htd_gn_relu_fwd(const void* x, int dtype, int N, int HW, int C, int G, const void* gamma,
+                    const void* beta, float eps, void* y, void* mean, void* rstd,
                     htd_stream_t stream);
 int htd_gn_relu_bwd(const void* x, const void* dy, int dtype, const void* mean, const void* rstd,
-                    const float* gamma, const float* beta, int N, int HW, int C, int G, void* dx,
-                    float* part, float* dgamma, float* dbeta, htd_stream_t stream);
+                    const void* gamma, const void* beta, int N, int HW, int C, int G, void* dx,
+                    float* part, void* dgamma, void* dbeta, htd_stream_t stream);
 
 /* ReLU + global average pool of the last tower conv (ConvModule without norm, htd_bbox_head.py:
  * 109-113, then avg_pool :188-189), channels-last x [N, HW, C], C % 8 == 0:

@@ -175,3 +175,45 @@ def test_dense_results_are_deterministic():
         dense.gemm(_lib.DENSE_NT, A, B, D, M=512, N=1024, K=4096, lda=4096, ldb=4096, ldd=1024)
         outs.append(D)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_linear_dual_autograd_vs_torch():
+    """H = [relu(x w^T + b); relu(x w^T + b + corr[cls])] and its backward (htd_dual_gate: gate,
+    bias gradient and per-class corr gradient in one pass) against plain PyTorch."""
+    from htd_b200 import dense
+    g = torch.Generator().manual_seed(3)
+    M, K, N, R = 1000, 520, 1024, 2
+    x = _rand(g, M, K).requires_grad_(True)
+    w = _rand(g, N, K, scale=1.0 / K ** 0.5).requires_grad_(True)
+    b = _rand(g, N).requires_grad_(True)
+    corr = _rand(g, R, N).requires_grad_(True)
+    cls = torch.randint(0, R, (M,), generator=g).float().cuda()
+    dH = _rand(g, 2 * M, N)
+    H = dense.linear_dual(x, w, b, corr, cls)
+    gx, gw, gb, gc = torch.autograd.grad(H, [x, w, b, corr], dH)
+    xf, wf, bf_, cf = (t.detach().float().requires_grad_(True) for t in (x, w, b, corr))
+    v = xf @ wf.t() + bf_
+    Hf = torch.cat([v, v + cf[cls.long()]], 0) * (H.detach() > 0)      # the product's own gates
+    fx, fw, fb, fc = torch.autograd.grad(Hf, [xf, wf, bf_, cf], dH.float())
+    assert _rel(H, Hf) <= 1e-2
+    for a, e in ((gx, fx), (gw, fw), (gb, fb), (gc, fc)):
+        assert _rel(a, e) <= 1e-2
+
+
+def test_add3_vs_torch():
+    from htd_b200 import dense
+    g = torch.Generator().manual_seed(4)
+    P, C, B = 37, 256, 3
+    a = _rand(g, P, C, 7, 7).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    b = _rand(g, P, C, 7, 7).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gg = _rand(g, B, C, 1, 1).requires_grad_(True)
+    rois = torch.zeros(P, 5, device='cuda')
+    rois[:, 0] = torch.randint(0, B, (P,), generator=g).float().cuda()
+    dy = _rand(g, P, C, 7, 7).contiguous(memory_format=torch.channels_last)
+    out = dense.add3(a, b, gg, rois, 1.0)
+    ga, gb, g3 = torch.autograd.grad(out, [a, b, gg], dy)
+    want = a.float() + b.float() + gg.float()[rois[:, 0].long()]
+    assert _rel(out, want) <= 1e-2
+    assert torch.equal(ga, dy) and torch.equal(gb, dy)
+    w3 = torch.zeros(B, C, device='cuda').index_add_(0, rois[:, 0].long(), dy.float().sum((2, 3)))
+    assert _rel(g3.reshape(B, C), w3) <= 1e-2

@@ -41,8 +41,19 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
              with_stack=True) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages(group_by_input_shape=True).table(sort_by='cuda_time_total', row_limit=70,
-                                                          max_name_column_width=48,
-                                                          max_shapes_column_width=70))
-print(prof.key_averages(group_by_stack_n=6).table(sort_by='cuda_time_total', row_limit=60,
-                                                  max_name_column_width=40, max_src_column_width=90))
+import collections
+agg = collections.defaultdict(lambda: [0, 0.0])
+for ev in prof.events():
+    if not ev.name.startswith('aten::') or ev.device_time_total <= 0 and ev.self_device_time_total <= 0:
+        continue
+    if ev.self_device_time_total <= 0:
+        continue
+    frames = [f for f in (ev.stack or []) if 'htd_b200' in f or 'oracle' in f or 'synth' in f]
+    site = ' <- '.join(f.split('/')[-1].strip() for f in frames[:3]) or '(autograd engine / library)'
+    k = (ev.name, site)
+    agg[k][0] += 1
+    agg[k][1] += ev.self_device_time_total
+tot = sum(v[1] for v in agg.values())
+print(f'ATen ops with device time: {sum(v[0] for v in agg.values())} launches, {tot:.0f} us')
+for (name, site), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:120]:
+    print(f'{n:4d} {t:8.1f} us  {name:28s} {site[:200]}')
