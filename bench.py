@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='htd_b200', choices=['htd_b200', 'reference'])
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--imgs-per-gpu', type=int, default=IMGS,
+                    help='images per GPU (BASELINE configs[1]: 2; configs[2] = C3: 8)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager steps instead of CUDA-graph replay')
     ap.add_argument('--overlap', action='store_true',
@@ -400,17 +402,18 @@ def run_gpu(args):
     head = head.to(dev).to(dtype)
     head.compute_dtype = dtype
     head.train()
-    img0 = rank * IMGS
-    pyr_host = [t.pin_memory() for t in synth.make_pyramid(IMGS, IMG_H, IMG_W, seed=1000 + img0)]
-    props_host = [p.pin_memory() for p in synth.make_proposals(IMGS, ROIS, IMG_H, IMG_W,
+    imgs = max(1, args.imgs_per_gpu)
+    img0 = rank * imgs
+    pyr_host = [t.pin_memory() for t in synth.make_pyramid(imgs, IMG_H, IMG_W, seed=1000 + img0)]
+    props_host = [p.pin_memory() for p in synth.make_proposals(imgs, ROIS, IMG_H, IMG_W,
                                                                seed=1234 + img0)]
-    gts = synth.make_gt(IMGS, props_host, num_pos=POS, seed=4321 + img0)
+    gts = synth.make_gt(imgs, props_host, num_pos=POS, seed=4321 + img0)
     gts = [{k: v.to(dev) for k, v in g.items()} for g in gts]
-    shapes = [(IMG_H, IMG_W, 3)] * IMGS
+    shapes = [(IMG_H, IMG_W, 3)] * imgs
     x_dev = [t.to(dev).requires_grad_(True) for t in pyr_host]
     props_dev = [p.to(dev) for p in props_host]
     reducer = GradAllReducer(head.parameters(), world) if world > 1 else None
-    rois_per_step = IMGS * ROIS
+    rois_per_step = imgs * ROIS
 
     def eager_step(x, props):
         for p in head.parameters():
@@ -442,9 +445,12 @@ def run_gpu(args):
     _lib.ACCOUNT = None
     launches_per_step -= 0          # accounting adds no launches of the library
     pg_flops = head.bbox_head[1].last_plan.flops()
-    alg = {}
-    for name, nbytes in account:
-        alg.setdefault(name, []).append(nbytes)
+    alg, alg_flops = {}, {}
+    for name, amount in account:
+        if name.endswith(':flops'):
+            alg_flops.setdefault(name[:-6], []).append(amount)
+        else:
+            alg.setdefault(name, []).append(amount)
     ksteps = min(args.steps, 10)
     _lib.TIMER = _lib.KernelTimer()
     ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -467,7 +473,7 @@ def run_gpu(args):
         try:
             gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1,
                                      early_modules=[head.bbox_head[1], head.bbox_roi_extractor[1]]
-                                     if world > 1 and args.overlap else None)
+                                     if world > 1 and args.overlap else None, flat_inputs=True)
         except Exception as e:                     # never lose the measurement to a capture problem
             print(f'[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager',
                   file=sys.stderr)
@@ -530,8 +536,10 @@ def run_gpu(args):
     for t, n in zip(parts, sizes):
         host_flat[off:off + n].copy_(t.reshape(-1))
         off += n
+    direct = use_graph and gstep.input_flat is not None
 
     def upload():
+        """Eager fallback: H2D into a fresh tensor on the copy stream (then copied into the step)."""
         with torch.cuda.stream(copy_stream):
             flat = host_flat.to(dev, non_blocking=True)
             views, off = [], 0
@@ -543,20 +551,44 @@ def run_gpu(args):
         return views[:len(pyr_host)], views[len(pyr_host):], evt, flat
 
     def e2e_loop(n):
-        """Per step: H2D of the step's inputs from pinned host memory (copy stream, one step
-        ahead), the step itself, and an asynchronous D2H of the 7 losses into pinned memory; the
-        host reads step i-1's losses while step i runs (every step's result still reaches the
-        host inside the timed region)."""
+        """Per step: H2D of the step's inputs from pinned host memory, the step itself, and an
+        asynchronous D2H of the 7 losses into pinned memory; the host reads step i-1's losses while
+        step i runs (every step's result still reaches the host inside the timed region).
+        Graph path: the copy stream writes STRAIGHT into the static buffers the graph reads (one
+        183 MB H2D, no staging tensor, no device-to-device copy); it may start as soon as the
+        running step has consumed its inputs (an event recorded inside the graph ~0.1 ms into
+        the step), so the upload of step i+1 overlaps the rest of step i."""
         pinned = [torch.empty(7, dtype=torch.float32).pin_memory() for _ in range(2)]
         done = [torch.cuda.Event() for _ in range(2)]
         seen = 0.0
+        cur = torch.cuda.current_stream()
+        if direct:
+            copy_stream.wait_stream(cur)
+            up = torch.cuda.Event()
+            for i in range(n):
+                with torch.cuda.stream(copy_stream):
+                    if i > 0:
+                        copy_stream.wait_event(gstep.inputs_consumed)   # step i-1 has read its inputs
+                    gstep.input_flat.copy_(host_flat, non_blocking=True)
+                    up.record(copy_stream)
+                cur.wait_event(up)
+                gstep.graph.replay()
+                allreduce_grads()
+                pinned[i & 1].copy_(gstep.loss_vec, non_blocking=True)
+                done[i & 1].record()
+                if i > 0:
+                    done[(i - 1) & 1].synchronize()
+                    seen += float(pinned[(i - 1) & 1][0])
+            done[(n - 1) & 1].synchronize()
+            seen += float(pinned[(n - 1) & 1][0])
+            return pinned[0].numel() * pinned[0].element_size()
         nxt = upload()
         for i in range(n):
             xs, ps, evt, flat = nxt
             if i + 1 < n:
                 nxt = upload()                      # next step's H2D overlaps this step's compute
-            torch.cuda.current_stream().wait_event(evt)
-            flat.record_stream(torch.cuda.current_stream())
+            cur.wait_event(evt)
+            flat.record_stream(cur)
             if not use_graph:
                 xs = [t.detach().requires_grad_(True) for t in xs]
             losses = step(xs, ps)
@@ -588,7 +620,7 @@ def run_gpu(args):
         try:
             from htd_b200.graphed import GraphedStaticTrainStep
             nprop = 2000                               # configs/htd/htd_resnet50_1x.py:115-121
-            sp, sg, sl, sn = (t.to(dev) for t in synth.make_detection_batch(IMGS, nprop))
+            sp, sg, sl, sn = (t.to(dev) for t in synth.make_detection_batch(imgs, nprop))
             metas = [dict(img_shape=s_, scale_factor=1.0) for s_ in shapes]
             sstep = GraphedStaticTrainStep(head, x_dev, metas, sp, sg, sl, sn)   # keys drawn in-graph
             for _ in range(3):
@@ -667,7 +699,7 @@ def run_gpu(args):
 
     # ---- north_star evidence in the driver-visible line (N = 1 only) ----------------------------
     roofline_tensor = sweep = comparator = None
-    if world == 1 and not args.no_static:
+    if world == 1 and not args.no_static and imgs == IMGS:
         flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
         for name, fn in (('roofline_tensor', lambda: pgraph_tensor_roofline(dev, flush)),
                          ('sweep', lambda: gather_sweep(dev, flush, hbm_peak)),
@@ -704,6 +736,16 @@ def run_gpu(args):
         kernels[name] = dict(launches=n, avg_ms=tot_ms / n, alg_MB_per_launch=sum(per_step) / len(per_step) / 1e6,
                              achieved_GBs=gbs, frac=gbs / hbm_peak,
                              share_of_step=(tot_ms / ksteps) / (ms / args.steps))
+    # own dense tcgen05 kernels (FC stacks, conv tower): flops / event time / measured bf16 peak
+    dense_kernels = {}
+    for name, (n, tot_ms) in ksum.items():
+        fl = alg_flops.get(name)
+        if not fl or n == 0:
+            continue
+        tf = sum(fl) * ksteps / (tot_ms * 1e-3) / 1e12
+        dense_kernels[name] = dict(launches=n, avg_ms=tot_ms / n, gflop_per_step=sum(fl) / 1e9,
+                                   achieved_TFLOPs=tf, frac_of_sustained_peak=tf / tc_peak,
+                                   share_of_step=(tot_ms / ksteps) / (ms / args.steps))
     dom = max(kernels, key=lambda k: kernels[k]['share_of_step']) if kernels else None
     roofline = None
     traffic = traffic_src = None
@@ -744,8 +786,9 @@ def run_gpu(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype=args.dtype, data='synthetic',
-                config=dict(workload=WORKLOAD,
-                            global_rois_per_step=rois_per_step * world,
+                config=dict(workload=WORKLOAD if imgs == IMGS else WORKLOAD.replace(
+                                '2 images/GPU', f'{imgs} images/GPU'),
+                            imgs_per_gpu=imgs, global_rois_per_step=rois_per_step * world,
                             parallelism=f'dp{world}' + (' + NCCL grad all-reduce' + (
                                 ' (stage-1 part overlapped with the rest of backward)'
                                 if gstep is not None and gstep.early_event is not None else '')
@@ -763,7 +806,8 @@ def run_gpu(args):
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches, clocks=clk, roofline=roofline, kernels=kernels,
-                roofline_tensor=roofline_tensor, sweep_config5=sweep, gpu_comparator=comparator,
+                dense_kernels=dense_kernels, roofline_tensor=roofline_tensor, sweep_config5=sweep,
+                gpu_comparator=comparator,
                 cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -112,16 +112,37 @@ class _GraphedStep:
 class GraphedTrainStep(_GraphedStep):
 
     def __init__(self, head, x, proposals, gts, img_shapes, num_pos, warmup=3, flat_grads=False,
-                 early_modules=None):
+                 early_modules=None, flat_inputs=False):
         """``flat_grads``: parameter gradients live in ONE flat buffer (``self.flat_grad``; every
         ``p.grad`` is a view of it) that the captured step zeroes and accumulates into - the
         data-parallel exchange is then an all-reduce of that buffer, no packing copies.
-        ``early_modules``: see ``_init_grads``."""
+        ``early_modules``: see ``_init_grads``.
+        ``flat_inputs``: the static pyramid levels and proposals are views of ONE device buffer
+        (``self.input_flat``, fp32) so that a step's inputs arrive with a single host-to-device
+        copy straight into the buffers the graph reads - no staging tensor, no device-to-device
+        copy.  ``self.inputs_consumed`` (an EXTERNAL event recorded inside the graph once the
+        layout conversion and the SFA head have read the inputs, ~0.1 ms into the step) tells a
+        copy stream when the next step's upload may overwrite them."""
         self.img_shapes, self.num_pos = img_shapes, num_pos
         dev = x[0].device
         self._init_grads(head, dev, flat_grads, early_modules)
-        self.x = [t.detach().clone().requires_grad_(True) for t in x]
-        self.proposals = [p.detach().clone() for p in proposals]
+        self.input_flat = self.inputs_consumed = None
+        if flat_inputs:
+            assert all(t.dtype == torch.float32 for t in list(x) + list(proposals))
+            parts = list(x) + list(proposals)
+            self.input_flat = torch.empty(sum(t.numel() for t in parts), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for t in parts:
+                v = self.input_flat[off:off + t.numel()].view(t.shape)
+                v.copy_(t.detach())
+                views.append(v)
+                off += t.numel()
+            self.x = [v.requires_grad_(True) for v in views[:len(x)]]
+            self.proposals = views[len(x):]
+            self.inputs_consumed = torch.cuda.Event(external=True)
+        else:
+            self.x = [t.detach().clone().requires_grad_(True) for t in x]
+            self.proposals = [p.detach().clone() for p in proposals]
         self.gts = [{k: v.detach().clone().to(dev) for k, v in g.items()} for g in gts]
         self._capture(dev, warmup)
 
@@ -130,11 +151,13 @@ class GraphedTrainStep(_GraphedStep):
         prev = self.head.overlap_ba
         if self.early_event is not None:
             self.head.overlap_ba = False
+        self.head.inputs_consumed_event = self.inputs_consumed
         try:
             self._finish(synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
                                                      self.img_shapes, self.num_pos))
         finally:
             self.head.overlap_ba = prev
+            self.head.inputs_consumed_event = None
 
     def load(self, x=None, proposals=None, gts=None, non_blocking=True):
         """Copy new inputs (device or pinned-host tensors) into the static buffers."""

@@ -83,6 +83,7 @@ class HTDRoIHead(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     overlap_ba = True        # class switch (diagnostics): BA extraction on a side stream in training
+    inputs_consumed_event = None   # optional CUDA event recorded once forward_train has read `x`
 
     def _side_stream(self, device):
         st = getattr(self, '_side', None)
@@ -195,11 +196,18 @@ class HTDRoIHead(nn.Module):
                 return sampling_fn(stage, props)
             return self._assign_sample(stage, props, gt_bboxes, gt_labels, gt_bboxes_ignore, x)
 
+        if self.inputs_consumed_event is not None:
+            proposal_list = [p.clone() for p in proposal_list]   # private copy: see the event below
         samp = sample(0, proposal_list)
         global_feat = None
         if self.with_global:
             mc_pred, global_feat = self.glbctx_head(x)
             losses['loss_global'] = self.glbctx_head.loss(mc_pred, gt_labels)
+        if self.inputs_consumed_event is not None and x[0].is_cuda:
+            # everything downstream reads the channels-last copy / the SFA head's cast of P6 only
+            # (and the proposals through copies made below): the caller may refill `x` from here on
+            # - graphed.GraphedTrainStep(flat_inputs=True) overlaps the next upload with this step
+            self.inputs_consumed_event.record()
         res = self._bbox_forward_train(0, x, samp, gt_bboxes, gt_labels, self.train_cfg[0],
                                        img_metas, global_feat, x_cl)
         lw = self.stage_loss_weights[0]
