@@ -634,16 +634,17 @@ static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParam
 
 static int pick_splits(long long tiles, int kblocks, int want, int sms) {
     if (want > 0) return want < kblocks ? want : (kblocks > 0 ? kblocks : 1);
-    // Split K only where it pays for the extra launch of the finishing pass: a long K loop
-    // (>= 32 k-blocks) on a grid that would leave more than half of the SMs idle.  Then as many
-    // slices as fit one wave, at least 8 k-blocks each.
-    if (kblocks < 32 || tiles * 2 > sms) return 1;
+    // A CTA's k-loop is latency bound (about 0.45 us per k-block once the 4-stage ring is primed),
+    // so a grid that leaves SMs idle is cut along K until every CTA has about one ring of k-blocks
+    // - as long as that saves more than the finishing pass costs (about 4 us: one more launch).
+    if (tiles >= sms) return 1;
     int s = (int)(sms / tiles);
-    while (s > 1 && kblocks / s < 8) --s;
-    return s < 1 ? 1 : s;
+    const int by_ring = (kblocks + kDStages - 1) / kDStages;
+    if (s > by_ring) s = by_ring;
+    if (s < 2) return 1;
+    const float saved_us = 0.45f * (float)kblocks * (1.f - 1.f / (float)s);
+    return saved_us > 4.f ? s : 1;
 }
-
-extern "C" {
 
 // fills the launch parameters (and, with `maps`, the tensor maps) of one problem
 static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, CUtensorMap* mb,
@@ -776,6 +777,8 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;      // no empty slice
     return HTD_OK;
 }
+
+extern "C" {
 
 long long htd_dense_gemm_workspace_bytes(const HtdDenseGemm* g) {
     DenseParams p;
