@@ -431,6 +431,210 @@ __global__ void __launch_bounds__(HTD_MAX_POOLED * 32) roi_align_fwd_kernel(cons
 }
 
 // ------------------------------------------------------------------------------------------
+// persistent forward (single-level extraction; every strip is small)
+// ------------------------------------------------------------------------------------------
+// The kernel above pays one exposed memory latency per CTA (a CTA = one bin row of one RoI) and
+// only three CTAs fit an SM, so 7168 CTAs take ~16 rounds of a few microseconds: 0.089 ms and 34 %
+// of the HBM roofline for SingleRoIExtractor at the bench size (ncu: DRAM at 12 % of peak).  Here one
+// CTA per SM stays resident and walks the same work units (RoI, bin row) in order:
+//   warp P      producer: reads the plan entries of a unit several units AHEAD of the consumers,
+//               carves the strip's footprint out of a byte ring in shared memory (~200 KB: five to
+//               seven strips in flight), starts one bulk copy per footprint row plus one for each
+//               slice of the separable axis-weight tables (cp.async.bulk, completion counted on the
+//               unit's mbarrier) and publishes a small descriptor;
+//   warps 0..P-1  one output bin (ph, pw) each: wait for the unit, reduce the bin from the strip
+//               with weights read from the staged tables (broadcast shared loads - no shuffles), add
+//               the SFA bias, store 512 B, release the unit.
+// The arithmetic (w = wy * wx, one fma per pixel in row-major order) is the one of the strip / ring
+// paths above, so results are bit-identical.  A strip that does not fit the ring (never the case
+// for a level-assigned RoI of an 800x1333 image) is reduced straight from global memory.
+constexpr int kPfUnits = 8;                      // descriptor ring (units in flight)
+constexpr int kPfRingBytes = 200 * 1024;         // staging ring
+struct PfUnit {
+    int valid, direct, buf_off, ny, nxs, b, wy_off, wx_off, W;
+    int dx0[HTD_MAX_POOLED], nx[HTD_MAX_POOLED];
+    long long out_off;
+    const void* gsrc;
+};
+constexpr int kPfSmem = kPfRingBytes + kPfUnits * (int)sizeof(PfUnit) + 2 * kPfUnits * 8 + 16;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__((HTD_MAX_POOLED) * 32, 1) roi_align_fwd_persist_kernel(const FwdParams p,
+                                                                                         long long units) {
+    extern __shared__ __align__(128) uint8_t pf_smem[];
+    uint8_t* ringb = pf_smem;
+    PfUnit* desc = reinterpret_cast<PfUnit*>(pf_smem + kPfRingBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + kPfUnits);
+    uint64_t* empty_bar = full_bar + kPfUnits;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = p.P, PP = P * P;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < kPfUnits; ++q) {
+            mbar_init(full_bar + q, 1);
+            mbar_init(empty_bar + q, P);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == P) {
+        // ===== producer =====
+        int head = 0, free_bytes = kPfRingBytes;
+        long long oldest = 0;                        // local index of the oldest unreleased unit
+        int used[kPfUnits];                          // ring bytes (strip + wrap waste) per slot
+#pragma unroll
+        for (int q = 0; q < kPfUnits; ++q) used[q] = 0;
+        long long i = 0;
+        for (long long u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+            const int q = (int)(i % kPfUnits);
+            const int ph = (int)(u % P);
+            const long long task = u / P;
+            const int k = (int)task;
+            const int l = p.roi_level[k];
+            const int b = (int)p.rois[(size_t)k * 5];
+            const bool valid = (b >= 0 && b < p.B) && (l >= 0 && l < p.L);
+            int ry0 = 0, ry1 = -1, bz = 0, bw = -1, cx0 = 0, cx1 = -1, fh = 0, bx = 0;
+            size_t off = 0;
+            if (valid) {
+                const size_t e = (size_t)l * p.K + k;
+                const int4 box = p.boxes[e];
+                if (box.y >= box.x && box.w >= box.z) {
+                    const int* rg = p.ranges + e * kRangeInts;
+                    ry0 = rg[ph]; ry1 = rg[HTD_MAX_POOLED + ph];
+                    if (lane < HTD_MAX_POOLED) {
+                        cx0 = rg[2 * HTD_MAX_POOLED + lane];
+                        cx1 = rg[3 * HTD_MAX_POOLED + lane];
+                    }
+                    off = (size_t)p.offsets[e];
+                    fh = box.y - box.x + 1;
+                    bx = box.x; bz = box.z; bw = box.w;
+                }
+            }
+            const int ny = ry1 - ry0 + 1, nxs = bw - bz + 1;
+            const bool live = valid && ny > 0 && nxs > 0;
+            const int H = live ? p.lv[l].H : 1, W = live ? p.lv[l].W : 1;
+            const int row_bytes = nxs * p.C * (int)sizeof(TIn);
+            const int tab_bytes = live ? (ny + nxs) * kTabW * 4 : 0;
+            long long strip = live ? (long long)ny * row_bytes : 0;
+            const bool direct = strip + tab_bytes > kPfRingBytes;
+            if (direct) strip = 0;
+            const int need = (int)strip + tab_bytes;         // multiple of 16
+            // ---- ring space: units are released in order
+            int waste = 0;
+            if (head + need > kPfRingBytes) waste = kPfRingBytes - head;
+            while (oldest + kPfUnits <= i || free_bytes < need + waste) {
+                const int oq = (int)(oldest % kPfUnits);
+                mbar_wait(empty_bar + oq, (uint32_t)(oldest / kPfUnits) & 1u);
+                free_bytes += used[oq];
+                ++oldest;
+            }
+            if (waste) head = 0;
+            const int buf = head;
+            head += need;
+            free_bytes -= need + waste;
+            used[q] = need + waste;
+            // ---- descriptor
+            PfUnit* d = desc + q;
+            if (lane < HTD_MAX_POOLED) {
+                d->dx0[lane] = cx0 - bz;
+                d->nx[lane] = live ? cx1 - cx0 + 1 : 0;
+            }
+            if (lane == 0) {
+                d->valid = live;
+                d->direct = direct;
+                d->buf_off = buf;
+                d->ny = ny; d->nxs = nxs; d->b = b; d->W = W;
+                d->wy_off = buf + (int)strip;
+                d->wx_off = buf + (int)strip + ny * kTabW * 4;
+                d->out_off = ((long long)task * PP + (long long)ph * P) * p.C;
+                d->gsrc = live ? static_cast<const void*>(static_cast<const TIn*>(p.lv[l].data) +
+                                                          (((size_t)b * H + ry0) * W + bz) * p.C)
+                               : nullptr;
+            }
+            __syncwarp();
+            if (!live) {
+                if (lane == 0) mbar_arrive(full_bar + q);
+                continue;
+            }
+            if (lane == 0) {
+                mbar_expect_tx(full_bar + q, (uint32_t)need);
+                bulk_g2s(ringb + d->wy_off, p.weights + (off + (size_t)(ry0 - bx)) * kTabW,
+                         (uint32_t)(ny * kTabW * 4), full_bar + q);
+                bulk_g2s(ringb + d->wx_off, p.weights + (off + (size_t)fh) * kTabW,
+                         (uint32_t)(nxs * kTabW * 4), full_bar + q);
+            }
+            __syncwarp();
+            if (!direct) {
+                const TIn* src = static_cast<const TIn*>(p.lv[l].data) + (((size_t)b * H + ry0) * W + bz) * p.C;
+                for (int r = lane; r < ny; r += 32)
+                    bulk_g2s(ringb + buf + (size_t)r * row_bytes, src + (size_t)r * W * p.C,
+                             (uint32_t)row_bytes, full_bar + q);
+            }
+        }
+    } else if (warp < P) {
+        // ===== consumers: bin (ph, pw = warp) of every unit =====
+        const int pw = warp;
+        const bool lane_on = lane * 8 < p.C;
+        long long i = 0;
+        for (long long u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+            const int q = (int)(i % kPfUnits);
+            mbar_wait(full_bar + q, (uint32_t)(i / kPfUnits) & 1u);
+            const PfUnit* d = desc + q;
+            float acc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+            const int b = d->b;
+            if (d->valid) {
+                const int ny = d->ny, nxs = d->nxs, nx = d->nx[pw], dx0 = d->dx0[pw];
+                const float* ty = reinterpret_cast<const float*>(ringb + d->wy_off) + (int)(u % P);
+                const float* tx = reinterpret_cast<const float*>(ringb + d->wx_off) + (size_t)dx0 * kTabW + pw;
+                if (nx > 0 && lane_on) {
+                    if (!d->direct) {
+                        const TIn* sb = reinterpret_cast<const TIn*>(ringb + d->buf_off) + (size_t)dx0 * p.C + lane * 8;
+                        for (int y = 0; y < ny; ++y) {
+                            const float wyv = ty[(size_t)y * kTabW];
+                            if (wyv == 0.f) continue;
+                            const TIn* src = sb + (size_t)y * nxs * p.C;
+                            for (int x = 0; x < nx; ++x) {
+                                const float w = wyv * tx[(size_t)x * kTabW];
+                                float v[8];
+                                ld_smem8<TIn>(src + (size_t)x * p.C, v);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+                            }
+                        }
+                    } else {
+                        const TIn* gb = static_cast<const TIn*>(d->gsrc) + (size_t)dx0 * p.C + lane * 8;
+                        for (int y = 0; y < ny; ++y) {
+                            const float wyv = ty[(size_t)y * kTabW];
+                            if (wyv == 0.f) continue;
+                            const TIn* src = gb + (size_t)y * d->W * p.C;
+                            for (int x = 0; x < nx; ++x) {
+                                const float w = wyv * tx[(size_t)x * kTabW];
+                                float v[8];
+                                ld_smem8<TIn>(src + (size_t)x * p.C, v);      // plain vector load
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, v[e], acc[e]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (p.bias && b >= 0 && b < p.B) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = lane * 8 + e;
+                    if (c < p.C) acc[e] += __ldg(p.bias + (size_t)b * p.C + c);
+                }
+            }
+            TOut* orow = static_cast<TOut*>(p.out) + d->out_off + (size_t)pw * p.C;
+            Vec8<TOut, false>::store(orow, lane, p.C, acc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + q);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
 struct BwdSource {                   // one extractor call whose gradient lands in dX
@@ -1324,6 +1528,32 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     dim3 grid((unsigned)blocks), block(pooled * 32);
     cudaStream_t st = (cudaStream_t)stream;
     const int cw = C < 256 ? C : 256;
+    // level-assigned extraction (SingleRoIExtractor): every strip is small - persistent CTAs with a
+    // producer warp that prefetches several work units ahead (HTD_FWD_KERNEL=cta keeps the
+    // CTA-per-strip kernel for measurements)
+    static int persist_on = -1;
+    if (persist_on < 0) {
+        const char* ev = getenv("HTD_FWD_KERNEL");
+        persist_on = (ev && (!strcmp(ev, "cta") || !strcmp(ev, "ring"))) ? 0 : 1;
+    }
+    if (persist_on && roi_level != nullptr && pooled < HTD_MAX_POOLED && C <= 256) {
+        const int sms = sm_count();
+        const unsigned pgrid = (unsigned)(blocks < sms ? blocks : sms);
+        p.region = 0;
+        p.strip = 1;
+#define HTD_FWDP_LAUNCH(TI, TO)                                                                   \
+    do {                                                                                          \
+        HTD_SMEM_OPTIN((roi_align_fwd_persist_kernel<TI, TO>), kPfSmem, "htd_roi_align_fwd");     \
+        roi_align_fwd_persist_kernel<TI, TO><<<pgrid, HTD_MAX_POOLED * 32, kPfSmem, st>>>(p, blocks); \
+    } while (0)
+        if (in_dtype == HTD_F32 && out_dtype == HTD_F32) HTD_FWDP_LAUNCH(float, float);
+        else if (in_dtype == HTD_F32 && out_dtype == HTD_BF16) HTD_FWDP_LAUNCH(float, __nv_bfloat16);
+        else if (in_dtype == HTD_BF16 && out_dtype == HTD_F32) HTD_FWDP_LAUNCH(__nv_bfloat16, float);
+        else HTD_FWDP_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+#undef HTD_FWDP_LAUNCH
+        HTD_CHECK_LAUNCH("htd_roi_align_fwd(persistent)");
+        return HTD_OK;
+    }
     // staging region: the per-warp rings, or at least kFwdStripBytes for the strip path (three CTAs
     // of 72 KB + barriers per SM); HTD_FWD_KERNEL=ring switches the strip path off (measurements)
     static int strip_on = -1;

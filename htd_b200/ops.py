@@ -357,18 +357,19 @@ def _fwd_launch(name, feats, scales, rois, roi_level, pooled, sampling_ratio, bi
     L, K = len(feats), rois.shape[0]
     B, C = feats[0].shape[0], feats[0].shape[1]
     lv = _lib.make_levels([_bhwc(f) for f in feats], scales)
-    if plan is None:
-        with _lib.timed('roi_plan'):
-            plan = RoIPlan(feats, scales, rois, roi_level, pooled, sampling_ratio)
-    if _lib.ACCOUNT is not None:      # fh*fw*C*b_in + 49*C*b_out + 20 per (RoI, level)
-        tasks = K if roi_level is not None else K * L
-        _lib.ACCOUNT.append((name, plan.pixels() * C * feats[0].element_size() +
-                             out.numel() * out.element_size() + 20 * tasks))
+    # the plan (footprints, scan, axis-weight tables) is part of the extraction: it is timed under
+    # the same name as the gather it serves
     with _lib.timed(name):
+        if plan is None:
+            plan = RoIPlan(feats, scales, rois, roi_level, pooled, sampling_ratio)
         check(lib().htd_roi_align_fwd(lv, L, B, C, dt(feats[0]), ptr(rois), K, ptr(roi_level),
                                       pooled, ptr(plan.boxes), ptr(plan.offsets), ptr(plan.ranges),
                                       ptr(plan.weights), ptr(bias_c), ptr(out), dt(out), stream()),
               'htd_roi_align_fwd')
+    if _lib.ACCOUNT is not None:      # fh*fw*C*b_in + 49*C*b_out + 20 per (RoI, level)
+        tasks = K if roi_level is not None else K * L
+        _lib.ACCOUNT.append((name, plan.pixels() * C * feats[0].element_size() +
+                             out.numel() * out.element_size() + 20 * tasks))
     return plan
 
 
