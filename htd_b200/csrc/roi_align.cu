@@ -520,14 +520,21 @@ __global__ void __launch_bounds__((HTD_MAX_POOLED) * 32, 1) roi_align_fwd_persis
             const int need = (int)strip + tab_bytes;         // multiple of 16
             // ---- ring space: units are released in order
             int waste = 0;
-            if (head + need > kPfRingBytes) waste = kPfRingBytes - head;
-            while (oldest + kPfUnits <= i || free_bytes < need + waste) {
+            bool wrap = false;
+            for (;;) {
+                wrap = head + need > kPfRingBytes;
+                waste = wrap ? kPfRingBytes - head : 0;
+                if (oldest + kPfUnits > i && free_bytes >= need + waste) break;
+                if (oldest == i) {           // ring drained: restart at its beginning (need <= ring)
+                    head = 0;
+                    continue;
+                }
                 const int oq = (int)(oldest % kPfUnits);
                 mbar_wait(empty_bar + oq, (uint32_t)(oldest / kPfUnits) & 1u);
                 free_bytes += used[oq];
                 ++oldest;
             }
-            if (waste) head = 0;
+            if (wrap) head = 0;
             const int buf = head;
             head += need;
             free_bytes -= need + waste;

@@ -93,3 +93,41 @@ def test_emu_levels_match_golden(emu):
     out = torch.empty(rois.shape[0], dtype=torch.int32)
     emu.emu_levels(_p(rois), rois.shape[0], 4, ctypes.c_float(56.0), _p(out))
     assert np.array_equal(out.numpy().astype(np.int8), z['levels'])
+
+
+def test_forward_ring_allocator_never_overlaps_or_stalls():
+    """Host model of the byte-ring carve-out of roi_align_fwd_persist_kernel's producer warp
+    (csrc/roi_align.cu): strips of arbitrary sizes (empty units, strips larger than half the ring)
+    never overlap a strip that is still in flight, never exceed the ring, and the producer never
+    waits for space that cannot appear (units are released in order)."""
+    import random
+    CAP, Q = 200 * 1024, 8
+    rnd = random.Random(0)
+    for _ in range(1500):
+        needs = [rnd.choice([0, 16 * rnd.randint(1, 800), 16 * rnd.randint(4000, 12800),
+                             16 * rnd.randint(1, 3000)]) for _ in range(rnd.randint(1, 80))]
+        head, free, oldest, used, live = 0, CAP, 0, [0] * Q, []
+        for i, need in enumerate(needs):
+            spins = 0
+            while True:
+                wrap = head + need > CAP
+                waste = CAP - head if wrap else 0
+                if oldest + Q > i and free >= need + waste:
+                    break
+                if oldest == i:
+                    head = 0
+                    spins += 1
+                    assert spins < 3
+                    continue
+                free += used[oldest % Q]
+                live.pop(0)
+                oldest += 1
+            if wrap:
+                head = 0
+            buf = head
+            head += need
+            free -= need + waste
+            used[i % Q] = need + waste
+            assert buf + need <= CAP and free >= 0
+            assert all(not (buf < b and a < buf + need) for a, b in live)
+            live.append((buf, buf + need))
