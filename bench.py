@@ -238,6 +238,63 @@ def _median_ms(fn, iters, flush):
     return ts[len(ts) // 2]
 
 
+def gather_kernel_times(dev, flush):
+    """Device time of the three gather launches of a step at the bench size (2 x 512 RoIs, 128
+    positives / image, bf16), each captured in a small CUDA graph and replayed with a cold L2 -
+    eager event timing of these launches is dominated by host launch gaps (the plan is three tiny
+    kernels).  forward figures include the sampling plan (footprints, scan, axis-weight tables)."""
+    import torch
+    from htd_b200 import ops, synth
+    scales = [0.25, 0.125, 0.0625, 0.03125]
+    C = 256
+    x = [ops.to_channels_last(t.to(dev), torch.bfloat16) for t in synth.make_pyramid(IMGS)[:4]]
+    shapes = [tuple(t.shape) for t in x]
+    props = synth.make_proposals(IMGS, ROIS)
+    rois = torch.cat([torch.cat([p.new_full((p.size(0), 1), i), p], 1) for i, p in enumerate(props)]).to(dev)
+    pos = torch.cat([torch.cat([p.new_full((POS, 1), i), p[:POS]], 1) for i, p in enumerate(props)]).to(dev)
+    lv = ops.level_assign(rois, 4)
+    K, P = rois.shape[0], pos.shape[0]
+    out = torch.empty(K, 7, 7, C, device=dev, dtype=torch.bfloat16)
+    outb = torch.empty(4, P, 7, 7, C, device=dev, dtype=torch.bfloat16)
+    plan = ops.RoIPlan(x, scales, rois, lv, 7, 0)
+    planb = ops.RoIPlan(x, scales, pos, None, 7, 0)
+    g = torch.randn(K, 7, 7, C, device=dev).to(torch.bfloat16)
+    gp = torch.randn(P, 7, 7, C, device=dev).to(torch.bfloat16)
+    wts = torch.rand(4, P, device=dev)
+    dm = torch.randn(4 * P, C, device=dev)
+    srcs = [dict(rois=rois, plan=plan.tensors(), dy=g, dy_per_level=False),
+            dict(rois=rois, plan=plan.tensors(), dy=g, dy_per_level=False),
+            dict(rois=pos, plan=planb.tensors(), dy=gp, dy_per_level=False, scale=wts, ring_edge=1,
+                 addvec=dm)]
+
+    def fwd_single():
+        pl = ops.RoIPlan(x, scales, rois, lv, 7, 0)
+        ops._fwd_launch('f', x, scales, rois, lv, 7, 0, None, out, plan=pl)
+
+    def fwd_ba():
+        pl = ops.RoIPlan(x, scales, pos, None, 7, 0)
+        ops._fwd_launch('f', x, scales, pos, None, 7, 0, None, outb, plan=pl)
+
+    def bwd_fused():
+        ops._bwd_multi(shapes, torch.bfloat16, False, scales, srcs, 7)
+
+    res = {}
+    for name, fn in (('roi_align_fwd(single)', fwd_single), ('roi_align_fwd(BA)', fwd_ba),
+                     ('roi_align_bwd(fused)', bwd_fused)):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        res[name] = _median_ms(gr.replay, 15, flush)
+    return res
+
+
 def pgraph_tensor_roofline(dev, flush):
     """The PGraph aggregation contraction A[n,n] x X[n,1024] (htd_bbox_head.py:213,216) of ONE dense
     group of n RoIs (BASELINE config 4 stress) on the tcgen05 kernel: 2 n^2 d flops / CUDA-event
@@ -697,6 +754,16 @@ def run_gpu(args):
             head.train()
             print(f'[bench] inference figure failed ({type(e).__name__}: {e})', file=sys.stderr)
 
+    # ---- device times of the gather launches (plan included), CUDA-graph replays ---------------
+    gtimes = None
+    if dtype == torch.bfloat16 and imgs == IMGS:
+        try:
+            fl_ = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+            gtimes = gather_kernel_times(dev, fl_)
+            del fl_
+        except Exception as e:
+            print(f'[bench] gather_kernel_times failed ({type(e).__name__}: {e})', file=sys.stderr)
+
     # ---- north_star evidence in the driver-visible line (N = 1 only) ----------------------------
     roofline_tensor = sweep = comparator = None
     if world == 1 and not args.no_static and imgs == IMGS:
@@ -735,7 +802,20 @@ def run_gpu(args):
         gbs = total_bytes / (tot_ms * 1e-3) / 1e9
         kernels[name] = dict(launches=n, avg_ms=tot_ms / n, alg_MB_per_launch=sum(per_step) / len(per_step) / 1e6,
                              achieved_GBs=gbs, frac=gbs / hbm_peak,
-                             share_of_step=(tot_ms / ksteps) / (ms / args.steps))
+                             share_of_step=(tot_ms / ksteps) / (ms / args.steps),
+                             timing='CUDA events around the launch in an eager pass of the step')
+        if gtimes and name in gtimes:
+            # device time of plan + gather from a CUDA-graph replay with a cold L2 (the eager figure
+            # above is dominated by host launch gaps between the plan's three small kernels)
+            k_ = kernels[name]
+            per_launch = sum(per_step) / len(per_step)
+            launches_per_step = len(per_step)
+            k_.update(eager_avg_ms=k_['avg_ms'], avg_ms=gtimes[name],
+                      achieved_GBs=per_launch / (gtimes[name] * 1e-3) / 1e9,
+                      frac=per_launch / (gtimes[name] * 1e-3) / 1e9 / hbm_peak,
+                      share_of_step=gtimes[name] * launches_per_step / (ms / args.steps),
+                      timing='CUDA-graph replay of the launch (forward: sampling plan included), '
+                             'L2 flushed before every replay, median of 15')
     # own dense tcgen05 kernels (FC stacks, conv tower): flops / event time / measured bf16 peak
     dense_kernels = {}
     for name, (n, tot_ms) in ksum.items():
