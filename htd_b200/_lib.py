@@ -133,7 +133,7 @@ SIGNATURES = {
 _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_dual_gate': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 3,
+KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_dual_gate': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 1,
                     'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2, 'htd_multiclass_nms': 4}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 

@@ -196,6 +196,84 @@ __global__ void __launch_bounds__(128) weight_table_kernel(const TableParams p) 
     }
 }
 
+// The whole plan in ONE launch (htd_roi_plan when no pixel count is requested): a CTA per entry
+// (level, RoI) computes the footprint box, the per-bin pixel ranges and both axis-weight tables.
+// Table rows sit at a fixed stride per entry - offsets[e] = K * (rows of the lower levels) +
+// k * (H_l + W_l), or k * max_l (H_l + W_l) for a level-assigned extraction - inside the capacity
+// htd_roi_plan_rows_bound already reserves, so no prefix scan (and no second and third launch:
+// 0.042 ms of 0.12 ms for the single-level extraction at the bench size) is needed.
+struct PlanParams {
+    LevelDev lv[HTD_MAX_LEVELS];
+    int L, B, K, P, sr;
+    int base[HTD_MAX_LEVELS];     // table rows before level l's block (all-level mode)
+    int ext[HTD_MAX_LEVELS];      // H_l + W_l
+    int ext_max;
+    const float* rois;
+    const int* roi_level;
+    int4* boxes;
+    int* offsets;
+    int* ranges;
+    float* weights;
+};
+
+__global__ void __launch_bounds__(128) roi_plan_fused_kernel(const PlanParams p) {
+    __shared__ Axis s_axis[2];
+    __shared__ int s_box[4];
+    const int e = blockIdx.x, tid = threadIdx.x;
+    const int l = e / p.K, k = e % p.K;
+    const float* r = p.rois + (size_t)k * 5;
+    const int b = (int)r[0];
+    const bool on = ((p.roi_level == nullptr) || (p.roi_level[k] == l)) && b >= 0 && b < p.B;
+    int* rg = p.ranges + (size_t)e * kRangeInts;
+    const int off = p.roi_level ? k * p.ext_max : p.K * p.base[l] + k * p.ext[l];
+    if (tid == 0) p.offsets[e] = off;
+    if (e == 0 && tid == 1)
+        p.offsets[p.L * p.K] = p.roi_level ? p.K * p.ext_max : p.K * (p.base[p.L - 1] + p.ext[p.L - 1]);
+    if (on) {
+        if (tid == 0) {
+            s_axis[0] = make_axis(r[2], r[4], (double)p.lv[l].scale, p.P, p.lv[l].H, p.sr, 1);
+            roi_range(s_axis[0], p.P, s_box[0], s_box[1]);
+        }
+        if (tid == 32) {
+            s_axis[1] = make_axis(r[1], r[3], (double)p.lv[l].scale, p.P, p.lv[l].W, p.sr, 1);
+            roi_range(s_axis[1], p.P, s_box[2], s_box[3]);
+        }
+    }
+    __syncthreads();
+    int4 box = make_int4(0, -1, 0, -1);
+    if (on && s_box[1] >= s_box[0] && s_box[3] >= s_box[2])
+        box = make_int4(s_box[0], s_box[1], s_box[2], s_box[3]);
+    if (tid == 0) p.boxes[e] = box;
+    if (box.y < box.x || box.w < box.z) {           // RoI does not touch this level
+        if (tid < kRangeInts) rg[tid] = (tid / HTD_MAX_POOLED) % 2 == 0 ? 0 : -1;
+        return;
+    }
+    if (tid < 2 * HTD_MAX_POOLED) {                 // per-bin pixel ranges
+        const int axis = tid / HTD_MAX_POOLED, pp = tid % HTD_MAX_POOLED;
+        int lo = 0, hi = -1;
+        if (pp < p.P) bin_range(s_axis[axis], pp, lo, hi);
+        rg[axis * 2 * HTD_MAX_POOLED + pp] = lo;
+        rg[axis * 2 * HTD_MAX_POOLED + HTD_MAX_POOLED + pp] = hi;
+    }
+    const int fh = box.y - box.x + 1, fw = box.w - box.z + 1;
+    float* tab = p.weights + (size_t)off * kTabW;
+    const int n = (fh + fw) * kTabW;
+    for (int base = 0; base < n; base += blockDim.x) {      // uniform trip count: shuffles below
+        const int i = base + tid;
+        const int row = i / kTabW, pp = i % kTabW;
+        float w = 0.f;
+        if (i < n && pp < p.P)
+            w = row < fh ? axis_weight(s_axis[0], pp, box.x + row)
+                         : axis_weight(s_axis[1], pp, box.z + (row - fh));
+        float sum = w;                                      // see weight_table_kernel
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        if (p.P < kTabW && pp == kTabW - 1) w = sum;
+        if (i < n) tab[i] = w;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
@@ -449,6 +527,9 @@ __global__ void __launch_bounds__(HTD_MAX_POOLED * 32) roi_align_fwd_kernel(cons
 // paths above, so results are bit-identical.  A strip that does not fit the ring (never the case
 // for a level-assigned RoI of an 800x1333 image) is reduced straight from global memory.
 constexpr int kPfUnits = 8;                      // descriptor ring (units in flight)
+constexpr int kPfGroups = 3;                     // consumer groups of P warps: units i, i+1, i+2 are reduced concurrently
+                                                 // (one group alone leaves the SM's schedulers idle: 7 warps
+                                                 // of dependent shared-load -> fma chains reached 0.095 ms)
 constexpr int kPfRingBytes = 200 * 1024;         // staging ring
 struct PfUnit {
     int valid, direct, buf_off, ny, nxs, b, wy_off, wx_off, W;
@@ -459,7 +540,7 @@ struct PfUnit {
 constexpr int kPfSmem = kPfRingBytes + kPfUnits * (int)sizeof(PfUnit) + 2 * kPfUnits * 8 + 16;
 
 template <typename TIn, typename TOut>
-__global__ void __launch_bounds__((HTD_MAX_POOLED) * 32, 1) roi_align_fwd_persist_kernel(const FwdParams p,
+__global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1) roi_align_fwd_persist_kernel(const FwdParams p,
                                                                                          long long units) {
     extern __shared__ __align__(128) uint8_t pf_smem[];
     uint8_t* ringb = pf_smem;
@@ -476,7 +557,7 @@ __global__ void __launch_bounds__((HTD_MAX_POOLED) * 32, 1) roi_align_fwd_persis
         fence_mbar_init();
     }
     __syncthreads();
-    if (warp == P) {
+    if (warp == kPfGroups * P) {
         // ===== producer =====
         int head = 0, free_bytes = kPfRingBytes;
         long long oldest = 0;                        // local index of the oldest unreleased unit
@@ -577,12 +658,13 @@ __global__ void __launch_bounds__((HTD_MAX_POOLED) * 32, 1) roi_align_fwd_persis
                              (uint32_t)row_bytes, full_bar + q);
             }
         }
-    } else if (warp < P) {
-        // ===== consumers: bin (ph, pw = warp) of every unit =====
-        const int pw = warp;
+    } else if (warp < kPfGroups * P) {
+        // ===== consumers: group g reduces the units i = g, g + G, ...; a warp = one bin (ph, pw) =====
+        const int pw = warp % P, grp = warp / P;
         const bool lane_on = lane * 8 < p.C;
-        long long i = 0;
-        for (long long u = blockIdx.x; u < units; u += gridDim.x, ++i) {
+        long long i = grp;
+        for (long long u = blockIdx.x + (long long)grp * gridDim.x; u < units;
+             u += (long long)kPfGroups * gridDim.x, i += kPfGroups) {
             const int q = (int)(i % kPfUnits);
             mbar_wait(full_bar + q, (uint32_t)(i / kPfUnits) & 1u);
             const PfUnit* d = desc + q;
@@ -601,6 +683,7 @@ __global__ void __launch_bounds__((HTD_MAX_POOLED) * 32, 1) roi_align_fwd_persis
                             const float wyv = ty[(size_t)y * kTabW];
                             if (wyv == 0.f) continue;
                             const TIn* src = sb + (size_t)y * nxs * p.C;
+#pragma unroll 4
                             for (int x = 0; x < nx; ++x) {
                                 const float w = wyv * tx[(size_t)x * kTabW];
                                 float v[8];
@@ -1483,8 +1566,36 @@ int htd_roi_plan(const HtdLevel* levels, int L, int B, const float* rois, int K,
                  const int32_t* roi_level, int pooled, int sampling_ratio, int32_t* boxes,
                  int32_t* offsets, int32_t* ranges, float* weights, long long rows_cap,
                  unsigned long long* pixel_count, htd_stream_t stream) {
-    int rc = htd_roi_footprints(levels, L, B, rois, K, roi_level, pooled, sampling_ratio, boxes,
-                                pixel_count, stream);
+    int rc;
+    if (pixel_count == nullptr && K > 0) {
+        // one launch: boxes, offsets (fixed stride), ranges and tables
+        HTD_CHECK_ARG(levels && L >= 1 && L <= HTD_MAX_LEVELS && B >= 1 && rois && boxes && offsets &&
+                          ranges && weights && pooled >= 1 && pooled <= HTD_MAX_POOLED,
+                      "htd_roi_plan: bad arguments");
+        const long long need1 = htd_roi_plan_rows_bound(levels, L, K, roi_level != nullptr);
+        HTD_CHECK_ARG(rows_cap >= need1, "htd_roi_plan: weight table capacity %lld rows < bound %lld",
+                      rows_cap, need1);
+        HTD_CHECK_ARG(need1 < 2147483647LL && (long long)L * K < 2147483647LL, "htd_roi_plan: table too large");
+        PlanParams q;
+        rc = fill_levels(q.lv, levels, L, "htd_roi_plan");
+        if (rc) return rc;
+        q.L = L; q.B = B; q.K = K; q.P = pooled; q.sr = sampling_ratio;
+        int acc = 0, mx = 0;
+        for (int l = 0; l < L; ++l) {
+            q.base[l] = acc;
+            q.ext[l] = levels[l].H + levels[l].W;
+            acc += q.ext[l];
+            if (q.ext[l] > mx) mx = q.ext[l];
+        }
+        q.ext_max = mx;
+        q.rois = rois; q.roi_level = roi_level; q.boxes = reinterpret_cast<int4*>(boxes);
+        q.offsets = offsets; q.ranges = ranges; q.weights = weights;
+        roi_plan_fused_kernel<<<L * K, 128, 0, (cudaStream_t)stream>>>(q);
+        HTD_CHECK_LAUNCH("htd_roi_plan(fused)");
+        return HTD_OK;
+    }
+    rc = htd_roi_footprints(levels, L, B, rois, K, roi_level, pooled, sampling_ratio, boxes,
+                            pixel_count, stream);
     if (rc) return rc;
     if (K == 0) return HTD_OK;
     HTD_CHECK_ARG(offsets && ranges && weights, "htd_roi_plan: null pointer");
@@ -1551,7 +1662,7 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
 #define HTD_FWDP_LAUNCH(TI, TO)                                                                   \
     do {                                                                                          \
         HTD_SMEM_OPTIN((roi_align_fwd_persist_kernel<TI, TO>), kPfSmem, "htd_roi_align_fwd");     \
-        roi_align_fwd_persist_kernel<TI, TO><<<pgrid, HTD_MAX_POOLED * 32, kPfSmem, st>>>(p, blocks); \
+        roi_align_fwd_persist_kernel<TI, TO><<<pgrid, (kPfGroups * pooled + 1) * 32, kPfSmem, st>>>(p, blocks); \
     } while (0)
         if (in_dtype == HTD_F32 && out_dtype == HTD_F32) HTD_FWDP_LAUNCH(float, float);
         else if (in_dtype == HTD_F32 && out_dtype == HTD_BF16) HTD_FWDP_LAUNCH(float, __nv_bfloat16);

@@ -84,7 +84,9 @@ int htd_roi_footprints(const HtdLevel* levels, int L, int B, const float* rois, 
 
 /* Sampling plan shared by forward and backward, built once per extractor call:
  *   boxes   [L*K][4]  footprint boxes as in htd_roi_footprints;
- *   offsets [L*K+1]   exclusive scan of (fh + fw) over the entries e = l*K + k (table row offsets);
+ *   offsets [L*K+1]   first table row of entry e = l*K + k (its fh + fw rows follow); entries sit at a
+ *                     fixed stride inside the htd_roi_plan_rows_bound capacity (one launch, no scan) -
+ *                     or densely packed (exclusive scan) when a pixel count is requested;
  *   ranges  [L*K][4*HTD_MAX_POOLED]  per output bin p: first/last feature row (y lo[8], y hi[8]) and
  *                     column (x lo[8], x hi[8]) it samples (hi < lo: empty bin);
  *   weights [rows_cap][HTD_MAX_POOLED] fp32 separable axis weights: row offsets[e] + (r - row0)
