@@ -28,30 +28,178 @@ __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Two forms, both reading and writing global memory in 16-byte vectors where the shape allows:
+//  * whole-matrix form (R*S <= kFlatMax): one CTA owns one [R,S] matrix; the source is read as a
+//    flat vector stream into a padded fp32 tile, re-read along R, packed into a flat image of
+//    the destination in shared memory and written out as a flat vector stream. This is the
+//    [P,49,C] <-> [P,C,49] flatten-order change of the pooled RoI maps (49 is odd, so neither
+//    side has vectorisable rows; the flat image is what makes both sides 16-byte traffic).
+//  * tiled form: 64 x 64 tiles, vector width chosen per side from the divisibility of S / R.
+//    This is the NCHW <-> NHWC pyramid conversion (R = 256 channels, S = H*W).
+constexpr int kFlatMax = 12800;   // elements: 49*256 = 12544 and a little slack
+
+template <typename T, int V>
+__device__ __forceinline__ void ldvec(const T* p, float (&v)[V]) {
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (V == 8) {
+            const float4 a = *reinterpret_cast<const float4*>(p);
+            const float4 b = *reinterpret_cast<const float4*>(p + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else if constexpr (V == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(p);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        } else if constexpr (V == 2) {
+            const float2 a = *reinterpret_cast<const float2*>(p);
+            v[0] = a.x; v[1] = a.y;
+        } else {
+            v[0] = p[0];
+        }
+    } else {
+        if constexpr (V == 8) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p);
+            const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[2 * i] = __uint_as_float(w[i] << 16);
+                v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            }
+        } else if constexpr (V == 4) {
+            const uint2 a = *reinterpret_cast<const uint2*>(p);
+            v[0] = __uint_as_float(a.x << 16); v[1] = __uint_as_float(a.x & 0xffff0000u);
+            v[2] = __uint_as_float(a.y << 16); v[3] = __uint_as_float(a.y & 0xffff0000u);
+        } else if constexpr (V == 2) {
+            const uint32_t a = *reinterpret_cast<const uint32_t*>(p);
+            v[0] = __uint_as_float(a << 16); v[1] = __uint_as_float(a & 0xffff0000u);
+        } else {
+            v[0] = to_f<T>(p[0]);
+        }
+    }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void stvec(T* p, const float (&v)[V]) {
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (V == 8) {
+            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else if constexpr (V == 4) {
+            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        } else if constexpr (V == 2) {
+            *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+        } else {
+            p[0] = v[0];
+        }
+    } else {
+        if constexpr (V == 1) {
+            p[0] = from_f<T>(v[0]);
+        } else {
+            uint32_t w[V / 2];
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            if constexpr (V == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+            else if constexpr (V == 4) *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+            else *reinterpret_cast<uint32_t*>(p) = w[0];
+        }
+    }
+}
+
+// whole-matrix form; dynamic shared memory = R*pitch source elements (pitch odd: the column walk
+// of the second phase then spreads over the banks) + R*S destination elements
 template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_flat_kernel(const TS* __restrict__ src,
+                                                             TD* __restrict__ dst, int R, int S,
+                                                             int pitch, int image_off) {
+    extern __shared__ __align__(16) unsigned char tr_smem[];
+    TS* tile = reinterpret_cast<TS*>(tr_smem);
+    TD* image = reinterpret_cast<TD*>(tr_smem + image_off);
+    const int E = R * S;                       // multiple of 8 (checked on the host)
+    const TS* s = src + (size_t)blockIdx.x * E;
+    TD* d = dst + (size_t)blockIdx.x * E;
+    constexpr int VL = 16 / (int)sizeof(TS);
+    // four 16-byte loads in flight per thread before the first of them is scattered into the tile
+    for (int i0 = threadIdx.x * VL; i0 < E; i0 += 4 * 256 * VL) {
+        uint4 raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * 256 * VL;
+            if (i < E) raw[k] = *reinterpret_cast<const uint4*>(s + i);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * 256 * VL;
+            if (i < E) {
+                const TS* e = reinterpret_cast<const TS*>(&raw[k]);
+                int r = i / S, c = i - r * S;
+#pragma unroll
+                for (int j = 0; j < VL; ++j) {
+                    tile[r * pitch + c] = e[j];
+                    if (++c == S) { c = 0; ++r; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // destination flat index o = c*R + r: consecutive lanes walk r, i.e. tile rows `pitch` apart;
+    // (c, r) advance by 256 flat positions per trip without a division
+    {
+        const int dc = 256 / R, dr = 256 - dc * R;
+        int c = threadIdx.x / R, r = threadIdx.x - c * R;
+#pragma unroll 4
+        for (int o = threadIdx.x; o < E; o += 256) {
+            image[o] = from_f<TD>(to_f<TS>(tile[r * pitch + c]));
+            c += dc;
+            r += dr;
+            if (r >= R) { r -= R; ++c; }
+        }
+    }
+    __syncthreads();
+    constexpr int VB = 16 / (int)sizeof(TD);
+    for (int i = threadIdx.x * VB; i < E; i += 256 * VB)
+        *reinterpret_cast<uint4*>(d + i) = *reinterpret_cast<const uint4*>(image + i);
+}
+
+// tiled form
+template <typename TS, typename TD, int VL, int VS>
 __global__ void __launch_bounds__(256) transpose_kernel(const TS* __restrict__ src,
                                                         TD* __restrict__ dst, long long N, int R,
                                                         int S, int tiles_r, int tiles_s) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[64][65];
     long long blk = blockIdx.x;
     const int ts = (int)(blk % tiles_s);
     blk /= tiles_s;
     const int tr = (int)(blk % tiles_r);
     const long long n = blk / tiles_r;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const TS* s = src + (size_t)n * R * S;
     TD* d = dst + (size_t)n * R * S;
-    const int r0 = tr * 32, s0 = ts * 32;
+    const int r0 = tr * 64, s0 = ts * 64;
+    constexpr int LV = 64 / VL;                // vectors per tile row on the load side
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = r0 + ty + i * 8, c = s0 + tx;
-        if (r < R && c < S) tile[ty + i * 8][tx] = to_f<TS>(s[(size_t)r * S + c]);
+    for (int i = threadIdx.x; i < 64 * LV; i += 256) {
+        const int rr = i / LV, cv = (i - rr * LV) * VL;
+        const int r = r0 + rr, c = s0 + cv;
+        if (r < R && c < S) {                  // S % VL == 0: a vector never straddles the edge
+            float v[VL];
+            ldvec<TS, VL>(s + (size_t)r * S + c, v);
+#pragma unroll
+            for (int j = 0; j < VL; ++j) tile[rr][cv + j] = v[j];
+        }
     }
     __syncthreads();
+    constexpr int SV = 64 / VS;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = s0 + ty + i * 8, r = r0 + tx;
-        if (r < R && c < S) d[(size_t)c * R + r] = from_f<TD>(tile[tx][ty + i * 8]);
+    for (int i = threadIdx.x; i < 64 * SV; i += 256) {
+        const int cc = i / SV, rv = (i - cc * SV) * VS;
+        const int c = s0 + cc, r = r0 + rv;
+        if (c < S && r < R) {
+            float v[VS];
+#pragma unroll
+            for (int j = 0; j < VS; ++j) v[j] = tile[rv + j][cc];
+            stvec<TD, VS>(d + (size_t)c * R + r, v);
+        }
     }
 }
 
@@ -247,15 +395,51 @@ int htd_layout_convert(const void* src, int src_dtype, void* dst, int dst_dtype,
     HTD_CHECK_ARG(N >= 0 && R >= 1 && S >= 1, "htd_layout_convert: bad sizes");
     if (N == 0) return HTD_OK;
     HTD_CHECK_ARG(src && dst, "htd_layout_convert: null pointer");
-    const int tr = (R + 31) / 32, ts = (S + 31) / 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t es = src_dtype == HTD_F32 ? 4 : 2, ed = dst_dtype == HTD_F32 ? 4 : 2;
+    const long long E = (long long)R * S;
+    const bool aligned16 = ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    // whole-matrix form: an odd row length keeps the column walk conflict free as it is
+    const int pitch = (S & 1) ? S : S + 1;
+    const size_t image_off = ((size_t)R * pitch * es + 15) & ~(size_t)15;
+    const size_t smem = image_off + (size_t)E * ed;
+    if (E <= kFlatMax && E % 8 == 0 && aligned16 && smem <= 100 * 1024 && N < 2147483647LL) {
+#define CALL(TS, TD)                                                                          \
+    do {                                                                                      \
+        HTD_SMEM_OPTIN((transpose_flat_kernel<TS, TD>), 100 * 1024, "htd_layout_convert");    \
+        transpose_flat_kernel<TS, TD><<<(unsigned)N, 256, smem, st>>>(                        \
+            static_cast<const TS*>(src), static_cast<TD*>(dst), R, S, pitch, (int)image_off); \
+    } while (0)
+        DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+        HTD_CHECK_LAUNCH("htd_layout_convert");
+        return HTD_OK;
+    }
+    const int tr = (R + 63) / 64, ts = (S + 63) / 64;
     const long long blocks = N * tr * ts;
     HTD_CHECK_ARG(blocks < 2147483647LL, "htd_layout_convert: tensor too large");
-    cudaStream_t st = (cudaStream_t)stream;
-#define CALL(TS, TD)                                                                          \
-    transpose_kernel<TS, TD><<<(unsigned)blocks, 256, 0, st>>>(static_cast<const TS*>(src),   \
-                                                               static_cast<TD*>(dst), N, R, S, tr, ts)
+    // widest vector each side allows: rows of the source are S long, rows of the destination R
+    // long, and every matrix starts E elements after the previous one
+    auto width = [&](int row, size_t esz, const void* base) {
+        int v = (int)(16 / esz);
+        while (v > 1 && (row % v != 0 || E % v != 0 || (uintptr_t)base % (v * esz) != 0)) v >>= 1;
+        return v > 4 ? 4 : v;                  // 4 elements per access keeps the tile loops short
+    };
+    const int vl = width(S, es, src), vs = width(R, ed, dst);
+#define LAUNCH(TS, TD, VL, VS)                                                                 \
+    transpose_kernel<TS, TD, VL, VS><<<(unsigned)blocks, 256, 0, st>>>(                        \
+        static_cast<const TS*>(src), static_cast<TD*>(dst), N, R, S, tr, ts)
+#define CALL(TS, TD)                                                                           \
+    do {                                                                                       \
+        if (vl == 4 && vs == 4) LAUNCH(TS, TD, 4, 4);                                          \
+        else if (vl == 4) LAUNCH(TS, TD, 4, 1);                                                \
+        else if (vl == 2 && vs == 4) LAUNCH(TS, TD, 2, 4);                                     \
+        else if (vs == 4) LAUNCH(TS, TD, 1, 4);                                                \
+        else LAUNCH(TS, TD, 1, 1);                                                             \
+    } while (0)
     DISPATCH2(src_dtype, dst_dtype, CALL);
 #undef CALL
+#undef LAUNCH
     HTD_CHECK_LAUNCH("htd_layout_convert");
     return HTD_OK;
 }

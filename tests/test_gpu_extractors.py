@@ -164,6 +164,25 @@ def test_layout_roundtrip():
     assert torch.equal(yb, x.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize('N,R,S', [
+    (5, 49, 256), (5, 256, 49),            # whole-matrix form, both directions of the flatten order
+    (2, 256, 200 * 336), (2, 256, 100 * 167), (2, 256, 25 * 42), (2, 256, 13 * 21),  # tiled, widths 4/4/2/1
+    (3, 72, 855), (1, 7, 3), (2, 64, 64), (4, 100, 96),
+])
+@pytest.mark.parametrize('sd,dd', [('f32', 'bf16'), ('bf16', 'f32'), ('bf16', 'bf16'), ('f32', 'f32')])
+def test_layout_convert_forms(N, R, S, sd, dd):
+    """htd_layout_convert [N,R,S] -> [N,S,R] in every kernel form the host dispatch picks
+    (whole-matrix / tiled, each vector width), bit-exact against a torch permute."""
+    from htd_b200 import ops
+    T = dict(f32=torch.float32, bf16=torch.bfloat16)
+    g = torch.Generator(device='cuda').manual_seed(N * 1000 + R + S)
+    src = torch.randn(N, R, S, device='cuda', generator=g).to(T[sd])
+    dst = torch.full((N, S, R), float('nan'), device='cuda', dtype=T[dd])
+    ops._convert(src, dst, N, R, S)
+    want = src.permute(0, 2, 1).to(T[dd])
+    assert torch.equal(dst, want)
+
+
 def test_full_size_forward_properties():
     """BASELINE config sizes (800x1333, 512 RoIs): linearity in the features and agreement of
     the single-level extractor with the all-level sampler on the assigned level; oracle compare

@@ -115,6 +115,16 @@ def main():
                               ms_best=best, alg_MB=nb / 1e6, GBs=nb / med / 1e6,
                               frac=nb / med / 1e6 / PEAK)))
 
+        # ---- flatten-order change of the pooled maps ([P,49,C] <-> [P,C,49])
+        for (R, S) in ((49, C), (C, 49)):
+            a_ = torch.randn(1024, R, S, device=dev).to(dtype)
+            b_ = torch.empty(1024, S, R, device=dev, dtype=dtype)
+            nb = 2 * a_.numel() * bs
+            med, best = timeit(lambda: ops._convert(a_, b_, 1024, R, S), a.iters, flush)
+            print(json.dumps(dict(kernel=f'layout_convert(pooled {R}x{S})', dtype=str(dtype), ms=med,
+                                  ms_best=best, alg_MB=nb / 1e6, GBs=nb / med / 1e6,
+                                  frac=nb / med / 1e6 / PEAK)))
+
 
 if __name__ == '__main__':
     main()
