@@ -266,6 +266,24 @@ class GradSink:
         self.scales, self.pooled = scales, pooled
         self.sources.append(source)
 
+    def hand_over(self, stream):
+        """The parked tensors travel outside autograd, so its cross-stream bookkeeping does not
+        see them: an extractor that ran on a side stream parks tensors from that stream's pool,
+        and the gather that reads them runs on the pyramid node's stream.  Tell the allocator,
+        or the blocks go back to the side stream's pool (and to its next kernels) as soon as the
+        sources are dropped, while the gather is still reading them."""
+        def walk(v):
+            if torch.is_tensor(v):
+                if v.is_cuda:
+                    v.record_stream(stream)
+            elif isinstance(v, (tuple, list)):
+                for u in v:
+                    walk(u)
+            elif isinstance(v, dict):
+                for u in v.values():
+                    walk(u)
+        walk(self.sources)
+
 
 class Pyramid(list):
     """Channels-last feature maps of one step + the token / sink that defer their gradient."""
@@ -309,6 +327,7 @@ class _PyramidFn(torch.autograd.Function):
         if not sink.sources:
             return (None, None) + tuple(torch.zeros(s, dtype=dt_, device=gtoken.device)
                                         for s, dt_ in zip(shapes, xdtypes))
+        sink.hand_over(torch.cuda.current_stream(gtoken.device))
         # channels-last gather (512 B coalesced stores) + one transpose/cast pass back to the
         # reference's NCHW layout; writing NCHW straight from the gather measured 30% slower
         cl = _bwd_multi(shapes, sink.sources[0]['dy'].dtype, False, sink.scales, sink.sources,

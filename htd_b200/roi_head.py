@@ -91,6 +91,29 @@ class HTDRoIHead(nn.Module):
             st = self._side = torch.cuda.Stream(device=device)
         return st
 
+    overlap_global = True    # class switch (diagnostics): global-context head on a side stream
+
+    def _global_context(self, x, loss_fn):
+        """Global-context head + its loss (htd_roi_head.py:245-249) next to the channels-last
+        conversion of the pyramid: both only read ``x``, the head's launches are small
+        (2 x 256 x 13 x 21 maps), so on a side stream it costs nothing on the forward critical
+        path, and autograd mirrors the branch in backward (next to the backward gather).
+        Returns (channels-last pyramid, loss, global_feat)."""
+        if not (self.overlap_global and x[0].is_cuda):
+            x_cl = self._pyramid(x)
+            mc_pred, global_feat = self.glbctx_head(x)
+            return x_cl, loss_fn(mc_pred), global_feat
+        cur, side = torch.cuda.current_stream(), self._side_stream(x[0].device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            mc_pred, global_feat = self.glbctx_head(x)
+            loss = loss_fn(mc_pred)
+        x_cl = self._pyramid(x)
+        cur.wait_stream(side)
+        for t in (loss, global_feat):
+            t.record_stream(cur)
+        return x_cl, loss, global_feat
+
     def _pyramid(self, x):
         """Channels-last copy of the levels the extractors read, made once per call."""
         n = self.bbox_roi_extractor[0].num_inputs
@@ -189,7 +212,7 @@ class HTDRoIHead(nn.Module):
         num_imgs = len(img_metas)
         if gt_bboxes_ignore is None:
             gt_bboxes_ignore = [None] * num_imgs
-        x_cl = self._pyramid(x)
+        x_cl = None if self.with_global else self._pyramid(x)
 
         def sample(stage, props):
             if sampling_fn is not None:
@@ -201,8 +224,8 @@ class HTDRoIHead(nn.Module):
         samp = sample(0, proposal_list)
         global_feat = None
         if self.with_global:
-            mc_pred, global_feat = self.glbctx_head(x)
-            losses['loss_global'] = self.glbctx_head.loss(mc_pred, gt_labels)
+            x_cl, losses['loss_global'], global_feat = self._global_context(
+                x, lambda mc_pred: self.glbctx_head.loss(mc_pred, gt_labels))
         if self.inputs_consumed_event is not None and x[0].is_cuda:
             # everything downstream reads the channels-last copy / the SFA head's cast of P6 only
             # (and the proposals through copies made below): the caller may refill `x` from here on
@@ -246,14 +269,16 @@ class HTDRoIHead(nn.Module):
         G = gt_bboxes.shape[1]
         dev = proposals.device
         losses = dict()
-        x_cl = self._pyramid(x)
         global_feat = None
         if self.with_global:
-            mc_pred, global_feat = self.glbctx_head(x)
-            real = torch.arange(G, device=dev)[None, :] < num_gt[:, None]
-            nc1 = mc_pred.size(1)
-            hot = (gt_labels[:, :, None] == torch.arange(nc1, device=dev)) & real[:, :, None]
-            losses['loss_global'] = self.glbctx_head.loss_multihot(mc_pred, hot.any(1))
+            def multihot_loss(mc_pred):
+                real = torch.arange(G, device=dev)[None, :] < num_gt[:, None]
+                nc1 = mc_pred.size(1)
+                hot = (gt_labels[:, :, None] == torch.arange(nc1, device=dev)) & real[:, :, None]
+                return self.glbctx_head.loss_multihot(mc_pred, hot.any(1))
+            x_cl, losses['loss_global'], global_feat = self._global_context(x, multihot_loss)
+        else:
+            x_cl = self._pyramid(x)
         cand, valid = proposals, None
         self.last_static = []
         for stage in range(self.num_stages):
