@@ -495,18 +495,58 @@ class HTDBBoxHead(BBoxHead):
 
     def forward(self, x_cls, x_reg, feat, rois, fc_cls_0, enhanced_feat=None, pos_rois=None,
                 global_feat=None, num_imgs=None, max_rois_per_img=None, row_valid=None,
-                x_cls_flat=None):
+                x_cls_flat=None, reg_stream=None):
         """Reference signature (htd_bbox_head.py:157).  ``num_imgs`` (optional) avoids the host
         sync of ``int(max(rois[:,0])) + 1`` (:159); ``global_feat`` gives it otherwise.
         ``max_rois_per_img`` (optional) bounds the PGraph group size (default: all RoIs);
         ``row_valid`` ([K] bool, optional) keeps pad rows of the static sampler out of the graph;
-        ``x_cls_flat`` (optional) is ``x_cls`` already flattened (``ops.flatten_with_prefix``)."""
+        ``x_cls_flat`` (optional) is ``x_cls`` already flattened (``ops.flatten_with_prefix``);
+        ``reg_stream`` (optional CUDA stream, the one ``enhanced_feat`` was produced on): the reg
+        branch - independent of the cls branch until the loss - runs there, as a parallel branch
+        of the step."""
         if num_imgs is None:
             num_imgs = global_feat.size(0) if global_feat is not None \
                 else int(torch.max(rois[..., 0])) + 1
         d = self.fc_out_channels
         prototype = torch.cat((fc_cls_0.weight, fc_cls_0.bias.unsqueeze(1)), 1).detach()
         g = global_feat.reshape(global_feat.size(0), -1) if global_feat is not None else None
+        # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool -> fc_reg
+        # (:161-189).  Independent of the cls branch: with ``reg_stream`` it is a parallel branch
+        def reg_branch(x_reg, enhanced_feat):
+            if callable(enhanced_feat):
+                enhanced_feat = enhanced_feat()
+            if BBoxHead.own_dense and dense.usable(x_reg, enhanced_feat) and x_reg.size(1) % 8 == 0 \
+                    and (g is None or g.dtype == x_reg.dtype):
+                # x_reg + global_feat[image] + alpha * BA in ONE pass (csrc/dense_gemm.cu
+                # add3_kernel) instead of a one-hot GEMM, three elementwise launches and their
+                # backward ops
+                x_reg = dense.add3(x_reg, enhanced_feat, g, pos_rois, self.alpha)
+            else:
+                if global_feat is not None:
+                    x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
+                x_reg = x_reg + self.alpha * enhanced_feat
+                x_reg = x_reg.contiguous(memory_format=torch.channels_last)
+            last = self.convs[-1] if len(self.convs) else None
+            if last is not None and last.gn is None and last.with_act and x_reg.is_cuda and \
+                    ConvModule.fused_gn and last.conv.out_channels % 8 == 0:
+                for m in self.convs[:-1]:
+                    x_reg = m(x_reg)
+                # last conv -> ReLU -> AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:109-113,188-189):
+                # activation and pool in one pass over the largest activation of the head
+                x_reg = ops.relu_mean_pool(last._conv(x_reg))
+            else:
+                x_reg = self.convs(x_reg).mean((2, 3))
+            return linear_aligned(self.fc_reg, x_reg) if self.with_reg else None
+
+        bbox_pred = None
+        if reg_stream is not None:
+            cur = torch.cuda.current_stream()
+            reg_stream.wait_stream(cur)                      # x_reg, g, pos_rois come from `cur`
+            for t in (x_reg, g, pos_rois):
+                if torch.is_tensor(t):
+                    t.record_stream(reg_stream)
+            with torch.cuda.stream(reg_stream):
+                bbox_pred = reg_branch(x_reg, enhanced_feat)
         # ---- cls branch: fcs on x_cls and on x_cls + SFA.  fcs.0 is linear, so
         # fcs.0(x + g (x) 1_49) = fcs.0(x) + g W_sum^T with W_sum = sum of W over the 49 bins:
         # one [K,12544]x[12544,1024] GEMM instead of the reference's two (:164 and :192).
@@ -549,34 +589,14 @@ class HTDBBoxHead(BBoxHead):
         layers = self.graph_layer_cls
         refined = pgraph.pgraph_refine(x_c, sam, [m.weight for m in layers],
                                        [m.bias for m in layers], plan)
-        # ---- reg branch: (x_reg + SFA) + alpha * BA  -> conv tower -> avg pool (:161-189).  It is
-        # independent of the cls branch above; it comes second so that a BA extraction running on a
-        # side stream (``enhanced_feat`` given as a callable that joins it) overlaps all of the above
-        if callable(enhanced_feat):
-            enhanced_feat = enhanced_feat()
-        if BBoxHead.own_dense and dense.usable(x_reg, enhanced_feat) and x_reg.size(1) % 8 == 0 and \
-                (g is None or g.dtype == x_reg.dtype):
-            # x_reg + global_feat[image] + alpha * BA in ONE pass (csrc/dense_gemm.cu add3_kernel)
-            # instead of a one-hot GEMM, three elementwise launches and their backward ops
-            x_reg = dense.add3(x_reg, enhanced_feat, g, pos_rois, self.alpha)
-        else:
-            if global_feat is not None:
-                x_reg = x_reg + (self._img_onehot(pos_rois, g.size(0), g.dtype) @ g)[:, :, None, None]
-            x_reg = x_reg + self.alpha * enhanced_feat
-            x_reg = x_reg.contiguous(memory_format=torch.channels_last)
-        last = self.convs[-1] if len(self.convs) else None
-        if last is not None and last.gn is None and last.with_act and x_reg.is_cuda and \
-                ConvModule.fused_gn and last.conv.out_channels % 8 == 0:
-            for m in self.convs[:-1]:
-                x_reg = m(x_reg)
-            # last conv -> ReLU -> AvgPool2d(7) on a 7x7 map (htd_bbox_head.py:109-113,188-189):
-            # activation and pool in one pass over the largest activation of the head
-            x_reg = ops.relu_mean_pool(last._conv(x_reg))
-        else:
-            x_reg = self.convs(x_reg).mean((2, 3))
         feat_cls_new = (x_glb if x_glb is not None else x_c) + refined
         cls_score = linear_aligned(self.fc_cls, feat_cls_new) if self.with_cls else None
-        bbox_pred = linear_aligned(self.fc_reg, x_reg) if self.with_reg else None
+        if reg_stream is None:
+            bbox_pred = reg_branch(x_reg, enhanced_feat)
+        else:
+            cur.wait_stream(reg_stream)
+            if bbox_pred is not None:
+                bbox_pred.record_stream(cur)
         return cls_score, bbox_pred
 
 

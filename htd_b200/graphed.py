@@ -148,15 +148,15 @@ class GraphedTrainStep(_GraphedStep):
 
     def _run(self):
         # the early-gradient event is recorded on ONE stream: keep the whole step on it
-        prev = self.head.overlap_ba
+        prev = self.head.overlap
         if self.early_event is not None:
-            self.head.overlap_ba = False
+            self.head.overlap = False
         self.head.inputs_consumed_event = self.inputs_consumed
         try:
             self._finish(synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
                                                      self.img_shapes, self.num_pos))
         finally:
-            self.head.overlap_ba = prev
+            self.head.overlap = prev
             self.head.inputs_consumed_event = None
 
     def load(self, x=None, proposals=None, gts=None, non_blocking=True):

@@ -26,6 +26,52 @@ class _StaticRows:
         self.pos_bboxes, self.neg_bboxes = pos_bboxes, neg_bboxes
 
 
+
+def _hand_over(obj, stream, depth=0):
+    """Tensors made on a branch stream and used on ``stream`` afterwards: tell the allocator
+    (the join itself is a ``wait_stream``; this is about when their memory may be reused)."""
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            _hand_over(v, stream, depth + 1)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _hand_over(v, stream, depth + 1)
+    elif hasattr(obj, '__dict__') and depth < 3:
+        _hand_over(vars(obj), stream, depth + 1)
+
+
+class _Branch:
+    """``with _Branch(stream, uses) as b:`` runs the body on ``stream`` after everything issued so
+    far on the current stream; ``b.join(results)`` makes the current stream wait for it.
+    ``stream=None``: no-op (the body runs in line)."""
+
+    def __init__(self, stream, uses=()):
+        self.stream, self.uses = stream, uses
+
+    def __enter__(self):
+        if self.stream is not None:
+            self.cur = torch.cuda.current_stream(self.stream.device)
+            self.stream.wait_stream(self.cur)
+            _hand_over(self.uses, self.stream)      # saved for a backward that runs over there
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.stream is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, results):
+        if self.stream is not None:
+            self.cur.wait_stream(self.stream)
+            _hand_over(results, self.cur)
+        return results
+
+
 @HEADS.register_module()
 class HTDRoIHead(nn.Module):
 
@@ -82,16 +128,34 @@ class HTDRoIHead(nn.Module):
             self.glbctx_head.init_weights()
 
     # ------------------------------------------------------------------------------------------
-    overlap_ba = True        # class switch (diagnostics): BA extraction on a side stream in training
+    # Independent parts of the step run as parallel branches (streams in eager mode, parallel
+    # branches of the graph once captured; autograd mirrors every branch in backward):
+    #   overlap_ba      BA extraction + the reg branch that consumes it, next to the single-level
+    #                   extraction, the cls-branch GEMMs and the PGraph
+    #   overlap_global  global-context head next to the pyramid conversion (forward) and the
+    #                   backward gather (backward), on a prioritised stream: its launches are tiny
+    #                   and would otherwise queue behind the thousands of CTAs of those kernels
+    #   overlap_stages  stage 0 on its own stream: forward is serial (stage 1 samples the refined
+    #                   boxes), but the two stages' backward passes are independent
+    # Class switches (diagnostics; ``overlap = False`` turns all of them off).
+    overlap = True
+    overlap_ba = True
+    overlap_global = True
+    overlap_stages = True
     inputs_consumed_event = None   # optional CUDA event recorded once forward_train has read `x`
 
-    def _side_stream(self, device):
-        st = getattr(self, '_side', None)
+    def _stream(self, name, device, priority=0):
+        pool = self.__dict__.setdefault('_streams', {})
+        st = pool.get(name)
         if st is None or st.device != device:
-            st = self._side = torch.cuda.Stream(device=device)
+            st = pool[name] = torch.cuda.Stream(device=device, priority=priority)
         return st
 
-    overlap_global = True    # class switch (diagnostics): global-context head on a side stream
+    def _side_stream(self, device):
+        return self._stream('side', device)
+
+    def _on(self, which, t):
+        return self.overlap and getattr(self, which) and t.is_cuda
 
     def _global_context(self, x, loss_fn):
         """Global-context head + its loss (htd_roi_head.py:245-249) next to the channels-last
@@ -99,11 +163,11 @@ class HTDRoIHead(nn.Module):
         (2 x 256 x 13 x 21 maps), so on a side stream it costs nothing on the forward critical
         path, and autograd mirrors the branch in backward (next to the backward gather).
         Returns (channels-last pyramid, loss, global_feat)."""
-        if not (self.overlap_global and x[0].is_cuda):
+        if not self._on('overlap_global', x[0]):
             x_cl = self._pyramid(x)
             mc_pred, global_feat = self.glbctx_head(x)
             return x_cl, loss_fn(mc_pred), global_feat
-        cur, side = torch.cuda.current_stream(), self._side_stream(x[0].device)
+        cur, side = torch.cuda.current_stream(), self._stream('global', x[0].device, priority=-1)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             mc_pred, global_feat = self.glbctx_head(x)
@@ -143,20 +207,17 @@ class HTDRoIHead(nn.Module):
         nimg = g.size(0) if g is not None else None
         if sampling_results:
             pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
-            if self.overlap_ba and rois.is_cuda:
-                # BA extraction (plan, 4-level gather, attention, fuse: latency-bound kernels) on a
-                # side stream next to the single-level extraction, the cls-branch GEMMs and the
-                # PGraph; the head joins the stream where it first needs the result.  Inside a CUDA
-                # graph this becomes a parallel branch; autograd mirrors it in backward.
-                cur, side = torch.cuda.current_stream(), self._side_stream(rois.device)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    enh_out = enh(x_cl, pos_rois)
-
-                def enhanced():
-                    cur.wait_stream(side)
-                    enh_out.record_stream(cur)
-                    return enh_out
+            reg_stream = None
+            if self._on('overlap_ba', rois):
+                # BA extraction (plan, 4-level gather, attention, fuse: latency-bound kernels) and
+                # the reg branch that consumes it (conv tower) on a side stream next to the
+                # single-level extraction, the cls-branch GEMMs and the PGraph; the head joins
+                # the stream once both branches are issued.  Inside a CUDA graph this becomes a
+                # parallel branch; autograd mirrors it in backward.
+                cur, reg_stream = torch.cuda.current_stream(), self._side_stream(rois.device)
+                reg_stream.wait_stream(cur)
+                with torch.cuda.stream(reg_stream):
+                    enhanced = enh(x_cl, pos_rois)
             else:
                 enhanced = enh(x_cl, pos_rois)
             bbox_feats = ext(x_cl, rois)
@@ -171,7 +232,7 @@ class HTDRoIHead(nn.Module):
             cls_score, bbox_pred = head(bbox_feats, pos_feats, x_cl, rois, fc0, enhanced,
                                         pos_rois, g, num_imgs=nimg or len(sampling_results),
                                         max_rois_per_img=max(p_ + n_ for _, p_, n_ in spans),
-                                        row_valid=row_valid, x_cls_flat=flat)
+                                        row_valid=row_valid, x_cls_flat=flat, reg_stream=reg_stream)
             parts, o2 = [], 0
             for _, npos, nneg in spans:
                 parts += [bbox_pred[o2:o2 + npos], bbox_pred.new_zeros(nneg, bbox_pred.size(1))]
@@ -231,8 +292,11 @@ class HTDRoIHead(nn.Module):
             # (and the proposals through copies made below): the caller may refill `x` from here on
             # - graphed.GraphedTrainStep(flat_inputs=True) overlaps the next upload with this step
             self.inputs_consumed_event.record()
-        res = self._bbox_forward_train(0, x, samp, gt_bboxes, gt_labels, self.train_cfg[0],
-                                       img_metas, global_feat, x_cl)
+        st0 = self._stream('stage0', x[0].device) if self._on('overlap_stages', x[0]) else None
+        with _Branch(st0, (list(x_cl), global_feat)) as br:
+            res = self._bbox_forward_train(0, x, samp, gt_bboxes, gt_labels, self.train_cfg[0],
+                                           img_metas, global_feat, x_cl)
+        br.join(res)
         lw = self.stage_loss_weights[0]
         for name, value in res['loss_bbox'].items():
             losses[f's0.{name}'] = value * lw if 'loss' in name else value
@@ -282,51 +346,55 @@ class HTDRoIHead(nn.Module):
         cand, valid = proposals, None
         self.last_static = []
         for stage in range(self.num_stages):
-            cfg = self.train_cfg[stage]
-            a, s = dict(cfg.assigner), dict(cfg.sampler)
-            head = self.bbox_head[stage]
-            assert head.reg_class_agnostic and not head.reg_decoded_bbox and \
-                a.get('ignore_iof_thr', -1) <= 0 and a.get('gt_max_assign_all', True) and \
-                not isinstance(a['neg_iou_thr'], (tuple, list)), \
-                'forward_train_static covers the configs/htd settings'
-            k = keys[stage] if keys is not None else \
-                torch.rand((B, G + cand.shape[1]), device=dev, dtype=torch.float32)
-            S = ops.assign_sample(cand, gt_bboxes, gt_labels, num_gt, k, valid=valid,
-                                  pos_iou_thr=a['pos_iou_thr'], neg_iou_thr=a['neg_iou_thr'],
-                                  min_pos_iou=a.get('min_pos_iou', 0.),
-                                  match_low_quality=a.get('match_low_quality', True),
-                                  add_gt_as_proposals=s.get('add_gt_as_proposals', True),
-                                  num=s['num'], pos_fraction=s['pos_fraction'],
-                                  neg_pos_ub=s.get('neg_pos_ub', -1))
-            self.last_static.append(S)
-            num, npos = S.num, S.num_pos
-            rois = S.rois
-            row_valid = S.kind != 2
-            samp = None
-            if stage > 0:
-                r3 = rois.view(B, num, 5)
-                samp = [_StaticRows(r3[b, :npos, 1:], r3[b, npos:, 1:]) for b in range(B)]
-            res = self._bbox_forward(stage, x, rois, global_feat, samp, img_metas, x_cl,
-                                     row_valid=row_valid)
-            pw = cfg.get('pos_weight', -1)
-            targets = ops.bbox_targets(rois[:, 1:], S.gt_boxes, S.gt_labels, S.kind,
-                                       head.num_classes, pw, head.bbox_coder.means,
-                                       head.bbox_coder.stds)
-            loss = head.loss(res['cls_score'], res['bbox_pred'], rois, *targets, pad_rows=True)
-            lw = self.stage_loss_weights[stage]
-            for name, value in loss.items():
-                losses[f's{stage}.{name}'] = value * lw if 'loss' in name else value
-            if stage < self.num_stages - 1:
-                with torch.no_grad():                      # refine_bboxes (bbox_head.py:227-303):
-                    if len({tuple(m['img_shape'][:2]) for m in img_metas}) == 1:
-                        cand = head.regress_by_class(rois[:, 1:], None, res['bbox_pred'],
-                                                     img_metas[0]).view(B, num, 4)
-                    else:                                  # gt rows are masked, not dropped
-                        r3, bp = rois.view(B, num, 5), res['bbox_pred'].view(B, num, -1)
-                        cand = torch.stack([head.regress_by_class(r3[b, :, 1:], None, bp[b],
-                                                                  img_metas[b]) for b in range(B)])
-                    valid = (row_valid & (S.is_gt == 0)).view(B, num)
-                    self.last_refined = cand
+            st0 = self._stream('stage0', dev) if stage == 0 and self.num_stages > 1 and \
+                self._on('overlap_stages', proposals) else None
+            with _Branch(st0, (list(x_cl), global_feat)) as br:
+                cfg = self.train_cfg[stage]
+                a, s = dict(cfg.assigner), dict(cfg.sampler)
+                head = self.bbox_head[stage]
+                assert head.reg_class_agnostic and not head.reg_decoded_bbox and \
+                    a.get('ignore_iof_thr', -1) <= 0 and a.get('gt_max_assign_all', True) and \
+                    not isinstance(a['neg_iou_thr'], (tuple, list)), \
+                    'forward_train_static covers the configs/htd settings'
+                k = keys[stage] if keys is not None else \
+                    torch.rand((B, G + cand.shape[1]), device=dev, dtype=torch.float32)
+                S = ops.assign_sample(cand, gt_bboxes, gt_labels, num_gt, k, valid=valid,
+                                      pos_iou_thr=a['pos_iou_thr'], neg_iou_thr=a['neg_iou_thr'],
+                                      min_pos_iou=a.get('min_pos_iou', 0.),
+                                      match_low_quality=a.get('match_low_quality', True),
+                                      add_gt_as_proposals=s.get('add_gt_as_proposals', True),
+                                      num=s['num'], pos_fraction=s['pos_fraction'],
+                                      neg_pos_ub=s.get('neg_pos_ub', -1))
+                self.last_static.append(S)
+                num, npos = S.num, S.num_pos
+                rois = S.rois
+                row_valid = S.kind != 2
+                samp = None
+                if stage > 0:
+                    r3 = rois.view(B, num, 5)
+                    samp = [_StaticRows(r3[b, :npos, 1:], r3[b, npos:, 1:]) for b in range(B)]
+                res = self._bbox_forward(stage, x, rois, global_feat, samp, img_metas, x_cl,
+                                         row_valid=row_valid)
+                pw = cfg.get('pos_weight', -1)
+                targets = ops.bbox_targets(rois[:, 1:], S.gt_boxes, S.gt_labels, S.kind,
+                                           head.num_classes, pw, head.bbox_coder.means,
+                                           head.bbox_coder.stds)
+                loss = head.loss(res['cls_score'], res['bbox_pred'], rois, *targets, pad_rows=True)
+                lw = self.stage_loss_weights[stage]
+                for name, value in loss.items():
+                    losses[f's{stage}.{name}'] = value * lw if 'loss' in name else value
+                if stage < self.num_stages - 1:
+                    with torch.no_grad():                      # refine_bboxes (bbox_head.py:227-303):
+                        if len({tuple(m['img_shape'][:2]) for m in img_metas}) == 1:
+                            cand = head.regress_by_class(rois[:, 1:], None, res['bbox_pred'],
+                                                         img_metas[0]).view(B, num, 4)
+                        else:                                  # gt rows are masked, not dropped
+                            r3, bp = rois.view(B, num, 5), res['bbox_pred'].view(B, num, -1)
+                            cand = torch.stack([head.regress_by_class(r3[b, :, 1:], None, bp[b],
+                                                                      img_metas[b]) for b in range(B)])
+                        valid = (row_valid & (S.is_gt == 0)).view(B, num)
+                        self.last_refined = cand
+            br.join((losses, cand, valid, S, getattr(self, 'last_refined', None)))
         return losses
 
     def simple_test_scores(self, x, proposal_list, img_metas):
