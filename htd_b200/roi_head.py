@@ -296,10 +296,13 @@ class HTDRoIHead(nn.Module):
         with _Branch(st0, (list(x_cl), global_feat)) as br:
             res = self._bbox_forward_train(0, x, samp, gt_bboxes, gt_labels, self.train_cfg[0],
                                            img_metas, global_feat, x_cl)
-        br.join(res)
-        lw = self.stage_loss_weights[0]
-        for name, value in res['loss_bbox'].items():
-            losses[f's0.{name}'] = value * lw if 'loss' in name else value
+            # the loss weights belong to the branch too: their backward nodes are the entry of
+            # stage 0's backward, and on the main stream they would be queued behind all of
+            # stage 1's (autograd issues later forward ops first)
+            lw = self.stage_loss_weights[0]
+            for name, value in res['loss_bbox'].items():
+                losses[f's0.{name}'] = value * lw if 'loss' in name else value
+        br.join((res, losses))
         roi_labels = res['bbox_targets'][0]
         with torch.no_grad():
             roi_labels = torch.where(roi_labels == self.bbox_head[0].num_classes,
