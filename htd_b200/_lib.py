@@ -76,6 +76,10 @@ SIGNATURES = {
                         c_void_p, c_void_p],
     'htd_bias_grad': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                       c_void_p],
+    'htd_ba_mlp_fwd': [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                       c_void_p, c_void_p, c_void_p],
+    'htd_ba_mlp_bwd': [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int,
+                       c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'htd_bbox_targets': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                          ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p],
@@ -133,7 +137,7 @@ SIGNATURES = {
 _lib = None
 
 # kernels launched by each entry point (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_dual_gate': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 1,
+KERNELS_PER_CALL = {'htd_gate_colsum': 2, 'htd_dual_gate': 2, 'htd_iou_graph_build': 2, 'htd_bias_grad': 2, 'htd_roi_plan': 1, 'htd_ba_mlp_bwd': 3,
                     'htd_gn_relu_bwd': 2, 'htd_rcnn_loss_fwd': 2, 'htd_multiclass_nms': 4}
 LAUNCHES = {'total': 0, 'by_entry': {}}
 
@@ -176,6 +180,10 @@ def lib():
         L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
         L.htd_multiclass_soft_nms_workspace_bytes.restype = c_ll
         L.htd_multiclass_soft_nms_workspace_bytes.argtypes = [c_int, c_int]
+        L.htd_ba_mlp_supported.restype = c_int
+        L.htd_ba_mlp_supported.argtypes = [c_int, c_int]
+        L.htd_ba_mlp_workspace_floats.restype = c_ll
+        L.htd_ba_mlp_workspace_floats.argtypes = [c_ll, c_int]
         L.htd_dense_gemm_workspace_bytes.restype = c_ll
         L.htd_dense_gemm_workspace_bytes.argtypes = [ctypes.POINTER(HtdDenseGemm)]
         L.htd_debug_set_bwd_trace.restype = None

@@ -373,6 +373,184 @@ __global__ void bias_grad_final_kernel(const float* __restrict__ partial, int nb
     dbias[i] = s;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Attention MLP of the BA extractor on the bin means (adaptative_roi_extractor.py:60-74: 1x1 conv
+// C->H, tanh, 1x1 conv H->1 on the pooled vectors): logits[r] = b2 + sum_j W2[j] tanh(b1[j] +
+// sum_c W1[j,c] m[r,c]).  rows = levels * RoIs (1024 at the bench size), H = 128: 67 MFLOP - the
+// cost is launches, so forward is ONE kernel and backward three (the row gradient dm, which the
+// backward gather waits for, first; the parameter sums after it), instead of ~8 and ~25
+// library / elementwise launches.
+// ------------------------------------------------------------------------------------------
+constexpr int kMlpH = 128, kMlpRows = 8, kMlpMaxC = 512, kMlpChunks = 8;
+
+template <typename TP>
+__global__ void __launch_bounds__(kMlpH) ba_mlp_fwd_kernel(const float* __restrict__ m, int rows,
+                                                           int C, const TP* __restrict__ w1,
+                                                           const TP* __restrict__ b1,
+                                                           const TP* __restrict__ w2,
+                                                           const TP* __restrict__ b2,
+                                                           float* __restrict__ h,
+                                                           float* __restrict__ logits) {
+    __shared__ float sm[kMlpRows][kMlpMaxC];
+    __shared__ float wt[kMlpH][33];
+    __shared__ float red[kMlpRows][kMlpH / 32];
+    const int j = threadIdx.x, r0 = blockIdx.x * kMlpRows;
+    for (int i = j; i < kMlpRows * C; i += kMlpH) {
+        const int r = i / C, c = i - r * C;
+        sm[r][c] = (r0 + r < rows) ? m[(size_t)(r0 + r) * C + c] : 0.f;
+    }
+    float acc[kMlpRows];
+    const float bj = ldv<TP>(b1 + j);
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) acc[r] = bj;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        __syncthreads();
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const int idx = i * kMlpH + j, jj = idx >> 5, cc = idx & 31;
+            wt[jj][cc] = ldv<TP>(w1 + (size_t)jj * C + c0 + cc);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int cc = 0; cc < 32; ++cc) {
+            const float w = wt[j][cc];
+#pragma unroll
+            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sm[r][c0 + cc], w, acc[r]);
+        }
+    }
+    const float w2j = ldv<TP>(w2 + j);
+#pragma unroll
+    for (int r = 0; r < kMlpRows; ++r) {
+        const float hv = tanhf(acc[r]);
+        if (r0 + r < rows) h[(size_t)(r0 + r) * kMlpH + j] = hv;
+        float v = hv * w2j;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((j & 31) == 0) red[r][j >> 5] = v;
+    }
+    __syncthreads();
+    if (j < kMlpRows && r0 + j < rows) {
+        float v = ldv<TP>(b2);
+#pragma unroll
+        for (int w = 0; w < kMlpH / 32; ++w) v += red[j][w];
+        logits[r0 + j] = v;
+    }
+}
+
+// dpre[r,j] = da[r] W2[j] (1 - h[r,j]^2)  (kept for the parameter sums);
+// dm[r,c] = inv_pp * sum_j dpre[r,j] W1[j,c]
+template <typename TP>
+__global__ void __launch_bounds__(256) ba_mlp_dm_kernel(const float* __restrict__ da,
+                                                        const float* __restrict__ h, int rows, int C,
+                                                        const TP* __restrict__ w1,
+                                                        const TP* __restrict__ w2, float inv_pp,
+                                                        float* __restrict__ dpre,
+                                                        float* __restrict__ dm) {
+    __shared__ float dp[kMlpRows][kMlpH];
+    const int r0 = blockIdx.x * kMlpRows;
+    for (int i = threadIdx.x; i < kMlpRows * kMlpH; i += 256) {
+        const int r = i / kMlpH, j = i - r * kMlpH;
+        float v = 0.f;
+        if (r0 + r < rows) {
+            const float hv = h[(size_t)(r0 + r) * kMlpH + j];
+            v = da[r0 + r] * ldv<TP>(w2 + j) * (1.f - hv * hv);
+            dpre[(size_t)(r0 + r) * kMlpH + j] = v;
+        }
+        dp[r][j] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float acc[kMlpRows];
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < kMlpH; ++j) {
+            const float w = ldv<TP>(w1 + (size_t)j * C + c);
+#pragma unroll
+            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(dp[r][j], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kMlpRows; ++r)
+            if (r0 + r < rows) dm[(size_t)(r0 + r) * C + c] = acc[r] * inv_pp;
+    }
+}
+
+// partial[chunk][j][c] = sum over the chunk's rows of dpre[r,j] m[r,c]; grid (H/8, kMlpChunks)
+__global__ void __launch_bounds__(256) ba_mlp_dw_partial_kernel(const float* __restrict__ dpre,
+                                                                const float* __restrict__ m,
+                                                                int rows, int C,
+                                                                float* __restrict__ partial) {
+    const int jg = blockIdx.x * 8, per = (rows + kMlpChunks - 1) / kMlpChunks;
+    const int ra = blockIdx.y * per, rb = min(rows, ra + per);
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+        for (int r = ra; r < rb; ++r) {
+            const float mv = m[(size_t)r * C + c];
+            const float4 a = *reinterpret_cast<const float4*>(dpre + (size_t)r * kMlpH + jg);
+            const float4 b = *reinterpret_cast<const float4*>(dpre + (size_t)r * kMlpH + jg + 4);
+            acc[0] = fmaf(a.x, mv, acc[0]); acc[1] = fmaf(a.y, mv, acc[1]);
+            acc[2] = fmaf(a.z, mv, acc[2]); acc[3] = fmaf(a.w, mv, acc[3]);
+            acc[4] = fmaf(b.x, mv, acc[4]); acc[5] = fmaf(b.y, mv, acc[5]);
+            acc[6] = fmaf(b.z, mv, acc[6]); acc[7] = fmaf(b.w, mv, acc[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            partial[((size_t)blockIdx.y * kMlpH + jg + k) * C + c] = acc[k];
+    }
+}
+
+// one CTA per hidden unit j: dW1[j,:] from the partials; db1[j], dW2[j] (and db2 in CTA 0) by a
+// block reduction over the rows, in a fixed order (deterministic)
+template <typename TP>
+__global__ void __launch_bounds__(256) ba_mlp_dw_final_kernel(const float* __restrict__ partial,
+                                                              const float* __restrict__ dpre,
+                                                              const float* __restrict__ da,
+                                                              const float* __restrict__ h, int rows,
+                                                              int C, TP* __restrict__ dw1,
+                                                              TP* __restrict__ db1,
+                                                              TP* __restrict__ dw2,
+                                                              TP* __restrict__ db2) {
+    __shared__ float red[3][8];
+    const int j = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMlpChunks; ++k) s += partial[((size_t)k * kMlpH + j) * C + c];
+        stv<TP>(dw1 + (size_t)j * C + c, s);
+    }
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int r = threadIdx.x; r < rows; r += 256) {
+        const float d = da[r];
+        s1 += dpre[(size_t)r * kMlpH + j];
+        s2 = fmaf(d, h[(size_t)r * kMlpH + j], s2);
+        s3 += d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s1;
+        red[1][threadIdx.x >> 5] = s2;
+        red[2][threadIdx.x >> 5] = s3;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { t1 += red[0][w]; t2 += red[1][w]; t3 += red[2][w]; }
+        stv<TP>(db1 + j, t1);
+        stv<TP>(dw2 + j, t2);
+        if (j == 0) stv<TP>(db2, t3);
+    }
+}
+
 }  // namespace htd
 
 using namespace htd;
@@ -519,6 +697,67 @@ int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, 
     }
     bias_grad_final_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(partial, nblk, B * C, dbias);
     HTD_CHECK_LAUNCH("htd_bias_grad(final)");
+    return HTD_OK;
+}
+
+
+int htd_ba_mlp_supported(int C, int H) {
+    return H == kMlpH && C >= 32 && C <= kMlpMaxC && C % 32 == 0;
+}
+
+long long htd_ba_mlp_workspace_floats(long long rows, int C) {
+    return rows * kMlpH + (long long)kMlpChunks * kMlpH * C;
+}
+
+int htd_ba_mlp_fwd(const float* m, long long rows, int C, int H, const void* w1, const void* b1,
+                   const void* w2, const void* b2, int p_dtype, float* h, float* logits,
+                   htd_stream_t stream) {
+    HTD_CHECK_ARG(htd_ba_mlp_supported(C, H) && dt_ok(p_dtype) && rows >= 0 && rows < 2147483647LL,
+                  "htd_ba_mlp_fwd: unsupported sizes C=%d H=%d", C, H);
+    if (rows == 0) return HTD_OK;
+    HTD_CHECK_ARG(m && w1 && b1 && w2 && b2 && h && logits, "htd_ba_mlp_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((rows + kMlpRows - 1) / kMlpRows);
+    if (p_dtype == HTD_F32)
+        ba_mlp_fwd_kernel<float><<<grid, kMlpH, 0, st>>>(
+            m, (int)rows, C, static_cast<const float*>(w1), static_cast<const float*>(b1),
+            static_cast<const float*>(w2), static_cast<const float*>(b2), h, logits);
+    else
+        ba_mlp_fwd_kernel<__nv_bfloat16><<<grid, kMlpH, 0, st>>>(
+            m, (int)rows, C, static_cast<const __nv_bfloat16*>(w1),
+            static_cast<const __nv_bfloat16*>(b1), static_cast<const __nv_bfloat16*>(w2),
+            static_cast<const __nv_bfloat16*>(b2), h, logits);
+    HTD_CHECK_LAUNCH("htd_ba_mlp_fwd");
+    return HTD_OK;
+}
+
+int htd_ba_mlp_bwd(const float* da, const float* h, const float* m, long long rows, int C, int H,
+                   const void* w1, const void* w2, int p_dtype, float inv_pp, float* dm,
+                   float* workspace, void* dw1, void* db1, void* dw2, void* db2,
+                   htd_stream_t stream) {
+    HTD_CHECK_ARG(htd_ba_mlp_supported(C, H) && dt_ok(p_dtype) && rows >= 1 && rows < 2147483647LL,
+                  "htd_ba_mlp_bwd: unsupported sizes C=%d H=%d rows=%lld", C, H, rows);
+    HTD_CHECK_ARG(da && h && m && w1 && w2 && dm && workspace && dw1 && db1 && dw2 && db2,
+                  "htd_ba_mlp_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dpre = workspace;
+    float* partial = workspace + rows * kMlpH;
+    const unsigned grid = (unsigned)((rows + kMlpRows - 1) / kMlpRows);
+#define CALL(TP)                                                                               \
+    do {                                                                                       \
+        ba_mlp_dm_kernel<TP><<<grid, 256, 0, st>>>(da, h, (int)rows, C,                        \
+                                                   static_cast<const TP*>(w1),                 \
+                                                   static_cast<const TP*>(w2), inv_pp, dpre, dm); \
+        ba_mlp_dw_partial_kernel<<<dim3(kMlpH / 8, kMlpChunks), 256, 0, st>>>(dpre, m, (int)rows, \
+                                                                             C, partial);      \
+        ba_mlp_dw_final_kernel<TP><<<kMlpH, 256, 0, st>>>(                                     \
+            partial, dpre, da, h, (int)rows, C, static_cast<TP*>(dw1), static_cast<TP*>(db1),  \
+            static_cast<TP*>(dw2), static_cast<TP*>(db2));                                     \
+    } while (0)
+    if (p_dtype == HTD_F32) CALL(float);
+    else CALL(__nv_bfloat16);
+#undef CALL
+    HTD_CHECK_LAUNCH("htd_ba_mlp_bwd");
     return HTD_OK;
 }
 

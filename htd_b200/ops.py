@@ -490,11 +490,25 @@ class _BAFunction(torch.autograd.Function):
         m = torch.empty((L * K, C), dtype=torch.float32, device=dev)
         check(lib().htd_ba_bin_mean(ptr(R), dt(R), L * K, PP, C, ptr(m), stream()),
               'htd_ba_bin_mean')
-        # attention MLP on the pooled vectors: two plain library GEMMs ([L*K,256]x[256,128], x[128,1])
-        W1 = w1.detach().reshape(w1.shape[0], -1).float()
-        W2 = w2.detach().reshape(1, -1).float()
-        h = torch.tanh(torch.addmm(b1.detach().float(), m, W1.t()))
-        logits = torch.addmm(b2.detach().float(), h, W2.t()).reshape(L, K).contiguous()
+        # attention MLP on the pooled vectors ([L*K,C] -> 128 -> 1): one fused launch for the
+        # configured sizes, plain library GEMMs otherwise
+        H1 = w1.shape[0]
+        pdt = w1.dtype
+        fused_mlp = bool(lib().htd_ba_mlp_supported(C, H1)) and w2.numel() == H1 and \
+            all(t.dtype == pdt and t.is_contiguous() for t in (w1, b1, w2, b2)) and \
+            pdt in (torch.float32, torch.bfloat16)
+        if fused_mlp:
+            W1, W2 = w1.detach(), w2.detach()
+            h = torch.empty((L * K, H1), dtype=torch.float32, device=dev)
+            logits = torch.empty((L, K), dtype=torch.float32, device=dev)
+            check(lib().htd_ba_mlp_fwd(ptr(m), L * K, C, H1, ptr(W1), ptr(b1.detach()), ptr(W2),
+                                       ptr(b2.detach()), dt(W1), ptr(h), ptr(logits), stream()),
+                  'htd_ba_mlp_fwd')
+        else:
+            W1 = w1.detach().reshape(w1.shape[0], -1).float()
+            W2 = w2.detach().reshape(1, -1).float()
+            h = torch.tanh(torch.addmm(b1.detach().float(), m, W1.t()))
+            logits = torch.addmm(b2.detach().float(), h, W2.t()).reshape(L, K).contiguous()
         wts = torch.empty((L, K), dtype=torch.float32, device=dev)
         out = torch.empty((K, pooled, pooled, C), dtype=fdt, device=dev)
         add_c = None
@@ -511,6 +525,7 @@ class _BAFunction(torch.autograd.Function):
         ctx.cfg = (scales, pooled, sampling_ratio, edge, [tuple(f.shape) for f in feats], fdt, B,
                    w1.shape, w2.shape, add is not None,
                    None if bias is None else tuple(bias.shape))
+        ctx.fused_mlp = fused_mlp
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -525,14 +540,27 @@ class _BAFunction(torch.autograd.Function):
         da = torch.empty((L, K), dtype=torch.float32, device=g.device)
         check(lib().htd_ba_fuse_bwd(ptr(R), dt(R), ptr(g), dt(g), ptr(wts), L, K, PP, C, ptr(da),
                                     stream()), 'htd_ba_fuse_bwd')
-        # backward of the tiny attention MLP (Appendix D of SURVEY.md), plain GEMMs
-        da_f = da.reshape(L * K, 1)
-        dW2 = (da_f * h).sum(0).reshape(w2_shape)
-        db2 = da_f.sum().reshape(1)
-        dpre = (da_f * W2) * (1.0 - h * h)
-        dW1 = (dpre.t() @ m).reshape(w1_shape)
-        db1 = dpre.sum(0)
-        dm = (dpre @ W1) * (1.0 / PP)                      # [L*K, C], gradient of the bin mean
+        # backward of the tiny attention MLP (Appendix D of SURVEY.md)
+        if ctx.fused_mlp:
+            H1 = W1.shape[0]
+            dm = torch.empty((L * K, C), dtype=torch.float32, device=g.device)
+            ws = torch.empty(int(lib().htd_ba_mlp_workspace_floats(L * K, C)), dtype=torch.float32,
+                             device=g.device)
+            dW1 = torch.empty(w1_shape, dtype=W1.dtype, device=g.device)
+            db1 = torch.empty(H1, dtype=W1.dtype, device=g.device)
+            dW2 = torch.empty(w2_shape, dtype=W1.dtype, device=g.device)
+            db2 = torch.empty(1, dtype=W1.dtype, device=g.device)
+            check(lib().htd_ba_mlp_bwd(ptr(da), ptr(h), ptr(m), L * K, C, H1, ptr(W1), ptr(W2),
+                                       dt(W1), 1.0 / PP, ptr(dm), ptr(ws), ptr(dW1), ptr(db1),
+                                       ptr(dW2), ptr(db2), stream()), 'htd_ba_mlp_bwd')
+        else:
+            da_f = da.reshape(L * K, 1)
+            dW2 = (da_f * h).sum(0).reshape(w2_shape)
+            db2 = da_f.sum().reshape(1)
+            dpre = (da_f * W2) * (1.0 - h * h)
+            dW1 = (dpre.t() @ m).reshape(w1_shape)
+            db1 = dpre.sum(0)
+            dm = (dpre @ W1) * (1.0 / PP)                  # [L*K, C], gradient of the bin mean
         grads = [None] * L
         gtoken = None
         if ctx.deferred:

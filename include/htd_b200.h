@@ -187,6 +187,24 @@ int htd_ba_fuse_fwd(const void* R, int r_dtype, const float* logits, int L, int 
 int htd_ba_fuse_bwd(const void* R, int r_dtype, const void* dout, int dout_dtype, const float* w,
                     int L, int K, int PP, int C, float* da, htd_stream_t stream);
 
+/* Attention MLP of the BA extractor on the bin means m [rows, C] (rows = levels * RoIs):
+ * h = tanh(m W1^T + b1) [rows, H], logits = h W2^T + b2 [rows]
+ * (AdptRoIExtractor's conv1 / tanh / conv2 on the globally pooled RoI maps,
+ * adaptative_roi_extractor.py:60-74; the 1x1 convs on 1x1 maps are these two products).
+ * Parameters are read in their own dtype (p_dtype: HTD_F32 / HTD_BF16, one for all four);
+ * H must be 128 and C a multiple of 32 up to 512 (htd_ba_mlp_supported).
+ * Backward: dm = inv_pp * (da W2 (1 - h^2)) W1 and the four parameter gradients (written in
+ * p_dtype); workspace = htd_ba_mlp_workspace_floats(rows, C) floats.  Deterministic. */
+int htd_ba_mlp_supported(int C, int H);
+long long htd_ba_mlp_workspace_floats(long long rows, int C);
+int htd_ba_mlp_fwd(const float* m, long long rows, int C, int H, const void* w1, const void* b1,
+                   const void* w2, const void* b2, int p_dtype, float* h, float* logits,
+                   htd_stream_t stream);
+int htd_ba_mlp_bwd(const float* da, const float* h, const float* m, long long rows, int C, int H,
+                   const void* w1, const void* w2, int p_dtype, float inv_pp, float* dm,
+                   float* workspace, void* dw1, void* db1, void* dw2, void* db2,
+                   htd_stream_t stream);
+
 /* Segmented sum of a [K,PP,C] gradient over bins and RoIs of the same image:
  * dbias[b,c] = sum_{k: batch(k)=b} sum_bin g[k,bin,c]  (backward of the fused SFA bias). */
 int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, int C, int B,

@@ -36,6 +36,8 @@ def test_python_binding_covers_the_header():
                                                              'htd_multiclass_nms_workspace_bytes',
                                                              'htd_multiclass_soft_nms_workspace_bytes',
                                                              'htd_dense_gemm_workspace_bytes',
+                                                             'htd_ba_mlp_supported',
+                                                             'htd_ba_mlp_workspace_floats',
                                                              'htd_debug_set_bwd_trace',
                                                              'htd_debug_set_bwd_variant',
                                                              'htd_roi_align_bwd_uses_tensor_pipe'}

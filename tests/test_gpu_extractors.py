@@ -164,6 +164,49 @@ def test_layout_roundtrip():
     assert torch.equal(yb, x.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize('rows,C', [(1024, 256), (37, 256), (8, 32), (260, 512)])
+@pytest.mark.parametrize('pd', ['f32', 'bf16'])
+def test_ba_attention_mlp_fused(rows, C, pd):
+    """htd_ba_mlp_fwd / _bwd (tanh MLP of the BA attention on the bin means) against the same
+    expressions in torch fp32 on the parameter values the kernel reads."""
+    from htd_b200 import _lib
+    from htd_b200._lib import check, dt, lib, ptr, stream
+    T = dict(f32=torch.float32, bf16=torch.bfloat16)[pd]
+    g = torch.Generator(device='cuda').manual_seed(rows + C)
+    rnd = lambda *s: torch.randn(*s, device='cuda', generator=g)
+    m = rnd(rows, C)
+    w1, b1, w2, b2 = (0.08 * rnd(128, C)).to(T), (0.1 * rnd(128)).to(T), rnd(128).to(T), rnd(1).to(T)
+    h = torch.empty(rows, 128, device='cuda')
+    logits = torch.empty(rows, device='cuda')
+    check(lib().htd_ba_mlp_fwd(ptr(m), rows, C, 128, ptr(w1), ptr(b1), ptr(w2), ptr(b2), dt(w1),
+                               ptr(h), ptr(logits), stream()), 'htd_ba_mlp_fwd')
+    W1, B1, W2, B2 = w1.float(), b1.float(), w2.float(), b2.float()
+    saved = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        h_ref = torch.tanh(m @ W1.t() + B1)
+        l_ref = h_ref @ W2 + B2
+        assert (h - h_ref).abs().max() <= 5e-6 and (logits - l_ref).abs().max() <= 5e-5   # fp32 sums, other order
+        da = rnd(rows)
+        dm = torch.empty(rows, C, device='cuda')
+        ws = torch.empty(int(lib().htd_ba_mlp_workspace_floats(rows, C)), device='cuda')
+        dw1, db1 = torch.empty_like(w1), torch.empty_like(b1)
+        dw2, db2 = torch.empty_like(w2), torch.empty_like(b2)
+        check(lib().htd_ba_mlp_bwd(ptr(da), ptr(h), ptr(m), rows, C, 128, ptr(w1), ptr(w2), dt(w1),
+                                   1.0 / 49, ptr(dm), ptr(ws), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2),
+                                   stream()), 'htd_ba_mlp_bwd')
+        dpre = (da[:, None] * W2[None, :]) * (1 - h_ref * h_ref)
+        tol = 1e-5 if pd == 'f32' else 8e-3
+        from oracle import cases
+        assert cases.rel_err(dm, dpre @ W1 / 49) <= 1e-5
+        assert cases.rel_err(dw1.float(), dpre.t() @ m) <= tol
+        assert cases.rel_err(db1.float(), dpre.sum(0)) <= tol
+        assert cases.rel_err(dw2.float(), (da[:, None] * h_ref).sum(0)) <= tol
+        assert cases.rel_err(db2.float(), da.sum().reshape(1)) <= tol
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+
+
 @pytest.mark.parametrize('N,R,S', [
     (5, 49, 256), (5, 256, 49),            # whole-matrix form, both directions of the flatten order
     (2, 256, 200 * 336), (2, 256, 100 * 167), (2, 256, 25 * 42), (2, 256, 13 * 21),  # tiled, widths 4/4/2/1
