@@ -94,6 +94,7 @@ struct DenseParams {
     const __nv_bfloat16* gate;    // [M, N] (row-major) or [N, M] (transposed): v *= gate > 0
     long long ldg;
     float* partial;               // [splits, M, N] fp32 (splits > 1)
+    int pair;                     // CTA-pair form (dense_pair_kernel): tiles_m counts 256-row tiles
 };
 
 __device__ __forceinline__ void fence_proxy_async() {
@@ -116,6 +117,108 @@ __device__ __forceinline__ bool dense_work(const DenseParams& p, int item, Dense
     wk.mt = rem - wk.nt * p.tiles_m;
     wk.two = kDSuper && p.M - wk.mt * kDTileM > kDBM;
     return true;
+}
+
+// One 32-column chunk of one accumulator row: f[j] = column n0 + j of row m, nc columns count.
+// conv_t tiles (D^T = [pixel, channel]): columns [jl, jh) of the chunk are padding between the two
+// halves of a CTA-pair tile and are skipped, the columns after them move up by jh - jl pixels
+// (jl = jh = 32: none).
+__device__ __forceinline__ void dense_store_chunk(const DenseParams& p, bool conv_t, int sp, int m,
+                                                  int rcls, int n0, int nc, int jl, int jh,
+                                                  float (&f)[32]) {
+    if (conv_t) {                                      // out[pixel, m]: lanes = channels
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + (size_t)n0 * p.ldd + m;
+        const __nv_bfloat16* g = p.gate ? p.gate + (size_t)n0 * p.ldg + m : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nc && !(j >= jl && j < jh)) {
+                const int r = j >= jh ? j - (jh - jl) : j;             // pixel row after the gap
+                float x = f[j];
+                if (p.relu) x = fmaxf(x, 0.f);
+                if (g && !(__bfloat162float(g[(size_t)r * p.ldg]) > 0.f)) x = 0.f;
+                o[(size_t)r * p.ldd] = __float2bfloat16_rn(x);
+            }
+        return;
+    }
+    if (p.splits > 1) {                                // fp32 partial, finished later
+        float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
+        if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nc) o[j] = f[j];
+        }
+        return;
+    }
+    // row-major: bias, second output with the per-row-class bias, relu, gate
+    if (p.bias != nullptr) {
+        if (p.bias_bf16) {
+            const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(p.bias) + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nc) f[j] += __bfloat162float(bb[j]);
+        } else {
+            const float* bb = static_cast<const float*>(p.bias) + n0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nc) f[j] += __ldg(bb + j);
+        }
+    }
+    if (p.D2 != nullptr) {
+        const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
+        __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nc) {
+                float x = f[j] + __ldg(rb + j);
+                if (p.relu) x = fmaxf(x, 0.f);
+                o2[j] = __float2bfloat16_rn(x);
+            }
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (p.gate != nullptr) {
+        const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
+    }
+    const size_t base = (size_t)m * p.ldd + n0;
+    if (p.d_bf16) {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
+        if (nc == 32 && (base & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t u[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
+                    u[t] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
+        }
+    } else {
+        float* o = static_cast<float*>(p.D) + base;
+        if (nc == 32 && (base & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nc) o[j] = f[j];
+        }
+    }
 }
 
 // Why 256 x 256 per CTA: the kernel is bound by the L2 -> SM operand delivery (about 35-40 B per
@@ -343,102 +446,10 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
                     if (!row_ok) continue;
                     const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
-                    const int n0 = col0 + ch * 32;
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (conv_t) {                                      // out[pixel, m]: lanes = channels
-                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + (size_t)n0 * p.ldd + m;
-                        const __nv_bfloat16* g = p.gate ? p.gate + (size_t)n0 * p.ldg + m : nullptr;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) {
-                                float x = f[j];
-                                if (p.relu) x = fmaxf(x, 0.f);
-                                if (g && !(__bfloat162float(g[(size_t)j * p.ldg]) > 0.f)) x = 0.f;
-                                o[(size_t)j * p.ldd] = __float2bfloat16_rn(x);
-                            }
-                        continue;
-                    }
-                    if (p.splits > 1) {                                // fp32 partial, finished later
-                        float* o = p.partial + ((size_t)sp * p.M + m) * p.N + n0;
-                        if (nc == 32 && (((size_t)m * p.N + n0) & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) o[j] = f[j];
-                        }
-                        continue;
-                    }
-                    // row-major: bias, second output with the per-row-class bias, relu, gate
-                    if (p.bias != nullptr) {
-                        if (p.bias_bf16) {
-                            const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(p.bias) + n0;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) f[j] += __bfloat162float(bb[j]);
-                        } else {
-                            const float* bb = static_cast<const float*>(p.bias) + n0;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) f[j] += __ldg(bb + j);
-                        }
-                    }
-                    if (p.D2 != nullptr) {
-                        const float* rb = p.row_bias + (size_t)rcls * p.ld_rb + n0;
-                        __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(p.D2) + (size_t)m * p.ldd + n0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc) {
-                                float x = f[j] + __ldg(rb + j);
-                                if (p.relu) x = fmaxf(x, 0.f);
-                                o2[j] = __float2bfloat16_rn(x);
-                            }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    if (p.gate != nullptr) {
-                        const __nv_bfloat16* g = p.gate + (size_t)m * p.ldg + n0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nc && !(__bfloat162float(g[j]) > 0.f)) f[j] = 0.f;
-                    }
-                    const size_t base = (size_t)m * p.ldd + n0;
-                    if (p.d_bf16) {
-                        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.D) + base;
-                        if (nc == 32 && (base & 7) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) {
-                                uint32_t u[4];
-#pragma unroll
-                                for (int t = 0; t < 4; ++t) {
-                                    __nv_bfloat162 h = __floats2bfloat162_rn(f[j + 2 * t], f[j + 2 * t + 1]);
-                                    u[t] = *reinterpret_cast<uint32_t*>(&h);
-                                }
-                                *reinterpret_cast<uint4*>(o + j) = make_uint4(u[0], u[1], u[2], u[3]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) o[j] = __float2bfloat16_rn(f[j]);
-                        }
-                    } else {
-                        float* o = static_cast<float*>(p.D) + base;
-                        if (nc == 32 && (base & 3) == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (j < nc) o[j] = f[j];
-                        }
-                    }
+                    dense_store_chunk(p, conv_t, sp, m, rcls, col0 + ch * 32, nc, 32, 32, f);
                 }
                 tc::fence_before();
                 __syncwarp();
@@ -451,6 +462,214 @@ __global__ void __launch_bounds__(kDThreads, 1)
     if (warp == 1) {
         tc::fence_after();
         tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair form (cta_group::2): a cluster of two CTAs works on one 256-row tile.  CTA r stages rows
+// m0 + 128 r .. of A and columns r * bn/2 .. of B, the even CTA issues M = 256 UMMAs that read both
+// CTAs' shared memory and write both CTAs' TMEM (its own 128 rows in each).  Per k-block and SM
+// that is 16 KB of A + half a B tile for a 128 x bn accumulator - two thirds of the bytes of the
+// single-CTA form, which is bound by L2 -> SM delivery (profiles/r02_dense_notes.md) - and stages
+// of 30-32 KB make the ring six deep.  Conv tiles are 4 RoIs: each CTA's half holds 2 RoIs = 98
+// pixel rows in a 104-row half (UMMA N = 208; columns 98..103 of each half are padding).
+//   full[s]   lives in the leader: 2 arrivals (one expect_tx per CTA) + the bytes of both CTAs
+//   empty[s]  in each CTA: the leader's commit arrives on both (multicast)
+//   tfull[a]  in each CTA: same;  tempty[a] in the leader: 8 arrivals (4 epilogue warps x 2 CTAs)
+// ------------------------------------------------------------------------------------------------
+constexpr int kPairStages = 6;
+constexpr int kPairRois = 2, kPairHalfRows = 104;        // conv: RoIs / rows of one CTA's B half
+constexpr int kPairJunk0 = kPairRois * kPP;              // 98: first padding column of a half
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
+    dense_pair_kernel(const __grid_constant__ CUtensorMap map_a,
+                      const __grid_constant__ CUtensorMap map_b, const DenseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    const int nst = p.nstages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDRingBytes);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tfull_bar = empty_bar + 8;              // [2] accumulator slots
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int first = (int)(blockIdx.x >> 1), stride = (int)(gridDim.x >> 1);
+    const bool conv_t = p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD;
+    const int half_n = p.bn / 2;                      // B columns (K-major: rows) per CTA
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_map(&map_a);
+        tc::prefetch_map(&map_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < 8; ++s) {
+                mbar_init(full_bar + s, 2);
+                mbar_init(empty_bar + s, 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(tfull_bar + a, 1);
+                mbar_init(tempty_bar + a, 8);
+            }
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc_pair(tmem_slot, 512);
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();                           // the peer's barriers exist before any remote arrive
+    tc::fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs: own half of A and of B, signalled to the leader) =====
+        if (lane == 0) {
+            unsigned it = 0;
+            DenseWork wk;
+            const unsigned tx = p.a_half_tx + p.b_tx;            // bytes this CTA lands per stage
+            for (int item = first; dense_work(p, item, wk); item += stride) {
+                const int nt = wk.nt, mh = wk.mt * 256 + (int)rank * kDBM;
+                const int kb0 = wk.sp * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % nst;
+                    mbar_wait(empty_bar + s, ((it / nst) & 1u) ^ 1u);
+                    const uint32_t bar = tc::map_to_cta(full_bar + s, 0);
+                    tc::mbar_expect_tx_cluster(bar, tx);
+                    uint8_t* sa = smem + s * p.stage_bytes;
+                    uint8_t* sb = sa + p.a_bytes;
+                    int tap = 0, kc = 0;
+                    if (conv_t) {
+                        tap = kb / p.kc_per_tap;
+                        kc = kb - tap * p.kc_per_tap;
+                    }
+                    switch (p.kind) {
+                        case HTD_DENSE_NT:
+                            tc::tma_load_2d_pair(&map_a, bar, sa, kb * kDBK, mh);
+                            tc::tma_load_2d_pair(&map_b, bar, sb, kb * kDBK, nt * p.bn + (int)rank * half_n);
+                            break;
+                        case HTD_DENSE_NN:
+                            tc::tma_load_2d_pair(&map_a, bar, sa, kb * kDBK, mh);
+                            for (int c = 0; c < half_n / 64; ++c)
+                                tc::tma_load_2d_pair(&map_b, bar, sb + c * kChunk,
+                                                     nt * p.bn + (int)rank * half_n + c * 64, kb * kDBK);
+                            break;
+                        case HTD_DENSE_TN:
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d_pair(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kDBK);
+                            for (int c = 0; c < half_n / 64; ++c)
+                                tc::tma_load_2d_pair(&map_b, bar, sb + c * kChunk,
+                                                     nt * p.bn + (int)rank * half_n + c * 64, kb * kDBK);
+                            break;
+                        case HTD_DENSE_CONV_FPROP:
+                            tc::tma_load_2d_pair(&map_a, bar, sa, tap * p.Cin + kc * 64, mh);
+                            tc::tma_load_4d_pair(&map_b, bar, sb, kc * 64, tap % 3 - 1, tap / 3 - 1,
+                                                 (nt * 2 + (int)rank) * kPairRois);
+                            break;
+                        default:   // HTD_DENSE_CONV_DGRAD
+                            for (int c = 0; c < 2; ++c)
+                                tc::tma_load_2d_pair(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
+                                                     kc * 64);
+                            tc::tma_load_4d_pair(&map_b, bar, sb, kc * 64, 1 - tap % 3, 1 - tap / 3,
+                                                 (nt * 2 + (int)rank) * kPairRois);
+                            break;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = tc::make_idesc(256, p.bn, p.a_mn, p.b_mn);
+            unsigned it = 0, uses[2] = {0u, 0u}, ntile = 0;
+            DenseWork wk;
+            for (int item = first; dense_work(p, item, wk); item += stride) {
+                const int kb0 = wk.sp * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+                const unsigned s0 = ntile++ & 1u;
+                mbar_wait(tempty_bar + s0, (uses[s0] & 1u) ^ 1u);
+                tc::fence_after();
+                const uint32_t acc0 = tmem_base + s0 * 256;
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int s = it % nst;
+                    mbar_wait(full_bar + s, (it / nst) & 1u);
+                    tc::fence_after();
+                    const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
+                    const uint32_t sb = sa + (uint32_t)p.a_bytes;
+#pragma unroll
+                    for (int k = 0; k < kDBK / 16; ++k) {
+                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
+                                                   : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
+                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
+                                                   : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
+                        tc::umma_bf16_pair(acc0, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    tc::commit_pair(empty_bar + s, 3);
+                }
+                tc::commit_pair(tfull_bar + s0, 3);
+                ++uses[s0];
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5 of both CTAs): rows m0 + 128 rank + .. of the pair tile =====
+        const int q = warp & 3;
+        unsigned uses[2] = {0u, 0u}, ntile = 0;
+        DenseWork wk;
+        for (int item = first; dense_work(p, item, wk); item += stride) {
+            const int sp = wk.sp, nt = wk.nt;
+            const bool has_k = sp * p.kb_per_split < p.kblocks;
+            // columns of this tile: conv = 4 RoIs in two halves with padding, GEMM = bn columns
+            const int col0 = conv_t ? nt * 2 * kPairRois * kPP : nt * p.bn;
+            const int ncols = conv_t ? p.bn : min(p.bn, p.N - col0);
+            const unsigned slot = ntile++ & 1u;
+            mbar_wait(tfull_bar + slot, uses[slot] & 1u);
+            ++uses[slot];
+            tc::fence_after();
+            const int m = wk.mt * 256 + (int)rank * kDBM + q * 32 + lane;
+            const bool row_ok = m < p.M && has_k;
+            const int rcls = (row_ok && p.row_class != nullptr) ? p.row_class[m] : 0;
+#pragma unroll 1
+            for (int ch = 0; ch * 32 < ncols; ++ch) {
+                uint32_t v[32];
+                __syncwarp();
+                tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
+                if (!row_ok) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                const int c0 = ch * 32;
+                int nc = min(32, ncols - c0), n0 = col0 + c0, jl = 32, jh = 32;
+                if (conv_t) {
+                    // column c of the tile: half = c / 104, pixel = col0 + half * 98 + c % 104 (< 98)
+                    const int half = c0 >= kPairHalfRows ? 1 : 0;
+                    const int in_half = c0 - half * kPairHalfRows;
+                    n0 = col0 + half * kPairJunk0 + in_half;
+                    // the padding window(s) that intersect this chunk, relative to the chunk
+                    int gl = kPairJunk0 - in_half, gh = kPairHalfRows - in_half;   // of this half
+                    if (gh <= 0) { gl += kPairHalfRows; gh += kPairHalfRows; }     // next half's
+                    jl = max(0, min(32, gl));
+                    jh = max(0, min(32, gh));
+                    const int room = p.N - n0;                   // pixels left in the output
+                    const int lim = room <= jl ? room : room + (jh - jl);
+                    nc = max(0, min(nc, lim));
+                }
+                dense_store_chunk(p, conv_t, sp, m, rcls, n0, nc, jl, jh, f);
+            }
+            tc::fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(tc::map_to_cta(tempty_bar + slot, 0));
+        }
+    }
+    tc::fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();                           // nobody leaves while the peer may still touch it
+    if (warp == 1) {
+        tc::fence_after();
+        tc::tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -618,10 +837,16 @@ static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParam
     if (per_split <= 0 || p.kblocks <= 0) return HTD_OK;
     const long long items = per_split * p.splits;
     HTD_CHECK_ARG(items < 2147483647LL, "htd_dense_gemm: too many tiles");
-    HTD_SMEM_OPTIN(dense_gemm_kernel, kDSmem, "htd_dense_gemm");
     const int sms = sm_count();
-    const unsigned grid = (unsigned)(items < sms ? items : sms);
-    dense_gemm_kernel<<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
+    if (p.pair) {
+        HTD_SMEM_OPTIN(dense_pair_kernel, kDSmem, "htd_dense_gemm(pair)");
+        const long long clusters = items < sms / 2 ? items : sms / 2;
+        dense_pair_kernel<<<(unsigned)(2 * clusters), kDThreads, kDSmem, st>>>(ma, mb, p);
+    } else {
+        HTD_SMEM_OPTIN(dense_gemm_kernel, kDSmem, "htd_dense_gemm");
+        const unsigned grid = (unsigned)(items < sms ? items : sms);
+        dense_gemm_kernel<<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
+    }
     HTD_CHECK_LAUNCH("htd_dense_gemm");
     if (p.splits > 1) {
         const long long quads = (long long)p.M * ((p.N + 3) / 4);
@@ -630,6 +855,15 @@ static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParam
         HTD_CHECK_LAUNCH("htd_dense_gemm(finish)");
     }
     return HTD_OK;
+}
+
+static int dense_pair_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("HTD_DENSE_PAIR");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
 }
 
 static int pick_splits(long long tiles, int kblocks, int want, int sms) {
@@ -770,9 +1004,41 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             }
         }
     }
+    // ---- CTA-pair form where it applies (HTD_DENSE_PAIR=0 turns it off, =2 extends it from the
+    // conv fprop / dgrad kinds to the plain GEMM kinds)
+    const int pair_mode = dense_pair_mode();
+    bool pair = false;
+    if (pair_mode >= 1 && (g->kind == HTD_DENSE_CONV_FPROP || g->kind == HTD_DENSE_CONV_DGRAD)) {
+        pair = true;
+        p.bn = 2 * kPairHalfRows;                                   // UMMA N = 208
+        p.tiles_n = (int)((g->P + 2 * kPairRois - 1) / (2 * kPairRois));
+        p.b_tx = (unsigned)(kPairRois * kPP * 128);
+        p.stage_bytes = kDAHalf + ((kPairHalfRows * 128 + 1023) & ~1023);
+        if (maps) {
+            const int ch = (int)(g->kind == HTD_DENSE_CONV_FPROP ? g->Cin : g->Cout);
+            rc = tc::make_map_roi(mb, g->B, g->P, 7, ch, kPairRois, "htd_dense_gemm(conv pair B)");
+            if (rc) return rc;
+        }
+    } else if (pair_mode >= 2 && g->kind <= HTD_DENSE_TN && p.M > kDBM &&
+               (p.b_mn ? p.bn % 128 == 0 : p.bn % 16 == 0) && p.bn >= 32) {
+        pair = true;
+        const int half_n = p.bn / 2;
+        p.b_tx = (unsigned)(p.b_mn ? half_n / 64 * kChunk : half_n * kDBK * 2);
+        p.stage_bytes = kDAHalf + (int)((p.b_tx + 1023u) & ~1023u);
+        if (maps && !p.b_mn) {                                      // K-major B: box of bn/2 rows
+            rc = tc::make_map_2d(mb, g->B, g->N, g->K, g->ldb, half_n, "htd_dense_gemm(pair B)");
+            if (rc) return rc;
+        }
+    }
+    if (pair) {
+        p.pair = 1;
+        p.tiles_m = (p.M + 255) / 256;
+        p.a_bytes = kDAHalf;
+        p.nstages = kDRingBytes / p.stage_bytes < kPairStages ? kDRingBytes / p.stage_bytes : kPairStages;
+    }
     const long long tiles = (long long)p.tiles_m * p.tiles_n;
     const bool can_split = !p.transposed;
-    p.splits = can_split ? pick_splits(tiles, p.kblocks, g->splits, sms) : 1;
+    p.splits = can_split ? pick_splits(tiles, p.kblocks, g->splits, pair ? sms / 2 : sms) : 1;
     p.kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;      // no empty slice
     return HTD_OK;
