@@ -861,7 +861,7 @@ static int dense_pair_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("HTD_DENSE_PAIR");
-        mode = e ? atoi(e) : 1;
+        mode = e ? atoi(e) : 0;   // off until validated on the GPU
     }
     return mode;
 }
