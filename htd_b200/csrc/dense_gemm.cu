@@ -44,6 +44,7 @@ namespace htd {
 #define HTD_DENSE_SUPER 0
 #endif
 constexpr int kDSuper = HTD_DENSE_SUPER;
+static_assert(kDSuper == 0, "the 256-row super tile was measured slower and its role loops were removed");
 constexpr int kDBM = 128, kDBK = 64, kDStages = kDSuper ? 3 : 4;
 constexpr int kDTileM = (kDSuper ? 2 : 1) * kDBM;    // rows of a work item
 constexpr int kDAHalf = kDBM * kDBK * 2;             // 16 KiB: one 128-row half of the A stage
@@ -95,6 +96,7 @@ struct DenseParams {
     long long ldg;
     float* partial;               // [splits, M, N] fp32 (splits > 1)
     int pair;                     // CTA-pair form (dense_pair_kernel): tiles_m counts 256-row tiles
+    int debug;                    // experiments (HTD_DENSE_DEBUG): 1 = no MMA issue, 2 = no TMA loads
 };
 
 __device__ __forceinline__ void fence_proxy_async() {
@@ -277,135 +279,136 @@ __global__ void __launch_bounds__(kDThreads, 1)
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            unsigned it = 0;
-            DenseWork wk;
-            for (int item = first; dense_work(p, item, wk); item += stride) {
-                const int nt = wk.nt, m0 = wk.mt * kDTileM;
-                const int kb0 = wk.sp * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                const int halves = wk.two ? 2 : 1;
-                const unsigned tx = p.b_tx + halves * p.a_half_tx;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % nst;
-                    mbar_wait(empty_bar + s, ((it / nst) & 1u) ^ 1u);
-                    mbar_expect_tx(full_bar + s, tx);
-                    uint8_t* stage = smem + s * p.stage_bytes;
-                    uint8_t* sb = stage + p.a_bytes;
+        // The loops of the two single-thread roles are executed by the WHOLE warp (waits by all
+        // lanes, the issue by lane 0), and their bodies are kept short: one warp retires a
+        // dependent instruction every 4-6 clocks, so the ~150 instructions per k-block of the first
+        // version (runtime divisions for stage / phase / filter tap, descriptors rebuilt from
+        // scratch) were a floor of ~700 clk per k-block on their own - more than the MMAs (490)
+        // and as much as the operand delivery (profiles/r02_dense_notes.md, section 6).
+        unsigned s = 0, ph = 0;                       // ring stage and its phase bit
+        DenseWork wk;
+        const bool conv_t = p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD;
+        for (int item = first; dense_work(p, item, wk); item += stride) {
+            const int nt = wk.nt, m0 = wk.mt * kDTileM;
+            const int kb0 = wk.sp * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+            const unsigned tx = p.b_tx + p.a_half_tx;
+            // filter tap (dx, dy) and 64-channel chunk of the k-block, advanced incrementally
+            int tap = 0, kc = 0, dx = -1, dy = -1;
+            if (conv_t) {
+                tap = kb0 / p.kc_per_tap;
+                kc = kb0 - tap * p.kc_per_tap;
+                dy = tap / 3 - 1;
+                dx = tap - (dy + 1) * 3 - 1;
+            }
+            const int wtap = p.kind == HTD_DENSE_CONV_WGRAD ? nt / p.nt_per_tap : 0;
+            const int wn = nt - wtap * p.nt_per_tap, wdy = wtap / 3 - 1, wdx = wtap - (wdy + 1) * 3 - 1;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar + s, ph ^ 1u);
+                if (lane == 0) {
                     uint64_t* bar = full_bar + s;
-                    int tap = 0, kc = 0;
-                    if (p.kind == HTD_DENSE_CONV_FPROP || p.kind == HTD_DENSE_CONV_DGRAD) {
-                        tap = kb / p.kc_per_tap;
-                        kc = kb - tap * p.kc_per_tap;
-                    }
-                    // ---- A: one or two 128-row halves
-                    for (int hh = 0; hh < halves; ++hh) {
-                        uint8_t* sa = stage + hh * kDAHalf;
-                        const int mh = m0 + hh * kDBM;
+                    uint8_t* sa = smem + s * p.stage_bytes;
+                    uint8_t* sb = sa + p.a_bytes;
+                    if (p.debug & 2) {                // experiment: barrier traffic only
+                        mbar_arrive(bar);
+                    } else {
+                        mbar_expect_tx(bar, tx);
                         switch (p.kind) {
                             case HTD_DENSE_NT:
+                                tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, m0);
+                                tc::tma_load_2d(&map_b, bar, sb, kb * kDBK, nt * p.bn);
+                                break;
                             case HTD_DENSE_NN:
-                                tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, mh);
+                                tc::tma_load_2d(&map_a, bar, sa, kb * kDBK, m0);
+                                for (int c = 0; c < nb_chunks; ++c)
+                                    tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
                                 break;
                             case HTD_DENSE_TN:
                                 for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kDBK);
+                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, m0 + c * 64, kb * kDBK);
+                                for (int c = 0; c < nb_chunks; ++c)
+                                    tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
                                 break;
                             case HTD_DENSE_CONV_FPROP:
-                                tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, mh);
+                                tc::tma_load_2d(&map_a, bar, sa, tap * p.Cin + kc * 64, m0);
+                                tc::tma_load_4d(&map_b, bar, sb, kc * 64, dx, dy, nt * kRoisPerTile);
                                 break;
                             case HTD_DENSE_CONV_DGRAD:
                                 for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
+                                    tc::tma_load_2d(&map_a, bar, sa + c * kChunk, tap * p.Cin + m0 + c * 64,
                                                     kc * 64);
+                                tc::tma_load_4d(&map_b, bar, sb, kc * 64, -dx, -dy, nt * kRoisPerTile);
                                 break;
                             default:   // HTD_DENSE_CONV_WGRAD: k-block = rois_per_kb RoIs
                                 for (int c = 0; c < 2; ++c)
-                                    tc::tma_load_2d(&map_a, bar, sa + c * p.chunk_bytes, mh + c * 64,
+                                    tc::tma_load_2d(&map_a, bar, sa + c * p.chunk_bytes, m0 + c * 64,
                                                     kb * p.rois_per_kb * kPP);
+                                for (int c = 0; c < nb_chunks; ++c)
+                                    tc::tma_load_4d(&map_b, bar, sb + c * p.chunk_bytes, wn * p.bn + c * 64,
+                                                    wdx, wdy, kb * p.rois_per_kb);
                                 break;
                         }
                     }
-                    // ---- B: one tile, shared by both halves
-                    switch (p.kind) {
-                        case HTD_DENSE_NT:
-                            tc::tma_load_2d(&map_b, bar, sb, kb * kDBK, nt * p.bn);
-                            break;
-                        case HTD_DENSE_NN:
-                        case HTD_DENSE_TN:
-                            for (int c = 0; c < nb_chunks; ++c)
-                                tc::tma_load_2d(&map_b, bar, sb + c * kChunk, nt * p.bn + c * 64, kb * kDBK);
-                            break;
-                        case HTD_DENSE_CONV_FPROP:
-                            tc::tma_load_4d(&map_b, bar, sb, kc * 64, tap % 3 - 1, tap / 3 - 1,
-                                            nt * kRoisPerTile);
-                            break;
-                        case HTD_DENSE_CONV_DGRAD:
-                            tc::tma_load_4d(&map_b, bar, sb, kc * 64, 1 - tap % 3, 1 - tap / 3,
-                                            nt * kRoisPerTile);
-                            break;
-                        default: {
-                            const int tp = nt / p.nt_per_tap, nn = nt - tp * p.nt_per_tap;
-                            for (int c = 0; c < nb_chunks; ++c)
-                                tc::tma_load_4d(&map_b, bar, sb + c * p.chunk_bytes, nn * p.bn + c * 64,
-                                                tp % 3 - 1, tp / 3 - 1, kb * p.rois_per_kb);
-                            break;
-                        }
-                    }
+                }
+                __syncwarp();
+                if (++s == (unsigned)nst) { s = 0; ph ^= 1u; }
+                if (conv_t && ++kc == p.kc_per_tap) {
+                    kc = 0;
+                    ++tap;
+                    if (++dx == 2) { dx = -1; ++dy; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = tc::make_idesc(kDBM, p.bn, p.a_mn, p.b_mn);
-            unsigned it = 0, uses[2] = {0u, 0u}, nsingle = 0;
-            DenseWork wk;
-            for (int item = first; dense_work(p, item, wk); item += stride) {
-                const int kb0 = wk.sp * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                // accumulator slots: a 256-row tile takes both, a 128-row tile alternates
-                const unsigned s0 = wk.two ? 0u : (nsingle++ & 1u);
-                mbar_wait(tempty_bar + s0, (uses[s0] & 1u) ^ 1u);
-                if (wk.two) mbar_wait(tempty_bar + 1, (uses[1] & 1u) ^ 1u);
+        // ===== MMA issuer (whole warp in the loop, lane 0 issues) =====
+        const uint32_t idesc = tc::make_idesc(kDBM, p.bn, p.a_mn, p.b_mn);
+        const uint32_t chunk = (uint32_t)p.chunk_bytes;
+        // descriptors of stage 0; a stage / a K=16 step further is an addition to the 14-bit
+        // start-address field (16-byte units; the ring ends below 2^18 bytes, so no carry out)
+        const uint32_t s0a = smem_u32(smem), s0b = s0a + (uint32_t)p.a_bytes;
+        const uint64_t ad0 = p.a_mn ? tc::desc_mnmajor(s0a, chunk) : tc::desc_kmajor(s0a);
+        const uint64_t bd0 = p.b_mn ? tc::desc_mnmajor(s0b, chunk) : tc::desc_kmajor(s0b);
+        const uint64_t a_k = p.a_mn ? 128u : 2u, b_k = p.b_mn ? 128u : 2u;   // 2048 B / 32 B per step
+        const uint64_t st_d = (uint64_t)(p.stage_bytes >> 4);
+        unsigned s = 0, ph = 0, uses[2] = {0u, 0u}, nsingle = 0;
+        DenseWork wk;
+        for (int item = first; dense_work(p, item, wk); item += stride) {
+            const int kb0 = wk.sp * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+            const unsigned slot = nsingle++ & 1u;     // accumulator slots alternate
+            mbar_wait(tempty_bar + slot, (uses[slot] & 1u) ^ 1u);
+            tc::fence_after();
+            const uint32_t acc0 = tmem_base + slot * 256;
+            uint32_t accum = 0u;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full_bar + s, ph);
                 tc::fence_after();
-                const uint32_t acc0 = tmem_base + s0 * 256, acc1 = tmem_base + 256;
-                const uint32_t chunk = (uint32_t)p.chunk_bytes;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % nst;
-                    mbar_wait(full_bar + s, (it / nst) & 1u);
-                    tc::fence_after();
-                    const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
-                    const uint32_t sb = sa + (uint32_t)p.a_bytes;
-                    auto mma_step = [&](int k) {
-                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, chunk)
-                                                   : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
-                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, chunk)
-                                                   : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
-                        const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-                        tc::umma_bf16(acc0, ad, bd, idesc, acc);
-                        if (wk.two) {
-                            const uint64_t ad1 = p.a_mn ? tc::desc_mnmajor(sa + kDAHalf + k * 2048, chunk)
-                                                        : tc::desc_kmajor(sa + kDAHalf) + (uint64_t)(2 * k);
-                            tc::umma_bf16(acc1, ad1, bd, idesc, acc);
-                        }
-                    };
-                    if (p.ksteps == kDBK / 16) {          // the common stage: 64 k = 4 steps, unrolled
+                if (lane == 0) {
+                    const uint64_t ad = ad0 + s * st_d, bd = bd0 + s * st_d;
+                    if (!(p.debug & 1)) {
+                        if (p.ksteps == kDBK / 16) {      // the common stage: 64 k = 4 steps, unrolled
 #pragma unroll
-                        for (int k = 0; k < kDBK / 16; ++k) mma_step(k);
-                    } else {
+                            for (int k = 0; k < kDBK / 16; ++k) {
+                                tc::umma_bf16(acc0, ad + k * a_k, bd + k * b_k, idesc, accum);
+                                accum = 1u;
+                            }
+                        } else {
 #pragma unroll 1
-                        for (int k = 0; k < p.ksteps; ++k) mma_step(k);
+                            for (int k = 0; k < p.ksteps; ++k) {
+                                tc::umma_bf16(acc0, ad + k * a_k, bd + k * b_k, idesc, accum);
+                                accum = 1u;
+                            }
+                        }
                     }
-                    tc::commit(empty_bar + s);
+                    if (p.debug & 8) mbar_arrive(empty_bar + s);   // experiment (with 1): no commit
+                    else tc::commit(empty_bar + s);
                 }
-                tc::commit(tfull_bar + s0);
-                ++uses[s0];
-                if (wk.two) {
-                    tc::commit(tfull_bar + 1);
-                    ++uses[1];
-                }
+                __syncwarp();
+                if (++s == (unsigned)nst) { s = 0; ph ^= 1u; }
             }
+            if (lane == 0) tc::commit(tfull_bar + slot);
+            ++uses[slot];
+            __syncwarp();
         }
     } else {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
@@ -430,10 +433,14 @@ __global__ void __launch_bounds__(kDThreads, 1)
                 col0 = nt * p.bn;
                 nvalid = min(p.bn, p.N - col0);
             }
-            const unsigned s0 = wk.two ? 0u : (nsingle++ & 1u);
-            for (int hh = 0; hh < (wk.two ? 2 : 1); ++hh) {
-                const unsigned slot = hh == 0 ? s0 : 1u;
-                mbar_wait(tfull_bar + slot, uses[slot] & 1u);
+            for (int hh = 0; hh < 1; ++hh) {
+                const unsigned slot = nsingle++ & 1u;
+                if (p.debug & 32) {                          // experiment: one polling lane per warp
+                    if (lane == 0) mbar_wait(tfull_bar + slot, uses[slot] & 1u);
+                    __syncwarp();
+                } else {
+                    mbar_wait(tfull_bar + slot, uses[slot] & 1u);
+                }
                 ++uses[slot];
                 tc::fence_after();
                 const int m = wk.mt * kDTileM + hh * kDBM + q * 32 + lane;
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     uint32_t v[32];
                     __syncwarp();
                     tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
-                    if (!row_ok) continue;
+                    if (!row_ok || (p.debug & 4)) continue;
                     const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
                     float f[32];
 #pragma unroll
@@ -527,91 +534,112 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs: own half of A and of B, signalled to the leader) =====
-        if (lane == 0) {
-            unsigned it = 0;
-            DenseWork wk;
-            const unsigned tx = p.a_half_tx + p.b_tx;            // bytes this CTA lands per stage
-            for (int item = first; dense_work(p, item, wk); item += stride) {
-                const int nt = wk.nt, mh = wk.mt * 256 + (int)rank * kDBM;
-                const int kb0 = wk.sp * p.kb_per_split;
-                const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % nst;
-                    mbar_wait(empty_bar + s, ((it / nst) & 1u) ^ 1u);
-                    const uint32_t bar = tc::map_to_cta(full_bar + s, 0);
-                    tc::mbar_expect_tx_cluster(bar, tx);
+        unsigned s = 0, ph = 0;
+        DenseWork wk;
+        const unsigned tx = p.a_half_tx + p.b_tx;            // bytes this CTA lands per stage
+        const int nhalf_chunks = half_n / 64;
+        uint32_t bar0 = 0;
+        if (lane == 0) bar0 = tc::map_to_cta(full_bar, 0);   // the leader's full[0]; full[s] = +8 s
+        for (int item = first; dense_work(p, item, wk); item += stride) {
+            const int nt = wk.nt, mh = wk.mt * 256 + (int)rank * kDBM;
+            const int kb0 = wk.sp * p.kb_per_split;
+            const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
+            const int nb = nt * p.bn + (int)rank * half_n;   // GEMM kinds: first B column of this CTA
+            const int roi0 = (nt * 2 + (int)rank) * kPairRois;
+            int tap = 0, kc = 0, dx = -1, dy = -1;
+            if (conv_t) {
+                tap = kb0 / p.kc_per_tap;
+                kc = kb0 - tap * p.kc_per_tap;
+                dy = tap / 3 - 1;
+                dx = tap - (dy + 1) * 3 - 1;
+            }
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(empty_bar + s, ph ^ 1u);
+                if (lane == 0) {
+                    const uint32_t bar = bar0 + 8u * s;
                     uint8_t* sa = smem + s * p.stage_bytes;
                     uint8_t* sb = sa + p.a_bytes;
-                    int tap = 0, kc = 0;
-                    if (conv_t) {
-                        tap = kb / p.kc_per_tap;
-                        kc = kb - tap * p.kc_per_tap;
+                    if (p.debug & 2) {                       // experiment: barrier traffic only
+                        tc::mbar_arrive_cluster(bar);
+                    } else {
+                        tc::mbar_expect_tx_cluster(bar, tx);
+                        switch (p.kind) {
+                            case HTD_DENSE_NT:
+                                tc::tma_load_2d_pair(&map_a, bar, sa, kb * kDBK, mh);
+                                tc::tma_load_2d_pair(&map_b, bar, sb, kb * kDBK, nb);
+                                break;
+                            case HTD_DENSE_NN:
+                                tc::tma_load_2d_pair(&map_a, bar, sa, kb * kDBK, mh);
+                                for (int c = 0; c < nhalf_chunks; ++c)
+                                    tc::tma_load_2d_pair(&map_b, bar, sb + c * kChunk, nb + c * 64, kb * kDBK);
+                                break;
+                            case HTD_DENSE_TN:
+                                for (int c = 0; c < 2; ++c)
+                                    tc::tma_load_2d_pair(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kDBK);
+                                for (int c = 0; c < nhalf_chunks; ++c)
+                                    tc::tma_load_2d_pair(&map_b, bar, sb + c * kChunk, nb + c * 64, kb * kDBK);
+                                break;
+                            case HTD_DENSE_CONV_FPROP:
+                                tc::tma_load_2d_pair(&map_a, bar, sa, tap * p.Cin + kc * 64, mh);
+                                tc::tma_load_4d_pair(&map_b, bar, sb, kc * 64, dx, dy, roi0);
+                                break;
+                            default:   // HTD_DENSE_CONV_DGRAD
+                                for (int c = 0; c < 2; ++c)
+                                    tc::tma_load_2d_pair(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
+                                                         kc * 64);
+                                tc::tma_load_4d_pair(&map_b, bar, sb, kc * 64, -dx, -dy, roi0);
+                                break;
+                        }
                     }
-                    switch (p.kind) {
-                        case HTD_DENSE_NT:
-                            tc::tma_load_2d_pair(&map_a, bar, sa, kb * kDBK, mh);
-                            tc::tma_load_2d_pair(&map_b, bar, sb, kb * kDBK, nt * p.bn + (int)rank * half_n);
-                            break;
-                        case HTD_DENSE_NN:
-                            tc::tma_load_2d_pair(&map_a, bar, sa, kb * kDBK, mh);
-                            for (int c = 0; c < half_n / 64; ++c)
-                                tc::tma_load_2d_pair(&map_b, bar, sb + c * kChunk,
-                                                     nt * p.bn + (int)rank * half_n + c * 64, kb * kDBK);
-                            break;
-                        case HTD_DENSE_TN:
-                            for (int c = 0; c < 2; ++c)
-                                tc::tma_load_2d_pair(&map_a, bar, sa + c * kChunk, mh + c * 64, kb * kDBK);
-                            for (int c = 0; c < half_n / 64; ++c)
-                                tc::tma_load_2d_pair(&map_b, bar, sb + c * kChunk,
-                                                     nt * p.bn + (int)rank * half_n + c * 64, kb * kDBK);
-                            break;
-                        case HTD_DENSE_CONV_FPROP:
-                            tc::tma_load_2d_pair(&map_a, bar, sa, tap * p.Cin + kc * 64, mh);
-                            tc::tma_load_4d_pair(&map_b, bar, sb, kc * 64, tap % 3 - 1, tap / 3 - 1,
-                                                 (nt * 2 + (int)rank) * kPairRois);
-                            break;
-                        default:   // HTD_DENSE_CONV_DGRAD
-                            for (int c = 0; c < 2; ++c)
-                                tc::tma_load_2d_pair(&map_a, bar, sa + c * kChunk, tap * p.Cin + mh + c * 64,
-                                                     kc * 64);
-                            tc::tma_load_4d_pair(&map_b, bar, sb, kc * 64, 1 - tap % 3, 1 - tap / 3,
-                                                 (nt * 2 + (int)rank) * kPairRois);
-                            break;
-                    }
+                }
+                __syncwarp();
+                if (++s == (unsigned)nst) { s = 0; ph ^= 1u; }
+                if (conv_t && ++kc == p.kc_per_tap) {
+                    kc = 0;
+                    ++tap;
+                    if (++dx == 2) { dx = -1; ++dy; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (leader CTA only) =====
-        if (lane == 0 && rank == 0) {
+        // ===== MMA issuer (leader CTA only; whole warp in the loop, lane 0 issues) =====
+        if (rank == 0) {
             const uint32_t idesc = tc::make_idesc(256, p.bn, p.a_mn, p.b_mn);
-            unsigned it = 0, uses[2] = {0u, 0u}, ntile = 0;
+            const uint32_t s0a = smem_u32(smem), s0b = s0a + (uint32_t)p.a_bytes;
+            const uint64_t ad0 = p.a_mn ? tc::desc_mnmajor(s0a, kChunk) : tc::desc_kmajor(s0a);
+            const uint64_t bd0 = p.b_mn ? tc::desc_mnmajor(s0b, kChunk) : tc::desc_kmajor(s0b);
+            const uint64_t a_k = p.a_mn ? 128u : 2u, b_k = p.b_mn ? 128u : 2u;
+            const uint64_t st_d = (uint64_t)(p.stage_bytes >> 4);
+            unsigned s = 0, ph = 0, uses[2] = {0u, 0u}, ntile = 0;
             DenseWork wk;
             for (int item = first; dense_work(p, item, wk); item += stride) {
                 const int kb0 = wk.sp * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kblocks);
-                const unsigned s0 = ntile++ & 1u;
-                mbar_wait(tempty_bar + s0, (uses[s0] & 1u) ^ 1u);
+                const unsigned slot = ntile++ & 1u;
+                mbar_wait(tempty_bar + slot, (uses[slot] & 1u) ^ 1u);
                 tc::fence_after();
-                const uint32_t acc0 = tmem_base + s0 * 256;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % nst;
-                    mbar_wait(full_bar + s, (it / nst) & 1u);
+                const uint32_t acc0 = tmem_base + slot * 256;
+                uint32_t accum = 0u;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full_bar + s, ph);
                     tc::fence_after();
-                    const uint32_t sa = smem_u32(smem + s * p.stage_bytes);
-                    const uint32_t sb = sa + (uint32_t)p.a_bytes;
+                    if (lane == 0) {
+                        const uint64_t ad = ad0 + s * st_d, bd = bd0 + s * st_d;
+                        if (!(p.debug & 1)) {
 #pragma unroll
-                    for (int k = 0; k < kDBK / 16; ++k) {
-                        const uint64_t bd = p.b_mn ? tc::desc_mnmajor(sb + k * 2048, kChunk)
-                                                   : tc::desc_kmajor(sb) + (uint64_t)(2 * k);
-                        const uint64_t ad = p.a_mn ? tc::desc_mnmajor(sa + k * 2048, kChunk)
-                                                   : tc::desc_kmajor(sa) + (uint64_t)(2 * k);
-                        tc::umma_bf16_pair(acc0, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kDBK / 16; ++k) {
+                                tc::umma_bf16_pair(acc0, ad + k * a_k, bd + k * b_k, idesc, accum);
+                                accum = 1u;
+                            }
+                        }
+                        tc::commit_pair(empty_bar + s, 3);
                     }
-                    tc::commit_pair(empty_bar + s, 3);
+                    __syncwarp();
+                    if (++s == (unsigned)nst) { s = 0; ph ^= 1u; }
                 }
-                tc::commit_pair(tfull_bar + s0, 3);
-                ++uses[s0];
+                if (lane == 0) tc::commit_pair(tfull_bar + slot, 3);
+                ++uses[slot];
+                __syncwarp();
             }
         }
     } else {
@@ -1030,11 +1058,23 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             if (rc) return rc;
         }
     }
+    {
+        static int dbg = -1, pst = -1;
+        if (dbg < 0) {
+            const char* e = getenv("HTD_DENSE_DEBUG");
+            dbg = e ? atoi(e) : 0;
+            const char* e2 = getenv("HTD_PAIR_STAGES");
+            pst = e2 ? atoi(e2) : 0;
+        }
+        p.debug = dbg;
+        if (pair && pst > 0) p.nstages = -pst;      // applied below
+    }
     if (pair) {
+        const int want_st = p.nstages < 0 ? -p.nstages : kPairStages;
         p.pair = 1;
         p.tiles_m = (p.M + 255) / 256;
         p.a_bytes = kDAHalf;
-        p.nstages = kDRingBytes / p.stage_bytes < kPairStages ? kDRingBytes / p.stage_bytes : kPairStages;
+        p.nstages = kDRingBytes / p.stage_bytes < want_st ? kDRingBytes / p.stage_bytes : want_st;
     }
     const long long tiles = (long long)p.tiles_m * p.tiles_n;
     const bool can_split = !p.transposed;

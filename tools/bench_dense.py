@@ -17,12 +17,26 @@ BF16 = torch.bfloat16
 
 
 def timeit(fn, iters, flush):
+    """Median device time of one launch of `fn`: captured once into a CUDA graph and replayed, so
+    that the host side of the call (descriptor setup, tensor-map encoding, ctypes) is not in the
+    interval - an event pair around an eager call of a 50 us kernel measures mostly that."""
+    fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    st.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(st):
+        fn()
+    torch.cuda.current_stream().wait_stream(st)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fn()
     ts = []
     for i in range(iters + 3):
         flush.fill_(float(i))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        fn()
+        gr.replay()
         b.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -35,6 +49,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--iters', type=int, default=10)
     ap.add_argument('--splits', type=int, default=0)
+    ap.add_argument('--only', default='', help='substring filter on the shape name')
+    ap.add_argument('--no-lib', action='store_true')
     a = ap.parse_args()
     dev = 'cuda'
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
@@ -44,6 +60,10 @@ def main():
         return torch.randn(*s, generator=g).to(BF16).to(dev)
 
     def report(name, flops, own, libf):
+        if a.only and a.only not in name:
+            return
+        if a.no_lib:
+            libf = None
         t_own = timeit(own, a.iters, flush)
         t_lib = timeit(libf, a.iters, flush) if libf is not None else None
         print(json.dumps(dict(shape=name, gflop=round(flops / 1e9, 2), own_ms=round(t_own, 4),
