@@ -9,7 +9,10 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get('HTD_B200_LIB') or os.path.join(_HERE, '_lib', 'libhtd_b200.so')
+# HTD_B200_HOOKS=1 (measurement tools): the -DHTD_DEBUG_HOOKS build, which honours the kernel-variant
+# environment switches; HTD_B200_LIB: an explicit path
+LIB_PATH = os.environ.get('HTD_B200_LIB') or os.path.join(
+    _HERE, '_lib', 'libhtd_b200_hooks.so' if os.environ.get('HTD_B200_HOOKS') == '1' else 'libhtd_b200.so')
 
 HTD_F32, HTD_BF16 = 0, 1
 MAX_LEVELS = 8
@@ -162,45 +165,72 @@ class _Counted:
         return call
 
 
+HOOKS_LIB_PATH = os.path.join(_HERE, '_lib', 'libhtd_b200_hooks.so')
+
+
+def _open(path):
+    if not os.path.isfile(path):
+        raise RuntimeError(
+            f'{path} is missing: build it with `python -m htd_b200.build` (nvcc, sm_100a). '
+            'htd_b200 has no CPU or PyTorch fallback.')
+    L = ctypes.CDLL(path)
+    L.htd_last_error.restype = ctypes.c_char_p
+    L.htd_abi_version.restype = c_int
+    L.htd_pgraph_max_tiles.restype = c_ll
+    L.htd_pgraph_max_tiles.argtypes = [c_int] * 9
+    L.htd_roi_plan_rows_bound.restype = c_ll
+    L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
+    L.htd_multiclass_nms_workspace_bytes.restype = c_ll
+    L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
+    L.htd_multiclass_soft_nms_workspace_bytes.restype = c_ll
+    L.htd_multiclass_soft_nms_workspace_bytes.argtypes = [c_int, c_int]
+    L.htd_ba_mlp_supported.restype = c_int
+    L.htd_ba_mlp_supported.argtypes = [c_int, c_int]
+    L.htd_ba_mlp_workspace_floats.restype = c_ll
+    L.htd_ba_mlp_workspace_floats.argtypes = [c_ll, c_int]
+    L.htd_dense_gemm_workspace_bytes.restype = c_ll
+    L.htd_dense_gemm_workspace_bytes.argtypes = [ctypes.POINTER(HtdDenseGemm)]
+    L.htd_roi_align_bwd_uses_tensor_pipe.restype = c_int
+    L.htd_roi_align_bwd_uses_tensor_pipe.argtypes = [c_int, c_int, c_int]
+    if hasattr(L, 'htd_debug_set_bwd_variant'):       # the -DHTD_DEBUG_HOOKS build only
+        L.htd_debug_set_bwd_trace.restype = None
+        L.htd_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
+        L.htd_debug_set_bwd_variant.restype = None
+        L.htd_debug_set_bwd_variant.argtypes = [c_int]
+        L.htd_debug_set_option.restype = None
+        L.htd_debug_set_option.argtypes = [ctypes.c_char_p, c_int]
+    for name, args in SIGNATURES.items():
+        if not hasattr(L, name):
+            raise RuntimeError(f'{path} does not export {name}: rebuild it '
+                               '(`python -m htd_b200.build --force`)')
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    return _Counted(L)
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.isfile(LIB_PATH):
-            raise RuntimeError(
-                f'{LIB_PATH} is missing: build it with `python -m htd_b200.build` (nvcc, sm_100a). '
-                'htd_b200 has no CPU or PyTorch fallback.')
-        L = ctypes.CDLL(LIB_PATH)
-        L.htd_last_error.restype = ctypes.c_char_p
-        L.htd_abi_version.restype = c_int
-        L.htd_pgraph_max_tiles.restype = c_ll
-        L.htd_pgraph_max_tiles.argtypes = [c_int] * 9
-        L.htd_roi_plan_rows_bound.restype = c_ll
-        L.htd_roi_plan_rows_bound.argtypes = [ctypes.POINTER(HtdLevel), c_int, c_int, c_int]
-        L.htd_multiclass_nms_workspace_bytes.restype = c_ll
-        L.htd_multiclass_nms_workspace_bytes.argtypes = [c_int, c_int]
-        L.htd_multiclass_soft_nms_workspace_bytes.restype = c_ll
-        L.htd_multiclass_soft_nms_workspace_bytes.argtypes = [c_int, c_int]
-        L.htd_ba_mlp_supported.restype = c_int
-        L.htd_ba_mlp_supported.argtypes = [c_int, c_int]
-        L.htd_ba_mlp_workspace_floats.restype = c_ll
-        L.htd_ba_mlp_workspace_floats.argtypes = [c_ll, c_int]
-        L.htd_dense_gemm_workspace_bytes.restype = c_ll
-        L.htd_dense_gemm_workspace_bytes.argtypes = [ctypes.POINTER(HtdDenseGemm)]
-        L.htd_debug_set_bwd_trace.restype = None
-        L.htd_debug_set_bwd_trace.argtypes = [ctypes.c_void_p]
-        L.htd_roi_align_bwd_uses_tensor_pipe.restype = c_int
-        L.htd_roi_align_bwd_uses_tensor_pipe.argtypes = [c_int, c_int, c_int]
-        L.htd_debug_set_bwd_variant.restype = None
-        L.htd_debug_set_bwd_variant.argtypes = [c_int]
-        for name, args in SIGNATURES.items():
-            if not hasattr(L, name):
-                raise RuntimeError(f'{LIB_PATH} does not export {name}: rebuild it '
-                                   '(`python -m htd_b200.build --force`)')
-            fn = getattr(L, name)
-            fn.argtypes = args
-            fn.restype = c_int
-        _lib = _Counted(L)
+        _lib = _open(LIB_PATH)
     return _lib
+
+
+class hooks_library:
+    """``with hooks_library() as L:`` routes every call of the package through the library built
+    with -DHTD_DEBUG_HOOKS (kernel-variant selection, backward trace, experiment switches) and
+    restores the product library afterwards.  For tests and measurement tools only."""
+
+    def __enter__(self):
+        global _lib
+        self.prev = _lib
+        _lib = _open(HOOKS_LIB_PATH)
+        return _lib
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self.prev
+        return False
 
 
 def check(rc, what=''):

@@ -66,6 +66,13 @@ constexpr int kChunk = 64 * 128;                     // one 64-element MN chunk 
 // row 104 (a multiple of 8: the 128-byte swizzle phase of a TMA destination) -> UMMA N = 208
 constexpr int kPP = 49, kRoisPerTile = 5;
 
+// experiment switches of the kernels (HTD_DENSE_DEBUG bits) exist in the -DHTD_DEBUG_HOOKS build only
+#ifdef HTD_DEBUG_HOOKS
+#define DENSE_DBG(p) ((p).debug)
+#else
+#define DENSE_DBG(p) 0
+#endif
+
 struct DenseParams {
     int kind;
     int M, N;                     // output extents (conv fprop/dgrad: N = P * 49 pixels)
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     uint64_t* bar = full_bar + s;
                     uint8_t* sa = smem + s * p.stage_bytes;
                     uint8_t* sb = sa + p.a_bytes;
-                    if (p.debug & 2) {                // experiment: barrier traffic only
+                    if (DENSE_DBG(p) & 2) {                // experiment: barrier traffic only
                         mbar_arrive(bar);
                     } else {
                         mbar_expect_tx(bar, tx);
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                 tc::fence_after();
                 if (lane == 0) {
                     const uint64_t ad = ad0 + s * st_d, bd = bd0 + s * st_d;
-                    if (!(p.debug & 1)) {
+                    if (!(DENSE_DBG(p) & 1)) {
                         if (p.ksteps == kDBK / 16) {      // the common stage: 64 k = 4 steps, unrolled
 #pragma unroll
                             for (int k = 0; k < kDBK / 16; ++k) {
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                             }
                         }
                     }
-                    if (p.debug & 8) mbar_arrive(empty_bar + s);   // experiment (with 1): no commit
+                    if (DENSE_DBG(p) & 8) mbar_arrive(empty_bar + s);   // experiment (with 1): no commit
                     else tc::commit(empty_bar + s);
                 }
                 __syncwarp();
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
             }
             for (int hh = 0; hh < 1; ++hh) {
                 const unsigned slot = nsingle++ & 1u;
-                if (p.debug & 32) {                          // experiment: one polling lane per warp
+                if (DENSE_DBG(p) & 32) {                          // experiment: one polling lane per warp
                     if (lane == 0) mbar_wait(tfull_bar + slot, uses[slot] & 1u);
                     __syncwarp();
                 } else {
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     uint32_t v[32];
                     __syncwarp();
                     tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
-                    if (!row_ok || (p.debug & 4)) continue;
+                    if (!row_ok || (DENSE_DBG(p) & 4)) continue;
                     const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
                     float f[32];
 #pragma unroll
@@ -559,7 +566,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
                     const uint32_t bar = bar0 + 8u * s;
                     uint8_t* sa = smem + s * p.stage_bytes;
                     uint8_t* sb = sa + p.a_bytes;
-                    if (p.debug & 2) {                       // experiment: barrier traffic only
+                    if (DENSE_DBG(p) & 2) {                       // experiment: barrier traffic only
                         tc::mbar_arrive_cluster(bar);
                     } else {
                         tc::mbar_expect_tx_cluster(bar, tx);
@@ -625,7 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
                     tc::fence_after();
                     if (lane == 0) {
                         const uint64_t ad = ad0 + s * st_d, bd = bd0 + s * st_d;
-                        if (!(p.debug & 1)) {
+                        if (!(DENSE_DBG(p) & 1)) {
 #pragma unroll
                             for (int k = 0; k < kDBK / 16; ++k) {
                                 tc::umma_bf16_pair(acc0, ad + k * a_k, bd + k * b_k, idesc, accum);
@@ -885,14 +892,23 @@ static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParam
     return HTD_OK;
 }
 
-static int dense_pair_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("HTD_DENSE_PAIR");
-        mode = e ? atoi(e) : 0;   // off until validated on the GPU
+// HTD_DENSE_PAIR (0 = off, 1 = conv fprop / dgrad, 2 = also the GEMM kinds), HTD_DENSE_DEBUG and
+// HTD_PAIR_STAGES are read by the -DHTD_DEBUG_HOOKS build only (or set through
+// htd_debug_set_option); the product library runs the single-CTA form, which measured faster at
+// the head's shapes (profiles/r02_dense_notes.md, section 5).
+#ifdef HTD_DEBUG_HOOKS
+static int g_dense_opt[3] = {-1, -1, -1};             // pair mode, debug bits, pair stages
+static int dense_option(int which, const char* env) {
+    if (g_dense_opt[which] < 0) {
+        const char* e = getenv(env);
+        g_dense_opt[which] = e ? atoi(e) : 0;
     }
-    return mode;
+    return g_dense_opt[which];
 }
+static int dense_pair_mode() { return dense_option(0, "HTD_DENSE_PAIR"); }
+#else
+static int dense_pair_mode() { return 0; }
+#endif
 
 static int pick_splits(long long tiles, int kblocks, int want, int sms) {
     if (want > 0) return want < kblocks ? want : (kblocks > 0 ? kblocks : 1);
@@ -1058,19 +1074,13 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
             if (rc) return rc;
         }
     }
-    {
-        static int dbg = -1, pst = -1;
-        if (dbg < 0) {
-            const char* e = getenv("HTD_DENSE_DEBUG");
-            dbg = e ? atoi(e) : 0;
-            const char* e2 = getenv("HTD_PAIR_STAGES");
-            pst = e2 ? atoi(e2) : 0;
-        }
-        p.debug = dbg;
-        if (pair && pst > 0) p.nstages = -pst;      // applied below
-    }
+    int pair_stages = 0;
+#ifdef HTD_DEBUG_HOOKS
+    p.debug = dense_option(1, "HTD_DENSE_DEBUG");
+    pair_stages = dense_option(2, "HTD_PAIR_STAGES");
+#endif
     if (pair) {
-        const int want_st = p.nstages < 0 ? -p.nstages : kPairStages;
+        const int want_st = pair_stages > 0 ? pair_stages : kPairStages;
         p.pair = 1;
         p.tiles_m = (p.M + 255) / 256;
         p.a_bytes = kDAHalf;
@@ -1085,6 +1095,14 @@ static int dense_setup(const HtdDenseGemm* g, DenseParams& p, CUtensorMap* ma, C
 }
 
 extern "C" {
+
+#ifdef HTD_DEBUG_HOOKS
+void htd_debug_set_option(const char* name, int value) {
+    if (!strcmp(name, "dense_pair")) g_dense_opt[0] = value;
+    else if (!strcmp(name, "dense_debug")) g_dense_opt[1] = value;
+    else if (!strcmp(name, "pair_stages")) g_dense_opt[2] = value;
+}
+#endif
 
 long long htd_dense_gemm_workspace_bytes(const HtdDenseGemm* g) {
     DenseParams p;

@@ -31,8 +31,18 @@
 namespace htd {
 
 static thread_local char g_err[512] = "";
+// Measurement hooks exist only in the -DHTD_DEBUG_HOOKS build (libhtd_b200_hooks.so): kernel-variant
+// selection, the backward trace and the HTD_FWD_KERNEL / HTD_BWD_KERNEL environment switches.  The
+// product library always runs the default kernels.
+#ifdef HTD_DEBUG_HOOKS
 static unsigned long long* g_bwd_trace = nullptr;    // see htd_debug_set_bwd_trace
 static int g_bwd_variant = -1;                       // see htd_debug_set_bwd_variant
+static const char* hook_env(const char* name) { return getenv(name); }
+#else
+static constexpr unsigned long long* g_bwd_trace = nullptr;
+static constexpr int g_bwd_variant = -1;
+static const char* hook_env(const char*) { return nullptr; }
+#endif
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -1516,8 +1526,10 @@ using namespace htd;
 extern "C" {
 
 int htd_abi_version(void) { return HTD_ABI_VERSION; }
+#ifdef HTD_DEBUG_HOOKS
 void htd_debug_set_bwd_trace(unsigned long long* records) { g_bwd_trace = records; }
 void htd_debug_set_bwd_variant(int variant) { g_bwd_variant = variant; }
+#endif
 const char* htd_last_error(void) { return g_err; }
 
 int htd_level_assign(const float* rois, int K, int num_levels, float finest_scale,
@@ -1651,7 +1663,7 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     // CTA-per-strip kernel for measurements)
     static int persist_on = -1;
     if (persist_on < 0) {
-        const char* ev = getenv("HTD_FWD_KERNEL");
+        const char* ev = hook_env("HTD_FWD_KERNEL");
         persist_on = (ev && (!strcmp(ev, "cta") || !strcmp(ev, "ring"))) ? 0 : 1;
     }
     if (persist_on && roi_level != nullptr && pooled < HTD_MAX_POOLED && C <= 256) {
@@ -1676,7 +1688,7 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
     // of 72 KB + barriers per SM); HTD_FWD_KERNEL=ring switches the strip path off (measurements)
     static int strip_on = -1;
     if (strip_on < 0) {
-        const char* ev = getenv("HTD_FWD_KERNEL");
+        const char* ev = hook_env("HTD_FWD_KERNEL");
         strip_on = (ev && !strcmp(ev, "ring")) ? 0 : 1;
     }
     size_t region = (size_t)pooled * kFwdStages * kFwdPx * cw * dtype_size(in_dtype);
@@ -1705,7 +1717,7 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
 static int bwd_variant() {
     static int env_variant = -1;
     if (env_variant < 0) {
-        const char* ev = getenv("HTD_BWD_KERNEL");
+        const char* ev = hook_env("HTD_BWD_KERNEL");
         env_variant = !ev ? 3 : !strcmp(ev, "scalar") ? 0 : !strcmp(ev, "mma1") ? 1 : !strcmp(ev, "mma2") ? 2 :
                       !strcmp(ev, "mma3") ? 3 : !strcmp(ev, "mma4") ? 4 : !strcmp(ev, "mma5") ? 5 : 3;
     }

@@ -154,15 +154,26 @@ int htd_roi_align_bwd_multi(const HtdLevel* grad_levels, int L, int B, int C, in
  * when this returns 1 and pooled < HTD_MAX_POOLED. */
 int htd_roi_align_bwd_uses_tensor_pipe(int C, int pooled, int dy_dtype);
 
-/* Diagnostics (tools/trace_bwd.py): when `records` is non-null the bf16 backward gather writes per
- * CTA six uint64 {globaltimer at start, at end, hits, K-step blocks, SM id, level} at
- * records[6 * blockIdx]; pass NULL to switch it off.  Not part of the reference's interface. */
+#ifdef HTD_DEBUG_HOOKS
+/* Measurement hooks: exported only by the library built with -DHTD_DEBUG_HOOKS
+ * (htd_b200/_lib/libhtd_b200_hooks.so, used by tests and tools that compare kernel variants).
+ * The product library does not export them and ignores the HTD_*_KERNEL / HTD_DENSE_* environment
+ * variables.  Not part of the reference's interface.
+ *
+ * htd_debug_set_bwd_trace (tools/trace_bwd.py): when `records` is non-null the bf16 backward gather
+ * writes per CTA six uint64 {globaltimer at start, at end, hits, K-step blocks, SM id, level} at
+ * records[6 * blockIdx]; pass NULL to switch it off. */
 void htd_debug_set_bwd_trace(unsigned long long* records);
 
-/* Diagnostics / tests: kernel used for bf16 dy by htd_roi_align_bwd(_multi).  0 = the scalar FFMA
- * gather (also the fp32 path), 1..5 = warp layouts / ring depths of the tensor-pipe gather (3 is
- * the default), -1 = back to the default (or the HTD_BWD_KERNEL environment variable). */
+/* Kernel used for bf16 dy by htd_roi_align_bwd(_multi).  0 = the scalar FFMA gather (also the fp32
+ * path), 1..5 = warp layouts / ring depths of the tensor-pipe gather (3 is the default), -1 = back
+ * to the default (or the HTD_BWD_KERNEL environment variable). */
 void htd_debug_set_bwd_variant(int variant);
+
+/* Dense-kernel options: "dense_pair" (0 off, 1 conv fprop / dgrad in the CTA-pair form, 2 also the
+ * GEMM kinds), "dense_debug" (experiment bits, csrc/dense_gemm.cu), "pair_stages" (ring depth). */
+void htd_debug_set_option(const char* name, int value);
+#endif
 
 /* Layout / dtype conversion: src [N, R, S] -> dst [N, S, R] (NCHW->NHWC with R=C, S=H*W and
  * back with R=H*W, S=C).  dtypes HTD_F32 / HTD_BF16 independently for src and dst. */

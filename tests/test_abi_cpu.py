@@ -15,9 +15,21 @@ def cdll():
     return ctypes.CDLL(build.build())
 
 
-def _declared():
+@pytest.fixture(scope='module')
+def hooks_cdll(cdll):
+    from htd_b200 import build
+    return ctypes.CDLL(build.LIB_HOOKS)
+
+
+def _declared(hooks=False):
+    """Names the header declares: the product interface, or only the -DHTD_DEBUG_HOOKS block."""
     src = open(os.path.join(ROOT, 'include', 'htd_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    blocks = re.findall(r'#ifdef HTD_DEBUG_HOOKS(.*?)#endif', src, flags=re.S)
+    if hooks:
+        src = '\n'.join(blocks)
+    else:
+        src = re.sub(r'#ifdef HTD_DEBUG_HOOKS.*?#endif', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b(htd_[a-z0-9_]+)\s*\(', src)))
 
 
@@ -26,6 +38,18 @@ def test_every_declared_symbol_is_exported(cdll):
     assert len(names) >= 17 and 'htd_pgraph_gemm' in names and 'htd_roi_align_bwd' in names
     for n in names:
         assert hasattr(cdll, n), f'{n} declared in include/htd_b200.h but not exported'
+
+
+def test_measurement_hooks_are_not_in_the_product_library(cdll, hooks_cdll):
+    """htd_debug_* exist only in the library built with -DHTD_DEBUG_HOOKS, which exports the
+    whole product interface as well."""
+    hooks = _declared(hooks=True)
+    assert 'htd_debug_set_bwd_variant' in hooks and 'htd_debug_set_option' in hooks
+    for n in hooks:
+        assert not hasattr(cdll, n), f'{n} leaked into the product library'
+        assert hasattr(hooks_cdll, n)
+    for n in _declared():
+        assert hasattr(hooks_cdll, n)
 
 
 def test_python_binding_covers_the_header():
@@ -38,8 +62,6 @@ def test_python_binding_covers_the_header():
                                                              'htd_dense_gemm_workspace_bytes',
                                                              'htd_ba_mlp_supported',
                                                              'htd_ba_mlp_workspace_floats',
-                                                             'htd_debug_set_bwd_trace',
-                                                             'htd_debug_set_bwd_variant',
                                                              'htd_roi_align_bwd_uses_tensor_pipe'}
     assert not missing, missing
 
@@ -63,7 +85,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.HtdBwdSource) == 8 * 8 + 4 * 4       # 8 pointers + K, dy_per_level, ring_edge, addvec_dtype
 
 
-def test_backward_kernel_choice_is_a_host_decision(cdll):
+def test_backward_kernel_choice_is_a_host_decision(cdll, hooks_cdll):
     """htd_roi_align_bwd_uses_tensor_pipe: bf16 dy with C a multiple of 64 in 64..256 takes the
     tensor-pipe gather unless it is switched off; everything else the exact scalar gather."""
     f = cdll.htd_roi_align_bwd_uses_tensor_pipe
@@ -71,12 +93,13 @@ def test_backward_kernel_choice_is_a_host_decision(cdll):
     assert f(256, 7, BF16) == 1 and f(64, 7, BF16) == 1 and f(128, 8, BF16) == 1
     assert f(256, 7, F32) == 0                     # fp32 gradients: exact kernel
     assert f(96, 7, BF16) == 0 and f(320, 7, BF16) == 0 and f(32, 7, BF16) == 0
-    cdll.htd_debug_set_bwd_variant(0)
+    fh = hooks_cdll.htd_roi_align_bwd_uses_tensor_pipe
+    hooks_cdll.htd_debug_set_bwd_variant(0)
     try:
-        assert f(256, 7, BF16) == 0
+        assert fh(256, 7, BF16) == 0
     finally:
-        cdll.htd_debug_set_bwd_variant(-1)
-    assert f(256, 7, BF16) == 1
+        hooks_cdll.htd_debug_set_bwd_variant(-1)
+    assert fh(256, 7, BF16) == 1
 
 
 def test_backward_source_validation_without_gpu(cdll):

@@ -68,13 +68,15 @@ def _fp32(src):
 
 
 def _run(shapes, dtype, nchw, src, variant, pooled=7):
-    L = _lib.lib()
-    L.htd_debug_set_bwd_variant(variant)
-    try:
-        out = ops._bwd_multi(shapes, dtype, nchw, SCALES, [dict(q) for q in src], pooled)
-        torch.cuda.synchronize()
-    finally:
-        L.htd_debug_set_bwd_variant(-1)
+    """One backward gather with a forced kernel variant: through the -DHTD_DEBUG_HOOKS build of
+    the library (the product library has no variant selection)."""
+    with _lib.hooks_library() as L:
+        L.htd_debug_set_bwd_variant(variant)
+        try:
+            out = ops._bwd_multi(shapes, dtype, nchw, SCALES, [dict(q) for q in src], pooled)
+            torch.cuda.synchronize()
+        finally:
+            L.htd_debug_set_bwd_variant(-1)
     return [o.float() for o in out]
 
 
@@ -170,15 +172,15 @@ def test_bf16_addvec_needs_the_tensor_pipe_kernel():
     shapes = _pyramid_shapes(B, C, H, W)
     pos = _rand_rois(16, B, H * 4, W * 4, gen)
     src, keep = _sources(shapes, pos, pos, C, gen)
-    L = _lib.lib()
-    L.htd_debug_set_bwd_variant(0)
-    try:
-        with pytest.raises(RuntimeError, match='addvec'):
-            q = dict(src[2])
-            q['addvec'] = q['addvec'].to(torch.bfloat16)
-            _force_bf16_addvec(shapes, q)
-    finally:
-        L.htd_debug_set_bwd_variant(-1)
+    with _lib.hooks_library() as L:
+        L.htd_debug_set_bwd_variant(0)
+        try:
+            with pytest.raises(RuntimeError, match='addvec'):
+                q = dict(src[2])
+                q['addvec'] = q['addvec'].to(torch.bfloat16)
+                _force_bf16_addvec(shapes, q)
+        finally:
+            L.htd_debug_set_bwd_variant(-1)
 
 
 def _force_bf16_addvec(shapes, q):

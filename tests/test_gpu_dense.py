@@ -217,3 +217,25 @@ def test_add3_vs_torch():
     assert torch.equal(ga, dy) and torch.equal(gb, dy)
     w3 = torch.zeros(B, C, device='cuda').index_add_(0, rois[:, 0].long(), dy.float().sum((2, 3)))
     assert _rel(g3.reshape(B, C), w3) <= 1e-2
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+def test_cta_pair_form_matches(mode):
+    """The CTA-pair (cta_group::2) form of the kernel - opt-in, hooks build only - against the
+    same torch references: conv fprop / dgrad (mode 1), and the three GEMM kinds too (mode 2)."""
+    from htd_b200 import _lib
+    with _lib.hooks_library() as L:
+        L.htd_debug_set_option(b'dense_pair', mode)
+        try:
+            for P, Cin, Cout in ((7, 256, 576), (256, 576, 576), (23, 576, 1024), (2, 64, 128)):
+                test_conv3x3_forward_dgrad_wgrad_vs_torch(P, Cin, Cout)
+            test_conv_epilogue_relu_and_gate()
+            if mode == 2:
+                test_gemm_nt_bias_relu_second_output(1024, 1024, 12544, 0)
+                test_gemm_nt_bias_relu_second_output(1000, 85, 1024, 0)
+                test_gemm_nn_with_relu_gate(1024, 12544, 1024, 0)
+                test_gemm_nn_with_relu_gate(130, 200, 260, 1)
+                test_gemm_tn(1024, 12544, 1024, 0)
+                test_gemm_tn(200, 130, 260, 1)
+        finally:
+            L.htd_debug_set_option(b'dense_pair', 0)

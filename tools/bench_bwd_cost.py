@@ -7,6 +7,8 @@ Usage: [HTD_BWD_KERNEL=mma3] python tools/bench_bwd_cost.py [--iters 20]
 import argparse
 import json
 import os
+
+os.environ.setdefault('HTD_B200_HOOKS', '1')   # variant switches live in the hooks build only
 import sys
 
 import torch

@@ -5,6 +5,8 @@ One JSON line per shape.  Usage: python tools/bench_dense.py [--iters 10]"""
 import argparse
 import json
 import os
+
+os.environ.setdefault('HTD_B200_HOOKS', '1')   # variant switches live in the hooks build only
 import sys
 
 import torch

@@ -5,6 +5,8 @@ per kernel.  Usage: python tools/bench_kernels.py [--imgs 2] [--rois 512] [--pos
 import argparse
 import json
 import os
+
+os.environ.setdefault('HTD_B200_HOOKS', '1')   # variant switches live in the hooks build only
 import sys
 
 import torch

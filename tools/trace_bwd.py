@@ -5,6 +5,8 @@ busy time of the busiest SM against the kernel span.  Usage: python tools/trace_
 """
 import json
 import os
+
+os.environ.setdefault('HTD_B200_HOOKS', '1')   # variant switches live in the hooks build only
 import sys
 
 import numpy as np
