@@ -47,8 +47,11 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager steps instead of CUDA-graph replay')
     ap.add_argument('--overlap', action='store_true',
-                    help='N > 1: all-reduce the stage-1 gradients on a side stream while the replay '
-                         'still runs the rest of backward (measured: no gain, see DESIGN.md)')
+                    help='N > 1: all-reduce the head gradients on a side stream, started by an '
+                         'in-graph event once they are complete, while the replay still runs the '
+                         'backward gather and the layout passes')
+    ap.add_argument('--nccl-channels', type=int, default=0,
+                    help='with --overlap: NCCL_MAX_NCHANNELS (fewer SMs taken from the gather)')
     ap.add_argument('--no-static', action='store_true',
                     help='skip the extra figure for the step with device-side assign + sample')
     return ap.parse_args()
@@ -430,12 +433,19 @@ def gpu_comparator(dev, pyr_host, props_host, gts, shapes):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
+    if args.nccl_channels > 0:
+        os.environ['NCCL_MAX_NCHANNELS'] = str(args.nccl_channels)
     if os.environ.get('NCCL_DEBUG'):        # keep NCCL's log (rank / transport evidence), but on
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # stderr: stdout is the JSON line
     import htd_b200
     from htd_b200 import _lib, synth
     from htd_b200.parallel import GradAllReducer
 
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner
+    # at communicator creation, whatever NCCL_DEBUG says) are sent to stderr for the whole run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -529,7 +539,8 @@ def run_gpu(args):
         from htd_b200.graphed import GraphedTrainStep
         try:
             gstep = GraphedTrainStep(head, x_dev, props_dev, gts, shapes, POS, flat_grads=world > 1,
-                                     early_modules=[head.bbox_head[1], head.bbox_roi_extractor[1]]
+                                     early_modules=[head.bbox_head[0], head.bbox_head[1],
+                                                    head.bbox_roi_extractor[1]]
                                      if world > 1 and args.overlap else None, flat_inputs=True)
         except Exception as e:                     # never lose the measurement to a capture problem
             print(f'[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager',
@@ -870,7 +881,7 @@ def run_gpu(args):
                                 '2 images/GPU', f'{imgs} images/GPU'),
                             imgs_per_gpu=imgs, global_rois_per_step=rois_per_step * world,
                             parallelism=f'dp{world}' + (' + NCCL grad all-reduce' + (
-                                ' (stage-1 part overlapped with the rest of backward)'
+                                ' (head gradients reduced next to the backward gather)'
                                 if gstep is not None and gstep.early_event is not None else '')
                                 if world > 1 else ''),
                             l2='inputs larger than L2: 183 MB fp32 pyramid + 94 MB bf16 weights per step',
@@ -889,7 +900,8 @@ def run_gpu(args):
                 dense_kernels=dense_kernels, roofline_tensor=roofline_tensor, sweep_config5=sweep,
                 gpu_comparator=comparator,
                 cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -60,13 +60,29 @@ class _GraphedStep:
                 self.early_grad, self.late_grad = self.flat_grad[:n_early], self.flat_grad[n_early:]
                 self.early_event = torch.cuda.Event(external=True)
                 self._early_seen, self.early_fired = 0, 0
+                self._early_marks = []
+                self._armed = False
+                self._join_stream = torch.cuda.Stream(device=dev)
 
                 def hook(_p, n=len(early)):
+                    # The step runs as parallel branches (streams): each early gradient is
+                    # accumulated on the stream of its own branch.  Every hook leaves a marker on
+                    # that stream; the last one makes a join stream wait for all of them and
+                    # records the external event there - "every early gradient is complete"
+                    # whatever the branch structure.  (Captured: markers and waits become edges.)
+                    if not self._armed:               # another step object is running backward
+                        return
+                    mark = torch.cuda.Event()
+                    mark.record()
+                    self._early_marks.append(mark)
                     self._early_seen += 1
                     if self._early_seen == n:
                         self._early_seen = 0
                         self.early_fired += 1
-                        self.early_event.record()     # captured as an event-record node
+                        for m in self._early_marks:
+                            self._join_stream.wait_event(m)
+                        self._early_marks = []
+                        self.early_event.record(self._join_stream)
                 self._early_handles = [p.register_post_accumulate_grad_hook(hook) for p in early]
         self.losses = None
         self.total = None
@@ -147,16 +163,15 @@ class GraphedTrainStep(_GraphedStep):
         self._capture(dev, warmup)
 
     def _run(self):
-        # the early-gradient event is recorded on ONE stream: keep the whole step on it
-        prev = self.head.overlap
-        if self.early_event is not None:
-            self.head.overlap = False
         self.head.inputs_consumed_event = self.inputs_consumed
+        self._armed = True
         try:
             self._finish(synth.sampled_forward_train(self.head, self.x, self.proposals, self.gts,
                                                      self.img_shapes, self.num_pos))
+            if self.early_event is not None:          # the join stream is part of the step
+                torch.cuda.current_stream().wait_stream(self._join_stream)
         finally:
-            self.head.overlap = prev
+            self._armed = False
             self.head.inputs_consumed_event = None
 
     def load(self, x=None, proposals=None, gts=None, non_blocking=True):
