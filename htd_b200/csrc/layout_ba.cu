@@ -206,6 +206,47 @@ __global__ void __launch_bounds__(256) transpose_kernel(const TS* __restrict__ s
 // ------------------------------------------------------------------------------------------
 // BA kernels
 // ------------------------------------------------------------------------------------------
+// out[n, c] = scale * sum over the PP bins of x[n, bin, c]: one CTA per row n; a thread owns 8
+// channels (one 16-byte load per bin) of every `groups`-th bin, the bin groups meet in shared
+// memory in a fixed order (deterministic).  C % 8 == 0, C <= 2048.
+template <typename T>
+__global__ void __launch_bounds__(256) bin_sum_kernel(const T* __restrict__ x, long long N, int PP,
+                                                      int C, float scale, float* __restrict__ out) {
+    __shared__ float red[8][256];                        // [bin group][channel], C <= 256
+    const long long n = blockIdx.x;
+    const T* xn = x + (size_t)n * PP * C;
+    const int vecs = C / 8;                              // <= 256
+    const bool exchange = C <= 256;
+    const int groups = exchange ? (256 / vecs < 8 ? 256 / vecs : 8) : 1;
+    const int v = threadIdx.x % vecs, g = threadIdx.x / vecs;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g < groups) {
+#pragma unroll 4
+        for (int b = g; b < PP; b += groups) {
+            float t[8];
+            ldvec<T, 8>(xn + (size_t)b * C + v * 8, t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += t[j];
+        }
+    }
+    if (exchange) {
+        if (g < groups) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[g][v * 8 + j] = acc[j];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            float t = 0.f;
+            for (int k = 0; k < groups; ++k) t += red[k][c];
+            out[(size_t)n * C + c] = t * scale;
+        }
+    } else if (g == 0) {                                 // wide C: one group, no exchange
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[(size_t)n * C + v * 8 + j] = acc[j] * scale;
+    }
+}
+
+// generic form (any C)
 template <typename T>
 __global__ void __launch_bounds__(256) bin_mean_kernel(const T* __restrict__ x, long long N, int PP,
                                                        int C, float* __restrict__ mean) {
@@ -341,9 +382,24 @@ __global__ void __launch_bounds__(256) ba_fuse_bwd_kernel(const TR* __restrict__
     }
 }
 
-// dbias, phase 1: block = kBiasRois consecutive RoIs, thread = channel
-constexpr int kBiasRois = 4;
+// dbias[b, c] = sum over the RoIs k of image b of rowsum[k, c] (rowsum = per-RoI bin sums from
+// bin_sum_kernel), in ascending k (deterministic); thread = (b, c)
+__global__ void __launch_bounds__(256) rows_by_image_kernel(const float* __restrict__ rowsum,
+                                                            const float* __restrict__ rois, int K,
+                                                            int C, int B, float* __restrict__ dbias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= C) return;
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < K; ++k) {
+        const float v = rowsum[(size_t)k * C + c];
+        if ((int)__ldg(rois + (size_t)k * 5) == b) s += v;
+    }
+    dbias[(size_t)b * C + c] = s;
+}
 
+// generic form (any C), phase 1: block = kBiasRois consecutive RoIs, thread = channel
+constexpr int kBiasRois = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) bias_grad_partial_kernel(const T* __restrict__ g,
                                                                 const float* __restrict__ rois,
@@ -382,7 +438,7 @@ __global__ void bias_grad_final_kernel(const float* __restrict__ partial, int nb
 // backward gather waits for, first; the parameter sums after it), instead of ~8 and ~25
 // library / elementwise launches.
 // ------------------------------------------------------------------------------------------
-constexpr int kMlpH = 128, kMlpRows = 8, kMlpMaxC = 512, kMlpChunks = 8;
+constexpr int kMlpH = 128, kMlpRows = 4, kMlpMaxC = 512, kMlpChunks = 32;
 
 template <typename TP>
 __global__ void __launch_bounds__(kMlpH) ba_mlp_fwd_kernel(const float* __restrict__ m, int rows,
@@ -628,11 +684,17 @@ int htd_ba_bin_mean(const void* x, int x_dtype, long long N, int PP, int C, floa
     if (N == 0) return HTD_OK;
     HTD_CHECK_ARG(x && mean && N < 2147483647LL, "htd_ba_bin_mean: null pointer / too large");
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_dtype == HTD_F32)
-        bin_mean_kernel<float><<<(unsigned)N, 256, 0, st>>>(static_cast<const float*>(x), N, PP, C, mean);
-    else
-        bin_mean_kernel<__nv_bfloat16><<<(unsigned)N, 256, 0, st>>>(
+    const bool vec = C % 8 == 0 && C <= 2048 && ((uintptr_t)x % 16 == 0);
+    const float inv = 1.f / (float)PP;
+    if (x_dtype == HTD_F32) {
+        if (vec) bin_sum_kernel<float><<<(unsigned)N, 256, 0, st>>>(static_cast<const float*>(x), N, PP, C, inv, mean);
+        else bin_mean_kernel<float><<<(unsigned)N, 256, 0, st>>>(static_cast<const float*>(x), N, PP, C, mean);
+    } else {
+        if (vec) bin_sum_kernel<__nv_bfloat16><<<(unsigned)N, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16*>(x), N, PP, C, inv, mean);
+        else bin_mean_kernel<__nv_bfloat16><<<(unsigned)N, 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(x), N, PP, C, mean);
+    }
     HTD_CHECK_LAUNCH("htd_ba_bin_mean");
     return HTD_OK;
 }
@@ -685,6 +747,18 @@ int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, 
                   "htd_bias_grad: bad arguments");
     HTD_CHECK_ARG(dbias && (K == 0 || (g && rois && partial)), "htd_bias_grad: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (C % 8 == 0 && C <= 2048 && ((uintptr_t)g % 16 == 0) && K > 0) {
+        // per-RoI bin sums [K, C] into the workspace, then the rows of each image
+        if (g_dtype == HTD_F32)
+            bin_sum_kernel<float><<<(unsigned)K, 256, 0, st>>>(static_cast<const float*>(g), K, PP, C, 1.f, partial);
+        else
+            bin_sum_kernel<__nv_bfloat16><<<(unsigned)K, 256, 0, st>>>(
+                static_cast<const __nv_bfloat16*>(g), K, PP, C, 1.f, partial);
+        HTD_CHECK_LAUNCH("htd_bias_grad(bin sums)");
+        rows_by_image_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(partial, rois, K, C, B, dbias);
+        HTD_CHECK_LAUNCH("htd_bias_grad(rows)");
+        return HTD_OK;
+    }
     const int nblk = (K + kBiasRois - 1) / kBiasRois;
     if (nblk > 0) {
         if (g_dtype == HTD_F32)

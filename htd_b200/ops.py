@@ -395,7 +395,7 @@ def _fwd_launch(name, feats, scales, rois, roi_level, pooled, sampling_ratio, bi
 def _bias_grad(g_kppc, rois, B):
     K, PP, C = g_kppc.shape[0], g_kppc.shape[1] * g_kppc.shape[2], g_kppc.shape[3]
     nblk = max((K + 3) // 4, 1)
-    partial = torch.empty((nblk, B, C), dtype=torch.float32, device=g_kppc.device)
+    partial = torch.empty(max(K, nblk * B, 1) * C, dtype=torch.float32, device=g_kppc.device)
     dbias = torch.empty((B, C), dtype=torch.float32, device=g_kppc.device)
     check(lib().htd_bias_grad(ptr(g_kppc), dt(g_kppc), ptr(rois), K, PP, C, B, ptr(partial),
                               ptr(dbias), stream()), 'htd_bias_grad')

@@ -219,7 +219,7 @@ int htd_ba_mlp_bwd(const float* da, const float* h, const float* m, long long ro
 /* Segmented sum of a [K,PP,C] gradient over bins and RoIs of the same image:
  * dbias[b,c] = sum_{k: batch(k)=b} sum_bin g[k,bin,c]  (backward of the fused SFA bias). */
 int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, int C, int B,
-                  float* partial /* workspace [ceil(K/4), B, C] fp32 */, float* dbias,
+                  float* partial /* workspace max(K, ceil(K/4) * B) * C fp32 */, float* dbias,
                   htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
