@@ -383,19 +383,31 @@ __global__ void __launch_bounds__(256) ba_fuse_bwd_kernel(const TR* __restrict__
 }
 
 // dbias[b, c] = sum over the RoIs k of image b of rowsum[k, c] (rowsum = per-RoI bin sums from
-// bin_sum_kernel), in ascending k (deterministic); thread = (b, c)
-__global__ void __launch_bounds__(256) rows_by_image_kernel(const float* __restrict__ rowsum,
-                                                            const float* __restrict__ rois, int K,
-                                                            int C, int B, float* __restrict__ dbias) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (c >= C) return;
+// bin_sum_kernel).  CTA = (32 channels, image b): 32 row lanes x 32 channels, lane l adds rows
+// l, l + 32, ... in ascending order, the lanes meet in shared memory in lane order (deterministic).
+__global__ void __launch_bounds__(1024) rows_by_image_kernel(const float* __restrict__ rowsum,
+                                                             const float* __restrict__ rois, int K,
+                                                             int C, int B, float* __restrict__ dbias) {
+    __shared__ float red[32][33];
+    const int cl = threadIdx.x & 31, l = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl, b = blockIdx.y;
     float s = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float v = rowsum[(size_t)k * C + c];
-        if ((int)__ldg(rois + (size_t)k * 5) == b) s += v;
+    if (c < C) {
+#pragma unroll 4
+        for (int k = l; k < K; k += 32) {
+            const float v = rowsum[(size_t)k * C + c];
+            const int img = (int)__ldg(rois + (size_t)k * 5);
+            s += img == b ? v : 0.f;
+        }
     }
-    dbias[(size_t)b * C + c] = s;
+    red[l][cl] = s;
+    __syncthreads();
+    if (l == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t += red[i][cl];
+        dbias[(size_t)b * C + c] = t;
+    }
 }
 
 // generic form (any C), phase 1: block = kBiasRois consecutive RoIs, thread = channel
@@ -438,64 +450,76 @@ __global__ void bias_grad_final_kernel(const float* __restrict__ partial, int nb
 // backward gather waits for, first; the parameter sums after it), instead of ~8 and ~25
 // library / elementwise launches.
 // ------------------------------------------------------------------------------------------
-constexpr int kMlpH = 128, kMlpRows = 4, kMlpMaxC = 512, kMlpChunks = 32;
+constexpr int kMlpH = 128, kMlpRows = 4, kMlpMaxC = 256, kMlpChunks = 32;
+
+constexpr int kMlpFwdRows = 16;                       // rows of m per CTA (two halves of 8)
 
 template <typename TP>
-__global__ void __launch_bounds__(kMlpH) ba_mlp_fwd_kernel(const float* __restrict__ m, int rows,
-                                                           int C, const TP* __restrict__ w1,
-                                                           const TP* __restrict__ b1,
-                                                           const TP* __restrict__ w2,
-                                                           const TP* __restrict__ b2,
-                                                           float* __restrict__ h,
-                                                           float* __restrict__ logits) {
-    __shared__ float sm[kMlpRows][kMlpMaxC];
-    __shared__ float wt[kMlpH][33];
-    __shared__ float red[kMlpRows][kMlpH / 32];
-    const int j = threadIdx.x, r0 = blockIdx.x * kMlpRows;
-    for (int i = j; i < kMlpRows * C; i += kMlpH) {
+__global__ void __launch_bounds__(2 * kMlpH) ba_mlp_fwd_kernel(const float* __restrict__ m, int rows,
+                                                               int C, const TP* __restrict__ w1,
+                                                               const TP* __restrict__ b1,
+                                                               const TP* __restrict__ w2,
+                                                               const TP* __restrict__ b2,
+                                                               float* __restrict__ h,
+                                                               float* __restrict__ logits) {
+    __shared__ __align__(16) float sm[kMlpFwdRows][kMlpMaxC];
+    __shared__ float wt[32][kMlpH + 1];               // W1 chunk, transposed: [c][j]
+    __shared__ float red[kMlpFwdRows][kMlpH / 32];
+    const int j = threadIdx.x % kMlpH, half = threadIdx.x / kMlpH;   // thread = hidden unit x 8 rows
+    const int r0 = blockIdx.x * kMlpFwdRows;
+    for (int i = threadIdx.x; i < kMlpFwdRows * C; i += 2 * kMlpH) {
         const int r = i / C, c = i - r * C;
         sm[r][c] = (r0 + r < rows) ? m[(size_t)(r0 + r) * C + c] : 0.f;
     }
-    float acc[kMlpRows];
+    float acc[8];
     const float bj = ldv<TP>(b1 + j);
 #pragma unroll
-    for (int r = 0; r < kMlpRows; ++r) acc[r] = bj;
+    for (int r = 0; r < 8; ++r) acc[r] = bj;
     for (int c0 = 0; c0 < C; c0 += 32) {
         __syncthreads();
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-            const int idx = i * kMlpH + j, jj = idx >> 5, cc = idx & 31;
-            wt[jj][cc] = ldv<TP>(w1 + (size_t)jj * C + c0 + cc);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {                // 128 x 32 tile, 32 consecutive c per warp
+            const int idx = i * 2 * kMlpH + threadIdx.x, jj = idx >> 5, cc = idx & 31;
+            wt[cc][jj] = ldv<TP>(w1 + (size_t)jj * C + c0 + cc);
         }
         __syncthreads();
-#pragma unroll 8
-        for (int cc = 0; cc < 32; ++cc) {
-            const float w = wt[j][cc];
 #pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(sm[r][c0 + cc], w, acc[r]);
+        for (int cq = 0; cq < 32; cq += 4) {
+            const float w0 = wt[cq][j], w1v = wt[cq + 1][j], w2v = wt[cq + 2][j], w3v = wt[cq + 3][j];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(&sm[half * 8 + r][c0 + cq]);
+                acc[r] = fmaf(x.x, w0, acc[r]);
+                acc[r] = fmaf(x.y, w1v, acc[r]);
+                acc[r] = fmaf(x.z, w2v, acc[r]);
+                acc[r] = fmaf(x.w, w3v, acc[r]);
+            }
         }
     }
     const float w2j = ldv<TP>(w2 + j);
 #pragma unroll
-    for (int r = 0; r < kMlpRows; ++r) {
+    for (int r = 0; r < 8; ++r) {
+        const int row = half * 8 + r;
         const float hv = tanhf(acc[r]);
-        if (r0 + r < rows) h[(size_t)(r0 + r) * kMlpH + j] = hv;
+        if (r0 + row < rows) h[(size_t)(r0 + row) * kMlpH + j] = hv;
         float v = hv * w2j;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((j & 31) == 0) red[r][j >> 5] = v;
+        if ((j & 31) == 0) red[row][j >> 5] = v;
     }
     __syncthreads();
-    if (j < kMlpRows && r0 + j < rows) {
+    if (threadIdx.x < kMlpFwdRows && r0 + (int)threadIdx.x < rows) {
         float v = ldv<TP>(b2);
 #pragma unroll
-        for (int w = 0; w < kMlpH / 32; ++w) v += red[j][w];
-        logits[r0 + j] = v;
+        for (int w = 0; w < kMlpH / 32; ++w) v += red[threadIdx.x][w];
+        logits[r0 + threadIdx.x] = v;
     }
 }
 
 // dpre[r,j] = da[r] W2[j] (1 - h[r,j]^2)  (kept for the parameter sums);
 // dm[r,c] = inv_pp * sum_j dpre[r,j] W1[j,c]
+constexpr int kMlpDmRows = 8;                         // rows per CTA of the dm kernel
+
 template <typename TP>
 __global__ void __launch_bounds__(256) ba_mlp_dm_kernel(const float* __restrict__ da,
                                                         const float* __restrict__ h, int rows, int C,
@@ -503,9 +527,9 @@ __global__ void __launch_bounds__(256) ba_mlp_dm_kernel(const float* __restrict_
                                                         const TP* __restrict__ w2, float inv_pp,
                                                         float* __restrict__ dpre,
                                                         float* __restrict__ dm) {
-    __shared__ float dp[kMlpRows][kMlpH];
-    const int r0 = blockIdx.x * kMlpRows;
-    for (int i = threadIdx.x; i < kMlpRows * kMlpH; i += 256) {
+    __shared__ __align__(16) float dp[kMlpDmRows][kMlpH];
+    const int r0 = blockIdx.x * kMlpDmRows;
+    for (int i = threadIdx.x; i < kMlpDmRows * kMlpH; i += 256) {
         const int r = i / kMlpH, j = i - r * kMlpH;
         float v = 0.f;
         if (r0 + r < rows) {
@@ -517,17 +541,24 @@ __global__ void __launch_bounds__(256) ba_mlp_dm_kernel(const float* __restrict_
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
-        float acc[kMlpRows];
+        float acc[kMlpDmRows];
 #pragma unroll
-        for (int r = 0; r < kMlpRows; ++r) acc[r] = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < kMlpH; ++j) {
-            const float w = ldv<TP>(w1 + (size_t)j * C + c);
+        for (int r = 0; r < kMlpDmRows; ++r) acc[r] = 0.f;
+#pragma unroll 2
+        for (int j = 0; j < kMlpH; j += 4) {          // four independent W1 loads in flight
+            const float w0 = ldv<TP>(w1 + (size_t)j * C + c), w1v = ldv<TP>(w1 + (size_t)(j + 1) * C + c);
+            const float w2v = ldv<TP>(w1 + (size_t)(j + 2) * C + c), w3v = ldv<TP>(w1 + (size_t)(j + 3) * C + c);
 #pragma unroll
-            for (int r = 0; r < kMlpRows; ++r) acc[r] = fmaf(dp[r][j], w, acc[r]);
+            for (int r = 0; r < kMlpDmRows; ++r) {
+                const float4 d = *reinterpret_cast<const float4*>(&dp[r][j]);
+                acc[r] = fmaf(d.x, w0, acc[r]);
+                acc[r] = fmaf(d.y, w1v, acc[r]);
+                acc[r] = fmaf(d.z, w2v, acc[r]);
+                acc[r] = fmaf(d.w, w3v, acc[r]);
+            }
         }
 #pragma unroll
-        for (int r = 0; r < kMlpRows; ++r)
+        for (int r = 0; r < kMlpDmRows; ++r)
             if (r0 + r < rows) dm[(size_t)(r0 + r) * C + c] = acc[r] * inv_pp;
     }
 }
@@ -755,7 +786,7 @@ int htd_bias_grad(const void* g, int g_dtype, const float* rois, int K, int PP, 
             bin_sum_kernel<__nv_bfloat16><<<(unsigned)K, 256, 0, st>>>(
                 static_cast<const __nv_bfloat16*>(g), K, PP, C, 1.f, partial);
         HTD_CHECK_LAUNCH("htd_bias_grad(bin sums)");
-        rows_by_image_kernel<<<dim3((C + 255) / 256, B), 256, 0, st>>>(partial, rois, K, C, B, dbias);
+        rows_by_image_kernel<<<dim3((C + 31) / 32, B), 1024, 0, st>>>(partial, rois, K, C, B, dbias);
         HTD_CHECK_LAUNCH("htd_bias_grad(rows)");
         return HTD_OK;
     }
@@ -791,13 +822,13 @@ int htd_ba_mlp_fwd(const float* m, long long rows, int C, int H, const void* w1,
     if (rows == 0) return HTD_OK;
     HTD_CHECK_ARG(m && w1 && b1 && w2 && b2 && h && logits, "htd_ba_mlp_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const unsigned grid = (unsigned)((rows + kMlpRows - 1) / kMlpRows);
+    const unsigned grid = (unsigned)((rows + kMlpFwdRows - 1) / kMlpFwdRows);
     if (p_dtype == HTD_F32)
-        ba_mlp_fwd_kernel<float><<<grid, kMlpH, 0, st>>>(
+        ba_mlp_fwd_kernel<float><<<grid, 2 * kMlpH, 0, st>>>(
             m, (int)rows, C, static_cast<const float*>(w1), static_cast<const float*>(b1),
             static_cast<const float*>(w2), static_cast<const float*>(b2), h, logits);
     else
-        ba_mlp_fwd_kernel<__nv_bfloat16><<<grid, kMlpH, 0, st>>>(
+        ba_mlp_fwd_kernel<__nv_bfloat16><<<grid, 2 * kMlpH, 0, st>>>(
             m, (int)rows, C, static_cast<const __nv_bfloat16*>(w1),
             static_cast<const __nv_bfloat16*>(b1), static_cast<const __nv_bfloat16*>(w2),
             static_cast<const __nv_bfloat16*>(b2), h, logits);
@@ -816,7 +847,7 @@ int htd_ba_mlp_bwd(const float* da, const float* h, const float* m, long long ro
     cudaStream_t st = (cudaStream_t)stream;
     float* dpre = workspace;
     float* partial = workspace + rows * kMlpH;
-    const unsigned grid = (unsigned)((rows + kMlpRows - 1) / kMlpRows);
+    const unsigned grid = (unsigned)((rows + kMlpDmRows - 1) / kMlpDmRows);
 #define CALL(TP)                                                                               \
     do {                                                                                       \
         ba_mlp_dm_kernel<TP><<<grid, 256, 0, st>>>(da, h, (int)rows, C,                        \

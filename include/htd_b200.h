@@ -203,7 +203,7 @@ int htd_ba_fuse_bwd(const void* R, int r_dtype, const void* dout, int dout_dtype
  * (AdptRoIExtractor's conv1 / tanh / conv2 on the globally pooled RoI maps,
  * adaptative_roi_extractor.py:60-74; the 1x1 convs on 1x1 maps are these two products).
  * Parameters are read in their own dtype (p_dtype: HTD_F32 / HTD_BF16, one for all four);
- * H must be 128 and C a multiple of 32 up to 512 (htd_ba_mlp_supported).
+ * H must be 128 and C a multiple of 32 up to 256 (htd_ba_mlp_supported).
  * Backward: dm = inv_pp * (da W2 (1 - h^2)) W1 and the four parameter gradients (written in
  * p_dtype); workspace = htd_ba_mlp_workspace_floats(rows, C) floats.  Deterministic. */
 int htd_ba_mlp_supported(int C, int H);

@@ -164,7 +164,7 @@ def test_layout_roundtrip():
     assert torch.equal(yb, x.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize('rows,C', [(1024, 256), (37, 256), (8, 32), (260, 512)])
+@pytest.mark.parametrize('rows,C', [(1024, 256), (37, 256), (8, 32), (260, 128)])
 @pytest.mark.parametrize('pd', ['f32', 'bf16'])
 def test_ba_attention_mlp_fused(rows, C, pd):
     """htd_ba_mlp_fwd / _bwd (tanh MLP of the BA attention on the bin means) against the same
