@@ -73,6 +73,8 @@ SIGNATURES = {
                                 ctypes.POINTER(HtdBwdSource), c_int, c_int, c_int, c_void_p],
     'htd_layout_convert': [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     'htd_ba_bin_mean': [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p],
+    'htd_roi_flatten': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                        c_void_p],
     'htd_ba_fuse_fwd': [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                         c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p],
     'htd_ba_fuse_bwd': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,

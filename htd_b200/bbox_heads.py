@@ -415,8 +415,12 @@ class ConvFCBBoxHead(BBoxHead):
             nn.init.xavier_uniform_(m.weight)
             nn.init.constant_(m.bias, 0)
 
-    def forward(self, x):
-        x = ops.flatten_roi_feats(x)
+    def forward(self, x, sfa_bias=None, rois=None):
+        """``sfa_bias`` ([B,C,1,1]) + ``rois`` (optional): the global-context vector the reference
+        adds to the RoI features before this head (``_fuse_global``, htd_roi_head.py:133-141),
+        added here while the features are flattened - the extraction that produced ``x`` then
+        does not depend on the global-context head."""
+        x = ops.flatten_roi_feats(x, sfa_bias, rois)
         for m in self.shared_fcs:
             x = fc(m, x, relu=True)
         return cls_reg_outputs(self, x)

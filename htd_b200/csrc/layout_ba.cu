@@ -112,7 +112,9 @@ __device__ __forceinline__ void stvec(T* p, const float (&v)[V]) {
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) transpose_flat_kernel(const TS* __restrict__ src,
                                                              TD* __restrict__ dst, int R, int S,
-                                                             int pitch, int image_off) {
+                                                             int pitch, int image_off,
+                                                             const float* __restrict__ bias,
+                                                             const float* __restrict__ rois, int B) {
     extern __shared__ __align__(16) unsigned char tr_smem[];
     TS* tile = reinterpret_cast<TS*>(tr_smem);
     TD* image = reinterpret_cast<TD*>(tr_smem + image_off);
@@ -146,11 +148,20 @@ __global__ void __launch_bounds__(256) transpose_flat_kernel(const TS* __restric
     // destination flat index o = c*R + r: consecutive lanes walk r, i.e. tile rows `pitch` apart;
     // (c, r) advance by 256 flat positions per trip without a division
     {
+        // optional per-(image, column) bias: matrix n belongs to image rois[5 n] (the SFA vector
+        // added to a RoI's channels while its map changes to the FC flatten order)
+        const float* bn = nullptr;
+        if (bias != nullptr) {
+            const int img = (int)rois[(size_t)blockIdx.x * 5];
+            if (img >= 0 && img < B) bn = bias + (size_t)img * S;
+        }
         const int dc = 256 / R, dr = 256 - dc * R;
         int c = threadIdx.x / R, r = threadIdx.x - c * R;
 #pragma unroll 4
         for (int o = threadIdx.x; o < E; o += 256) {
-            image[o] = from_f<TD>(to_f<TS>(tile[r * pitch + c]));
+            float v = to_f<TS>(tile[r * pitch + c]);
+            if (bn != nullptr) v += bn[c];
+            image[o] = from_f<TD>(v);
             c += dc;
             r += dr;
             if (r >= R) { r -= R; ++c; }
@@ -475,13 +486,28 @@ __global__ void __launch_bounds__(2 * kMlpH) ba_mlp_fwd_kernel(const float* __re
     const float bj = ldv<TP>(b1 + j);
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = bj;
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        __syncthreads();
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {                // 128 x 32 tile, 32 consecutive c per warp
-            const int idx = i * 2 * kMlpH + threadIdx.x, jj = idx >> 5, cc = idx & 31;
-            wt[cc][jj] = ldv<TP>(w1 + (size_t)jj * C + c0 + cc);
+    // W1 chunk [128 j][32 c] as 16-byte vectors: VW elements per vector, NV vectors per thread;
+    // the next chunk's vectors are in flight while the current one is consumed
+    constexpr int VW = 16 / (int)sizeof(TP), NV = kMlpH * 32 / VW / (2 * kMlpH);
+    uint4 pre[NV];
+    auto fetch = [&](int c0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = i * 2 * kMlpH + threadIdx.x, jj = v / (32 / VW), cq = (v % (32 / VW)) * VW;
+            pre[i] = *reinterpret_cast<const uint4*>(w1 + (size_t)jj * C + c0 + cq);
         }
+    };
+    fetch(0);
+    for (int c0 = 0; c0 < C; c0 += 32) {
+        __syncthreads();                              // previous chunk consumed (and sm filled)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = i * 2 * kMlpH + threadIdx.x, jj = v / (32 / VW), cq = (v % (32 / VW)) * VW;
+            const TP* e = reinterpret_cast<const TP*>(&pre[i]);
+#pragma unroll
+            for (int k = 0; k < VW; ++k) wt[cq + k][jj] = ldv<TP>(e + k);
+        }
+        if (c0 + 32 < C) fetch(c0 + 32);
         __syncthreads();
 #pragma unroll
         for (int cq = 0; cq < 32; cq += 4) {
@@ -544,17 +570,21 @@ __global__ void __launch_bounds__(256) ba_mlp_dm_kernel(const float* __restrict_
         float acc[kMlpDmRows];
 #pragma unroll
         for (int r = 0; r < kMlpDmRows; ++r) acc[r] = 0.f;
-#pragma unroll 2
-        for (int j = 0; j < kMlpH; j += 4) {          // four independent W1 loads in flight
-            const float w0 = ldv<TP>(w1 + (size_t)j * C + c), w1v = ldv<TP>(w1 + (size_t)(j + 1) * C + c);
-            const float w2v = ldv<TP>(w1 + (size_t)(j + 2) * C + c), w3v = ldv<TP>(w1 + (size_t)(j + 3) * C + c);
+#pragma unroll 1
+        for (int j0 = 0; j0 < kMlpH; j0 += 16) {      // sixteen independent W1 loads in flight
+            float w[16];
 #pragma unroll
-            for (int r = 0; r < kMlpDmRows; ++r) {
-                const float4 d = *reinterpret_cast<const float4*>(&dp[r][j]);
-                acc[r] = fmaf(d.x, w0, acc[r]);
-                acc[r] = fmaf(d.y, w1v, acc[r]);
-                acc[r] = fmaf(d.z, w2v, acc[r]);
-                acc[r] = fmaf(d.w, w3v, acc[r]);
+            for (int k = 0; k < 16; ++k) w[k] = ldv<TP>(w1 + (size_t)(j0 + k) * C + c);
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+#pragma unroll
+                for (int r = 0; r < kMlpDmRows; ++r) {
+                    const float4 d = *reinterpret_cast<const float4*>(&dp[r][j0 + k]);
+                    acc[r] = fmaf(d.x, w[k], acc[r]);
+                    acc[r] = fmaf(d.y, w[k + 1], acc[r]);
+                    acc[r] = fmaf(d.z, w[k + 2], acc[r]);
+                    acc[r] = fmaf(d.w, w[k + 3], acc[r]);
+                }
             }
         }
 #pragma unroll
@@ -673,7 +703,8 @@ int htd_layout_convert(const void* src, int src_dtype, void* dst, int dst_dtype,
     do {                                                                                      \
         HTD_SMEM_OPTIN((transpose_flat_kernel<TS, TD>), 100 * 1024, "htd_layout_convert");    \
         transpose_flat_kernel<TS, TD><<<(unsigned)N, 256, smem, st>>>(                        \
-            static_cast<const TS*>(src), static_cast<TD*>(dst), R, S, pitch, (int)image_off); \
+            static_cast<const TS*>(src), static_cast<TD*>(dst), R, S, pitch, (int)image_off,  \
+            nullptr, nullptr, 0);                                                             \
     } while (0)
         DISPATCH2(src_dtype, dst_dtype, CALL);
 #undef CALL
@@ -706,6 +737,36 @@ int htd_layout_convert(const void* src, int src_dtype, void* dst, int dst_dtype,
 #undef CALL
 #undef LAUNCH
     HTD_CHECK_LAUNCH("htd_layout_convert");
+    return HTD_OK;
+}
+
+int htd_roi_flatten(const void* src, int src_dtype, void* dst, int dst_dtype, int K, int PP, int C,
+                    const float* bias, const float* rois, int B, htd_stream_t stream) {
+    HTD_CHECK_ARG(dt_ok(src_dtype) && dt_ok(dst_dtype) && K >= 0 && PP >= 1 && C >= 1,
+                  "htd_roi_flatten: bad arguments");
+    HTD_CHECK_ARG(!bias || (rois && B >= 1), "htd_roi_flatten: bias needs rois and B");
+    if (K == 0) return HTD_OK;
+    HTD_CHECK_ARG(src && dst, "htd_roi_flatten: null pointer");
+    const size_t es = src_dtype == HTD_F32 ? 4 : 2, ed = dst_dtype == HTD_F32 ? 4 : 2;
+    const long long E = (long long)PP * C;
+    const int pitch = (C & 1) ? C : C + 1;
+    const size_t image_off = ((size_t)PP * pitch * es + 15) & ~(size_t)15;
+    const size_t smem = image_off + (size_t)E * ed;
+    HTD_CHECK_ARG(E <= kFlatMax && E % 8 == 0 && smem <= 100 * 1024 &&
+                      ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0),
+                  "htd_roi_flatten: a RoI map of %d bins x %d channels does not fit the "
+                  "whole-matrix kernel (use htd_layout_convert)", PP, C);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(TS, TD)                                                                          \
+    do {                                                                                      \
+        HTD_SMEM_OPTIN((transpose_flat_kernel<TS, TD>), 100 * 1024, "htd_roi_flatten");       \
+        transpose_flat_kernel<TS, TD><<<(unsigned)K, 256, smem, st>>>(                        \
+            static_cast<const TS*>(src), static_cast<TD*>(dst), PP, C, pitch, (int)image_off, \
+            bias, rois, B);                                                                   \
+    } while (0)
+    DISPATCH2(src_dtype, dst_dtype, CALL);
+#undef CALL
+    HTD_CHECK_LAUNCH("htd_roi_flatten");
     return HTD_OK;
 }
 

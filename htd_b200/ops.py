@@ -64,14 +64,25 @@ def to_channels_last(x, dtype=None):
 class _FlattenRoIFeats(torch.autograd.Function):
     """[K,C,P,P] RoI features with channels-last strides -> [K, C*P*P] in the reference's
     flatten order (c*PP + bin), which the FC weights index (htd_bbox_head.py:191,
-    convfc_bbox_head.py:145).  Tiled transpose kernel in both directions instead of ATen's
-    strided copy (0.1 ms per 25 MB in the round-1 profile)."""
+    convfc_bbox_head.py:145).  Transpose kernel in both directions instead of ATen's strided copy
+    (0.1 ms per 25 MB in the round-1 profile).  With ``bias`` ([B,C,1,1]) and ``rois`` the SFA
+    vector of each RoI's image is added on the way (``_fuse_global``, htd_roi_head.py:133-141)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, bias, rois):
         K, C, P, Q = x.shape
         out = torch.empty((K, C * P * Q), dtype=x.dtype, device=x.device)
-        _convert(x, out, K, P * Q, C)            # memory [K, PQ, C] -> [K, C, PQ]
+        ctx.bias_shape = None
+        if bias is None:
+            _convert(x, out, K, P * Q, C)        # memory [K, PQ, C] -> [K, C, PQ]
+        else:
+            B = bias.shape[0]
+            bias_c = bias.detach().reshape(B, C).float().contiguous()
+            rois_c = rois.detach().float().contiguous()
+            check(lib().htd_roi_flatten(ptr(x), dt(x), ptr(out), dt(out), K, P * Q, C, ptr(bias_c),
+                                        ptr(rois_c), B, stream()), 'htd_roi_flatten')
+            ctx.bias_shape, ctx.bias_dtype = tuple(bias.shape), bias.dtype
+            ctx.save_for_backward(rois_c)
         ctx.shape = (K, C, P, Q)
         return out
 
@@ -81,7 +92,11 @@ class _FlattenRoIFeats(torch.autograd.Function):
         g = g.contiguous()
         out = torch.empty((K, P, Q, C), dtype=g.dtype, device=g.device)
         _convert(g, out, K, C, P * Q)            # [K, C, PQ] -> [K, PQ, C]
-        return out.permute(0, 3, 1, 2)
+        dbias = None
+        if ctx.bias_shape is not None and ctx.needs_input_grad[1]:
+            rois_c, = ctx.saved_tensors
+            dbias = _bias_grad(out, rois_c, ctx.bias_shape[0]).reshape(ctx.bias_shape).to(ctx.bias_dtype)
+        return out.permute(0, 3, 1, 2), dbias, None
 
 
 class _FlattenWithPrefix(torch.autograd.Function):
@@ -124,11 +139,27 @@ def flatten_with_prefix(x, spans):
     return _FlattenWithPrefix.apply(x, spans)
 
 
-def flatten_roi_feats(x):
-    """``x.flatten(1)`` for RoI features; uses the transpose kernel when ``x`` is a CUDA
-    channels-last tensor, plain flatten otherwise."""
+def flatten_fuses_bias(x):
+    """True when ``flatten_roi_feats(x, bias, rois)`` adds the bias inside the transpose kernel."""
+    return x.is_cuda and x.dim() == 4 and _is_cl(x) and x.dtype in _lib._DT and x.shape[1] > 1 and \
+        x.shape[1] * x.shape[2] * x.shape[3] <= 12800 and (x.shape[1] * x.shape[2] * x.shape[3]) % 8 == 0
+
+
+def flatten_fuses_bias_shape(C, output_size):
+    """Same question for a [K, C, P, Q] channels-last CUDA map that does not exist yet."""
+    P, Q = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+    return C > 1 and C * P * Q <= 12800 and (C * P * Q) % 8 == 0
+
+
+def flatten_roi_feats(x, bias=None, rois=None):
+    """``x.flatten(1)`` for RoI features (+ the per-image ``bias`` [B,C,1,1] of the RoIs' images,
+    ``rois`` [K,5]); uses the transpose kernel when ``x`` is a CUDA channels-last tensor, plain
+    flatten otherwise."""
+    if bias is not None and not flatten_fuses_bias(x):
+        x = x + bias[rois[:, 0].long()].to(x.dtype)
+        bias = None
     if x.is_cuda and x.dim() == 4 and _is_cl(x) and x.dtype in _lib._DT and x.shape[1] > 1:
-        return _FlattenRoIFeats.apply(x)
+        return _FlattenRoIFeats.apply(x, bias, rois)
     return x.flatten(1)
 
 

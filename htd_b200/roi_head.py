@@ -157,26 +157,37 @@ class HTDRoIHead(nn.Module):
     def _on(self, which, t):
         return self.overlap and getattr(self, which) and t.is_cuda
 
-    def _global_context(self, x, loss_fn):
+    def _global_context(self, x, loss_fn, defer=False):
         """Global-context head + its loss (htd_roi_head.py:245-249) next to the channels-last
         conversion of the pyramid: both only read ``x``, the head's launches are small
         (2 x 256 x 13 x 21 maps), so on a side stream it costs nothing on the forward critical
         path, and autograd mirrors the branch in backward (next to the backward gather).
-        Returns (channels-last pyramid, loss, global_feat)."""
+        Returns (channels-last pyramid, loss, global_feat, join).  ``defer``: the current stream
+        does NOT wait for the branch here; ``global_feat.ready`` is an event a consumer stream
+        waits on before it reads the vector (stage 0 does so after its extraction), and ``join()``
+        makes the current stream wait for the whole branch (vector and loss)."""
         if not self._on('overlap_global', x[0]):
             x_cl = self._pyramid(x)
             mc_pred, global_feat = self.glbctx_head(x)
-            return x_cl, loss_fn(mc_pred), global_feat
+            return x_cl, loss_fn(mc_pred), global_feat, lambda: None
         cur, side = torch.cuda.current_stream(), self._stream('global', x[0].device, priority=-1)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             mc_pred, global_feat = self.glbctx_head(x)
+            ready = torch.cuda.Event()
+            ready.record()
             loss = loss_fn(mc_pred)
         x_cl = self._pyramid(x)
-        cur.wait_stream(side)
-        for t in (loss, global_feat):
-            t.record_stream(cur)
-        return x_cl, loss, global_feat
+
+        def join():
+            cur.wait_stream(side)
+            for t in (loss, global_feat):
+                t.record_stream(cur)
+        if defer:
+            global_feat.ready = ready
+        else:
+            join()
+        return x_cl, loss, global_feat, join
 
     def _pyramid(self, x):
         """Channels-last copy of the levels the extractors read, made once per call."""
@@ -199,6 +210,19 @@ class HTDRoIHead(nn.Module):
             x_cl = self._pyramid(x)
         g = global_feat if self.with_global else None
         if stage == 0:
+            late = getattr(global_feat, 'ready', None) if g is not None else None
+            if late is not None and ops.flatten_fuses_bias_shape(ext.out_channels,
+                                                                  ext.roi_layers[0].output_size):
+                # the global-context head is still running on its own stream: extract without the
+                # SFA vector, wait for it only now, and add it while the features are flattened
+                # for the FCs (same sum, one more rounding in bf16); `bbox_feats` is returned
+                # WITHOUT the vector in this mode
+                bbox_feats = ext(x_cl, rois)
+                torch.cuda.current_stream().wait_event(late)
+                cls_score, bbox_pred = self.bbox_head[0](bbox_feats, sfa_bias=g, rois=rois)
+                return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
+            if late is not None:
+                torch.cuda.current_stream().wait_event(late)
             bbox_feats = ext(x_cl, rois, bias=g)          # RoIAlign + SFA add in one launch
             cls_score, bbox_pred = self.bbox_head[0](bbox_feats)
             return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
@@ -284,15 +308,21 @@ class HTDRoIHead(nn.Module):
             proposal_list = [p.clone() for p in proposal_list]   # private copy: see the event below
         samp = sample(0, proposal_list)
         global_feat = None
-        if self.with_global:
-            x_cl, losses['loss_global'], global_feat = self._global_context(
-                x, lambda mc_pred: self.glbctx_head.loss(mc_pred, gt_labels))
-        if self.inputs_consumed_event is not None and x[0].is_cuda:
-            # everything downstream reads the channels-last copy / the SFA head's cast of P6 only
-            # (and the proposals through copies made below): the caller may refill `x` from here on
-            # - graphed.GraphedTrainStep(flat_inputs=True) overlaps the next upload with this step
-            self.inputs_consumed_event.record()
         st0 = self._stream('stage0', x[0].device) if self._on('overlap_stages', x[0]) else None
+        join_global = lambda: None
+        if self.with_global:
+            x_cl, losses['loss_global'], global_feat, join_global = self._global_context(
+                x, lambda mc_pred: self.glbctx_head.loss(mc_pred, gt_labels), defer=st0 is not None)
+
+        def inputs_consumed():
+            if self.inputs_consumed_event is not None and x[0].is_cuda:
+                # everything downstream reads the channels-last copy / the SFA head's cast of P6
+                # only (and the proposals through copies made above): the caller may refill `x`
+                # from here on - graphed.GraphedTrainStep(flat_inputs=True) overlaps the next
+                # upload with this step
+                self.inputs_consumed_event.record()
+        if st0 is None:
+            inputs_consumed()
         with _Branch(st0, (list(x_cl), global_feat)) as br:
             res = self._bbox_forward_train(0, x, samp, gt_bboxes, gt_labels, self.train_cfg[0],
                                            img_metas, global_feat, x_cl)
@@ -302,6 +332,11 @@ class HTDRoIHead(nn.Module):
             lw = self.stage_loss_weights[0]
             for name, value in res['loss_bbox'].items():
                 losses[f's0.{name}'] = value * lw if 'loss' in name else value
+        if st0 is not None:                 # stage 0 is issued: now this stream needs the vector
+            join_global()
+            if global_feat is not None and hasattr(global_feat, 'ready'):
+                del global_feat.ready
+            inputs_consumed()
         br.join((res, losses))
         roi_labels = res['bbox_targets'][0]
         with torch.no_grad():
@@ -343,7 +378,7 @@ class HTDRoIHead(nn.Module):
                 nc1 = mc_pred.size(1)
                 hot = (gt_labels[:, :, None] == torch.arange(nc1, device=dev)) & real[:, :, None]
                 return self.glbctx_head.loss_multihot(mc_pred, hot.any(1))
-            x_cl, losses['loss_global'], global_feat = self._global_context(x, multihot_loss)
+            x_cl, losses['loss_global'], global_feat, _ = self._global_context(x, multihot_loss)
         else:
             x_cl = self._pyramid(x)
         cand, valid = proposals, None

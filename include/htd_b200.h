@@ -198,6 +198,15 @@ int htd_ba_fuse_fwd(const void* R, int r_dtype, const float* logits, int L, int 
 int htd_ba_fuse_bwd(const void* R, int r_dtype, const void* dout, int dout_dtype, const float* w,
                     int L, int K, int PP, int C, float* da, htd_stream_t stream);
 
+/* RoI maps [K, PP, C] (channels-last) -> the FC flatten order [K, C, PP] of the reference
+ * (x.flatten(1) of an NCHW tensor, convfc_bbox_head.py:145), optionally adding the SFA vector of
+ * the RoI's image on the way: dst[k, c, p] = src[k, p, c] + bias[image(k), c]
+ * (HTDRoIHead._fuse_global, htd_roi_head.py:133-141, for stage 0: the extraction then does not
+ * wait for the global-context head).  bias [B, C] fp32 or NULL; rois [K, 5] (image index first).
+ * PP * C <= 12800 and a multiple of 8. */
+int htd_roi_flatten(const void* src, int src_dtype, void* dst, int dst_dtype, int K, int PP, int C,
+                    const float* bias, const float* rois, int B, htd_stream_t stream);
+
 /* Attention MLP of the BA extractor on the bin means m [rows, C] (rows = levels * RoIs):
  * h = tanh(m W1^T + b1) [rows, H], logits = h W2^T + b2 [rows]
  * (AdptRoIExtractor's conv1 / tanh / conv2 on the globally pooled RoI maps,

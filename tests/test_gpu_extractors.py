@@ -164,6 +164,29 @@ def test_layout_roundtrip():
     assert torch.equal(yb, x.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_flatten_with_sfa_bias(dtype):
+    """ops.flatten_roi_feats(x, bias, rois) = (x + bias[image]).flatten(1) and its gradients
+    (htd_roi_flatten: the SFA vector added while the RoI maps change to the FC flatten order)."""
+    from htd_b200 import ops
+    from oracle import cases
+    g = torch.Generator(device='cuda').manual_seed(3)
+    K, C, B = 37, 256, 3
+    x = torch.randn(K, 7, 7, C, device='cuda', generator=g).to(dtype).permute(0, 3, 1, 2).requires_grad_(True)
+    bias = torch.randn(B, C, 1, 1, device='cuda', generator=g).to(dtype).requires_grad_(True)
+    rois = torch.rand(K, 5, device='cuda', generator=g) * 100
+    rois[:, 0] = torch.randint(0, B, (K,), device='cuda', generator=g).float()
+    assert ops.flatten_fuses_bias(x)
+    y = ops.flatten_roi_feats(x, bias, rois)
+    want = (x.float() + bias.float()[rois[:, 0].long()]).flatten(1)
+    tol = 1e-6 if dtype == torch.float32 else 8e-3
+    assert y.shape == want.shape and cases.rel_err(y.float(), want) <= tol
+    dy = torch.randn_like(y)
+    gx, gb = torch.autograd.grad((y.float() * dy.float()).sum(), (x, bias))
+    wx, wb = torch.autograd.grad((want * dy.float()).sum(), (x, bias))
+    assert cases.rel_err(gx.float(), wx.float()) <= tol and cases.rel_err(gb.float(), wb.float()) <= tol
+
+
 @pytest.mark.parametrize('rows,C', [(1024, 256), (37, 256), (8, 32), (260, 128)])
 @pytest.mark.parametrize('pd', ['f32', 'bf16'])
 def test_ba_attention_mlp_fused(rows, C, pd):
