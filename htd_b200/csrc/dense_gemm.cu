@@ -60,7 +60,11 @@ constexpr int kWgStage = (2 + 4) * kWgChunk;         // A: 2 chunks, B: up to 4 
 // for conv wgrad
 constexpr int kDRingBytes = 3 * 5 * kWgChunk > kDStages * kDStage ? 3 * 5 * kWgChunk : kDStages * kDStage;
 static_assert(2 * kWgStage <= kDRingBytes && kDRingBytes + 1280 <= 232448, "shared-memory ring");
-constexpr int kDSmem = kDRingBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kConvStage = 2 * 32 * 128 * 2;         // conv epilogue: two [32 px][128 ch] bf16 blocks
+// largest launch: the wgrad ring, or the 4 x 48 KB ring plus the conv epilogue staging
+constexpr int kDSmem = (kDRingBytes > kDStages * kDStage + kConvStage ? kDRingBytes : kDStages * kDStage + kConvStage) +
+                       1024 /*align*/ + 256 /*barriers*/;
+static_assert(kDSmem <= 232448, "shared memory per CTA");
 constexpr int kChunk = 64 * 128;                     // one 64-element MN chunk x 64 k rows
 // conv fprop / dgrad N tile: 4 RoIs as two halves of 2 RoIs (98 rows) whose second half starts at
 // row 104 (a multiple of 8: the 128-byte swizzle phase of a TMA destination) -> UMMA N = 208
@@ -103,6 +107,7 @@ struct DenseParams {
     long long ldg;
     float* partial;               // [splits, M, N] fp32 (splits > 1)
     int pair;                     // CTA-pair form (dense_pair_kernel): tiles_m counts 256-row tiles
+    int ring_bytes;               // nstages * stage_bytes: the barriers follow the ring
     int debug;                    // experiments (HTD_DENSE_DEBUG): 1 = no MMA issue, 2 = no TMA loads
 };
 
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
                                                ~static_cast<uintptr_t>(1023));
     // stage s = [A part | B part] at smem + s * stage_bytes (sizes are multiples of 1024 B)
     const int nst = p.nstages;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDRingBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
     uint64_t* empty_bar = full_bar + kDMaxStages;
     uint64_t* tfull_bar = empty_bar + kDMaxStages;    // [2] accumulator slots
     uint64_t* tempty_bar = tfull_bar + 2;             // [2]
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(kDThreads, 1)
 
     if (p.zero_fill) {                                // uniform
         uint4* z = reinterpret_cast<uint4*>(smem);
-        for (int i = threadIdx.x; i < kDRingBytes / 16; i += kDThreads)
+        for (int i = threadIdx.x; i < p.ring_bytes / 16; i += kDThreads)
             z[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();                          // generic-proxy zeros -> visible to UMMA / TMA
     }
@@ -458,6 +463,55 @@ __global__ void __launch_bounds__(kDThreads, 1)
                     uint32_t v[32];
                     __syncwarp();
                     tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256 + (uint32_t)(ch * 32), v);
+                    if (conv_t) {
+                        // D^T = [pixel, channel]: a lane holds ONE channel of 32 pixels.  The four
+                        // warps put their [32 px][32 ch] blocks side by side in shared memory and
+                        // the 128 threads then write whole pixel rows (256 B of channels) with
+                        // 16-byte stores; the ReLU gate of the backward is read the same way.
+                        // (2-byte stores, 64 B per warp instruction, cost ~8 us per tile.)
+                        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(smem + p.ring_bytes + 256) +
+                                             (ch & 1) * (32 * 128);
+                        if (!(DENSE_DBG(p) & 4)) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float x = __uint_as_float(v[j]);
+                                if (p.relu) x = fmaxf(x, 0.f);
+                                stg[j * 128 + q * 32 + lane] = __float2bfloat16_rn(x);
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (has_k && !(DENSE_DBG(p) & 4)) {
+                            const int nc = min(32, nvalid - ch * 32);
+                            const int m0t = wk.mt * kDTileM;
+                            const int valid_ch = min(128, p.M - m0t);      // multiple of 8
+                            const int t128 = q * 32 + lane;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int vv = t128 + i * 128, px = vv >> 4, c8 = (vv & 15) * 8;
+                                if (px < nc && c8 < valid_ch) {
+                                    uint4 val = *reinterpret_cast<const uint4*>(stg + px * 128 + c8);
+                                    const size_t row = (size_t)(col0 + ch * 32 + px);
+                                    if (p.gate != nullptr) {
+                                        const uint4 gv = *reinterpret_cast<const uint4*>(
+                                            p.gate + row * p.ldg + m0t + c8);
+                                        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                                        uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k) {
+                                            // gate > 0 per bf16 half: sign bit clear and not zero
+                                            const uint32_t lo = gw[k] & 0xffffu, hi = gw[k] >> 16;
+                                            const bool klo = lo != 0u && lo < 0x8000u;
+                                            const bool khi = hi != 0u && hi < 0x8000u;
+                                            w[k] = (klo ? (w[k] & 0xffffu) : 0u) | (khi ? (w[k] & 0xffff0000u) : 0u);
+                                        }
+                                        val = make_uint4(w[0], w[1], w[2], w[3]);
+                                    }
+                                    *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.D) + row * p.ldd + m0t + c8) = val;
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     if (!row_ok || (DENSE_DBG(p) & 4)) continue;
                     const int nc = min(32, nvalid - ch * 32);          // valid columns of this chunk
                     float f[32];
@@ -502,7 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kDThreads, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
     const int nst = p.nstages;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kDRingBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.ring_bytes);
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* tfull_bar = empty_bar + 8;              // [2] accumulator slots
     uint64_t* tempty_bar = tfull_bar + 2;             // [2]
@@ -873,14 +927,20 @@ static int dense_launch(const CUtensorMap& ma, const CUtensorMap& mb, DenseParam
     const long long items = per_split * p.splits;
     HTD_CHECK_ARG(items < 2147483647LL, "htd_dense_gemm: too many tiles");
     const int sms = sm_count();
+    // only the ring this problem needs (4 x 48 KB for the GEMM / fprop / dgrad kinds): the rest of
+    // the SM's shared memory stays free for the small kernels of the step's other branches, which
+    // otherwise wait for a whole persistent CTA to retire
+    p.ring_bytes = p.nstages * p.stage_bytes;
+    const size_t smem = (size_t)p.ring_bytes + 1024 /*align*/ + 256 /*barriers*/ +
+                        (p.transposed && !p.pair ? kConvStage : 0);
     if (p.pair) {
         HTD_SMEM_OPTIN(dense_pair_kernel, kDSmem, "htd_dense_gemm(pair)");
         const long long clusters = items < sms / 2 ? items : sms / 2;
-        dense_pair_kernel<<<(unsigned)(2 * clusters), kDThreads, kDSmem, st>>>(ma, mb, p);
+        dense_pair_kernel<<<(unsigned)(2 * clusters), kDThreads, smem, st>>>(ma, mb, p);
     } else {
         HTD_SMEM_OPTIN(dense_gemm_kernel, kDSmem, "htd_dense_gemm");
         const unsigned grid = (unsigned)(items < sms ? items : sms);
-        dense_gemm_kernel<<<grid, kDThreads, kDSmem, st>>>(ma, mb, p);
+        dense_gemm_kernel<<<grid, kDThreads, smem, st>>>(ma, mb, p);
     }
     HTD_CHECK_LAUNCH("htd_dense_gemm");
     if (p.splits > 1) {
