@@ -69,6 +69,47 @@ def bbox2result(bboxes, labels, num_classes):
     return [b[l == i, :] for i in range(num_classes)]
 
 
+_FLIP_AXES = {'horizontal': (1,), 'vertical': (0,), 'diagonal': (1, 0)}
+
+
+def bbox_flip(bboxes, img_shape, direction='horizontal'):
+    """core/bbox/transforms.py:5-32 - mirror (..., 4k) boxes inside an image of img_shape (h, w):
+    per mirrored axis the two coordinates swap and become extent - coordinate."""
+    assert bboxes.shape[-1] % 4 == 0
+    out = bboxes.clone()
+    for axis in _FLIP_AXES[direction]:            # axis 1 = x (image width), axis 0 = y
+        lo, hi = (0, 2) if axis == 1 else (1, 3)
+        out[..., lo::4] = img_shape[axis] - bboxes[..., hi::4]
+        out[..., hi::4] = img_shape[axis] - bboxes[..., lo::4]
+    return out
+
+
+def bbox_mapping(bboxes, img_shape, scale_factor, flip, flip_direction='horizontal'):
+    """core/bbox/transforms.py:35-44 - original image -> augmented test image."""
+    scaled = bboxes * bboxes.new_tensor(scale_factor)
+    return bbox_flip(scaled, img_shape, flip_direction) if flip else scaled
+
+
+def bbox_mapping_back(bboxes, img_shape, scale_factor, flip, flip_direction='horizontal'):
+    """core/bbox/transforms.py:47-56 - augmented test image -> original image."""
+    unflipped = bbox_flip(bboxes, img_shape, flip_direction) if flip else bboxes
+    return (unflipped.view(-1, 4) / unflipped.new_tensor(scale_factor)).view(bboxes.shape)
+
+
+def merge_aug_bboxes(aug_bboxes, aug_scores, img_metas, rcnn_test_cfg=None):
+    """core/post_processing/merge_augs.py:50-76 - boxes of every augmentation mapped back to the
+    original image and averaged; scores averaged."""
+    back = []
+    for boxes, meta in zip(aug_bboxes, img_metas):
+        m = meta[0]
+        back.append(bbox_mapping_back(boxes, m['img_shape'], m['scale_factor'], m['flip'],
+                                      m.get('flip_direction', 'horizontal')))
+    merged = torch.stack(back).mean(dim=0)
+    if aug_scores is None:
+        return merged
+    return merged, torch.stack(aug_scores).mean(dim=0)
+
+
 def bbox_overlaps(bboxes1, bboxes2, mode='iou', eps=1e-6):
     """core/bbox/iou_calculators/iou2d_calculator.py:43-158, non-aligned 'iou' / 'iof'."""
     assert mode in ('iou', 'iof')

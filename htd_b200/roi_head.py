@@ -14,7 +14,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .core import as_cfg, bbox2result, bbox2roi
+from .core import (as_cfg, bbox2result, bbox2roi, bbox_mapping, merge_aug_bboxes,
+                   multiclass_nms)
 from .registry import HEADS, build_assigner, build_head, build_roi_extractor, build_sampler
 
 
@@ -464,6 +465,29 @@ class HTDRoIHead(nn.Module):
             results.append(bbox2result(det_bbox, det_label, self.bbox_head[-1].num_classes))
         return results
 
+    def aug_test_merged(self, features, proposal_list, img_metas):
+        """htd_roi_head.py:388-433: every augmented view (one image each) through both stages, the
+        class boxes mapped back to the original image and averaged over the views, scores
+        averaged.  Returns (merged_bboxes [n, 4*classes], merged_scores [n, classes+1])."""
+        aug_bboxes, aug_scores = [], []
+        for x, meta in zip(features, img_metas):
+            m = meta[0]
+            proposals = bbox_mapping(proposal_list[0][:, :4], m['img_shape'], m['scale_factor'],
+                                     m['flip'], m.get('flip_direction', 'horizontal'))
+            rois, cls_score, bbox_pred = self.simple_test_scores(x, [proposals], [m])
+            bboxes, scores = self.bbox_head[-1].get_bboxes(rois, cls_score, bbox_pred,
+                                                           m['img_shape'], m['scale_factor'],
+                                                           rescale=False, cfg=None)
+            aug_bboxes.append(bboxes)
+            aug_scores.append(scores)
+        return merge_aug_bboxes(aug_bboxes, aug_scores, img_metas, self.test_cfg)
+
     def aug_test(self, features, proposal_list, img_metas, rescale=False):
-        raise NotImplementedError('test-time augmentation is outside the accelerated path '
-                                  '(SURVEY.md §8: callers, next)')
+        """htd_roi_head.py:388-440 (configs/htd define no mask branch).  As in the reference the
+        merged boxes are in the original image's scale whatever `rescale` says, and the result is
+        the per-class list of ONE image."""
+        merged_bboxes, merged_scores = self.aug_test_merged(features, proposal_list, img_metas)
+        cfg = as_cfg(self.test_cfg)
+        det_bboxes, det_labels = multiclass_nms(merged_bboxes, merged_scores, cfg.score_thr,
+                                                cfg.nms, cfg.max_per_img)
+        return bbox2result(det_bboxes, det_labels, self.bbox_head[-1].num_classes)
