@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "roi_axis.h"
+#include "tc05.cuh"
 
 namespace htd {
 
@@ -229,25 +230,65 @@ struct PlanParams {
 __global__ void __launch_bounds__(128) roi_plan_fused_kernel(const PlanParams p) {
     __shared__ Axis s_axis[2];
     __shared__ int s_box[4];
-    const int e = blockIdx.x, tid = threadIdx.x;
-    const int l = e / p.K, k = e % p.K;
+    __shared__ int s_rng[kRangeInts];               // y lo[8], y hi[8], x lo[8], x hi[8]
+    const int tid = threadIdx.x;
+    // level-assigned extraction: one CTA per RoI - the entries of the levels the RoI is NOT on are
+    // empty boxes / ranges, written by the same CTA; all-level extraction: one CTA per (level, RoI)
+    const int k = p.roi_level ? blockIdx.x : blockIdx.x % p.K;
     const float* r = p.rois + (size_t)k * 5;
     const int b = (int)r[0];
-    const bool on = ((p.roi_level == nullptr) || (p.roi_level[k] == l)) && b >= 0 && b < p.B;
+    int l = p.roi_level ? p.roi_level[k] : blockIdx.x / p.K;
+    if (p.roi_level) {
+        for (int lo = 0; lo < p.L; ++lo) {
+            if (lo == l && b >= 0 && b < p.B) continue;
+            const int eo = lo * p.K + k;
+            if (tid == 0) {
+                p.offsets[eo] = k * p.ext_max;
+                p.boxes[eo] = make_int4(0, -1, 0, -1);
+            }
+            if (tid < kRangeInts)
+                p.ranges[(size_t)eo * kRangeInts + tid] = (tid / HTD_MAX_POOLED) % 2 == 0 ? 0 : -1;
+        }
+        if (k == 0 && tid == 1) p.offsets[p.L * p.K] = p.K * p.ext_max;
+        if (!(l >= 0 && l < p.L && b >= 0 && b < p.B)) return;
+    }
+    const int e = l * p.K + k;
+    const bool on = b >= 0 && b < p.B;
     int* rg = p.ranges + (size_t)e * kRangeInts;
     const int off = p.roi_level ? k * p.ext_max : p.K * p.base[l] + k * p.ext[l];
     if (tid == 0) p.offsets[e] = off;
-    if (e == 0 && tid == 1)
-        p.offsets[p.L * p.K] = p.roi_level ? p.K * p.ext_max : p.K * (p.base[p.L - 1] + p.ext[p.L - 1]);
+    if (!p.roi_level && e == 0 && tid == 1)
+        p.offsets[p.L * p.K] = p.K * (p.base[p.L - 1] + p.ext[p.L - 1]);
+    // the serial fp64 chains are what a CTA costs in time: the two axes are set up by two threads,
+    // the 2 x P bin ranges by 2 x P threads, and the footprint box is the union of the bin ranges
+    // (roi_range on one thread per axis ran the P bin ranges one after the other: 2/3 of the time)
     if (on) {
-        if (tid == 0) {
-            s_axis[0] = make_axis(r[2], r[4], (double)p.lv[l].scale, p.P, p.lv[l].H, p.sr, 1);
-            roi_range(s_axis[0], p.P, s_box[0], s_box[1]);
+        if (tid == 0) s_axis[0] = make_axis(r[2], r[4], (double)p.lv[l].scale, p.P, p.lv[l].H, p.sr, 1);
+        if (tid == 32) s_axis[1] = make_axis(r[1], r[3], (double)p.lv[l].scale, p.P, p.lv[l].W, p.sr, 1);
+    }
+    __syncthreads();
+    if (tid < kRangeInts) {                         // per-bin pixel ranges (one warp: 2 x P lanes busy)
+        const int axis = tid / (2 * HTD_MAX_POOLED), hi_half = (tid / HTD_MAX_POOLED) & 1;
+        const int pp = tid % HTD_MAX_POOLED;
+        int lo = 0, hi = -1;
+        if (on && !hi_half && pp < p.P) bin_range(s_axis[axis], pp, lo, hi);
+        // lane pp computed both ends; the "hi" lane (pp + 8) takes the second one from it
+        const int hi_from = __shfl_sync(0xffffffffu, hi, (tid & 16) + pp);
+        s_rng[tid] = hi_half ? hi_from : lo;
+    }
+    __syncthreads();
+    if (tid < 2) {                                  // union of the non-empty bin ranges of an axis
+        const int* lo = s_rng + tid * 2 * HTD_MAX_POOLED;
+        const int* hi = lo + HTD_MAX_POOLED;
+        int jlo = 0, jhi = -1;
+        bool any = false;
+        for (int pp = 0; pp < p.P; ++pp) {
+            if (hi[pp] < lo[pp]) continue;
+            if (!any) { jlo = lo[pp]; jhi = hi[pp]; any = true; }
+            else { jlo = min(jlo, lo[pp]); jhi = max(jhi, hi[pp]); }
         }
-        if (tid == 32) {
-            s_axis[1] = make_axis(r[1], r[3], (double)p.lv[l].scale, p.P, p.lv[l].W, p.sr, 1);
-            roi_range(s_axis[1], p.P, s_box[2], s_box[3]);
-        }
+        s_box[2 * tid] = jlo;
+        s_box[2 * tid + 1] = jhi;
     }
     __syncthreads();
     int4 box = make_int4(0, -1, 0, -1);
@@ -258,29 +299,56 @@ __global__ void __launch_bounds__(128) roi_plan_fused_kernel(const PlanParams p)
         if (tid < kRangeInts) rg[tid] = (tid / HTD_MAX_POOLED) % 2 == 0 ? 0 : -1;
         return;
     }
-    if (tid < 2 * HTD_MAX_POOLED) {                 // per-bin pixel ranges
-        const int axis = tid / HTD_MAX_POOLED, pp = tid % HTD_MAX_POOLED;
-        int lo = 0, hi = -1;
-        if (pp < p.P) bin_range(s_axis[axis], pp, lo, hi);
-        rg[axis * 2 * HTD_MAX_POOLED + pp] = lo;
-        rg[axis * 2 * HTD_MAX_POOLED + HTD_MAX_POOLED + pp] = hi;
-    }
+    if (tid < kRangeInts) rg[tid] = s_rng[tid];
+    // Axis-weight tables, 64 rows at a time.  A row (pixel) has non-zero weight only for the bins
+    // whose pixel range contains it - usually one or two of the P - and axis_weight (an fp64 sample
+    // search, ~600 instructions) is what this kernel costs.  A thread PAIR owns a row: the threads
+    // first pick their bins (pair member 0 the 1st, 3rd, .. covering bin, member 1 the 2nd, 4th, ..),
+    // then every lane of the warp makes ONE converged axis_weight call; looping over the bins with
+    // the call inside ran it once per bin touched by any of the warp's rows.
+    __shared__ __align__(16) float s_tab[64][kTabW];
     const int fh = box.y - box.x + 1, fw = box.w - box.z + 1;
+    const int rows = fh + fw;
     float* tab = p.weights + (size_t)off * kTabW;
-    const int n = (fh + fw) * kTabW;
-    for (int base = 0; base < n; base += blockDim.x) {      // uniform trip count: shuffles below
-        const int i = base + tid;
-        const int row = i / kTabW, pp = i % kTabW;
-        float w = 0.f;
-        if (i < n && pp < p.P)
-            w = row < fh ? axis_weight(s_axis[0], pp, box.x + row)
-                         : axis_weight(s_axis[1], pp, box.z + (row - fh));
-        float sum = w;                                      // see weight_table_kernel
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        if (p.P < kTabW && pp == kTabW - 1) w = sum;
-        if (i < n) tab[i] = w;
+    const int rl = tid >> 1, slot = tid & 1;
+    for (int base = 0; base < rows; base += 64) {
+        for (int i = tid; i < 64 * kTabW; i += 128) (&s_tab[0][0])[i] = 0.f;
+        __syncthreads();
+        const int row = base + rl;
+        if (row < rows) {
+            const int axis = row < fh ? 0 : 1;
+            const int j = axis == 0 ? box.x + row : box.z + (row - fh);
+            const int* lo = s_rng + axis * 2 * HTD_MAX_POOLED;
+            const int* hi = lo + HTD_MAX_POOLED;
+            int mine = -1, more = 0, seen = 0;
+            for (int pp = 0; pp < p.P; ++pp)
+                if (j >= lo[pp] && j <= hi[pp]) {
+                    if ((seen & 1) == slot) {
+                        if (mine < 0) mine = pp;
+                        else more = 1;
+                    }
+                    ++seen;
+                }
+            if (mine >= 0) s_tab[rl][mine] = axis_weight(s_axis[axis], mine, j);
+            if (more) {                               // bins narrower than a pixel: rare
+                seen = 0;
+                for (int pp = 0; pp < p.P; ++pp)
+                    if (j >= lo[pp] && j <= hi[pp]) {
+                        if ((seen & 1) == slot && pp != mine)
+                            s_tab[rl][pp] = axis_weight(s_axis[axis], pp, j);
+                        ++seen;
+                    }
+            }
+        }
+        __syncthreads();
+        if (row < rows) {
+            const float* t = s_tab[rl];
+            float4 v = *reinterpret_cast<const float4*>(t + slot * 4);
+            if (slot == 1 && p.P < kTabW)             // entry 7: the row sum (entries P .. 6 are 0)
+                v.w = ((t[6] + t[7]) + (t[4] + t[5])) + ((t[2] + t[3]) + (t[0] + t[1]));
+            *reinterpret_cast<float4*>(tab + (size_t)row * kTabW + slot * 4) = v;
+        }
+        __syncthreads();
     }
 }
 
@@ -541,35 +609,36 @@ constexpr int kPfGroups = 3;                     // consumer groups of P warps: 
                                                  // (one group alone leaves the SM's schedulers idle: 7 warps
                                                  // of dependent shared-load -> fma chains reached 0.095 ms)
 constexpr int kPfRingBytes = 200 * 1024;         // staging ring
+// One unit = one bin row of one RoI; 32 ints, so that the producer's lanes move it with one shared
+// load and one shared store each.
 struct PfUnit {
-    int valid, direct, buf_off, ny, nxs, b, wy_off, wx_off, W;
-    int dx0[HTD_MAX_POOLED], nx[HTD_MAX_POOLED];
-    long long out_off;
-    const void* gsrc;
-};
-// plan of one unit as the producer's lanes read it from global memory, a batch of units at a time
-struct PfPlan {
     const void* gsrc;            // first footprint pixel of the strip
     const float* wy_src;         // the strip's rows / the RoI's columns in the axis-weight tables
     const float* wx_src;
-    int live, b, ny, nxs, W;
-    int dx0[HTD_MAX_POOLED], nx[HTD_MAX_POOLED];
+    long long out_off;           // output element offset of bin (ph, 0)
+    int live, direct, b, ny, nxs, W, need;       // need: ring bytes (strip + both table slices)
+    int dx0[HTD_MAX_POOLED], nx[HTD_MAX_POOLED - 1];
+    int ph;
+    int buf_off;                 // ring offset of the strip; the table slices follow it
 };
+static_assert(sizeof(PfUnit) == 128 && HTD_MAX_POOLED == 8, "PfUnit is moved as 32 ints");
 constexpr int kPfBatch = 32;                     // units whose plan is fetched at once (one per lane)
-constexpr int kPfSmem = kPfRingBytes + kPfUnits * (int)sizeof(PfUnit) + 2 * kPfUnits * 8 +
-                        kPfBatch * (int)sizeof(PfPlan) + 16;
+constexpr int kPfSmem = kPfRingBytes + (kPfUnits + kPfBatch) * (int)sizeof(PfUnit) + 2 * kPfUnits * 8 +
+                        kPfUnits * 4 + 16;
 
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1) roi_align_fwd_persist_kernel(const FwdParams p,
-                                                                                         long long units) {
+                                                                                         int units) {
     extern __shared__ __align__(128) uint8_t pf_smem[];
     uint8_t* ringb = pf_smem;
     PfUnit* desc = reinterpret_cast<PfUnit*>(pf_smem + kPfRingBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(desc + kPfUnits);
+    PfUnit* plan = desc + kPfUnits;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(plan + kPfBatch);
     uint64_t* empty_bar = full_bar + kPfUnits;
-    PfPlan* plan = reinterpret_cast<PfPlan*>(empty_bar + kPfUnits);
+    int* used = reinterpret_cast<int*>(empty_bar + kPfUnits);   // ring bytes (strip + wrap waste) per slot
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int P = p.P, PP = P * P;
+    const int grid = (int)gridDim.x;
     if (threadIdx.x == 0) {
         for (int q = 0; q < kPfUnits; ++q) {
             mbar_init(full_bar + q, 1);
@@ -580,32 +649,35 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
     __syncthreads();
     if (warp == kPfGroups * P) {
         // ===== producer =====
-        // The plan entries of a unit sit behind two dependent global reads (level -> box / ranges /
-        // offset): read one unit at a time that is ~2 L2 round trips per unit on the only warp
-        // that starts copies (measured: 4300 clk per unit, consumers idle on the full barrier 77 %
-        // of the time).  So the lanes fetch the plans of kPfBatch units at once - one unit per
-        // lane, the same two round trips per BATCH - into shared memory, and the issue loop below
-        // only reads shared memory.
+        // It is the only warp that starts copies, so everything it does per unit is serial time of
+        // the whole CTA (ncu: the consumers sat on the full barrier 58 - 77 % of the time).  (1) The
+        // plan entries of a unit sit behind two dependent global reads (level -> box / ranges /
+        // offset): the lanes fetch the plans of kPfBatch units at once - one unit per lane, the
+        // same two round trips per BATCH - and derive every per-unit quantity there, in parallel.
+        // (2) The issue loop then only allocates ring space, moves the 128-byte record into the
+        // descriptor ring (one int per lane) and starts the copies; indices are 32-bit.
         int head = 0, free_bytes = kPfRingBytes;
-        long long oldest = 0;                        // local index of the oldest unreleased unit
-        int used[kPfUnits];                          // ring bytes (strip + wrap waste) per slot
-#pragma unroll
-        for (int q = 0; q < kPfUnits; ++q) used[q] = 0;
-        long long i = 0;
-        for (long long u0 = blockIdx.x; u0 < units; u0 += (long long)kPfBatch * gridDim.x) {
+        int oldest = 0;                              // local index of the oldest unreleased unit
+        int i = 0;
+        for (int u0 = (int)blockIdx.x; u0 < units; u0 += kPfBatch * grid) {
             {
-                const long long u = u0 + (long long)lane * gridDim.x;
-                PfPlan pl;
-                pl.gsrc = nullptr; pl.wy_src = nullptr; pl.wx_src = nullptr;
-                pl.live = 0; pl.b = -1; pl.ny = 0; pl.nxs = 0; pl.W = 1;
+                const long long u = (long long)u0 + (long long)lane * grid;
+                PfUnit pl;
+                pl.gsrc = nullptr; pl.wy_src = nullptr; pl.wx_src = nullptr; pl.out_off = 0;
+                pl.live = 0; pl.direct = 0; pl.b = -1; pl.ny = 0; pl.nxs = 0; pl.W = 1; pl.need = 0;
+                pl.ph = 0; pl.buf_off = 0;
 #pragma unroll
-                for (int j = 0; j < HTD_MAX_POOLED; ++j) { pl.dx0[j] = 0; pl.nx[j] = 0; }
+                for (int j = 0; j < HTD_MAX_POOLED; ++j) pl.dx0[j] = 0;
+#pragma unroll
+                for (int j = 0; j < HTD_MAX_POOLED - 1; ++j) pl.nx[j] = 0;
                 if (u < units) {
-                    const int ph = (int)(u % P);
-                    const int k = (int)(u / P);
+                    const int k = (int)u / P;
+                    const int ph = (int)u - k * P;
                     const int l = p.roi_level[k];
                     const int b = (int)p.rois[(size_t)k * 5];
                     pl.b = b;
+                    pl.ph = ph;
+                    pl.out_off = ((long long)k * PP + (long long)ph * P) * p.C;
                     if ((b >= 0 && b < p.B) && (l >= 0 && l < p.L)) {
                         const size_t e = (size_t)l * p.K + k;
                         const int4 box = p.boxes[e];
@@ -620,10 +692,14 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
                             const int cx0[8] = {lo0.x, lo0.y, lo0.z, lo0.w, lo1.x, lo1.y, lo1.z, lo1.w};
                             const int cx1[8] = {hi0.x, hi0.y, hi0.z, hi0.w, hi1.x, hi1.y, hi1.z, hi1.w};
 #pragma unroll
-                            for (int j = 0; j < HTD_MAX_POOLED; ++j) {
-                                pl.dx0[j] = cx0[j] - box.z;
+                            for (int j = 0; j < HTD_MAX_POOLED; ++j) pl.dx0[j] = cx0[j] - box.z;
+#pragma unroll
+                            for (int j = 0; j < HTD_MAX_POOLED - 1; ++j)
                                 pl.nx[j] = j < P ? cx1[j] - cx0[j] + 1 : 0;
-                            }
+                            const long long strip = (long long)ny * nxs * p.C * (long long)sizeof(TIn);
+                            const int tab_bytes = (ny + nxs) * kTabW * 4;
+                            pl.direct = strip + tab_bytes > kPfRingBytes;
+                            pl.need = (pl.direct ? 0 : (int)strip) + tab_bytes;      // multiple of 16
                             pl.live = 1; pl.ny = ny; pl.nxs = nxs; pl.W = W;
                             pl.gsrc = static_cast<const TIn*>(p.lv[l].data) +
                                       (((size_t)b * H + ry0) * W + box.z) * p.C;
@@ -635,21 +711,11 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
                 plan[lane] = pl;
             }
             __syncwarp();
-            for (int j = 0; j < kPfBatch; ++j, ++i) {
-                const long long u = u0 + (long long)j * gridDim.x;
-                if (u >= units) break;
-                const PfPlan* pl = plan + j;
-                const int q = (int)(i % kPfUnits);
-                const int ph = (int)(u % P);
-                const long long task = u / P;
-                const bool live = pl->live != 0;
-                const int ny = pl->ny, nxs = pl->nxs;
-                const int row_bytes = nxs * p.C * (int)sizeof(TIn);
-                const int tab_bytes = live ? (ny + nxs) * kTabW * 4 : 0;
-                long long strip = live ? (long long)ny * row_bytes : 0;
-                const bool direct = strip + tab_bytes > kPfRingBytes;
-                if (direct) strip = 0;
-                const int need = (int)strip + tab_bytes;         // multiple of 16
+            const int nb = min(kPfBatch, (units - u0 + grid - 1) / grid);
+            for (int j = 0; j < nb; ++j, ++i) {
+                const PfUnit* pl = plan + j;
+                const int q = i % kPfUnits;
+                const int need = pl->need;
                 // ---- ring space: units are released in order
                 int waste = 0;
                 bool wrap = false;
@@ -661,7 +727,7 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
                         head = 0;
                         continue;
                     }
-                    const int oq = (int)(oldest % kPfUnits);
+                    const int oq = oldest % kPfUnits;
                     mbar_wait(empty_bar + oq, (uint32_t)(oldest / kPfUnits) & 1u);
                     free_bytes += used[oq];
                     ++oldest;
@@ -670,35 +736,26 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
                 const int buf = head;
                 head += need;
                 free_bytes -= need + waste;
-                used[q] = need + waste;
-                // ---- descriptor
-                PfUnit* d = desc + q;
-                if (lane < HTD_MAX_POOLED) {
-                    d->dx0[lane] = pl->dx0[lane];
-                    d->nx[lane] = pl->nx[lane];
-                }
-                if (lane == 0) {
-                    d->valid = live;
-                    d->direct = direct;
-                    d->buf_off = buf;
-                    d->ny = ny; d->nxs = nxs; d->b = pl->b; d->W = pl->W;
-                    d->wy_off = buf + (int)strip;
-                    d->wx_off = buf + (int)strip + ny * kTabW * 4;
-                    d->out_off = ((long long)task * PP + (long long)ph * P) * p.C;
-                    d->gsrc = pl->gsrc;
-                }
+                // ---- descriptor: one int per lane, the last one is the ring offset
+                reinterpret_cast<int*>(desc + q)[lane] =
+                    lane == 31 ? buf : reinterpret_cast<const int*>(pl)[lane];
+                if (lane == 0) used[q] = need + waste;
+                const int live = pl->live, ny = pl->ny, nxs = pl->nxs;
                 __syncwarp();
                 if (!live) {
                     if (lane == 0) mbar_arrive(full_bar + q);
                     continue;
                 }
-                if (lane == 0) {
-                    mbar_expect_tx(full_bar + q, (uint32_t)need);
-                    bulk_g2s(ringb + d->wy_off, pl->wy_src, (uint32_t)(ny * kTabW * 4), full_bar + q);
-                    bulk_g2s(ringb + d->wx_off, pl->wx_src, (uint32_t)(nxs * kTabW * 4), full_bar + q);
-                }
+                if (lane == 0) mbar_expect_tx(full_bar + q, (uint32_t)need);
                 __syncwarp();
-                if (!direct) {
+                const int row_bytes = nxs * p.C * (int)sizeof(TIn);
+                const int strip = pl->direct ? 0 : ny * row_bytes;
+                if (lane == 31)
+                    bulk_g2s(ringb + buf + strip, pl->wy_src, (uint32_t)(ny * kTabW * 4), full_bar + q);
+                else if (lane == 30)
+                    bulk_g2s(ringb + buf + strip + ny * kTabW * 4, pl->wx_src,
+                             (uint32_t)(nxs * kTabW * 4), full_bar + q);
+                if (strip) {
                     const TIn* src = static_cast<const TIn*>(pl->gsrc);
                     const size_t gstride = (size_t)pl->W * p.C;
                     for (int r = lane; r < ny; r += 32)
@@ -712,10 +769,9 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
         // ===== consumers: group g reduces the units i = g, g + G, ...; a warp = one bin (ph, pw) =====
         const int pw = warp % P, grp = warp / P;
         const bool lane_on = lane * 8 < p.C;
-        long long i = grp;
-        for (long long u = blockIdx.x + (long long)grp * gridDim.x; u < units;
-             u += (long long)kPfGroups * gridDim.x, i += kPfGroups) {
-            const int q = (int)(i % kPfUnits);
+        int i = grp;
+        for (int u = (int)blockIdx.x + grp * grid; u < units; u += kPfGroups * grid, i += kPfGroups) {
+            const int q = i % kPfUnits;
             mbar_wait(full_bar + q, (uint32_t)(i / kPfUnits) & 1u);
             const PfUnit* d = desc + q;
             float acc[8];
@@ -729,10 +785,11 @@ __global__ void __launch_bounds__((kPfGroups * (HTD_MAX_POOLED - 1) + 1) * 32, 1
 #pragma unroll
                 for (int e = 0; e < 8; ++e) bv[e] = __ldg(p.bias + (size_t)b * p.C + lane * 8 + e);
             }
-            if (d->valid) {
+            if (d->live) {
                 const int ny = d->ny, nxs = d->nxs, nx = d->nx[pw], dx0 = d->dx0[pw];
-                const float* ty = reinterpret_cast<const float*>(ringb + d->wy_off) + (int)(u % P);
-                const float* tx = reinterpret_cast<const float*>(ringb + d->wx_off) + (size_t)dx0 * kTabW + pw;
+                const int strip = d->direct ? 0 : ny * nxs * p.C * (int)sizeof(TIn);
+                const float* ty = reinterpret_cast<const float*>(ringb + d->buf_off + strip) + d->ph;
+                const float* tx = ty - d->ph + (size_t)(ny + dx0) * kTabW + pw;
                 if (nx > 0 && lane_on) {
                     if (!d->direct) {
                         const TIn* sb = reinterpret_cast<const TIn*>(ringb + d->buf_off) + (size_t)dx0 * p.C + lane * 8;
@@ -1545,6 +1602,388 @@ __global__ void __launch_bounds__((4 * kCG + 1) * 32, kMinCtas) roi_align_bwd_mm
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// tensor-pipe forward (level-assigned extraction, bf16 features)
+// ------------------------------------------------------------------------------------------
+// The scalar kernels above spend ~19 instructions per (pixel, 8 channels) visit and are bound by
+// instruction issue and by the dependent shared-load -> fma chains of few warps (ncu, persistent
+// kernel: consumers wait for data 54 % of the time although the copy warp is idle 2/3 of it,
+// because every strip stays in the ring for the ~3000 clk its reduction takes).  Here the x
+// reduction of a footprint row is a small matrix product on the tensor pipe,
+//     T[c, pw] = sum_px F[y, px, c] * wx[px, pw]        (M = 16 channels, N = 8 bins, K = 16 px)
+// and the y reduction out[ph][pw][c] += wy[y][ph] * T[c, pw] stays on the accumulator fragments.
+//   * task = up to kMfSeg consecutive bin rows of one RoI (two tasks per RoI at pooled 7: the
+//     RoI-wide work - descriptor, x-table, B fragments - is paid twice per RoI instead of once per
+//     bin row, and 2 K tasks still balance over 2 x 148 groups); tasks alternate between kMfGroups
+//     groups of 4 consumer + 4 producer warps; inside a group warp pair cc owns channels
+//     [64 cc, 64 cc + 64) and streams them through its OWN ring of 4 KB tiles - no cross-pair barrier.
+//   * a tile = 32 pixels of one footprint row x 64 channels, fetched by ONE cp.async.bulk.tensor
+//     (UTMALDG; 4-D map (C, W, H, B) of the level, box 64 x 32 x 1 x 1, 128-byte swizzle, zero
+//     fill right of the image) - the swizzle makes the transposing ldmatrix of the A fragments
+//     bank-conflict free, which plain row copies (pixels 512 B apart) cannot be.
+//   * producer 0 of a group fetches the plans of 32 tasks at once (one per lane), publishes each as a
+//     128-byte descriptor a few tasks AHEAD of the tiles and bulk-copies the task's slices of the
+//     axis-weight tables behind it.
+//   * weights enter the MMA as bf16 (2^-9 relative, inside the 2e-2 bf16 gate, like the backward
+//     gather); with fp32 OUTPUT they enter as bf16 hi + lo pairs (two MMAs, ~2^-17 relative).
+//   * footprints wider than 64 px or tasks spanning more than 64 rows (never a level-assigned RoI
+//     of an 800x1333 image) are reduced straight from global memory by the consumer warps.
+constexpr int kMfGroups = 2;
+constexpr int kMfTiles = 5;                      // 4 KB tiles in flight per (group, channel chunk)
+constexpr int kMfDesc = 4;                       // task descriptors in flight per group
+constexpr int kMfAhead = 2;                      // descriptors published ahead of the tile issue
+constexpr int kMfSeg = 2;                        // bin rows per task
+constexpr int kMfMaxRows = 64, kMfMaxPx = 64;
+constexpr int kMfTileBytes = 32 * 128;
+struct MfUnit {                                  // 32 ints: moved by the producer's lanes, one int each
+    const void* gsrc;                            // pixel (row y0, column x0) of the footprint (fallback path)
+    const float* wy_src;                         // the task's rows / the RoI's columns in the tables
+    const float* wx_src;
+    long long out_off;                           // output element offset of bin (ph0, 0)
+    int live, fallback, b, l, nrows, nxs, nchunk, ph0, nph, x0, y0, W;
+    short yoff[kMfSeg], nyb[kMfSeg];             // per bin row: first footprint row (from y0), rows
+    short dx0[HTD_MAX_POOLED - 1], nx[HTD_MAX_POOLED - 1];    // per bin column (fallback path)
+    int wcls;                                    // box width class of chunk 0 (bits 0-1) and 1 (bits 2-3)
+    int pad[2];
+};
+static_assert(sizeof(MfUnit) == 128, "MfUnit is moved as 32 ints");
+struct MfSlot {
+    MfUnit u;
+    float wy[kMfMaxRows][kTabW];
+    float wx[kMfMaxPx][kTabW];
+};
+// box width classes of a tile: 16 / 24 / 32 pixels (footprints of level-assigned RoIs are 15 - 30
+// px wide: always fetching 32 doubled the L2 -> SM traffic, which is what bounds this kernel)
+constexpr int kMfWidths = 3;
+struct FwdMaps {
+    CUtensorMap m[HTD_MAX_LEVELS * kMfWidths];
+};
+constexpr int kMfSmem = kMfGroups * 4 * kMfTiles * kMfTileBytes + kMfGroups * kMfDesc * (int)sizeof(MfSlot) +
+                        kMfGroups * 32 * (int)sizeof(MfUnit) +
+                        (kMfGroups * 4 * kMfTiles * 2 + kMfGroups * kMfDesc * 2) * 8 + 1024;
+static_assert(kMfSmem <= 232448, "shared memory per CTA");
+
+template <typename TOut>
+__global__ void __launch_bounds__(kMfGroups * 8 * 32, 1)
+    roi_align_fwd_mma_kernel(const __grid_constant__ FwdMaps maps, const FwdParams p, int tasks) {
+    constexpr bool kLo = sizeof(TOut) == 4;              // fp32 output: weights as bf16 hi + lo
+    extern __shared__ uint8_t mf_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(mf_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp >> 3, role = warp & 7;
+    const int cc = role & 3;                             // channel chunk of the warp's pair
+    const bool producer = role >= 4;
+    const int nact = p.C >> 6;                           // active pairs per group (C % 64 == 0)
+    uint8_t* tiles = smem + (size_t)((grp * 4 + cc) * kMfTiles) * kMfTileBytes;
+    MfSlot* slots = reinterpret_cast<MfSlot*>(smem + kMfGroups * 4 * kMfTiles * kMfTileBytes) + grp * kMfDesc;
+    MfUnit* plan = reinterpret_cast<MfUnit*>(smem + kMfGroups * 4 * kMfTiles * kMfTileBytes +
+                                             kMfGroups * kMfDesc * sizeof(MfSlot)) + grp * 32;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kMfGroups * 4 * kMfTiles * kMfTileBytes +
+                                                 kMfGroups * kMfDesc * sizeof(MfSlot) +
+                                                 kMfGroups * 32 * sizeof(MfUnit));
+    uint64_t* full_bar = bars + (size_t)((grp * 4 + cc) * 2) * kMfTiles;
+    uint64_t* empty_bar = full_bar + kMfTiles;
+    uint64_t* dfull = bars + kMfGroups * 4 * kMfTiles * 2 + grp * 2 * kMfDesc;
+    uint64_t* dempty = dfull + kMfDesc;
+    const int P = p.P, PP = P * P;
+    const int nseg = (P + kMfSeg - 1) / kMfSeg;          // tasks per RoI
+    const int grid = (int)gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kMfGroups * 4 * kMfTiles * 2; ++i) mbar_init(bars + i, 1);
+        for (int g = 0; g < kMfGroups; ++g)
+            for (int q = 0; q < kMfDesc; ++q) {
+                mbar_init(bars + kMfGroups * 4 * kMfTiles * 2 + g * 2 * kMfDesc + q, 1);
+                mbar_init(bars + kMfGroups * 4 * kMfTiles * 2 + g * 2 * kMfDesc + kMfDesc + q,
+                          2 * nact - 1);                 // consumers + the producers that only read
+            }
+        fence_mbar_init();
+    }
+    {   // narrow boxes leave the tail of a tile untouched: no stale NaN patterns under zero weights
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = threadIdx.x; i < kMfGroups * 4 * kMfTiles * kMfTileBytes / 16; i += blockDim.x)
+            z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+    if (cc >= nact) return;
+    // tasks of this CTA: i = 0, 1, ... -> task blockIdx.x + i * grid; group g takes i = g (mod groups)
+    const int total_i = (int)blockIdx.x < tasks ? (tasks - (int)blockIdx.x + grid - 1) / grid : 0;
+    const int n_g = total_i > grp ? (total_i - grp + kMfGroups - 1) / kMfGroups : 0;
+    int t = 0;                                           // tiles of the pair so far
+
+    if (producer) {
+        int pub = 0;                                     // descriptors published so far (producer 0)
+        for (int i0 = 0; i0 < n_g; i0 += 32 - kMfAhead) {
+            // producer 0 keeps a window of 32 staged plans starting at i0; the window moves by
+            // 32 - kMfAhead so that the tasks published ahead are still staged
+            if (cc == 0) {
+                const int ii = i0 + lane;
+                MfUnit pl;
+                pl.gsrc = nullptr; pl.wy_src = nullptr; pl.wx_src = nullptr; pl.out_off = 0;
+                pl.live = 0; pl.fallback = 0; pl.b = -1; pl.l = 0; pl.nrows = 0; pl.nxs = 0; pl.nchunk = 0;
+                pl.ph0 = 0; pl.nph = 0; pl.x0 = 0; pl.y0 = 0; pl.W = 1; pl.wcls = 0; pl.pad[0] = pl.pad[1] = 0;
+#pragma unroll
+                for (int j = 0; j < kMfSeg; ++j) { pl.yoff[j] = 0; pl.nyb[j] = 0; }
+#pragma unroll
+                for (int j = 0; j < HTD_MAX_POOLED - 1; ++j) { pl.dx0[j] = 0; pl.nx[j] = 0; }
+                if (ii < n_g) {
+                    const int tk = (int)blockIdx.x + (ii * kMfGroups + grp) * grid;
+                    const int k = tk / nseg;
+                    const int ph0 = (tk - k * nseg) * kMfSeg;
+                    const int nph = min(kMfSeg, P - ph0);
+                    const int l = p.roi_level[k];
+                    const int b = (int)p.rois[(size_t)k * 5];
+                    pl.b = b;
+                    pl.ph0 = ph0;
+                    pl.nph = nph;
+                    pl.out_off = ((long long)k * PP + (long long)ph0 * P) * p.C;
+                    if ((b >= 0 && b < p.B) && (l >= 0 && l < p.L)) {
+                        const size_t e = (size_t)l * p.K + k;
+                        const int4 box = p.boxes[e];
+                        const int4* rq = reinterpret_cast<const int4*>(p.ranges + e * kRangeInts);
+                        const int4 ya = rq[0], yb = rq[1], yc = rq[2], yd = rq[3];
+                        const int4 lo0 = rq[4], lo1 = rq[5], hi0 = rq[6], hi1 = rq[7];
+                        const size_t off = (size_t)p.offsets[e];
+                        const int ylo[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+                        const int yhi[8] = {yc.x, yc.y, yc.z, yc.w, yd.x, yd.y, yd.z, yd.w};
+                        // rows of the task: from the first non-empty bin row's first row on
+                        int y0 = 0x7fffffff, y1 = -1;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j >= ph0 && j < ph0 + nph && yhi[j] >= ylo[j]) {
+                                y0 = min(y0, ylo[j]);
+                                y1 = max(y1, yhi[j]);
+                            }
+                        const int nxs = box.w - box.z + 1;
+                        if (box.y >= box.x && box.w >= box.z && y1 >= y0 && nxs > 0) {
+                            const int H = p.lv[l].H, W = p.lv[l].W;
+                            const int cx0[8] = {lo0.x, lo0.y, lo0.z, lo0.w, lo1.x, lo1.y, lo1.z, lo1.w};
+                            const int cx1[8] = {hi0.x, hi0.y, hi0.z, hi0.w, hi1.x, hi1.y, hi1.z, hi1.w};
+#pragma unroll
+                            for (int j = 0; j < HTD_MAX_POOLED - 1; ++j) {
+                                pl.dx0[j] = (short)(cx0[j] - box.z);
+                                pl.nx[j] = (short)(j < P ? cx1[j] - cx0[j] + 1 : 0);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j >= ph0 && j < ph0 + nph && yhi[j] >= ylo[j]) {
+                                    pl.yoff[j - ph0] = (short)(ylo[j] - y0);
+                                    pl.nyb[j - ph0] = (short)(yhi[j] - ylo[j] + 1);
+                                }
+                            pl.live = 1; pl.l = l; pl.nrows = y1 - y0 + 1; pl.nxs = nxs; pl.W = W;
+                            pl.fallback = (nxs > kMfMaxPx || pl.nrows > kMfMaxRows) ? 1 : 0;
+                            pl.nchunk = (nxs + 31) >> 5;
+                            {
+                                const int w0 = min(nxs, 32), w1 = nxs - 32;     // pixels of chunk 0 / 1
+                                const int c0 = w0 <= 16 ? 0 : w0 <= 24 ? 1 : 2;
+                                const int c1 = w1 <= 16 ? 0 : w1 <= 24 ? 1 : 2;
+                                pl.wcls = c0 | (c1 << 2);
+                            }
+                            pl.x0 = box.z; pl.y0 = y0;
+                            pl.gsrc = static_cast<const __nv_bfloat16*>(p.lv[l].data) +
+                                      (((size_t)b * H + y0) * W + box.z) * p.C;
+                            pl.wy_src = p.weights + (off + (size_t)(y0 - box.x)) * kTabW;
+                            pl.wx_src = p.weights + (off + (size_t)(box.y - box.x + 1)) * kTabW;
+                        }
+                    }
+                }
+                __syncwarp();
+                plan[lane] = pl;
+                __syncwarp();
+            }
+            const int nb = min(32 - kMfAhead, n_g - i0);
+            for (int j = 0; j < nb; ++j) {
+                const int ii = i0 + j;
+                const int q = ii % kMfDesc;
+                MfSlot* sl = slots + q;
+                const MfUnit* d;
+                if (cc == 0) {
+                    // publish the descriptors (and table slices) of the tasks up to ii + kMfAhead
+                    const int upto = min(min(ii + kMfAhead, n_g - 1), i0 + 31);
+                    for (; pub <= upto; ++pub) {
+                        const int pq = pub % kMfDesc;
+                        MfSlot* ps = slots + pq;
+                        const MfUnit* pd = plan + (pub - i0);
+                        mbar_wait(dempty + pq, (uint32_t)((pub / kMfDesc) & 1) ^ 1u);
+                        reinterpret_cast<int*>(&ps->u)[lane] = reinterpret_cast<const int*>(pd)[lane];
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (pd->live && !pd->fallback) {
+                                mbar_expect_tx(dfull + pq, (uint32_t)((pd->nrows + pd->nxs) * kTabW * 4));
+                                bulk_g2s(&ps->wy[0][0], pd->wy_src, (uint32_t)(pd->nrows * kTabW * 4), dfull + pq);
+                                bulk_g2s(&ps->wx[0][0], pd->wx_src, (uint32_t)(pd->nxs * kTabW * 4), dfull + pq);
+                            } else {
+                                mbar_arrive(dfull + pq);
+                            }
+                        }
+                    }
+                    d = plan + j;
+                } else {
+                    d = &sl->u;
+                    mbar_wait(dfull + q, (uint32_t)((ii / kMfDesc) & 1));
+                }
+                if (d->live && !d->fallback) {
+                    const int nph = d->nph, nchunk = d->nchunk, x0 = d->x0, y0 = d->y0, b = d->b;
+                    const int wcls = d->wcls;
+                    for (int pi = 0; pi < nph; ++pi) {
+                        const int ya = y0 + d->yoff[pi], ny = d->nyb[pi];
+                        for (int r = 0; r < ny; ++r)
+                            for (int xc = 0; xc < nchunk; ++xc, ++t) {
+                                const int s = t % kMfTiles;
+                                mbar_wait(empty_bar + s, (uint32_t)((t / kMfTiles) & 1) ^ 1u);
+                                if (lane == 0) {
+                                    const int wc = (wcls >> (2 * xc)) & 3;
+                                    mbar_expect_tx(full_bar + s, (uint32_t)((16 + 8 * wc) * 128));
+                                    tc::tma_load_4d(&maps.m[d->l * kMfWidths + wc], full_bar + s,
+                                                    tiles + s * kMfTileBytes, cc * 64, x0 + xc * 32, ya + r, b);
+                                }
+                            }
+                    }
+                }
+                if (cc != 0) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dempty + q);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int g8 = lane >> 2, tq = lane & 3;             // mma fragment coordinates
+    // ldmatrix lane address inside a tile: matrix m = lane >> 3 -> channel half (m & 1) of the
+    // 16-channel block, pixel half (m >> 1); row i = lane & 7 is the pixel -> swizzle phase i
+    const int lm = lane >> 3, li = lane & 7;
+    const uint32_t ld_row = (uint32_t)(((lm >> 1) * 8 + li) * 128);
+    uint32_t ld_unit[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) ld_unit[mt] = (uint32_t)(((2 * mt + (lm & 1)) ^ li) << 4);
+    const uint32_t tiles_u32 = smem_u32(tiles);
+    for (int ii = 0; ii < n_g; ++ii) {
+        const int q = ii % kMfDesc;
+        const MfSlot* sl = slots + q;
+        mbar_wait(dfull + q, (uint32_t)((ii / kMfDesc) & 1));
+        const MfUnit* d = &sl->u;
+        const int b = d->b, ph0 = d->ph0, nph = d->nph;
+        const bool bias_on = p.bias && b >= 0 && b < p.B;
+        TOut* obase = static_cast<TOut*>(p.out) + d->out_off + cc * 64;
+        if (d->live && d->fallback) {
+            // scalar reduction straight from global memory: a lane = 2 channels of the chunk
+            const __nv_bfloat16* gb = static_cast<const __nv_bfloat16*>(d->gsrc) + cc * 64 + lane * 2;
+            const int W = d->W;
+            for (int pi = 0; pi < nph; ++pi) {
+                const int ph = ph0 + pi, ny = d->nyb[pi], yo = d->yoff[pi];
+                for (int pw = 0; pw < P; ++pw) {
+                    float a0 = 0.f, a1 = 0.f;
+                    const int nx = d->nx[pw], dx0 = d->dx0[pw];
+                    for (int y = yo; y < yo + ny; ++y) {
+                        const float wyv = __ldg(d->wy_src + (size_t)y * kTabW + ph);
+                        if (wyv == 0.f) continue;
+                        for (int x = 0; x < nx; ++x) {
+                            const float w = wyv * __ldg(d->wx_src + (size_t)(dx0 + x) * kTabW + pw);
+                            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(
+                                gb + ((size_t)y * W + dx0 + x) * p.C));
+                            a0 = fmaf(w, __uint_as_float(v << 16), a0);
+                            a1 = fmaf(w, __uint_as_float(v & 0xffff0000u), a1);
+                        }
+                    }
+                    if (bias_on) {
+                        a0 += __ldg(p.bias + (size_t)b * p.C + cc * 64 + lane * 2);
+                        a1 += __ldg(p.bias + (size_t)b * p.C + cc * 64 + lane * 2 + 1);
+                    }
+                    st_elem(obase + (size_t)(pi * P + pw) * p.C + lane * 2, a0);
+                    st_elem(obase + (size_t)(pi * P + pw) * p.C + lane * 2 + 1, a1);
+                }
+            }
+        } else {
+            float bv[8];                                 // SFA bias of the lane's 8 channels
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                bv[e] = bias_on ? __ldg(p.bias + (size_t)b * p.C + cc * 64 + (e >> 1) * 16 + (e & 1) * 8 + g8)
+                                : 0.f;
+            const int nxs = d->nxs, nchunk = d->live ? d->nchunk : 0;
+            const int wcls = d->wcls;
+            // B fragments = wx[px][bin g8] of the lane's k rows, as bf16 (hi + lo for fp32 output)
+            uint32_t bhi[2][2][2], blo[2][2][2];
+#pragma unroll
+            for (int xc = 0; xc < 2; ++xc)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int px = xc * 32 + ks * 16 + h * 8 + 2 * tq;
+                        float w0 = 0.f, w1 = 0.f;
+                        if (xc < nchunk && g8 < P) {
+                            if (px < nxs) w0 = sl->wx[px][g8];
+                            if (px + 1 < nxs) w1 = sl->wx[px + 1][g8];
+                        }
+                        const uint32_t hi = pack_bf16x2(w0, w1);
+                        bhi[xc][ks][h] = hi;
+                        blo[xc][ks][h] = kLo ? pack_bf16x2(w0 - __uint_as_float(hi << 16),
+                                                            w1 - __uint_as_float(hi & 0xffff0000u))
+                                             : 0u;
+                    }
+            for (int pi = 0; pi < nph; ++pi) {
+                const int ph = ph0 + pi;
+                const int ny = d->live ? d->nyb[pi] : 0, yo = d->yoff[pi];
+                float out[4][4];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) out[mt][e] = 0.f;
+                for (int r = 0; r < ny; ++r) {
+                    float tacc[4][4];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) tacc[mt][e] = 0.f;
+                    const float wyv = sl->wy[yo + r][ph];
+#pragma unroll
+                    for (int xc = 0; xc < 2; ++xc) {
+                        if (xc < nchunk) {
+                            const int s = t % kMfTiles;
+                            mbar_wait(full_bar + s, (uint32_t)((t / kMfTiles) & 1));
+                            const uint32_t tb = tiles_u32 + (uint32_t)(s * kMfTileBytes) + ld_row;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                if (ks == 1 && ((wcls >> (2 * xc)) & 3) == 0) break;   // 16-px box
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt) {
+                                    uint32_t a[4];
+                                    ldmatrix_x4_trans(tb + (uint32_t)(ks * 2048) + ld_unit[mt], a);
+                                    mma_bf16_16816(tacc[mt], a, bhi[xc][ks][0], bhi[xc][ks][1]);
+                                    if (kLo) mma_bf16_16816(tacc[mt], a, blo[xc][ks][0], blo[xc][ks][1]);
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(empty_bar + s);
+                            ++t;
+                        }
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) out[mt][e] = fmaf(wyv, tacc[mt][e], out[mt][e]);
+                }
+                // fragment element e of block mt: channel mt*16 + g8 + 8*(e >> 1), bin 2*tq + (e & 1)
+                TOut* orow = obase + (size_t)pi * P * p.C;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int bin = 2 * tq + (e & 1);
+                        if (bin < P)
+                            st_elem(orow + (size_t)bin * p.C + mt * 16 + (e >> 1) * 8 + g8,
+                                    out[mt][e] + bv[mt * 2 + (e >> 1)]);
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dempty + q);
+    }
+}
+
 static int fill_levels(LevelDev* dst, const HtdLevel* src, int L, const char* who) {
     HTD_CHECK_ARG(src != nullptr && L >= 1 && L <= HTD_MAX_LEVELS, "%s: need 1..%d levels, got %d",
                   who, HTD_MAX_LEVELS, L);
@@ -1644,7 +2083,7 @@ int htd_roi_plan(const HtdLevel* levels, int L, int B, const float* rois, int K,
         q.ext_max = mx;
         q.rois = rois; q.roi_level = roi_level; q.boxes = reinterpret_cast<int4*>(boxes);
         q.offsets = offsets; q.ranges = ranges; q.weights = weights;
-        roi_plan_fused_kernel<<<L * K, 128, 0, (cudaStream_t)stream>>>(q);
+        roi_plan_fused_kernel<<<roi_level ? K : L * K, 128, 0, (cudaStream_t)stream>>>(q);
         HTD_CHECK_LAUNCH("htd_roi_plan(fused)");
         return HTD_OK;
     }
@@ -1708,6 +2147,43 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
         const char* ev = hook_env("HTD_FWD_KERNEL");
         persist_on = (ev && (!strcmp(ev, "cta") || !strcmp(ev, "ring"))) ? 0 : 1;
     }
+    // bf16 features: the tensor-pipe kernel (HTD_FWD_KERNEL=persist keeps the scalar persistent one)
+    static int mma_on = -1;
+    if (mma_on < 0) {
+        const char* ev = hook_env("HTD_FWD_KERNEL");
+        mma_on = (ev && !strcmp(ev, "persist")) ? 0 : 1;
+    }
+    if (persist_on && mma_on && roi_level != nullptr && pooled < HTD_MAX_POOLED && in_dtype == HTD_BF16 &&
+        C % 64 == 0 && C <= 256) {
+        FwdMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        for (int l = 0; l < L; ++l) {
+            const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)levels[l].W, (cuuint64_t)levels[l].H,
+                                        (cuuint64_t)B};
+            const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)levels[l].W * C * 2,
+                                           (cuuint64_t)levels[l].H * levels[l].W * C * 2};
+            for (int wc = 0; wc < kMfWidths; ++wc) {
+                const cuuint32_t box[4] = {64u, (cuuint32_t)(16 + 8 * wc), 1u, 1u};
+                rc = tc::make_map(&maps.m[l * kMfWidths + wc], levels[l].data, 4, dims, strides, box,
+                                  "htd_roi_align_fwd(map)");
+                if (rc) return rc;
+            }
+        }
+        const int sms = sm_count();
+        const long long mtasks = (long long)K * ((pooled + kMfSeg - 1) / kMfSeg);
+        const unsigned mgrid = (unsigned)(mtasks < sms ? mtasks : sms);
+        p.region = 0;
+        p.strip = 1;
+        if (out_dtype == HTD_F32) {
+            HTD_SMEM_OPTIN((roi_align_fwd_mma_kernel<float>), kMfSmem, "htd_roi_align_fwd");
+            roi_align_fwd_mma_kernel<float><<<mgrid, kMfGroups * 8 * 32, kMfSmem, st>>>(maps, p, (int)mtasks);
+        } else {
+            HTD_SMEM_OPTIN((roi_align_fwd_mma_kernel<__nv_bfloat16>), kMfSmem, "htd_roi_align_fwd");
+            roi_align_fwd_mma_kernel<__nv_bfloat16><<<mgrid, kMfGroups * 8 * 32, kMfSmem, st>>>(maps, p, (int)mtasks);
+        }
+        HTD_CHECK_LAUNCH("htd_roi_align_fwd(tensor pipe)");
+        return HTD_OK;
+    }
     if (persist_on && roi_level != nullptr && pooled < HTD_MAX_POOLED && C <= 256) {
         const int sms = sm_count();
         const unsigned pgrid = (unsigned)(blocks < sms ? blocks : sms);
@@ -1716,7 +2192,7 @@ int htd_roi_align_fwd(const HtdLevel* levels, int L, int B, int C, int in_dtype,
 #define HTD_FWDP_LAUNCH(TI, TO)                                                                   \
     do {                                                                                          \
         HTD_SMEM_OPTIN((roi_align_fwd_persist_kernel<TI, TO>), kPfSmem, "htd_roi_align_fwd");     \
-        roi_align_fwd_persist_kernel<TI, TO><<<pgrid, (kPfGroups * pooled + 1) * 32, kPfSmem, st>>>(p, blocks); \
+        roi_align_fwd_persist_kernel<TI, TO><<<pgrid, (kPfGroups * pooled + 1) * 32, kPfSmem, st>>>(p, (int)blocks); \
     } while (0)
         if (in_dtype == HTD_F32 && out_dtype == HTD_F32) HTD_FWDP_LAUNCH(float, float);
         else if (in_dtype == HTD_F32 && out_dtype == HTD_BF16) HTD_FWDP_LAUNCH(float, __nv_bfloat16);

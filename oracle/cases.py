@@ -137,6 +137,30 @@ def run_train(head, train_fn, test_fn, name, dtype, device='cpu'):
     return out
 
 
+def aug_inputs(name, dtype=torch.float32, device='cpu'):
+    """Test-time augmentation case built on case `name` (its first image): three views - plain,
+    horizontally flipped, vertically flipped with another feature content - all at scale factor
+    0.5 of the 'original' image, so that bbox_mapping / bbox_mapping_back do real work."""
+    import numpy as np
+    c, x, props, gts, shapes = case_inputs(name, dtype, device)
+    sf = np.array([0.5, 0.5, 0.5, 0.5], dtype=np.float32)
+    x0 = [t[:1] for t in x]
+    x1 = [torch.flip(t[:1], dims=[3]).contiguous() for t in x]
+    x2 = [(0.5 * torch.flip(t[-1:], dims=[2])).contiguous() for t in x]
+    metas = [[dict(img_shape=shapes[0], scale_factor=sf, flip=False, flip_direction='horizontal')],
+             [dict(img_shape=shapes[0], scale_factor=sf, flip=True, flip_direction='horizontal')],
+             [dict(img_shape=shapes[0], scale_factor=sf, flip=True, flip_direction='vertical')]]
+    proposals = props[0] / props[0].new_tensor(sf)          # 'original image' coordinates
+    return [x0, x1, x2], proposals, metas
+
+
+def run_aug(head, aug_fn, name, dtype, device='cpu'):
+    feats, proposals, metas = aug_inputs(name, dtype, device)
+    with torch.no_grad():
+        out = aug_fn(head, feats, proposals, metas)
+    return {'aug.bboxes': out[0], 'aug.scores': out[1]}
+
+
 # ------------------------------------------------------------------ fixtures
 def summarize(t, nsample=1024):
     t = t.detach().to('cpu')

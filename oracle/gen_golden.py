@@ -146,6 +146,9 @@ def gen_cases(ns, ext, only=None):
             outs.update(cases.run_head(head, name, dt))
             outs.update(cases.run_train(head, ref_driver.ref_forward_train_sampled,
                                         ref_driver.ref_simple_test_scores, name, dt))
+            if name == 'small':                      # test-time augmentation: the reference's aug_test
+                aug = cases.run_aug(head, lambda h, *a: ref_driver.ref_aug_test(h, *a)[:2], name, dt)
+                cases.save_fixture(os.path.join(OUT, f'aug_{name}_{tag}.npz'), aug)
             path = os.path.join(OUT, f'{name}_{tag}.npz')
             cases.save_fixture(path, outs)
             print(name, tag, len(outs), 'tensors ->', path, os.path.getsize(path) // 1024, 'KiB',

@@ -147,3 +147,28 @@ def ref_forward_train_assigned(head, x, proposals, gt_bboxes, gt_labels, keys, c
             if 'random_choice' in sampler.__dict__:
                 del sampler.random_choice
     return losses, dict(samp0=rec[0], samp1=rec[1], refined=refined)
+
+
+def ref_aug_test(head, features, proposals, img_metas):
+    """The reference's own HTDRoIHead.aug_test (htd_roi_head.py:388-440), unmodified; its
+    multiclass_nms call is wrapped only to capture the merged boxes / scores it receives.
+    Returns (merged_bboxes, merged_scores, det_bboxes, det_labels)."""
+    import sys
+    refshim.load()
+    rh = sys.modules['mmdet.models.roi_heads.htd_roi_head']
+    seen = {}
+    real = rh.multiclass_nms
+
+    def capture(bboxes, scores, *a, **k):
+        seen['bboxes'], seen['scores'] = bboxes, scores
+        det = real(bboxes, scores, *a, **k)
+        seen['det'] = det
+        return det
+
+    rh.multiclass_nms = capture
+    try:
+        head.aug_test(features, [proposals], img_metas)
+    finally:
+        rh.multiclass_nms = real
+    return seen['bboxes'], seen['scores'], seen['det'][0], seen['det'][1]
+

@@ -180,7 +180,7 @@ def load():
     if not available():
         raise RuntimeError(f'reference tree not found at {REF}')
     mmcv = _mod('mmcv', path='/nonexistent', __version__='1.2.1')
-    _mod('mmcv.ops', path='/nonexistent', RoIAlign=_RoIAlign)
+    _mod('mmcv.ops', path='/nonexistent', RoIAlign=_RoIAlign, nms=None)
     mmcv.ops = sys.modules['mmcv.ops']
     _mod('mmcv.ops.nms', batched_nms=_batched_nms)
     _mod('mmcv.cnn', path='/nonexistent', ConvModule=_ConvModule, normal_init=_normal_init,
@@ -228,7 +228,10 @@ def load():
     core.build_sampler = bb.build_sampler
     pp = imp('mmdet.core.post_processing.bbox_nms')
     core.multiclass_nms = pp.multiclass_nms
-    core.merge_aug_bboxes = None
+    for k in ['bbox_mapping_back', 'bbox_flip']:
+        setattr(sys.modules['mmdet.core.bbox'], k, getattr(tr, k))
+    ma = imp('mmdet.core.post_processing.merge_augs')
+    core.merge_aug_bboxes = ma.merge_aug_bboxes
     core.merge_aug_masks = None
     sys.modules['mmdet.core.bbox'].demodata = imp('mmdet.core.bbox.demodata')
     ar = imp('mmdet.core.bbox.assigners.assign_result')

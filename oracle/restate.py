@@ -842,3 +842,40 @@ class HTDRoIHead(nn.Module):
                                   img_shapes)])
         r1 = self._bbox_forward(1, x, new_rois, g)
         return new_rois, (r0['cls_score'] + r1['cls_score']) / 2.0, r1['bbox_pred']
+
+    def aug_test_merged(self, features, proposals, img_metas):
+        """htd_roi_head.py:388-433 with core/bbox/transforms.py:5-56 (bbox_flip / bbox_mapping /
+        bbox_mapping_back), bbox_head.py:189-219 (get_bboxes with cfg=None: softmax scores, class
+        boxes decoded and clipped, no rescale) and core/post_processing/merge_augs.py:50-76: the
+        class boxes of every augmented view mapped back to the original image and averaged,
+        scores averaged.  `proposals` is the [n, >=4] tensor of the (one) image, in the original
+        image's coordinates."""
+        def flip(b, shape, direction):
+            out = b.clone()
+            if direction in ('horizontal', 'diagonal'):
+                out[..., 0::4] = shape[1] - b[..., 2::4]
+                out[..., 2::4] = shape[1] - b[..., 0::4]
+            if direction in ('vertical', 'diagonal'):
+                out[..., 1::4] = shape[0] - b[..., 3::4]
+                out[..., 3::4] = shape[0] - b[..., 1::4]
+            return out
+
+        boxes, scores = [], []
+        for x, meta in zip(features, img_metas):
+            m = meta[0]
+            sf = proposals.new_tensor(m['scale_factor'])
+            direction = m.get('flip_direction', 'horizontal')
+            pr = proposals[:, :4] * sf
+            if m['flip']:
+                pr = flip(pr, m['img_shape'], direction)
+            rois, cls_score, bbox_pred = self.simple_test_scores(x, [pr], [m['img_shape']])
+            sc = torch.softmax(cls_score, dim=1)
+            head = self.bbox_head[-1]
+            bx = delta2bbox(rois[:, 1:], bbox_pred, head.target_means, head.target_stds,
+                            max_shape=m['img_shape'])
+            if m['flip']:
+                bx = flip(bx, m['img_shape'], direction)
+            boxes.append((bx.view(-1, 4) / sf).view(bx.shape))
+            scores.append(sc)
+        return torch.stack(boxes).mean(dim=0), torch.stack(scores).mean(dim=0)
+

@@ -308,3 +308,49 @@ def test_fused_group_norm_relu(dtype, tol, C, G, HW):
         else:
             num = (a.double().cpu() - want).norm() / want.norm()
             assert float(num) <= 3e-2, (name, float(num))
+
+
+@pytest.mark.parametrize('C,hw,out_dtype', [(256, (200, 336), torch.bfloat16),
+                                            (256, (200, 336), torch.float32),
+                                            (128, (96, 160), torch.float32),
+                                            (64, (640, 704), torch.float32)])
+def test_single_level_tensor_pipe_forward(C, hw, out_dtype):
+    """Level-assigned extraction of bf16 features (roi_align_fwd_mma_kernel: TMA tensor tiles +
+    tensor-pipe x reduction) against the fp64 oracle RoIAlign on the SAME bf16-rounded features:
+    fp32 output <= 2e-5 (weights enter as bf16 hi + lo pairs), bf16 output <= 2e-2.  Covers 1 / 2
+    / 4 channel chunks, the SFA bias, RoIs outside / degenerate / on the border, and footprints
+    wider than 64 px (hw[1] / 32 > 64 on the coarsest level: reduced from global memory)."""
+    from htd_b200 import ops
+    from oracle import restate
+    H, W = hw
+    B, strides = 2, [4, 8, 16, 32]
+    g = torch.Generator().manual_seed(C + H)
+    feats = [torch.randn(B, C, -(-H // (s // 4)), -(-W // (s // 4)), generator=g).bfloat16() for s in strides]
+    props = synth.make_proposals(B, 150, H * 4, W * 4, seed=7, min_scale=6.0, max_scale=3.0 * W)
+    rois = torch.cat([torch.cat([p.new_full((p.size(0), 1), i), p], 1) for i, p in enumerate(props)])
+    rois = torch.cat([rois, _edge_rois(H, W, 4), torch.tensor([[0, 0.0, 0.0, 4.0 * W, 4.0 * H],
+                                                               [1, 3.0, 2.0, 4.0 * W - 5, 40.0]])])
+    bias = torch.randn(B, C, generator=g)
+    # oracle: per-level RoIAlign of the assigned level, fp64, on the bf16 values
+    lv_cpu = restate.map_roi_levels(rois, 4) if hasattr(restate, 'map_roi_levels') else None
+    x_cl = [ops.to_channels_last(f.cuda(), torch.bfloat16) for f in feats]
+    r = rois.cuda()
+    lv = ops.level_assign(r, 4)
+    if lv_cpu is not None:
+        assert torch.equal(lv.cpu().long(), lv_cpu.long())
+    want = torch.zeros(rois.size(0), C, 7, 7, dtype=torch.float64)
+    for l, s in enumerate(strides):
+        idx = (lv.cpu() == l).nonzero().squeeze(1)
+        if idx.numel():
+            want[idx] = restate.RoIAlign(7, 1.0 / s, 0)(feats[l].double(), rois[idx].double())
+    want = want + bias.double()[rois[:, 0].long()][:, :, None, None]
+    out = torch.empty(rois.size(0), 7, 7, C, device='cuda', dtype=out_dtype)
+    ops._fwd_launch('f', x_cl, [1.0 / s for s in strides], r, lv, 7, 0, bias.cuda().contiguous(), out)
+    got = out.permute(0, 3, 1, 2).double().cpu()
+    den = want.abs().max().item()
+    err = (got - want).abs().max().item() / den
+    assert err <= (2e-5 if out_dtype == torch.float32 else TOL_BF16), err
+    if W // 8 > 64:
+        bx = ops.RoIPlan(x_cl, [1.0 / s for s in strides], r, lv, 7, 0).boxes
+        widths = (bx[..., 3] - bx[..., 2] + 1).max().item()
+        assert widths > 64, widths                     # the wide-footprint path was taken

@@ -662,3 +662,33 @@ def test_graph_step_early_gradient_event_orders_a_side_stream():
     views = {id(p): v for p, v in step._views}
     for k, p in head.named_parameters():
         assert torch.equal(views[id(p)], got[k]), k
+
+
+def test_aug_test_against_the_oracle_and_the_reference_fixture():
+    """HTDRoIHead.aug_test (htd_roi_head.py:388-440): merged class boxes / scores of three
+    augmented views (plain, h-flip, v-flip; scale factor 0.5) in fp32 against the fp64 oracle and
+    the fixture written by the reference's own aug_test; then the real test_cfg NMS on them."""
+    from htd_b200.core import multiclass_nms
+    from oracle import cases, restate
+    c = cases.CASES['small']
+    ohead = restate.HTDRoIHead().double()
+    synth.fill_params_(ohead, c['scheme'], c['seed'])
+    want = cases.run_aug(ohead, lambda h, *a: h.aug_test_merged(*a), 'small', torch.float64)
+    head = _product_head("small", torch.float32)
+    got = cases.run_aug(head, lambda h, *a: h.aug_test_merged(*a), 'small', torch.float32, 'cuda')
+    for k in want:
+        e = cases.rel_err(got[k], want[k])
+        assert e <= 1e-5, (k, e)
+    fix = cases.load_fixture(os.path.join(GOLD, 'aug_small_f64.npz'))
+    cases.compare_to_fixture(got, fix, 1e-5)
+    feats, proposals, metas = cases.aug_inputs('small', torch.float32, 'cuda')
+    with torch.no_grad():
+        res = head.aug_test(feats, [proposals], metas)
+    assert len(res) == head.bbox_head[-1].num_classes and all(r.shape[1] == 5 for r in res)
+    cfg = head.test_cfg
+    det, lab = multiclass_nms(got['aug.bboxes'], got['aug.scores'], cfg['score_thr'], cfg['nms'],
+                              cfg['max_per_img'])
+    assert sum(len(r) for r in res) == det.shape[0]
+    for cls in range(len(res)):
+        assert np.array_equal(res[cls], det[lab == cls].float().cpu().numpy())
+

@@ -142,6 +142,55 @@ def test_restatement_equals_reference_live():
         assert cases.rel_err(b[k], a[k]) <= 1e-6, k
 
 
+# ---- test-time augmentation (htd_roi_head.py:388-440) ---------------------------------------------
+@pytest.mark.parametrize('tag,dt,tol', [('f64', torch.float64, 1e-10), ('f32', torch.float32, 2e-5)])
+def test_aug_test_restatement_matches_reference_golden(tag, dt, tol):
+    """tests/golden/aug_small_*.npz hold the merged boxes / scores the reference's OWN aug_test
+    hands to multiclass_nms (three views: plain, h-flip, v-flip, scale factor 0.5)."""
+    c = cases.CASES['small']
+    head = restate.HTDRoIHead().to(dt)
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    outs = cases.run_aug(head, lambda h, *a: h.aug_test_merged(*a), 'small', dt)
+    fix = cases.load_fixture(os.path.join(GOLD, f'aug_small_{tag}.npz'))
+    assert set(outs) == set(fix)
+    cases.compare_to_fixture(outs, fix, tol)
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference not present')
+def test_aug_test_restatement_equals_reference_live():
+    from oracle import ref_driver
+    c = cases.CASES['small']
+    ref = refshim.build_head(double=True)
+    synth.fill_params_(ref, c['scheme'], c['seed'])
+    a = cases.run_aug(ref, lambda h, *x: ref_driver.ref_aug_test(h, *x)[:2], 'small', torch.float64)
+    head = restate.HTDRoIHead().double()
+    synth.fill_params_(head, c['scheme'], c['seed'])
+    b = cases.run_aug(head, lambda h, *x: h.aug_test_merged(*x), 'small', torch.float64)
+    for k in a:
+        assert cases.rel_err(b[k], a[k]) <= 1e-12, k
+
+
+def test_bbox_mapping_helpers_round_trip():
+    """Host logic of the product's aug_test: mapping to an augmented view and back is the identity,
+    and flips are involutions (core/bbox/transforms.py:5-56)."""
+    from htd_b200.core import bbox_flip, bbox_mapping, bbox_mapping_back, merge_aug_bboxes
+    g = torch.Generator().manual_seed(3)
+    b = torch.rand(17, 4, generator=g) * 200
+    sf = np.array([0.5, 0.75, 0.5, 0.75], dtype=np.float32)
+    for d in ('horizontal', 'vertical', 'diagonal'):
+        assert torch.allclose(bbox_flip(bbox_flip(b, (300, 400), d), (300, 400), d), b, atol=1e-4)
+        m = bbox_mapping(b, (300, 400), sf, True, d)
+        assert torch.allclose(bbox_mapping_back(m, (300, 400), sf, True, d), b, atol=1e-4)
+    wide = torch.rand(5, 8, generator=g) * 100
+    assert bbox_flip(wide, (300, 400), 'horizontal').shape == wide.shape
+    metas = [[dict(img_shape=(300, 400, 3), scale_factor=sf, flip=False)],
+             [dict(img_shape=(300, 400, 3), scale_factor=sf, flip=True, flip_direction='vertical')]]
+    views = [bbox_mapping(b, (300, 400), sf, m[0]['flip'], m[0].get('flip_direction', 'horizontal'))
+             for m in metas]
+    merged, sc = merge_aug_bboxes(views, [torch.ones(17, 3), 3 * torch.ones(17, 3)], metas)
+    assert torch.allclose(merged, b, atol=1e-4) and torch.equal(sc, 2 * torch.ones(17, 3))
+
+
 # ---- assign + sample (SURVEY §8 f2) --------------------------------------------------------------
 def _assign_fixture():
     z = np.load(os.path.join(GOLD, 'assign_sample.npz'))

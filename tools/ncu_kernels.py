@@ -20,6 +20,7 @@ shapes = [tuple(t.shape) for t in x]
 lv = ops.level_assign(rois, 4)
 K, P = rois.shape[0], pos_rois.shape[0]
 plan_s = ops.RoIPlan(x, scales, rois, lv, 7, 0)
+PLAN_IN_RUN = len(sys.argv) > 2 and sys.argv[2] == "plan"
 plan_b = ops.RoIPlan(x, scales, pos_rois, None, 7, 0)
 out_s = torch.empty(K, 7, 7, C, device=dev, dtype=dtype)
 out_b = torch.empty(4, P, 7, 7, C, device=dev, dtype=dtype)
@@ -30,6 +31,9 @@ dm = torch.randn(4 * P, C, device=dev)
 
 def run_all():
     flush.fill_(1.0)
+    if PLAN_IN_RUN:
+        ops.RoIPlan(x, scales, rois, lv, 7, 0)
+        ops.RoIPlan(x, scales, pos_rois, None, 7, 0)
     ops._fwd_launch('f', x, scales, rois, lv, 7, 0, None, out_s, plan=plan_s)
     flush.fill_(2.0)
     ops._roi_align_bwd(shapes, dtype, scales, rois, plan_s.tensors(), 7, g_s, False)
