@@ -497,6 +497,27 @@ int htd_multiclass_soft_nms(const float* boxes, int box_classes, const float* sc
                             void* workspace, htd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * FPN glue on channels-last maps - the producer of the head's pyramid (SURVEY.md section 8 row f4;
+ * mmdet/models/necks/fpn.py:165-216).  Maps are [B, H, W, C] in memory, fp32 or bf16 (dtype), C a
+ * multiple of 4 (fp32) / 8 (bf16).  The 1x1 lateral convolutions are htd_dense_gemm (kind NT).
+ *   htd_fpn_topdown_fwd: out = fine + interpolate(coarse, size=(Hf, Wf), mode='nearest')
+ *                        (fpn.py:187-190; ATen's source index min(floor(dst * in/out), in - 1));
+ *                        out may alias fine.
+ *   htd_fpn_topdown_bwd: dcoarse = the nearest-neighbour backward of dout (every coarse pixel sums
+ *                        its fine pixels in ascending order, fp32 accumulation: deterministic);
+ *                        the gradient of `fine` is dout itself.
+ *   htd_fpn_subsample:   backward == 0: out [B, (H-1)/2+1, (W-1)/2+1, C] = in[:, ::2, ::2, :]
+ *                        (max_pool2d(x, 1, stride=2), fpn.py:201); backward != 0: `in` is the
+ *                        gradient of that output, out [B, H, W, C] receives it at the even pixels
+ *                        and zero elsewhere. */
+int htd_fpn_topdown_fwd(const void* fine, const void* coarse, void* out, int dtype, int B, int Hf,
+                        int Wf, int Hc, int Wc, int C, htd_stream_t stream);
+int htd_fpn_topdown_bwd(const void* dout, void* dcoarse, int dtype, int B, int Hf, int Wf, int Hc,
+                        int Wc, int C, htd_stream_t stream);
+int htd_fpn_subsample(const void* in, void* out, int dtype, int B, int H, int W, int C, int backward,
+                      htd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
  * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and
  * (C / G) % 8 == 0; gamma / beta / dgamma / dbeta in the tensor dtype; mean / rstd [N*G]: fp32 for HTD_BF16 tensors, fp64 for

@@ -161,6 +161,65 @@ def run_aug(head, aug_fn, name, dtype, device='cpu'):
     return {'aug.bboxes': out[0], 'aug.scores': out[1]}
 
 
+FPN_SIZES = ((37, 53), (19, 27), (10, 14), (5, 7))     # odd sizes: non-integer nearest scales
+
+
+def fpn_fill_(fpn, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in sorted(fpn.named_parameters()):
+            std = 0.1 if n.endswith('bias') else (2.0 / p[0].numel()) ** 0.5
+            p.copy_((std * torch.randn(p.shape, generator=g)).to(p.dtype))
+    return fpn
+
+
+def fpn_inputs(dtype=torch.float32, device='cpu', B=2, in_channels=(256, 512, 1024, 2048)):
+    return [seeded_like(torch.empty(B, c, h, w), 70 + i).to(dtype).to(device)
+            for i, (c, (h, w)) in enumerate(zip(in_channels, FPN_SIZES))]
+
+
+def run_fpn(fpn, dtype, device='cpu'):
+    """FPN forward (five outputs) and the gradients of a seeded linear loss w.r.t. inputs / weights."""
+    xs = [x.requires_grad_(True) for x in fpn_inputs(dtype, device)]
+    outs = fpn(xs)
+    res = {f'fpn.out{i}': o for i, o in enumerate(outs)}
+    loss = sum((o.float() * seeded_like(o, 90 + i).float()).sum() for i, o in enumerate(outs))
+    named = sorted(fpn.named_parameters())
+    grads = torch.autograd.grad(loss, xs + [p for _, p in named])
+    for i in range(len(xs)):
+        res[f'fpn.dx{i}'] = grads[i]
+    for (n, _), g in zip(named, grads[len(xs):]):
+        res['fpn.d.' + n] = g
+    return res
+
+
+RPN_CASES = {
+    # name: image (h, w), nms_pre, nms_post, nms_thr, min_bbox_size, seed
+    'train': dict(hw=(200, 304), nms_pre=2000, nms_post=2000, nms_thr=0.7, min_bbox_size=0, seed=11),
+    'test': dict(hw=(160, 256), nms_pre=1000, nms_post=1000, nms_thr=0.7, min_bbox_size=0, seed=12),
+    'minsize': dict(hw=(96, 128), nms_pre=300, nms_post=100, nms_thr=0.5, min_bbox_size=12, seed=13),
+}
+
+
+def rpn_inputs(name, dtype=torch.float32, device='cpu'):
+    """RPN head outputs of one image on the five levels: objectness logits [3, H, W] (distinct
+    values: a random permutation of an evenly spaced grid, so the ranking has no ties) and box
+    deltas [12, H, W]."""
+    c = RPN_CASES[name]
+    H, W = c['hw']
+    g = torch.Generator().manual_seed(c['seed'])
+    cls, reg = [], []
+    for s in (4, 8, 16, 32, 64):
+        h, w = -(-H // s), -(-W // s)
+        n = 3 * h * w
+        vals = torch.linspace(-6.0, 4.0, n, dtype=torch.float64)[torch.randperm(n, generator=g)]
+        cls.append(vals.view(3, h, w).to(dtype).to(device))
+        reg.append((0.35 * torch.randn(12, h, w, generator=g)).to(dtype).to(device))
+    return cls, reg, (H, W, 3), dict(nms_across_levels=False, nms_pre=c['nms_pre'],
+                                     nms_post=c['nms_post'], max_num=c['nms_post'],
+                                     nms_thr=c['nms_thr'], min_bbox_size=c['min_bbox_size'])
+
+
 # ------------------------------------------------------------------ fixtures
 def summarize(t, nsample=1024):
     t = t.detach().to('cpu')

@@ -108,6 +108,27 @@ def main():
     if only is None:
         gen_assign_sample()
         gen_nms()
+        gen_fpn(ns)
+        gen_rpn()
+
+
+def gen_fpn(ns):
+    # --- FPN neck: the reference's own FPN, fp64 ---------------------------------
+    fpn = cases.fpn_fill_(ns.FPN([256, 512, 1024, 2048], 256, 5).double())
+    outs = cases.run_fpn(fpn, torch.float64)
+    cases.save_fixture(os.path.join(OUT, 'fpn_f64.npz'), outs)
+    print('fpn:', len(outs), 'tensors')
+
+
+def gen_rpn():
+    # --- RPN proposals: the reference's own _get_bboxes_single -------------------
+    flat = {}
+    for name in cases.RPN_CASES:
+        cls, reg, shape, cfg = cases.rpn_inputs(name)
+        det = ref_driver.ref_rpn_proposals(cls, reg, shape, cfg)
+        flat[name] = det.numpy()
+        print('rpn', name, tuple(det.shape))
+    np.savez_compressed(os.path.join(OUT, 'rpn_proposals.npz'), **flat)
 
 
 def gen_levels(ext):

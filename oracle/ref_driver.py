@@ -172,3 +172,37 @@ def ref_aug_test(head, features, proposals, img_metas):
         rh.multiclass_nms = real
     return seen['bboxes'], seen['scores'], seen['det'][0], seen['det'][1]
 
+
+def ref_rpn_function():
+    """The reference's RPNHead._get_bboxes_single (dense_heads/rpn_head.py:77-168), taken from
+    its source file and executed unmodified.  Importing the class would pull in the whole
+    anchor-head / loss stack of mmdet; the method only needs torch and mmcv.ops.batched_nms
+    (mmcv is un-vendored: refshim's torchvision-based stand-in, as for the RoI head's NMS)."""
+    import ast
+    path = refshim.REF + '/mmdet/models/dense_heads/rpn_head.py'
+    src = open(path).read()
+    fn = [n for n in ast.walk(ast.parse(src))
+          if isinstance(n, ast.FunctionDef) and n.name == '_get_bboxes_single'][0]
+    code = ast.get_source_segment(src, fn)
+    import textwrap
+    g = {'torch': torch, 'batched_nms': refshim._batched_nms}
+    exec(compile(textwrap.dedent(code), path, 'exec'), g)
+    return g['_get_bboxes_single']
+
+
+def ref_rpn_proposals(cls_scores, bbox_preds, img_shape, cfg):
+    """One image through the reference's _get_bboxes_single with the reference's own
+    AnchorGenerator and DeltaXYWHBBoxCoder (configs/htd/htd_resnet50_1x.py:22-37)."""
+    import importlib
+    from types import SimpleNamespace
+    ns = refshim.load()
+    refshim._mod('mmdet.core.anchor', path=refshim.REF + '/mmdet/core/anchor')
+    ag = importlib.import_module('mmdet.core.anchor.anchor_generator').AnchorGenerator(
+        strides=[4, 8, 16, 32, 64], ratios=[0.5, 1.0, 2.0], scales=[8])
+    anchors = ag.grid_anchors([c.shape[-2:] for c in cls_scores], device='cpu')
+    anchors = [a.to(cls_scores[0].dtype) for a in anchors]
+    self = SimpleNamespace(use_sigmoid_cls=True, test_cfg=cfg, bbox_coder=ns.DeltaXYWHBBoxCoder(
+        target_means=[.0, .0, .0, .0], target_stds=[1.0, 1.0, 1.0, 1.0]))
+    return ref_rpn_function()(self, cls_scores, bbox_preds, anchors, img_shape, 1.0,
+                              refshim.AttrDict.wrap(dict(cfg)))
+

@@ -259,7 +259,10 @@ def load():
     _mod('mmdet.models.roi_heads.test_mixins', BBoxTestMixin=type('BBoxTestMixin', (), {}),
          MaskTestMixin=type('MaskTestMixin', (), {}))
     rh = imp('mmdet.models.roi_heads.htd_roi_head')
+    _mod('mmdet.models.necks', path=REF + '/mmdet/models/necks')
+    fpn = imp('mmdet.models.necks.fpn')
     ns = types.SimpleNamespace(
+        FPN=fpn.FPN, merge_aug_bboxes=ma.merge_aug_bboxes,
         HTDRoIHead=rh.HTDRoIHead, HTDBBoxHead=htdh.HTDBBoxHead,
         AdptRoIExtractor=ada.AdptRoIExtractor, SingleRoIExtractor=sle.SingleRoIExtractor,
         GlobalContextHead=gch.GlobalContextHead, Shared2FCBBoxHead=cf.Shared2FCBBoxHead,

@@ -265,19 +265,20 @@ class AdptRoIExtractor(nn.Module):
 class ConvModule(nn.Module):
     """mmcv ConvModule defaults used by the reference: conv -> GN -> ReLU, bias='auto'."""
 
-    def __init__(self, i, o, k, padding=0, norm_groups=None, bias='auto'):
+    def __init__(self, i, o, k, padding=0, norm_groups=None, bias='auto', act=True):
         super().__init__()
         with_norm = norm_groups is not None
         if bias == 'auto':
             bias = not with_norm
         self.conv = nn.Conv2d(i, o, k, 1, padding, bias=bias)
         self.gn = nn.GroupNorm(norm_groups, o) if with_norm else None
+        self.act = act                    # act_cfg=None (FPN): no activation
 
     def forward(self, x):
         x = self.conv(x)
         if self.gn is not None:
             x = self.gn(x)
-        return F.relu(x)
+        return F.relu(x) if self.act else x
 
 
 class GlobalContextHead(nn.Module):
@@ -477,6 +478,73 @@ class HTDBBoxHead(BBoxHeadBase):
 # --------------------------------------------------------------------------------------
 # multi-class NMS - checker of csrc/nms.cu
 # --------------------------------------------------------------------------------------
+class FPN(nn.Module):
+    """necks/fpn.py:9-216 with the configs/htd arguments (htd_resnet50_1x.py:17-21: no extra convs,
+    no norm / activation, nearest top-down by target size, extra levels = max_pool2d(x, 1, 2))."""
+
+    def __init__(self, in_channels=(256, 512, 1024, 2048), out_channels=256, num_outs=5):
+        super().__init__()
+        self.num_outs = num_outs
+        self.lateral_convs = nn.ModuleList()
+        self.fpn_convs = nn.ModuleList()
+        for c in in_channels:                                    # fpn.py:110-131
+            self.lateral_convs.append(ConvModule(c, out_channels, 1, act=False))
+            self.fpn_convs.append(ConvModule(out_channels, out_channels, 3, padding=1, act=False))
+
+    def forward(self, inputs):
+        lat = [conv(x) for conv, x in zip(self.lateral_convs, inputs)]           # fpn.py:170-174
+        for i in range(len(lat) - 1, 0, -1):                                     # fpn.py:177-190
+            lat[i - 1] = lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode='nearest')
+        outs = [conv(x) for conv, x in zip(self.fpn_convs, lat)]                 # fpn.py:194-196
+        while len(outs) < self.num_outs:                                         # fpn.py:198-201
+            outs.append(F.max_pool2d(outs[-1], 1, stride=2))
+        return tuple(outs)
+
+
+def anchor_grid(featmap_sizes, strides=(4, 8, 16, 32, 64), ratios=(0.5, 1.0, 2.0), scales=(8.,)):
+    """core/anchor/anchor_generator.py:142-187 (base anchors, scale_major, center_offset 0) and
+    :232-272 (grid): per level [H*W*A, 4], rows ordered (y, x, anchor)."""
+    out = []
+    r, sc = torch.Tensor(ratios), torch.Tensor(scales)
+    for (h, w), stride in zip(featmap_sizes, strides):
+        hr = torch.sqrt(r)
+        wr = 1 / hr
+        ws = (stride * wr[:, None] * sc[None, :]).view(-1)
+        hs = (stride * hr[:, None] * sc[None, :]).view(-1)
+        base = torch.stack([-0.5 * ws, -0.5 * hs, 0.5 * ws, 0.5 * hs], dim=-1)
+        sx = torch.arange(0, int(w)) * stride
+        sy = torch.arange(0, int(h)) * stride
+        xx, yy = sx.repeat(len(sy)), sy.view(-1, 1).repeat(1, len(sx)).view(-1)
+        shifts = torch.stack([xx, yy, xx, yy], dim=-1).type_as(base)
+        out.append((base[None] + shifts[:, None]).view(-1, 4))
+    return out
+
+
+def rpn_proposals_single(cls_scores, bbox_preds, mlvl_anchors, img_shape, nms_pre, nms_post, nms_thr,
+                         min_bbox_size=0):
+    """dense_heads/rpn_head.py:77-168 (use_sigmoid_cls): per level the nms_pre best anchors by
+    sigmoid score, delta2bbox with means 0 / stds 1 clipped to the image, batched NMS with the
+    level index as the class (mmcv batched_nms: boxes shifted by level * (max coordinate + 1),
+    greedy NMS in descending score order), first nms_post.  Returns [n, 5]."""
+    scores, boxes, ids = [], [], []
+    for l, (c, d, a) in enumerate(zip(cls_scores, bbox_preds, mlvl_anchors)):
+        s = c.permute(1, 2, 0).reshape(-1).sigmoid()
+        d = d.permute(1, 2, 0).reshape(-1, 4)
+        if nms_pre > 0 and s.shape[0] > nms_pre:
+            rs, ri = s.sort(descending=True)
+            s, d, a = rs[:nms_pre], d[ri[:nms_pre]], a[ri[:nms_pre]]
+        scores.append(s)
+        boxes.append(delta2bbox(a, d, (0., 0., 0., 0.), (1., 1., 1., 1.), max_shape=img_shape))
+        ids.append(torch.full((s.shape[0],), l, dtype=torch.long))
+    scores, boxes, ids = torch.cat(scores), torch.cat(boxes), torch.cat(ids)
+    if min_bbox_size > 0:
+        ok = ((boxes[:, 2] - boxes[:, 0]) >= min_bbox_size) & ((boxes[:, 3] - boxes[:, 1]) >= min_bbox_size)
+        scores, boxes, ids = scores[ok], boxes[ok], ids[ok]
+    shifted = boxes + (ids.to(boxes) * (boxes.max() + 1))[:, None]
+    keep = nms_greedy(shifted, scores, nms_thr)
+    return torch.cat([boxes[keep], scores[keep, None]], dim=1)[:nms_post]
+
+
 def nms_greedy(boxes, scores, iou_thr):
     """mmcv.ops.nms (mmcv-full 1.2.1, un-vendored; the same published algorithm as
     torchvision.ops.nms, against which tests/test_oracle_cpu.py pins this function): visit boxes

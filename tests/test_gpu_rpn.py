@@ -1,0 +1,66 @@
+"""GPU parity tests of the RPN proposal path (producer side):
+htd_b200.dense_heads.RPNHead.get_bboxes (torch.sort ranking, htd_bbox_decode, htd_multiclass_nms with
+the level as the class) against the CPU oracle (oracle/restate.py rpn_proposals_single) and the
+fixture written by the reference's own RPNHead._get_bboxes_single."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _head():
+    from htd_b200.dense_heads import RPNHead
+    return RPNHead(256, 256).cuda()
+
+
+@pytest.mark.parametrize('name', ['train', 'test', 'minsize'])
+def test_rpn_proposals_vs_oracle_and_reference_fixture(name):
+    """Same proposals in the same order: scores <= 1e-6, boxes <= 1e-3 px (the decode's exp differs
+    in the last bit between the host and the device)."""
+    from oracle import cases, restate
+    cls, reg, shape, cfg = cases.rpn_inputs(name)
+    anchors = restate.anchor_grid([c.shape[-2:] for c in cls])
+    want = restate.rpn_proposals_single(cls, reg, anchors, shape, cfg['nms_pre'], cfg['nms_post'],
+                                        cfg['nms_thr'], cfg['min_bbox_size'])
+    head = _head()
+    got = head.get_bboxes([c[None].cuda() for c in cls], [r[None].cuda() for r in reg],
+                          [dict(img_shape=shape, scale_factor=1.0)], cfg)
+    assert len(got) == 1
+    g = got[0].cpu()
+    assert g.shape == want.shape, (g.shape, want.shape)
+    assert torch.allclose(g[:, 4], want[:, 4], atol=1e-6, rtol=0)
+    assert torch.allclose(g[:, :4], want[:, :4], atol=1e-3, rtol=0)
+    z = np.load(os.path.join(GOLD, 'rpn_proposals.npz'))
+    assert np.allclose(g.numpy(), z[name], atol=1e-3, rtol=0)
+    assert (g[:-1, 4] >= g[1:, 4]).all()
+
+
+def test_rpn_head_end_to_end_two_images_from_fpn_outputs():
+    """FPN (channels-last bf16) -> RPN head -> proposals for two images -> HTDRoIHead.simple_test."""
+    import htd_b200
+    from htd_b200 import synth
+    from htd_b200.necks import FPN
+    from oracle import cases
+    fpn = cases.fpn_fill_(FPN([256, 512, 1024, 2048], 256, 5)).cuda().bfloat16()
+    rpn = _head().bfloat16().to(memory_format=torch.channels_last)
+    head = htd_b200.build_htd_roi_head()
+    synth.fill_params_(head, 'n005', 0)
+    head = head.cuda().bfloat16()
+    head.compute_dtype = torch.bfloat16
+    xs = cases.fpn_inputs(torch.float32, 'cuda')
+    H, W = cases.FPN_SIZES[0]
+    metas = [dict(img_shape=(4 * H, 4 * W, 3), scale_factor=1.0)] * 2
+    cfg = dict(nms_across_levels=False, nms_pre=1000, nms_post=300, max_num=300, nms_thr=0.7,
+               min_bbox_size=0)
+    with torch.no_grad():
+        feats = fpn(xs)
+        props = rpn.get_bboxes(*rpn(feats), metas, cfg)
+        assert len(props) == 2 and all(p.shape[1] == 5 and 0 < p.shape[0] <= 300 for p in props)
+        for p in props:
+            assert (p[:, 0] >= 0).all() and (p[:, 2] <= 4 * W).all() and (p[:, 3] <= 4 * H).all()
+        res = head.simple_test(feats, props, metas)
+    assert len(res) == 2 and len(res[0]) == head.bbox_head[-1].num_classes

@@ -191,6 +191,65 @@ def test_bbox_mapping_helpers_round_trip():
     assert torch.allclose(merged, b, atol=1e-4) and torch.equal(sc, 2 * torch.ones(17, 3))
 
 
+# ---- FPN neck -----------------------------------------------------------------------
+def test_fpn_restatement_matches_reference_golden():
+    """tests/golden/fpn_f64.npz: outputs and input / weight gradients of the reference's own FPN
+    (necks/fpn.py) on odd-sized maps (non-integer nearest scales)."""
+    fpn = cases.fpn_fill_(restate.FPN().double())
+    outs = cases.run_fpn(fpn, torch.float64)
+    fix = cases.load_fixture(os.path.join(GOLD, 'fpn_f64.npz'))
+    assert set(outs) == set(fix)
+    cases.compare_to_fixture(outs, fix, 1e-10)
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference not present')
+def test_fpn_restatement_equals_reference_live():
+    ns = refshim.load()
+    ref = cases.fpn_fill_(ns.FPN([256, 512, 1024, 2048], 256, 5).double())
+    a = cases.run_fpn(ref, torch.float64)
+    b = cases.run_fpn(cases.fpn_fill_(restate.FPN().double()), torch.float64)
+    assert set(ref.state_dict()) == set(restate.FPN().state_dict())
+    for k in a:
+        assert cases.rel_err(b[k], a[k]) <= 1e-12, k
+
+
+# ---- RPN proposals (SURVEY §8 f4) ------------------------------------------------------------------
+@pytest.mark.parametrize('name', list(cases.RPN_CASES))
+def test_rpn_restatement_matches_reference_golden(name):
+    """tests/golden/rpn_proposals.npz: output of the reference's own RPNHead._get_bboxes_single
+    (source of dense_heads/rpn_head.py:77-168 executed unmodified) with its AnchorGenerator."""
+    z = np.load(os.path.join(GOLD, 'rpn_proposals.npz'))
+    cls, reg, shape, cfg = cases.rpn_inputs(name)
+    anchors = restate.anchor_grid([c.shape[-2:] for c in cls])
+    det = restate.rpn_proposals_single(cls, reg, anchors, shape, cfg['nms_pre'], cfg['nms_post'],
+                                       cfg['nms_thr'], cfg['min_bbox_size'])
+    assert np.array_equal(det.numpy(), z[name])
+
+
+@pytest.mark.skipif(not refshim.available(), reason='/root/reference not present')
+def test_rpn_restatement_equals_reference_live():
+    from oracle import ref_driver
+    cls, reg, shape, cfg = cases.rpn_inputs('minsize')
+    want = ref_driver.ref_rpn_proposals(cls, reg, shape, cfg)
+    anchors = restate.anchor_grid([c.shape[-2:] for c in cls])
+    got = restate.rpn_proposals_single(cls, reg, anchors, shape, cfg['nms_pre'], cfg['nms_post'],
+                                       cfg['nms_thr'], cfg['min_bbox_size'])
+    assert torch.equal(got, want)
+
+
+def test_product_anchor_generator_equals_the_restatement():
+    """Host logic of htd_b200.dense_heads.AnchorGenerator (anchor_generator.py:142-272)."""
+    from htd_b200.dense_heads import AnchorGenerator
+    sizes = [(50, 76), (25, 38), (13, 19), (7, 10), (4, 5)]
+    ag = AnchorGenerator(strides=[4, 8, 16, 32, 64], ratios=[0.5, 1.0, 2.0], scales=[8])
+    assert ag.num_base_anchors == [3] * 5 and ag.num_levels == 5
+    got = ag.grid_anchors(sizes, device='cpu')
+    want = restate.anchor_grid(sizes)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert ag.grid_anchors(sizes, device='cpu')[0] is got[0]          # cached
+
+
 # ---- assign + sample (SURVEY §8 f2) --------------------------------------------------------------
 def _assign_fixture():
     z = np.load(os.path.join(GOLD, 'assign_sample.npz'))
