@@ -765,6 +765,52 @@ def run_gpu(args):
             head.train()
             print(f'[bench] inference figure failed ({type(e).__name__}: {e})', file=sys.stderr)
 
+    # ---- producers of the path: FPN neck + RPN proposals at the same image size ----
+    producers = None
+    if world == 1 and not args.no_static and dtype == torch.bfloat16:
+        try:
+            from htd_b200.dense_heads import RPNHead
+            from htd_b200.necks import FPN
+            fpn = FPN([256, 512, 1024, 2048], 256, 5).to(dev).to(dtype)
+            rpn = RPNHead(256, 256).to(dev).to(dtype).to(memory_format=torch.channels_last)
+            gb = torch.Generator().manual_seed(5)
+            cs = [(torch.randn(imgs, c, t.shape[2], t.shape[3], generator=gb) * 0.5).to(dev)
+                  .to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+                  for c, t in zip((256, 512, 1024, 2048), x_dev)]
+            pmeta = [dict(img_shape=shapes[0], scale_factor=1.0)] * imgs
+            pcfg = dict(nms_across_levels=False, nms_pre=2000, nms_post=2000, max_num=2000, nms_thr=0.7,
+                        min_bbox_size=0)
+
+            def fpn_step():
+                outs = fpn(cs)
+                torch.autograd.backward(outs, [torch.ones_like(o) for o in outs])
+                return outs
+
+            def timed(fn, n=5):
+                for _ in range(2):
+                    r = fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    r = fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) / n, r
+            f_ms, outs = timed(fpn_step)
+            with torch.no_grad():
+                feats = [o.detach() for o in outs]
+                r_ms, props = timed(lambda: rpn.get_bboxes(*rpn(feats), pmeta, pcfg))
+            producers = dict(what='htd_b200.necks.FPN forward+backward (C2-C5 channels-last bf16 in, five '
+                                  'channels-last bf16 maps out: the head reads them without a layout pass) '
+                                  'and htd_b200.dense_heads.RPNHead forward + get_bboxes (nms_pre 2000, '
+                                  'nms 0.7, nms_post 2000) for the same images; eager, random weights',
+                             fpn_fwd_bwd_ms=f_ms, rpn_proposals_ms=r_ms,
+                             proposals_per_img=[int(p.shape[0]) for p in props])
+            del fpn, rpn, cs, outs, feats
+        except Exception as e:
+            print(f'[bench] producer figure failed ({type(e).__name__}: {e})', file=sys.stderr)
+
     # ---- device times of the gather launches (plan included), CUDA-graph replays ---------------
     gtimes = None
     if dtype == torch.bfloat16 and imgs == IMGS:
@@ -892,6 +938,7 @@ def run_gpu(args):
                             full_step_with_sampling=static,
                             channels_last_bf16_pyramid=nhwc,
                             inference=infer,
+                            producers=producers,
                             kernel_timing='CUDA events around each own launch in an eager pass of '
                                           'the same step (events cannot be placed inside a graph)'),
                 e2e=dict(value=value_e2e, unit=UNIT, h2d_bytes_per_step=h2d_bytes,
