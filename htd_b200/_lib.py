@@ -109,6 +109,7 @@ SIGNATURES = {
                             c_void_p],
     'htd_fpn_topdown_bwd': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     'htd_fpn_subsample': [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    'htd_topk_sorted': [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'htd_add3': [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                  c_void_p, c_void_p],
     'htd_assign_sample': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,

@@ -8,9 +8,10 @@ Per image: per level the ``nms_pre`` best anchors by objectness, decoded with th
 unit-std DeltaXYWH coder and clipped (``htd_bbox_decode``), then ONE class-aware NMS over the levels
 (mmcv ``batched_nms`` with the level index as the class: exactly what ``htd_multiclass_nms`` computes
 when candidate row k holds the rank-k box of every level) and the ``nms_post`` best survivors - no
-host synchronisation before the final count.  The ranking itself is ``torch.sort`` (library) on
-the LOGITS: the sigmoid is monotonic, so the order is the reference's wherever that is defined
-(equal scores have no defined order there: an unstable sort).  The anchor-target / loss side of the
+host synchronisation before the final count.  The ranking is ``htd_topk_sorted`` (radix select +
+shared-memory bitonic sort, one CTA per level) on the LOGITS: the sigmoid is monotonic, so the order
+is the reference's wherever that is defined (equal scores have no defined order there: an unstable
+sort; here they come in anchor order).  The anchor-target / loss side of the
 RPN is training of another head and is not part of this path.
 """
 import torch
@@ -141,9 +142,13 @@ class RPNHead(nn.Module):
             delta = bbox_preds[l].permute(1, 2, 0).reshape(-1, 4)
             anchors = mlvl_anchors[l]
             if cfg.nms_pre > 0 and logit.shape[0] > cfg.nms_pre:
-                ranked, idx = logit.sort(descending=True)
-                idx = idx[:cfg.nms_pre]
-                logit, delta, anchors = ranked[:cfg.nms_pre], delta[idx], anchors[idx]
+                if cfg.nms_pre <= MAX_CANDIDATES:
+                    ranked, idx = ops.topk_sorted(logit.contiguous()[None], cfg.nms_pre)
+                    ranked, idx = ranked[0], idx[0]
+                else:
+                    ranked, idx = logit.sort(descending=True)
+                    ranked, idx = ranked[:cfg.nms_pre], idx[:cfg.nms_pre]
+                logit, delta, anchors = ranked, delta[idx], anchors[idx]
             if logit.shape[0] > MAX_CANDIDATES:
                 raise NotImplementedError(f'{logit.shape[0]} candidates on level {l}: nms_pre <= '
                                           f'{MAX_CANDIDATES} (configs/htd: 2000 / 1000)')

@@ -892,3 +892,19 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, iou_thr, max_num, soft
                                    float(iou_thr), max_num, ptr(det), ptr(labels), ptr(count),
                                    ptr(ws), stream()), 'htd_multiclass_nms')
     return det, labels, count
+
+
+def topk_sorted(keys, k):
+    """The k largest of every row of a [rows, n] fp32 tensor (rows may be strided) in descending
+    order, equal keys by ascending position: (values [rows, k], positions [rows, k] int64).
+    htd_topk_sorted - the ranking of the RPN proposal path (rpn_head.py:125-134)."""
+    _lib.require_cuda(keys)
+    assert keys.dim() == 2 and keys.dtype == torch.float32 and keys.stride(1) == 1, \
+        (keys.shape, keys.dtype, keys.stride())
+    rows, n = keys.shape
+    vals = torch.empty((rows, k), dtype=torch.float32, device=keys.device)
+    idx = torch.empty((rows, k), dtype=torch.int32, device=keys.device)
+    check(lib().htd_topk_sorted(ptr(keys), keys.stride(0) if rows > 1 else n, rows, n, int(k), ptr(vals),
+                                ptr(idx), stream()), 'htd_topk_sorted')
+    return vals, idx.long()
+

@@ -517,6 +517,16 @@ int htd_fpn_topdown_bwd(const void* dout, void* dcoarse, int dtype, int B, int H
 int htd_fpn_subsample(const void* in, void* out, int dtype, int B, int H, int W, int C, int backward,
                       htd_stream_t stream);
 
+/* Ranking step of the RPN proposal path (mmdet/models/dense_heads/rpn_head.py:125-134:
+ * `scores.sort(descending=True)` and the first nms_pre entries): for each of `rows` rows of n fp32
+ * keys (row r at keys + r * row_stride) the k largest in descending order - out_keys [rows, k] - and
+ * their positions - out_idx [rows, k]; equal keys in ascending position (a stable sort; the
+ * reference's sort is unstable).  1 <= k <= min(n, HTD_TOPK_MAX).  One CTA per row: radix select of
+ * the k-th largest key, one collecting pass, bitonic sort in shared memory. */
+#define HTD_TOPK_MAX 4096
+int htd_topk_sorted(const float* keys, long long row_stride, int rows, int n, int k, float* out_keys,
+                    int32_t* out_idx, htd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused GroupNorm + ReLU of the regression conv tower (mmcv ConvModule conv -> GN -> ReLU,
  * htd_bbox_head.py:75-113,186).  x, y, dy, dx: [N, HW, C] channels-last, C % G == 0 and

@@ -64,3 +64,33 @@ def test_rpn_head_end_to_end_two_images_from_fpn_outputs():
             assert (p[:, 0] >= 0).all() and (p[:, 2] <= 4 * W).all() and (p[:, 3] <= 4 * H).all()
         res = head.simple_test(feats, props, metas)
     assert len(res) == 2 and len(res[0]) == head.bbox_head[-1].num_classes
+
+
+@pytest.mark.parametrize('n,k', [(201600, 2000), (50400, 1000), (3150, 2000), (819, 819), (5000, 4096),
+                                 (7, 3), (1, 1)])
+def test_topk_sorted_equals_a_stable_descending_sort(n, k):
+    """htd_topk_sorted against torch.sort(stable=True, descending=True): values and positions
+    bit-exact, several rows (strided), negative / positive / repeated keys."""
+    from htd_b200 import ops
+    g = torch.Generator().manual_seed(n + k)
+    keys = torch.randn(3, n + 5, generator=g).cuda()[:, :n]            # row stride n + 5
+    keys[1] = (keys[1] * 4).round() / 4                                 # many exact ties
+    if n > 10:
+        keys[2, ::3] = -keys[2, ::3].abs() * 1e-20                      # denormal-range negatives
+    vals, idx = ops.topk_sorted(keys, k)
+    sv, si = torch.sort(keys, dim=1, descending=True, stable=True)
+    assert torch.equal(vals, sv[:, :k])
+    assert torch.equal(idx, si[:, :k])
+
+
+def test_topk_sorted_massive_ties_take_the_index_ordered_path():
+    """More threshold-valued keys than the collection buffer holds (saturated logits): the first
+    ones in position order are taken."""
+    from htd_b200 import ops
+    n, k = 60000, 1500
+    keys = torch.full((2, n), 3.5, device='cuda')
+    keys[0, 100:600] = 9.0                      # 500 above the tie value
+    keys[1, ::7] = -1.0
+    vals, idx = ops.topk_sorted(keys, k)
+    sv, si = torch.sort(keys, dim=1, descending=True, stable=True)
+    assert torch.equal(vals, sv[:, :k]) and torch.equal(idx, si[:, :k])
