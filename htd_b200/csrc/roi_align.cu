@@ -1628,11 +1628,23 @@ __global__ void __launch_bounds__((4 * kCG + 1) * 32, kMinCtas) roi_align_bwd_mm
 //     gather); with fp32 OUTPUT they enter as bf16 hi + lo pairs (two MMAs, ~2^-17 relative).
 //   * footprints wider than 64 px or tasks spanning more than 64 rows (never a level-assigned RoI
 //     of an 800x1333 image) are reduced straight from global memory by the consumer warps.
+#ifndef HTD_MF_TILES                             // tuning builds (tools/fwd_variants.py) override these
+#define HTD_MF_TILES 5
+#endif
+#ifndef HTD_MF_DESC
+#define HTD_MF_DESC 4
+#endif
+#ifndef HTD_MF_AHEAD
+#define HTD_MF_AHEAD 2
+#endif
+#ifndef HTD_MF_SEG
+#define HTD_MF_SEG 2
+#endif
 constexpr int kMfGroups = 2;
-constexpr int kMfTiles = 5;                      // 4 KB tiles in flight per (group, channel chunk)
-constexpr int kMfDesc = 4;                       // task descriptors in flight per group
-constexpr int kMfAhead = 2;                      // descriptors published ahead of the tile issue
-constexpr int kMfSeg = 2;                        // bin rows per task
+constexpr int kMfTiles = HTD_MF_TILES;           // 4 KB tiles in flight per (group, channel chunk)
+constexpr int kMfDesc = HTD_MF_DESC;             // task descriptors in flight per group
+constexpr int kMfAhead = HTD_MF_AHEAD;           // descriptors published ahead of the tile issue
+constexpr int kMfSeg = HTD_MF_SEG;               // bin rows per task
 constexpr int kMfMaxRows = 64, kMfMaxPx = 64;
 constexpr int kMfTileBytes = 32 * 128;
 struct MfUnit {                                  // 32 ints: moved by the producer's lanes, one int each
@@ -1641,12 +1653,11 @@ struct MfUnit {                                  // 32 ints: moved by the produc
     const float* wx_src;
     long long out_off;                           // output element offset of bin (ph0, 0)
     int live, fallback, b, l, nrows, nxs, nchunk, ph0, nph, x0, y0, W;
-    short yoff[kMfSeg], nyb[kMfSeg];             // per bin row: first footprint row (from y0), rows
+    short yoff[4], nyb[4];                       // per bin row: first footprint row (from y0), rows
     short dx0[HTD_MAX_POOLED - 1], nx[HTD_MAX_POOLED - 1];    // per bin column (fallback path)
     int wcls;                                    // box width class of chunk 0 (bits 0-1) and 1 (bits 2-3)
-    int pad[2];
 };
-static_assert(sizeof(MfUnit) == 128, "MfUnit is moved as 32 ints");
+static_assert(sizeof(MfUnit) == 128 && kMfSeg <= 4, "MfUnit is moved as 32 ints");
 struct MfSlot {
     MfUnit u;
     float wy[kMfMaxRows][kTabW];
@@ -1722,9 +1733,9 @@ __global__ void __launch_bounds__(kMfGroups * 8 * 32, 1)
                 MfUnit pl;
                 pl.gsrc = nullptr; pl.wy_src = nullptr; pl.wx_src = nullptr; pl.out_off = 0;
                 pl.live = 0; pl.fallback = 0; pl.b = -1; pl.l = 0; pl.nrows = 0; pl.nxs = 0; pl.nchunk = 0;
-                pl.ph0 = 0; pl.nph = 0; pl.x0 = 0; pl.y0 = 0; pl.W = 1; pl.wcls = 0; pl.pad[0] = pl.pad[1] = 0;
+                pl.ph0 = 0; pl.nph = 0; pl.x0 = 0; pl.y0 = 0; pl.W = 1; pl.wcls = 0;
 #pragma unroll
-                for (int j = 0; j < kMfSeg; ++j) { pl.yoff[j] = 0; pl.nyb[j] = 0; }
+                for (int j = 0; j < 4; ++j) { pl.yoff[j] = 0; pl.nyb[j] = 0; }
 #pragma unroll
                 for (int j = 0; j < HTD_MAX_POOLED - 1; ++j) { pl.dx0[j] = 0; pl.nx[j] = 0; }
                 if (ii < n_g) {

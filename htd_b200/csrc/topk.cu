@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1)
     __shared__ unsigned s_scan[kTopkThreads / 32];
     const int tid = threadIdx.x;
     const float* row = keys + (long long)blockIdx.x * row_stride;
+    const bool vec = (reinterpret_cast<uintptr_t>(row) & 15u) == 0;
     float* ok = out_keys + (long long)blockIdx.x * k;
     int* oi = out_idx + (long long)blockIdx.x * k;
 
@@ -43,9 +44,23 @@ __global__ void __launch_bounds__(kTopkThreads, 1)
         if (tid < 256) s_hist[tid] = 0u;
         __syncthreads();
         const unsigned prefix = s_prefix;
-        for (int base = 0; base < n; base += kTopkThreads) {       // uniform trip count: ballots below
-            const int i = base + tid;
-            const uint32_t u = i < n ? key_of(row[i]) : 0u;
+        // four elements per thread and trip (16-byte loads when the row allows): the passes are bound
+        // by the latency of the row reads, one CTA has only 32 warps to hide it
+        for (int base = 0; base < n; base += 4 * kTopkThreads) {   // uniform trip count: ballots below
+          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int i0 = base + 4 * tid;
+          if (vec && i0 + 3 < n) v4 = *reinterpret_cast<const float4*>(row + i0);
+          else {
+              if (i0 < n) v4.x = row[i0];
+              if (i0 + 1 < n) v4.y = row[i0 + 1];
+              if (i0 + 2 < n) v4.z = row[i0 + 2];
+              if (i0 + 3 < n) v4.w = row[i0 + 3];
+          }
+          const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            const uint32_t u = i < n ? key_of(vv[e]) : 0u;
             bool valid = i < n && (pass == 0 || (u >> (shift + 8)) == prefix);
             const unsigned digit = (u >> shift) & 255u;
             if (pass == 0) {
@@ -63,6 +78,7 @@ __global__ void __launch_bounds__(kTopkThreads, 1)
                 }
             }
             if (valid) atomicAdd(&s_hist[digit], 1u);
+          }
         }
         __syncthreads();
         if (tid == 0) {
@@ -87,11 +103,26 @@ __global__ void __launch_bounds__(kTopkThreads, 1)
 
     // ---- 2. collect (key, ~index): descending 64-bit order = key descending, index ascending
     if (all_eq) {
-        for (int i = tid; i < n; i += kTopkThreads) {
-            const uint32_t u = key_of(row[i]);
-            if (u >= thr) {
-                const unsigned at = atomicAdd(&s_count, 1u);
-                s_pairs[at] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+        for (int base = 0; base < n; base += 4 * kTopkThreads) {
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int i0 = base + 4 * tid;
+            if (vec && i0 + 3 < n) v4 = *reinterpret_cast<const float4*>(row + i0);
+            else {
+                if (i0 < n) v4.x = row[i0];
+                if (i0 + 1 < n) v4.y = row[i0 + 1];
+                if (i0 + 2 < n) v4.z = row[i0 + 2];
+                if (i0 + 3 < n) v4.w = row[i0 + 3];
+            }
+            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                if (i >= n) continue;
+                const uint32_t u = key_of(vv[e]);
+                if (u >= thr) {
+                    const unsigned at = atomicAdd(&s_count, 1u);
+                    s_pairs[at] = ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+                }
             }
         }
     } else {
