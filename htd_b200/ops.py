@@ -349,6 +349,11 @@ class _PyramidFn(torch.autograd.Function):
         ctx.sink = sink
         ctx.meta = ([tuple(x.shape) for x in xs], [x.dtype for x in xs], is_cl)
         ctx.mark_non_differentiable(*outs)
+        # autograd otherwise hands backward a ZERO-FILLED tensor for every non-differentiable output:
+        # five fills of the whole bf16 pyramid (92 MB, 38 us) on the critical path right before the
+        # backward gather (profiles/r02_launches_step_bf16_final.csv of the previous build)
+        ctx.set_materialize_grads(False)
+        ctx.device = xs[0].device
         return (token,) + tuple(outs)
 
     @staticmethod
@@ -356,9 +361,9 @@ class _PyramidFn(torch.autograd.Function):
         shapes, xdtypes, is_cl = ctx.meta
         sink = ctx.sink
         if not sink.sources:
-            return (None, None) + tuple(torch.zeros(s, dtype=dt_, device=gtoken.device)
+            return (None, None) + tuple(torch.zeros(s, dtype=dt_, device=ctx.device)
                                         for s, dt_ in zip(shapes, xdtypes))
-        sink.hand_over(torch.cuda.current_stream(gtoken.device))
+        sink.hand_over(torch.cuda.current_stream(ctx.device))
         # channels-last gather (512 B coalesced stores) + one transpose/cast pass back to the
         # reference's NCHW layout; writing NCHW straight from the gather measured 30% slower
         cl = _bwd_multi(shapes, sink.sources[0]['dy'].dtype, False, sink.scales, sink.sources,
