@@ -316,6 +316,18 @@ class GradSink:
         walk(self.sources)
 
 
+_AUX_STREAMS = {}
+
+
+def _aux_stream(device):
+    """One auxiliary stream per device for launches that run next to the current stream's."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    st = _AUX_STREAMS.get(key)
+    if st is None:
+        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class Pyramid(list):
     """Channels-last feature maps of one step + the token / sink that defer their gradient."""
     token = None
@@ -333,7 +345,14 @@ class _PyramidFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dtype, sink, *xs):
         outs, is_cl = [], []
-        for x in xs:
+        # the small levels are converted on a side stream NEXT to the largest one (their launches
+        # are latency-bound: one after the other they add ~25 us in front of the first extraction)
+        cur = torch.cuda.current_stream(xs[0].device)
+        side = _aux_stream(xs[0].device) if len(xs) > 1 else None
+        big = max(range(len(xs)), key=lambda i: xs[i].numel())
+        if side is not None:
+            side.wait_stream(cur)
+        for i, x in enumerate(xs):
             B, C, H, W = x.shape
             if _is_cl(x):
                 # producer already emits channels-last: no transpose; a cast only
@@ -341,10 +360,15 @@ class _PyramidFn(torch.autograd.Function):
                 outs.append(x.detach() if x.dtype == dtype else x.detach().to(dtype))
                 is_cl.append(True)
                 continue
-            o = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
-            _convert(x, o, B, C, H * W)
+            with torch.cuda.stream(cur if (side is None or i == big) else side):
+                o = torch.empty((B, H, W, C), dtype=dtype, device=x.device)
+                _convert(x, o, B, C, H * W)
+            if side is not None and i != big:
+                o.record_stream(cur)
             outs.append(o.permute(0, 3, 1, 2))
             is_cl.append(False)
+        if side is not None:
+            cur.wait_stream(side)
         token = torch.zeros(1, dtype=torch.float32, device=xs[0].device)
         ctx.sink = sink
         ctx.meta = ([tuple(x.shape) for x in xs], [x.dtype for x in xs], is_cl)
@@ -369,15 +393,27 @@ class _PyramidFn(torch.autograd.Function):
         cl = _bwd_multi(shapes, sink.sources[0]['dy'].dtype, False, sink.scales, sink.sources,
                         sink.pooled)
         grads = []
-        for g, shp, xdt, keep_cl in zip(cl, shapes, xdtypes, is_cl):
+        cur = torch.cuda.current_stream(ctx.device)
+        side = _aux_stream(ctx.device) if len(cl) > 1 else None
+        big = max(range(len(cl)), key=lambda i: cl[i].numel())
+        if side is not None:
+            side.wait_stream(cur)
+        for i, (g, shp, xdt, keep_cl) in enumerate(zip(cl, shapes, xdtypes, is_cl)):
             B, C, H, W = shp
             if keep_cl:                            # gradient stays channels-last, like the input
                 assert g.shape == shp              # [B,C,H,W] view of the [B,H,W,C] gather buffer
                 grads.append(g if g.dtype == xdt else g.to(xdt))
                 continue
-            o = torch.empty(shp, dtype=xdt, device=g.device)
-            _convert(g, o, B, H * W, C)
+            on_side = side is not None and i != big
+            with torch.cuda.stream(side if on_side else cur):
+                o = torch.empty(shp, dtype=xdt, device=g.device)
+                _convert(g, o, B, H * W, C)
+            if on_side:
+                g.record_stream(side)              # read there, allocated on `cur`
+                o.record_stream(cur)
             grads.append(o)
+        if side is not None:
+            cur.wait_stream(side)
         sink.sources = []
         return (None, None) + tuple(grads)
 
