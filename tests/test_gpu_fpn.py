@@ -83,3 +83,25 @@ def test_fpn_outputs_feed_the_head_without_a_layout_pass():
         assert o.dtype == torch.bfloat16 and o.shape[1] == 256
         assert o.is_contiguous(memory_format=torch.channels_last)
         assert ops.to_channels_last(o, torch.bfloat16).data_ptr() == o.data_ptr()
+
+
+def test_fpn_small_odd_configuration_falls_back_for_narrow_channels():
+    """in_channels that are not multiples of 64 (the dense kernel does not apply), one image, three
+    outputs of which one is the subsampled extra level, bf16 and fp32, against torch ops."""
+    import torch.nn.functional as F
+    from htd_b200.necks import FPN
+    g = torch.Generator().manual_seed(1)
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        fpn = FPN([32, 48], 32, 3).cuda()
+        xs = [torch.randn(1, 32, 21, 30, generator=g).cuda(), torch.randn(1, 48, 11, 15, generator=g).cuda()]
+        with torch.no_grad():
+            lat = [F.conv2d(x, c.conv.weight, c.conv.bias) for x, c in zip(xs, fpn.lateral_convs)]
+            lat[0] = lat[0] + F.interpolate(lat[1], size=lat[0].shape[2:], mode='nearest')
+            want = [F.conv2d(l, c.conv.weight, c.conv.bias, padding=1) for l, c in zip(lat, fpn.fpn_convs)]
+            want.append(F.max_pool2d(want[-1], 1, stride=2))
+            got = fpn.to(dtype)([x.to(dtype) for x in xs])
+        assert len(got) == 3
+        for a, b in zip(got, want):
+            assert a.shape == b.shape
+            err = (a.float() - b).abs().max().item() / b.abs().max().item()
+            assert err <= tol, (dtype, err)

@@ -117,3 +117,17 @@ def test_topk_sorted_massive_ties_take_the_index_ordered_path():
     vals, idx = ops.topk_sorted(keys, k)
     sv, si = torch.sort(keys, dim=1, descending=True, stable=True)
     assert torch.equal(vals, sv[:, :k]) and torch.equal(idx, si[:, :k])
+
+
+def test_rpn_proposals_without_ranking_and_with_one_level_empty_after_the_size_filter():
+    """nms_pre larger than every level (the reference then keeps the anchor order: no ranking) and a
+    min_bbox_size that removes most boxes; compared with the oracle like the other cases."""
+    from oracle import cases, restate
+    cls, reg, shape, _ = cases.rpn_inputs('minsize')
+    cfg = dict(nms_across_levels=False, nms_pre=4000, nms_post=50, max_num=50, nms_thr=0.6, min_bbox_size=40)
+    anchors = restate.anchor_grid([c.shape[-2:] for c in cls])
+    want = restate.rpn_proposals_single(cls, reg, anchors, shape, cfg['nms_pre'], cfg['nms_post'],
+                                        cfg['nms_thr'], cfg['min_bbox_size'])
+    got = _head().get_bboxes([c[None].cuda() for c in cls], [r[None].cuda() for r in reg],
+                             [dict(img_shape=shape, scale_factor=1.0)], cfg)[0].cpu()
+    _same_proposals(got, want)

@@ -213,6 +213,24 @@ def test_fpn_restatement_equals_reference_live():
         assert cases.rel_err(b[k], a[k]) <= 1e-12, k
 
 
+def test_product_fpn_and_rpn_state_dicts_match_the_reference_layout():
+    """Checkpoint compatibility (host logic): parameter names and shapes of htd_b200.necks.FPN /
+    dense_heads.RPNHead are the reference's (necks/fpn.py:110-131, rpn_head.py:24-31)."""
+    from htd_b200.dense_heads import RPNHead
+    from htd_b200.necks import FPN
+    mine = {k: tuple(v.shape) for k, v in FPN([256, 512, 1024, 2048], 256, 5).state_dict().items()}
+    want = {k: tuple(v.shape) for k, v in restate.FPN().state_dict().items()}
+    assert mine == want
+    rpn = {k: tuple(v.shape) for k, v in RPNHead(256, 256).state_dict().items()}
+    assert rpn == {'rpn_conv.weight': (256, 256, 3, 3), 'rpn_conv.bias': (256,),
+                   'rpn_cls.weight': (3, 256, 1, 1), 'rpn_cls.bias': (3,),
+                   'rpn_reg.weight': (12, 256, 1, 1), 'rpn_reg.bias': (12,)}
+    if refshim.available():
+        ns = refshim.load()
+        ref = {k: tuple(v.shape) for k, v in ns.FPN([256, 512, 1024, 2048], 256, 5).state_dict().items()}
+        assert mine == ref
+
+
 # ---- RPN proposals (SURVEY §8 f4) ------------------------------------------------------------------
 @pytest.mark.parametrize('name', list(cases.RPN_CASES))
 def test_rpn_restatement_matches_reference_golden(name):
