@@ -10,6 +10,8 @@ from .core import (CrossEntropyLoss, DeltaXYWHBBoxCoder, MaxIoUAssigner,  # noqa
 from .bbox_heads import (BBoxHead, ConvFCBBoxHead, GlobalContextHead,  # noqa: F401
                          HTDBBoxHead, Shared2FCBBoxHead)
 from .roi_head import HTDRoIHead  # noqa: F401
+from .necks import FPN  # noqa: F401
+from .dense_heads import AnchorGenerator, RPNHead  # noqa: F401
 from .config import htd_roi_head_cfg, build_htd_roi_head  # noqa: F401
 
 __version__ = '0.1.0'
