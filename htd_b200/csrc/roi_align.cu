@@ -1612,9 +1612,9 @@ __global__ void __launch_bounds__((4 * kCG + 1) * 32, kMinCtas) roi_align_bwd_mm
 // reduction of a footprint row is a small matrix product on the tensor pipe,
 //     T[c, pw] = sum_px F[y, px, c] * wx[px, pw]        (M = 16 channels, N = 8 bins, K = 16 px)
 // and the y reduction out[ph][pw][c] += wy[y][ph] * T[c, pw] stays on the accumulator fragments.
-//   * task = up to kMfSeg consecutive bin rows of one RoI (two tasks per RoI at pooled 7: the
+//   * task = up to kMfSeg = 4 consecutive bin rows of one RoI (two tasks per RoI at pooled 7: the
 //     RoI-wide work - descriptor, x-table, B fragments - is paid twice per RoI instead of once per
-//     bin row, and 2 K tasks still balance over 2 x 148 groups); tasks alternate between kMfGroups
+//     bin row), numbered segment-major so that every CTA sees both segment sizes; tasks alternate between kMfGroups
 //     groups of 4 consumer + 4 producer warps; inside a group warp pair cc owns channels
 //     [64 cc, 64 cc + 64) and streams them through its OWN ring of 4 KB tiles - no cross-pair barrier.
 //   * a tile = 32 pixels of one footprint row x 64 channels, fetched by ONE cp.async.bulk.tensor
@@ -1638,7 +1638,7 @@ __global__ void __launch_bounds__((4 * kCG + 1) * 32, kMinCtas) roi_align_bwd_mm
 #define HTD_MF_AHEAD 2
 #endif
 #ifndef HTD_MF_SEG
-#define HTD_MF_SEG 2
+#define HTD_MF_SEG 4
 #endif
 constexpr int kMfGroups = 2;
 constexpr int kMfTiles = HTD_MF_TILES;           // 4 KB tiles in flight per (group, channel chunk)
@@ -1739,9 +1739,13 @@ __global__ void __launch_bounds__(kMfGroups * 8 * 32, 1)
 #pragma unroll
                 for (int j = 0; j < HTD_MAX_POOLED - 1; ++j) { pl.dx0[j] = 0; pl.nx[j] = 0; }
                 if (ii < n_g) {
+                    // segment-major task numbers: a CTA's tasks tk = blockIdx.x + i * grid then run
+                    // through all segments (RoI-major numbering gave CTA b the SAME segment b % nseg of
+                    // every RoI whenever nseg divides the grid - and the last segment has one bin row)
                     const int tk = (int)blockIdx.x + (ii * kMfGroups + grp) * grid;
-                    const int k = tk / nseg;
-                    const int ph0 = (tk - k * nseg) * kMfSeg;
+                    const int sg = tk / p.K;
+                    const int k = tk - sg * p.K;
+                    const int ph0 = sg * kMfSeg;
                     const int nph = min(kMfSeg, P - ph0);
                     const int l = p.roi_level[k];
                     const int b = (int)p.rois[(size_t)k * 5];

@@ -9,10 +9,10 @@ build() { # name tiles desc ahead seg
   nvcc -shared -o $V/lib_$1.so $V/roi_$1.o $others -lcudart -lcuda && echo built $1
 }
 build t5d4a2s2 5 4 2 2 &
-build t6d3a1s2 6 3 1 2 &
+build t4d4a2s4 4 4 2 4 &
 build t5d4a2s1 5 4 2 1 &
 build t5d4a2s4 5 4 2 4 &
 build t4d4a2s2 4 4 2 2 &
-build t5d4a1s2 5 4 1 2 &
+build t5d4a3s2 5 4 3 2 &
 wait
 ls -la $V/*.so
