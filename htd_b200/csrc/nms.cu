@@ -184,6 +184,124 @@ __global__ void __launch_bounds__(1024) nms_class_kernel(
     }
 }
 
+// ---- few classes, many candidates per class (the RPN: 5 levels x 2000 boxes) ----------------------
+// One CTA per class walks its candidates one after the other however it is organised; here the
+// pair tests go to the whole GPU instead: (1) nms_sort_kernel orders a class's candidates (rank
+// counting) into the workspace, (2) nms_mask_kernel - a grid of 64 x 64 blocks per class - writes
+// for every candidate the 64-bit words of the LATER candidates it overlaps, (3) nms_reduce_kernel
+// resolves a class sequentially on those words, 64 candidates per trip from shared memory.  Same
+// decisions in the same order as the greedy loop (mmcv's CUDA nms is organised the same way, with
+// step 3 on the host).
+constexpr int kMaskMaxClasses = 8;
+
+__global__ void __launch_bounds__(1024) nms_sort_kernel(
+    const float* __restrict__ boxes, int box_classes, const float* __restrict__ scores, int K, int C,
+    const int* __restrict__ cand_k, const int* __restrict__ ws_n, const float* __restrict__ ws_f,
+    float4* __restrict__ sbox, float* __restrict__ sscore, int* __restrict__ sk) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* u_score = reinterpret_cast<float*>(smem);
+    const int c = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int n = ws_n[c];
+    if (n == 0) return;
+    const float shift = __fmul_rn((float)c, __fadd_rn(ws_f[0], 1.f));       // idxs * (max + 1)
+    const int* ck = cand_k + (size_t)c * K;
+    for (int j = tid; j < n; j += nthr) u_score[j] = scores[(size_t)ck[j] * (C + 1) + c];
+    __syncthreads();
+    for (int j = tid; j < n; j += nthr) {
+        const float sj = u_score[j];
+        int rank = 0;
+        for (int i = 0; i < n; ++i) {
+            const float si = u_score[i];
+            rank += (si > sj) || (si == sj && i < j);            // candidates are in ascending k
+        }
+        const int k = ck[j];
+        const float4 b = *reinterpret_cast<const float4*>(
+            boxes + ((size_t)k * box_classes + (box_classes > 1 ? c : 0)) * 4);
+        sbox[(size_t)c * K + rank] = make_float4(__fadd_rn(b.x, shift), __fadd_rn(b.y, shift),
+                                                 __fadd_rn(b.z, shift), __fadd_rn(b.w, shift));
+        sscore[(size_t)c * K + rank] = sj;
+        sk[(size_t)c * K + rank] = k;
+    }
+}
+
+// block (bx, by, c): rows by*64 .. +63 against columns bx*64 .. +63 (bx >= by); mask[c][row][bx]
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox,
+                                                      const int* __restrict__ ws_n, int K, int words,
+                                                      float iou_thr,
+                                                      unsigned long long* __restrict__ mask) {
+    const int c = blockIdx.z, bx = blockIdx.x, by = blockIdx.y, t = threadIdx.x;
+    const int n = ws_n[c];
+    if (bx < by || by * 64 >= n || bx * 64 >= n) return;
+    __shared__ float4 s_col[64];
+    const float4* b = sbox + (size_t)c * K;
+    const int col = bx * 64 + t;
+    if (col < n) s_col[t] = b[col];
+    __syncthreads();
+    const int row = by * 64 + t;
+    if (row >= n) return;
+    const float4 br = b[row];
+    const int ncol = min(64, n - bx * 64);
+    unsigned long long w = 0ull;
+    for (int j = (bx == by ? t + 1 : 0); j < ncol; ++j)
+        if (nms_over(br, s_col[j], iou_thr)) w |= 1ull << j;
+    mask[((size_t)c * K + row) * words + bx] = w;
+}
+
+__global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long long* __restrict__ mask,
+                                                         const float* __restrict__ sscore,
+                                                         const int* __restrict__ sk, int K, int C,
+                                                         int words, int* __restrict__ ws_n,
+                                                         int* __restrict__ kept_k,
+                                                         float* __restrict__ kept_score) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long* s_rows = reinterpret_cast<unsigned long long*>(smem);      // [64][words]
+    __shared__ unsigned long long s_keep[64];                                      // per chunk (<= 4096 / 64)
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int n = ws_n[c];
+    if (n == 0) return;
+    const int nw = (n + 63) >> 6;
+    unsigned long long r0 = 0ull, r1 = 0ull;      // warp 0: removed words lane and lane + 32
+    for (int w = 0; w < nw; ++w) {
+        const int rows = min(64, n - w * 64);
+        // rows of this chunk, words w .. nw-1 (the only ones the mask kernel wrote)
+        for (int i = tid; i < rows * (nw - w); i += 256) {
+            const int rr = i / (nw - w), ww = w + i - rr * (nw - w);
+            s_rows[rr * words + ww] = mask[((size_t)c * K + w * 64 + rr) * words + ww];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned long long cw = __shfl_sync(0xffffffffu, w < 32 ? r0 : r1, w & 31);
+            unsigned long long keep = 0ull;
+            for (int b = 0; b < rows; ++b) {
+                if (!((cw >> b) & 1ull)) {
+                    keep |= 1ull << b;
+                    cw |= s_rows[b * words + w];
+                    if (lane >= w && lane < nw) r0 |= s_rows[b * words + lane];
+                    if (lane + 32 >= w && lane + 32 < nw) r1 |= s_rows[b * words + lane + 32];
+                }
+            }
+            if (lane == 0) s_keep[w] = keep;
+        }
+        __syncthreads();
+    }
+    // compact the survivors in order
+    if (tid < 32) {
+        int base = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + tid;
+            const bool keep = j < n && ((s_keep[j >> 6] >> (j & 63)) & 1ull);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int r = base + __popc(m & ((1u << tid) - 1u));
+                kept_k[(size_t)c * K + r] = sk[(size_t)c * K + j];
+                kept_score[(size_t)c * K + r] = sscore[(size_t)c * K + j];
+            }
+            base += __popc(m);
+        }
+        if (tid == 0) ws_n[C + c] = base;
+    }
+}
+
 // every survivor finds its global rank by (score desc, k * C + c asc); ranks < max_num are written
 __global__ void __launch_bounds__(kNmsThreads) nms_merge_kernel(
     const float* __restrict__ boxes, int box_classes, int K, int C, const int* __restrict__ ws_n,
@@ -449,9 +567,15 @@ using namespace htd;
 
 extern "C" {
 
+static bool nms_mask_path(int K, int C) { return C <= kMaskMaxClasses && K > 512; }
+
 long long htd_multiclass_nms_workspace_bytes(int K, int C) {
     // cand_k, kept_k (int), kept_score (float): [C, K] each; counters [2C] ints; 1 float (16 B slot)
-    return (long long)C * K * 12 + (long long)C * 8 + 16;
+    long long b = (long long)C * K * 12 + (long long)C * 8 + 16;
+    b = (b + 15) / 16 * 16;
+    if (nms_mask_path(K, C))   // sorted boxes / scores / k + the overlap words [C, K, ceil(K / 64)]
+        b += (long long)C * K * 24 + (long long)C * K * ((K + 63) / 64) * 8;
+    return b;
 }
 
 int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores, int K, int C,
@@ -477,12 +601,31 @@ int htd_multiclass_nms(const float* boxes, int box_classes, const float* scores,
         nms_collect_kernel<<<C, kNmsThreads, 0, st>>>(boxes, box_classes, scores, K, C, score_thr,
                                                       cand_k, ws_n, ws_f);
         HTD_CHECK_LAUNCH("htd_multiclass_nms(collect)");
+        if (nms_mask_path(K, C)) {
+            const int words = (K + 63) / 64;
+            size_t off = ((size_t)C * K * 12 + (size_t)C * 8 + 16 + 15) / 16 * 16;
+            float4* sbox = reinterpret_cast<float4*>(w + off);
+            float* sscore = reinterpret_cast<float*>(sbox + (size_t)C * K);
+            int* sk = reinterpret_cast<int*>(sscore + (size_t)C * K);
+            unsigned long long* mask = reinterpret_cast<unsigned long long*>(sk + (size_t)C * K);
+            HTD_SMEM_OPTIN(nms_sort_kernel, HTD_NMS_MAX_ROIS * 4, "htd_multiclass_nms");
+            nms_sort_kernel<<<C, 1024, (size_t)K * 4, st>>>(boxes, box_classes, scores, K, C, cand_k, ws_n,
+                                                            ws_f, sbox, sscore, sk);
+            HTD_CHECK_LAUNCH("htd_multiclass_nms(sort)");
+            nms_mask_kernel<<<dim3(words, words, C), 64, 0, st>>>(sbox, ws_n, K, words, iou_thr, mask);
+            HTD_CHECK_LAUNCH("htd_multiclass_nms(mask)");
+            HTD_SMEM_OPTIN(nms_reduce_kernel, 64 * 64 * 8, "htd_multiclass_nms");
+            nms_reduce_kernel<<<C, 256, (size_t)64 * words * 8, st>>>(mask, sscore, sk, K, C, words, ws_n,
+                                                                     kept_k, kept_score);
+            HTD_CHECK_LAUNCH("htd_multiclass_nms(reduce)");
+        } else {
         const size_t smem = (size_t)K * (16 + 4 + 4 + 4 + 1);
         HTD_SMEM_OPTIN(nms_class_kernel, HTD_NMS_MAX_ROIS * 29, "htd_multiclass_nms");
         nms_class_kernel<<<C, K > 256 ? 1024 : kNmsThreads, smem, st>>>(boxes, box_classes, scores, K, C,
                                                                         iou_thr, cand_k, ws_n, ws_f,
                                                                         kept_k, kept_score);
         HTD_CHECK_LAUNCH("htd_multiclass_nms(class)");
+        }
     }
     const int bx = K > 0 ? (K + kNmsThreads - 1) / kNmsThreads : 1;
     nms_merge_kernel<<<dim3(bx, C), kNmsThreads, 0, st>>>(boxes, box_classes, K, C, ws_n, kept_k,

@@ -472,7 +472,9 @@ int htd_assign_sample(const float* props, const unsigned char* valid, int B, int
  *   batched_nms does; greedy suppression in descending score order when IoU > iou_thr; output =
  *   the survivors in descending score order (ties: ascending k*C + c), the first max_num.
  *   det [max_num,5] (x1,y1,x2,y2,score) and labels [max_num] are written for rows < count[0];
- *   workspace: htd_multiclass_nms_workspace_bytes(K, C) bytes.  No host sync, three launches. */
+ *   workspace: htd_multiclass_nms_workspace_bytes(K, C) bytes.  No host sync, three launches
+ *   (five for C <= 8 and K > 512 - the RPN's level-as-class call - where the pair tests are a
+ *   bit matrix computed by the whole GPU and resolved sequentially per class). */
 #define HTD_NMS_MAX_ROIS 4096
 #define HTD_NMS_MAX_CLASSES 1024
 long long htd_multiclass_nms_workspace_bytes(int K, int C);

@@ -26,7 +26,9 @@ def test_multiclass_nms_matches_reference_golden(name):
 
 def test_multiclass_nms_matches_restatement_random_sizes():
     g = torch.Generator().manual_seed(7)
-    for K, C, per_class in ((1, 1, False), (37, 3, True), (1000, 80, False), (2048, 5, False)):
+    # (2048, 5), (3000, 3) and (4096, 2): few classes with many candidates each - the bit-matrix path
+    for K, C, per_class in ((1, 1, False), (37, 3, True), (1000, 80, False), (2048, 5, False),
+                            (3000, 3, True), (4096, 2, False), (513, 8, False)):
         cases.NMS_CASES['_t'] = dict(K=K, C=C, per_class=per_class, score_thr=0.02, iou_thr=0.45,
                                      max_num=150, seed=int(torch.randint(0, 1000, (1,), generator=g)),
                                      dup=0.5, temp=2.0)
