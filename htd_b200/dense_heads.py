@@ -129,26 +129,44 @@ class RPNHead(nn.Module):
         raise NotImplementedError('the anchor-target / loss side of the RPN is outside the accelerated '
                                   'path (SURVEY.md §8): proposals only')
 
+    def _rank(self, cls_scores, cfg):
+        """Per level the nms_pre best logits of EVERY image in one launch ([B, nms_pre] values and
+        positions), None for a level that is not ranked (rpn_head.py:125)."""
+        out = []
+        for c in cls_scores:
+            B = c.shape[0]
+            logit = c.permute(0, 2, 3, 1).reshape(B, -1)
+            if cfg.nms_pre > 0 and logit.shape[1] > cfg.nms_pre:
+                logit = logit.float().contiguous()
+                if cfg.nms_pre <= MAX_CANDIDATES:
+                    out.append(ops.topk_sorted(logit, cfg.nms_pre))
+                else:
+                    ranked, idx = logit.sort(dim=1, descending=True)
+                    out.append((ranked[:, :cfg.nms_pre], idx[:, :cfg.nms_pre]))
+            else:
+                out.append(None)
+        return out
+
     def _get_bboxes_single(self, cls_scores, bbox_preds, mlvl_anchors, img_shape, scale_factor, cfg,
-                           rescale=False):
+                           rescale=False, ranked=None):
         """rpn_head.py:77-168 for one image.  Returns [n, 5] (x1, y1, x2, y2, score), n <= nms_post,
-        in descending score order."""
+        in descending score order.  ``ranked``: this image's rows of ``_rank`` (computed here when
+        absent)."""
         cfg = as_cfg(self.test_cfg if cfg is None else cfg)
         L = len(cls_scores)
         dev = cls_scores[0].device
+        if ranked is None:
+            ranked = [None if r is None else (r[0][0], r[1][0])
+                      for r in self._rank([c[None] for c in cls_scores], cfg)]
         per_level = []
         for l in range(L):
-            logit = cls_scores[l].permute(1, 2, 0).reshape(-1).float()
             delta = bbox_preds[l].permute(1, 2, 0).reshape(-1, 4)
             anchors = mlvl_anchors[l]
-            if cfg.nms_pre > 0 and logit.shape[0] > cfg.nms_pre:
-                if cfg.nms_pre <= MAX_CANDIDATES:
-                    ranked, idx = ops.topk_sorted(logit.contiguous()[None], cfg.nms_pre)
-                    ranked, idx = ranked[0], idx[0]
-                else:
-                    ranked, idx = logit.sort(descending=True)
-                    ranked, idx = ranked[:cfg.nms_pre], idx[:cfg.nms_pre]
-                logit, delta, anchors = ranked, delta[idx], anchors[idx]
+            if ranked[l] is not None:
+                logit, idx = ranked[l]
+                delta, anchors = delta[idx], anchors[idx]
+            else:
+                logit = cls_scores[l].permute(1, 2, 0).reshape(-1).float()
             if logit.shape[0] > MAX_CANDIDATES:
                 raise NotImplementedError(f'{logit.shape[0]} candidates on level {l}: nms_pre <= '
                                           f'{MAX_CANDIDATES} (configs/htd: 2000 / 1000)')
@@ -177,12 +195,14 @@ class RPNHead(nn.Module):
         assert len(cls_scores) == len(bbox_preds) and with_nms
         sizes = [c.shape[-2:] for c in cls_scores]
         anchors = self.anchor_generator.grid_anchors(sizes, device=cls_scores[0].device)
+        ranked = self._rank([c.detach() for c in cls_scores], as_cfg(self.test_cfg if cfg is None else cfg))
         out = []
         for i, meta in enumerate(img_metas):
             out.append(self._get_bboxes_single([c[i].detach() for c in cls_scores],
                                                [b[i].detach() for b in bbox_preds], anchors,
                                                meta['img_shape'], meta.get('scale_factor', 1.0), cfg,
-                                               rescale))
+                                               rescale, ranked=[None if r is None else (r[0][i], r[1][i])
+                                                                for r in ranked]))
         return out
 
     def simple_test_rpn(self, x, img_metas):
